@@ -1,0 +1,254 @@
+/*
+ * gtsam_b200.h — C-ABI of the B200-native Gauss-Newton / Levenberg-Marquardt
+ * inner loop (linearize + multifrontal Cholesky solve) that drops in behind
+ * GTSAM's LevenbergMarquardtOptimizer / GaussNewtonOptimizer /
+ * GaussianFactorGraph::optimize path.
+ *
+ * Plain C, plain pointers and sizes, opaque handles, int status codes.  No
+ * torch, no GTSAM, no C++ types cross this boundary.  All file:line citations
+ * are relative to the reference tree (borglab/gtsam @ 0ffe6c93).
+ *
+ * Conventions (identical to the reference):
+ *  - all arithmetic FP64; tangent order for Pose3 is (omega, v), rotation first
+ *    (gtsam/geometry/Pose3.cpp:169-208); perturbations are right-multiplied
+ *    (gtsam/base/Lie.h:131-160);
+ *  - a Pose3 value is 12 doubles: R row-major (9) then t (3);
+ *  - variables are addressed by dense ids 0..nvars-1.  The GTSAM-side shim
+ *    assigns ids in ascending Key order (the iteration order of
+ *    gtsam::Values, gtsam/nonlinear/Values.h:74-79), so "sorted by id" ==
+ *    "sorted by Key" (needed to reproduce gtsam/linear/Scatter.cpp:69-72);
+ *  - `ordering[k]` is the id of the k-th eliminated variable (the contents of
+ *    a gtsam::Ordering, gtsam/inference/Ordering.h:217-236).  It is an INPUT:
+ *    COLAMD/METIS/Schur orderings are produced by the caller.
+ */
+#ifndef GTSAM_B200_H
+#define GTSAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (replace the reference's C++ exceptions) --------------- */
+enum {
+  B200_OK = 0,
+  B200_INDETERMINATE = 1,      /* gtsam::IndeterminantLinearSystemException,
+                                  gtsam/linear/HessianFactor.cpp:476-483,
+                                  gtsam/linear/linearAlgorithms-inst.h:99 */
+  B200_UNSUPPORTED_FACTOR = 2, /* factor type outside the hot path          */
+  B200_UNSUPPORTED_NOISE = 3,  /* Constrained / Robust noise models          */
+  B200_INVALID_ARGUMENT = 4,   /* std::invalid_argument / ValuesKeyDoesNotExist */
+  B200_CUDA_ERROR = 5,
+  B200_NCCL_ERROR = 6,
+  B200_NO_DEVICE = 7           /* no CUDA device: there is NO CPU fallback   */
+};
+
+/* ---- variable (gtsam::Value) types --------------------------------------- */
+enum {
+  B200_VAR_POSE3 = 0,       /* gtsam::Pose3; storage 12 (R row-major, t); dim 6 */
+  B200_VAR_POINT3 = 1,      /* gtsam::Point3; storage 3; dim 3                  */
+  B200_VAR_CAM_BUNDLER = 2  /* PinholeCamera<Cal3Bundler>; storage 17 =
+                               R(9) t(3) f k1 k2 u0 v0; dim 9 = pose(6)+f,k1,k2
+                               (gtsam/geometry/PinholeCamera.h:199-205)         */
+};
+
+/* ---- factor types --------------------------------------------------------- */
+enum {
+  /* BetweenFactor<Pose3>, gtsam/slam/BetweenFactor.h:111-124.
+     keys (p1,p2); meas = measured Pose3 (12); residual dim 6 */
+  B200_FACTOR_BETWEEN_POSE3 = 0,
+  /* PriorFactor<Pose3>, gtsam/nonlinear/PriorFactor.h:98-102. key; meas 12; dim 6 */
+  B200_FACTOR_PRIOR_POSE3 = 1,
+  /* PriorFactor<Point3>. key; meas 3; dim 3 */
+  B200_FACTOR_PRIOR_POINT3 = 2,
+  /* GenericProjectionFactor<Pose3,Point3,Cal3_S2>, gtsam/slam/ProjectionFactor.h:138-166
+     (no body_P_sensor, throwCheirality=false). keys (pose,point); meas z (2);
+     dim 2; per-factor calibration index into desc.cal (5 doubles fx fy s u0 v0) */
+  B200_FACTOR_PROJECTION_CAL3S2 = 3,
+  /* GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>, gtsam/slam/GeneralSFMFactor.h:127-177.
+     keys (camera,point); meas z (2); dim 2 */
+  B200_FACTOR_SFM_BUNDLER = 4,
+  /* PriorFactor<PinholeCamera<Cal3Bundler>>. key; meas 17; dim 9 */
+  B200_FACTOR_PRIOR_CAM_BUNDLER = 5,
+  B200_NUM_FACTOR_TYPES = 6
+};
+
+/* ---- noise models (gtsam/linear/NoiseModel.cpp:83-130,163-238,322-340,646-675) */
+enum {
+  B200_NOISE_UNIT = 0,      /* no payload                                      */
+  B200_NOISE_ISOTROPIC = 1, /* 1 double: sigma                                  */
+  B200_NOISE_DIAGONAL = 2,  /* d doubles: sigmas                                */
+  B200_NOISE_GAUSSIAN = 3   /* d*d doubles: sqrt information R (upper
+                               triangular), row-major; whitened r = R r       */
+};
+
+/* One homogeneous run of factors (same type, same noise kind).  Factors of a
+ * group occupy consecutive positions graph_index0 .. graph_index0+count-1 of
+ * the NonlinearFactorGraph (position matters for the symbolic structure:
+ * gtsam/inference/VariableIndex-inl.h:27-50 lists factor indices ascending). */
+typedef struct b200_factor_group {
+  int32_t type;             /* B200_FACTOR_*                                    */
+  int32_t noise_kind;       /* B200_NOISE_*                                     */
+  int32_t noise_per_factor; /* 0: one shared model for the group, 1: per factor */
+  int32_t reserved;
+  int64_t count;
+  int64_t graph_index0;     /* -1: append after the previous group              */
+  const int64_t* keys;      /* count*arity variable ids                         */
+  const double* meas;       /* count*meas_size                                  */
+  const double* noise;      /* payload: shared or count*payload_size            */
+  const int32_t* cal_index; /* PROJECTION_CAL3S2 only; NULL => calibration 0    */
+} b200_factor_group;
+
+typedef struct b200_problem_desc {
+  int64_t nvars;
+  const int32_t* var_type;  /* nvars                                            */
+  const double* values;     /* packed per variable in id order (storage sizes)  */
+  const int64_t* ordering;  /* nvars: elimination order (variable ids)          */
+  int64_t ncal;
+  const double* cal;        /* ncal*5 Cal3_S2 (fx fy s u0 v0)                   */
+  int64_t ngroups;
+  const b200_factor_group* groups;
+} b200_problem_desc;
+
+/* LevenbergMarquardtParams subset, gtsam/nonlinear/LevenbergMarquardtParams.h:49-101
+ * + NonlinearOptimizerParams.h:35-60. */
+typedef struct b200_lm_params {
+  int32_t max_iterations;        /* maxIterations (100)                         */
+  double relative_error_tol;     /* 1e-5                                        */
+  double absolute_error_tol;     /* 1e-5                                        */
+  double error_tol;              /* 0                                           */
+  double lambda_initial;         /* 1e-5                                        */
+  double lambda_factor;          /* 10                                          */
+  double lambda_upper_bound;     /* 1e5                                         */
+  double lambda_lower_bound;     /* 0                                           */
+  double min_model_fidelity;     /* 1e-3                                        */
+  int32_t diagonal_damping;      /* false                                       */
+  int32_t use_fixed_lambda_factor; /* true                                      */
+  double min_diagonal;           /* 1e-6                                        */
+  double max_diagonal;           /* 1e32                                        */
+} b200_lm_params;
+
+typedef struct b200_lm_state {
+  double error;                  /* NonlinearOptimizerState::error              */
+  double lambda;
+  double current_factor;
+  int32_t iterations;
+  int32_t total_inner_iterations;
+} b200_lm_state;
+
+/* Sizes of the junction tree the symbolic phase built (a11). */
+typedef struct b200_symbolic_info {
+  int64_t ncliques;
+  int64_t nlevels;
+  int64_t total_dim;        /* sum of variable dims                             */
+  int64_t max_frontal_dim;
+  int64_t max_separator_dim;
+  int64_t frontal_list_len; /* sum over cliques of #frontal variables           */
+  int64_t separator_list_len;
+  double factor_flops;      /* sum f^3/3 + f^2 s + f s^2                        */
+  int64_t front_bytes;      /* bytes of all frontal matrices                    */
+} b200_symbolic_info;
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_problem b200_problem;
+typedef struct b200_lm b200_lm;
+
+/* Static layout tables. */
+int b200_var_storage(int32_t var_type);   /* doubles of storage */
+int b200_var_dim(int32_t var_type);       /* tangent dimension  */
+int b200_factor_arity(int32_t factor_type);
+int b200_factor_meas_size(int32_t factor_type);
+int b200_factor_dim(int32_t factor_type); /* residual rows      */
+
+/* Context = one CUDA device + streams.  One per process in multi-GPU runs.
+ * Fails with B200_NO_DEVICE when no GPU is visible (no CPU fallback). */
+int b200_ctx_create(int device, b200_ctx** ctx);
+int b200_ctx_destroy(b200_ctx* ctx);
+const char* b200_last_error_string(void);
+/* Number of kernels this library has launched since ctx creation. */
+int64_t b200_launch_count(const b200_ctx* ctx);
+/* CUDA stream (cudaStream_t as void*) the library launches on. */
+void* b200_ctx_stream(const b200_ctx* ctx);
+
+/* One-time pack + symbolic phase.  Replaces the walk over
+ * NonlinearFactorGraph / Values (gtsam/nonlinear/NonlinearFactorGraph.cpp:239-278)
+ * and VariableIndex + EliminationTree + JunctionTree construction
+ * (gtsam/inference/EliminateableFactorGraph-inst.h:123-146), hoisted out of
+ * the per-solve path.  Copies everything; retains no host pointer. */
+int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* desc, b200_problem** prob);
+int b200_problem_destroy(b200_problem* prob);
+
+/* Values in / out (host buffers, packed like desc.values). */
+int b200_set_values(b200_problem* prob, const double* packed_values);
+int b200_get_values(b200_problem* prob, double* packed_values);
+int64_t b200_values_size(const b200_problem* prob); /* doubles in packed values */
+int64_t b200_delta_size(const b200_problem* prob);  /* total tangent dim        */
+
+/* NonlinearFactorGraph::error(values), gtsam/nonlinear/NonlinearFactorGraph.cpp:170-179 */
+int b200_error(b200_problem* prob, double* error);
+
+/* NonlinearFactorGraph::linearize(values): whitened per-factor [A1 A2 b],
+ * device-resident (gtsam/nonlinear/NonlinearFactor.cpp:150-182). */
+int b200_linearize(b200_problem* prob);
+/* Debug/parity: copy a group's Jacobians to host, factor-major; each factor is
+ * a column-major d x (n1 + n2 + 1) block [A1 A2 b] like VerticalBlockMatrix. */
+int b200_get_jacobians(b200_problem* prob, int64_t group, double* out);
+
+/* GaussianFactorGraph::hessianDiagonal(), gtsam/linear/GaussianFactorGraph.cpp:279-287.
+ * out: delta_size doubles, variable-id order. */
+int b200_hessian_diagonal(b200_problem* prob, double* out);
+
+/* Damped multifrontal Cholesky solve of the current linearization:
+ * buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)
+ * + GaussianFactorGraph::optimize (gtsam/linear/GaussianFactorGraph.cpp:316-319)
+ * + the two linear.error() calls of tryLambda
+ * (gtsam/nonlinear/LevenbergMarquardtOptimizer.cpp:170-171).
+ * lambda == 0 => undamped (Gauss-Newton).  Returns B200_INDETERMINATE and the
+ * id of a frontal variable of the failing clique in *fail_var. */
+int b200_solve(b200_problem* prob, double lambda, int diagonal_damping,
+               double min_diagonal, double max_diagonal,
+               double* linear_error_zero, double* linear_error_delta,
+               int64_t* fail_var);
+/* delta of the last solve, delta_size doubles in variable-id order. */
+int b200_get_delta(b200_problem* prob, double* out);
+
+/* newValues = values.retract(delta) into scratch + graph.error(newValues)
+ * (gtsam/nonlinear/Values.cpp:52-63). */
+int b200_try_step(b200_problem* prob, double* new_error);
+/* values <- newValues */
+int b200_accept_step(b200_problem* prob);
+
+/* Whole optimizers (host control logic a17/a18 unchanged, data on device). */
+void b200_lm_params_legacy(b200_lm_params* p); /* LevenbergMarquardtParams::SetLegacyDefaults */
+void b200_lm_params_ceres(b200_lm_params* p);  /* ::SetCeresDefaults                          */
+int b200_lm_create(b200_problem* prob, const b200_lm_params* params, b200_lm** lm);
+int b200_lm_destroy(b200_lm* lm);
+/* LevenbergMarquardtOptimizer::iterate(), .cpp:273-308 */
+int b200_lm_iterate(b200_lm* lm);
+/* NonlinearOptimizer::defaultOptimize(), NonlinearOptimizer.cpp:62-117 */
+int b200_lm_optimize(b200_lm* lm);
+int b200_lm_get_state(const b200_lm* lm, b200_lm_state* state);
+/* Reset state to (current device values, lambda_initial, iteration 0); recomputes error. */
+int b200_lm_reset(b200_lm* lm);
+/* GaussNewtonOptimizer::iterate(), gtsam/nonlinear/GaussNewtonOptimizer.cpp:44-67 */
+int b200_gn_iterate(b200_problem* prob, double* new_error);
+
+/* Symbolic-phase introspection (parity of a11 against the reference's
+ * junction tree).  Cliques are numbered in elimination post-order. */
+int b200_symbolic_info_get(const b200_problem* prob, b200_symbolic_info* info);
+/* frontal_ptr/separator_ptr: ncliques+1; frontal_vars/separator_vars: list
+ * lengths from b200_symbolic_info; parent: ncliques (-1 for roots). */
+int b200_get_cliques(const b200_problem* prob, int64_t* frontal_ptr, int64_t* frontal_vars,
+                     int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
+
+/* Multi-GPU: the dense frontal storage of the cliques that are
+ * shared between ranks (the top of the tree) as one contiguous device buffer,
+ * so the caller's communicator (NCCL via torch.distributed) can sum it between
+ * "eliminate local subtrees" and "eliminate shared top".  See DESIGN.md. */
+int b200_shared_front_buffer(b200_problem* prob, void** device_ptr, int64_t* ndoubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTSAM_B200_H */

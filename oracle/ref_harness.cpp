@@ -1,0 +1,485 @@
+/*
+ * ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * Drives the UNMODIFIED reference (oracle/_ref/libgtsam_ref.so, built by
+ * oracle/Makefile from the sources under /root/reference) through its own
+ * public API on problems written by gtsam_b200.problem.Problem.save().
+ * Used to (1) pin the C oracle and generate tests/golden/ fixtures
+ * (tests/golden/make_golden.py), (2) produce COLAMD / METIS orderings (inputs
+ * at the C-ABI boundary), (3) time the reference's CPU path for bench.py's
+ * `--impl reference` arm and `cpu_baseline`.
+ *
+ * Variable id i <-> gtsam::Key i (plain integers), so Key order == id order.
+ */
+#include <gtsam/geometry/Cal3Bundler.h>
+#include <gtsam/geometry/Cal3_S2.h>
+#include <gtsam/geometry/PinholeCamera.h>
+#include <gtsam/geometry/Point3.h>
+#include <gtsam/geometry/Pose3.h>
+#include <gtsam/inference/Ordering.h>
+#include <gtsam/linear/GaussianBayesTree.h>
+#include <gtsam/linear/GaussianEliminationTree.h>
+#include <gtsam/linear/GaussianJunctionTree.h>
+#include <gtsam/linear/JacobianFactor.h>
+#include <gtsam/nonlinear/GaussNewtonOptimizer.h>
+#include <gtsam/nonlinear/LevenbergMarquardtOptimizer.h>
+#include <gtsam/nonlinear/NonlinearFactorGraph.h>
+#include <gtsam/nonlinear/PriorFactor.h>
+#include <gtsam/nonlinear/Values.h>
+#include <gtsam/slam/BetweenFactor.h>
+#include <gtsam/slam/GeneralSFMFactor.h>
+#include <gtsam/slam/ProjectionFactor.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace gtsam;
+typedef PinholeCamera<Cal3Bundler> BCam;
+
+static const int VAR_STORAGE[3] = {12, 3, 17};
+static const int F_ARITY[6] = {2, 1, 1, 2, 2, 1};
+static const int F_MEAS[6] = {12, 12, 3, 2, 2, 17};
+static const int F_DIM[6] = {6, 6, 3, 2, 2, 9};
+
+struct Group {
+  int32_t type, noise_kind, per_factor, has_cal;
+  int64_t count, gi0;
+  std::vector<int64_t> keys;
+  std::vector<double> meas, noise;
+  std::vector<int32_t> cal_index;
+};
+struct Prob {
+  int64_t nvars;
+  std::vector<int32_t> var_type;
+  std::vector<double> values;
+  std::vector<int64_t> ordering;
+  std::vector<double> cal;
+  std::vector<Group> groups;
+};
+
+template <class T>
+static void rd(std::ifstream& f, T* p, size_t n) { f.read((char*)p, (std::streamsize)(n * sizeof(T))); }
+
+static Prob load(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+  char magic[8];
+  rd(f, magic, 8);
+  if (memcmp(magic, "B200PRB1", 8)) { fprintf(stderr, "bad magic\n"); exit(2); }
+  Prob p;
+  rd(f, &p.nvars, 1);
+  p.var_type.resize(p.nvars);
+  rd(f, p.var_type.data(), p.nvars);
+  int64_t nval;
+  rd(f, &nval, 1);
+  p.values.resize(nval);
+  rd(f, p.values.data(), nval);
+  p.ordering.resize(p.nvars);
+  rd(f, p.ordering.data(), p.nvars);
+  int64_t ncal;
+  rd(f, &ncal, 1);
+  p.cal.resize(ncal * 5);
+  rd(f, p.cal.data(), ncal * 5);
+  int64_t ng;
+  rd(f, &ng, 1);
+  p.groups.resize(ng);
+  for (auto& g : p.groups) {
+    rd(f, &g.type, 1); rd(f, &g.noise_kind, 1); rd(f, &g.per_factor, 1); rd(f, &g.has_cal, 1);
+    rd(f, &g.count, 1); rd(f, &g.gi0, 1);
+    g.keys.resize(g.count * F_ARITY[g.type]);
+    rd(f, g.keys.data(), g.keys.size());
+    g.meas.resize(g.count * F_MEAS[g.type]);
+    rd(f, g.meas.data(), g.meas.size());
+    int64_t nn;
+    rd(f, &nn, 1);
+    g.noise.resize(nn);
+    rd(f, g.noise.data(), nn);
+    if (g.has_cal) { g.cal_index.resize(g.count); rd(f, g.cal_index.data(), g.count); }
+  }
+  return p;
+}
+
+static Pose3 mkpose(const double* x) {
+  Matrix3 R;
+  R << x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8];
+  return Pose3(Rot3(R), Point3(x[9], x[10], x[11]));
+}
+static BCam mkcam(const double* x) { return BCam(mkpose(x), Cal3Bundler(x[12], x[13], x[14], x[15], x[16])); }
+static void putpose(const Pose3& p, double* x) {
+  Matrix3 R = p.rotation().matrix();
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) x[3 * i + j] = R(i, j);
+  x[9] = p.x(); x[10] = p.y(); x[11] = p.z();
+}
+
+static SharedNoiseModel mknoise(const Group& g, int64_t i) {
+  const int d = F_DIM[g.type];
+  const int pay = g.noise_kind == 0 ? 0 : g.noise_kind == 1 ? 1 : g.noise_kind == 2 ? d : d * d;
+  const double* nz = g.noise.data() + (g.per_factor ? i * pay : 0);
+  switch (g.noise_kind) {
+    case 0: return noiseModel::Unit::Create(d);
+    case 1: return noiseModel::Isotropic::Sigma(d, nz[0]);
+    case 2: { Vector s(d); for (int k = 0; k < d; k++) s(k) = nz[k]; return noiseModel::Diagonal::Sigmas(s); }
+    default: {
+      Matrix R(d, d);
+      for (int r = 0; r < d; r++) for (int c = 0; c < d; c++) R(r, c) = nz[r * d + c];
+      return noiseModel::Gaussian::SqrtInformation(R);
+    }
+  }
+}
+
+struct Built {
+  NonlinearFactorGraph graph;
+  Values values;
+  Ordering ordering;
+  std::vector<int64_t> val_off;
+};
+
+static Built build(const Prob& p) {
+  Built b;
+  b.val_off.assign(p.nvars + 1, 0);
+  for (int64_t v = 0; v < p.nvars; v++) b.val_off[v + 1] = b.val_off[v] + VAR_STORAGE[p.var_type[v]];
+  for (int64_t v = 0; v < p.nvars; v++) {
+    const double* x = p.values.data() + b.val_off[v];
+    switch (p.var_type[v]) {
+      case 0: b.values.insert(Key(v), mkpose(x)); break;
+      case 1: b.values.insert(Key(v), Point3(x[0], x[1], x[2])); break;
+      case 2: b.values.insert(Key(v), mkcam(x)); break;
+    }
+  }
+  for (int64_t j = 0; j < p.nvars; j++) b.ordering.push_back(Key(p.ordering[j]));
+  int64_t total = 0;
+  for (auto& g : p.groups) total += g.count;
+  std::vector<NonlinearFactor::shared_ptr> fs(total);
+  std::vector<std::shared_ptr<Cal3_S2>> Ks;
+  for (size_t c = 0; c < p.cal.size() / 5; c++) {
+    const double* k = p.cal.data() + 5 * c;
+    Ks.push_back(std::make_shared<Cal3_S2>(k[0], k[1], k[2], k[3], k[4]));
+  }
+  for (auto& g : p.groups) {
+    SharedNoiseModel shared = g.per_factor ? SharedNoiseModel() : mknoise(g, 0);
+    for (int64_t i = 0; i < g.count; i++) {
+      SharedNoiseModel nm = g.per_factor ? mknoise(g, i) : shared;
+      const int64_t* k = g.keys.data() + i * F_ARITY[g.type];
+      const double* z = g.meas.data() + i * F_MEAS[g.type];
+      NonlinearFactor::shared_ptr f;
+      switch (g.type) {
+        case 0: f = std::make_shared<BetweenFactor<Pose3>>(k[0], k[1], mkpose(z), nm); break;
+        case 1: f = std::make_shared<PriorFactor<Pose3>>(k[0], mkpose(z), nm); break;
+        case 2: f = std::make_shared<PriorFactor<Point3>>(k[0], Point3(z[0], z[1], z[2]), nm); break;
+        case 3:
+          f = std::make_shared<GenericProjectionFactor<Pose3, Point3, Cal3_S2>>(
+              Point2(z[0], z[1]), nm, k[0], k[1], Ks[g.has_cal ? g.cal_index[i] : 0]);
+          break;
+        case 4: f = std::make_shared<GeneralSFMFactor<BCam, Point3>>(Point2(z[0], z[1]), nm, k[0], k[1]); break;
+        case 5: f = std::make_shared<PriorFactor<BCam>>(k[0], mkcam(z), nm); break;
+      }
+      fs[g.gi0 + i] = f;
+    }
+  }
+  for (auto& f : fs) b.graph.push_back(f);
+  return b;
+}
+
+/* ---- named-array output container ---------------------------------------- */
+struct Out {
+  std::ofstream f;
+  explicit Out(const std::string& path) : f(path, std::ios::binary) { f.write("B200OUT1", 8); }
+  void put(const std::string& name, const std::vector<double>& a) { rec(name, 'd', a.data(), a.size(), 8); }
+  void put(const std::string& name, const std::vector<int64_t>& a) { rec(name, 'q', a.data(), a.size(), 8); }
+  void put(const std::string& name, double x) { put(name, std::vector<double>{x}); }
+  void rec(const std::string& name, char t, const void* d, size_t n, size_t sz) {
+    int32_t nl = (int32_t)name.size();
+    int64_t cnt = (int64_t)n;
+    f.write((char*)&nl, 4); f.write(name.data(), nl); f.write(&t, 1); f.write((char*)&cnt, 8);
+    f.write((const char*)d, (std::streamsize)(n * sz));
+  }
+};
+
+static std::vector<double> pack_values(const Prob& p, const Built& b, const Values& v) {
+  std::vector<double> out(b.val_off[p.nvars]);
+  for (int64_t i = 0; i < p.nvars; i++) {
+    double* x = out.data() + b.val_off[i];
+    switch (p.var_type[i]) {
+      case 0: putpose(v.at<Pose3>(i), x); break;
+      case 1: { Point3 q = v.at<Point3>(i); x[0] = q.x(); x[1] = q.y(); x[2] = q.z(); break; }
+      case 2: {
+        const BCam& c = v.at<BCam>(i);
+        putpose(c.pose(), x);
+        x[12] = c.calibration().fx(); x[13] = c.calibration().k1(); x[14] = c.calibration().k2();
+        x[15] = c.calibration().px(); x[16] = c.calibration().py();
+        break;
+      }
+    }
+  }
+  return out;
+}
+
+static std::vector<double> pack_vv(const Prob& p, const VectorValues& vv) {
+  std::vector<double> out;
+  for (int64_t i = 0; i < p.nvars; i++) {
+    const Vector& x = vv.at(Key(i));
+    for (int k = 0; k < x.size(); k++) out.push_back(x(k));
+  }
+  return out;
+}
+
+/* whitened [A1 A2 b] of every factor of a group, factor-major, col-major blocks */
+static void dump_jacobians(const Prob& p, const GaussianFactorGraph& lin, Out& out) {
+  for (size_t gi = 0; gi < p.groups.size(); gi++) {
+    const Group& g = p.groups[gi];
+    std::vector<double> J;
+    for (int64_t i = 0; i < g.count; i++) {
+      auto jf = std::dynamic_pointer_cast<JacobianFactor>(lin[g.gi0 + i]);
+      if (!jf) { fprintf(stderr, "factor %ld is not a JacobianFactor\n", (long)(g.gi0 + i)); exit(3); }
+      /* apply any remaining (non-unit) model so the dump is the whitened system */
+      Matrix Ab = jf->augmentedJacobian();  // whitened [A b]
+      /* columns are in the factor's key order, which for our factors is (key1,key2) */
+      for (int c = 0; c < Ab.cols(); c++) for (int r = 0; r < Ab.rows(); r++) J.push_back(Ab(r, c));
+    }
+    out.put("J" + std::to_string(gi), J);
+  }
+}
+
+static void dump_tree(const Prob& p, const GaussianFactorGraph& gfg, const Ordering& ordering, Out& out) {
+  auto bt = gfg.eliminateMultifrontal(ordering, EliminatePreferCholesky);
+  std::vector<int64_t> fptr{0}, fvars, sptr{0}, svars, head;
+  std::vector<double> conds;  // [R S d] col-major per clique, in the order dumped
+  std::vector<int64_t> cptr{0};
+  // traverse
+  std::vector<GaussianBayesTree::sharedClique> stack(bt->roots().begin(), bt->roots().end());
+  while (!stack.empty()) {
+    auto c = stack.back();
+    stack.pop_back();
+    auto cond = c->conditional();
+    for (auto it = cond->beginFrontals(); it != cond->endFrontals(); ++it) fvars.push_back((int64_t)*it);
+    for (auto it = cond->beginParents(); it != cond->endParents(); ++it) svars.push_back((int64_t)*it);
+    fptr.push_back((int64_t)fvars.size());
+    sptr.push_back((int64_t)svars.size());
+    Matrix Ab = cond->augmentedJacobian();  // [R S d], unit model
+    for (int cc = 0; cc < Ab.cols(); cc++) for (int r = 0; r < Ab.rows(); r++) conds.push_back(Ab(r, cc));
+    cptr.push_back((int64_t)conds.size());
+    for (auto& ch : c->children) stack.push_back(ch);
+  }
+  out.put("clique_frontal_ptr", fptr);
+  out.put("clique_frontal_vars", fvars);
+  out.put("clique_separator_ptr", sptr);
+  out.put("clique_separator_vars", svars);
+  out.put("clique_cond_ptr", cptr);
+  out.put("clique_cond", conds);
+}
+
+static int cmd_dump(const std::string& in, const std::string& outp, double lambda, bool diag) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  out.put("error", b.graph.error(b.values));
+  auto lin = b.graph.linearize(b.values);
+  dump_jacobians(p, *lin, out);
+  out.put("hessian_diagonal", pack_vv(p, lin->hessianDiagonal()));
+  LevenbergMarquardtParams params;
+  params.ordering = b.ordering;
+  params.lambdaInitial = lambda > 0 ? lambda : 1e-5;
+  params.diagonalDamping = diag;
+  LevenbergMarquardtOptimizer lm(b.graph, b.values, params);
+  GaussianFactorGraph sys = *lin;
+  if (lambda > 0) {
+    VectorValues sqrtHD;
+    if (diag) {
+      sqrtHD = lin->hessianDiagonal();
+      for (auto& kv : sqrtHD) kv.second = kv.second.cwiseMax(params.minDiagonal).cwiseMin(params.maxDiagonal).cwiseSqrt();
+    }
+    sys = lm.buildDampedSystem(*lin, sqrtHD);
+  }
+  int status = 0;
+  VectorValues delta;
+  try {
+    delta = sys.optimize(b.ordering, EliminatePreferCholesky);
+  } catch (const IndeterminantLinearSystemException& e) {
+    status = 1;
+    out.put("fail_var", std::vector<int64_t>{(int64_t)e.nearbyVariable()});
+  }
+  out.put("status", std::vector<int64_t>{status});
+  if (!status) {
+    out.put("delta", pack_vv(p, delta));
+    out.put("linear_error_zero", lin->error(VectorValues::Zero(delta)));
+    out.put("linear_error_delta", lin->error(delta));
+    Values nv = b.values.retract(delta);
+    out.put("new_values", pack_values(p, b, nv));
+    out.put("new_error", b.graph.error(nv));
+    dump_tree(p, sys, b.ordering, out);
+  }
+  return 0;
+}
+
+static LevenbergMarquardtParams lm_params(const Built& b, bool ceres, int maxit) {
+  LevenbergMarquardtParams params = ceres ? LevenbergMarquardtParams::CeresDefaults() : LevenbergMarquardtParams::LegacyDefaults();
+  params.ordering = b.ordering;
+  params.maxIterations = maxit;
+  return params;
+}
+
+static int cmd_lm(const std::string& in, const std::string& outp, int maxit, bool ceres) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  LevenbergMarquardtOptimizer lm(b.graph, b.values, lm_params(b, ceres, maxit));
+  std::vector<double> errs{lm.error()}, lams{lm.lambda()};
+  std::vector<int64_t> inner{0};
+  /* NonlinearOptimizer::defaultOptimize loop, with a trace */
+  double currentError, newError = lm.error();
+  const auto& prm = lm.params();
+  if (!(newError <= prm.errorTol)) {
+    do {
+      currentError = newError;
+      lm.iterate();
+      newError = lm.error();
+      errs.push_back(newError);
+      lams.push_back(lm.lambda());
+      inner.push_back(lm.getInnerIterations());
+    } while ((int)lm.iterations() < maxit &&
+             !checkConvergence(prm.relativeErrorTol, prm.absoluteErrorTol, prm.errorTol, currentError, newError) &&
+             std::isfinite(currentError));
+  }
+  out.put("lm_errors", errs);
+  out.put("lm_lambdas", lams);
+  out.put("lm_inner", inner);
+  out.put("lm_iterations", std::vector<int64_t>{(int64_t)lm.iterations()});
+  out.put("final_values", pack_values(p, b, lm.values()));
+  return 0;
+}
+
+static int cmd_gn(const std::string& in, const std::string& outp, int iters) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  GaussNewtonParams params;
+  params.ordering = b.ordering;
+  GaussNewtonOptimizer gn(b.graph, b.values, params);
+  std::vector<double> errs{gn.error()};
+  for (int i = 0; i < iters; i++) { gn.iterate(); errs.push_back(gn.error()); }
+  out.put("gn_errors", errs);
+  out.put("final_values", pack_values(p, b, gn.values()));
+  return 0;
+}
+
+static double now() {
+  return std::chrono::duration<double>(std::chrono::high_resolution_clock::now().time_since_epoch()).count();
+}
+
+/* time LM iterate() of the stock reference: each step = fresh optimizer on the
+ * initial values (construction untimed) + one iterate() (timed) */
+static int cmd_time(const std::string& in, int steps, int warmup, bool ceres) {
+  Prob p = load(in);
+  Built b = build(p);
+  std::vector<double> ts, tl, tsv;
+  double err_after = 0;
+  int inner = 0;
+  for (int s = 0; s < warmup + steps; s++) {
+    LevenbergMarquardtOptimizer lm(b.graph, b.values, lm_params(b, ceres, 100));
+    double t0 = now();
+    lm.iterate();
+    double t1 = now();
+    if (s >= warmup) ts.push_back(t1 - t0);
+    err_after = lm.error();
+    inner = lm.getInnerIterations();
+  }
+  { /* split: linearize and one damped solve */
+    double t0 = now();
+    auto lin = b.graph.linearize(b.values);
+    double t1 = now();
+    LevenbergMarquardtOptimizer lm(b.graph, b.values, lm_params(b, ceres, 100));
+    auto sys = lm.buildDampedSystem(*lin, VectorValues());
+    double t2 = now();
+    auto d = sys.optimize(b.ordering, EliminatePreferCholesky);
+    double t3 = now();
+    tl.push_back(t1 - t0);
+    tsv.push_back(t3 - t2);
+  }
+  double sum = 0, mx = 0;
+  for (double t : ts) { sum += t; mx = std::max(mx, t); }
+  printf("{\"steps\": %d, \"warmup\": %d, \"total_s\": %.6f, \"mean_s\": %.6f, \"max_s\": %.6f, "
+         "\"linearize_s\": %.6f, \"solve_s\": %.6f, \"error_after\": %.12g, \"inner_iterations\": %d, "
+         "\"nfactors\": %zu, \"nvars\": %ld}\n",
+         steps, warmup, sum, sum / std::max<size_t>(1, ts.size()), mx, tl[0], tsv[0], err_after, inner,
+         b.graph.size(), (long)p.nvars);
+  return 0;
+}
+
+static int cmd_order(const std::string& in, const std::string& kind, const std::string& outp) {
+  Prob p = load(in);
+  Built b = build(p);
+  Ordering ord;
+  if (kind == "colamd") ord = Ordering::Colamd(b.graph);
+  else if (kind == "metis") ord = Ordering::Metis(b.graph);
+  else if (kind == "natural") ord = Ordering::Natural(b.graph);
+  else { fprintf(stderr, "unknown ordering %s\n", kind.c_str()); return 2; }
+  std::vector<int64_t> o;
+  for (Key k : ord) o.push_back((int64_t)k);
+  Out out(outp);
+  out.put("ordering", o);
+  return 0;
+}
+
+/* known-answer vectors for the geometry primitives, incl. near-0 / near-pi */
+static int cmd_kat(const std::string& outp) {
+  std::mt19937 rng(123);
+  std::normal_distribution<double> N(0, 1);
+  std::vector<double> xi_in, T_out, log_out, ad_out, inv_out, comp_out, so3_w, so3_R, so3_log;
+  std::vector<Vector6> xis;
+  for (int i = 0; i < 40; i++) { Vector6 x; for (int k = 0; k < 6; k++) x(k) = N(rng); xis.push_back(x); }
+  for (double s : {1e-12, 1e-9, 1e-7, 1e-4}) { Vector6 x; for (int k = 0; k < 6; k++) x(k) = N(rng); x.head<3>() *= s; xis.push_back(x); }
+  for (double eps : {0.0, 1e-9, 1e-6, 1e-4, 1e-2}) {  // rotations near pi about varied axes
+    for (int a = 0; a < 4; a++) {
+      Vector3 ax(N(rng), N(rng), N(rng));
+      if (a < 3) { ax = Vector3::Zero(); ax(a) = 1; }
+      ax.normalize();
+      Vector6 x; x << ax * (M_PI - eps), N(rng), N(rng), N(rng);
+      xis.push_back(x);
+    }
+  }
+  Pose3 prev;
+  for (auto& x : xis) {
+    Pose3 T = Pose3::Expmap(x);
+    double buf[12];
+    for (int k = 0; k < 6; k++) xi_in.push_back(x(k));
+    putpose(T, buf); T_out.insert(T_out.end(), buf, buf + 12);
+    Vector6 l = Pose3::Logmap(T);
+    for (int k = 0; k < 6; k++) log_out.push_back(l(k));
+    Matrix6 Ad = T.AdjointMap();
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) ad_out.push_back(Ad(r, c));
+    putpose(T.inverse(), buf); inv_out.insert(inv_out.end(), buf, buf + 12);
+    putpose(prev * T, buf); comp_out.insert(comp_out.end(), buf, buf + 12);
+    prev = T;
+    Vector3 w = x.head<3>();
+    Rot3 R = Rot3::Expmap(w);
+    Vector3 lw = Rot3::Logmap(R);
+    for (int k = 0; k < 3; k++) { so3_w.push_back(w(k)); so3_log.push_back(lw(k)); }
+    Matrix3 Rm = R.matrix();
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) so3_R.push_back(Rm(r, c));
+  }
+  Out out(outp);
+  out.put("xi", xi_in); out.put("expmap", T_out); out.put("logmap", log_out); out.put("adjoint", ad_out);
+  out.put("inverse", inv_out); out.put("compose_prev", comp_out);
+  out.put("so3_w", so3_w); out.put("so3_R", so3_R); out.put("so3_log", so3_log);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: ref_harness dump|lm|gn|time|order|kat ...\n"); return 2; }
+  std::string cmd = argv[1];
+  if (cmd == "dump" && argc >= 4) return cmd_dump(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0, argc > 5 && atoi(argv[5]));
+  if (cmd == "lm" && argc >= 4) return cmd_lm(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 100, argc > 5 && atoi(argv[5]));
+  if (cmd == "gn" && argc >= 4) return cmd_gn(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 3);
+  if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));
+  if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);
+  if (cmd == "kat" && argc >= 3) return cmd_kat(argv[2]);
+  fprintf(stderr, "bad arguments\n");
+  return 2;
+}
