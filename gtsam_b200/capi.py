@@ -1,0 +1,237 @@
+"""ctypes binding of the C-ABI shared library (include/gtsam_b200.h).
+
+The library is the product; this module only loads it and marshals numpy
+buffers.  It fails loudly when the CUDA extension is missing or no GPU is
+visible — there is no CPU fallback (the oracle under oracle/ is test
+infrastructure and is never imported from here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import problem as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgtsam_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "b200_var_storage", "b200_var_dim", "b200_factor_arity", "b200_factor_meas_size", "b200_factor_dim",
+    "b200_ctx_create", "b200_ctx_destroy", "b200_last_error_string", "b200_launch_count", "b200_ctx_stream",
+    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_get_values", "b200_values_size",
+    "b200_delta_size", "b200_error", "b200_linearize", "b200_get_jacobians", "b200_hessian_diagonal",
+    "b200_solve", "b200_get_delta", "b200_try_step", "b200_accept_step", "b200_lm_params_legacy",
+    "b200_lm_params_ceres", "b200_lm_create", "b200_lm_destroy", "b200_lm_iterate", "b200_lm_optimize",
+    "b200_lm_get_state", "b200_lm_reset", "b200_gn_iterate", "b200_symbolic_info_get", "b200_get_cliques",
+    "b200_get_conditional", "b200_shared_front_buffer",
+]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gtsam_b200 status {code}: {msg}")
+        self.code = code
+
+
+class IndeterminantLinearSystemException(B200Error):
+    """Mirror of gtsam::IndeterminantLinearSystemException (gtsam/linear/linearExceptions.h)."""
+
+    def __init__(self, var):
+        B200Error.__init__(self, P.INDETERMINATE, f"indeterminant linear system near variable {var}")
+        self.nearby_variable = var
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(gtsam_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        vp = C.c_void_p
+        L.b200_last_error_string.restype = C.c_char_p
+        L.b200_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.b200_ctx_destroy.argtypes = [vp]
+        L.b200_launch_count.argtypes = [vp]
+        L.b200_launch_count.restype = C.c_int64
+        L.b200_ctx_stream.argtypes = [vp]
+        L.b200_ctx_stream.restype = vp
+        L.b200_problem_create.argtypes = [vp, C.POINTER(P.CProblemDesc), C.POINTER(vp)]
+        L.b200_problem_destroy.argtypes = [vp]
+        L.b200_set_values.argtypes = [vp, dp]
+        L.b200_get_values.argtypes = [vp, dp]
+        L.b200_values_size.argtypes = [vp]
+        L.b200_values_size.restype = C.c_int64
+        L.b200_delta_size.argtypes = [vp]
+        L.b200_delta_size.restype = C.c_int64
+        L.b200_error.argtypes = [vp, dp]
+        L.b200_linearize.argtypes = [vp]
+        L.b200_get_jacobians.argtypes = [vp, C.c_int64, dp]
+        L.b200_hessian_diagonal.argtypes = [vp, dp]
+        L.b200_solve.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp, ip]
+        L.b200_get_delta.argtypes = [vp, dp]
+        L.b200_try_step.argtypes = [vp, dp]
+        L.b200_accept_step.argtypes = [vp]
+        L.b200_lm_params_legacy.argtypes = [C.POINTER(P.CLMParams)]
+        L.b200_lm_params_ceres.argtypes = [C.POINTER(P.CLMParams)]
+        L.b200_lm_create.argtypes = [vp, C.POINTER(P.CLMParams), C.POINTER(vp)]
+        L.b200_lm_destroy.argtypes = [vp]
+        L.b200_lm_iterate.argtypes = [vp]
+        L.b200_lm_optimize.argtypes = [vp]
+        L.b200_lm_get_state.argtypes = [vp, C.POINTER(P.CLMState)]
+        L.b200_lm_reset.argtypes = [vp]
+        L.b200_gn_iterate.argtypes = [vp, dp]
+        L.b200_symbolic_info_get.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
+        L.b200_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
+        L.b200_get_conditional.argtypes = [vp, C.c_int64, dp]
+        L.b200_shared_front_buffer.argtypes = [vp, C.POINTER(vp), ip]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200Error(rc, lib().b200_last_error_string().decode())
+
+
+class Context:
+    """One CUDA device + stream (b200_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.b200_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def launch_count(self) -> int:
+        return int(self.L.b200_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.L.b200_ctx_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            self.L.b200_ctx_destroy(self.h)
+            self.h = None
+
+
+class DeviceProblem:
+    """Device-resident problem (b200_problem): values, factor tables, junction tree."""
+
+    def __init__(self, ctx: Context, prob: P.Problem):
+        self.ctx, self.prob, self.L = ctx, prob, ctx.L
+        desc, keep = prob.c_desc()
+        h = C.c_void_p()
+        _check(self.L.b200_problem_create(ctx.h, C.byref(desc), C.byref(h)))
+        del keep
+        self.h = h
+        self.nval = int(self.L.b200_values_size(h))
+        self.ndelta = int(self.L.b200_delta_size(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_values(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.size == self.nval
+        _check(self.L.b200_set_values(self.h, _dp(v)))
+
+    def get_values(self):
+        out = np.zeros(self.nval)
+        _check(self.L.b200_get_values(self.h, _dp(out)))
+        return out
+
+    def error(self) -> float:
+        e = C.c_double()
+        _check(self.L.b200_error(self.h, C.byref(e)))
+        return e.value
+
+    def linearize(self):
+        _check(self.L.b200_linearize(self.h))
+
+    def get_jacobians(self, group: int):
+        g = self.prob.groups[group]
+        d, nc = P.FACTOR_DIM[g.type], P.factor_ncols(g.type)
+        out = np.zeros(g.count * d * nc)
+        _check(self.L.b200_get_jacobians(self.h, group, _dp(out)))
+        return out.reshape(g.count, nc, d).transpose(0, 2, 1)
+
+    def hessian_diagonal(self):
+        out = np.zeros(self.ndelta)
+        _check(self.L.b200_hessian_diagonal(self.h, _dp(out)))
+        return out
+
+    def solve(self, lam=0.0, diagonal_damping=False, min_diagonal=1e-6, max_diagonal=1e32):
+        """Returns (status, linear_error(0), linear_error(delta), fail_var)."""
+        e0, e1, fv = C.c_double(), C.c_double(), C.c_int64(-1)
+        rc = self.L.b200_solve(self.h, lam, int(diagonal_damping), min_diagonal, max_diagonal,
+                               C.byref(e0), C.byref(e1), C.byref(fv))
+        if rc not in (P.OK, P.INDETERMINATE):
+            _check(rc)
+        return rc, e0.value, e1.value, fv.value
+
+    def get_delta(self):
+        out = np.zeros(self.ndelta)
+        _check(self.L.b200_get_delta(self.h, _dp(out)))
+        return out
+
+    def try_step(self) -> float:
+        e = C.c_double()
+        _check(self.L.b200_try_step(self.h, C.byref(e)))
+        return e.value
+
+    def accept_step(self):
+        _check(self.L.b200_accept_step(self.h))
+
+    def gn_iterate(self):
+        e = C.c_double()
+        rc = self.L.b200_gn_iterate(self.h, C.byref(e))
+        if rc not in (P.OK, P.INDETERMINATE):
+            _check(rc)
+        return rc, e.value
+
+    def symbolic_info(self) -> P.CSymbolicInfo:
+        info = P.CSymbolicInfo()
+        _check(self.L.b200_symbolic_info_get(self.h, C.byref(info)))
+        return info
+
+    def cliques(self):
+        info = self.symbolic_info()
+        fp = np.zeros(info.ncliques + 1, dtype=np.int64)
+        sp = np.zeros(info.ncliques + 1, dtype=np.int64)
+        fv = np.zeros(max(1, info.frontal_list_len), dtype=np.int64)
+        sv = np.zeros(max(1, info.separator_list_len), dtype=np.int64)
+        par = np.zeros(max(1, info.ncliques), dtype=np.int64)
+        _check(self.L.b200_get_cliques(self.h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par)))
+        return fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques]
+
+    def conditional(self, c: int):
+        fp, fv, sp, sv, _ = self.cliques()
+        dims = np.asarray(P.VAR_DIM)[self.prob.var_type]
+        f = int(dims[fv[fp[c]:fp[c + 1]]].sum())
+        s = int(dims[sv[sp[c]:sp[c + 1]]].sum())
+        out = np.zeros(f * (f + s + 1))
+        _check(self.L.b200_get_conditional(self.h, c, _dp(out)))
+        return out.reshape(f + s + 1, f).T

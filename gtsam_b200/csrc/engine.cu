@@ -1,0 +1,803 @@
+// engine.cu — C-ABI of include/gtsam_b200.h: packing, symbolic phase, kernel
+// scheduling (level-by-level walk of the junction tree) and the LM / GN host
+// control logic.  No CPU fallback anywhere: every numeric step is a kernel.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "kernels.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+static const int VAR_STORAGE[3] = {12, 3, 17};
+static const int VAR_DIM[3] = {6, 3, 9};
+static const int F_ARITY[B200_NUM_FACTOR_TYPES] = {2, 1, 1, 2, 2, 1};
+static const int F_MEAS[B200_NUM_FACTOR_TYPES] = {12, 12, 3, 2, 2, 17};
+static const int F_DIM[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
+static const int F_VT[B200_NUM_FACTOR_TYPES][2] = {{0, 0}, {0, -1}, {1, -1}, {0, 1}, {2, 1}, {2, -1}};
+
+static int noise_payload(int kind, int d) {
+  switch (kind) {
+    case B200_NOISE_UNIT: return 0;
+    case B200_NOISE_ISOTROPIC: return 1;
+    case B200_NOISE_DIAGONAL: return d;
+    case B200_NOISE_GAUSSIAN: return d * d;
+  }
+  return -1;
+}
+
+template <class T>
+static int upload(T** dst, const T* src, size_t n, cudaStream_t st) {
+  B200_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) B200_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return B200_OK;
+}
+template <class T>
+static int upload(T** dst, const std::vector<T>& v, cudaStream_t st) { return upload(dst, v.data(), v.size(), st); }
+
+static GroupView view(const b200_problem::Group& g) {
+  GroupView v;
+  v.type = g.type; v.noise_kind = g.noise_kind; v.per_factor = g.per_factor; v.noise_size = g.noise_size;
+  v.count = (int)g.count; v.keys = g.d_keys; v.meas = g.d_meas; v.noise = g.d_noise; v.cal_index = g.d_cal;
+  v.J = g.d_J; v.scat = g.d_scat;
+  return v;
+}
+static TreeView tview(const b200_problem* p) {
+  TreeView t;
+  t.arena = p->d_arena; t.off = p->d_off; t.nf = p->d_nf; t.ns = p->d_ns; t.parent = p->d_parent;
+  t.ea_ptr = p->d_ea_ptr; t.ea_map = p->d_ea_map; t.didx_ptr = p->d_didx_ptr; t.didx = p->d_didx;
+  return t;
+}
+static EvalCtx ectx(const b200_problem* p, const double* values) {
+  EvalCtx c;
+  c.values = values; c.val_off = p->d_val_off; c.cal = p->d_cal;
+  return c;
+}
+
+#define DISPATCH_TYPE(T, STMT)                                                                  \
+  switch (T) {                                                                                  \
+    case B200_FACTOR_BETWEEN_POSE3: { constexpr int TY = B200_FACTOR_BETWEEN_POSE3; STMT; break; }         \
+    case B200_FACTOR_PRIOR_POSE3: { constexpr int TY = B200_FACTOR_PRIOR_POSE3; STMT; break; }             \
+    case B200_FACTOR_PRIOR_POINT3: { constexpr int TY = B200_FACTOR_PRIOR_POINT3; STMT; break; }           \
+    case B200_FACTOR_PROJECTION_CAL3S2: { constexpr int TY = B200_FACTOR_PROJECTION_CAL3S2; STMT; break; } \
+    case B200_FACTOR_SFM_BUNDLER: { constexpr int TY = B200_FACTOR_SFM_BUNDLER; STMT; break; }             \
+    case B200_FACTOR_PRIOR_CAM_BUNDLER: { constexpr int TY = B200_FACTOR_PRIOR_CAM_BUNDLER; STMT; break; } \
+  }
+
+static int reduce_blocks(int64_t count, int threads, int sm) {
+  int64_t b = (count + threads - 1) / threads;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm * 8));
+}
+
+// graph.error(values) -> *slot (device double)
+static int enqueue_error(b200_problem* p, const double* values, double* slot) {
+  cudaStream_t st = p->ctx->stream;
+  bool first = true;
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = reduce_blocks(g.count, 256, p->ctx->sm_count);
+    DISPATCH_TYPE(g.type, (error_kernel<TY><<<nb, 256, 0, st>>>(view(g), ectx(p, values), p->d_partials)));
+    reduce_partials_kernel<<<1, 256, 0, st>>>(p->d_partials, nb, slot, first ? 0 : 1);
+    p->ctx->launches += 2;
+    first = false;
+  }
+  if (first) B200_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), st));
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+static int enqueue_linearize(b200_problem* p) {
+  cudaStream_t st = p->ctx->stream;
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = (int)((g.count + 127) / 128);
+    DISPATCH_TYPE(g.type, (linearize_kernel<TY><<<nb, 128, 0, st>>>(view(g), ectx(p, p->d_values))));
+    p->ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  p->linearized = true;
+  return B200_OK;
+}
+
+static int enqueue_hdiag(b200_problem* p) {
+  cudaStream_t st = p->ctx->stream;
+  B200_CUDA(cudaMemsetAsync(p->d_hdiag, 0, (size_t)p->ndelta * sizeof(double), st));
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = (int)((g.count + 127) / 128);
+    DISPATCH_TYPE(g.type, (hdiag_kernel<TY><<<nb, 128, 0, st>>>(view(g), p->d_var_dof, p->d_hdiag)));
+    p->ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// assemble + damp + eliminate + back-substitute + linear errors; no host sync
+static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double min_diag, double max_diag) {
+  cudaStream_t st = p->ctx->stream;
+  b200_ctx* ctx = p->ctx;
+  const TreeView t = tview(p);
+  B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->sym.arena_doubles * sizeof(double), st));
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = (int)((g.count + 127) / 128);
+    DISPATCH_TYPE(g.type, (assemble_kernel<TY><<<nb, 128, 0, st>>>(view(g), t)));
+    ctx->launches++;
+  }
+  if (lambda > 0) {
+    if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
+    damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, lambda,
+                                                                diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
+    ctx->launches++;
+  }
+  // ---- elimination, leaves to roots ----
+  for (size_t l = 0; l < p->levels.size(); l++) {
+    const LevelPlan& L = p->levels[l];
+    if (L.small_count) {
+      const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const size_t smem = (size_t)kWarpsPerBlock * p->max_small_n * p->max_small_n * sizeof(double);
+      elim_small_kernel<<<nb, kWarpsPerBlock * 32, smem, st>>>(t, p->d_lvl_small + L.small_begin, L.small_count,
+                                                               p->max_small_n, p->d_scalars);
+      ctx->launches++;
+    }
+    if (L.large_count) {
+      const int* list = p->d_lvl_large + L.large_begin;
+      for (int k0 = 0; k0 < L.large_max_nf; k0 += kNB) {
+        potrf_trsm_kernel<<<L.large_count, 256, 0, st>>>(t, list, k0, p->d_scalars);
+        const int m = L.large_max_n - k0 - 1;
+        if (m > 0) {
+          const int T = (m + kTile - 1) / kTile;
+          syrk_kernel<<<dim3(T * (T + 1) / 2, L.large_count), 256, 0, st>>>(t, list, k0);
+          ctx->launches++;
+        }
+        ctx->launches++;
+      }
+      const int64_t w = L.large_max_ns + 1;
+      const int gx = (int)std::min<int64_t>((w * w + 255) / 256, 4096);
+      extend_add_kernel<<<dim3(gx, L.large_count), 256, 0, st>>>(t, list);
+      ctx->launches++;
+    }
+  }
+  // ---- back-substitution, roots to leaves ----
+  for (int l = (int)p->levels.size() - 1; l >= 0; l--) {
+    const LevelPlan& L = p->levels[l];
+    if (L.large_count) {
+      const size_t smem = (size_t)(L.large_max_nf + L.large_max_ns) * sizeof(double);
+      backsub_large_kernel<<<L.large_count, 256, smem, st>>>(t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars);
+      ctx->launches++;
+    }
+    if (L.small_count) {
+      const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      backsub_small_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, p->d_lvl_small + L.small_begin, L.small_count,
+                                                               p->d_delta, p->d_scalars);
+      ctx->launches++;
+    }
+  }
+  // ---- linear errors on the undamped graph ----
+  bool first = true;
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
+    double* p0 = p->d_partials;
+    double* p1 = p->d_partials + p->partial_cap / 2;
+    DISPATCH_TYPE(g.type, (linerr_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_delta, p->d_var_dof, p0, p1)));
+    reduce_partials_kernel<<<1, 256, 0, st>>>(p0, nb, &p->d_scalars->lin_err0, first ? 0 : 1);
+    reduce_partials_kernel<<<1, 256, 0, st>>>(p1, nb, &p->d_scalars->lin_err_delta, first ? 0 : 1);
+    ctx->launches += 3;
+    first = false;
+  }
+  B200_CUDA(cudaGetLastError());
+  p->solved = true;
+  return B200_OK;
+}
+
+static int enqueue_try_step(b200_problem* p) {
+  cudaStream_t st = p->ctx->stream;
+  retract_kernel<<<(int)((p->nvars + 127) / 128), 128, 0, st>>>(p->d_values, p->d_delta, p->d_val_off, p->d_var_dof,
+                                                                 p->d_var_type, (int)p->nvars, p->d_new_values);
+  p->ctx->launches++;
+  return enqueue_error(p, p->d_new_values, &p->d_scalars->new_error);
+}
+
+static int reset_flags(b200_problem* p) {
+  static const int init[2] = {INT_MAX, INT_MAX};
+  B200_CUDA(cudaMemcpyAsync(&p->d_scalars->fail_clique, init, 2 * sizeof(int), cudaMemcpyHostToDevice, p->ctx->stream));
+  return B200_OK;
+}
+static int fetch_scalars(b200_problem* p) {
+  B200_CUDA(cudaMemcpyAsync(p->h_scalars, p->d_scalars, sizeof(Scalars), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return B200_OK;
+}
+static int solve_status(const b200_problem* p, int64_t* fail_var) {
+  const Scalars* s = p->h_scalars;
+  int c = std::min(s->fail_clique, s->nan_clique);
+  if (c == INT_MAX) { if (fail_var) *fail_var = -1; return B200_OK; }
+  if (fail_var) *fail_var = p->sym.front_vars[p->sym.front_ptr[c]];
+  return B200_INDETERMINATE;
+}
+
+// Validation of a problem description + the symbolic phase.  Host only: needs
+// no GPU, so it is also exposed through b200_symbolic_create for CPU tests.
+struct PackedGroup { int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas; int64_t count, gi0; };
+struct Packed {
+  std::vector<int> val_off, var_dof, var_dim;
+  std::vector<int64_t> fkey0, fkey1;
+  std::vector<PackedGroup> groups;
+  int64_t total = 0;
+  Symbolic sym;
+};
+static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
+#define FAIL(code, msg) do { set_error(msg); return code; } while (0)
+  if (!d || d->nvars < 0 || d->ngroups < 0) FAIL(B200_INVALID_ARGUMENT, "bad problem description");
+  const int64_t n = d->nvars;
+  pk->val_off.assign(n + 1, 0); pk->var_dof.assign(n + 1, 0); pk->var_dim.assign(n, 0);
+  for (int64_t v = 0; v < n; v++) {
+    const int t = d->var_type[v];
+    if (t < 0 || t > 2) FAIL(B200_INVALID_ARGUMENT, "unknown variable type");
+    pk->var_dim[v] = VAR_DIM[t];
+    pk->val_off[v + 1] = pk->val_off[v] + VAR_STORAGE[t];
+    pk->var_dof[v + 1] = pk->var_dof[v] + VAR_DIM[t];
+  }
+  int64_t total = 0, next = 0;
+  for (int64_t g = 0; g < d->ngroups; g++) total += d->groups[g].count;
+  pk->total = total;
+  pk->fkey0.assign(total, -1); pk->fkey1.assign(total, -1);
+  std::vector<char> used(total, 0);
+  pk->groups.resize(d->ngroups);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+    const b200_factor_group& s = d->groups[gi];
+    PackedGroup& g = pk->groups[gi];
+    if (s.type < 0 || s.type >= B200_NUM_FACTOR_TYPES) FAIL(B200_UNSUPPORTED_FACTOR, "unsupported factor type");
+    g.type = s.type; g.noise_kind = s.noise_kind; g.per_factor = s.noise_per_factor; g.count = s.count;
+    g.d = F_DIM[s.type]; g.arity = F_ARITY[s.type]; g.meas = F_MEAS[s.type];
+    g.ncols = VAR_DIM[F_VT[s.type][0]] + (g.arity == 2 ? VAR_DIM[F_VT[s.type][1]] : 0) + 1;
+    g.noise_size = noise_payload(s.noise_kind, g.d);
+    if (g.noise_size < 0) FAIL(B200_UNSUPPORTED_NOISE, "unsupported noise model (Constrained/Robust are out of scope)");
+    g.gi0 = s.graph_index0 < 0 ? next : s.graph_index0;
+    next = g.gi0 + s.count;
+    if (s.count < 0 || g.gi0 + s.count > total) FAIL(B200_INVALID_ARGUMENT, "graph_index0 out of range");
+    if (s.count > INT_MAX / 2) FAIL(B200_INVALID_ARGUMENT, "factor group too large");
+    for (int64_t i = 0; i < s.count; i++) {
+      if (used[g.gi0 + i]) FAIL(B200_INVALID_ARGUMENT, "overlapping graph positions");
+      used[g.gi0 + i] = 1;
+      for (int a = 0; a < g.arity; a++) {
+        const int64_t k = s.keys[i * g.arity + a];
+        if (k < 0 || k >= n || d->var_type[k] != F_VT[s.type][a])
+          FAIL(B200_INVALID_ARGUMENT, "factor key missing or of the wrong value type (ValuesKeyDoesNotExist / ValuesIncorrectType)");
+      }
+      pk->fkey0[g.gi0 + i] = s.keys[i * g.arity];
+      if (g.arity == 2) pk->fkey1[g.gi0 + i] = s.keys[i * g.arity + 1];
+    }
+    if (s.type == B200_FACTOR_PROJECTION_CAL3S2) {
+      if (d->ncal < 1) FAIL(B200_INVALID_ARGUMENT, "projection factors need a calibration");
+      if (s.cal_index)
+        for (int64_t i = 0; i < s.count; i++)
+          if (s.cal_index[i] < 0 || s.cal_index[i] >= d->ncal) FAIL(B200_INVALID_ARGUMENT, "calibration index out of range");
+    }
+  }
+  const char* serr = "";
+  if (!build_symbolic(n, pk->var_dim.data(), d->ordering, total, pk->fkey0.data(), pk->fkey1.data(), &pk->sym, &serr))
+    FAIL(B200_INVALID_ARGUMENT, serr);
+#undef FAIL
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int b200_var_storage(int32_t t) { return (t >= 0 && t < 3) ? VAR_STORAGE[t] : -1; }
+int b200_var_dim(int32_t t) { return (t >= 0 && t < 3) ? VAR_DIM[t] : -1; }
+int b200_factor_arity(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_ARITY[t] : -1; }
+int b200_factor_meas_size(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_MEAS[t] : -1; }
+int b200_factor_dim(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_DIM[t] : -1; }
+const char* b200_last_error_string(void) { return g_err.c_str(); }
+
+int b200_ctx_create(int device, b200_ctx** out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device visible: gtsam_b200 has no CPU fallback");
+    return B200_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(device));
+  b200_ctx* c = new b200_ctx();
+  c->device = device;
+  B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
+  B200_CUDA(cudaFuncSetAttribute(backsub_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  *out = c;
+  return B200_OK;
+}
+int b200_ctx_destroy(b200_ctx* c) {
+  if (!c) return B200_OK;
+  cudaSetDevice(c->device);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return B200_OK;
+}
+int64_t b200_launch_count(const b200_ctx* c) { return c->launches; }
+void* b200_ctx_stream(const b200_ctx* c) { return (void*)c->stream; }
+
+int b200_problem_destroy(b200_problem* p) {
+  if (!p) return B200_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (auto& g : p->groups) {
+    cudaFree(g.d_keys); cudaFree(g.d_meas); cudaFree(g.d_noise); cudaFree(g.d_cal); cudaFree(g.d_J); cudaFree(g.d_scat);
+  }
+  cudaFree(p->d_values); cudaFree(p->d_new_values); cudaFree(p->d_delta); cudaFree(p->d_hdiag);
+  cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
+  cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
+  cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
+  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_partials); cudaFree(p->d_scalars);
+  cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned);
+  delete p;
+  return B200_OK;
+}
+
+int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem** out) {
+  if (!ctx || !d || !out) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  b200_problem* p = new b200_problem();
+  p->ctx = ctx;
+#define FAIL(code, msg) do { set_error(msg); b200_problem_destroy(p); return code; } while (0)
+  Packed pk;
+  {
+    const int rc = pack_and_symbolic(d, &pk);
+    if (rc) { b200_problem_destroy(p); return rc; }
+  }
+  const int64_t n = d->nvars;
+  const int64_t total = pk.total;
+  p->nvars = n; p->nval = pk.val_off[n]; p->ndelta = pk.var_dof[n]; p->nfactors = total;
+  p->var_type.assign(d->var_type, d->var_type + n);
+  std::vector<int>&val_off = pk.val_off, &var_dof = pk.var_dof, &var_dim = pk.var_dim;
+  std::vector<int64_t>&fkey0 = pk.fkey0, &fkey1 = pk.fkey1;
+  p->groups.resize(d->ngroups);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+    auto& g = p->groups[gi];
+    const PackedGroup& q = pk.groups[gi];
+    g.type = q.type; g.noise_kind = q.noise_kind; g.per_factor = q.per_factor; g.noise_size = q.noise_size;
+    g.d = q.d; g.ncols = q.ncols; g.arity = q.arity; g.meas = q.meas; g.count = q.count; g.gi0 = q.gi0;
+  }
+  p->sym = std::move(pk.sym);
+  const Symbolic& S = p->sym;
+#define UP(call) do { int rc_ = (call); if (rc_) { b200_problem_destroy(p); return rc_; } } while (0)
+  // ---- values & variable tables ----
+  UP(upload(&p->d_values, d->values, (size_t)p->nval, st));
+  B200_CUDA(cudaMalloc((void**)&p->d_new_values, std::max<int64_t>(1, p->nval) * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&p->d_delta, std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  B200_CUDA(cudaMemsetAsync(p->d_delta, 0, std::max<int64_t>(1, p->ndelta) * sizeof(double), st));
+  B200_CUDA(cudaMalloc((void**)&p->d_hdiag, std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  UP(upload(&p->d_val_off, val_off, st));
+  UP(upload(&p->d_var_dof, var_dof, st));
+  UP(upload(&p->d_var_type, p->var_type, st));
+  UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
+  // ---- factor tables ----
+  std::vector<std::vector<int2>> hkeys(d->ngroups);
+  std::vector<std::vector<int4>> hscat(d->ngroups);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+    const b200_factor_group& s = d->groups[gi];
+    auto& g = p->groups[gi];
+    hkeys[gi].resize(s.count);
+    hscat[gi].resize(s.count);
+    for (int64_t i = 0; i < s.count; i++) {
+      const int64_t pos = g.gi0 + i;
+      hkeys[gi][i] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
+      hscat[gi][i] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], 0);
+    }
+    UP(upload(&g.d_keys, hkeys[gi], st));
+    UP(upload(&g.d_scat, hscat[gi], st));
+    UP(upload(&g.d_meas, s.meas, (size_t)s.count * g.meas, st));
+    UP(upload(&g.d_noise, s.noise, (size_t)g.noise_size * (s.noise_per_factor ? s.count : 1), st));
+    if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.cal_index) {
+      UP(upload(&g.d_cal, s.cal_index, (size_t)s.count, st));
+    }
+    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)s.count * g.d * g.ncols) * sizeof(double)));
+  }
+  // ---- junction tree tables ----
+  std::vector<int> parent32(S.ncliques);
+  for (int64_t c = 0; c < S.ncliques; c++) parent32[c] = (int)S.parent[c];
+  UP(upload(&p->d_off, S.off, st));
+  UP(upload(&p->d_nf, S.nf, st));
+  UP(upload(&p->d_ns, S.ns, st));
+  UP(upload(&p->d_parent, parent32, st));
+  UP(upload(&p->d_ea_ptr, S.ea_ptr, st));
+  UP(upload(&p->d_ea_map, S.ea_map, st));
+  UP(upload(&p->d_didx_ptr, S.didx_ptr, st));
+  UP(upload(&p->d_didx, S.didx, st));
+  std::vector<int64_t> diag_index(p->ndelta);
+  for (int64_t v = 0; v < n; v++) {
+    const int c = S.var_clique[v];
+    const int64_t nn = S.nf[c] + S.ns[c] + 1;
+    for (int k = 0; k < var_dim[v]; k++) diag_index[var_dof[v] + k] = S.off[c] + (S.var_slot[v] + k) * (nn + 1);
+  }
+  UP(upload(&p->d_diag_index, diag_index, st));
+  // ---- level plans: small (one warp per clique) / large (blocked) ----
+  std::vector<int> small, large;
+  p->levels.resize(S.nlevels);
+  p->max_small_n = 1;
+  for (int64_t l = 0; l < S.nlevels; l++) {
+    LevelPlan& L = p->levels[l];
+    L = LevelPlan();
+    L.small_begin = (int)small.size();
+    L.large_begin = (int)large.size();
+    for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
+      const int c = S.lvl_cliques[q];
+      const int nn = S.nf[c] + S.ns[c] + 1;
+      if (nn <= kSmallMaxN) {
+        small.push_back(c);
+        p->max_small_n = std::max(p->max_small_n, nn);
+      } else {
+        large.push_back(c);
+        L.large_max_nf = std::max(L.large_max_nf, S.nf[c]);
+        L.large_max_ns = std::max(L.large_max_ns, S.ns[c]);
+        L.large_max_n = std::max(L.large_max_n, nn);
+      }
+    }
+    L.small_count = (int)small.size() - L.small_begin;
+    L.large_count = (int)large.size() - L.large_begin;
+    if ((size_t)(L.large_max_nf + L.large_max_ns) * sizeof(double) > 200 * 1024)
+      FAIL(B200_INVALID_ARGUMENT, "front too large for the single-CTA back-substitution of this build");
+  }
+  UP(upload(&p->d_lvl_small, small, st));
+  UP(upload(&p->d_lvl_large, large, st));
+  // ---- arena + scratch ----
+  B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, S.arena_doubles) * sizeof(double)));
+  p->partial_cap = 2 * ctx->sm_count * 8;
+  B200_CUDA(cudaMalloc((void**)&p->d_partials, (size_t)p->partial_cap * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&p->d_scalars, sizeof(Scalars)));
+  B200_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(Scalars), st));
+  B200_CUDA(cudaMallocHost((void**)&p->h_scalars, sizeof(Scalars)));
+  B200_CUDA(cudaMallocHost((void**)&p->h_pinned, std::max<int64_t>(1, std::max(p->nval, p->ndelta)) * sizeof(double)));
+  B200_CUDA(cudaStreamSynchronize(st));
+#undef FAIL
+#undef UP
+  *out = p;
+  return B200_OK;
+}
+
+int64_t b200_values_size(const b200_problem* p) { return p->nval; }
+int64_t b200_delta_size(const b200_problem* p) { return p->ndelta; }
+
+int b200_set_values(b200_problem* p, const double* v) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  memcpy(p->h_pinned, v, (size_t)p->nval * sizeof(double));
+  B200_CUDA(cudaMemcpyAsync(p->d_values, p->h_pinned, (size_t)p->nval * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  p->linearized = p->solved = false;
+  return B200_OK;
+}
+int b200_get_values(b200_problem* p, double* v) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  memcpy(v, p->h_pinned, (size_t)p->nval * sizeof(double));
+  return B200_OK;
+}
+
+int b200_error(b200_problem* p, double* err) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  int rc = enqueue_error(p, p->d_values, &p->d_scalars->error);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  *err = p->h_scalars->error;
+  return B200_OK;
+}
+
+int b200_linearize(b200_problem* p) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  return enqueue_linearize(p);
+}
+
+int b200_get_jacobians(b200_problem* p, int64_t gi, double* out) {
+  if (gi < 0 || gi >= (int64_t)p->groups.size()) { set_error("group out of range"); return B200_INVALID_ARGUMENT; }
+  if (!p->linearized) { set_error("b200_get_jacobians before b200_linearize"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  auto& g = p->groups[gi];
+  const size_t per = (size_t)g.d * g.ncols;
+  std::vector<double> soa(per * g.count);
+  B200_CUDA(cudaMemcpyAsync(soa.data(), g.d_J, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  for (int64_t f = 0; f < g.count; f++)
+    for (size_t e = 0; e < per; e++) out[f * per + e] = soa[e * g.count + f];
+  return B200_OK;
+}
+
+int b200_hessian_diagonal(b200_problem* p, double* out) {
+  if (!p->linearized) { set_error("b200_hessian_diagonal before b200_linearize"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  int rc = enqueue_hdiag(p);
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_hdiag, (size_t)p->ndelta * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  memcpy(out, p->h_pinned, (size_t)p->ndelta * sizeof(double));
+  return B200_OK;
+}
+
+int b200_solve(b200_problem* p, double lambda, int diagonal, double min_diag, double max_diag, double* e0, double* e1,
+               int64_t* fail_var) {
+  if (!p->linearized) { set_error("b200_solve before b200_linearize"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  int rc = reset_flags(p);
+  if (rc) return rc;
+  rc = enqueue_solve(p, lambda, diagonal, min_diag, max_diag);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  if (e0) *e0 = p->h_scalars->lin_err0;
+  if (e1) *e1 = p->h_scalars->lin_err_delta;
+  return solve_status(p, fail_var);
+}
+
+int b200_get_delta(b200_problem* p, double* out) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_delta, (size_t)p->ndelta * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  memcpy(out, p->h_pinned, (size_t)p->ndelta * sizeof(double));
+  return B200_OK;
+}
+
+int b200_try_step(b200_problem* p, double* new_error) {
+  if (!p->solved) { set_error("b200_try_step before b200_solve"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  int rc = enqueue_try_step(p);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  *new_error = p->h_scalars->new_error;
+  return B200_OK;
+}
+
+int b200_accept_step(b200_problem* p) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  std::swap(p->d_values, p->d_new_values);
+  p->linearized = p->solved = false;
+  return B200_OK;
+}
+
+// ---- symbolic introspection ------------------------------------------------------
+int b200_symbolic_info_get(const b200_problem* p, b200_symbolic_info* info) {
+  const Symbolic& S = p->sym;
+  info->ncliques = S.ncliques; info->nlevels = S.nlevels; info->total_dim = p->ndelta;
+  info->max_frontal_dim = S.max_nf; info->max_separator_dim = S.max_ns;
+  info->frontal_list_len = (int64_t)S.front_vars.size(); info->separator_list_len = (int64_t)S.sep_vars.size();
+  info->factor_flops = S.flops; info->front_bytes = S.arena_doubles * 8;
+  return B200_OK;
+}
+int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  const Symbolic& S = p->sym;
+  memcpy(fp, S.front_ptr.data(), S.front_ptr.size() * sizeof(int64_t));
+  memcpy(fv, S.front_vars.data(), S.front_vars.size() * sizeof(int64_t));
+  memcpy(sp, S.sep_ptr.data(), S.sep_ptr.size() * sizeof(int64_t));
+  memcpy(sv, S.sep_vars.data(), S.sep_vars.size() * sizeof(int64_t));
+  memcpy(parent, S.parent.data(), S.parent.size() * sizeof(int64_t));
+  return B200_OK;
+}
+/* conditional [R S d] of clique c after a solve: nf x (nf+ns+1) column-major */
+int b200_get_conditional(b200_problem* p, int64_t c, double* out) {
+  const Symbolic& S = p->sym;
+  if (c < 0 || c >= S.ncliques || !p->solved) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  const int64_t f = S.nf[c], nn = f + S.ns[c] + 1;
+  std::vector<double> M((size_t)(nn * nn));
+  B200_CUDA(cudaMemcpyAsync(M.data(), p->d_arena + S.off[c], M.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  for (int64_t j = 0; j < nn; j++)
+    for (int64_t i = 0; i < f; i++) out[i + j * f] = (i <= j) ? M[(size_t)(i + j * nn)] : 0.0;
+  return B200_OK;
+}
+struct b200_symbolic { Symbolic sym; int64_t ndelta; };
+int b200_symbolic_create(const b200_problem_desc* d, b200_symbolic** out) {
+  Packed pk;
+  const int rc = pack_and_symbolic(d, &pk);
+  if (rc) return rc;
+  b200_symbolic* s = new b200_symbolic();
+  s->ndelta = pk.var_dof[d->nvars];
+  s->sym = std::move(pk.sym);
+  *out = s;
+  return B200_OK;
+}
+int b200_symbolic_destroy(b200_symbolic* s) { delete s; return B200_OK; }
+static void fill_info(const Symbolic& S, int64_t ndelta, b200_symbolic_info* info) {
+  info->ncliques = S.ncliques; info->nlevels = S.nlevels; info->total_dim = ndelta;
+  info->max_frontal_dim = S.max_nf; info->max_separator_dim = S.max_ns;
+  info->frontal_list_len = (int64_t)S.front_vars.size(); info->separator_list_len = (int64_t)S.sep_vars.size();
+  info->factor_flops = S.flops; info->front_bytes = S.arena_doubles * 8;
+}
+static void fill_cliques(const Symbolic& S, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  memcpy(fp, S.front_ptr.data(), S.front_ptr.size() * sizeof(int64_t));
+  memcpy(fv, S.front_vars.data(), S.front_vars.size() * sizeof(int64_t));
+  memcpy(sp, S.sep_ptr.data(), S.sep_ptr.size() * sizeof(int64_t));
+  memcpy(sv, S.sep_vars.data(), S.sep_vars.size() * sizeof(int64_t));
+  memcpy(parent, S.parent.data(), S.parent.size() * sizeof(int64_t));
+}
+int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info) { fill_info(s->sym, s->ndelta, info); return B200_OK; }
+int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  fill_cliques(s->sym, fp, fv, sp, sv, parent);
+  return B200_OK;
+}
+int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level) {
+  for (int64_t c = 0; c < s->sym.ncliques; c++) level[c] = s->sym.level[c];
+  return B200_OK;
+}
+
+int b200_shared_front_buffer(b200_problem* p, void** ptr, int64_t* nd) {
+  (void)p; *ptr = nullptr; *nd = 0;
+  set_error("multi-GPU sharding not built yet in this round");
+  return B200_INVALID_ARGUMENT;
+}
+
+// ---- LM / GN host control (a17, a18) -----------------------------------------------
+void b200_lm_params_legacy(b200_lm_params* P) {
+  /* LevenbergMarquardtParams::SetLegacyDefaults, gtsam/nonlinear/LevenbergMarquardtParams.h:69-84 */
+  P->max_iterations = 100; P->relative_error_tol = 1e-5; P->absolute_error_tol = 1e-5; P->error_tol = 0.0;
+  P->lambda_initial = 1e-5; P->lambda_factor = 10.0; P->lambda_upper_bound = 1e5; P->lambda_lower_bound = 0.0;
+  P->min_model_fidelity = 1e-3; P->diagonal_damping = 0; P->use_fixed_lambda_factor = 1;
+  P->min_diagonal = 1e-6; P->max_diagonal = 1e32;
+}
+void b200_lm_params_ceres(b200_lm_params* P) {
+  /* ::SetCeresDefaults, :87-99 */
+  b200_lm_params_legacy(P);
+  P->max_iterations = 50; P->absolute_error_tol = 0; P->relative_error_tol = 1e-6;
+  P->lambda_upper_bound = 1e32; P->lambda_lower_bound = 1e-16; P->lambda_initial = 1e-4; P->lambda_factor = 2.0;
+  P->min_model_fidelity = 1e-3; P->diagonal_damping = 1; P->use_fixed_lambda_factor = 0;
+}
+
+int b200_lm_reset(b200_lm* lm) {
+  double e;
+  int rc = b200_error(lm->prob, &e);
+  if (rc) return rc;
+  lm->state.error = e;
+  lm->state.lambda = lm->params.lambda_initial;
+  lm->state.current_factor = lm->params.lambda_factor;
+  lm->state.iterations = 0;
+  lm->state.total_inner_iterations = 0;
+  return B200_OK;
+}
+int b200_lm_create(b200_problem* p, const b200_lm_params* params, b200_lm** out) {
+  b200_lm* lm = new b200_lm();
+  lm->prob = p;
+  lm->params = *params;
+  int rc = b200_lm_reset(lm);
+  if (rc) { delete lm; return rc; }
+  *out = lm;
+  return B200_OK;
+}
+int b200_lm_destroy(b200_lm* lm) { delete lm; return B200_OK; }
+int b200_lm_get_state(const b200_lm* lm, b200_lm_state* s) { *s = lm->state; return B200_OK; }
+
+/* LevenbergMarquardtOptimizer::tryLambda (gtsam/nonlinear/LevenbergMarquardtOptimizer.cpp:121-270):
+ * one damped solve + retract + error enqueued back to back, ONE host sync, then
+ * the reference's accept/reject logic on four scalars.  *done = 1 when the
+ * lambda search of this outer iteration is over. */
+static int try_lambda(b200_lm* lm, int* done) {
+  b200_problem* p = lm->prob;
+  const b200_lm_params& P = lm->params;
+  b200_lm_state& S = lm->state;
+  int rc = reset_flags(p);
+  if (rc) return rc;
+  rc = enqueue_solve(p, S.lambda, P.diagonal_damping, P.min_diagonal, P.max_diagonal);
+  if (rc) return rc;
+  rc = enqueue_try_step(p);  // computed speculatively; discarded when the step is invalid
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  const bool solved = solve_status(p, nullptr) == B200_OK;
+  double modelFidelity = 0.0, newError = INFINITY, costChange = 0.0;
+  bool step_is_successful = false, stopSearchingLambda = false;
+  if (solved) {
+    const double oldLin = p->h_scalars->lin_err0, newLin = p->h_scalars->lin_err_delta;
+    const double linearizedCostChange = oldLin - newLin;
+    if (linearizedCostChange >= 0) {
+      newError = p->h_scalars->new_error;
+      costChange = S.error - newError;
+      if (linearizedCostChange > std::numeric_limits<double>::epsilon() * oldLin) {
+        modelFidelity = costChange / linearizedCostChange;
+        step_is_successful = modelFidelity > P.min_model_fidelity;
+      }
+      const double minAbsoluteTolerance = P.relative_error_tol * S.error;
+      if (std::abs(costChange) < minAbsoluteTolerance) stopSearchingLambda = true;
+    }
+  }
+  if (step_is_successful) {
+    /* decreaseLambda, internal/LevenbergMarquardtState.h:81-94 */
+    double newLambda = S.lambda, newFactor = S.current_factor;
+    if (P.use_fixed_lambda_factor) {
+      newLambda /= S.current_factor;
+    } else {
+      newLambda *= std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * modelFidelity - 1.0, 3));
+      newFactor = 2.0 * S.current_factor;
+    }
+    newLambda = std::max(P.lambda_lower_bound, newLambda);
+    b200_accept_step(p);
+    S.error = newError; S.lambda = newLambda; S.current_factor = newFactor;
+    S.iterations += 1; S.total_inner_iterations += 1;
+    *done = 1;
+  } else if (!stopSearchingLambda) {
+    /* increaseLambda, :70-76 */
+    S.lambda *= S.current_factor;
+    S.total_inner_iterations += 1;
+    if (!P.use_fixed_lambda_factor) S.current_factor *= 2.0;
+    *done = S.lambda >= P.lambda_upper_bound ? 1 : 0;
+  } else {
+    *done = 1;
+  }
+  return B200_OK;
+}
+
+int b200_lm_iterate(b200_lm* lm) {
+  B200_CUDA(cudaSetDevice(lm->prob->ctx->device));
+  int rc = enqueue_linearize(lm->prob);
+  if (rc) return rc;
+  int done = 0;
+  while (!done) {
+    rc = try_lambda(lm, &done);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+
+/* checkConvergence, gtsam/nonlinear/NonlinearOptimizer.cpp:182-231 */
+static bool check_convergence(double rel, double absT, double errT, double cur, double nw) {
+  if (nw <= errT) return true;
+  const double absoluteDecrease = cur - nw;
+  const double relativeDecrease = absoluteDecrease / cur;
+  return (rel && (relativeDecrease <= rel)) || (absoluteDecrease <= absT);
+}
+
+/* NonlinearOptimizer::defaultOptimize, gtsam/nonlinear/NonlinearOptimizer.cpp:62-117 */
+int b200_lm_optimize(b200_lm* lm) {
+  const b200_lm_params& P = lm->params;
+  double currentError = lm->state.error;
+  if (currentError <= P.error_tol) return B200_OK;
+  if (lm->state.iterations >= P.max_iterations) return B200_OK;
+  double newError = currentError;
+  do {
+    currentError = newError;
+    int rc = b200_lm_iterate(lm);
+    if (rc) return rc;
+    newError = lm->state.error;
+  } while (lm->state.iterations < P.max_iterations &&
+           !check_convergence(P.relative_error_tol, P.absolute_error_tol, P.error_tol, currentError, newError) &&
+           std::isfinite(currentError));
+  return B200_OK;
+}
+
+/* GaussNewtonOptimizer::iterate, gtsam/nonlinear/GaussNewtonOptimizer.cpp:44-67 */
+int b200_gn_iterate(b200_problem* p, double* new_error) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  int rc = enqueue_linearize(p);
+  if (rc) return rc;
+  rc = reset_flags(p);
+  if (rc) return rc;
+  rc = enqueue_solve(p, 0.0, 0, 0, 0);
+  if (rc) return rc;
+  rc = enqueue_try_step(p);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  int64_t fv;
+  rc = solve_status(p, &fv);
+  if (rc) { set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
+  b200_accept_step(p);
+  if (new_error) *new_error = p->h_scalars->new_error;
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// engine.cuh — internal structures shared by the kernels and the C-ABI glue.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/gtsam_b200.h"
+#include "symbolic.h"
+
+namespace b200 {
+
+void set_error(const std::string& s);
+
+#define B200_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ::b200::set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " at " +     \
+                        __FILE__ + ":" + std::to_string(__LINE__));                       \
+      return B200_CUDA_ERROR;                                                             \
+    }                                                                                     \
+  } while (0)
+
+// Device-side view of one factor group (passed to kernels by value).
+struct GroupView {
+  int type, noise_kind, per_factor, noise_size;
+  int count;
+  const int2* keys;        // (key0, key1 or -1)
+  const double* meas;      // AoS, MEAS doubles per factor
+  const double* noise;     // shared payload or per-factor AoS
+  const int* cal_index;    // may be null
+  double* J;               // SoA: J[e * count + f], e = r + c*D (column-major element order)
+  const int4* scat;        // (clique, slot0, slot1, unused) per factor
+};
+
+// Device-side view of the junction tree + frontal arena.
+struct TreeView {
+  double* arena;           // all fronts, each (nf+ns+1)^2 col-major, upper triangle used
+  const int64_t* off;      // per clique offset into arena
+  const int* nf;
+  const int* ns;
+  const int* parent;
+  const int64_t* ea_ptr;
+  const int* ea_map;
+  const int64_t* didx_ptr;
+  const int* didx;
+};
+
+struct Scalars {           // device scalars fetched once per LM try
+  double error;            // graph.error(values)
+  double lin_err0;         // linear.error(0)
+  double lin_err_delta;    // linear.error(delta)
+  double new_error;        // graph.error(newValues)
+  int fail_clique;         // min clique id whose partial Cholesky failed (INT_MAX if none)
+  int nan_clique;          // min clique id with NaN in back-substitution
+  int pad[2];
+};
+
+struct LevelPlan {
+  int small_begin, small_count;   // range in d_lvl_small
+  int large_begin, large_count;   // range in d_lvl_large
+  int large_max_nf, large_max_n;  // over the large cliques of the level
+  int large_max_ns;
+};
+
+}  // namespace b200
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int sm_count = 0;
+};
+
+struct b200_problem {
+  b200_ctx* ctx = nullptr;
+  b200::Symbolic sym;
+  int64_t nvars = 0, nfactors = 0, nval = 0, ndelta = 0;
+  std::vector<int> var_type;
+  // host copies of group metadata
+  struct Group {
+    int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas;
+    int64_t count, gi0;
+    int2* d_keys = nullptr;
+    double* d_meas = nullptr;
+    double* d_noise = nullptr;
+    int* d_cal = nullptr;
+    double* d_J = nullptr;
+    int4* d_scat = nullptr;
+  };
+  std::vector<Group> groups;
+  // device state
+  double *d_values = nullptr, *d_new_values = nullptr, *d_delta = nullptr, *d_hdiag = nullptr;
+  int *d_val_off = nullptr, *d_var_type = nullptr, *d_var_dof = nullptr;
+  double* d_cal = nullptr;
+  double* d_arena = nullptr;
+  int64_t* d_off = nullptr;
+  int *d_nf = nullptr, *d_ns = nullptr, *d_parent = nullptr;
+  int64_t *d_ea_ptr = nullptr, *d_didx_ptr = nullptr;
+  int *d_ea_map = nullptr, *d_didx = nullptr;
+  int64_t* d_diag_index = nullptr;  // per delta scalar: arena index of its diagonal entry
+  int *d_lvl_small = nullptr, *d_lvl_large = nullptr;
+  std::vector<b200::LevelPlan> levels;
+  double* d_partials = nullptr;     // block partial sums
+  int partial_cap = 0;
+  b200::Scalars* d_scalars = nullptr;
+  b200::Scalars* h_scalars = nullptr;  // pinned
+  double* h_pinned = nullptr;          // pinned staging for values
+  bool linearized = false, solved = false;
+  int max_small_n = 0;
+};
+
+struct b200_lm {
+  b200_problem* prob;
+  b200_lm_params params;
+  b200_lm_state state;
+};

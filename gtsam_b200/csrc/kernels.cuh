@@ -1,0 +1,541 @@
+// kernels.cuh — the sm_100a kernels of the hot path (FP64).
+//
+//  linearize_kernel   a1-a7  residual + Jacobian + whitening, one thread / factor,
+//                            SoA (element-major) stores => every store coalesced
+//  error_kernel       a8     0.5*|R r|^2 block partial sums (deterministic 2-stage)
+//  assemble_kernel    a12    J^T J / J^T b / b^T b scatter-add into the owning front
+//  damp_kernel        a10    lambda*I or lambda*clip(diag H) on the diagonal
+//  hdiag_kernel       a10    hessianDiagonal
+//  elim_small_kernel  a13/14 one warp per clique: partial Cholesky in shared
+//                            memory + fused extend-add into the parent front
+//  potrf_trsm_kernel, syrk_kernel, extend_add_kernel   a13/14 for large fronts
+//  backsub_*_kernel   a15    x_F = R^-1 (d - S x_S), level by level
+//  linerr_kernel      a16    0.5*|A delta - b|^2 and 0.5*|b|^2
+//  retract_kernel     a9     x (+) delta per variable
+#pragma once
+#include <cooperative_groups.h>
+
+#include "engine.cuh"
+#include "factors.cuh"
+
+namespace b200 {
+
+constexpr int kSmallMaxN = 48;   // fronts up to this size run one-warp-per-clique
+constexpr int kWarpsPerBlock = 4;
+constexpr int kNB = 32;          // panel width of the blocked large-front path
+constexpr int kTile = 64;        // SYRK tile
+
+// ---------------------------------------------------------------------------
+// block reduction helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0;
+  if (w == 0) {
+    r = lane < NT / 32 ? sh[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+// out[0] (+)= sum(partials[0..n)) in a fixed order => bitwise reproducible
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n, double* out, int accumulate) {
+  __shared__ double sh[32];
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+  s = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) *out = accumulate ? (*out + s) : s;
+}
+
+// ---------------------------------------------------------------------------
+// linearize
+// ---------------------------------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(128) linearize_kernel(GroupView g, EvalCtx c) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const int2 k = g.keys[f];
+  double M[D * NC];
+  Eval<TYPE, true>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, M);
+  whiten<D, NC, 0>(M, g.noise_kind, g.noise + (g.per_factor ? (size_t)f * g.noise_size : 0));
+  double* J = g.J + f;
+#pragma unroll
+  for (int cc = 0; cc < NC; cc++)
+#pragma unroll
+    for (int r = 0; r < D; r++) J[(size_t)(r + cc * D) * g.count] = M[r * NC + cc];
+}
+
+// ---------------------------------------------------------------------------
+// nonlinear error: partial sums of 0.5*|whiten(r)|^2
+// ---------------------------------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, double* __restrict__ partials) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
+  __shared__ double sh[32];
+  double acc = 0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
+    const int2 k = g.keys[f];
+    double M[D * NC];
+    Eval<TYPE, false>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, M);
+    whiten<D, NC, NC - 1>(M, g.noise_kind, g.noise + (g.per_factor ? (size_t)f * g.noise_size : 0));
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < D; r++) s += M[r * NC + NC - 1] * M[r * NC + NC - 1];
+    acc += 0.5 * s;
+  }
+  acc = block_sum<256>(acc, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// linear error on the undamped linearization
+// ---------------------------------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* __restrict__ delta,
+                                                     const int* __restrict__ var_dof, double* __restrict__ p0,
+                                                     double* __restrict__ p1) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
+  __shared__ double sh[32];
+  double a0 = 0, a1 = 0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
+    const int2 k = g.keys[f];
+    const double* J = g.J + f;
+    double e[D], b[D];
+#pragma unroll
+    for (int r = 0; r < D; r++) { b[r] = J[(size_t)(r + (NC - 1) * D) * g.count]; e[r] = -b[r]; }
+    const double* d0 = delta + var_dof[k.x];
+#pragma unroll
+    for (int cc = 0; cc < N1; cc++) {
+      const double x = d0[cc];
+#pragma unroll
+      for (int r = 0; r < D; r++) e[r] += J[(size_t)(r + cc * D) * g.count] * x;
+    }
+    if (N2 > 0) {
+      const double* d1 = delta + var_dof[k.y];
+#pragma unroll
+      for (int cc = 0; cc < N2; cc++) {
+        const double x = d1[cc];
+#pragma unroll
+        for (int r = 0; r < D; r++) e[r] += J[(size_t)(r + (N1 + cc) * D) * g.count] * x;
+      }
+    }
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int r = 0; r < D; r++) { s0 += b[r] * b[r]; s1 += e[r] * e[r]; }
+    a0 += 0.5 * s0;
+    a1 += 0.5 * s1;
+  }
+  a0 = block_sum<256>(a0, sh);
+  a1 = block_sum<256>(a1, sh);
+  if (threadIdx.x == 0) { p0[blockIdx.x] = a0; p1[blockIdx.x] = a1; }
+}
+
+// ---------------------------------------------------------------------------
+// Hessian assembly: updateHessian semantics (gtsam/linear/JacobianFactor.cpp:563-598,
+// gtsam/linear/BinaryJacobianFactor.h:51-82) straight into the owning clique's
+// front.  Upper triangle only; FP64 red.global.add.
+// ---------------------------------------------------------------------------
+template <int D, int NA, int NB_>
+__device__ __forceinline__ void add_block(double* __restrict__ Mf, int ld, int sa, int sb, const double* A,
+                                          const double* B, bool diag) {
+  // entry (sa+ca, sb+cb) += A[:,ca] . B[:,cb]; stored in the upper triangle
+#pragma unroll
+  for (int ca = 0; ca < NA; ca++)
+#pragma unroll
+    for (int cb = 0; cb < NB_; cb++) {
+      if (diag && ca > cb) continue;
+      double s = 0;
+#pragma unroll
+      for (int r = 0; r < D; r++) s += A[ca * D + r] * B[cb * D + r];
+      const int i = sa + ca, j = sb + cb;
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      atomicAdd(Mf + lo + (size_t)hi * ld, s);
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const int4 sc = g.scat[f];
+  double Jl[D * NC];  // column-major
+  const double* J = g.J + f;
+#pragma unroll
+  for (int e = 0; e < D * NC; e++) Jl[e] = J[(size_t)e * g.count];
+  double* Mf = t.arena + t.off[sc.x];
+  const int ld = t.nf[sc.x] + t.ns[sc.x] + 1;
+  const int sb = ld - 1;
+  const double* A1 = Jl;
+  const double* bb = Jl + (N1 + N2) * D;
+  add_block<D, N1, N1>(Mf, ld, sc.y, sc.y, A1, A1, true);
+  add_block<D, N1, 1>(Mf, ld, sc.y, sb, A1, bb, false);
+  if (N2 > 0) {
+    const double* A2 = Jl + N1 * D;
+    add_block<D, N1, (N2 > 0 ? N2 : 1)>(Mf, ld, sc.y, sc.z, A1, A2, false);
+    add_block<D, (N2 > 0 ? N2 : 1), (N2 > 0 ? N2 : 1)>(Mf, ld, sc.z, sc.z, A2, A2, true);
+    add_block<D, (N2 > 0 ? N2 : 1), 1>(Mf, ld, sc.z, sb, A2, bb, false);
+  }
+  add_block<D, 1, 1>(Mf, ld, sb, sb, bb, bb, true);
+}
+
+// hessianDiagonal: gtsam/linear/JacobianFactor.cpp:516-541
+template <int TYPE>
+__global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __restrict__ var_dof, double* hdiag) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, N1 = FT::N1, N2 = FT::N2 };
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const int2 k = g.keys[f];
+  const double* J = g.J + f;
+#pragma unroll
+  for (int cc = 0; cc < N1 + N2; cc++) {
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < D; r++) { const double a = J[(size_t)(r + cc * D) * g.count]; s += a * a; }
+    const int idx = cc < N1 ? var_dof[k.x] + cc : var_dof[k.y] + (cc - N1);
+    atomicAdd(hdiag + idx, s);
+  }
+}
+
+// damping priors of buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)
+__global__ void damp_kernel(double* arena, const int64_t* __restrict__ diag_index, int n, double lambda,
+                            const double* __restrict__ hdiag, double min_diag, double max_diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a2 = 1.0;
+  if (hdiag) {
+    double h = fmin(fmax(hdiag[i], min_diag), max_diag);
+    const double sq = sqrt(h);
+    a2 = sq * sq;
+  }
+  const double sl = 1.0 / (1.0 / sqrt(lambda));
+  arena[diag_index[i]] += (sl * sl) * a2;
+}
+
+// ---------------------------------------------------------------------------
+// small fronts: one warp per clique, front staged in shared memory
+//   choleskyPartial (gtsam/base/cholesky.cpp:107-158) + extend-add of the
+//   Schur complement into the parent (gtsam/linear/HessianFactor.cpp:348-374)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int dexp(double x) {
+  int e;
+  (void)frexp(x, &e);
+  return e;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_n, Scalars* sc) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (idx >= count) return;
+  const int c = list[idx];
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  double* M = t.arena + t.off[c];
+  double* A = smem + (size_t)warp * smem_n * smem_n;
+  for (int e = lane; e < n * n; e += 32) A[e] = M[e];
+  __syncwarp();
+  bool ok = true;
+  for (int k = 0; k < f; k++) {
+    const double piv = A[k + k * n];
+    if (!(piv > 0.0)) ok = false;  // Eigen LLT: fail when pivot <= 0
+    const double r = sqrt(piv);
+    __syncwarp();
+    for (int j = k + lane; j < n; j += 32) A[k + j * n] = (j == k) ? r : A[k + j * n] / r;
+    __syncwarp();
+    const int w = n - k - 1;
+    for (int e = lane; e < w * w; e += 32) {
+      const int i = k + 1 + e % w, j = k + 1 + e / w;
+      if (i <= j) A[i + j * n] -= A[k + i * n] * A[k + j * n];
+    }
+    __syncwarp();
+  }
+  if (f >= 2) {
+    if (!(dexp(A[(f - 2) + (f - 2) * n]) - dexp(A[(f - 1) + (f - 1) * n]) < 12)) ok = false;
+  } else if (f == 1) {
+    if (!(dexp(A[0]) > -12)) ok = false;
+  }
+  if (!ok && lane == 0) atomicMin(&sc->fail_clique, c);
+  // conditional [R S d] back to the front (rows 0..f-1)
+  for (int e = lane; e < f * n; e += 32) {
+    const int i = e % f, j = e / f;
+    if (i <= j) M[i + (size_t)j * n] = A[i + j * n];
+  }
+  const int p = t.parent[c];
+  if (p >= 0) {
+    double* P = t.arena + t.off[p];
+    const int pn = t.nf[p] + t.ns[p] + 1;
+    const int* map = t.ea_map + t.ea_ptr[c];
+    const int w = s + 1;
+    for (int e = lane; e < w * w; e += 32) {
+      const int i = e % w, j = e / w;
+      if (i <= j) {
+        const int pi = map[i], pj = map[j];
+        const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+        atomicAdd(P + lo + (size_t)hi * pn, A[(f + i) + (f + j) * n]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// large fronts: blocked right-looking partial Cholesky in global memory.
+// Per panel [k0, k0+nb): (1) potrf of the nb x nb diagonal block + TRSM of the
+// row panel (one CTA per clique), (2) SYRK update of the trailing upper
+// triangle (grid of 64x64 tiles).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+potrf_trsm_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc) {
+  __shared__ double Dg[kNB][kNB + 1];
+  __shared__ int bad;
+  const int c = list[blockIdx.x];
+  const int f = t.nf[c], n = f + t.ns[c] + 1;
+  if (k0 >= f) return;
+  const int nb = min(kNB, f - k0);
+  double* M = t.arena + t.off[c];
+  const int tid = threadIdx.x;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e % nb, j = e / nb;
+    Dg[i][j] = (i <= j) ? M[(k0 + i) + (size_t)(k0 + j) * n] : 0.0;
+  }
+  __syncthreads();
+  // unblocked upper Cholesky of the diagonal block (right-looking)
+  for (int k = 0; k < nb; k++) {
+    const double piv = Dg[k][k];
+    __syncthreads();
+    if (tid == 0 && !(piv > 0.0)) bad = 1;
+    const double r = sqrt(piv);
+    if (tid < nb - k) {
+      const int j = k + tid;
+      Dg[k][j] = (j == k) ? r : Dg[k][j] / r;
+    }
+    __syncthreads();
+    const int w = nb - k - 1;
+    for (int e = tid; e < w * w; e += 256) {
+      const int i = k + 1 + e % w, j = k + 1 + e / w;
+      if (i <= j) Dg[i][j] -= Dg[k][i] * Dg[k][j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (k0 + nb == f) {  // last panel: underconstrained check on the last two pivots
+      if (f >= 2) {
+        const double r2 = nb >= 2 ? Dg[nb - 2][nb - 2] : M[(f - 2) + (size_t)(f - 2) * n];
+        if (!(dexp(r2) - dexp(Dg[nb - 1][nb - 1]) < 12)) bad = 1;
+      } else if (!(dexp(Dg[0][0]) > -12)) bad = 1;
+    }
+    if (bad) atomicMin(&sc->fail_clique, c);
+  }
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e % nb, j = e / nb;
+    if (i <= j) M[(k0 + i) + (size_t)(k0 + j) * n] = Dg[i][j];
+  }
+  // TRSM: columns j >= k0+nb : x = R^-T a (forward substitution), thread per column
+  for (int j = k0 + nb + tid; j < n; j += 256) {
+    double* col = M + (k0) + (size_t)j * n;
+    double x[kNB];
+#pragma unroll
+    for (int p = 0; p < kNB; p++) x[p] = p < nb ? col[p] : 0.0;
+#pragma unroll
+    for (int p = 0; p < kNB; p++) {
+      if (p < nb) {
+        double s = x[p];
+#pragma unroll
+        for (int q = 0; q < kNB; q++)
+          if (q < p) s -= Dg[q][p] * x[q];
+        x[p] = s / Dg[p][p];
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kNB; p++)
+      if (p < nb) col[p] = x[p];
+  }
+}
+
+// C[i][j] -= sum_p P[p][i] P[p][j] for i<=j in the trailing block, 64x64 tiles
+__global__ void __launch_bounds__(256) syrk_kernel(TreeView t, const int* __restrict__ list, int k0) {
+  __shared__ double Pi[kNB][kTile + 1];
+  __shared__ double Pj[kNB][kTile + 1];
+  const int c = list[blockIdx.y];
+  const int f = t.nf[c], n = f + t.ns[c] + 1;
+  if (k0 >= f) return;
+  const int nb = min(kNB, f - k0);
+  const int base = k0 + nb;
+  const int m = n - base;                       // trailing size
+  const int T = (m + kTile - 1) / kTile;
+  // linear tile id -> (ti <= tj)
+  int tid_lin = blockIdx.x;
+  if (tid_lin >= T * (T + 1) / 2) return;
+  int tj = 0;
+  while ((tj + 1) * (tj + 2) / 2 <= tid_lin) tj++;
+  const int ti = tid_lin - tj * (tj + 1) / 2;
+  double* M = t.arena + t.off[c];
+  const int i0 = base + ti * kTile, j0 = base + tj * kTile;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < kNB * kTile; e += 256) {
+    const int p = e % kNB, cc = e / kNB;
+    const int gi = i0 + cc, gj = j0 + cc;
+    Pi[p][cc] = (p < nb && gi < n) ? M[(k0 + p) + (size_t)gi * n] : 0.0;
+    Pj[p][cc] = (p < nb && gj < n) ? M[(k0 + p) + (size_t)gj * n] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int p = 0; p < kNB; p++) {
+    double ai[4], bj[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) ai[a] = Pi[p][tx + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; b++) bj[b] = Pj[p][ty + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] += ai[a] * bj[b];
+  }
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int gi = i0 + tx + 16 * a, gj = j0 + ty + 16 * b;
+      if (gi < n && gj < n && gi <= gj) M[gi + (size_t)gj * n] -= acc[a][b];
+    }
+}
+
+__global__ void __launch_bounds__(256) extend_add_kernel(TreeView t, const int* __restrict__ list) {
+  const int c = list[blockIdx.y];
+  const int p = t.parent[c];
+  if (p < 0) return;
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1, w = s + 1;
+  const int64_t total = (int64_t)w * w;
+  const double* M = t.arena + t.off[c];
+  double* P = t.arena + t.off[p];
+  const int pn = t.nf[p] + t.ns[p] + 1;
+  const int* map = t.ea_map + t.ea_ptr[c];
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int i = (int)(e % w), j = (int)(e / w);
+    if (i <= j) {
+      const int pi = map[i], pj = map[j];
+      const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+      atomicAdd(P + lo + (size_t)hi * pn, M[(f + i) + (size_t)(f + j) * n]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// back-substitution (gtsam/linear/linearAlgorithms-inst.h:50-117)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double* delta, Scalars* sc) {
+  __shared__ double xs[kWarpsPerBlock][kSmallMaxN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (idx >= count) return;
+  const int c = list[idx];
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  const double* M = t.arena + t.off[c];
+  const int* di = t.didx + t.didx_ptr[c];
+  double* x = xs[warp];
+  for (int i = lane; i < f; i += 32) {
+    double r = M[i + (size_t)(n - 1) * n];
+    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * n] * delta[di[f + cc]];
+    x[i] = r;
+  }
+  __syncwarp();
+  for (int i = f - 1; i >= 0; i--) {
+    if (lane == 0) x[i] = x[i] / M[i + (size_t)i * n];
+    __syncwarp();
+    const double xi = x[i];
+    for (int k = lane; k < i; k += 32) x[k] -= M[k + (size_t)i * n] * xi;
+    __syncwarp();
+  }
+  bool nan = false;
+  for (int i = lane; i < f; i += 32) {
+    delta[di[i]] = x[i];
+    if (isnan(x[i])) nan = true;
+  }
+  if (nan) atomicMin(&sc->nan_clique, c);
+}
+
+__global__ void __launch_bounds__(256)
+backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc) {
+  extern __shared__ double sh[];  // x[f] then xs[s]
+  const int c = list[blockIdx.x];
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  const double* M = t.arena + t.off[c];
+  const int* di = t.didx + t.didx_ptr[c];
+  double* x = sh;
+  double* xsep = sh + f;
+  const int tid = threadIdx.x;
+  for (int cc = tid; cc < s; cc += 256) xsep[cc] = delta[di[f + cc]];
+  __syncthreads();
+  for (int i = tid; i < f; i += 256) {
+    double r = M[i + (size_t)(n - 1) * n];
+    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * n] * xsep[cc];
+    x[i] = r;
+  }
+  __syncthreads();
+  for (int i = f - 1; i >= 0; i--) {
+    if (tid == 0) x[i] = x[i] / M[i + (size_t)i * n];
+    __syncthreads();
+    const double xi = x[i];
+    for (int k = tid; k < i; k += 256) x[k] -= M[k + (size_t)i * n] * xi;
+    __syncthreads();
+  }
+  bool nan = false;
+  for (int i = tid; i < f; i += 256) {
+    delta[di[i]] = x[i];
+    if (isnan(x[i])) nan = true;
+  }
+  if (nan) atomicMin(&sc->nan_clique, c);
+}
+
+// ---------------------------------------------------------------------------
+// retract: Values::retract (gtsam/nonlinear/Values.cpp:52-63)
+// ---------------------------------------------------------------------------
+__global__ void retract_kernel(const double* __restrict__ values, const double* __restrict__ delta,
+                               const int* __restrict__ val_off, const int* __restrict__ var_dof,
+                               const int* __restrict__ var_type, int nvars, double* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvars) return;
+  const double* x = values + val_off[v];
+  const double* d = delta + var_dof[v];
+  double* y = out + val_off[v];
+  const int ty = var_type[v];
+  if (ty == B200_VAR_POINT3) {
+    y[0] = x[0] + d[0]; y[1] = x[1] + d[1]; y[2] = x[2] + d[2];
+  } else {
+    double xi[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) xi[i] = d[i];
+    store_pose(pose_retract(load_pose(x), xi), y);
+    if (ty == B200_VAR_CAM_BUNDLER) {
+      // PinholeCamera::retract (gtsam/geometry/PinholeCamera.h:199-205), Cal3Bundler::retract
+      y[12] = x[12] + d[6]; y[13] = x[13] + d[7]; y[14] = x[14] + d[8];
+      y[15] = x[15]; y[16] = x[16];
+    }
+  }
+}
+
+}  // namespace b200

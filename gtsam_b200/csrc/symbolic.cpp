@@ -1,0 +1,248 @@
+// symbolic.cpp — see symbolic.h.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace b200 {
+
+bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int64_t m,
+                    const int64_t* fkey0, const int64_t* fkey1, Symbolic* S, const char** err) {
+  S->nvars = n;
+  S->var_dim.assign(var_dim, var_dim + n);
+  S->var_dof.assign(n + 1, 0);
+  for (int64_t v = 0; v < n; v++) S->var_dof[v + 1] = S->var_dof[v] + var_dim[v];
+  std::vector<int64_t> pos(n, -1);
+  for (int64_t j = 0; j < n; j++) {
+    const int64_t v = ordering[j];
+    if (v < 0 || v >= n || pos[v] != -1) { *err = "ordering is not a permutation of the variable ids"; return false; }
+    pos[v] = j;
+  }
+  // ---- variable index (CSR, factor positions ascending per variable) ----------
+  std::vector<int64_t> vi_ptr(n + 1, 0);
+  for (int64_t i = 0; i < m; i++) {
+    if (fkey0[i] < 0 || fkey0[i] >= n || fkey1[i] >= n) { *err = "factor key out of range"; return false; }
+    vi_ptr[fkey0[i] + 1]++;
+    if (fkey1[i] >= 0) vi_ptr[fkey1[i] + 1]++;
+  }
+  for (int64_t v = 0; v < n; v++) vi_ptr[v + 1] += vi_ptr[v];
+  std::vector<int64_t> vi(vi_ptr[n]);
+  {
+    std::vector<int64_t> cur(vi_ptr.begin(), vi_ptr.end() - 1);
+    for (int64_t i = 0; i < m; i++) {
+      vi[cur[fkey0[i]]++] = i;
+      if (fkey1[i] >= 0) vi[cur[fkey1[i]]++] = i;
+    }
+  }
+  // ---- elimination tree with path compression ----------------------------------
+  std::vector<int64_t> eparent(n, -1), anc(n, -1), prevCol(m, -1), node_of_factor(m, -1);
+  std::vector<int64_t> first_child(n, -1), last_child(n, -1), next_sib(n, -1);
+  for (int64_t j = 0; j < n; j++) {
+    const int64_t v = ordering[j];
+    for (int64_t q = vi_ptr[v]; q < vi_ptr[v + 1]; q++) {
+      const int64_t i = vi[q];
+      if (prevCol[i] != -1) {
+        int64_t r = prevCol[i];
+        while (anc[r] != -1 && anc[r] != j) {
+          const int64_t nx = anc[r];
+          anc[r] = j;
+          r = nx;
+        }
+        if (anc[r] == -1 && r != j) {
+          anc[r] = j;
+          eparent[r] = j;
+          if (last_child[j] == -1) first_child[j] = r; else next_sib[last_child[j]] = r;
+          last_child[j] = r;
+        }
+      } else {
+        node_of_factor[i] = j;
+      }
+      prevCol[i] = j;
+    }
+  }
+  // node -> own factors (CSR, ascending factor position)
+  std::vector<int64_t> nf_ptr(n + 1, 0);
+  for (int64_t i = 0; i < m; i++) nf_ptr[node_of_factor[i] + 1]++;
+  for (int64_t j = 0; j < n; j++) nf_ptr[j + 1] += nf_ptr[j];
+  std::vector<int64_t> nfac(m);
+  {
+    std::vector<int64_t> cur(nf_ptr.begin(), nf_ptr.end() - 1);
+    for (int64_t i = 0; i < m; i++) nfac[cur[node_of_factor[i]]++] = i;
+  }
+  // ---- symbolic elimination: separator (as positions) of every etree node -------
+  std::vector<int64_t> sep_off(n + 1, 0), sep_pool;
+  sep_pool.reserve((size_t)(2 * m + n));
+  std::vector<int64_t> mark(n, -1);
+  std::vector<std::vector<int64_t>> cfront(n);  // frontal positions of the cluster headed by j
+  std::vector<char> alive(n, 1);
+  std::vector<int64_t> absorbed_into(n, -1);
+  for (int64_t j = 0; j < n; j++) {
+    const size_t s0 = sep_pool.size();
+    for (int64_t q = nf_ptr[j]; q < nf_ptr[j + 1]; q++) {
+      const int64_t i = nfac[q];
+      const int64_t ks[2] = {fkey0[i], fkey1[i]};
+      for (int a = 0; a < 2; a++) {
+        if (ks[a] < 0) continue;
+        const int64_t pj = pos[ks[a]];
+        if (pj != j && mark[pj] != j) { mark[pj] = j; sep_pool.push_back(pj); }
+      }
+    }
+    for (int64_t c = first_child[j]; c != -1; c = next_sib[c])
+      for (int64_t q = sep_off[c]; q < sep_off[c + 1]; q++) {
+        const int64_t pj = sep_pool[q];
+        if (pj != j && mark[pj] != j) { mark[pj] = j; sep_pool.push_back(pj); }
+      }
+    sep_off[j + 1] = (int64_t)sep_pool.size();
+    const int64_t myNrParents = (int64_t)(sep_pool.size() - s0);
+    // merge rule of JunctionTree-inst.h:98-118 + Cluster::mergeChildren
+    int64_t myNrFrontals = 1;
+    std::vector<int64_t>& fr = cfront[j];
+    fr.push_back(j);
+    bool merged_any = false;
+    for (int64_t c = first_child[j]; c != -1; c = next_sib[c]) {
+      const int64_t childParents = sep_off[c + 1] - sep_off[c];
+      if (myNrParents + myNrFrontals == childParents) {
+        myNrFrontals += (int64_t)cfront[c].size();
+        fr.insert(fr.end(), cfront[c].rbegin(), cfront[c].rend());
+        std::vector<int64_t>().swap(cfront[c]);
+        alive[c] = 0;
+        absorbed_into[c] = j;
+        merged_any = true;
+      }
+    }
+    if (merged_any) std::reverse(fr.begin(), fr.end());
+  }
+  // ---- clique tables --------------------------------------------------------------
+  std::vector<int64_t> cid(n, -1);
+  int64_t nc = 0;
+  for (int64_t j = 0; j < n; j++) if (alive[j]) cid[j] = nc++;
+  // node -> clique: follow absorption upwards (heads have larger positions)
+  std::vector<int64_t> clique_of_node(n, -1);
+  for (int64_t j = n - 1; j >= 0; j--) clique_of_node[j] = alive[j] ? cid[j] : clique_of_node[absorbed_into[j]];
+  S->ncliques = nc;
+  S->front_ptr.assign(nc + 1, 0); S->sep_ptr.assign(nc + 1, 0);
+  S->parent.assign(nc, -1); S->nf.assign(nc, 0); S->ns.assign(nc, 0);
+  S->off.assign(nc + 1, 0); S->level.assign(nc, 0);
+  S->var_clique.assign(n, -1); S->var_slot.assign(n, -1);
+  S->front_vars.clear(); S->sep_vars.clear();
+  S->front_vars.reserve(n);
+  for (int64_t j = 0; j < n; j++) {
+    if (!alive[j]) continue;
+    const int64_t c = cid[j];
+    int slot = 0;
+    for (int64_t pj : cfront[j]) {
+      const int64_t v = ordering[pj];
+      S->front_vars.push_back(v);
+      S->var_clique[v] = (int)c;
+      S->var_slot[v] = slot;
+      slot += var_dim[v];
+    }
+    S->nf[c] = slot;
+    S->front_ptr[c + 1] = (int64_t)S->front_vars.size();
+    const size_t s0 = S->sep_vars.size();
+    int sdim = 0;
+    for (int64_t q = sep_off[j]; q < sep_off[j + 1]; q++) {
+      const int64_t v = ordering[sep_pool[q]];
+      S->sep_vars.push_back(v);
+      sdim += var_dim[v];
+    }
+    // separator keys sorted by id (== by Key): gtsam/linear/Scatter.cpp:69-72
+    std::sort(S->sep_vars.begin() + (int64_t)s0, S->sep_vars.end());
+    S->ns[c] = sdim;
+    S->sep_ptr[c + 1] = (int64_t)S->sep_vars.size();
+    if (eparent[j] != -1) S->parent[c] = clique_of_node[eparent[j]];
+    const int64_t nn = (int64_t)S->nf[c] + sdim + 1;
+    S->off[c + 1] = S->off[c] + nn * nn;
+    S->max_nf = std::max<int64_t>(S->max_nf, S->nf[c]);
+    S->max_ns = std::max<int64_t>(S->max_ns, sdim);
+    const double f = S->nf[c], s = sdim;
+    S->flops += f * f * f / 3.0 + f * f * s + f * s * s;
+  }
+  S->arena_doubles = S->off[nc];
+  // levels (children have smaller ids than parents)
+  int maxlvl = 0;
+  for (int64_t c = 0; c < nc; c++) {
+    const int64_t p = S->parent[c];
+    if (p >= 0) S->level[p] = std::max(S->level[p], S->level[c] + 1);
+    maxlvl = std::max(maxlvl, S->level[c]);
+  }
+  S->nlevels = nc ? maxlvl + 1 : 0;
+  S->lvl_ptr.assign(S->nlevels + 1, 0);
+  for (int64_t c = 0; c < nc; c++) S->lvl_ptr[S->level[c] + 1]++;
+  for (int64_t l = 0; l < S->nlevels; l++) S->lvl_ptr[l + 1] += S->lvl_ptr[l];
+  S->lvl_cliques.assign(nc, 0);
+  {
+    std::vector<int64_t> cur(S->lvl_ptr.begin(), S->lvl_ptr.end() - 1);
+    for (int64_t c = 0; c < nc; c++) S->lvl_cliques[cur[S->level[c]]++] = (int)c;
+  }
+  // ---- scatter maps ------------------------------------------------------------------
+  // factors by owning clique
+  S->fac_clique.assign(m, -1); S->fac_slot0.assign(m, -1); S->fac_slot1.assign(m, -1);
+  std::vector<int64_t> cf_ptr(nc + 1, 0);
+  for (int64_t i = 0; i < m; i++) {
+    S->fac_clique[i] = (int)clique_of_node[node_of_factor[i]];
+    cf_ptr[S->fac_clique[i] + 1]++;
+  }
+  for (int64_t c = 0; c < nc; c++) cf_ptr[c + 1] += cf_ptr[c];
+  std::vector<int64_t> cf(m);
+  {
+    std::vector<int64_t> cur(cf_ptr.begin(), cf_ptr.end() - 1);
+    for (int64_t i = 0; i < m; i++) cf[cur[S->fac_clique[i]]++] = i;
+  }
+  // children by clique
+  std::vector<int64_t> ch_ptr(nc + 1, 0);
+  for (int64_t c = 0; c < nc; c++) if (S->parent[c] >= 0) ch_ptr[S->parent[c] + 1]++;
+  for (int64_t c = 0; c < nc; c++) ch_ptr[c + 1] += ch_ptr[c];
+  std::vector<int64_t> ch(ch_ptr[nc]);
+  {
+    std::vector<int64_t> cur(ch_ptr.begin(), ch_ptr.end() - 1);
+    for (int64_t c = 0; c < nc; c++) if (S->parent[c] >= 0) ch[cur[S->parent[c]]++] = c;
+  }
+  S->ea_ptr.assign(nc + 1, 0); S->didx_ptr.assign(nc + 1, 0);
+  for (int64_t c = 0; c < nc; c++) {
+    S->ea_ptr[c + 1] = S->ea_ptr[c] + S->ns[c] + 1;
+    S->didx_ptr[c + 1] = S->didx_ptr[c] + S->nf[c] + S->ns[c];
+  }
+  S->ea_map.assign(S->ea_ptr[nc], -1);
+  S->didx.assign(S->didx_ptr[nc], -1);
+  std::vector<int> slot(n, -1);
+  for (int64_t c = 0; c < nc; c++) {
+    int k = 0;
+    int64_t dq = S->didx_ptr[c];
+    for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) {
+      const int64_t v = S->front_vars[q];
+      slot[v] = k;
+      for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
+      k += var_dim[v];
+    }
+    for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) {
+      const int64_t v = S->sep_vars[q];
+      slot[v] = k;
+      for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
+      k += var_dim[v];
+    }
+    const int nn = k + 1;
+    for (int64_t q = cf_ptr[c]; q < cf_ptr[c + 1]; q++) {
+      const int64_t i = cf[q];
+      S->fac_slot0[i] = slot[fkey0[i]];
+      if (fkey1[i] >= 0) S->fac_slot1[i] = slot[fkey1[i]];
+      if (S->fac_slot0[i] < 0 || (fkey1[i] >= 0 && S->fac_slot1[i] < 0)) { *err = "internal: factor variable not in owning clique"; return false; }
+    }
+    for (int64_t q = ch_ptr[c]; q < ch_ptr[c + 1]; q++) {
+      const int64_t cc = ch[q];
+      int64_t e = S->ea_ptr[cc];
+      for (int64_t qq = S->sep_ptr[cc]; qq < S->sep_ptr[cc + 1]; qq++) {
+        const int64_t v = S->sep_vars[qq];
+        if (slot[v] < 0) { *err = "internal: child separator variable not in parent clique"; return false; }
+        for (int t = 0; t < var_dim[v]; t++) S->ea_map[e++] = slot[v] + t;
+      }
+      S->ea_map[e] = nn - 1;
+    }
+    // reset scratch
+    for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) slot[S->front_vars[q]] = -1;
+    for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) slot[S->sep_vars[q]] = -1;
+  }
+  return true;
+}
+
+}  // namespace b200

@@ -1,0 +1,47 @@
+// symbolic.h — host-side symbolic phase: variable index -> elimination tree ->
+// junction tree (supernodes) -> level schedule + scatter maps.
+//
+// Produces exactly the cliques the reference builds on every solve
+// (gtsam/inference/VariableIndex-inl.h:27-50,
+//  gtsam/inference/EliminationTree-inst.h:77-155,
+//  gtsam/inference/JunctionTree-inst.h:63-151,
+//  gtsam/inference/ClusterTree-inst.h:46-95) — including its child-merge rule,
+// under which at most the first qualifying child is absorbed — but computes
+// them once per problem, with path-compressed root finding, and emits flat
+// integer tables the device kernels walk level by level.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace b200 {
+
+struct Symbolic {
+  int64_t nvars = 0, ncliques = 0, nlevels = 0;
+  std::vector<int> var_dim;
+  std::vector<int64_t> var_dof;       // nvars+1 prefix of dims (delta layout)
+  // cliques, numbered by ascending elimination position of their head variable
+  std::vector<int64_t> front_ptr, front_vars, sep_ptr, sep_vars;
+  std::vector<int64_t> parent;        // -1 for roots
+  std::vector<int> nf, ns;            // scalar frontal / separator dims
+  std::vector<int64_t> off;           // offset (doubles) of the (nf+ns+1)^2 col-major front
+  std::vector<int> level;
+  std::vector<int64_t> lvl_ptr;       // nlevels+1
+  std::vector<int> lvl_cliques;       // cliques grouped by level (ascending id inside a level)
+  std::vector<int64_t> ea_ptr;        // ncliques+1; per clique ns+1 entries
+  std::vector<int> ea_map;            // scalar row/col in the parent front of each trailing index
+  std::vector<int64_t> didx_ptr;      // ncliques+1; per clique nf+ns entries
+  std::vector<int> didx;              // index into delta of each front row/col
+  std::vector<int> var_clique, var_slot;  // owning clique + scalar slot of each variable
+  std::vector<int> fac_clique;        // per graph position: owning clique
+  std::vector<int> fac_slot0, fac_slot1;  // scalar slots of key 0 / key 1 in that clique (-1 if unary)
+  int64_t arena_doubles = 0;
+  int64_t max_nf = 0, max_ns = 0;
+  double flops = 0;
+};
+
+// fkey0/fkey1: variable ids of every factor by graph position (fkey1 = -1 for
+// unary factors).  Returns false (and fills err) on invalid input.
+bool build_symbolic(int64_t nvars, const int* var_dim, const int64_t* ordering, int64_t nfactors,
+                    const int64_t* fkey0, const int64_t* fkey1, Symbolic* out, const char** err);
+
+}  // namespace b200

@@ -36,7 +36,7 @@ NOISE_UNIT, NOISE_ISOTROPIC, NOISE_DIAGONAL, NOISE_GAUSSIAN = range(4)
 
 
 def noise_payload(kind: int, d: int) -> int:
-    return (0, 1, d, d * d)[kind]
+    return (0, 1, d, d * d)[kind] if 0 <= kind < 4 else 0   # unknown kinds are rejected by the library
 
 
 def factor_ncols(ftype: int) -> int:

@@ -242,6 +242,20 @@ int b200_symbolic_info_get(const b200_problem* prob, b200_symbolic_info* info);
 int b200_get_cliques(const b200_problem* prob, int64_t* frontal_ptr, int64_t* frontal_vars,
                      int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
 
+/* Host-only symbolic phase (no GPU needed): the same junction tree
+ * b200_problem_create builds, for inspection and CPU-side tests of a11. */
+typedef struct b200_symbolic b200_symbolic;
+int b200_symbolic_create(const b200_problem_desc* desc, b200_symbolic** out);
+int b200_symbolic_destroy(b200_symbolic* s);
+int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info);
+int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* frontal_ptr, int64_t* frontal_vars,
+                              int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
+int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level); /* ncliques */
+
+/* Parity of a14: the conditional [R S d] of clique c after a solve
+ * (gtsam/linear/HessianFactor.cpp:459-487), nf x (nf+ns+1) column-major. */
+int b200_get_conditional(b200_problem* prob, int64_t clique, double* out);
+
 /* Multi-GPU: the dense frontal storage of the cliques that are
  * shared between ranks (the top of the tree) as one contiguous device buffer,
  * so the caller's communicator (NCCL via torch.distributed) can sum it between

@@ -29,6 +29,8 @@
 #include <gtsam/slam/BetweenFactor.h>
 #include <gtsam/slam/GeneralSFMFactor.h>
 #include <gtsam/slam/ProjectionFactor.h>
+#include <gtsam/sfm/SfmData.h>
+#include <gtsam/inference/Symbol.h>
 
 #include <chrono>
 #include <cstdint>
@@ -427,6 +429,88 @@ static int cmd_order(const std::string& in, const std::string& kind, const std::
   return 0;
 }
 
+template <class T>
+static void wr(std::ofstream& f, const T* p, size_t n) { f.write((const char*)p, (std::streamsize)(n * sizeof(T))); }
+
+static void save(const Prob& p, const std::string& path) {
+  std::ofstream f(path, std::ios::binary);
+  f.write("B200PRB1", 8);
+  wr(f, &p.nvars, 1);
+  wr(f, p.var_type.data(), p.var_type.size());
+  int64_t nval = (int64_t)p.values.size();
+  wr(f, &nval, 1);
+  wr(f, p.values.data(), p.values.size());
+  wr(f, p.ordering.data(), p.ordering.size());
+  int64_t ncal = (int64_t)p.cal.size() / 5;
+  wr(f, &ncal, 1);
+  wr(f, p.cal.data(), p.cal.size());
+  int64_t ng = (int64_t)p.groups.size();
+  wr(f, &ng, 1);
+  for (auto& g : p.groups) {
+    wr(f, &g.type, 1); wr(f, &g.noise_kind, 1); wr(f, &g.per_factor, 1); wr(f, &g.has_cal, 1);
+    wr(f, &g.count, 1); wr(f, &g.gi0, 1);
+    wr(f, g.keys.data(), g.keys.size());
+    wr(f, g.meas.data(), g.meas.size());
+    int64_t nn = (int64_t)g.noise.size();
+    wr(f, &nn, 1);
+    wr(f, g.noise.data(), g.noise.size());
+    if (g.has_cal) wr(f, g.cal_index.data(), g.cal_index.size());
+  }
+}
+
+/* Convert a BAL file through the reference's own loader (gtsam/sfm/SfmData.cpp:189-246)
+ * into a problem file.  mode 0: tests/testGeneralSFMFactorB.cpp:44-63 (unit noise,
+ * default COLAMD ordering); mode 1: examples/SFMExample_bal.cpp:36-78 (isotropic
+ * noise + priors on camera 0 and point 0, COLAMD). */
+static int cmd_balfile(const std::string& path, const std::string& outp, int mode) {
+  SfmData db = SfmData::FromBalFile(path);
+  const int64_t nc = (int64_t)db.numberCameras(), np = (int64_t)db.numberTracks();
+  Prob p;
+  p.nvars = nc + np;
+  p.var_type.assign(nc, 2);
+  p.var_type.insert(p.var_type.end(), np, 1);
+  NonlinearFactorGraph graph;
+  auto camkey = [&](size_t i) { return mode == 0 ? Key(i) : Key(Symbol('c', i)); };
+  auto ptkey = [&](size_t j) { return Key(Symbol('p', j)); };
+  for (auto& cam : db.cameras) {
+    double x[17];
+    putpose(cam.pose(), x);
+    x[12] = cam.calibration().fx(); x[13] = cam.calibration().k1(); x[14] = cam.calibration().k2();
+    x[15] = cam.calibration().px(); x[16] = cam.calibration().py();
+    p.values.insert(p.values.end(), x, x + 17);
+  }
+  for (auto& t : db.tracks) { p.values.push_back(t.p.x()); p.values.push_back(t.p.y()); p.values.push_back(t.p.z()); }
+  Group g;
+  g.type = 4; g.noise_kind = mode == 0 ? 0 : 1; g.per_factor = 0; g.has_cal = 0; g.gi0 = 0;
+  if (mode == 1) g.noise.push_back(1.0);
+  auto noise = mode == 0 ? SharedNoiseModel(noiseModel::Unit::Create(2)) : SharedNoiseModel(noiseModel::Isotropic::Sigma(2, 1.0));
+  for (size_t j = 0; j < db.numberTracks(); j++)
+    for (const SfmMeasurement& m : db.tracks[j].measurements) {
+      graph.emplace_shared<GeneralSFMFactor<BCam, Point3>>(m.second, noise, camkey(m.first), ptkey(j));
+      g.keys.push_back((int64_t)m.first); g.keys.push_back(nc + (int64_t)j);
+      g.meas.push_back(m.second.x()); g.meas.push_back(m.second.y());
+    }
+  g.count = (int64_t)g.meas.size() / 2;
+  p.groups.push_back(g);
+  if (mode == 1) {
+    graph.addPrior(camkey(0), db.cameras[0], noiseModel::Isotropic::Sigma(9, 0.1));
+    graph.addPrior(ptkey(0), db.tracks[0].p, noiseModel::Isotropic::Sigma(3, 0.1));
+    Group gc; gc.type = 5; gc.noise_kind = 1; gc.per_factor = 0; gc.has_cal = 0; gc.count = 1; gc.gi0 = g.count;
+    gc.keys = {0}; gc.meas.assign(p.values.begin(), p.values.begin() + 17); gc.noise = {0.1};
+    Group gp; gp.type = 2; gp.noise_kind = 1; gp.per_factor = 0; gp.has_cal = 0; gp.count = 1; gp.gi0 = g.count + 1;
+    gp.keys = {nc}; gp.meas = {db.tracks[0].p.x(), db.tracks[0].p.y(), db.tracks[0].p.z()}; gp.noise = {0.1};
+    p.groups.push_back(gc); p.groups.push_back(gp);
+  }
+  Ordering ord = Ordering::Colamd(graph);
+  for (Key k : ord) {
+    Symbol s(k);
+    int64_t id = (mode == 0 && k < (Key)nc) ? (int64_t)k : (s.chr() == 'c' ? (int64_t)s.index() : nc + (int64_t)s.index());
+    p.ordering.push_back(id);
+  }
+  save(p, outp);
+  return 0;
+}
+
 /* known-answer vectors for the geometry primitives, incl. near-0 / near-pi */
 static int cmd_kat(const std::string& outp) {
   std::mt19937 rng(123);
@@ -480,6 +564,7 @@ int main(int argc, char** argv) {
   if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));
   if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);
   if (cmd == "kat" && argc >= 3) return cmd_kat(argv[2]);
+  if (cmd == "balfile" && argc >= 4) return cmd_balfile(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 0);
   fprintf(stderr, "bad arguments\n");
   return 2;
 }

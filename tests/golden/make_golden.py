@@ -1,0 +1,64 @@
+"""Regenerates tests/golden/*.bin by running the UNMODIFIED reference
+(oracle/_ref/ref_harness, built by oracle/Makefile from /root/reference) on
+small seeded problems.  Run from the repo root in the build container:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the C oracle (tests/test_oracle_golden.py) and the CUDA path
+(tests/test_gpu_parity.py).  Each case stores the problem (*.prob.bin, the
+gtsam_b200.problem.Problem.save format) and the reference's outputs
+(*.dump0.bin: lambda=0; *.dump1.bin: lambda=1e-2 with diagonal damping;
+*.lm.bin: LevenbergMarquardtOptimizer trace; *.gn.bin: GaussNewton trace).
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from gtsam_b200 import datasets  # noqa: E402
+from oracle import refio  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+H = refio.HARNESS
+REF_DATA = "/root/reference/examples/Data"
+
+
+def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False):
+    ppath = os.path.join(HERE, f"{name}.prob.bin")
+    prob.save(ppath)
+    subprocess.check_call([H, "dump", ppath, os.path.join(HERE, f"{name}.dump0.bin"), "0", "0"])
+    subprocess.check_call([H, "dump", ppath, os.path.join(HERE, f"{name}.dump1.bin"), "1e-2", "1"])
+    subprocess.check_call([H, "lm", ppath, os.path.join(HERE, f"{name}.lm.bin"), str(lm_iters), str(int(ceres))])
+    if gn_iters:
+        subprocess.check_call([H, "gn", ppath, os.path.join(HERE, f"{name}.gn.bin"), str(gn_iters)])
+    print("wrote", name, prob.nvars, "vars", prob.nfactors, "factors")
+
+
+def with_ordering(prob, kind):
+    o = refio.run("order", prob, kind)["ordering"]
+    prob.ordering = o.copy()
+    return prob
+
+
+def main():
+    assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    subprocess.check_call([H, "kat", os.path.join(HERE, "geometry_kat.bin")])
+    emit("bal_tiny_s2", datasets.make("bal_tiny"))
+    emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True)
+    emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"))
+    emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3)
+    emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
+    emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
+    # the reference's own end-to-end golden: tests/testGeneralSFMFactorB.cpp:44-63 (0.0199833 +- 1e-5)
+    from gtsam_b200.problem import Problem
+    with tempfile.TemporaryDirectory() as td:
+        for mode, nm in ((0, "dubrovnik_3_7_unit"), (1, "dubrovnik_3_7_priors")):
+            tmp = os.path.join(td, "p.bin")
+            subprocess.check_call([H, "balfile", os.path.join(REF_DATA, "dubrovnik-3-7-pre.txt"), tmp, str(mode)])
+            emit(nm, Problem.load(tmp), lm_iters=100)
+
+
+if __name__ == "__main__":
+    main()

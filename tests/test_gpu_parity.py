@@ -1,0 +1,181 @@
+"""GPU: the CUDA path, called through the C-ABI, against (1) the golden vectors
+of the unmodified reference, (2) the C oracle on seeded mid-size problems and
+(3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (FP64 path): whitened [A|b] max-abs-diff <= 1e-12
+relative; graph.error rel <= 1e-12; delta rel-2-norm <= 1e-8 (conditioning
+limited, FP64 atomics make Hessian sums order dependent); LM traces: same
+accept/reject + lambda sequence, errors rel <= 1e-7."""
+import numpy as np
+import pytest
+
+import util
+from gtsam_b200 import capi, datasets, optimizer, problem as P
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", util.CASES)
+@pytest.mark.parametrize("kind,lam,diag", [("dump0", 0.0, 0), ("dump1", 1e-2, 1)])
+def test_cuda_matches_reference_dump(gpu_ctx, case, kind, lam, diag):
+    prob = util.load_case(case)
+    dev = capi.DeviceProblem(gpu_ctx, prob)
+    util.check_against_dump(dev, prob, util.golden(case, kind), lam, diag)
+    dev.close()
+
+
+@pytest.mark.parametrize("case", util.CASES)
+def test_cuda_lm_trace_matches_reference(gpu_ctx, case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "lm")
+    prm = optimizer.LevenbergMarquardtParams.CeresDefaults() if case in util.CERES_CASES else optimizer.LevenbergMarquardtParams()
+    prm.maxIterations = 100 if case.startswith("dub") else 30
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, prob, prm)
+    errs, lams, inner = [], [], []
+    prm.iterationHook = lambda it, old, new: (errs.append(new), lams.append(lm.lambda_()), inner.append(lm.getInnerIterations()))
+    e0 = lm.error()
+    lm.optimize()
+    errs, lams, inner = [e0] + errs, [prm.lambdaInitial] + lams, [0] + inner
+    assert len(errs) == len(ref["lm_errors"])
+    assert np.allclose(errs, ref["lm_errors"], rtol=1e-5 if case.startswith("dub") else 1e-7, atol=1e-10)
+    assert np.allclose(lams, ref["lm_lambdas"], rtol=1e-12)
+    assert inner == list(ref["lm_inner"])
+    assert util.relmax(lm.values(), ref["final_values"]) <= (1e-3 if case.startswith("dub") else 1e-6)
+
+
+def test_cuda_reference_end_to_end_golden(gpu_ctx):
+    """tests/testGeneralSFMFactorB.cpp:44-63 through the drop-in: 0.0199833 +- 1e-5."""
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, util.load_case("dubrovnik_3_7_unit"))
+    lm.optimize()
+    assert abs(lm.error() - 0.0199833) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["sphere_tiny", "sphere_small_colamd"])
+def test_cuda_gn_trace(gpu_ctx, case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "gn")
+    gn = optimizer.GaussNewtonOptimizer(gpu_ctx, prob)
+    errs = [gn.error()]
+    for _ in range(len(ref["gn_errors"]) - 1):
+        gn.iterate()
+        errs.append(gn.error())
+    assert np.allclose(errs, ref["gn_errors"], rtol=1e-8)
+
+
+MID = [("bal_tiny", dict(ncams=24, npoints=3000, visibility="scattered")),
+       ("bal_tiny", dict(ncams=40, npoints=4000, visibility="banded", camera_model="bundler")),
+       ("sphere_tiny", dict(layers=14, per_ring=24)),                       # large fronts (natural ordering)
+       ("sphere_tiny", dict(layers=14, per_ring=24, ordering="reverse"))]
+
+
+@pytest.mark.parametrize("name,kw", MID)
+@pytest.mark.parametrize("lam,diag", [(0.0, False), (1e-3, False), (1e-2, True)])
+def test_cuda_matches_oracle_mid_size(gpu_ctx, name, kw, lam, diag):
+    prob = datasets.make(name, **kw)
+    dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+    eo = orc.error()
+    assert abs(dev.error() - eo) <= 1e-12 * eo
+    dev.linearize(); orc.linearize()
+    for gi in range(len(prob.groups)):
+        assert util.relmax(dev.get_jacobians(gi), orc.get_jacobians(gi)) <= 1e-12
+    assert util.relmax(dev.hessian_diagonal(), orc.hessian_diagonal()) <= 1e-12
+    st, e0, e1, _ = dev.solve(lam, diag)
+    so, f0, f1, _ = orc.solve(lam, diag)
+    assert st == so == 0
+    assert util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+    assert abs(e0 - f0) <= 1e-12 * f0 and abs(e1 - f1) <= 1e-9 * f0
+    ne, no = dev.try_step(), orc.try_step()
+    assert abs(ne - no) <= 1e-8 * max(1.0, no)
+    dev.accept_step(); orc.accept_step()
+    assert util.relmax(dev.get_values(), orc.get_values()) <= 1e-9
+    # conditionals of a few cliques, incl. the root
+    info = dev.symbolic_info()
+    for c in sorted({0, info.ncliques // 2, info.ncliques - 1}):
+        a, b = dev.conditional(c), orc.conditional(c)
+        assert np.abs(a - b).max() <= 1e-7 * max(1.0, np.abs(b).max())
+    dev.close()
+
+
+def test_cuda_indeterminate_system_reported(gpu_ctx):
+    """Gauge-free BAL (no priors): the undamped system is singular -> B200_INDETERMINATE
+    with a nearby variable, like IndeterminantLinearSystemException; LM recovers by raising lambda."""
+    prob = datasets.make("bal_tiny")
+    prob.groups = prob.groups[:1]
+    prob = P.Problem(prob.var_type, prob.values, prob.ordering, prob.groups, prob.cal)
+    dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+    dev.linearize(); orc.linearize()
+    st, _, _, fv = dev.solve(0.0)
+    so, _, _, fo = orc.solve(0.0)
+    assert so == P.INDETERMINATE and st == P.INDETERMINATE and fv >= 0
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, prob, device_problem=dev)
+    e0 = lm.error()
+    lm.iterate()
+    assert lm.error() < e0
+
+
+def test_cuda_cheirality(gpu_ctx):
+    pose = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
+    K = np.array([[500.0, 500.0, 0.0, 320.0, 240.0]])
+    prob = P.Problem(np.array([P.VAR_POSE3, P.VAR_POINT3]), np.concatenate([pose, [0.1, 0.2, -3.0]]), np.array([1, 0]),
+                     [P.FactorGroup(P.FACTOR_PROJECTION_CAL3S2, np.array([[0, 1]]), np.array([[1.0, 2.0]]), P.NOISE_UNIT)], K)
+    dev = capi.DeviceProblem(gpu_ctx, prob)
+    dev.linearize()
+    J = dev.get_jacobians(0)[0]
+    assert np.all(J[:, :9] == 0) and np.allclose(J[:, 9], -1000.0)
+    assert abs(dev.error() - 1e6) < 1e-6
+
+
+def _normal_equation_residual(prob, dev, lam):
+    """|J^T (J d - b) + lam d| / |J^T b| from the device Jacobians, with scipy.sparse."""
+    import scipy.sparse as sp
+    dof = prob.dof_offsets()
+    n = int(dof[-1])
+    rows, cols, vals, bs = [], [], [], []
+    r0 = 0
+    for gi, g in enumerate(prob.groups):
+        J = dev.get_jacobians(gi)
+        d = P.FACTOR_DIM[g.type]
+        rr = r0 + (np.arange(g.count)[:, None] * d + np.arange(d)[None]).astype(np.int64)     # (count, d)
+        c0 = 0
+        for a, vt in enumerate(P.FACTOR_VAR_TYPES[g.type]):
+            nv = P.VAR_DIM[vt]
+            cc = dof[g.keys[:, a]][:, None] + np.arange(nv)[None]                                # (count, nv)
+            rows.append(np.repeat(rr[:, :, None], nv, 2).ravel())
+            cols.append(np.repeat(cc[:, None, :], d, 1).ravel())
+            vals.append(J[:, :, c0:c0 + nv].ravel())
+            c0 += nv
+        bs.append(J[:, :, -1].ravel())
+        r0 += g.count * d
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(r0, n))
+    b = np.concatenate(bs)
+    dl = dev.get_delta()
+    g0 = A.T @ b
+    return float(np.linalg.norm(A.T @ (A @ dl - b) + lam * dl) / np.linalg.norm(g0)), A, b, dl
+
+
+@pytest.mark.parametrize("workload,lam", [("bal_c3", 1e-5), ("sphere2500", 0.0)])
+def test_full_size_normal_equations(gpu_ctx, workload, lam):
+    """BASELINE.json configs[2] / configs[1] at full size: delta satisfies the damped normal
+    equations to 1e-9 and the reported linear errors equal 0.5|b|^2 and 0.5|A delta - b|^2."""
+    prob = datasets.make(workload)
+    dev = capi.DeviceProblem(gpu_ctx, prob)
+    dev.linearize()
+    st, e0, e1, _ = dev.solve(lam)
+    assert st == 0
+    res, A, b, dl = _normal_equation_residual(prob, dev, lam)
+    assert res <= 1e-9, res
+    assert abs(e0 - 0.5 * b @ b) <= 1e-11 * e0
+    r = A @ dl - b
+    assert abs(e1 - 0.5 * r @ r) <= 1e-9 * e0
+    ne = dev.try_step()
+    assert ne < dev.error()
+    dev.close()
+
+
+def test_full_size_lm_iteration_decreases_error(gpu_ctx):
+    prob = datasets.make("bal_c3")
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, prob)
+    e0 = lm.error()
+    lm.iterate()
+    assert lm.error() < 0.1 * e0 and lm.iterations() == 1

@@ -1,0 +1,144 @@
+"""CPU: host logic — the C-ABI library loads and exports every symbol the header
+declares, static tables, the no-GPU error path, the problem container, and the
+host symbolic phase (a11) against the oracle and the reference's junction trees."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+from gtsam_b200 import capi, datasets, problem as P
+from oracle import oracle_py as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _symbolic(prob):
+    L = capi.lib()
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    L.b200_symbolic_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(C.c_void_p)]
+    rc = L.b200_symbolic_create(C.byref(desc), C.byref(h))
+    assert rc == 0, L.b200_last_error_string()
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info.argtypes = [C.c_void_p, C.POINTER(P.CSymbolicInfo)]
+    L.b200_symbolic_get_info(h, C.byref(info))
+    ip = C.POINTER(C.c_int64)
+    fp = np.zeros(info.ncliques + 1, dtype=np.int64); sp = np.zeros(info.ncliques + 1, dtype=np.int64)
+    fv = np.zeros(max(1, info.frontal_list_len), dtype=np.int64); sv = np.zeros(max(1, info.separator_list_len), dtype=np.int64)
+    par = np.zeros(max(1, info.ncliques), dtype=np.int64)
+    L.b200_symbolic_get_cliques.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
+    L.b200_symbolic_get_cliques(h, fp.ctypes.data_as(ip), fv.ctypes.data_as(ip), sp.ctypes.data_as(ip),
+                                sv.ctypes.data_as(ip), par.ctypes.data_as(ip))
+    lvl = np.zeros(max(1, info.ncliques), dtype=np.int32)
+    L.b200_symbolic_get_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.b200_symbolic_get_levels(h, lvl.ctypes.data_as(C.POINTER(C.c_int32)))
+    L.b200_symbolic_destroy.argtypes = [C.c_void_p]
+    L.b200_symbolic_destroy(h)
+    return info, fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques], lvl[:info.ncliques]
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "gtsam_b200.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    L = capi.lib()
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(capi.EXPORTS) <= declared
+
+
+def test_static_tables(built):
+    L = capi.lib()
+    for t in range(3):
+        assert L.b200_var_storage(t) == P.VAR_STORAGE[t] and L.b200_var_dim(t) == P.VAR_DIM[t]
+    for t in range(6):
+        assert L.b200_factor_arity(t) == P.FACTOR_ARITY[t]
+        assert L.b200_factor_meas_size(t) == P.FACTOR_MEAS[t]
+        assert L.b200_factor_dim(t) == P.FACTOR_DIM[t]
+    assert L.b200_var_dim(7) == -1
+
+
+def test_no_gpu_fails_loudly(built):
+    """No CPU fallback: without a device ctx creation reports B200_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(capi.B200Error) as e:
+        capi.Context(0)
+    assert e.value.code == P.NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_problem_roundtrip(tmp_path):
+    for prob in (datasets.make("bal_tiny"), datasets.make("bal_tiny", camera_model="bundler"), datasets.make("sphere_tiny")):
+        path = str(tmp_path / "p.bin")
+        prob.save(path)
+        q = P.Problem.load(path)
+        assert np.array_equal(q.values, prob.values) and np.array_equal(q.ordering, prob.ordering)
+        assert len(q.groups) == len(prob.groups)
+        for a, b in zip(q.groups, prob.groups):
+            assert a.type == b.type and np.array_equal(a.keys, b.keys) and np.array_equal(a.meas, b.meas)
+            assert np.array_equal(a.noise, b.noise) and a.graph_index0 == b.graph_index0
+
+
+def test_linearize_bytes_accounting():
+    """184 B per Cal3_S2 projection factor, 232 B per 9-DoF SFM factor,
+    776 B per Pose3 Between factor (with shared noise: 720 + ids + measurement)."""
+    g = lambda t, n: P.FactorGroup(t, np.zeros((n, P.FACTOR_ARITY[t]), dtype=np.int64), np.zeros((n, P.FACTOR_MEAS[t])))
+    pr = P.Problem(np.zeros(1, dtype=np.int32), np.zeros(12), np.zeros(1, dtype=np.int64), [g(P.FACTOR_PROJECTION_CAL3S2, 10)])
+    assert pr.linearize_bytes() - 96 == 10 * 184
+    pr = P.Problem(np.zeros(1, dtype=np.int32), np.zeros(12), np.zeros(1, dtype=np.int64), [g(P.FACTOR_SFM_BUNDLER, 10)])
+    assert pr.linearize_bytes() - 96 == 10 * 232
+    pr = P.Problem(np.zeros(1, dtype=np.int32), np.zeros(12), np.zeros(1, dtype=np.int64), [g(P.FACTOR_BETWEEN_POSE3, 10)])
+    assert pr.linearize_bytes() - 96 == 10 * (96 + 8 + 624)
+
+
+@pytest.mark.parametrize("case", util.CASES)
+def test_symbolic_matches_reference_junction_tree(built, case):
+    """Cliques (frontals + separators) equal the reference's Bayes-tree cliques — bit exact."""
+    prob = util.load_case(case)
+    info, fp, fv, sp, sv, par, lvl = _symbolic(prob)
+    for kind in ("dump1",):
+        ref = util.golden(case, kind)
+        assert util.clique_set(fp, fv, sp, sv) == util.ref_clique_set(ref)
+    # parents precede children in elimination order, levels consistent
+    for c in range(info.ncliques):
+        if par[c] >= 0:
+            assert par[c] > c and lvl[par[c]] > lvl[c]
+
+
+@pytest.mark.parametrize("name,kw", [("bal_tiny", {}), ("sphere_tiny", {}), ("bal_tiny", dict(ncams=30, npoints=3000, visibility="scattered")),
+                                     ("sphere_tiny", dict(layers=12, per_ring=20)),
+                                     ("sphere_tiny", dict(layers=12, per_ring=20, ordering="reverse"))])
+def test_symbolic_matches_oracle(built, name, kw):
+    """Path-compressed C++ symbolic phase == literal C restatement (independent code)."""
+    prob = datasets.make(name, **kw)
+    info, fp, fv, sp, sv, par, lvl = _symbolic(prob)
+    op = O.OracleProblem(prob)
+    ofp, ofv, osp, osv, opar = op.cliques()
+    assert np.array_equal(fp, ofp) and np.array_equal(fv, ofv) and np.array_equal(sp, osp)
+    assert np.array_equal(sv, osv) and np.array_equal(par, opar)
+    oi = op.symbolic_info()
+    assert (info.ncliques, info.nlevels, info.max_frontal_dim, info.max_separator_dim) == \
+           (oi.ncliques, oi.nlevels, oi.max_frontal_dim, oi.max_separator_dim)
+    assert abs(info.factor_flops - oi.factor_flops) <= 1e-9 * oi.factor_flops
+
+
+def test_invalid_inputs_rejected(built):
+    L = capi.lib()
+    L.b200_symbolic_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(C.c_void_p)]
+    prob = datasets.make("bal_tiny")
+    prob.ordering[0] = prob.ordering[1]            # not a permutation
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    assert L.b200_symbolic_create(C.byref(desc), C.byref(h)) == P.INVALID_ARGUMENT
+    prob = datasets.make("bal_tiny")
+    prob.groups[0].keys[0, 1] = 0                  # point slot references a camera: wrong value type
+    desc, keep = prob.c_desc()
+    assert L.b200_symbolic_create(C.byref(desc), C.byref(h)) == P.INVALID_ARGUMENT
+    assert b"wrong value type" in L.b200_last_error_string()
+    prob = datasets.make("bal_tiny")
+    prob.groups[0].noise_kind = 9                  # e.g. a Constrained / Robust model
+    desc, keep = prob.c_desc()
+    assert L.b200_symbolic_create(C.byref(desc), C.byref(h)) == P.UNSUPPORTED_NOISE
