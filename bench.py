@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/sec (linearize + damped multifrontal solve + retract + error)
+on the BAL-style workload of BASELINE.json, through the C-ABI library.
+
+    python bench.py --gpus N --steps K --warmup W [--workload bal_c3] [--impl reference]
+
+One "step" = one LevenbergMarquardtOptimizer::iterate() from the same initial
+estimate (values restored, lambda reset), i.e. one linearize + >=1 damped
+factor/solve/retract/error tries.  `value` times it with the inputs resident in
+HBM; `e2e` times the same step through the public call with HOST buffers
+(host->device copy of the Values, device->host read-back of the new Values and
+the error inside the timed region).  `--impl reference` times the UNMODIFIED
+reference (oracle/_ref, built from /root/reference by oracle/Makefile; falls
+back to the plain-C oracle port when that binary is absent) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="bal_c3")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+METRIC = "LM iterations/sec (linearize+solve) on BAL-style graph"
+UNIT = "iterations/s"
+
+
+def workload_config(prob, args):
+    from gtsam_b200 import problem as P
+    return {
+        "workload": f"{args.workload}: {prob.name}", "factors": prob.nfactors, "variables": prob.nvars,
+        "factor_types": sorted({int(g.type) for g in prob.groups}),
+        "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else "natural",
+        "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
+        "cache": "working set (fronts + Jacobians) exceeds the 126 MB L2; no explicit flush",
+        "parallelism": "single GPU" if args.gpus == 1 else f"{args.gpus} independent replicas (sharded solve: next round)",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+def reference_time(prob, steps, warmup):
+    """Times LevenbergMarquardtOptimizer::iterate() of the reference on the host cores.
+    Returns (seconds per iterate, dict describing the run)."""
+    from oracle import refio
+    ncores = os.cpu_count()
+    if refio.have_ref():
+        try:
+            r = refio.time_lm(prob, steps, warmup)
+            return r["mean_s"], {"kind": "reference", "cores": 1, "host_cores": ncores,
+                                 "sample": f"{steps} x LevenbergMarquardtOptimizer::iterate() of the unmodified reference "
+                                           f"(oracle/_ref, -O3, no TBB in this image => single thread) on the full workload, "
+                                           f"{warmup} warm-up; linearize {r['linearize_s']:.3f}s, damped solve {r['solve_s']:.3f}s",
+                                 "error_after": r["error_after"], "inner_iterations": r["inner_iterations"]}
+        except Exception as e:  # binary present but not runnable on this box
+            note = f"oracle/_ref not runnable here ({type(e).__name__}); "
+    else:
+        note = "oracle/_ref absent; "
+    from gtsam_b200 import problem as P
+    from oracle import oracle_py as O
+    import ctypes as C
+    op = O.OracleProblem(prob)
+    v0 = prob.values.copy()
+    prm = P.CLMParams(100, 1e-5, 1e-5, 0.0, 1e-5, 10.0, 1e5, 0.0, 1e-3, 0, 1, 1e-6, 1e32)
+    ts = []
+    for s in range(warmup + steps):
+        op.set_values(v0)
+        lm = op.lm(prm)
+        t0 = time.perf_counter()
+        op.lm_iterate(lm)
+        if s >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), {"kind": "port", "cores": 1, "host_cores": ncores,
+                               "sample": note + f"{steps} x LM iterate of the plain-C oracle port on the full workload"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gtsam_b200 import datasets
+    prob = datasets.make(args.workload)
+    # bounded: the reference needs 1.7 s (bal_c3) .. 40 s (bal_c4) per iterate
+    est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0, "bal_c5": 200.0, "sphere2500": 0.3}.get(args.workload, 1.0)
+    steps = max(1, min(args.steps, int(150.0 / est)))
+    warmup = min(args.warmup, 1 if est > 1 else 3)
+    sec, info = reference_time(prob, steps, warmup)
+    val = 1.0 / sec
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload_config(prob, args),
+            "cpu_baseline": dict(info, value=val, unit=UNIT),
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    from gtsam_b200 import capi, datasets, optimizer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — gtsam_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    prob = datasets.make(args.workload)
+    ctx = capi.Context(local)
+    dev = capi.DeviceProblem(ctx, prob)
+    lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, device_problem=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    L = dev.L
+    host_values = prob.values.copy()
+    dev.save_values()
+
+    def step_resident():
+        dev.restore_values()                    # D2D: inputs already in HBM
+        capi._check(L.b200_lm_reset(lm.h))      # state <- (values, lambda0); recomputes graph.error
+        lm.iterate()
+
+    def step_e2e():
+        dev.set_values(host_values)             # host -> pinned -> device
+        capi._check(L.b200_lm_reset(lm.h))
+        lm.iterate()
+        out = dev.get_values()                  # device -> host
+        return out, lm.error()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall, ctx.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, wall, launches = timed(step_resident, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, 1)
+
+    # phase profile (separate pass; event records add ~1 us per phase)
+    dev.profile_enable(True)
+    for _ in range(args.steps):
+        step_resident()
+    dev.synchronize()
+    prof = dev.profile()
+    dev.profile_enable(False)
+    st = lm._state()
+
+    if rank != 0:
+        return
+    value = world * args.steps / (ms * 1e-3)
+    e2e = world * args.steps / (ms_e2e * 1e-3)
+    info = dev.symbolic_info()
+    peak, peak_src = measured_peaks()
+    per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in prof.items()}
+    # algorithmic bytes per step of the HBM-bound phases
+    lin_bytes = prob.linearize_bytes()
+    jac_bytes = sum(g.count * 8 * P_ncols(g) for g in prob.groups)
+    alg_bytes = {
+        "linearize": lin_bytes,                                  # 184 B/projection factor + Values
+        "memset_fronts": info.front_bytes,
+        "assemble": jac_bytes + info.front_bytes,                # read [A|b] once, touch every front entry once
+        "eliminate_small": 2 * info.front_bytes,                 # read each front, write [R S d] + Schur update
+        "eliminate_large": 2 * info.front_bytes,
+    }
+    dom = max(per_step, key=lambda k: per_step[k][0])
+    tries = max(1.0, per_step["assemble"][1])
+
+    def roof(name):
+        """achieved = algorithmic bytes of one pass / its average duration (CUDA events on the
+        launching stream, from the library's phase timers); linearize runs once per step, the
+        solve phases once per lambda try."""
+        ms_phase, _calls = per_step[name]
+        if ms_phase <= 0 or name not in alg_bytes:
+            return None
+        units = 1.0 if name == "linearize" else tries
+        ach = alg_bytes[name] * units / (ms_phase * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_phase / units,
+                "algorithmic_bytes_per_launch": alg_bytes[name]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(prob, args),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_values.nbytes),
+                "d2h_bytes_per_step": int(host_values.nbytes) + 64, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roof(dom) or roof("linearize"),
+        "roofline_linearize": roof("linearize"),
+        "phases_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
+        "lm": {"error_after": st.error, "lambda_after": st.lambda_, "tries_per_step": tries},
+        "tree": {"cliques": info.ncliques, "levels": info.nlevels, "max_frontal": info.max_frontal_dim,
+                 "max_separator": info.max_separator_dim, "factor_flops": info.factor_flops,
+                 "front_bytes": info.front_bytes},
+        "wall_ms_per_step": wall * 1e3 / args.steps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0}.get(args.workload, 1.0)
+            n = max(1, min(5, int(20.0 / est)))
+            sec, cinfo = reference_time(prob, n, 1)
+            line["cpu_baseline"] = dict(cinfo, value=1.0 / sec, unit=UNIT)
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def P_ncols(g):
+    from gtsam_b200 import problem as P
+    return P.FACTOR_DIM[g.type] * P.factor_ncols(g.type)
+
+
+if __name__ == "__main__":
+    main()

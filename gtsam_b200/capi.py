@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -26,7 +27,10 @@ EXPORTS = [
     "b200_solve", "b200_get_delta", "b200_try_step", "b200_accept_step", "b200_lm_params_legacy",
     "b200_lm_params_ceres", "b200_lm_create", "b200_lm_destroy", "b200_lm_iterate", "b200_lm_optimize",
     "b200_lm_get_state", "b200_lm_reset", "b200_gn_iterate", "b200_symbolic_info_get", "b200_get_cliques",
-    "b200_get_conditional", "b200_shared_front_buffer",
+    "b200_get_conditional", "b200_shared_front_buffer", "b200_save_values", "b200_restore_values",
+    "b200_synchronize", "b200_profile_enable", "b200_profile_phase_count", "b200_profile_phase_name",
+    "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
+    "b200_symbolic_get_cliques", "b200_symbolic_get_levels",
 ]
 
 
@@ -90,6 +94,13 @@ def lib():
         L.b200_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_get_conditional.argtypes = [vp, C.c_int64, dp]
         L.b200_shared_front_buffer.argtypes = [vp, C.POINTER(vp), ip]
+        L.b200_save_values.argtypes = [vp]
+        L.b200_restore_values.argtypes = [vp]
+        L.b200_synchronize.argtypes = [vp]
+        L.b200_profile_enable.argtypes = [vp, C.c_int]
+        L.b200_profile_phase_name.argtypes = [C.c_int]
+        L.b200_profile_phase_name.restype = C.c_char_p
+        L.b200_profile_get.argtypes = [vp, dp, ip]
         _LIB = L
     return _LIB
 
@@ -116,6 +127,7 @@ class Context:
         _check(self.L.b200_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self._problems = weakref.WeakSet()
 
     def launch_count(self) -> int:
         return int(self.L.b200_launch_count(self.h))
@@ -125,6 +137,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for p in list(self._problems):   # problems hold a pointer to the ctx: free them first
+                p.close()
             self.L.b200_ctx_destroy(self.h)
             self.h = None
 
@@ -141,11 +155,33 @@ class DeviceProblem:
         self.h = h
         self.nval = int(self.L.b200_values_size(h))
         self.ndelta = int(self.L.b200_delta_size(h))
+        ctx._problems.add(self)
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.b200_problem_destroy(self.h)
+            if self.ctx.h:
+                self.L.b200_problem_destroy(self.h)
             self.h = None
+
+    # -- benchmark / profiling helpers ------------------------------------------------
+    def save_values(self):
+        _check(self.L.b200_save_values(self.h))
+
+    def restore_values(self):
+        _check(self.L.b200_restore_values(self.h))
+
+    def synchronize(self):
+        _check(self.L.b200_synchronize(self.h))
+
+    def profile_enable(self, on=True):
+        _check(self.L.b200_profile_enable(self.h, int(on)))
+
+    def profile(self):
+        """{phase: (milliseconds, calls)} accumulated since profile_enable()."""
+        n = self.L.b200_profile_phase_count()
+        ms, calls = np.zeros(16), np.zeros(16, dtype=np.int64)
+        _check(self.L.b200_profile_get(self.h, _dp(ms), _ip(calls)))
+        return {self.L.b200_profile_phase_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
 
     def __del__(self):
         try:

@@ -69,6 +69,37 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
     case B200_FACTOR_PRIOR_CAM_BUNDLER: { constexpr int TY = B200_FACTOR_PRIOR_CAM_BUNDLER; STMT; break; } \
   }
 
+// ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
+// CUDA events on the launching stream, resolved at the next host sync. -----------------
+enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_COUNT };
+struct PhaseScope {
+  b200_problem* p; int ph; size_t idx; bool on;
+  PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
+    if (!on) return;
+    if (p->ev_used == p->ev_pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      p->ev_pool.push_back({a, b});
+    }
+    idx = p->ev_used++;
+    p->ev_phase.resize(p->ev_used);
+    p->ev_phase[idx] = ph;
+    cudaEventRecord(p->ev_pool[idx].first, p->ctx->stream);
+  }
+  ~PhaseScope() { if (on) cudaEventRecord(p->ev_pool[idx].second, p->ctx->stream); }
+};
+static void resolve_profile(b200_problem* p) {  // call after a stream sync
+  for (size_t i = 0; i < p->ev_used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->ev_pool[i].first, p->ev_pool[i].second) == cudaSuccess) {
+      p->phase_ms[p->ev_phase[i]] += ms;
+      p->phase_calls[p->ev_phase[i]] += 1;
+    }
+  }
+  p->ev_used = 0;
+}
+
 static int reduce_blocks(int64_t count, int threads, int sm) {
   int64_t b = (count + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm * 8));
@@ -77,6 +108,7 @@ static int reduce_blocks(int64_t count, int threads, int sm) {
 // graph.error(values) -> *slot (device double)
 static int enqueue_error(b200_problem* p, const double* values, double* slot) {
   cudaStream_t st = p->ctx->stream;
+  PhaseScope ps(p, PH_ERROR);
   bool first = true;
   for (auto& g : p->groups) {
     if (!g.count) continue;
@@ -93,6 +125,7 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
 
 static int enqueue_linearize(b200_problem* p) {
   cudaStream_t st = p->ctx->stream;
+  PhaseScope ps(p, PH_LINEARIZE);
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = (int)((g.count + 127) / 128);
@@ -122,14 +155,21 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   cudaStream_t st = p->ctx->stream;
   b200_ctx* ctx = p->ctx;
   const TreeView t = tview(p);
-  B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->sym.arena_doubles * sizeof(double), st));
-  for (auto& g : p->groups) {
-    if (!g.count) continue;
-    const int nb = (int)((g.count + 127) / 128);
-    DISPATCH_TYPE(g.type, (assemble_kernel<TY><<<nb, 128, 0, st>>>(view(g), t)));
-    ctx->launches++;
+  {
+    PhaseScope ps(p, PH_MEMSET);
+    B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->sym.arena_doubles * sizeof(double), st));
+  }
+  {
+    PhaseScope ps(p, PH_ASSEMBLE);
+    for (auto& g : p->groups) {
+      if (!g.count) continue;
+      const int nb = (int)((g.count + 127) / 128);
+      DISPATCH_TYPE(g.type, (assemble_kernel<TY><<<nb, 128, 0, st>>>(view(g), t)));
+      ctx->launches++;
+    }
   }
   if (lambda > 0) {
+    PhaseScope ps(p, PH_DAMP);
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
     damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
@@ -139,6 +179,7 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   for (size_t l = 0; l < p->levels.size(); l++) {
     const LevelPlan& L = p->levels[l];
     if (L.small_count) {
+      PhaseScope ps(p, PH_ELIM_SMALL);
       const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t smem = (size_t)kWarpsPerBlock * p->max_small_n * p->max_small_n * sizeof(double);
       elim_small_kernel<<<nb, kWarpsPerBlock * 32, smem, st>>>(t, p->d_lvl_small + L.small_begin, L.small_count,
@@ -146,6 +187,7 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
       ctx->launches++;
     }
     if (L.large_count) {
+      PhaseScope ps(p, PH_ELIM_LARGE);
       const int* list = p->d_lvl_large + L.large_begin;
       for (int k0 = 0; k0 < L.large_max_nf; k0 += kNB) {
         potrf_trsm_kernel<<<L.large_count, 256, 0, st>>>(t, list, k0, p->d_scalars);
@@ -164,6 +206,8 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     }
   }
   // ---- back-substitution, roots to leaves ----
+  {
+  PhaseScope ps(p, PH_BACKSUB);
   for (int l = (int)p->levels.size() - 1; l >= 0; l--) {
     const LevelPlan& L = p->levels[l];
     if (L.large_count) {
@@ -178,7 +222,9 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
       ctx->launches++;
     }
   }
+  }
   // ---- linear errors on the undamped graph ----
+  PhaseScope pl(p, PH_LINERR);
   bool first = true;
   for (auto& g : p->groups) {
     if (!g.count) continue;
@@ -193,14 +239,18 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   }
   B200_CUDA(cudaGetLastError());
   p->solved = true;
+  p->factored = true;
   return B200_OK;
 }
 
 static int enqueue_try_step(b200_problem* p) {
   cudaStream_t st = p->ctx->stream;
-  retract_kernel<<<(int)((p->nvars + 127) / 128), 128, 0, st>>>(p->d_values, p->d_delta, p->d_val_off, p->d_var_dof,
-                                                                 p->d_var_type, (int)p->nvars, p->d_new_values);
-  p->ctx->launches++;
+  {
+    PhaseScope ps(p, PH_RETRACT);
+    retract_kernel<<<(int)((p->nvars + 127) / 128), 128, 0, st>>>(p->d_values, p->d_delta, p->d_val_off, p->d_var_dof,
+                                                                   p->d_var_type, (int)p->nvars, p->d_new_values);
+    p->ctx->launches++;
+  }
   return enqueue_error(p, p->d_new_values, &p->d_scalars->new_error);
 }
 
@@ -212,11 +262,13 @@ static int reset_flags(b200_problem* p) {
 static int fetch_scalars(b200_problem* p) {
   B200_CUDA(cudaMemcpyAsync(p->h_scalars, p->d_scalars, sizeof(Scalars), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (p->profile) resolve_profile(p);
   return B200_OK;
 }
 static int solve_status(const b200_problem* p, int64_t* fail_var) {
   const Scalars* s = p->h_scalars;
-  int c = std::min(s->fail_clique, s->nan_clique);
+  // a failed factorisation poisons everything below it: report the Cholesky failure first
+  int c = s->fail_clique != INT_MAX ? s->fail_clique : s->nan_clique;
   if (c == INT_MAX) { if (fail_var) *fail_var = -1; return B200_OK; }
   if (fail_var) *fail_var = p->sym.front_vars[p->sym.front_ptr[c]];
   return B200_INDETERMINATE;
@@ -345,6 +397,8 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_partials); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned);
+  cudaFree(p->d_saved_values);
+  for (auto& e : p->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete p;
   return B200_OK;
 }
@@ -571,6 +625,43 @@ int b200_accept_step(b200_problem* p) {
   return B200_OK;
 }
 
+/* device-side snapshot / restore of Values (benchmarks: reset without host traffic) */
+int b200_save_values(b200_problem* p) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  if (!p->d_saved_values) B200_CUDA(cudaMalloc((void**)&p->d_saved_values, std::max<int64_t>(1, p->nval) * sizeof(double)));
+  B200_CUDA(cudaMemcpyAsync(p->d_saved_values, p->d_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
+  return B200_OK;
+}
+int b200_restore_values(b200_problem* p) {
+  if (!p->d_saved_values) { set_error("b200_restore_values before b200_save_values"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_saved_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
+  p->linearized = p->solved = false;
+  return B200_OK;
+}
+int b200_synchronize(b200_problem* p) {
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (p->profile) resolve_profile(p);
+  return B200_OK;
+}
+int b200_profile_enable(b200_problem* p, int on) {
+  p->profile = on != 0;
+  for (int i = 0; i < PH_COUNT; i++) { p->phase_ms[i] = 0; p->phase_calls[i] = 0; }
+  p->ev_used = 0;
+  return B200_OK;
+}
+int b200_profile_phase_count(void) { return PH_COUNT; }
+const char* b200_profile_phase_name(int i) {
+  static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
+                                        "eliminate_large", "back_substitute", "linear_error", "retract", "error"};
+  return (i >= 0 && i < PH_COUNT) ? names[i] : "";
+}
+int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {
+  for (int i = 0; i < PH_COUNT; i++) { ms[i] = p->phase_ms[i]; calls[i] = p->phase_calls[i]; }
+  return B200_OK;
+}
+
 // ---- symbolic introspection ------------------------------------------------------
 int b200_symbolic_info_get(const b200_problem* p, b200_symbolic_info* info) {
   const Symbolic& S = p->sym;
@@ -592,7 +683,7 @@ int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* s
 /* conditional [R S d] of clique c after a solve: nf x (nf+ns+1) column-major */
 int b200_get_conditional(b200_problem* p, int64_t c, double* out) {
   const Symbolic& S = p->sym;
-  if (c < 0 || c >= S.ncliques || !p->solved) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
+  if (c < 0 || c >= S.ncliques || !p->factored) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   const int64_t f = S.nf[c], nn = f + S.ns[c] + 1;
   std::vector<double> M((size_t)(nn * nn));

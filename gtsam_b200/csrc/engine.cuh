@@ -108,7 +108,15 @@ struct b200_problem {
   b200::Scalars* d_scalars = nullptr;
   b200::Scalars* h_scalars = nullptr;  // pinned
   double* h_pinned = nullptr;          // pinned staging for values
-  bool linearized = false, solved = false;
+  bool linearized = false, solved = false, factored = false;
+  double* d_saved_values = nullptr;
+  // phase timers
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_phase;
+  size_t ev_used = 0;
+  double phase_ms[16] = {0};
+  int64_t phase_calls[16] = {0};
   int max_small_n = 0;
 };
 

@@ -219,6 +219,20 @@ int b200_try_step(b200_problem* prob, double* new_error);
 /* values <- newValues */
 int b200_accept_step(b200_problem* prob);
 
+/* Device-side snapshot / restore of the Values (reset between benchmark steps
+ * without host traffic) and an explicit stream sync. */
+int b200_save_values(b200_problem* prob);
+int b200_restore_values(b200_problem* prob);
+int b200_synchronize(b200_problem* prob);
+
+/* Built-in phase timers — the counterpart of the reference's gttic/gttoc call
+ * tree (gtsam/base/timing.h:245-302): CUDA events on the launching stream
+ * around each phase, accumulated in milliseconds. */
+int b200_profile_enable(b200_problem* prob, int on);
+int b200_profile_phase_count(void);
+const char* b200_profile_phase_name(int phase);
+int b200_profile_get(b200_problem* prob, double* ms, int64_t* calls);
+
 /* Whole optimizers (host control logic a17/a18 unchanged, data on device). */
 void b200_lm_params_legacy(b200_lm_params* p); /* LevenbergMarquardtParams::SetLegacyDefaults */
 void b200_lm_params_ceres(b200_lm_params* p);  /* ::SetCeresDefaults                          */
