@@ -263,6 +263,7 @@ def main():
         "assemble": jac_bytes + info.front_bytes,                # read [A|b] once, touch every front entry once
         "eliminate_small": 2 * info.front_bytes,                 # read each front, write [R S d] + Schur update
         "eliminate_large": 2 * info.front_bytes,
+        "leaf_fused": jac_bytes + info.front_bytes,              # read [A|b] of the leaf factors, write [R S d]
     }
     dom = max(per_step, key=lambda k: per_step[k][0])
     tries = max(1.0, per_step["assemble"][1])

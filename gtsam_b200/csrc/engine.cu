@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -49,7 +50,7 @@ static GroupView view(const b200_problem::Group& g) {
 }
 static TreeView tview(const b200_problem* p) {
   TreeView t;
-  t.arena = p->d_arena; t.off = p->d_off; t.nf = p->d_nf; t.ns = p->d_ns; t.parent = p->d_parent;
+  t.arena = p->d_arena; t.off = p->d_off; t.nf = p->d_nf; t.ns = p->d_ns; t.parent = p->d_parent; t.ld = p->d_ld;
   t.ea_ptr = p->d_ea_ptr; t.ea_map = p->d_ea_map; t.didx_ptr = p->d_didx_ptr; t.didx = p->d_didx;
   return t;
 }
@@ -72,7 +73,7 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
-             PH_LINERR, PH_RETRACT, PH_ERROR, PH_COUNT };
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_COUNT };
 struct PhaseScope {
   b200_problem* p; int ph; size_t idx; bool on;
   PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
@@ -157,12 +158,12 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   const TreeView t = tview(p);
   {
     PhaseScope ps(p, PH_MEMSET);
-    B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->sym.arena_doubles * sizeof(double), st));
+    if (p->zero_doubles) B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->zero_doubles * sizeof(double), st));
   }
   {
     PhaseScope ps(p, PH_ASSEMBLE);
     for (auto& g : p->groups) {
-      if (!g.count) continue;
+      if (!g.n_nonleaf) continue;   // every factor of the group is owned by a fused leaf clique
       const int nb = (int)((g.count + 127) / 128);
       DISPATCH_TYPE(g.type, (assemble_kernel<TY><<<nb, 128, 0, st>>>(view(g), t)));
       ctx->launches++;
@@ -173,6 +174,16 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
     damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
+    ctx->launches++;
+  }
+  if (p->n_fused) {
+    PhaseScope ps(p, PH_LEAF);
+    GroupTable gt;
+    for (size_t gi = 0; gi < p->groups.size(); gi++) gt.g[gi] = view(p->groups[gi]);
+    const int nb = (p->n_fused + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    leaf_fused_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, gt, p->d_fused_list, p->n_fused, p->d_fused_fac_ptr,
+                                                          p->d_fused_fac, lambda, (lambda > 0 && diagonal) ? p->d_hdiag : nullptr,
+                                                          min_diag, max_diag, p->d_scalars);
     ctx->launches++;
   }
   // ---- elimination, leaves to roots ----
@@ -211,13 +222,13 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   for (int l = (int)p->levels.size() - 1; l >= 0; l--) {
     const LevelPlan& L = p->levels[l];
     if (L.large_count) {
-      const size_t smem = (size_t)(L.large_max_nf + L.large_max_ns) * sizeof(double);
+      const size_t smem = (size_t)(L.large_max_nf + L.large_max_ns + 32 * 33) * sizeof(double);
       backsub_large_kernel<<<L.large_count, 256, smem, st>>>(t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars);
       ctx->launches++;
     }
-    if (L.small_count) {
-      const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      backsub_small_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, p->d_lvl_small + L.small_begin, L.small_count,
+    if (L.bsmall_count) {
+      const int nb = (L.bsmall_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      backsub_small_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, p->d_lvl_bsmall + L.bsmall_begin, L.bsmall_count,
                                                                p->d_delta, p->d_scalars);
       ctx->launches++;
     }
@@ -395,7 +406,8 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
   cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
-  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_partials); cudaFree(p->d_scalars);
+  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_ld);
+  cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned);
   cudaFree(p->d_saved_values);
   for (auto& e : p->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -441,6 +453,30 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   UP(upload(&p->d_var_dof, var_dof, st));
   UP(upload(&p->d_var_type, p->var_type, st));
   UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
+  // ---- storage plan: fused leaf cliques keep only their f x n conditional -------------
+  const bool leaf_path = d->ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
+  std::vector<char> fused(S.ncliques, 0);
+  std::vector<int> fused_list;
+  for (int64_t c = 0; c < S.ncliques; c++) {
+    const int64_t nn = S.nf[c] + S.ns[c] + 1;
+    if (leaf_path && S.level[c] == 0 && S.nf[c] <= kLeafMaxF && (int64_t)S.nf[c] * nn <= kLeafMaxFN) {
+      fused[c] = 1;
+      fused_list.push_back((int)c);
+    }
+  }
+  p->n_fused = (int)fused_list.size();
+  p->h_off.assign(S.ncliques + 1, 0);
+  p->h_ld.assign(S.ncliques, 0);
+  {
+    int64_t o = 0;
+    for (int64_t c = 0; c < S.ncliques; c++)
+      if (!fused[c]) { const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = (int)nn; o += nn * nn; }
+    p->zero_doubles = o;   // everything below is accumulated into by atomics: zeroed per solve
+    for (int64_t c = 0; c < S.ncliques; c++)
+      if (fused[c]) { const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = S.nf[c]; o += (int64_t)S.nf[c] * nn; }
+    p->arena_doubles = o;
+    p->h_off[S.ncliques] = o;
+  }
   // ---- factor tables ----
   std::vector<std::vector<int2>> hkeys(d->ngroups);
   std::vector<std::vector<int4>> hscat(d->ngroups);
@@ -452,7 +488,9 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     for (int64_t i = 0; i < s.count; i++) {
       const int64_t pos = g.gi0 + i;
       hkeys[gi][i] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
-      hscat[gi][i] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], 0);
+      const int isleaf = fused[S.fac_clique[pos]];
+      hscat[gi][i] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
+      if (!isleaf) g.n_nonleaf++;
     }
     UP(upload(&g.d_keys, hkeys[gi], st));
     UP(upload(&g.d_scat, hscat[gi], st));
@@ -466,7 +504,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   // ---- junction tree tables ----
   std::vector<int> parent32(S.ncliques);
   for (int64_t c = 0; c < S.ncliques; c++) parent32[c] = (int)S.parent[c];
-  UP(upload(&p->d_off, S.off, st));
+  UP(upload(&p->d_off, p->h_off, st));
+  UP(upload(&p->d_ld, p->h_ld, st));
   UP(upload(&p->d_nf, S.nf, st));
   UP(upload(&p->d_ns, S.ns, st));
   UP(upload(&p->d_parent, parent32, st));
@@ -478,11 +517,33 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   for (int64_t v = 0; v < n; v++) {
     const int c = S.var_clique[v];
     const int64_t nn = S.nf[c] + S.ns[c] + 1;
-    for (int k = 0; k < var_dim[v]; k++) diag_index[var_dof[v] + k] = S.off[c] + (S.var_slot[v] + k) * (nn + 1);
+    for (int k = 0; k < var_dim[v]; k++)
+      diag_index[var_dof[v] + k] = fused[c] ? -1 : p->h_off[c] + (S.var_slot[v] + k) * (nn + 1);
   }
   UP(upload(&p->d_diag_index, diag_index, st));
+  // fused leaf cliques: CSR of their factors as (group, index), graph order
+  if (p->n_fused) {
+    std::vector<int> lpos(S.ncliques, -1), fptr(p->n_fused + 1, 0);
+    for (int i = 0; i < p->n_fused; i++) lpos[fused_list[i]] = i;
+    for (int64_t pos = 0; pos < total; pos++) if (fused[S.fac_clique[pos]]) fptr[lpos[S.fac_clique[pos]] + 1]++;
+    for (int i = 0; i < p->n_fused; i++) fptr[i + 1] += fptr[i];
+    std::vector<int2> ffac(fptr[p->n_fused]);
+    std::vector<int> cur(fptr.begin(), fptr.end() - 1);
+    for (int64_t gi = 0; gi < d->ngroups; gi++)
+      for (int64_t i = 0; i < p->groups[gi].count; i++) {
+        const int64_t pos = p->groups[gi].gi0 + i;
+        if (fused[S.fac_clique[pos]]) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)i);
+      }
+    // keep graph order inside each clique (groups may interleave in the graph)
+    for (int i = 0; i < p->n_fused; i++)
+      std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) {
+        return p->groups[a.x].gi0 + a.y < p->groups[b.x].gi0 + b.y; });
+    UP(upload(&p->d_fused_list, fused_list, st));
+    UP(upload(&p->d_fused_fac_ptr, fptr, st));
+    UP(upload(&p->d_fused_fac, ffac, st));
+  }
   // ---- level plans: small (one warp per clique) / large (blocked) ----
-  std::vector<int> small, large;
+  std::vector<int> small, large, bsmall;
   p->levels.resize(S.nlevels);
   p->max_small_n = 1;
   for (int64_t l = 0; l < S.nlevels; l++) {
@@ -490,11 +551,15 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     L = LevelPlan();
     L.small_begin = (int)small.size();
     L.large_begin = (int)large.size();
+    L.bsmall_begin = (int)bsmall.size();
     for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
-      if (nn <= kSmallMaxN) {
+      if (fused[c]) {
+        bsmall.push_back(c);   // eliminated by leaf_fused_kernel; back-substituted one warp per clique
+      } else if (nn <= kSmallMaxN) {
         small.push_back(c);
+        bsmall.push_back(c);
         p->max_small_n = std::max(p->max_small_n, nn);
       } else {
         large.push_back(c);
@@ -504,14 +569,16 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       }
     }
     L.small_count = (int)small.size() - L.small_begin;
+    L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
     L.large_count = (int)large.size() - L.large_begin;
-    if ((size_t)(L.large_max_nf + L.large_max_ns) * sizeof(double) > 200 * 1024)
+    if ((size_t)(L.large_max_nf + L.large_max_ns + 32 * 33) * sizeof(double) > 200 * 1024)
       FAIL(B200_INVALID_ARGUMENT, "front too large for the single-CTA back-substitution of this build");
   }
   UP(upload(&p->d_lvl_small, small, st));
+  UP(upload(&p->d_lvl_bsmall, bsmall, st));
   UP(upload(&p->d_lvl_large, large, st));
   // ---- arena + scratch ----
-  B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, S.arena_doubles) * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, p->arena_doubles) * sizeof(double)));
   p->partial_cap = 2 * ctx->sm_count * 8;
   B200_CUDA(cudaMalloc((void**)&p->d_partials, (size_t)p->partial_cap * sizeof(double)));
   B200_CUDA(cudaMalloc((void**)&p->d_scalars, sizeof(Scalars)));
@@ -654,7 +721,8 @@ int b200_profile_enable(b200_problem* p, int on) {
 int b200_profile_phase_count(void) { return PH_COUNT; }
 const char* b200_profile_phase_name(int i) {
   static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
-                                        "eliminate_large", "back_substitute", "linear_error", "retract", "error"};
+                                        "eliminate_large", "back_substitute", "linear_error", "retract", "error",
+                                        "leaf_fused"};
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {
@@ -668,7 +736,7 @@ int b200_symbolic_info_get(const b200_problem* p, b200_symbolic_info* info) {
   info->ncliques = S.ncliques; info->nlevels = S.nlevels; info->total_dim = p->ndelta;
   info->max_frontal_dim = S.max_nf; info->max_separator_dim = S.max_ns;
   info->frontal_list_len = (int64_t)S.front_vars.size(); info->separator_list_len = (int64_t)S.sep_vars.size();
-  info->factor_flops = S.flops; info->front_bytes = S.arena_doubles * 8;
+  info->factor_flops = S.flops; info->front_bytes = p->arena_doubles * 8;
   return B200_OK;
 }
 int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
@@ -685,12 +753,12 @@ int b200_get_conditional(b200_problem* p, int64_t c, double* out) {
   const Symbolic& S = p->sym;
   if (c < 0 || c >= S.ncliques || !p->factored) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
-  const int64_t f = S.nf[c], nn = f + S.ns[c] + 1;
-  std::vector<double> M((size_t)(nn * nn));
-  B200_CUDA(cudaMemcpyAsync(M.data(), p->d_arena + S.off[c], M.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  const int64_t f = S.nf[c], nn = f + S.ns[c] + 1, ld = p->h_ld[c];
+  std::vector<double> M((size_t)(ld * nn));
+  B200_CUDA(cudaMemcpyAsync(M.data(), p->d_arena + p->h_off[c], M.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
   for (int64_t j = 0; j < nn; j++)
-    for (int64_t i = 0; i < f; i++) out[i + j * f] = (i <= j) ? M[(size_t)(i + j * nn)] : 0.0;
+    for (int64_t i = 0; i < f; i++) out[i + j * f] = (i <= j) ? M[(size_t)(i + j * ld)] : 0.0;
   return B200_OK;
 }
 struct b200_symbolic { Symbolic sym; int64_t ndelta; };

@@ -42,6 +42,7 @@ struct TreeView {
   const int* nf;
   const int* ns;
   const int* parent;
+  const int* ld;           // leading dimension of the stored block (n, or nf for fused leaves)
   const int64_t* ea_ptr;
   const int* ea_map;
   const int64_t* didx_ptr;
@@ -59,7 +60,8 @@ struct Scalars {           // device scalars fetched once per LM try
 };
 
 struct LevelPlan {
-  int small_begin, small_count;   // range in d_lvl_small
+  int small_begin, small_count;   // range in d_lvl_small (elimination, one warp per clique)
+  int bsmall_begin, bsmall_count; // range in d_lvl_bsmall (back-substitution: small + fused leaves)
   int large_begin, large_count;   // range in d_lvl_large
   int large_max_nf, large_max_n;  // over the large cliques of the level
   int large_max_ns;
@@ -89,6 +91,7 @@ struct b200_problem {
     int* d_cal = nullptr;
     double* d_J = nullptr;
     int4* d_scat = nullptr;
+    int64_t n_nonleaf = 0;   // factors NOT owned by a fused leaf clique
   };
   std::vector<Group> groups;
   // device state
@@ -97,11 +100,18 @@ struct b200_problem {
   double* d_cal = nullptr;
   double* d_arena = nullptr;
   int64_t* d_off = nullptr;
-  int *d_nf = nullptr, *d_ns = nullptr, *d_parent = nullptr;
+  int *d_nf = nullptr, *d_ns = nullptr, *d_parent = nullptr, *d_ld = nullptr;
+  std::vector<int64_t> h_off;       // final arena offsets (fused leaves store f x n only)
+  std::vector<int> h_ld;
+  // fused leaf path
+  int n_fused = 0;
+  int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr;
+  int2* d_fused_fac = nullptr;
+  int64_t arena_doubles = 0, zero_doubles = 0;  // [0, zero_doubles) = non-leaf fronts (memset per solve)
   int64_t *d_ea_ptr = nullptr, *d_didx_ptr = nullptr;
   int *d_ea_map = nullptr, *d_didx = nullptr;
   int64_t* d_diag_index = nullptr;  // per delta scalar: arena index of its diagonal entry
-  int *d_lvl_small = nullptr, *d_lvl_large = nullptr;
+  int *d_lvl_small = nullptr, *d_lvl_large = nullptr, *d_lvl_bsmall = nullptr;
   std::vector<b200::LevelPlan> levels;
   double* d_partials = nullptr;     // block partial sums
   int partial_cap = 0;

@@ -24,6 +24,14 @@ constexpr int kSmallMaxN = 48;   // fronts up to this size run one-warp-per-cliq
 constexpr int kWarpsPerBlock = 4;
 constexpr int kNB = 32;          // panel width of the blocked large-front path
 constexpr int kTile = 64;        // SYRK tile
+constexpr int kLeafMaxF = 6;     // leaf cliques up to this frontal dim take the fused path
+constexpr int kLeafMaxFN = 768;  // doubles of [F S d] staged per warp in shared memory
+constexpr int kMaxGroups = 8;    // factor groups addressable by the fused leaf kernel
+
+struct GroupTable { GroupView g[kMaxGroups]; };
+__constant__ int kFD[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
+__constant__ int kFN1[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 6, 9, 9};
+__constant__ int kFN2[B200_NUM_FACTOR_TYPES] = {6, 0, 0, 3, 3, 0};
 
 // ---------------------------------------------------------------------------
 // block reduction helpers
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) 
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= g.count) return;
   const int4 sc = g.scat[f];
+  if (sc.w) return;   // owned by a fused leaf clique: handled by leaf_fused_kernel
   double Jl[D * NC];  // column-major
   const double* J = g.J + f;
 #pragma unroll
@@ -218,6 +227,7 @@ __global__ void damp_kernel(double* arena, const int64_t* __restrict__ diag_inde
                             const double* __restrict__ hdiag, double min_diag, double max_diag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (diag_index[i] < 0) return;  // variable of a fused leaf clique (damped inside leaf_fused_kernel)
   double a2 = 1.0;
   if (hdiag) {
     double h = fmin(fmax(hdiag[i], min_diag), max_diag);
@@ -290,6 +300,115 @@ elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_
         const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
         atomicAdd(P + lo + (size_t)hi * pn, A[(f + i) + (f + j) * n]);
       }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// fused leaf path (the BAL "point" cliques, and any leaf clique with a small
+// frontal block): ONE kernel does Hessian assembly of the clique's own factors
+// (a12), the damping priors (a10), the partial Cholesky (a13/a14) and the
+// extend-add of the Schur complement into the parent — without ever
+// materialising the (f+s+1)^2 front in HBM.  One warp per clique; only the
+// f x (f+s+1) block [F S d] lives in shared memory:
+//   * factor contributions whose row is frontal accumulate into [F S d];
+//   * contributions between separator variables (A_cam^T A_cam, A_cam^T b, b^T b)
+//     do not take part in the elimination, so they go straight to the parent;
+//   * after R = chol(F), S' = R^-T [S d], the update -S'^T S' goes to the parent.
+// The conditional [R S' d'] is stored compactly (f x n, ld = f).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int count,
+                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, double lambda,
+                  const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc) {
+  __shared__ double sm[kWarpsPerBlock][kLeafMaxFN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (idx >= count) return;
+  const int c = list[idx];
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  double* LB = sm[warp];  // row-major f x n
+  for (int e = lane; e < f * n; e += 32) LB[e] = 0.0;
+  const int p = t.parent[c];
+  double* P = p >= 0 ? t.arena + t.off[p] : nullptr;
+  const int pn = p >= 0 ? t.nf[p] + t.ns[p] + 1 : 0;
+  const int* map = t.ea_map + t.ea_ptr[c];
+  __syncwarp();
+  for (int q = fac_ptr[idx]; q < fac_ptr[idx + 1]; q++) {
+    const int2 gf = fac[q];
+    const GroupView& g = gt.g[gf.x];
+    const int D = kFD[g.type], N1 = kFN1[g.type], N2 = kFN2[g.type], NC = N1 + N2 + 1;
+    const int4 scat = g.scat[gf.y];
+    const double* J = g.J + gf.y;
+    const int NP = NC * (NC + 1) / 2;
+    for (int pi = lane; pi < NP; pi += 32) {
+      int ca = 0, rem = pi;
+      while (rem >= NC - ca) { rem -= NC - ca; ca++; }
+      const int cb = ca + rem;
+      double dot = 0;
+      for (int r = 0; r < D; r++) dot += J[(size_t)(r + ca * D) * g.count] * J[(size_t)(r + cb * D) * g.count];
+      int I = ca < N1 ? scat.y + ca : (ca < N1 + N2 ? scat.z + (ca - N1) : n - 1);
+      int Jx = cb < N1 ? scat.y + cb : (cb < N1 + N2 ? scat.z + (cb - N1) : n - 1);
+      if (I > Jx) { const int tmp = I; I = Jx; Jx = tmp; }
+      if (I < f) {
+        LB[I * n + Jx] += dot;  // distinct (ca,cb) -> distinct entries: no intra-warp conflict
+      } else if (P) {
+        const int a = map[I - f], b = map[Jx - f];
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        atomicAdd(P + lo + (size_t)hi * pn, dot);
+      }
+    }
+    __syncwarp();
+  }
+  if (lambda > 0 && lane < f) {  // damping prior of each frontal scalar
+    double a2 = 1.0;
+    if (hdiag) {
+      const double h = fmin(fmax(hdiag[t.didx[t.didx_ptr[c] + lane]], min_diag), max_diag);
+      const double sq = sqrt(h);
+      a2 = sq * sq;
+    }
+    const double sl = 1.0 / (1.0 / sqrt(lambda));
+    LB[lane * n + lane] += (sl * sl) * a2;
+  }
+  __syncwarp();
+  bool ok = true;
+  for (int k = 0; k < f; k++) {
+    const double piv = LB[k * n + k];
+    if (!(piv > 0.0)) ok = false;
+    const double r = sqrt(piv);
+    __syncwarp();
+    for (int j = k + lane; j < n; j += 32) LB[k * n + j] = (j == k) ? r : LB[k * n + j] / r;
+    __syncwarp();
+    for (int e = lane; e < (f - k - 1) * n; e += 32) {
+      const int i = k + 1 + e / n, j = e % n;
+      if (j >= i) LB[i * n + j] -= LB[k * n + i] * LB[k * n + j];
+    }
+    __syncwarp();
+  }
+  if (f >= 2) {
+    if (!(dexp(LB[(f - 2) * n + f - 2]) - dexp(LB[(f - 1) * n + f - 1]) < 12)) ok = false;
+  } else if (f == 1) {
+    if (!(dexp(LB[0]) > -12)) ok = false;
+  }
+  if (!ok && lane == 0) atomicMin(&sc->fail_clique, c);
+  double* M = t.arena + t.off[c];  // compact conditional, column-major f x n
+  for (int e = lane; e < f * n; e += 32) {
+    const int i = e % f, j = e / f;
+    M[e] = (i <= j) ? LB[i * n + j] : 0.0;
+  }
+  if (P) {
+    const int w = s + 1, total = w * (w + 1) / 2;
+    for (int e = lane; e < total; e += 32) {
+      int j = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((j + 1) * (j + 2) / 2 <= e) j++;
+      while (j * (j + 1) / 2 > e) j--;
+      const int i = e - j * (j + 1) / 2;
+      double v = 0;
+      for (int k = 0; k < f; k++) v += LB[k * n + f + i] * LB[k * n + f + j];
+      const int a = map[i], b = map[j];
+      const int lo = a < b ? a : b, hi = a < b ? b : a;
+      atomicAdd(P + lo + (size_t)hi * pn, -v);
     }
   }
 }
@@ -453,21 +572,21 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
   const int idx = blockIdx.x * kWarpsPerBlock + warp;
   if (idx >= count) return;
   const int c = list[idx];
-  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  const int f = t.nf[c], s = t.ns[c], n = f + s + 1, ld = t.ld[c];
   const double* M = t.arena + t.off[c];
   const int* di = t.didx + t.didx_ptr[c];
   double* x = xs[warp];
   for (int i = lane; i < f; i += 32) {
-    double r = M[i + (size_t)(n - 1) * n];
-    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * n] * delta[di[f + cc]];
+    double r = M[i + (size_t)(n - 1) * ld];
+    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * ld] * delta[di[f + cc]];
     x[i] = r;
   }
   __syncwarp();
   for (int i = f - 1; i >= 0; i--) {
-    if (lane == 0) x[i] = x[i] / M[i + (size_t)i * n];
+    if (lane == 0) x[i] = x[i] / M[i + (size_t)i * ld];
     __syncwarp();
     const double xi = x[i];
-    for (int k = lane; k < i; k += 32) x[k] -= M[k + (size_t)i * n] * xi;
+    for (int k = lane; k < i; k += 32) x[k] -= M[k + (size_t)i * ld] * xi;
     __syncwarp();
   }
   bool nan = false;
@@ -480,14 +599,19 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
 
 __global__ void __launch_bounds__(256)
 backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc) {
-  extern __shared__ double sh[];  // x[f] then xs[s]
+  // x_F = R^-1 (d - S x_S) for one large clique per CTA.  The triangular solve runs in
+  // 32-row blocks from the bottom: the 32x32 diagonal block is staged in shared memory and
+  // solved by one warp with shuffles (no dependent global load per row), then all threads
+  // apply the block's columns to the rows above (coalesced column reads).
+  extern __shared__ double sh[];  // x[f], xsep[s], Dg[32][33]
   const int c = list[blockIdx.x];
   const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
   const double* M = t.arena + t.off[c];
   const int* di = t.didx + t.didx_ptr[c];
   double* x = sh;
   double* xsep = sh + f;
-  const int tid = threadIdx.x;
+  double (*Dg)[33] = reinterpret_cast<double (*)[33]>(sh + f + s);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int cc = tid; cc < s; cc += 256) xsep[cc] = delta[di[f + cc]];
   __syncthreads();
   for (int i = tid; i < f; i += 256) {
@@ -496,11 +620,28 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
     x[i] = r;
   }
   __syncthreads();
-  for (int i = f - 1; i >= 0; i--) {
-    if (tid == 0) x[i] = x[i] / M[i + (size_t)i * n];
+  for (int b1 = f; b1 > 0; b1 -= 32) {
+    const int b0 = b1 > 32 ? b1 - 32 : 0, nb = b1 - b0;
+    for (int e = tid; e < nb * nb; e += 256) {
+      const int i = e % nb, j = e / nb;
+      Dg[i][j] = (i <= j) ? M[(b0 + i) + (size_t)(b0 + j) * n] : 0.0;
+    }
     __syncthreads();
-    const double xi = x[i];
-    for (int k = tid; k < i; k += 256) x[k] -= M[k + (size_t)i * n] * xi;
+    if (warp == 0) {
+      double xv = lane < nb ? x[b0 + lane] : 0.0;
+      for (int k = nb - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(0xffffffffu, xv, k) / Dg[k][k];
+        if (lane == k) xv = xk;
+        else if (lane < k) xv -= Dg[lane][k] * xk;
+      }
+      if (lane < nb) x[b0 + lane] = xv;
+    }
+    __syncthreads();
+    for (int i = tid; i < b0; i += 256) {
+      double acc = 0;
+      for (int j = 0; j < nb; j++) acc += M[i + (size_t)(b0 + j) * n] * x[b0 + j];
+      x[i] -= acc;
+    }
     __syncthreads();
   }
   bool nan = false;
