@@ -1,0 +1,340 @@
+// B200Optimizers.cpp — see B200Optimizers.h.  Host glue only: packs the GTSAM
+// objects once, then every numeric step is a C-ABI call into libgtsam_b200.so.
+#include "B200Optimizers.h"
+
+#include <gtsam/geometry/Cal3Bundler.h>
+#include <gtsam/geometry/Cal3_S2.h>
+#include <gtsam/geometry/PinholeCamera.h>
+#include <gtsam/geometry/Pose3.h>
+#include <gtsam/linear/JacobianFactor.h>
+#include <gtsam/linear/linearExceptions.h>
+#include <gtsam/nonlinear/PriorFactor.h>
+#include <gtsam/nonlinear/internal/LevenbergMarquardtState.h>
+#include <gtsam/nonlinear/internal/NonlinearOptimizerState.h>
+#include <gtsam/slam/BetweenFactor.h>
+#include <gtsam/slam/GeneralSFMFactor.h>
+#include <gtsam/slam/ProjectionFactor.h>
+
+#include <cstdlib>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gtsam_b200.h"
+
+using namespace gtsam;
+
+namespace gtsam_b200 {
+
+typedef PinholeCamera<Cal3Bundler> BCam;
+typedef GenericProjectionFactor<Pose3, Point3, Cal3_S2> ProjFactor;
+typedef GeneralSFMFactor<BCam, Point3> SfmFactor;
+
+static void check(int rc, const char* what) {
+  if (rc == B200_OK) return;
+  throw std::runtime_error(std::string("gtsam_b200: ") + what + ": " + b200_last_error_string());
+}
+
+static void putPose(const Pose3& p, std::vector<double>& out) {
+  const Matrix3 R = p.rotation().matrix();
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out.push_back(R(i, j));
+  out.push_back(p.x()); out.push_back(p.y()); out.push_back(p.z());
+}
+static void putCam(const BCam& c, std::vector<double>& out) {
+  putPose(c.pose(), out);
+  const Cal3Bundler& k = c.calibration();
+  out.push_back(k.fx()); out.push_back(k.k1()); out.push_back(k.k2()); out.push_back(k.px()); out.push_back(k.py());
+}
+static Pose3 getPose(const double* x) {
+  Matrix3 R;
+  R << x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8];
+  return Pose3(Rot3(R), Point3(x[9], x[10], x[11]));
+}
+
+struct GroupBuf {
+  int type, noise_kind;
+  std::vector<int64_t> keys;
+  std::vector<double> meas, noise;
+  std::vector<int32_t> cal;
+  int64_t count = 0, gi0 = 0;
+};
+
+struct DeviceState {
+  std::vector<Key> id2key;
+  std::map<Key, int64_t> key2id;
+  std::vector<int32_t> var_type;
+  std::vector<int64_t> val_off, dof_off;
+  std::vector<GroupBuf> groups;
+  std::vector<double> cal;
+  b200_ctx* ctx = nullptr;
+  b200_problem* prob = nullptr;
+  b200_lm* lm = nullptr;
+
+  ~DeviceState() {
+    if (lm) b200_lm_destroy(lm);
+    if (prob) b200_problem_destroy(prob);
+    if (ctx) b200_ctx_destroy(ctx);
+  }
+
+  std::vector<double> packValues(const Values& values) {
+    std::vector<double> out;
+    for (Key k : id2key) {
+      const Value& v = values.at(k);
+      if (auto p = dynamic_cast<const GenericValue<Pose3>*>(&v)) putPose(p->value(), out);
+      else if (auto q = dynamic_cast<const GenericValue<Point3>*>(&v)) { out.push_back(q->value().x()); out.push_back(q->value().y()); out.push_back(q->value().z()); }
+      else if (auto c = dynamic_cast<const GenericValue<BCam>*>(&v)) putCam(c->value(), out);
+      else throw std::invalid_argument("gtsam_b200: unsupported Value type for key " + DefaultKeyFormatter(k));
+    }
+    return out;
+  }
+
+  Values unpackValues(const std::vector<double>& x) const {
+    Values out;
+    for (size_t i = 0; i < id2key.size(); i++) {
+      const double* v = x.data() + val_off[i];
+      switch (var_type[i]) {
+        case B200_VAR_POSE3: out.insert(id2key[i], getPose(v)); break;
+        case B200_VAR_POINT3: out.insert(id2key[i], Point3(v[0], v[1], v[2])); break;
+        case B200_VAR_CAM_BUNDLER: out.insert(id2key[i], BCam(getPose(v), Cal3Bundler(v[12], v[13], v[14], v[15], v[16]))); break;
+      }
+    }
+    return out;
+  }
+
+  // noise model -> (kind, payload); Constrained / Robust are rejected like an unsupported factor
+  static int noiseOf(const SharedNoiseModel& nm, int d, std::vector<double>& payload) {
+    payload.clear();
+    if (!nm || nm->isUnit()) return B200_NOISE_UNIT;
+    if (nm->isConstrained()) throw std::invalid_argument("gtsam_b200: Constrained noise models are out of scope (need QR)");
+    if (auto iso = std::dynamic_pointer_cast<noiseModel::Isotropic>(nm)) { payload.push_back(iso->sigma()); return B200_NOISE_ISOTROPIC; }
+    if (auto dg = std::dynamic_pointer_cast<noiseModel::Diagonal>(nm)) {
+      for (int i = 0; i < d; i++) payload.push_back(dg->sigma(i));
+      return B200_NOISE_DIAGONAL;
+    }
+    if (auto g = std::dynamic_pointer_cast<noiseModel::Gaussian>(nm)) {
+      const Matrix R = g->R();
+      for (int r = 0; r < d; r++) for (int c = 0; c < d; c++) payload.push_back(R(r, c));
+      return B200_NOISE_GAUSSIAN;
+    }
+    throw std::invalid_argument("gtsam_b200: unsupported noise model (Robust models are a 'next' row)");
+  }
+
+  void pack(const NonlinearFactorGraph& graph, const Values& values, const Ordering& ordering) {
+    // ids in ascending Key order == iteration order of Values (gtsam/nonlinear/Values.h:74-79)
+    for (const auto& kv : values) {
+      key2id[kv.key] = (int64_t)id2key.size();
+      id2key.push_back(kv.key);
+    }
+    val_off.assign(1, 0); dof_off.assign(1, 0);
+    for (Key k : id2key) {
+      const Value& v = values.at(k);
+      int t;
+      if (dynamic_cast<const GenericValue<Pose3>*>(&v)) t = B200_VAR_POSE3;
+      else if (dynamic_cast<const GenericValue<Point3>*>(&v)) t = B200_VAR_POINT3;
+      else if (dynamic_cast<const GenericValue<BCam>*>(&v)) t = B200_VAR_CAM_BUNDLER;
+      else throw std::invalid_argument("gtsam_b200: unsupported Value type for key " + DefaultKeyFormatter(k));
+      var_type.push_back(t);
+      val_off.push_back(val_off.back() + b200_var_storage(t));
+      dof_off.push_back(dof_off.back() + b200_var_dim(t));
+    }
+    std::map<const Cal3_S2*, int32_t> calIds;
+    std::vector<double> pay;
+    int64_t pos = 0;
+    for (const auto& f : graph) {
+      if (!f) throw std::invalid_argument("gtsam_b200: null factors are not supported");
+      int type, d;
+      std::vector<int64_t> keys;
+      std::vector<double> meas;
+      int32_t cal_id = 0;
+      SharedNoiseModel nm;
+      auto id = [&](Key k) {
+        auto it = key2id.find(k);
+        if (it == key2id.end()) throw ValuesKeyDoesNotExist("gtsam_b200 pack", k);
+        return it->second;
+      };
+      if (auto b = dynamic_cast<const BetweenFactor<Pose3>*>(f.get())) {
+        type = B200_FACTOR_BETWEEN_POSE3; keys = {id(b->key1()), id(b->key2())}; putPose(b->measured(), meas); nm = b->noiseModel();
+      } else if (auto p3 = dynamic_cast<const PriorFactor<Pose3>*>(f.get())) {
+        type = B200_FACTOR_PRIOR_POSE3; keys = {id(p3->key())}; putPose(p3->prior(), meas); nm = p3->noiseModel();
+      } else if (auto pp = dynamic_cast<const PriorFactor<Point3>*>(f.get())) {
+        type = B200_FACTOR_PRIOR_POINT3; keys = {id(pp->key())};
+        meas = {pp->prior().x(), pp->prior().y(), pp->prior().z()}; nm = pp->noiseModel();
+      } else if (auto pc = dynamic_cast<const PriorFactor<BCam>*>(f.get())) {
+        type = B200_FACTOR_PRIOR_CAM_BUNDLER; keys = {id(pc->key())}; putCam(pc->prior(), meas); nm = pc->noiseModel();
+      } else if (auto pj = dynamic_cast<const ProjFactor*>(f.get())) {
+        if (pj->body_P_sensor()) throw std::invalid_argument("gtsam_b200: body_P_sensor is a 'next' row");
+        type = B200_FACTOR_PROJECTION_CAL3S2; keys = {id(pj->key1()), id(pj->key2())};
+        meas = {pj->measured().x(), pj->measured().y()}; nm = pj->noiseModel();
+        const Cal3_S2* K = pj->calibration().get();
+        auto it = calIds.find(K);
+        if (it == calIds.end()) {
+          it = calIds.emplace(K, (int32_t)calIds.size()).first;
+          cal.insert(cal.end(), {K->fx(), K->fy(), K->skew(), K->px(), K->py()});
+        }
+        cal_id = it->second;
+      } else if (auto sf = dynamic_cast<const SfmFactor*>(f.get())) {
+        type = B200_FACTOR_SFM_BUNDLER; keys = {id(sf->key1()), id(sf->key2())};
+        meas = {sf->measured().x(), sf->measured().y()}; nm = sf->noiseModel();
+      } else {
+        throw std::invalid_argument("gtsam_b200: unsupported factor type at graph position " + std::to_string(pos) +
+                                    " (no CPU fallback; supported: Between<Pose3>, Prior<Pose3|Point3|SfmCamera>, "
+                                    "GenericProjectionFactor<Pose3,Point3,Cal3_S2>, GeneralSFMFactor<SfmCamera,Point3>)");
+      }
+      d = b200_factor_dim(type);
+      const int kind = noiseOf(nm, d, pay);
+      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind) {
+        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos;
+        groups.push_back(g);
+      }
+      GroupBuf& g = groups.back();
+      g.keys.insert(g.keys.end(), keys.begin(), keys.end());
+      g.meas.insert(g.meas.end(), meas.begin(), meas.end());
+      g.noise.insert(g.noise.end(), pay.begin(), pay.end());
+      g.cal.push_back(cal_id);
+      g.count++;
+      pos++;
+    }
+    // ---- C-ABI description ----
+    std::vector<int64_t> ord;
+    for (Key k : ordering) {
+      auto it = key2id.find(k);
+      if (it == key2id.end()) throw std::invalid_argument("gtsam_b200: ordering contains a key that is not in Values");
+      ord.push_back(it->second);
+    }
+    if (ord.size() != id2key.size()) throw std::invalid_argument("gtsam_b200: ordering must cover every variable");
+    std::vector<b200_factor_group> cg(groups.size());
+    for (size_t i = 0; i < groups.size(); i++) {
+      cg[i].type = groups[i].type; cg[i].noise_kind = groups[i].noise_kind;
+      cg[i].noise_per_factor = groups[i].noise_kind != B200_NOISE_UNIT && groups[i].count > 1;
+      cg[i].reserved = 0; cg[i].count = groups[i].count; cg[i].graph_index0 = groups[i].gi0;
+      cg[i].keys = groups[i].keys.data(); cg[i].meas = groups[i].meas.data(); cg[i].noise = groups[i].noise.data();
+      cg[i].cal_index = groups[i].type == B200_FACTOR_PROJECTION_CAL3S2 ? groups[i].cal.data() : nullptr;
+    }
+    const std::vector<double> packed = packValues(values);
+    b200_problem_desc desc;
+    desc.nvars = (int64_t)id2key.size(); desc.var_type = var_type.data(); desc.values = packed.data();
+    desc.ordering = ord.data(); desc.ncal = (int64_t)cal.size() / 5; desc.cal = cal.data();
+    desc.ngroups = (int64_t)cg.size(); desc.groups = cg.data();
+    const char* devEnv = std::getenv("B200_DEVICE");
+    check(b200_ctx_create(devEnv ? std::atoi(devEnv) : 0, &ctx), "b200_ctx_create");
+    check(b200_problem_create(ctx, &desc, &prob), "b200_problem_create");
+  }
+
+  Values currentValues() const {
+    std::vector<double> x((size_t)b200_values_size(prob));
+    check(b200_get_values(prob, x.data()), "b200_get_values");
+    return unpackValues(x);
+  }
+
+  VectorValues currentDelta() const {
+    std::vector<double> dl((size_t)b200_delta_size(prob));
+    check(b200_get_delta(prob, dl.data()), "b200_get_delta");
+    VectorValues out;
+    for (size_t i = 0; i < id2key.size(); i++)
+      out.insert(id2key[i], Eigen::Map<const Vector>(dl.data() + dof_off[i], dof_off[i + 1] - dof_off[i]));
+    return out;
+  }
+};
+
+static b200_lm_params toC(const LevenbergMarquardtParams& p) {
+  b200_lm_params c;
+  c.max_iterations = (int)p.maxIterations; c.relative_error_tol = p.relativeErrorTol;
+  c.absolute_error_tol = p.absoluteErrorTol; c.error_tol = p.errorTol; c.lambda_initial = p.lambdaInitial;
+  c.lambda_factor = p.lambdaFactor; c.lambda_upper_bound = p.lambdaUpperBound; c.lambda_lower_bound = p.lambdaLowerBound;
+  c.min_model_fidelity = p.minModelFidelity; c.diagonal_damping = p.diagonalDamping;
+  c.use_fixed_lambda_factor = p.useFixedLambdaFactor; c.min_diagonal = p.minDiagonal; c.max_diagonal = p.maxDiagonal;
+  return c;
+}
+
+// ---- Levenberg-Marquardt ---------------------------------------------------------
+B200LevenbergMarquardtOptimizer::B200LevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                                 const LevenbergMarquardtParams& params)
+    : LevenbergMarquardtOptimizer(graph, initialValues, params) { init(); }
+B200LevenbergMarquardtOptimizer::B200LevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                                 const Ordering& ordering, const LevenbergMarquardtParams& params)
+    : LevenbergMarquardtOptimizer(graph, initialValues, ordering, params) { init(); }
+B200LevenbergMarquardtOptimizer::~B200LevenbergMarquardtOptimizer() {}
+
+void B200LevenbergMarquardtOptimizer::init() {
+  dev_ = std::make_shared<DeviceState>();
+  dev_->pack(graph_, state_->values, *params_.ordering);  // ordering is always set by the base ctor
+  const b200_lm_params c = toC(params_);
+  check(b200_lm_create(dev_->prob, &c, &dev_->lm), "b200_lm_create");
+}
+
+GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::iterate() {
+  check(b200_lm_iterate(dev_->lm), "b200_lm_iterate");
+  b200_lm_state s;
+  b200_lm_get_state(dev_->lm, &s);
+  typedef internal::LevenbergMarquardtState State;
+  state_.reset(new State(dev_->currentValues(), s.error, s.lambda, s.current_factor, (unsigned)s.iterations,
+                         (unsigned)s.total_inner_iterations));
+  return GaussianFactorGraph::shared_ptr();
+}
+
+GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::linearize() const {
+  check(b200_linearize(dev_->prob), "b200_linearize");
+  size_t total = 0;
+  for (auto& g : dev_->groups) total = std::max<size_t>(total, (size_t)(g.gi0 + g.count));
+  std::vector<GaussianFactor::shared_ptr> out(total);
+  for (size_t gi = 0; gi < dev_->groups.size(); gi++) {
+    const GroupBuf& g = dev_->groups[gi];
+    const int d = b200_factor_dim(g.type), ar = b200_factor_arity(g.type);
+    int ncols = 1;
+    std::vector<int> dims;
+    for (int a = 0; a < ar; a++) { dims.push_back(b200_var_dim(dev_->var_type[g.keys[a]])); ncols += dims.back(); }
+    std::vector<double> J((size_t)g.count * d * ncols);
+    check(b200_get_jacobians(dev_->prob, (int64_t)gi, J.data()), "b200_get_jacobians");
+    for (int64_t i = 0; i < g.count; i++) {
+      Eigen::Map<const Matrix> Ab(J.data() + (size_t)i * d * ncols, d, ncols);
+      const Vector b = Ab.col(ncols - 1);
+      const Key k1 = dev_->id2key[g.keys[i * ar]];
+      if (ar == 1) out[g.gi0 + i] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), b);
+      else out[g.gi0 + i] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), dev_->id2key[g.keys[i * ar + 1]],
+                                                             Matrix(Ab.middleCols(dims[0], dims[1])), b);
+    }
+  }
+  auto gfg = std::make_shared<GaussianFactorGraph>();
+  for (auto& f : out) gfg->push_back(f);
+  return gfg;
+}
+
+long long B200LevenbergMarquardtOptimizer::launchCount() const { return b200_launch_count(dev_->ctx); }
+
+// ---- Gauss-Newton ------------------------------------------------------------------
+B200GaussNewtonOptimizer::B200GaussNewtonOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                   const GaussNewtonParams& params)
+    : GaussNewtonOptimizer(graph, initialValues, params) { init(); }
+B200GaussNewtonOptimizer::B200GaussNewtonOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                   const Ordering& ordering)
+    : GaussNewtonOptimizer(graph, initialValues, ordering) { init(); }
+B200GaussNewtonOptimizer::~B200GaussNewtonOptimizer() {}
+
+void B200GaussNewtonOptimizer::init() {
+  dev_ = std::make_shared<DeviceState>();
+  dev_->pack(graph_, state_->values, *params_.ordering);
+}
+
+GaussianFactorGraph::shared_ptr B200GaussNewtonOptimizer::iterate() {
+  double e = 0;
+  const int rc = b200_gn_iterate(dev_->prob, &e);
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(0);
+  check(rc, "b200_gn_iterate");
+  state_.reset(new internal::NonlinearOptimizerState(dev_->currentValues(), e, state_->iterations + 1));
+  return GaussianFactorGraph::shared_ptr();
+}
+
+VectorValues solveOnDevice(const NonlinearFactorGraph& graph, const Values& values, const Ordering& ordering, double lambda) {
+  DeviceState dev;
+  dev.pack(graph, values, ordering);
+  check(b200_linearize(dev.prob), "b200_linearize");
+  double e0, e1;
+  int64_t fv = -1;
+  const int rc = b200_solve(dev.prob, lambda, 0, 1e-6, 1e32, &e0, &e1, &fv);
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(fv >= 0 ? dev.id2key[(size_t)fv] : 0);
+  check(rc, "b200_solve");
+  return dev.currentDelta();
+}
+
+}  // namespace gtsam_b200

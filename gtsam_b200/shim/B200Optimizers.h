@@ -1,0 +1,76 @@
+/**
+ * B200Optimizers.h — the GTSAM-side drop-in: subclasses of the reference's own
+ * optimizers whose virtual seams run on the B200 through the C-ABI
+ * (include/gtsam_b200.h).  User code changes one type name:
+ *
+ *     gtsam::LevenbergMarquardtOptimizer lm(graph, initial, params);          // before
+ *     gtsam_b200::B200LevenbergMarquardtOptimizer lm(graph, initial, params);  // after
+ *     Values result = lm.optimize();
+ *
+ * Seams overridden (reference file:line):
+ *   - NonlinearOptimizer::iterate()            gtsam/nonlinear/NonlinearOptimizer.h:136
+ *     (LevenbergMarquardtOptimizer.cpp:273-308, GaussNewtonOptimizer.cpp:44-67):
+ *     linearize + damped multifrontal solve + retract + error stay on the device;
+ *   - LevenbergMarquardtOptimizer::linearize() gtsam/nonlinear/LevenbergMarquardtOptimizer.h:112-113:
+ *     returns the device linearization as whitened JacobianFactors (debug / parity).
+ * params(), lambda(), error(), values(), iterations(), getInnerIterations(),
+ * optimize(), iterationHook and verbosity behave as in the reference because
+ * the unmodified base-class loop (NonlinearOptimizer::defaultOptimize) drives iterate().
+ *
+ * Supported factors (anything else => std::invalid_argument, there is no CPU fallback):
+ * BetweenFactor<Pose3>, PriorFactor<Pose3|Point3|PinholeCamera<Cal3Bundler>>,
+ * GenericProjectionFactor<Pose3,Point3,Cal3_S2> (no body_P_sensor),
+ * GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>; noise models Unit,
+ * Isotropic, Diagonal, Gaussian (Constrained / Robust => std::invalid_argument).
+ */
+#pragma once
+#include <gtsam/nonlinear/GaussNewtonOptimizer.h>
+#include <gtsam/nonlinear/LevenbergMarquardtOptimizer.h>
+
+#include <memory>
+
+namespace gtsam_b200 {
+
+struct DeviceState;  // packed problem + C-ABI handles
+
+class B200LevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimizer {
+ public:
+  B200LevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                  const gtsam::LevenbergMarquardtParams& params = gtsam::LevenbergMarquardtParams());
+  B200LevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                  const gtsam::Ordering& ordering,
+                                  const gtsam::LevenbergMarquardtParams& params = gtsam::LevenbergMarquardtParams());
+  ~B200LevenbergMarquardtOptimizer() override;
+
+  /// One LM iteration on the device.  Returns nullptr: the linear graph stays in HBM
+  /// (call linearize() to materialise it on the host).
+  gtsam::GaussianFactorGraph::shared_ptr iterate() override;
+  gtsam::GaussianFactorGraph::shared_ptr linearize() const override;
+  /// kernels launched so far (evidence that the device path ran)
+  long long launchCount() const;
+
+ private:
+  void init();
+  std::shared_ptr<DeviceState> dev_;
+};
+
+class B200GaussNewtonOptimizer : public gtsam::GaussNewtonOptimizer {
+ public:
+  B200GaussNewtonOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                           const gtsam::GaussNewtonParams& params = gtsam::GaussNewtonParams());
+  B200GaussNewtonOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                           const gtsam::Ordering& ordering);
+  ~B200GaussNewtonOptimizer() override;
+  gtsam::GaussianFactorGraph::shared_ptr iterate() override;
+
+ private:
+  void init();
+  std::shared_ptr<DeviceState> dev_;
+};
+
+/// GaussianFactorGraph::optimize-level entry for the nonlinear graph at `values`:
+/// one undamped (lambda = 0) or damped linearize + multifrontal solve on the device.
+gtsam::VectorValues solveOnDevice(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& values,
+                                  const gtsam::Ordering& ordering, double lambda = 0.0);
+
+}  // namespace gtsam_b200
