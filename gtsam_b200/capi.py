@@ -30,7 +30,8 @@ EXPORTS = [
     "b200_get_conditional", "b200_shared_front_buffer", "b200_save_values", "b200_restore_values",
     "b200_synchronize", "b200_profile_enable", "b200_profile_phase_count", "b200_profile_phase_name",
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
-    "b200_symbolic_get_cliques", "b200_symbolic_get_levels",
+    "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
+    "b200_shard_plan",
 ]
 
 
@@ -101,6 +102,12 @@ def lib():
         L.b200_profile_phase_name.argtypes = [C.c_int]
         L.b200_profile_phase_name.restype = C.c_char_p
         L.b200_profile_get.argtypes = [vp, dp, ip]
+        L.b200_nccl_unique_id.argtypes = [C.c_char_p]
+        L.b200_ctx_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+        L.b200_shard_plan.argtypes = [C.POINTER(P.CProblemDesc), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.b200_symbolic_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(vp)]
+        L.b200_symbolic_destroy.argtypes = [vp]
+        L.b200_symbolic_get_info.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
         _LIB = L
     return _LIB
 
@@ -118,6 +125,30 @@ def _check(rc):
         raise B200Error(rc, lib().b200_last_error_string().decode())
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (rank 0 creates it; ship it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+def shard_plan(prob: P.Problem, world: int):
+    """(clique_owner, factor_owner) of the sharding b200_problem_create applies at `world`
+    ranks; host only (no GPU needed).  clique_owner = -1 for the replicated top."""
+    L = lib()
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    _check(L.b200_symbolic_create(C.byref(desc), C.byref(h)))
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info(h, C.byref(info))
+    L.b200_symbolic_destroy(h)
+    co = np.zeros(max(1, info.ncliques), dtype=np.int32)
+    fo = np.zeros(max(1, prob.nfactors), dtype=np.int32)
+    _check(L.b200_shard_plan(C.byref(desc), world, co.ctypes.data_as(C.POINTER(C.c_int32)),
+                             fo.ctypes.data_as(C.POINTER(C.c_int32))))
+    return co[:info.ncliques], fo[:prob.nfactors]
+
+
 class Context:
     """One CUDA device + stream (b200_ctx)."""
 
@@ -127,7 +158,13 @@ class Context:
         _check(self.L.b200_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self.rank, self.world = 0, 1
         self._problems = weakref.WeakSet()
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the NCCL communicator (one process per GPU); call before creating problems."""
+        _check(self.L.b200_ctx_comm_init(self.h, unique_id, rank, world))
+        self.rank, self.world = rank, world
 
     def launch_count(self) -> int:
         return int(self.L.b200_launch_count(self.h))

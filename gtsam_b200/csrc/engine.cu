@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <limits>
 
@@ -73,7 +74,7 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
-             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_COUNT };
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_COUNT };
 struct PhaseScope {
   b200_problem* p; int ph; size_t idx; bool on;
   PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
@@ -101,6 +102,9 @@ static void resolve_profile(b200_problem* p) {  // call after a stream sync
   p->ev_used = 0;
 }
 
+static int allreduce_sum(b200_problem* p, double* buf, size_t n);
+static int allreduce_min_int(b200_problem* p, int* buf, size_t n);
+
 static int reduce_blocks(int64_t count, int threads, int sm) {
   int64_t b = (count + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm * 8));
@@ -121,7 +125,7 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
   }
   if (first) B200_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), st));
   B200_CUDA(cudaGetLastError());
-  return B200_OK;
+  return allreduce_sum(p, slot, 1);   // sharded: partial sums over the rank's own factors
 }
 
 static int enqueue_linearize(b200_problem* p) {
@@ -148,7 +152,7 @@ static int enqueue_hdiag(b200_problem* p) {
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
-  return B200_OK;
+  return allreduce_sum(p, p->d_hdiag, (size_t)p->ndelta);
 }
 
 // assemble + damp + eliminate + back-substitute + linear errors; no host sync
@@ -172,6 +176,7 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   if (lambda > 0) {
     PhaseScope ps(p, PH_DAMP);
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
+    if (ctx->rank == 0)   // the shared top is summed over ranks: its damping priors are added once
     damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
     ctx->launches++;
@@ -185,6 +190,13 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
                                                           p->d_fused_fac, lambda, (lambda > 0 && diagonal) ? p->d_hdiag : nullptr,
                                                           min_diag, max_diag, p->d_scalars);
     ctx->launches++;
+  }
+  if (ctx->world > 1) {
+    // the one exchange step of the solve — sum the Schur complements every rank
+    // accumulated into its copy of the shared top fronts (NCCL over NVLink, in place, on-stream)
+    PhaseScope ps(p, PH_ALLREDUCE);
+    const int rc = allreduce_sum(p, p->d_arena, (size_t)p->zero_doubles);
+    if (rc) return rc;
   }
   // ---- elimination, leaves to roots ----
   for (size_t l = 0; l < p->levels.size(); l++) {
@@ -248,7 +260,14 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     ctx->launches += 3;
     first = false;
   }
+  if (first) B200_CUDA(cudaMemsetAsync(&p->d_scalars->lin_err0, 0, 2 * sizeof(double), st));
   B200_CUDA(cudaGetLastError());
+  if (ctx->world > 1) {
+    int rc = allreduce_sum(p, &p->d_scalars->lin_err0, 2);          // lin_err0, lin_err_delta are adjacent
+    if (rc) return rc;
+    rc = allreduce_min_int(p, &p->d_scalars->fail_clique, 2);        // every rank takes the same decision
+    if (rc) return rc;
+  }
   p->solved = true;
   p->factored = true;
   return B200_OK;
@@ -351,6 +370,82 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
   return B200_OK;
 }
 
+// ---- sharding plan ------------------------------------------------------
+// Which leaf cliques take the fused path, and which rank owns each of them.  Fused leaf
+// cliques (+ their factors and frontal variables) are partitioned over the ranks in clique
+// order, balanced by factor count; every other clique is the shared "top" of the tree,
+// replicated on all ranks; factors owned by top cliques belong to rank 0.
+static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int world, std::vector<char>* fused,
+                       std::vector<int>* clique_owner, std::vector<int>* factor_owner) {
+  const bool leaf_path = ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
+  fused->assign(S.ncliques, 0);
+  for (int64_t c = 0; c < S.ncliques; c++) {
+    const int64_t nn = S.nf[c] + S.ns[c] + 1;
+    if (leaf_path && S.level[c] == 0 && S.nf[c] <= kLeafMaxF && (int64_t)S.nf[c] * nn <= kLeafMaxFN) (*fused)[c] = 1;
+  }
+  std::vector<int64_t> nfac(S.ncliques, 0);
+  int64_t leaf_total = 0;
+  for (int64_t pos = 0; pos < total; pos++)
+    if ((*fused)[S.fac_clique[pos]]) { nfac[S.fac_clique[pos]]++; leaf_total++; }
+  clique_owner->assign(S.ncliques, -1);
+  int64_t prefix = 0;
+  for (int64_t c = 0; c < S.ncliques; c++) {
+    if (!(*fused)[c]) continue;
+    (*clique_owner)[c] = leaf_total ? (int)std::min<int64_t>(world - 1, prefix * world / leaf_total) : 0;
+    prefix += nfac[c];
+  }
+  factor_owner->assign(total, 0);
+  for (int64_t pos = 0; pos < total; pos++) {
+    const int o = (*clique_owner)[S.fac_clique[pos]];
+    (*factor_owner)[pos] = o < 0 ? 0 : o;
+  }
+}
+
+// ---- NCCL, loaded lazily so the single-GPU path never needs it ------------------------
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, ncclUniqueIdBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return B200_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error(std::string("cannot load libnccl.so.2: ") + dlerror()); return B200_NCCL_ERROR; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, ncclUniqueIdBlob, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { set_error("libnccl.so.2 lacks required symbols"); return B200_NCCL_ERROR; }
+  g_nccl.h = h;
+  return B200_OK;
+}
+enum { kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3 };  // ncclDataType_t / ncclRedOp_t (nccl.h)
+#define B200_NCCL(call)                                                                              \
+  do {                                                                                               \
+    int r_ = (call);                                                                                 \
+    if (r_ != 0) {                                                                                   \
+      set_error(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+      return B200_NCCL_ERROR;                                                                        \
+    }                                                                                                \
+  } while (0)
+static int allreduce_sum(b200_problem* p, double* buf, size_t n) {
+  if (p->ctx->world <= 1 || n == 0) return B200_OK;
+  B200_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, p->ctx->comm, p->ctx->stream));
+  p->ctx->launches++;
+  return B200_OK;
+}
+static int allreduce_min_int(b200_problem* p, int* buf, size_t n) {
+  if (p->ctx->world <= 1) return B200_OK;
+  B200_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclInt32, kNcclMin, p->ctx->comm, p->ctx->stream));
+  p->ctx->launches++;
+  return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -385,9 +480,28 @@ int b200_ctx_create(int device, b200_ctx** out) {
   *out = c;
   return B200_OK;
 }
+int b200_nccl_unique_id(void* out128) {
+  const int rc = nccl_load();
+  if (rc) return rc;
+  B200_NCCL(g_nccl.GetUniqueId(out128));
+  return B200_OK;
+}
+int b200_ctx_comm_init(b200_ctx* c, const void* id128, int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return B200_INVALID_ARGUMENT; }
+  c->rank = rank; c->world = world;
+  if (world == 1) return B200_OK;
+  const int rc = nccl_load();
+  if (rc) return rc;
+  B200_CUDA(cudaSetDevice(c->device));
+  ncclUniqueIdBlob id;
+  memcpy(&id, id128, sizeof id);
+  B200_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  return B200_OK;
+}
 int b200_ctx_destroy(b200_ctx* c) {
   if (!c) return B200_OK;
   cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaStreamDestroy(c->stream);
   delete c;
   return B200_OK;
@@ -453,17 +567,14 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   UP(upload(&p->d_var_dof, var_dof, st));
   UP(upload(&p->d_var_type, p->var_type, st));
   UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
-  // ---- storage plan: fused leaf cliques keep only their f x n conditional -------------
-  const bool leaf_path = d->ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
-  std::vector<char> fused(S.ncliques, 0);
-  std::vector<int> fused_list;
-  for (int64_t c = 0; c < S.ncliques; c++) {
-    const int64_t nn = S.nf[c] + S.ns[c] + 1;
-    if (leaf_path && S.level[c] == 0 && S.nf[c] <= kLeafMaxF && (int64_t)S.nf[c] * nn <= kLeafMaxFN) {
-      fused[c] = 1;
-      fused_list.push_back((int)c);
-    }
-  }
+  // ---- storage plan: fused leaf cliques keep only their f x n conditional; sharding -----
+  std::vector<char> fused;
+  std::vector<int> clique_owner, factor_owner;
+  shard_plan(S, d->ngroups, total, ctx->world, &fused, &clique_owner, &factor_owner);
+  const int rank = ctx->rank;
+  std::vector<int> fused_list;   // the fused leaf cliques THIS rank owns
+  for (int64_t c = 0; c < S.ncliques; c++)
+    if (fused[c] && clique_owner[c] == rank) fused_list.push_back((int)c);
   p->n_fused = (int)fused_list.size();
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
@@ -483,23 +594,33 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   for (int64_t gi = 0; gi < d->ngroups; gi++) {
     const b200_factor_group& s = d->groups[gi];
     auto& g = p->groups[gi];
-    hkeys[gi].resize(s.count);
-    hscat[gi].resize(s.count);
-    for (int64_t i = 0; i < s.count; i++) {
-      const int64_t pos = g.gi0 + i;
-      hkeys[gi][i] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
+    // keep only the factors this rank owns (all of them when world == 1)
+    std::vector<int64_t>& keep = g.local_index;
+    for (int64_t i = 0; i < s.count; i++) if (factor_owner[g.gi0 + i] == rank) keep.push_back(i);
+    const int64_t nl = (int64_t)keep.size();
+    hkeys[gi].resize(nl);
+    hscat[gi].resize(nl);
+    std::vector<double> hmeas((size_t)nl * g.meas), hnoise;
+    std::vector<int> hcal;
+    if (s.noise_per_factor) hnoise.resize((size_t)nl * g.noise_size);
+    for (int64_t li = 0; li < nl; li++) {
+      const int64_t i = keep[li], pos = g.gi0 + i;
+      hkeys[gi][li] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
       const int isleaf = fused[S.fac_clique[pos]];
-      hscat[gi][i] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
+      hscat[gi][li] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
       if (!isleaf) g.n_nonleaf++;
+      memcpy(hmeas.data() + (size_t)li * g.meas, s.meas + (size_t)i * g.meas, (size_t)g.meas * sizeof(double));
+      if (s.noise_per_factor) memcpy(hnoise.data() + (size_t)li * g.noise_size, s.noise + (size_t)i * g.noise_size, (size_t)g.noise_size * sizeof(double));
+      if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.cal_index) hcal.push_back(s.cal_index[i]);
     }
+    g.count = nl;
     UP(upload(&g.d_keys, hkeys[gi], st));
     UP(upload(&g.d_scat, hscat[gi], st));
-    UP(upload(&g.d_meas, s.meas, (size_t)s.count * g.meas, st));
-    UP(upload(&g.d_noise, s.noise, (size_t)g.noise_size * (s.noise_per_factor ? s.count : 1), st));
-    if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.cal_index) {
-      UP(upload(&g.d_cal, s.cal_index, (size_t)s.count, st));
-    }
-    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)s.count * g.d * g.ncols) * sizeof(double)));
+    UP(upload(&g.d_meas, hmeas, st));
+    if (s.noise_per_factor) UP(upload(&g.d_noise, hnoise, st));
+    else UP(upload(&g.d_noise, s.noise, (size_t)g.noise_size, st));
+    if (!hcal.empty()) UP(upload(&g.d_cal, hcal, st));
+    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)nl * g.d * g.ncols) * sizeof(double)));
   }
   // ---- junction tree tables ----
   std::vector<int> parent32(S.ncliques);
@@ -525,19 +646,19 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   if (p->n_fused) {
     std::vector<int> lpos(S.ncliques, -1), fptr(p->n_fused + 1, 0);
     for (int i = 0; i < p->n_fused; i++) lpos[fused_list[i]] = i;
-    for (int64_t pos = 0; pos < total; pos++) if (fused[S.fac_clique[pos]]) fptr[lpos[S.fac_clique[pos]] + 1]++;
+    for (int64_t pos = 0; pos < total; pos++) if (lpos[S.fac_clique[pos]] >= 0) fptr[lpos[S.fac_clique[pos]] + 1]++;
     for (int i = 0; i < p->n_fused; i++) fptr[i + 1] += fptr[i];
     std::vector<int2> ffac(fptr[p->n_fused]);
     std::vector<int> cur(fptr.begin(), fptr.end() - 1);
     for (int64_t gi = 0; gi < d->ngroups; gi++)
-      for (int64_t i = 0; i < p->groups[gi].count; i++) {
-        const int64_t pos = p->groups[gi].gi0 + i;
-        if (fused[S.fac_clique[pos]]) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)i);
+      for (int64_t li = 0; li < p->groups[gi].count; li++) {
+        const int64_t pos = p->groups[gi].gi0 + p->groups[gi].local_index[li];
+        if (lpos[S.fac_clique[pos]] >= 0) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)li);
       }
     // keep graph order inside each clique (groups may interleave in the graph)
     for (int i = 0; i < p->n_fused; i++)
       std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) {
-        return p->groups[a.x].gi0 + a.y < p->groups[b.x].gi0 + b.y; });
+        return p->groups[a.x].gi0 + p->groups[a.x].local_index[a.y] < p->groups[b.x].gi0 + p->groups[b.x].local_index[b.y]; });
     UP(upload(&p->d_fused_list, fused_list, st));
     UP(upload(&p->d_fused_fac_ptr, fptr, st));
     UP(upload(&p->d_fused_fac, ffac, st));
@@ -556,7 +677,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
       if (fused[c]) {
-        bsmall.push_back(c);   // eliminated by leaf_fused_kernel; back-substituted one warp per clique
+        // eliminated by leaf_fused_kernel on the owning rank; back-substituted one warp per clique
+        if (clique_owner[c] == rank) bsmall.push_back(c);
       } else if (nn <= kSmallMaxN) {
         small.push_back(c);
         bsmall.push_back(c);
@@ -722,7 +844,7 @@ int b200_profile_phase_count(void) { return PH_COUNT; }
 const char* b200_profile_phase_name(int i) {
   static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
                                         "eliminate_large", "back_substitute", "linear_error", "retract", "error",
-                                        "leaf_fused"};
+                                        "leaf_fused", "allreduce_top"};
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {
@@ -796,10 +918,25 @@ int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level) {
   return B200_OK;
 }
 
+/* Host-only: the sharding plan problem creation uses at `world` ranks.
+ * clique_owner[c] = owning rank of a fused leaf clique, -1 for the replicated top;
+ * factor_owner[pos] = rank that linearizes the factor at graph position pos. */
+int b200_shard_plan(const b200_problem_desc* d, int world, int32_t* clique_owner, int32_t* factor_owner) {
+  if (world < 1) { set_error("world < 1"); return B200_INVALID_ARGUMENT; }
+  Packed pk;
+  const int rc = pack_and_symbolic(d, &pk);
+  if (rc) return rc;
+  std::vector<char> fused;
+  std::vector<int> co, fo;
+  shard_plan(pk.sym, d->ngroups, pk.total, world, &fused, &co, &fo);
+  for (size_t c = 0; c < co.size(); c++) clique_owner[c] = co[c];
+  for (size_t i = 0; i < fo.size(); i++) factor_owner[i] = fo[i];
+  return B200_OK;
+}
+
 int b200_shared_front_buffer(b200_problem* p, void** ptr, int64_t* nd) {
-  (void)p; *ptr = nullptr; *nd = 0;
-  set_error("multi-GPU sharding not built yet in this round");
-  return B200_INVALID_ARGUMENT;
+  *ptr = p->d_arena; *nd = p->zero_doubles;   // the replicated top fronts = the all-reduced region
+  return B200_OK;
 }
 
 // ---- LM / GN host control (a17, a18) -----------------------------------------------

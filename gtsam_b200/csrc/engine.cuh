@@ -69,7 +69,11 @@ struct LevelPlan {
 
 }  // namespace b200
 
+namespace b200 { struct ncclUniqueIdBlob { char internal[128]; }; }
+
 struct b200_ctx {
+  int rank = 0, world = 1;   // one process per GPU; world > 1 after b200_ctx_comm_init
+  void* comm = nullptr;      // ncclComm_t
   int device = 0;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
@@ -92,6 +96,7 @@ struct b200_problem {
     double* d_J = nullptr;
     int4* d_scat = nullptr;
     int64_t n_nonleaf = 0;   // factors NOT owned by a fused leaf clique
+    std::vector<int64_t> local_index;  // index in the caller's group of every factor kept on this rank
   };
   std::vector<Group> groups;
   // device state

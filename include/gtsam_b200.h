@@ -270,7 +270,19 @@ int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level); /* nclique
  * (gtsam/linear/HessianFactor.cpp:459-487), nf x (nf+ns+1) column-major. */
 int b200_get_conditional(b200_problem* prob, int64_t clique, double* out);
 
-/* Multi-GPU: the dense frontal storage of the cliques that are
+/* Multi-GPU, one process per GPU.  Rank 0 calls b200_nccl_unique_id and
+ * ships the 128 bytes to the other ranks (torch.distributed / MPI / a file); every rank then
+ * calls b200_ctx_comm_init BEFORE b200_problem_create.  The problem description is the
+ * full graph on every rank; each rank keeps the fused leaf cliques (BAL points) it owns and
+ * their factors, the top of the tree is replicated.  Per solve there is ONE exchange step:
+ * an in-place ncclAllReduce (FP64 sum, NVLink) of the top fronts, plus a 2-double / 2-int
+ * all-reduce of the scalars LM branches on.  b200_get_values returns this rank's view
+ * (owned leaf variables + the replicated top variables are current). */
+int b200_nccl_unique_id(void* out128);
+int b200_ctx_comm_init(b200_ctx* ctx, const void* id128, int rank, int world);
+int b200_shard_plan(const b200_problem_desc* desc, int world, int32_t* clique_owner, int32_t* factor_owner);
+
+/* The dense frontal storage of the cliques that are
  * shared between ranks (the top of the tree) as one contiguous device buffer,
  * so the caller's communicator (NCCL via torch.distributed) can sum it between
  * "eliminate local subtrees" and "eliminate shared top".  See DESIGN.md. */
