@@ -103,7 +103,7 @@ static void resolve_profile(b200_problem* p) {  // call after a stream sync
 }
 
 static int allreduce_sum(b200_problem* p, double* buf, size_t n);
-static int allreduce_min_int(b200_problem* p, int* buf, size_t n);
+static int allreduce_max_int(b200_problem* p, int* buf, size_t n);
 
 static int reduce_blocks(int64_t count, int threads, int sm) {
   int64_t b = (count + threads - 1) / threads;
@@ -156,7 +156,8 @@ static int enqueue_hdiag(b200_problem* p) {
 }
 
 // assemble + damp + eliminate + back-substitute + linear errors; no host sync
-static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double min_diag, double max_diag) {
+// lambda lives in p->d_lambda (written by the caller); `damped` only says whether lambda > 0 may occur
+static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_diag, double max_diag) {
   cudaStream_t st = p->ctx->stream;
   b200_ctx* ctx = p->ctx;
   const TreeView t = tview(p);
@@ -173,11 +174,11 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
       ctx->launches++;
     }
   }
-  if (lambda > 0) {
+  if (damped) {
     PhaseScope ps(p, PH_DAMP);
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
     if (ctx->rank == 0)   // the shared top is summed over ranks: its damping priors are added once
-    damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, lambda,
+    damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, p->d_lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
     ctx->launches++;
   }
@@ -187,7 +188,7 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     for (size_t gi = 0; gi < p->groups.size(); gi++) gt.g[gi] = view(p->groups[gi]);
     const int nb = (p->n_fused + kWarpsPerBlock - 1) / kWarpsPerBlock;
     leaf_fused_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, gt, p->d_fused_list, p->n_fused, p->d_fused_fac_ptr,
-                                                          p->d_fused_fac, lambda, (lambda > 0 && diagonal) ? p->d_hdiag : nullptr,
+                                                          p->d_fused_fac, p->d_lambda, (damped && diagonal) ? p->d_hdiag : nullptr,
                                                           min_diag, max_diag, p->d_scalars);
     ctx->launches++;
   }
@@ -212,15 +213,31 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     if (L.large_count) {
       PhaseScope ps(p, PH_ELIM_LARGE);
       const int* list = p->d_lvl_large + L.large_begin;
-      for (int k0 = 0; k0 < L.large_max_nf; k0 += kNB) {
-        potrf_trsm_kernel<<<L.large_count, 256, 0, st>>>(t, list, k0, p->d_scalars);
-        const int m = L.large_max_n - k0 - 1;
-        if (m > 0) {
-          const int T = (m + kTile - 1) / kTile;
-          syrk_kernel<<<dim3(T * (T + 1) / 2, L.large_count), 256, 0, st>>>(t, list, k0);
+      const bool big = L.large_max_n >= 1024;   // big fronts: one K=128 trailing update per 128 columns
+      auto tiles = [](int rows, int cols, int T) {   // upper-trapezoid tile count
+        const int TR = (rows + T - 1) / T, TC = (cols + T - 1) / T;
+        int cnt = 0;
+        for (int ti = 0; ti < TR; ti++) cnt += std::max(0, TC - ti);
+        return std::max(1, cnt);
+      };
+      for (int K0 = 0; K0 < L.large_max_nf; K0 += kBig) {
+        for (int k0 = K0; k0 < std::min(K0 + kBig, L.large_max_nf); k0 += kNB) {
+          const int ncol = L.large_max_n - k0 - 1;
+          panel_kernel<<<dim3(std::max(1, (ncol + kTrsmCols - 1) / kTrsmCols), L.large_count), kTrsmCols, 0, st>>>(
+              t, list, k0, p->d_scalars, p->d_rdiag);
+          if (!big) {
+            update_kernel<64, 4><<<dim3(tiles(ncol, ncol, 64), L.large_count), 256, 0, st>>>(t, list, 0, K0, k0, p->d_rdiag);
+          } else {
+            const int rows = std::min(K0 + kBig, L.large_max_nf) - k0 - 1;
+            update_kernel<64, 4><<<dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count), 256, 0, st>>>(t, list, 1, K0, k0, p->d_rdiag);
+          }
+          ctx->launches += 2;
+        }
+        if (big) {
+          const int m = L.large_max_n - K0 - 1;
+          update_kernel<128, 8><<<dim3(tiles(m, m, 128), L.large_count), 256, 0, st>>>(t, list, 2, K0, 0, p->d_rdiag);
           ctx->launches++;
         }
-        ctx->launches++;
       }
       const int64_t w = L.large_max_ns + 1;
       const int gx = (int)std::min<int64_t>((w * w + 255) / 256, 4096);
@@ -229,13 +246,15 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
     }
   }
   // ---- back-substitution, roots to leaves ----
+  if (p->n_bs_flags) B200_CUDA(cudaMemsetAsync(p->d_bs_flags, 0, (size_t)p->n_bs_flags * sizeof(int), st));
   {
   PhaseScope ps(p, PH_BACKSUB);
   for (int l = (int)p->levels.size() - 1; l >= 0; l--) {
     const LevelPlan& L = p->levels[l];
     if (L.large_count) {
-      const size_t smem = (size_t)(L.large_max_nf + L.large_max_ns + 32 * 33) * sizeof(double);
-      backsub_large_kernel<<<L.large_count, 256, smem, st>>>(t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars);
+      const int nblk = (L.large_max_nf + kBsRows - 1) / kBsRows;
+      backsub_large_kernel<<<dim3(nblk, L.large_count), 256, 0, st>>>(t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars,
+                                                                      p->d_bs_flags, p->d_bs_flag_base, L.large_begin, 1);
       ctx->launches++;
     }
     if (L.bsmall_count) {
@@ -265,7 +284,7 @@ static int enqueue_solve(b200_problem* p, double lambda, int diagonal, double mi
   if (ctx->world > 1) {
     int rc = allreduce_sum(p, &p->d_scalars->lin_err0, 2);          // lin_err0, lin_err_delta are adjacent
     if (rc) return rc;
-    rc = allreduce_min_int(p, &p->d_scalars->fail_clique, 2);        // every rank takes the same decision
+    rc = allreduce_max_int(p, &p->d_scalars->fail_code, 2);          // every rank takes the same decision
     if (rc) return rc;
   }
   p->solved = true;
@@ -285,8 +304,12 @@ static int enqueue_try_step(b200_problem* p) {
 }
 
 static int reset_flags(b200_problem* p) {
-  static const int init[2] = {INT_MAX, INT_MAX};
-  B200_CUDA(cudaMemcpyAsync(&p->d_scalars->fail_clique, init, 2 * sizeof(int), cudaMemcpyHostToDevice, p->ctx->stream));
+  B200_CUDA(cudaMemsetAsync(&p->d_scalars->fail_code, 0, 2 * sizeof(int), p->ctx->stream));
+  return B200_OK;
+}
+static int set_lambda(b200_problem* p, double lambda) {
+  *p->h_lambda = lambda;
+  B200_CUDA(cudaMemcpyAsync(p->d_lambda, p->h_lambda, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
   return B200_OK;
 }
 static int fetch_scalars(b200_problem* p) {
@@ -298,8 +321,9 @@ static int fetch_scalars(b200_problem* p) {
 static int solve_status(const b200_problem* p, int64_t* fail_var) {
   const Scalars* s = p->h_scalars;
   // a failed factorisation poisons everything below it: report the Cholesky failure first
-  int c = s->fail_clique != INT_MAX ? s->fail_clique : s->nan_clique;
-  if (c == INT_MAX) { if (fail_var) *fail_var = -1; return B200_OK; }
+  const int code = s->fail_code ? s->fail_code : s->nan_code;
+  if (code == 0) { if (fail_var) *fail_var = -1; return B200_OK; }
+  const int c = INT_MAX - code;
   if (fail_var) *fail_var = p->sym.front_vars[p->sym.front_ptr[c]];
   return B200_INDETERMINATE;
 }
@@ -424,7 +448,7 @@ static int nccl_load() {
   g_nccl.h = h;
   return B200_OK;
 }
-enum { kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3 };  // ncclDataType_t / ncclRedOp_t (nccl.h)
+enum { kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };  // ncclDataType_t / ncclRedOp_t (nccl.h)
 #define B200_NCCL(call)                                                                              \
   do {                                                                                               \
     int r_ = (call);                                                                                 \
@@ -439,10 +463,51 @@ static int allreduce_sum(b200_problem* p, double* buf, size_t n) {
   p->ctx->launches++;
   return B200_OK;
 }
-static int allreduce_min_int(b200_problem* p, int* buf, size_t n) {
+static int allreduce_max_int(b200_problem* p, int* buf, size_t n) {
   if (p->ctx->world <= 1) return B200_OK;
-  B200_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclInt32, kNcclMin, p->ctx->comm, p->ctx->stream));
+  B200_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclInt32, kNcclMax, p->ctx->comm, p->ctx->stream));
   p->ctx->launches++;
+  return B200_OK;
+}
+
+// One LM try = flags reset + damped solve + (speculative) retract + error.  The launch
+// sequence does not depend on lambda (device resident), so it is captured once into a CUDA
+// graph per problem and replayed: ~100-300 small kernels per try would otherwise be bound by
+// the host's launch rate, not by the GPU.  Eager when profiling (phase timers), when sharded
+// (NCCL on-stream) or when B200_NO_GRAPH is set.
+static int enqueue_try(b200_problem* p, int diagonal, double min_diag, double max_diag) {
+  int rc = reset_flags(p);
+  if (rc) return rc;
+  rc = enqueue_solve(p, true, diagonal, min_diag, max_diag);
+  if (rc) return rc;
+  return enqueue_try_step(p);
+}
+static int launch_try(b200_problem* p, int diagonal, double min_diag, double max_diag) {
+  static const bool no_graph = getenv("B200_NO_GRAPH") != nullptr;
+  if (no_graph || p->profile || p->ctx->world > 1) return enqueue_try(p, diagonal, min_diag, max_diag);
+  const int key = diagonal ? 1 : 0;
+  if (p->try_graph[key] && (p->graph_min_diag != min_diag || p->graph_max_diag != max_diag)) {
+    cudaGraphExecDestroy(p->try_graph[key]);
+    p->try_graph[key] = nullptr;
+  }
+  if (!p->try_graph[key]) {
+    cudaStream_t st = p->ctx->stream;
+    const int64_t launches0 = p->ctx->launches;
+    B200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_try(p, diagonal, min_diag, max_diag);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return B200_CUDA_ERROR; }
+    B200_CUDA(cudaGraphInstantiate(&p->try_graph[key], graph, 0));
+    cudaGraphDestroy(graph);
+    p->graph_min_diag = min_diag; p->graph_max_diag = max_diag;
+    p->try_launches = p->ctx->launches - launches0;   // kernels inside one replay
+    p->ctx->launches = launches0;
+  }
+  B200_CUDA(cudaGraphLaunch(p->try_graph[key], p->ctx->stream));
+  p->ctx->launches += p->try_launches;
+  p->solved = p->factored = true;
   return B200_OK;
 }
 
@@ -476,7 +541,6 @@ int b200_ctx_create(int device, b200_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
-  B200_CUDA(cudaFuncSetAttribute(backsub_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   *out = c;
   return B200_OK;
 }
@@ -521,8 +585,10 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_ld);
+  cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_scalars);
-  cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned);
+  cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
+  for (int i = 0; i < 2; i++) if (p->try_graph[i]) cudaGraphExecDestroy(p->try_graph[i]);
   cudaFree(p->d_saved_values);
   for (auto& e : p->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete p;
@@ -693,12 +759,23 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     L.small_count = (int)small.size() - L.small_begin;
     L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
     L.large_count = (int)large.size() - L.large_begin;
-    if ((size_t)(L.large_max_nf + L.large_max_ns + 32 * 33) * sizeof(double) > 200 * 1024)
-      FAIL(B200_INVALID_ARGUMENT, "front too large for the single-CTA back-substitution of this build");
   }
   UP(upload(&p->d_lvl_small, small, st));
   UP(upload(&p->d_lvl_bsmall, bsmall, st));
   UP(upload(&p->d_lvl_large, large, st));
+  {
+    std::vector<int> fbase(large.size() + 1, 0);
+    for (size_t i = 0; i < large.size(); i++) fbase[i + 1] = fbase[i] + (S.nf[large[i]] + kBsRows - 1) / kBsRows;
+    UP(upload(&p->d_bs_flag_base, fbase, st));
+    p->n_bs_flags = fbase.back();
+    B200_CUDA(cudaMalloc((void**)&p->d_bs_flags, (size_t)std::max(1, fbase.back()) * sizeof(int)));
+    B200_CUDA(cudaMemsetAsync(p->d_bs_flags, 0, (size_t)std::max(1, fbase.back()) * sizeof(int), st));
+  }
+  {
+    int maxl = 1;
+    for (auto& L : p->levels) maxl = std::max(maxl, L.large_count);
+    B200_CUDA(cudaMalloc((void**)&p->d_rdiag, (size_t)maxl * kNB * kNB * sizeof(double)));
+  }
   // ---- arena + scratch ----
   B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, p->arena_doubles) * sizeof(double)));
   p->partial_cap = 2 * ctx->sm_count * 8;
@@ -706,6 +783,9 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   B200_CUDA(cudaMalloc((void**)&p->d_scalars, sizeof(Scalars)));
   B200_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(Scalars), st));
   B200_CUDA(cudaMallocHost((void**)&p->h_scalars, sizeof(Scalars)));
+  B200_CUDA(cudaMalloc((void**)&p->d_lambda, sizeof(double)));
+  B200_CUDA(cudaMemsetAsync(p->d_lambda, 0, sizeof(double), st));
+  B200_CUDA(cudaMallocHost((void**)&p->h_lambda, sizeof(double)));
   B200_CUDA(cudaMallocHost((void**)&p->h_pinned, std::max<int64_t>(1, std::max(p->nval, p->ndelta)) * sizeof(double)));
   B200_CUDA(cudaStreamSynchronize(st));
 #undef FAIL
@@ -779,7 +859,9 @@ int b200_solve(b200_problem* p, double lambda, int diagonal, double min_diag, do
   B200_CUDA(cudaSetDevice(p->ctx->device));
   int rc = reset_flags(p);
   if (rc) return rc;
-  rc = enqueue_solve(p, lambda, diagonal, min_diag, max_diag);
+  rc = set_lambda(p, lambda);
+  if (rc) return rc;
+  rc = enqueue_solve(p, lambda > 0, diagonal, min_diag, max_diag);
   if (rc) return rc;
   rc = fetch_scalars(p);
   if (rc) return rc;
@@ -809,7 +891,8 @@ int b200_try_step(b200_problem* p, double* new_error) {
 
 int b200_accept_step(b200_problem* p) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
-  std::swap(p->d_values, p->d_new_values);
+  // copy, not pointer swap: the captured CUDA graph of the LM try has the buffer roles baked in
+  B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_new_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
   p->linearized = p->solved = false;
   return B200_OK;
 }
@@ -986,11 +1069,9 @@ static int try_lambda(b200_lm* lm, int* done) {
   b200_problem* p = lm->prob;
   const b200_lm_params& P = lm->params;
   b200_lm_state& S = lm->state;
-  int rc = reset_flags(p);
+  int rc = set_lambda(p, S.lambda);
   if (rc) return rc;
-  rc = enqueue_solve(p, S.lambda, P.diagonal_damping, P.min_diagonal, P.max_diagonal);
-  if (rc) return rc;
-  rc = enqueue_try_step(p);  // computed speculatively; discarded when the step is invalid
+  rc = launch_try(p, P.diagonal_damping, P.min_diagonal, P.max_diagonal);  // solve + retract + error
   if (rc) return rc;
   rc = fetch_scalars(p);
   if (rc) return rc;
@@ -1082,7 +1163,9 @@ int b200_gn_iterate(b200_problem* p, double* new_error) {
   if (rc) return rc;
   rc = reset_flags(p);
   if (rc) return rc;
-  rc = enqueue_solve(p, 0.0, 0, 0, 0);
+  rc = set_lambda(p, 0.0);
+  if (rc) return rc;
+  rc = enqueue_solve(p, false, 0, 0, 0);
   if (rc) return rc;
   rc = enqueue_try_step(p);
   if (rc) return rc;

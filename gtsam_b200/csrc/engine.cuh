@@ -54,8 +54,8 @@ struct Scalars {           // device scalars fetched once per LM try
   double lin_err0;         // linear.error(0)
   double lin_err_delta;    // linear.error(delta)
   double new_error;        // graph.error(newValues)
-  int fail_clique;         // min clique id whose partial Cholesky failed (INT_MAX if none)
-  int nan_clique;          // min clique id with NaN in back-substitution
+  int fail_code;           // INT_MAX - (min clique id whose partial Cholesky failed); 0 = none
+  int nan_code;            // INT_MAX - (min clique id with NaN in back-substitution); 0 = none
   int pad[2];
 };
 
@@ -118,6 +118,14 @@ struct b200_problem {
   int64_t* d_diag_index = nullptr;  // per delta scalar: arena index of its diagonal entry
   int *d_lvl_small = nullptr, *d_lvl_large = nullptr, *d_lvl_bsmall = nullptr;
   std::vector<b200::LevelPlan> levels;
+  int *d_bs_flags = nullptr, *d_bs_flag_base = nullptr;  // publish flags of the multi-CTA back-substitution
+  int n_bs_flags = 0;
+  double* d_lambda = nullptr;       // lambda of the current try (device resident)
+  double* h_lambda = nullptr;       // pinned
+  cudaGraphExec_t try_graph[2] = {nullptr, nullptr};  // LM try (solve + retract + error), by diagonal flag
+  double graph_min_diag = 0, graph_max_diag = 0;
+  int64_t try_launches = 0;
+  double* d_rdiag = nullptr;        // factored diagonal blocks published by panel_kernel
   double* d_partials = nullptr;     // block partial sums
   int partial_cap = 0;
   b200::Scalars* d_scalars = nullptr;

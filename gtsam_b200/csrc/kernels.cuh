@@ -8,12 +8,12 @@
 //  hdiag_kernel       a10    hessianDiagonal
 //  elim_small_kernel  a13/14 one warp per clique: partial Cholesky in shared
 //                            memory + fused extend-add into the parent front
-//  potrf_trsm_kernel, syrk_kernel, extend_add_kernel   a13/14 for large fronts
+//  panel_kernel, update_kernel, extend_add_kernel   a13/14 for large fronts
 //  backsub_*_kernel   a15    x_F = R^-1 (d - S x_S), level by level
 //  linerr_kernel      a16    0.5*|A delta - b|^2 and 0.5*|b|^2
 //  retract_kernel     a9     x (+) delta per variable
 #pragma once
-#include <cooperative_groups.h>
+#include <climits>
 
 #include "engine.cuh"
 #include "factors.cuh"
@@ -223,10 +223,13 @@ __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __re
 }
 
 // damping priors of buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)
-__global__ void damp_kernel(double* arena, const int64_t* __restrict__ diag_index, int n, double lambda,
-                            const double* __restrict__ hdiag, double min_diag, double max_diag) {
+__global__ void damp_kernel(double* arena, const int64_t* __restrict__ diag_index, int n,
+                            const double* __restrict__ lambda_ptr, const double* __restrict__ hdiag, double min_diag,
+                            double max_diag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const double lambda = *lambda_ptr;   // device resident: the launch sequence is lambda independent (CUDA graph)
+  if (!(lambda > 0)) return;
   if (diag_index[i] < 0) return;  // variable of a fused leaf clique (damped inside leaf_fused_kernel)
   double a2 = 1.0;
   if (hdiag) {
@@ -281,7 +284,7 @@ elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_
   } else if (f == 1) {
     if (!(dexp(A[0]) > -12)) ok = false;
   }
-  if (!ok && lane == 0) atomicMin(&sc->fail_clique, c);
+  if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
   // conditional [R S d] back to the front (rows 0..f-1)
   for (int e = lane; e < f * n; e += 32) {
     const int i = e % f, j = e / f;
@@ -320,9 +323,10 @@ elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int count,
-                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, double lambda,
+                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
                   const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc) {
   __shared__ double sm[kWarpsPerBlock][kLeafMaxFN];
+  const double lambda = *lambda_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerBlock + warp;
   if (idx >= count) return;
@@ -391,7 +395,7 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int c
   } else if (f == 1) {
     if (!(dexp(LB[0]) > -12)) ok = false;
   }
-  if (!ok && lane == 0) atomicMin(&sc->fail_clique, c);
+  if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
   double* M = t.arena + t.off[c];  // compact conditional, column-major f x n
   for (int e = lane; e < f * n; e += 32) {
     const int i = e % f, j = e / f;
@@ -419,24 +423,32 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int c
 // row panel (one CTA per clique), (2) SYRK update of the trailing upper
 // triangle (grid of 64x64 tiles).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-potrf_trsm_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc) {
+// (1) panel kernel: every CTA re-factors the kNB x kNB diagonal block in shared memory from
+// the (fully updated, still unfactored) front, so no CTA waits for another and nobody reads a
+// half-written block; CTA 0 publishes R_kk to a side buffer (rdiag) and does the pivot checks;
+// then each CTA solves its kTrsmCols columns of the row panel (one thread per column).
+// The following update kernel copies rdiag into the front.
+constexpr int kTrsmCols = 128;
+
+__global__ void __launch_bounds__(kTrsmCols)
+panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, double* __restrict__ rdiag) {
   __shared__ double Dg[kNB][kNB + 1];
   __shared__ int bad;
-  const int c = list[blockIdx.x];
+  const int c = list[blockIdx.y];
   const int f = t.nf[c], n = f + t.ns[c] + 1;
   if (k0 >= f) return;
   const int nb = min(kNB, f - k0);
+  const int j0 = k0 + nb + blockIdx.x * kTrsmCols;
+  if (j0 >= n && blockIdx.x != 0) return;
   double* M = t.arena + t.off[c];
   const int tid = threadIdx.x;
   if (tid == 0) bad = 0;
-  for (int e = tid; e < nb * nb; e += 256) {
+  for (int e = tid; e < nb * nb; e += kTrsmCols) {
     const int i = e % nb, j = e / nb;
     Dg[i][j] = (i <= j) ? M[(k0 + i) + (size_t)(k0 + j) * n] : 0.0;
   }
   __syncthreads();
-  // unblocked upper Cholesky of the diagonal block (right-looking)
-  for (int k = 0; k < nb; k++) {
+  for (int k = 0; k < nb; k++) {  // unblocked right-looking Cholesky (upper) of the diagonal block
     const double piv = Dg[k][k];
     __syncthreads();
     if (tid == 0 && !(piv > 0.0)) bad = 1;
@@ -447,28 +459,28 @@ potrf_trsm_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc)
     }
     __syncthreads();
     const int w = nb - k - 1;
-    for (int e = tid; e < w * w; e += 256) {
+    for (int e = tid; e < w * w; e += kTrsmCols) {
       const int i = k + 1 + e % w, j = k + 1 + e / w;
       if (i <= j) Dg[i][j] -= Dg[k][i] * Dg[k][j];
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    if (k0 + nb == f) {  // last panel: underconstrained check on the last two pivots
-      if (f >= 2) {
-        const double r2 = nb >= 2 ? Dg[nb - 2][nb - 2] : M[(f - 2) + (size_t)(f - 2) * n];
-        if (!(dexp(r2) - dexp(Dg[nb - 1][nb - 1]) < 12)) bad = 1;
-      } else if (!(dexp(Dg[0][0]) > -12)) bad = 1;
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      if (k0 + nb == f) {  // last panel: underconstrained check on the last two pivots
+        if (f >= 2) {
+          const double r2 = nb >= 2 ? Dg[nb - 2][nb - 2] : M[(f - 2) + (size_t)(f - 2) * n];
+          if (!(dexp(r2) - dexp(Dg[nb - 1][nb - 1]) < 12)) bad = 1;
+        } else if (!(dexp(Dg[0][0]) > -12)) bad = 1;
+      }
+      if (bad) atomicMax(&sc->fail_code, INT_MAX - c);
     }
-    if (bad) atomicMin(&sc->fail_clique, c);
+    double* R = rdiag + (size_t)blockIdx.y * kNB * kNB;
+    for (int e = tid; e < nb * nb; e += kTrsmCols) R[e] = Dg[e % nb][e / nb];
   }
-  for (int e = tid; e < nb * nb; e += 256) {
-    const int i = e % nb, j = e / nb;
-    if (i <= j) M[(k0 + i) + (size_t)(k0 + j) * n] = Dg[i][j];
-  }
-  // TRSM: columns j >= k0+nb : x = R^-T a (forward substitution), thread per column
-  for (int j = k0 + nb + tid; j < n; j += 256) {
-    double* col = M + (k0) + (size_t)j * n;
+  const int j = j0 + tid;
+  if (j < n) {  // x = R_kk^-T a, forward substitution
+    double* col = M + k0 + (size_t)j * n;
     double x[kNB];
 #pragma unroll
     for (int p = 0; p < kNB; p++) x[p] = p < nb ? col[p] : 0.0;
@@ -488,57 +500,83 @@ potrf_trsm_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc)
   }
 }
 
-// C[i][j] -= sum_p P[p][i] P[p][j] for i<=j in the trailing block, 64x64 tiles
-__global__ void __launch_bounds__(256) syrk_kernel(TreeView t, const int* __restrict__ list, int k0) {
-  __shared__ double Pi[kNB][kTile + 1];
-  __shared__ double Pj[kNB][kTile + 1];
+// (2) update kernel: C[i][j] -= sum_{p in [pa,pb)} M[p][i] M[p][j] for rows i in [ia,ib),
+// columns j in [i, n), tiled TILE x TILE with RB x RB register blocking.  Modes:
+//   0 SIMPLE  pa=k0      pb=k0+kNB  rows [pb, n)             (small fronts: full update per panel)
+//   1 BAND    pa=k0      pb=k0+kNB  rows [pb, K0+kBig)       (rest of the current big panel only)
+//   2 TRAIL   pa=K0      pb=K0+kBig rows [pb, n)             (one K=kBig update per big panel)
+// The CTA with blockIdx.x == 0 also moves R_kk from rdiag into the front (modes 0 and 1).
+constexpr int kBig = 128;
+constexpr int kKC = 16;
+
+template <int TILE, int RB>
+__global__ void __launch_bounds__(256)
+update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0, const double* __restrict__ rdiag) {
+  __shared__ double Pi[kKC][TILE + 1];
+  __shared__ double Pj[kKC][TILE + 1];
   const int c = list[blockIdx.y];
   const int f = t.nf[c], n = f + t.ns[c] + 1;
-  if (k0 >= f) return;
-  const int nb = min(kNB, f - k0);
-  const int base = k0 + nb;
-  const int m = n - base;                       // trailing size
-  const int T = (m + kTile - 1) / kTile;
-  // linear tile id -> (ti <= tj)
-  int tid_lin = blockIdx.x;
-  if (tid_lin >= T * (T + 1) / 2) return;
-  int tj = 0;
-  while ((tj + 1) * (tj + 2) / 2 <= tid_lin) tj++;
-  const int ti = tid_lin - tj * (tj + 1) / 2;
   double* M = t.arena + t.off[c];
-  const int i0 = base + ti * kTile, j0 = base + tj * kTile;
   const int tid = threadIdx.x;
-  for (int e = tid; e < kNB * kTile; e += 256) {
-    const int p = e % kNB, cc = e / kNB;
-    const int gi = i0 + cc, gj = j0 + cc;
-    Pi[p][cc] = (p < nb && gi < n) ? M[(k0 + p) + (size_t)gi * n] : 0.0;
-    Pj[p][cc] = (p < nb && gj < n) ? M[(k0 + p) + (size_t)gj * n] : 0.0;
+  if (mode != 2) {
+    if (k0 >= f) return;
+    if (blockIdx.x == 0) {
+      const int nb = min(kNB, f - k0);
+      const double* R = rdiag + (size_t)blockIdx.y * kNB * kNB;
+      for (int e = tid; e < nb * nb; e += 256) {
+        const int i = e % nb, j = e / nb;
+        if (i <= j) M[(k0 + i) + (size_t)(k0 + j) * n] = R[e];
+      }
+    }
+  } else if (K0 >= f) {
+    return;
   }
-  __syncthreads();
+  const int pa = mode == 2 ? K0 : k0;
+  const int pb = mode == 2 ? min(K0 + kBig, f) : min(k0 + kNB, f);
+  const int ia = pb;
+  const int ib = mode == 1 ? min(K0 + kBig, f) : n;
+  if (ia >= ib) return;
+  const int TR = (ib - ia + TILE - 1) / TILE, TC = (n - ia + TILE - 1) / TILE;
+  int rem = blockIdx.x, ti = 0;
+  while (ti < TR && rem >= TC - ti) { rem -= TC - ti; ti++; }
+  if (ti >= TR) return;
+  const int tj = ti + rem;
+  const int i0 = ia + ti * TILE, j0 = ia + tj * TILE;
   const int tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  double acc[RB][RB];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int a = 0; a < RB; a++)
 #pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int p = 0; p < kNB; p++) {
-    double ai[4], bj[4];
+    for (int b = 0; b < RB; b++) acc[a][b] = 0.0;
+  for (int kk = pa; kk < pb; kk += kKC) {
+    for (int e = tid; e < kKC * TILE; e += 256) {
+      const int p = e % kKC, cc = e / kKC;
+      const int gi = i0 + cc, gj = j0 + cc;
+      const bool pv = kk + p < pb;
+      Pi[p][cc] = (pv && gi < ib) ? M[(kk + p) + (size_t)gi * n] : 0.0;
+      Pj[p][cc] = (pv && gj < n) ? M[(kk + p) + (size_t)gj * n] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < kKC; p++) {
+      double ai[RB], bj[RB];
 #pragma unroll
-    for (int a = 0; a < 4; a++) ai[a] = Pi[p][tx + 16 * a];
+      for (int a = 0; a < RB; a++) ai[a] = Pi[p][tx + 16 * a];
 #pragma unroll
-    for (int b = 0; b < 4; b++) bj[b] = Pj[p][ty + 16 * b];
+      for (int b = 0; b < RB; b++) bj[b] = Pj[p][ty + 16 * b];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+      for (int a = 0; a < RB; a++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] += ai[a] * bj[b];
+        for (int b = 0; b < RB; b++) acc[a][b] += ai[a] * bj[b];
+    }
+    __syncthreads();
   }
 #pragma unroll
-  for (int b = 0; b < 4; b++)
+  for (int b = 0; b < RB; b++)
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
+    for (int a = 0; a < RB; a++) {
       const int gi = i0 + tx + 16 * a, gj = j0 + ty + 16 * b;
-      if (gi < n && gj < n && gi <= gj) M[gi + (size_t)gj * n] -= acc[a][b];
+      if (gi < ib && gj < n && gi <= gj) M[gi + (size_t)gj * n] -= acc[a][b];
     }
 }
 
@@ -594,62 +632,90 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
     delta[di[i]] = x[i];
     if (isnan(x[i])) nan = true;
   }
-  if (nan) atomicMin(&sc->nan_clique, c);
+  if (nan) atomicMax(&sc->nan_code, INT_MAX - c);
 }
 
+// Large cliques: x_F = R^-1 (d - S x_S) with several CTAs per clique and no global barrier.
+// CTA b owns a block of kBsRows rows of the clique (blockIdx.x = 0 is the BOTTOM block, which
+// depends on nobody; a CTA only ever waits on CTAs with a smaller blockIdx.x, so the wait cannot
+// deadlock).  Each CTA accumulates d - S x_S for its rows, then consumes the x blocks below it as
+// they are published (flag = epoch of this solve, release/acquire through L2), solves its own
+// 64x64 diagonal block as two 32x32 warp-shuffle solves, and publishes.  The critical path per
+// block is one flag hop + one 64-column GEMV + the in-block solve; everything else overlaps.
+constexpr int kBsRows = 64;
+
 __global__ void __launch_bounds__(256)
-backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc) {
-  // x_F = R^-1 (d - S x_S) for one large clique per CTA.  The triangular solve runs in
-  // 32-row blocks from the bottom: the 32x32 diagonal block is staged in shared memory and
-  // solved by one warp with shuffles (no dependent global load per row), then all threads
-  // apply the block's columns to the rows above (coalesced column reads).
-  extern __shared__ double sh[];  // x[f], xsep[s], Dg[32][33]
-  const int c = list[blockIdx.x];
+backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc, int* flags,
+                     const int* __restrict__ flag_base, int list_begin, int epoch) {
+  __shared__ double part[4][kBsRows];
+  __shared__ double rhs[kBsRows];
+  __shared__ double Dg[32][33];
+  const int c = list[blockIdx.y];
   const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
+  const int nblk = (f + kBsRows - 1) / kBsRows;
+  if ((int)blockIdx.x >= nblk) return;
+  const int rb = nblk - 1 - blockIdx.x;
+  const int r0 = rb * kBsRows, r1 = min(f, r0 + kBsRows), nr = r1 - r0;
   const double* M = t.arena + t.off[c];
   const int* di = t.didx + t.didx_ptr[c];
-  double* x = sh;
-  double* xsep = sh + f;
-  double (*Dg)[33] = reinterpret_cast<double (*)[33]>(sh + f + s);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int cc = tid; cc < s; cc += 256) xsep[cc] = delta[di[f + cc]];
-  __syncthreads();
-  for (int i = tid; i < f; i += 256) {
-    double r = M[i + (size_t)(n - 1) * n];
-    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * n] * xsep[cc];
-    x[i] = r;
+  int* fl = flags + flag_base[list_begin + blockIdx.y];
+  const int tid = threadIdx.x, row = tid & (kBsRows - 1), q = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  double acc = 0.0;
+  if (row < nr) {
+    const double* Mr = M + r0 + row;
+    for (int cc = q; cc < s; cc += 4) acc += Mr[(size_t)(f + cc) * n] * delta[di[f + cc]];
   }
+  for (int jb = nblk - 1; jb > rb; jb--) {
+    if (tid == 0) {
+      int spins = 0;   // bounded: a scheduling surprise must never hang the GPU
+      while (atomicAdd(fl + jb, 0) != epoch && ++spins < (1 << 22)) {}
+      if (spins >= (1 << 22)) atomicMax(&sc->nan_code, INT_MAX - c);
+      __threadfence();
+    }
+    __syncthreads();
+    const int c0 = jb * kBsRows, c1 = min(f, c0 + kBsRows);
+    if (row < nr) {
+      const double* Mr = M + r0 + row;
+      for (int j = c0 + q; j < c1; j += 4) acc += Mr[(size_t)j * n] * __ldcg(delta + di[j]);
+    }
+  }
+  part[q][row] = acc;
   __syncthreads();
-  for (int b1 = f; b1 > 0; b1 -= 32) {
-    const int b0 = b1 > 32 ? b1 - 32 : 0, nb = b1 - b0;
+  if (tid < nr) rhs[tid] = M[r0 + tid + (size_t)(n - 1) * n] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+  __syncthreads();
+  for (int sb = (nr > 32 ? 1 : 0); sb >= 0; sb--) {
+    const int b0 = 32 * sb, nb = min(32, nr - b0);
     for (int e = tid; e < nb * nb; e += 256) {
       const int i = e % nb, j = e / nb;
-      Dg[i][j] = (i <= j) ? M[(b0 + i) + (size_t)(b0 + j) * n] : 0.0;
+      Dg[i][j] = (i <= j) ? M[(r0 + b0 + i) + (size_t)(r0 + b0 + j) * n] : 0.0;
     }
     __syncthreads();
     if (warp == 0) {
-      double xv = lane < nb ? x[b0 + lane] : 0.0;
+      double xv = lane < nb ? rhs[b0 + lane] : 0.0;
       for (int k = nb - 1; k >= 0; k--) {
         const double xk = __shfl_sync(0xffffffffu, xv, k) / Dg[k][k];
         if (lane == k) xv = xk;
         else if (lane < k) xv -= Dg[lane][k] * xk;
       }
-      if (lane < nb) x[b0 + lane] = xv;
+      if (lane < nb) rhs[b0 + lane] = xv;
     }
     __syncthreads();
-    for (int i = tid; i < b0; i += 256) {
-      double acc = 0;
-      for (int j = 0; j < nb; j++) acc += M[i + (size_t)(b0 + j) * n] * x[b0 + j];
-      x[i] -= acc;
+    if (sb == 1 && tid < 32) {  // rows [0,32) of this block see the upper sub-block's solution
+      double a = 0;
+      for (int j = 0; j < nb; j++) a += M[(r0 + tid) + (size_t)(r0 + 32 + j) * n] * rhs[32 + j];
+      rhs[tid] -= a;
     }
     __syncthreads();
   }
   bool nan = false;
-  for (int i = tid; i < f; i += 256) {
-    delta[di[i]] = x[i];
-    if (isnan(x[i])) nan = true;
+  if (tid < nr) {
+    delta[di[r0 + tid]] = rhs[tid];
+    nan = isnan(rhs[tid]);
   }
-  if (nan) atomicMin(&sc->nan_clique, c);
+  if (nan) atomicMax(&sc->nan_code, INT_MAX - c);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicExch(fl + rb, epoch);
 }
 
 // ---------------------------------------------------------------------------
