@@ -186,11 +186,31 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     PhaseScope ps(p, PH_LEAF);
     GroupTable gt;
     for (size_t gi = 0; gi < p->groups.size(); gi++) gt.g[gi] = view(p->groups[gi]);
-    const int nb = (p->n_fused + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    leaf_fused_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, gt, p->d_fused_list, p->n_fused, p->d_fused_fac_ptr,
-                                                          p->d_fused_fac, p->d_lambda, (damped && diagonal) ? p->d_hdiag : nullptr,
-                                                          min_diag, max_diag, p->d_scalars);
-    ctx->launches++;
+    const double* hd = (damped && diagonal) ? p->d_hdiag : nullptr;
+    if (p->leaf_run_end[0] > p->leaf_run_begin[0]) {
+      const int nr = p->leaf_run_end[0] - p->leaf_run_begin[0], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const size_t sm = (size_t)kWarpsPerBlock * p->leaf_lb_cap * sizeof(double);
+      leaf_fused_kernel<<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[0], nr,
+                                                           p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
+                                                           p->d_scalars, p->leaf_lb_cap, 0);
+      ctx->launches++;
+    }
+    if (p->leaf_run_end[1] > p->leaf_run_begin[1]) {
+      const int nr = p->leaf_run_end[1] - p->leaf_run_begin[1], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 6 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
+      leaf_point_kernel<6><<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[1], nr,
+                                                              p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
+                                                              p->d_scalars, p->leaf_acc_cap);
+      ctx->launches++;
+    }
+    if (p->leaf_run_end[2] > p->leaf_run_begin[2]) {
+      const int nr = p->leaf_run_end[2] - p->leaf_run_begin[2], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 9 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
+      leaf_point_kernel<9><<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[2], nr,
+                                                              p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
+                                                              p->d_scalars, p->leaf_acc_cap);
+      ctx->launches++;
+    }
   }
   if (ctx->world > 1) {
     // the one exchange step of the solve — sum the Schur complements every rank
@@ -539,6 +559,22 @@ int b200_ctx_create(int device, b200_ctx** out) {
   cudaDeviceProp prop;
   B200_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  {
+    unsigned char pa[B200_NUM_FACTOR_TYPES][kMaxPairs] = {}, pb[B200_NUM_FACTOR_TYPES][kMaxPairs] = {};
+    for (int ty = 0; ty < B200_NUM_FACTOR_TYPES; ty++) {
+      const int nc = VAR_DIM[F_VT[ty][0]] + (F_ARITY[ty] == 2 ? VAR_DIM[F_VT[ty][1]] : 0) + 1;
+      int q = 0;
+      for (int a = 0; a < nc; a++) for (int b = a; b < nc; b++) { pa[ty][q] = (unsigned char)a; pb[ty][q] = (unsigned char)b; q++; }
+    }
+    B200_CUDA(cudaMemcpyToSymbol(kPairA, pa, sizeof pa));
+    B200_CUDA(cudaMemcpyToSymbol(kPairB, pb, sizeof pb));
+  }
+  B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
+  B200_CUDA(cudaFuncSetAttribute(leaf_point_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWarpsPerBlock * (kPtMaxObs * 32 + 8 + kLeafAccMax) * sizeof(double))));
+  B200_CUDA(cudaFuncSetAttribute(leaf_point_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWarpsPerBlock * (kPtMaxObs * 47 + 8 + kLeafAccMax) * sizeof(double))));
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
   *out = c;
@@ -586,6 +622,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
+  cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
   for (int i = 0; i < 2; i++) if (p->try_graph[i]) cudaGraphExecDestroy(p->try_graph[i]);
@@ -641,6 +678,77 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   std::vector<int> fused_list;   // the fused leaf cliques THIS rank owns
   for (int64_t c = 0; c < S.ncliques; c++)
     if (fused[c] && clique_owner[c] == rank) fused_list.push_back((int)c);
+  // group the owned fused leaves into runs that share (parent, separator variables): one warp
+  // reduces a run's Schur complements in shared memory before the extend-add
+  std::vector<int> run_ptr;
+  {
+    auto sig_less = [&](int a, int b) {
+      if (S.parent[a] != S.parent[b]) return S.parent[a] < S.parent[b];
+      const int64_t la = S.sep_ptr[a + 1] - S.sep_ptr[a], lb = S.sep_ptr[b + 1] - S.sep_ptr[b];
+      if (la != lb) return la < lb;
+      for (int64_t q = 0; q < la; q++) {
+        const int64_t va = S.sep_vars[S.sep_ptr[a] + q], vb = S.sep_vars[S.sep_ptr[b] + q];
+        if (va != vb) return va < vb;
+      }
+      return a < b;
+    };
+    auto sig_eq = [&](int a, int b) {
+      if (S.parent[a] != S.parent[b] || S.ns[a] != S.ns[b]) return false;
+      const int64_t la = S.sep_ptr[a + 1] - S.sep_ptr[a];
+      if (la != S.sep_ptr[b + 1] - S.sep_ptr[b]) return false;
+      for (int64_t q = 0; q < la; q++)
+        if (S.sep_vars[S.sep_ptr[a] + q] != S.sep_vars[S.sep_ptr[b] + q]) return false;
+      return true;
+    };
+    // kind 1/2: BAL point cliques (one Point3 frontal, m <= kPtMaxObs binary projection factors on
+    // distinct cameras) take leaf_point_kernel<6>/<9>; everything else the generic leaf kernel
+    std::vector<int> cf_count(S.ncliques, 0), cf_mask(S.ncliques, 0), kind(S.ncliques, 0);
+    for (int64_t gi = 0; gi < d->ngroups; gi++)
+      for (int64_t i = 0; i < d->groups[gi].count; i++) {
+        const int c = S.fac_clique[p->groups[gi].gi0 + i];
+        if (fused[c]) { cf_count[c]++; cf_mask[c] |= 1 << d->groups[gi].type; }
+      }
+    const bool fast = !getenv("B200_NO_POINT_KERNEL");
+    for (int c : fused_list) {
+      const int64_t nsep = S.sep_ptr[c + 1] - S.sep_ptr[c];
+      const bool point = S.front_ptr[c + 1] - S.front_ptr[c] == 1 && d->var_type[S.front_vars[S.front_ptr[c]]] == B200_VAR_POINT3;
+      if (!fast || !point || cf_count[c] != nsep || cf_count[c] > kPtMaxObs || cf_count[c] < 1) continue;
+      if (cf_mask[c] == (1 << B200_FACTOR_PROJECTION_CAL3S2)) kind[c] = 1;
+      else if (cf_mask[c] == (1 << B200_FACTOR_SFM_BUNDLER)) kind[c] = 2;
+    }
+    std::sort(fused_list.begin(), fused_list.end(), [&](int a, int b) {
+      if (kind[a] != kind[b]) return kind[a] < kind[b];
+      return sig_less(a, b);
+    });
+    const int nfl = (int)fused_list.size();
+    const int run_max_pt = getenv("B200_NO_LEAF_RUNS") ? 1 : std::max(1, std::min(64, nfl / (ctx->sm_count * 32)));
+    run_ptr.push_back(0);
+    for (int kd = 0; kd < 3; kd++) p->leaf_run_begin[kd] = p->leaf_run_end[kd] = 0;
+    for (int i = 1; i <= nfl; i++) {
+      const int kprev = kind[fused_list[i - 1]];
+      const int rmax = kprev == 0 ? 1 : run_max_pt;
+      if (i == nfl || i - run_ptr.back() >= rmax || kind[fused_list[i]] != kprev || !sig_eq(fused_list[i - 1], fused_list[i])) {
+        run_ptr.push_back(i);
+      }
+    }
+    p->n_runs = (int)run_ptr.size() - 1;
+    {
+      int r = 0;
+      for (int kd = 0; kd < 3; kd++) {
+        p->leaf_run_begin[kd] = r;
+        while (r < p->n_runs && kind[fused_list[run_ptr[r]]] == kd) r++;
+        p->leaf_run_end[kd] = r;
+      }
+    }
+    // shared memory per warp: the widest [F S d] block (generic) / packed Schur triangle (point kernels)
+    int lb = 1, tri = 0;
+    for (int c : fused_list) {
+      const int nn = S.nf[c] + S.ns[c] + 1, w = S.ns[c] + 1;
+      if (kind[c] == 0) lb = std::max(lb, S.nf[c] * nn);
+      else if (w * (w + 1) / 2 <= kLeafAccMax) tri = std::max(tri, w * (w + 1) / 2);
+    }
+    p->leaf_lb_cap = lb; p->leaf_acc_cap = tri;
+  }
   p->n_fused = (int)fused_list.size();
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
@@ -726,6 +834,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) {
         return p->groups[a.x].gi0 + p->groups[a.x].local_index[a.y] < p->groups[b.x].gi0 + p->groups[b.x].local_index[b.y]; });
     UP(upload(&p->d_fused_list, fused_list, st));
+    UP(upload(&p->d_fused_run_ptr, run_ptr, st));
     UP(upload(&p->d_fused_fac_ptr, fptr, st));
     UP(upload(&p->d_fused_fac, ffac, st));
   }

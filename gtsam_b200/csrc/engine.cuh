@@ -109,8 +109,9 @@ struct b200_problem {
   std::vector<int64_t> h_off;       // final arena offsets (fused leaves store f x n only)
   std::vector<int> h_ld;
   // fused leaf path
-  int n_fused = 0;
-  int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr;
+  int n_fused = 0, n_runs = 0, leaf_lb_cap = 1, leaf_acc_cap = 0;
+  int leaf_run_begin[3] = {0, 0, 0}, leaf_run_end[3] = {0, 0, 0};  // run ranges: generic / point DC=6 / point DC=9
+  int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr, *d_fused_run_ptr = nullptr;
   int2* d_fused_fac = nullptr;
   int64_t arena_doubles = 0, zero_doubles = 0;  // [0, zero_doubles) = non-leaf fronts (memset per solve)
   int64_t *d_ea_ptr = nullptr, *d_didx_ptr = nullptr;

@@ -32,6 +32,11 @@ struct GroupTable { GroupView g[kMaxGroups]; };
 __constant__ int kFD[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
 __constant__ int kFN1[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 6, 9, 9};
 __constant__ int kFN2[B200_NUM_FACTOR_TYPES] = {6, 0, 0, 3, 3, 0};
+// column pairs (ca <= cb) of a factor's [A1 A2 b] block, per factor type (filled at ctx creation)
+constexpr int kMaxPairs = 96;   // 13*14/2 = 91
+// (global memory, read through L1: the index differs per lane, which would serialise in the constant cache)
+__device__ unsigned char kPairA[B200_NUM_FACTOR_TYPES][kMaxPairs];
+__device__ unsigned char kPairB[B200_NUM_FACTOR_TYPES][kMaxPairs];
 
 // ---------------------------------------------------------------------------
 // block reduction helpers
@@ -321,98 +326,338 @@ elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_
 //   * after R = chol(F), S' = R^-T [S d], the update -S'^T S' goes to the parent.
 // The conditional [R S' d'] is stored compactly (f x n, ld = f).
 // ---------------------------------------------------------------------------
+constexpr int kLeafAccMax = 1024;  // (s+1)(s+2)/2 accumulators per warp for grouped runs
+
+// Triangular index e -> (i <= j) with e = j(j+1)/2 + i
+__device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
+  j = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+  while ((j + 1) * (j + 2) / 2 <= e) j++;
+  while (j * (j + 1) / 2 > e) j--;
+  i = e - j * (j + 1) / 2;
+}
+
+// One warp processes a RUN of leaf cliques that share parent and separator set (points seen by
+// the same cameras).  Their contributions to the parent are first summed in shared memory
+// (lane-private accumulators, no conflicts) and extend-added once per run, which divides the
+// number of FP64 atomics into the top fronts by the run length.  A run of length 1 whose
+// separator is too wide for the accumulators falls back to direct atomics.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int count,
-                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
-                  const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc) {
-  __shared__ double sm[kWarpsPerBlock][kLeafMaxFN];
+leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
+                  int nruns, const int* __restrict__ fac_ptr, const int2* __restrict__ fac,
+                  const double* __restrict__ lambda_ptr, const double* __restrict__ hdiag, double min_diag,
+                  double max_diag, Scalars* sc, int lb_cap, int acc_cap) {
+  extern __shared__ double leaf_sm[];
   const double lambda = *lambda_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kWarpsPerBlock + warp;
-  if (idx >= count) return;
-  const int c = list[idx];
-  const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
-  double* LB = sm[warp];  // row-major f x n
-  for (int e = lane; e < f * n; e += 32) LB[e] = 0.0;
-  const int p = t.parent[c];
+  const int run = blockIdx.x * kWarpsPerBlock + warp;
+  if (run >= nruns) return;
+  double* LB = leaf_sm + (size_t)warp * (lb_cap + acc_cap);  // row-major f x n
+  double* acc = LB + lb_cap;
+  const int r0 = run_ptr[run], r1 = run_ptr[run + 1];
+  const int c0 = list[r0];
+  const int s = t.ns[c0], w = s + 1, ntri = w * (w + 1) / 2;
+  const int p = t.parent[c0];
   double* P = p >= 0 ? t.arena + t.off[p] : nullptr;
   const int pn = p >= 0 ? t.nf[p] + t.ns[p] + 1 : 0;
-  const int* map = t.ea_map + t.ea_ptr[c];
-  __syncwarp();
-  for (int q = fac_ptr[idx]; q < fac_ptr[idx + 1]; q++) {
-    const int2 gf = fac[q];
-    const GroupView& g = gt.g[gf.x];
-    const int D = kFD[g.type], N1 = kFN1[g.type], N2 = kFN2[g.type], NC = N1 + N2 + 1;
-    const int4 scat = g.scat[gf.y];
-    const double* J = g.J + gf.y;
-    const int NP = NC * (NC + 1) / 2;
-    for (int pi = lane; pi < NP; pi += 32) {
-      int ca = 0, rem = pi;
-      while (rem >= NC - ca) { rem -= NC - ca; ca++; }
-      const int cb = ca + rem;
-      double dot = 0;
-      for (int r = 0; r < D; r++) dot += J[(size_t)(r + ca * D) * g.count] * J[(size_t)(r + cb * D) * g.count];
-      int I = ca < N1 ? scat.y + ca : (ca < N1 + N2 ? scat.z + (ca - N1) : n - 1);
-      int Jx = cb < N1 ? scat.y + cb : (cb < N1 + N2 ? scat.z + (cb - N1) : n - 1);
-      if (I > Jx) { const int tmp = I; I = Jx; Jx = tmp; }
-      if (I < f) {
-        LB[I * n + Jx] += dot;  // distinct (ca,cb) -> distinct entries: no intra-warp conflict
-      } else if (P) {
-        const int a = map[I - f], b = map[Jx - f];
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        atomicAdd(P + lo + (size_t)hi * pn, dot);
+  const int* map = t.ea_map + t.ea_ptr[c0];
+  const bool grouped = P && ntri <= acc_cap;
+  if (grouped)
+    for (int e = lane; e < ntri; e += 32) acc[e] = 0.0;
+  for (int idx = r0; idx < r1; idx++) {
+    const int c = list[idx];
+    const int f = t.nf[c], n = f + s + 1;
+    for (int e = lane; e < f * n; e += 32) LB[e] = 0.0;
+    __syncwarp();
+    for (int q = fac_ptr[idx]; q < fac_ptr[idx + 1]; q++) {
+      const int2 gf = fac[q];
+      const GroupView& g = gt.g[gf.x];
+      const int D = kFD[g.type], N1 = kFN1[g.type], N2 = kFN2[g.type], NC = N1 + N2 + 1;
+      const int4 scat = g.scat[gf.y];
+      const double* J = g.J + gf.y;
+      const int NP = NC * (NC + 1) / 2;
+      const size_t cnt = (size_t)g.count;
+      for (int pi = lane; pi < NP; pi += 32) {
+        const int ca = __ldg(&kPairA[g.type][pi]), cb = __ldg(&kPairB[g.type][pi]);
+        const double* Ja = J + (size_t)(ca * D) * cnt;
+        const double* Jb = J + (size_t)(cb * D) * cnt;
+        double dot = 0;
+        for (int r = 0; r < D; r++) dot += Ja[r * cnt] * Jb[r * cnt];
+        int I = ca < N1 ? scat.y + ca : (ca < N1 + N2 ? scat.z + (ca - N1) : n - 1);
+        int Jx = cb < N1 ? scat.y + cb : (cb < N1 + N2 ? scat.z + (cb - N1) : n - 1);
+        if (I > Jx) { const int tmp = I; I = Jx; Jx = tmp; }
+        if (I < f) {
+          LB[I * n + Jx] += dot;  // distinct (ca,cb) -> distinct entries: no intra-warp conflict
+        } else if (grouped) {
+          const int i = I - f, j = Jx - f;
+          acc[j * (j + 1) / 2 + i] += dot;   // separator-separator term: passes through to the parent
+        } else if (P) {
+          const int a = map[I - f], b = map[Jx - f];
+          const int lo = a < b ? a : b, hi = a < b ? b : a;
+          atomicAdd(P + lo + (size_t)hi * pn, dot);
+        }
+      }
+      __syncwarp();
+    }
+    if (lambda > 0 && lane < f) {  // damping prior of each frontal scalar
+      double a2 = 1.0;
+      if (hdiag) {
+        const double h = fmin(fmax(hdiag[t.didx[t.didx_ptr[c] + lane]], min_diag), max_diag);
+        const double sq = sqrt(h);
+        a2 = sq * sq;
+      }
+      const double sl = 1.0 / (1.0 / sqrt(lambda));
+      LB[lane * n + lane] += (sl * sl) * a2;
+    }
+    __syncwarp();
+    bool ok = true;
+    for (int k = 0; k < f; k++) {
+      const double piv = LB[k * n + k];
+      if (!(piv > 0.0)) ok = false;
+      const double r = sqrt(piv);
+      __syncwarp();
+      for (int j = k + lane; j < n; j += 32) LB[k * n + j] = (j == k) ? r : LB[k * n + j] / r;
+      __syncwarp();
+      for (int i = k + 1; i < f; i++) {
+        const double rki = LB[k * n + i];
+        for (int j = i + lane; j < n; j += 32) LB[i * n + j] -= rki * LB[k * n + j];
+      }
+      __syncwarp();
+    }
+    if (f >= 2) {
+      if (!(dexp(LB[(f - 2) * n + f - 2]) - dexp(LB[(f - 1) * n + f - 1]) < 12)) ok = false;
+    } else if (f == 1) {
+      if (!(dexp(LB[0]) > -12)) ok = false;
+    }
+    if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
+    double* M = t.arena + t.off[c];  // compact conditional, column-major f x n
+    for (int j = lane; j < n; j += 32)
+      for (int i = 0; i < f; i++) M[i + j * f] = (i <= j) ? LB[i * n + j] : 0.0;
+    if (P) {
+      int i, j;
+      tri_decode(lane, i, j);
+      for (int e = lane; e < ntri; e += 32) {
+        if (e != lane) {   // advance (i,j) by 32 positions along the packed upper triangle
+          i += 32;
+          while (i > j) { i -= j + 1; j++; }
+        }
+        double v = 0;
+        for (int k = 0; k < f; k++) v += LB[k * n + f + i] * LB[k * n + f + j];
+        if (grouped) {
+          acc[e] -= v;
+        } else {
+          const int a = map[i], b = map[j];
+          const int lo = a < b ? a : b, hi = a < b ? b : a;
+          atomicAdd(P + lo + (size_t)hi * pn, -v);
+        }
       }
     }
     __syncwarp();
   }
-  if (lambda > 0 && lane < f) {  // damping prior of each frontal scalar
-    double a2 = 1.0;
-    if (hdiag) {
-      const double h = fmin(fmax(hdiag[t.didx[t.didx_ptr[c] + lane]], min_diag), max_diag);
-      const double sq = sqrt(h);
-      a2 = sq * sq;
-    }
-    const double sl = 1.0 / (1.0 / sqrt(lambda));
-    LB[lane * n + lane] += (sl * sl) * a2;
-  }
-  __syncwarp();
-  bool ok = true;
-  for (int k = 0; k < f; k++) {
-    const double piv = LB[k * n + k];
-    if (!(piv > 0.0)) ok = false;
-    const double r = sqrt(piv);
-    __syncwarp();
-    for (int j = k + lane; j < n; j += 32) LB[k * n + j] = (j == k) ? r : LB[k * n + j] / r;
-    __syncwarp();
-    for (int e = lane; e < (f - k - 1) * n; e += 32) {
-      const int i = k + 1 + e / n, j = e % n;
-      if (j >= i) LB[i * n + j] -= LB[k * n + i] * LB[k * n + j];
-    }
-    __syncwarp();
-  }
-  if (f >= 2) {
-    if (!(dexp(LB[(f - 2) * n + f - 2]) - dexp(LB[(f - 1) * n + f - 1]) < 12)) ok = false;
-  } else if (f == 1) {
-    if (!(dexp(LB[0]) > -12)) ok = false;
-  }
-  if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
-  double* M = t.arena + t.off[c];  // compact conditional, column-major f x n
-  for (int e = lane; e < f * n; e += 32) {
-    const int i = e % f, j = e / f;
-    M[e] = (i <= j) ? LB[i * n + j] : 0.0;
-  }
-  if (P) {
-    const int w = s + 1, total = w * (w + 1) / 2;
-    for (int e = lane; e < total; e += 32) {
-      int j = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while ((j + 1) * (j + 2) / 2 <= e) j++;
-      while (j * (j + 1) / 2 > e) j--;
-      const int i = e - j * (j + 1) / 2;
-      double v = 0;
-      for (int k = 0; k < f; k++) v += LB[k * n + f + i] * LB[k * n + f + j];
+  if (grouped) {
+    int i, j;
+    tri_decode(lane, i, j);
+    for (int e = lane; e < ntri; e += 32) {
+      if (e != lane) {
+        i += 32;
+        while (i > j) { i -= j + 1; j++; }
+      }
       const int a = map[i], b = map[j];
       const int lo = a < b ? a : b, hi = a < b ? b : a;
-      atomicAdd(P + lo + (size_t)hi * pn, -v);
+      atomicAdd(P + lo + (size_t)hi * pn, acc[e]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BAL fast path of the fused leaf kernel: cliques whose single frontal variable is a Point3
+// observed by m <= kPtMaxObs DISTINCT cameras through binary projection factors
+// (GenericProjectionFactor: DC = 6, GeneralSFMFactor<Cal3Bundler>: DC = 9).  Same maths and
+// same outputs as leaf_fused_kernel, but one LANE per factor does the factor work in registers
+// (no divergent index decoding), the 3x3 Cholesky is done redundantly in registers after a
+// warp all-reduce, and the Schur update is emitted as (camera pair, row) items: 6-9 outputs
+// per lane per round instead of one.
+// ---------------------------------------------------------------------------
+constexpr int kPtMaxObs = 8;
+
+template <int DC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+leaf_point_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr, int nruns,
+                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
+                  const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int acc_cap) {
+  constexpr int FS = 5 * DC + 2;   // per factor: S' (3 x DC), A_c (2 x DC), b (2)
+  extern __shared__ double leaf_sm[];
+  const double lambda = *lambda_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int run = blockIdx.x * kWarpsPerBlock + warp;
+  if (run >= nruns) return;
+  const int per_warp = kPtMaxObs * FS + 8 + acc_cap;
+  double* fs = leaf_sm + (size_t)warp * per_warp;   // factor stash
+  double* dd = fs + kPtMaxObs * FS;                 // d'[3], bb
+  double* acc = dd + 8;
+  __shared__ int tks[kWarpsPerBlock][kPtMaxObs];
+  const int r0 = run_ptr[run], r1 = run_ptr[run + 1];
+  const int c0 = list[r0];
+  const int s = t.ns[c0], w = s + 1, ntri = w * (w + 1) / 2, n = 3 + w;
+  const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
+  const int p = t.parent[c0];
+  double* P = p >= 0 ? t.arena + t.off[p] : nullptr;
+  const int pn = p >= 0 ? t.nf[p] + t.ns[p] + 1 : 0;
+  const int* map = t.ea_map + t.ea_ptr[c0];
+  const bool grouped = P && ntri <= acc_cap;
+  if (grouped)
+    for (int e = lane; e < ntri; e += 32) acc[e] = 0.0;
+  const int npairs = m * (m + 1) / 2;
+  for (int idx = r0; idx < r1; idx++) {
+    const int c = list[idx];
+    double Ac[2][DC], Ap[2][3], b[2];
+    int tk = 0;
+    double v[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) v[i] = 0.0;
+    if (lane < m) {
+      const int2 gf = fac[fac_ptr[idx] + lane];
+      const GroupView& g = gt.g[gf.x];
+      const size_t cnt = (size_t)g.count;
+      const double* J = g.J + gf.y;
+      tk = g.scat[gf.y].y - 3;
+#pragma unroll
+      for (int cc = 0; cc < DC; cc++) { Ac[0][cc] = J[(size_t)(2 * cc) * cnt]; Ac[1][cc] = J[(size_t)(2 * cc + 1) * cnt]; }
+#pragma unroll
+      for (int j = 0; j < 3; j++) { Ap[0][j] = J[(size_t)(2 * (DC + j)) * cnt]; Ap[1][j] = J[(size_t)(2 * (DC + j) + 1) * cnt]; }
+      b[0] = J[(size_t)(2 * (DC + 3)) * cnt]; b[1] = J[(size_t)(2 * (DC + 3) + 1) * cnt];
+      v[0] = Ap[0][0] * Ap[0][0] + Ap[1][0] * Ap[1][0];
+      v[1] = Ap[0][0] * Ap[0][1] + Ap[1][0] * Ap[1][1];
+      v[2] = Ap[0][0] * Ap[0][2] + Ap[1][0] * Ap[1][2];
+      v[3] = Ap[0][1] * Ap[0][1] + Ap[1][1] * Ap[1][1];
+      v[4] = Ap[0][1] * Ap[0][2] + Ap[1][1] * Ap[1][2];
+      v[5] = Ap[0][2] * Ap[0][2] + Ap[1][2] * Ap[1][2];
+      v[6] = Ap[0][0] * b[0] + Ap[1][0] * b[1];
+      v[7] = Ap[0][1] * b[0] + Ap[1][1] * b[1];
+      v[8] = Ap[0][2] * b[0] + Ap[1][2] * b[1];
+      v[9] = b[0] * b[0] + b[1] * b[1];
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    if (lambda > 0) {
+      const double sl = 1.0 / (1.0 / sqrt(lambda));
+      double a2[3] = {1.0, 1.0, 1.0};
+      if (hdiag) {
+        const int* di = t.didx + t.didx_ptr[c];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const double sq = sqrt(fmin(fmax(hdiag[di[i]], min_diag), max_diag)); a2[i] = sq * sq; }
+      }
+      v[0] += (sl * sl) * a2[0]; v[3] += (sl * sl) * a2[1]; v[5] += (sl * sl) * a2[2];
+    }
+    // 3x3 partial Cholesky in registers (every lane, identical): gtsam/base/cholesky.cpp:107-158
+    bool ok = v[0] > 0.0;
+    const double r00 = sqrt(v[0]);
+    const double r01 = v[1] / r00, r02 = v[2] / r00;
+    const double p11 = v[3] - r01 * r01;
+    ok = ok && p11 > 0.0;
+    const double r11 = sqrt(p11);
+    const double r12 = (v[4] - r01 * r02) / r11;
+    const double p22 = v[5] - r02 * r02 - r12 * r12;
+    ok = ok && p22 > 0.0;
+    const double r22 = sqrt(p22);
+    if (!(dexp(r11) - dexp(r22) < 12)) ok = false;
+    if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
+    const double d0 = v[6] / r00;
+    const double d1 = (v[7] - r01 * d0) / r11;
+    const double d2 = (v[8] - r02 * d0 - r12 * d1) / r22;
+    double* M = t.arena + t.off[c];   // compact conditional [R S' d'], column-major 3 x n
+    if (lane == 0) {
+      M[0] = r00; M[1] = 0.0; M[2] = 0.0;
+      M[3] = r01; M[4] = r11; M[5] = 0.0;
+      M[6] = r02; M[7] = r12; M[8] = r22;
+      M[3 * (n - 1)] = d0; M[3 * (n - 1) + 1] = d1; M[3 * (n - 1) + 2] = d2;
+      dd[0] = d0; dd[1] = d1; dd[2] = d2; dd[3] = v[9];
+    }
+    if (lane < m) {
+      double* F = fs + lane * FS;
+      double* Mc = M + 3 * (3 + tk);
+#pragma unroll
+      for (int cc = 0; cc < DC; cc++) {
+        const double w0 = Ap[0][0] * Ac[0][cc] + Ap[1][0] * Ac[1][cc];
+        const double w1 = Ap[0][1] * Ac[0][cc] + Ap[1][1] * Ac[1][cc];
+        const double w2 = Ap[0][2] * Ac[0][cc] + Ap[1][2] * Ac[1][cc];
+        const double s0 = w0 / r00;
+        const double s1 = (w1 - r01 * s0) / r11;
+        const double s2 = (w2 - r02 * s0 - r12 * s1) / r22;
+        Mc[3 * cc] = s0; Mc[3 * cc + 1] = s1; Mc[3 * cc + 2] = s2;
+        F[cc] = s0; F[DC + cc] = s1; F[2 * DC + cc] = s2;
+        F[3 * DC + cc] = Ac[0][cc]; F[4 * DC + cc] = Ac[1][cc];
+      }
+      F[5 * DC] = b[0]; F[5 * DC + 1] = b[1];
+      tks[warp][lane] = tk;
+    }
+    __syncwarp();
+    if (P) {
+      // (A) camera-pair blocks: item = (pair (k<=l), row r of the k block) -> DC outputs
+      const int nitems = npairs * DC;
+      for (int q = lane; q < nitems; q += 32) {
+        const int pr = q / DC, r = q - pr * DC;
+        int kk = 0, rem = pr;
+        while (rem >= m - kk) { rem -= m - kk; kk++; }
+        const int ll = kk + rem;
+        const double* Fk = fs + kk * FS;
+        const double* Fl = fs + ll * FS;
+        const double sk0 = Fk[r], sk1 = Fk[DC + r], sk2 = Fk[2 * DC + r];
+        const double ak0 = Fk[3 * DC + r], ak1 = Fk[4 * DC + r];
+        const int ti = tks[warp][kk] + r, tl0 = tks[warp][ll];
+#pragma unroll
+        for (int cc = 0; cc < DC; cc++) {
+          if (kk == ll && cc < r) continue;
+          double val = -(sk0 * Fl[cc] + sk1 * Fl[DC + cc] + sk2 * Fl[2 * DC + cc]);
+          if (kk == ll) val += ak0 * Fl[3 * DC + cc] + ak1 * Fl[4 * DC + cc];
+          const int tj = tl0 + cc;
+          const int i = ti < tj ? ti : tj, j = ti < tj ? tj : ti;
+          if (grouped) {
+            acc[j * (j + 1) / 2 + i] += val;
+          } else {
+            const int a = map[i], bq = map[j];
+            const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+            atomicAdd(P + lo + (size_t)hi * pn, val);
+          }
+        }
+      }
+      // (B) rhs column (tk + r, s) and (C) the constant term (s, s)
+      for (int q = lane; q < m * DC + 1; q += 32) {
+        double val;
+        int i;
+        if (q < m * DC) {
+          const int kk = q / DC, r = q - kk * DC;
+          const double* Fk = fs + kk * FS;
+          val = Fk[3 * DC + r] * Fk[5 * DC] + Fk[4 * DC + r] * Fk[5 * DC + 1] -
+                (Fk[r] * dd[0] + Fk[DC + r] * dd[1] + Fk[2 * DC + r] * dd[2]);
+          i = tks[warp][kk] + r;
+        } else {
+          val = dd[3] - (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+          i = s;
+        }
+        if (grouped) {
+          acc[s * (s + 1) / 2 + i] += val;
+        } else {
+          const int a = map[i], bq = map[s];
+          const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+          atomicAdd(P + lo + (size_t)hi * pn, val);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (grouped) {
+    int i, j;
+    tri_decode(lane, i, j);
+    for (int e = lane; e < ntri; e += 32) {
+      if (e != lane) {
+        i += 32;
+        while (i > j) { i -= j + 1; j++; }
+      }
+      const int a = map[i], b = map[j];
+      const int lo = a < b ? a : b, hi = a < b ? b : a;
+      atomicAdd(P + lo + (size_t)hi * pn, acc[e]);
     }
   }
 }
@@ -442,29 +687,39 @@ panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, doub
   if (j0 >= n && blockIdx.x != 0) return;
   double* M = t.arena + t.off[c];
   const int tid = threadIdx.x;
+  __shared__ double invd[kNB];
   if (tid == 0) bad = 0;
-  for (int e = tid; e < nb * nb; e += kTrsmCols) {
-    const int i = e % nb, j = e / nb;
-    Dg[i][j] = (i <= j) ? M[(k0 + i) + (size_t)(k0 + j) * n] : 0.0;
+  __syncthreads();
+  // Cholesky of the diagonal block by ONE warp, the matrix in registers: lane j owns column j.
+  // Step k: r = sqrt(a_kk) (lane k), row k scaled, then lane j subtracts R(k,i) R(k,j) from its
+  // a_ij with R(k,i) fetched from lane i by shuffle.  No block barrier inside the 32 steps.
+  if (tid < 32) {
+    const int lane = tid;
+    double a[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; i++)
+      a[i] = (lane < nb && i <= lane) ? M[(k0 + i) + (size_t)(k0 + lane) * n] : ((i == lane) ? 1.0 : 0.0);
+    bool notpd = false;
+#pragma unroll
+    for (int k = 0; k < kNB; k++) {
+      const double akk = __shfl_sync(0xffffffffu, a[k], k);
+      if (k < nb && !(akk > 0.0)) notpd = true;
+      const double r = sqrt(akk);
+      if (lane == k) a[k] = r;
+      else if (lane > k) a[k] = a[k] / r;
+#pragma unroll
+      for (int i = k + 1; i < kNB; i++) {
+        const double rki = __shfl_sync(0xffffffffu, a[k], i);
+        if (lane >= i) a[i] -= rki * a[k];
+      }
+    }
+    if (notpd && lane == 0) bad = 1;
+#pragma unroll
+    for (int i = 0; i < kNB; i++) Dg[i][lane] = (i <= lane) ? a[i] : 0.0;
   }
   __syncthreads();
-  for (int k = 0; k < nb; k++) {  // unblocked right-looking Cholesky (upper) of the diagonal block
-    const double piv = Dg[k][k];
-    __syncthreads();
-    if (tid == 0 && !(piv > 0.0)) bad = 1;
-    const double r = sqrt(piv);
-    if (tid < nb - k) {
-      const int j = k + tid;
-      Dg[k][j] = (j == k) ? r : Dg[k][j] / r;
-    }
-    __syncthreads();
-    const int w = nb - k - 1;
-    for (int e = tid; e < w * w; e += kTrsmCols) {
-      const int i = k + 1 + e % w, j = k + 1 + e / w;
-      if (i <= j) Dg[i][j] -= Dg[k][i] * Dg[k][j];
-    }
-    __syncthreads();
-  }
+  if (tid < 32) invd[tid] = 1.0 / Dg[tid][tid];
+  __syncthreads();
   if (blockIdx.x == 0) {
     if (tid == 0) {
       if (k0 + nb == f) {  // last panel: underconstrained check on the last two pivots
@@ -491,7 +746,7 @@ panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, doub
 #pragma unroll
         for (int q = 0; q < kNB; q++)
           if (q < p) s -= Dg[q][p] * x[q];
-        x[p] = s / Dg[p][p];
+        x[p] = s * invd[p];
       }
     }
 #pragma unroll
@@ -614,10 +869,24 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
   const double* M = t.arena + t.off[c];
   const int* di = t.didx + t.didx_ptr[c];
   double* x = xs[warp];
-  for (int i = lane; i < f; i += 32) {
-    double r = M[i + (size_t)(n - 1) * ld];
-    for (int cc = 0; cc < s; cc++) r -= M[i + (size_t)(f + cc) * ld] * delta[di[f + cc]];
-    x[i] = r;
+  // rhs = d - S x_S with the lanes spread over the separator columns (coalesced: the f entries of a
+  // column are contiguous and consecutive columns are adjacent), 8 rows at a time, warp-reduced
+  for (int i0 = 0; i0 < f; i0 += 8) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 0.0;
+    for (int cc = lane; cc < s; cc += 32) {
+      const double xsv = delta[di[f + cc]];
+      const double* col = M + (size_t)(f + cc) * ld + i0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (i0 + k < f) a[k] += col[k] * xsv;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double sum = warp_sum(a[k]);
+      if (lane == 0 && i0 + k < f) x[i0 + k] = M[(i0 + k) + (size_t)(n - 1) * ld] - sum;
+    }
   }
   __syncwarp();
   for (int i = f - 1; i >= 0; i--) {
@@ -649,7 +918,8 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
                      const int* __restrict__ flag_base, int list_begin, int epoch) {
   __shared__ double part[4][kBsRows];
   __shared__ double rhs[kBsRows];
-  __shared__ double Dg[32][33];
+  __shared__ double Dg[3][32][33];   // [0]: rows 0..31 diag, [1]: rows 32..63 diag, [2]: coupling rows 0..31 x cols 32..63
+  __shared__ double invd[kBsRows];
   const int c = list[blockIdx.y];
   const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
   const int nblk = (f + kBsRows - 1) / kBsRows;
@@ -660,6 +930,14 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
   const int* di = t.didx + t.didx_ptr[c];
   int* fl = flags + flag_base[list_begin + blockIdx.y];
   const int tid = threadIdx.x, row = tid & (kBsRows - 1), q = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  // stage this block's 64x64 upper-triangular diagonal block now: it overlaps with the waits below
+  for (int e = tid; e < 3 * 1024; e += 256) {
+    const int blk = e >> 10, i = e & 31, j = (e >> 5) & 31;
+    const int gi = (blk == 1 ? 32 : 0) + i, gj = (blk == 0 ? 0 : 32) + j;
+    double v = 0.0;
+    if (gi < nr && gj < nr && gi <= gj) v = M[(r0 + gi) + (size_t)(r0 + gj) * n];
+    Dg[blk][i][j] = v;
+  }
   double acc = 0.0;
   if (row < nr) {
     const double* Mr = M + r0 + row;
@@ -681,32 +959,31 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
   }
   part[q][row] = acc;
   __syncthreads();
-  if (tid < nr) rhs[tid] = M[r0 + tid + (size_t)(n - 1) * n] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+  if (tid < nr) {
+    rhs[tid] = M[r0 + tid + (size_t)(n - 1) * n] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+    invd[tid] = 1.0 / Dg[tid >> 5][tid & 31][tid & 31];
+  }
   __syncthreads();
-  for (int sb = (nr > 32 ? 1 : 0); sb >= 0; sb--) {
-    const int b0 = 32 * sb, nb = min(32, nr - b0);
-    for (int e = tid; e < nb * nb; e += 256) {
-      const int i = e % nb, j = e / nb;
-      Dg[i][j] = (i <= j) ? M[(r0 + b0 + i) + (size_t)(r0 + b0 + j) * n] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
+  if (warp == 0) {   // one warp: solve rows 32..63, apply the coupling block, solve rows 0..31
+    for (int sb = (nr > 32 ? 1 : 0); sb >= 0; sb--) {
+      const int b0 = 32 * sb, nb = min(32, nr - b0);
       double xv = lane < nb ? rhs[b0 + lane] : 0.0;
       for (int k = nb - 1; k >= 0; k--) {
-        const double xk = __shfl_sync(0xffffffffu, xv, k) / Dg[k][k];
+        const double xk = __shfl_sync(0xffffffffu, xv, k) * invd[b0 + k];
         if (lane == k) xv = xk;
-        else if (lane < k) xv -= Dg[lane][k] * xk;
+        else if (lane < k) xv -= Dg[sb][lane][k] * xk;
       }
       if (lane < nb) rhs[b0 + lane] = xv;
+      __syncwarp();
+      if (sb == 1) {
+        double a = 0;
+        for (int j = 0; j < nb; j++) a += Dg[2][lane][j] * rhs[32 + j];
+        rhs[lane] -= a;
+        __syncwarp();
+      }
     }
-    __syncthreads();
-    if (sb == 1 && tid < 32) {  // rows [0,32) of this block see the upper sub-block's solution
-      double a = 0;
-      for (int j = 0; j < nb; j++) a += M[(r0 + tid) + (size_t)(r0 + 32 + j) * n] * rhs[32 + j];
-      rhs[tid] -= a;
-    }
-    __syncthreads();
   }
+  __syncthreads();
   bool nan = false;
   if (tid < nr) {
     delta[di[r0 + tid]] = rhs[tid];
