@@ -48,7 +48,7 @@ def workload_config(prob, args):
     return {
         "workload": f"{args.workload}: {prob.name}", "factors": prob.nfactors, "variables": prob.nvars,
         "factor_types": sorted({int(g.type) for g in prob.groups}),
-        "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else "natural",
+        "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else prob.meta.get("ordering", "natural"),
         "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
         "cache": "working set (fronts + Jacobians) exceeds the 126 MB L2; no explicit flush",
         "parallelism": "single GPU" if args.gpus == 1 else
@@ -277,21 +277,35 @@ def main():
         "eliminate_large": 2 * info.front_bytes,
         "leaf_fused": jac_bytes + info.front_bytes,              # read [A|b] of the leaf factors, write [R S d]
     }
-    dom = max(per_step, key=lambda k: per_step[k][0])
-    tries = max(1.0, per_step["assemble"][1])
+    tries = max(1.0, per_step["leaf_fused"][1] if per_step["leaf_fused"][1] else per_step["back_substitute"][1])
+    # phases that are ONE kernel launch (per group): the candidates for "the dominant kernel"
+    single = {"linearize": "linearize_kernel", "leaf_fused": "leaf_point_kernel / leaf_fused_kernel",
+              "memset_fronts": "memset", "assemble": "assemble_kernel", "linear_error": "linerr_kernel", "error": "error_kernel"}
+    dom = max(single, key=lambda k: per_step[k][0])
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tpath) and args.workload == "bal_c3" and world == 1:
+        traffic = json.load(open(tpath))
 
     def roof(name):
-        """achieved = algorithmic bytes of one pass / its average duration (CUDA events on the
+        """achieved = algorithmic bytes of one launch / its average duration (CUDA events on the
         launching stream, from the library's phase timers); linearize runs once per step, the
-        solve phases once per lambda try."""
+        solve phases once per lambda try.  traffic = dram read+write of one launch from ncu --set full."""
         ms_phase, _calls = per_step[name]
         if ms_phase <= 0 or name not in alg_bytes:
             return None
         units = 1.0 if name == "linearize" else tries
-        ach = alg_bytes[name] * units / (ms_phase * 1e-3) / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_phase / units,
-                "algorithmic_bytes_per_launch": alg_bytes[name]}
+        nbytes = alg_bytes[name] / world     # each rank handles its shard
+        ach = nbytes * units / (ms_phase * 1e-3) / 1e9
+        return {"kernel": single.get(name, name), "phase": name, "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(name, {}).get("dram_bytes"),
+                "peak_source": peak_src, "ms_per_launch": ms_phase / units, "algorithmic_bytes_per_launch": nbytes,
+                "note": "FP64 path: latency/instruction bound at this size (see profiles/); tensor pipe unused (no FP64 tcgen05 kind)"}
+
+    large_ms = per_step["eliminate_large"][0] / tries
+    large = {"flops_per_solve": info.factor_flops, "ms_per_solve": large_ms,
+             "achieved_tflops": (info.factor_flops / (large_ms * 1e-3) / 1e12) if large_ms > 0 else None,
+             "note": "panel Cholesky + TRSM + rank-k updates of the non-leaf fronts, FP64 FMA pipe"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -302,6 +316,7 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof(dom) or roof("linearize"),
         "roofline_linearize": roof("linearize"),
+        "large_fronts": large,
         "phases_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
         "lm": {"error_after": st.error, "lambda_after": st.lambda_, "tries_per_step": tries},
         "tree": {"cliques": info.ncliques, "levels": info.nlevels, "max_frontal": info.max_frontal_dim,

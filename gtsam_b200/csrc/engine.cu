@@ -118,9 +118,8 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = reduce_blocks(g.count, 256, p->ctx->sm_count);
-    DISPATCH_TYPE(g.type, (error_kernel<TY><<<nb, 256, 0, st>>>(view(g), ectx(p, values), p->d_partials)));
-    reduce_partials_kernel<<<1, 256, 0, st>>>(p->d_partials, nb, slot, first ? 0 : 1);
-    p->ctx->launches += 2;
+    DISPATCH_TYPE(g.type, (error_kernel<TY><<<nb, 256, 0, st>>>(view(g), ectx(p, values), p->d_partials, p->d_counters, slot, first ? 0 : 1)));
+    p->ctx->launches += 1;
     first = false;
   }
   if (first) B200_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), st));
@@ -246,16 +245,16 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
           panel_kernel<<<dim3(std::max(1, (ncol + kTrsmCols - 1) / kTrsmCols), L.large_count), kTrsmCols, 0, st>>>(
               t, list, k0, p->d_scalars, p->d_rdiag);
           if (!big) {
-            update_kernel<64, 4><<<dim3(tiles(ncol, ncol, 64), L.large_count), 256, 0, st>>>(t, list, 0, K0, k0, p->d_rdiag);
+            update_kernel<64, 4, 32><<<dim3(tiles(ncol, ncol, 64), L.large_count), 256, 0, st>>>(t, list, 0, K0, k0, p->d_rdiag);
           } else {
             const int rows = std::min(K0 + kBig, L.large_max_nf) - k0 - 1;
-            update_kernel<64, 4><<<dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count), 256, 0, st>>>(t, list, 1, K0, k0, p->d_rdiag);
+            update_kernel<64, 4, 32><<<dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count), 256, 0, st>>>(t, list, 1, K0, k0, p->d_rdiag);
           }
           ctx->launches += 2;
         }
         if (big) {
           const int m = L.large_max_n - K0 - 1;
-          update_kernel<128, 8><<<dim3(tiles(m, m, 128), L.large_count), 256, 0, st>>>(t, list, 2, K0, 0, p->d_rdiag);
+          update_kernel<128, 8, 16><<<dim3(tiles(m, m, 128), L.large_count), 256, 0, st>>>(t, list, 2, K0, 0, p->d_rdiag);
           ctx->launches++;
         }
       }
@@ -293,10 +292,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
-    DISPATCH_TYPE(g.type, (linerr_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_delta, p->d_var_dof, p0, p1)));
-    reduce_partials_kernel<<<1, 256, 0, st>>>(p0, nb, &p->d_scalars->lin_err0, first ? 0 : 1);
-    reduce_partials_kernel<<<1, 256, 0, st>>>(p1, nb, &p->d_scalars->lin_err_delta, first ? 0 : 1);
-    ctx->launches += 3;
+    DISPATCH_TYPE(g.type, (linerr_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
+                                                                 &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1)));
+    ctx->launches += 1;
     first = false;
   }
   if (first) B200_CUDA(cudaMemsetAsync(&p->d_scalars->lin_err0, 0, 2 * sizeof(double), st));
@@ -623,7 +621,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_fused_run_ptr);
-  cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_scalars);
+  cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
   for (int i = 0; i < 2; i++) if (p->try_graph[i]) cudaGraphExecDestroy(p->try_graph[i]);
   cudaFree(p->d_saved_values);
@@ -889,6 +887,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, p->arena_doubles) * sizeof(double)));
   p->partial_cap = 2 * ctx->sm_count * 8;
   B200_CUDA(cudaMalloc((void**)&p->d_partials, (size_t)p->partial_cap * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&p->d_counters, 4 * sizeof(unsigned)));
+  B200_CUDA(cudaMemsetAsync(p->d_counters, 0, 4 * sizeof(unsigned), st));
   B200_CUDA(cudaMalloc((void**)&p->d_scalars, sizeof(Scalars)));
   B200_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(Scalars), st));
   B200_CUDA(cudaMallocHost((void**)&p->h_scalars, sizeof(Scalars)));

@@ -128,6 +128,7 @@ struct b200_problem {
   int64_t try_launches = 0;
   double* d_rdiag = nullptr;        // factored diagonal blocks published by panel_kernel
   double* d_partials = nullptr;     // block partial sums
+  unsigned* d_counters = nullptr;   // tickets of the last-block reductions
   int partial_cap = 0;
   b200::Scalars* d_scalars = nullptr;
   b200::Scalars* h_scalars = nullptr;  // pinned

@@ -61,6 +61,27 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return r;  // valid in thread 0
 }
 
+// Deterministic single-launch reduction: every block writes its partial, the LAST block to
+// finish (atomic ticket) adds them up in index order, so the result does not depend on the
+// order in which blocks ran.  `counter` must be 0 on entry and is reset for the next use.
+__device__ __forceinline__ void finish_sum(double block_value, double* partials, unsigned* counter, double* out,
+                                           int accumulate, double* sh) {
+  __shared__ bool last;
+  __syncthreads();   // `last` may still be read by a previous call in the same kernel
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = block_value;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;   // wraps back to 0
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partials + i);
+  s = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) *out = accumulate ? (*out + s) : s;
+}
+
 // out[0] (+)= sum(partials[0..n)) in a fixed order => bitwise reproducible
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int n, double* out, int accumulate) {
   __shared__ double sh[32];
@@ -94,7 +115,8 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupView g, EvalCtx c) 
 // nonlinear error: partial sums of 0.5*|whiten(r)|^2
 // ---------------------------------------------------------------------------
 template <int TYPE>
-__global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, double* partials, unsigned* counter,
+                                                    double* out, int accumulate) {
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
   __shared__ double sh[32];
@@ -110,7 +132,7 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
     acc += 0.5 * s;
   }
   acc = block_sum<256>(acc, sh);
-  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  finish_sum(acc, partials, counter, out, accumulate, sh);
 }
 
 // ---------------------------------------------------------------------------
@@ -118,8 +140,8 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
 // ---------------------------------------------------------------------------
 template <int TYPE>
 __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* __restrict__ delta,
-                                                     const int* __restrict__ var_dof, double* __restrict__ p0,
-                                                     double* __restrict__ p1) {
+                                                     const int* __restrict__ var_dof, double* p0, double* p1,
+                                                     unsigned* counters, double* out0, double* out1, int accumulate) {
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
   __shared__ double sh[32];
@@ -154,7 +176,8 @@ __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* 
   }
   a0 = block_sum<256>(a0, sh);
   a1 = block_sum<256>(a1, sh);
-  if (threadIdx.x == 0) { p0[blockIdx.x] = a0; p1[blockIdx.x] = a1; }
+  finish_sum(a0, p0, counters, out0, accumulate, sh);
+  finish_sum(a1, p1, counters + 1, out1, accumulate, sh);
 }
 
 // ---------------------------------------------------------------------------
@@ -693,6 +716,12 @@ panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, doub
   const int tid = threadIdx.x;
   __shared__ double invd[kNB];
   if (tid == 0) bad = 0;
+  // this thread's column of the row panel: issued now, consumed after the diagonal block is factored
+  const int j = j0 + tid;
+  double* col = M + k0 + (size_t)(j < n ? j : 0) * n;
+  double x[kNB];
+#pragma unroll
+  for (int p = 0; p < kNB; p++) x[p] = (j < n && p < nb) ? col[p] : 0.0;
   __syncthreads();
   // Cholesky of the diagonal block by ONE warp, the matrix in registers: lane j owns column j.
   // Step k: r = sqrt(a_kk) (lane k), row k scaled, then lane j subtracts R(k,i) R(k,j) from its
@@ -739,12 +768,7 @@ panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, doub
     double* R = rdiag + (size_t)blockIdx.y * kNB * kNB;
     for (int e = tid; e < nb * nb; e += kTrsmCols) R[e] = Dg[e % nb][e / nb];
   }
-  const int j = j0 + tid;
   if (j < n) {  // x = R_kk^-T a, forward substitution
-    double* col = M + k0 + (size_t)j * n;
-    double x[kNB];
-#pragma unroll
-    for (int p = 0; p < kNB; p++) x[p] = p < nb ? col[p] : 0.0;
 #pragma unroll
     for (int p = 0; p < kNB; p++) {
       if (p < nb) {
@@ -768,9 +792,8 @@ panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, doub
 //   2 TRAIL   pa=K0      pb=K0+kBig rows [pb, n)             (one K=kBig update per big panel)
 // The CTA with blockIdx.x == 0 also moves R_kk from rdiag into the front (modes 0 and 1).
 constexpr int kBig = 128;
-constexpr int kKC = 16;
 
-template <int TILE, int RB>
+template <int TILE, int RB, int kKC>
 __global__ void __launch_bounds__(256)
 update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0, const double* __restrict__ rdiag) {
   __shared__ double Pi[kKC][TILE + 1];

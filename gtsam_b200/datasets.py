@@ -112,10 +112,19 @@ def sphere(layers: int = 50, per_ring: int = 50, radius: float = 50.0, seed: int
         order = np.arange(n)
     elif ordering == "reverse":
         order = np.arange(n)[::-1].copy()
+    elif ordering in ("colamd", "metis"):
+        # orderings are INPUTS at the boundary: these were produced by the reference's own
+        # Ordering::Colamd / Ordering::Metis (oracle/ref_harness order) for exactly this graph
+        # (layers=50, per_ring=50; the structure does not depend on the seed) and are shipped as data
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"data_sphere{n}_{ordering}.npy")
+        if not os.path.exists(path):
+            raise ValueError(f"no stored {ordering} ordering for a {n}-pose sphere ({path})")
+        order = np.load(path).astype(np.int64)
     else:
         raise ValueError(ordering)
     pr = P.Problem(np.full(n, P.VAR_POSE3), values, order, [between, prior], name=f"sphere{n}")
-    pr.meta = dict(kind="sphere", layers=layers, per_ring=per_ring, seed=seed, gt=pack_pose(R, t))
+    pr.meta = dict(kind="sphere", layers=layers, per_ring=per_ring, seed=seed, gt=pack_pose(R, t), ordering=ordering)
     return pr
 
 
@@ -192,7 +201,9 @@ def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibili
 
 WORKLOADS = {
     # name: (builder, kwargs) — BASELINE.json configs
-    "sphere2500": (sphere, dict(layers=50, per_ring=50)),
+    "sphere2500": (sphere, dict(layers=50, per_ring=50, ordering="colamd")),   # configs[1]: 2.5k Pose3 / 9.8k Between, COLAMD
+    "sphere2500_metis": (sphere, dict(layers=50, per_ring=50, ordering="metis")),
+    "sphere2500_natural": (sphere, dict(layers=50, per_ring=50)),
     "bal_c3": (bal, dict(ncams=100, npoints=50000)),                 # configs[2]: 300k factors
     "bal_1m": (bal, dict(ncams=300, npoints=166667)),                # north_star 1M-factor target
     "bal_c4": (bal, dict(ncams=1000, npoints=500000)),               # configs[3]: 3M factors
