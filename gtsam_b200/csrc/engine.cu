@@ -719,7 +719,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       return sig_less(a, b);
     });
     const int nfl = (int)fused_list.size();
-    const int run_max_pt = getenv("B200_NO_LEAF_RUNS") ? 1 : std::max(1, std::min(64, nfl / (ctx->sm_count * 32)));
+    int run_max_pt = getenv("B200_NO_LEAF_RUNS") ? 1 : std::max(1, std::min(64, nfl / (ctx->sm_count * 32)));
+    if (getenv("B200_LEAF_RUN_MAX")) run_max_pt = std::max(1, atoi(getenv("B200_LEAF_RUN_MAX")));
     run_ptr.push_back(0);
     for (int kd = 0; kd < 3; kd++) p->leaf_run_begin[kd] = p->leaf_run_end[kd] = 0;
     for (int i = 1; i <= nfl; i++) {
