@@ -76,7 +76,7 @@ def rot_ypr(y, p, r):
 
 # ---- config 2: sphere ------------------------------------------------------------
 def sphere(layers: int = 50, per_ring: int = 50, radius: float = 50.0, seed: int = 7,
-           ordering: str = "natural") -> P.Problem:
+           ordering: str = "natural", noise: str = "diagonal") -> P.Problem:
     rng = np.random.default_rng(seed)
     n = layers * per_ring
     idx = np.arange(n)
@@ -106,7 +106,18 @@ def sphere(layers: int = 50, per_ring: int = 50, radius: float = 50.0, seed: int
     values = pack_pose(R0, t0).ravel()
     prior = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0]]), pack_pose(R[0], t[0])[None],
                           P.NOISE_DIAGONAL, np.sqrt(np.array([1e-6] * 3 + [1e-4] * 3)))
-    between = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, edges, pack_pose(Rz, tz), P.NOISE_DIAGONAL, sig)
+    if noise == "diagonal":
+        between = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, edges, pack_pose(Rz, tz), P.NOISE_DIAGONAL, sig)
+    elif noise == "gaussian":
+        # per-factor full information matrices (what g2o EDGE_SE3:QUAT lines carry,
+        # gtsam/slam/dataset.cpp:838-859): R = upper Cholesky factor of a random SPD information
+        ne = edges.shape[0]
+        A = rng.normal(size=(ne, 6, 6)) * 0.3
+        info = np.einsum("nij,nkj->nik", A, A) + np.diag(prec)[None]
+        Rup = np.transpose(np.linalg.cholesky(info), (0, 2, 1))          # info = R^T R, R upper
+        between = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, edges, pack_pose(Rz, tz), P.NOISE_GAUSSIAN, Rup.reshape(ne, 36))
+    else:
+        raise ValueError(noise)
     # graph order as Pose3SLAMExample_g2o builds it: between factors, then the prior
     if ordering == "natural":
         order = np.arange(n)

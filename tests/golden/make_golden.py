@@ -50,6 +50,7 @@ def main():
     emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"))
     emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3)
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
+    emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2)
     emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
     # the reference's own end-to-end golden: tests/testGeneralSFMFactorB.cpp:44-63 (0.0199833 +- 1e-5)
     from gtsam_b200.problem import Problem

@@ -181,3 +181,25 @@ def test_full_size_lm_iteration_decreases_error(gpu_ctx):
     e0 = lm.error()
     lm.iterate()
     assert lm.error() < 0.1 * e0 and lm.iterations() == 1
+
+
+@pytest.mark.parametrize("name", ["priors_only", "two_components_empty_group", "single_observation_points"])
+def test_cuda_edge_cases(gpu_ctx, name):
+    """Forests, empty groups, rank-deficient leaves: same status, delta and LM behaviour as the oracle."""
+    prob = util.edge_case_problems()[name]
+    dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+    assert abs(dev.error() - orc.error()) <= 1e-12 * max(1.0, orc.error())
+    dev.linearize(); orc.linearize()
+    for lam in (0.0, 1e-3):
+        st, e0, e1, _ = dev.solve(lam)
+        so, f0, f1, _ = orc.solve(lam)
+        assert st == so
+        if st == 0:
+            assert util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+            assert abs(e1 - f1) <= 1e-9 * max(1.0, f0)
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, prob, device_problem=dev)
+    olm = orc.lm(lm.params()._c)
+    for _ in range(3):
+        lm.iterate(); orc.lm_iterate(olm)
+        assert abs(lm.error() - olm.state.error) <= 1e-8 * max(1.0, olm.state.error)
+        assert lm.lambda_() == olm.state.lambda_

@@ -142,3 +142,14 @@ def test_invalid_inputs_rejected(built):
     prob.groups[0].noise_kind = 9                  # e.g. a Constrained / Robust model
     desc, keep = prob.c_desc()
     assert L.b200_symbolic_create(C.byref(desc), C.byref(h)) == P.UNSUPPORTED_NOISE
+
+
+@pytest.mark.parametrize("name", ["priors_only", "two_components_empty_group", "single_observation_points"])
+def test_symbolic_edge_cases_match_oracle(built, name):
+    prob = util.edge_case_problems()[name]
+    info, fp, fv, sp, sv, par, lvl = _symbolic(prob)
+    ofp, ofv, osp, osv, opar = O.OracleProblem(prob).cliques()
+    assert np.array_equal(fp, ofp) and np.array_equal(fv, ofv) and np.array_equal(sp, osp)
+    assert np.array_equal(sv, osv) and np.array_equal(par, opar)
+    if name == "priors_only":
+        assert info.ncliques == 4 and np.all(par == -1) and info.nlevels == 1

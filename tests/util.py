@@ -7,7 +7,7 @@ from gtsam_b200 import problem as P
 from oracle import refio
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["bal_tiny_s2", "bal_tiny_bundler", "bal_tiny_colamd", "sphere_tiny", "sphere_small_colamd",
+CASES = ["bal_tiny_s2", "bal_tiny_bundler", "bal_tiny_colamd", "sphere_tiny", "sphere_tiny_gaussian", "sphere_small_colamd",
          "sphere_small_metis", "dubrovnik_3_7_unit", "dubrovnik_3_7_priors"]
 CERES_CASES = {"bal_tiny_bundler"}   # LM trace generated with LevenbergMarquardtParams::CeresDefaults
 
@@ -121,3 +121,33 @@ def check_against_dump(be, prob, ref, lam, diag, tol_j=1e-12, tol_delta=1e-8, to
         cols.append(mine.shape[1] - 1)
         scale = max(1.0, np.abs(Rref).max())
         assert np.abs(mine[:, cols] - Rref).max() <= 1e-7 * scale * loose, (c, fr)
+
+
+def edge_case_problems():
+    """Degenerate shapes the reference handles: a forest of single-variable cliques (priors only),
+    an empty factor group, two disconnected components, a point observed by one camera only."""
+    import numpy as np
+    from gtsam_b200 import datasets
+    out = {}
+    rng = np.random.default_rng(0)
+    R, t = datasets.se3_exp(rng.normal(size=(4, 6)) * 0.3)
+    poses = datasets.pack_pose(R, t)
+    pri = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.arange(4)[:, None], poses + 0.01, P.NOISE_ISOTROPIC, np.array([0.5]))
+    out["priors_only"] = P.Problem(np.full(4, P.VAR_POSE3), poses.ravel(), np.array([2, 0, 3, 1]), [pri])
+    empty = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, np.zeros((0, 2)), np.zeros((0, 12)), P.NOISE_DIAGONAL, np.ones(6))
+    btw = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, np.array([[0, 1], [2, 3]]), poses[:2] * 0 + datasets.pack_pose(*datasets.se3_exp(rng.normal(size=(2, 6)) * 0.2)),
+                        P.NOISE_DIAGONAL, np.full(6, 0.3))
+    pri2 = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0], [2]]), poses[[0, 2]], P.NOISE_UNIT)
+    out["two_components_empty_group"] = P.Problem(np.full(4, P.VAR_POSE3), poses.ravel(), np.arange(4), [empty, btw, pri2])
+    b = datasets.make("bal_tiny", ncams=10, npoints=30)
+    # keep only the first observation of the last 5 points: one-camera points (rank deficient without damping)
+    g = b.groups[0]
+    keep = np.ones(g.count, dtype=bool)
+    for pt in range(25, 30):
+        idx = np.where(g.keys[:, 1] == 10 + pt)[0]
+        keep[idx[1:]] = False
+    pg = b.groups[1]
+    b = P.Problem(b.var_type, b.values, b.ordering, [P.FactorGroup(g.type, g.keys[keep], g.meas[keep], g.noise_kind, g.noise),
+                                                     P.FactorGroup(pg.type, pg.keys, pg.meas, pg.noise_kind, pg.noise)], b.cal)
+    out["single_observation_points"] = b
+    return out
