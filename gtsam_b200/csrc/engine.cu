@@ -74,7 +74,7 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
-             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_COUNT };
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_LINEARIZE_MINOR, PH_COUNT };
 struct PhaseScope {
   b200_problem* p; int ph; size_t idx; bool on;
   PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
@@ -102,6 +102,20 @@ static void resolve_profile(b200_problem* p) {  // call after a stream sync
   p->ev_used = 0;
 }
 
+// Kernel launch with the programmatic-dependent-launch attribute (see pdl_sync in kernels.cuh).
+static const bool g_use_pdl = getenv("B200_NO_PDL") == nullptr;
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int allreduce_sum(b200_problem* p, double* buf, size_t n);
 static int allreduce_max_int(b200_problem* p, int* buf, size_t n);
 
@@ -118,7 +132,7 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = reduce_blocks(g.count, 256, p->ctx->sm_count);
-    DISPATCH_TYPE(g.type, (error_kernel<TY><<<nb, 256, 0, st>>>(view(g), ectx(p, values), p->d_partials, p->d_counters, slot, first ? 0 : 1)));
+    DISPATCH_TYPE(g.type, (launch_k(error_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), ectx(p, values), p->d_partials, p->d_counters, slot, first ? 0 : 1)));
     p->ctx->launches += 1;
     first = false;
   }
@@ -129,11 +143,12 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
 
 static int enqueue_linearize(b200_problem* p) {
   cudaStream_t st = p->ctx->stream;
-  PhaseScope ps(p, PH_LINEARIZE);
   for (auto& g : p->groups) {
     if (!g.count) continue;
+    // tiny groups (a handful of priors) are pure launch latency: timed apart from the bandwidth kernels
+    PhaseScope ps(p, g.count >= 4096 ? PH_LINEARIZE : PH_LINEARIZE_MINOR);
     const int nb = (int)((g.count + 127) / 128);
-    DISPATCH_TYPE(g.type, (linearize_kernel<TY><<<nb, 128, 0, st>>>(view(g), ectx(p, p->d_values))));
+    DISPATCH_TYPE(g.type, (launch_k(linearize_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values))));
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
@@ -147,7 +162,7 @@ static int enqueue_hdiag(b200_problem* p) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = (int)((g.count + 127) / 128);
-    DISPATCH_TYPE(g.type, (hdiag_kernel<TY><<<nb, 128, 0, st>>>(view(g), p->d_var_dof, p->d_hdiag)));
+    DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag)));
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
@@ -169,7 +184,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     for (auto& g : p->groups) {
       if (!g.n_nonleaf) continue;   // every factor of the group is owned by a fused leaf clique
       const int nb = (int)((g.count + 127) / 128);
-      DISPATCH_TYPE(g.type, (assemble_kernel<TY><<<nb, 128, 0, st>>>(view(g), t)));
+      DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), t)));
       ctx->launches++;
     }
   }
@@ -177,7 +192,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     PhaseScope ps(p, PH_DAMP);
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
     if (ctx->rank == 0)   // the shared top is summed over ranks: its damping priors are added once
-    damp_kernel<<<(int)((p->ndelta + 255) / 256), 256, 0, st>>>(p->d_arena, p->d_diag_index, (int)p->ndelta, p->d_lambda,
+    launch_k(damp_kernel, dim3((int)((p->ndelta + 255) / 256)), dim3(256), 0, st, p->d_arena, p->d_diag_index, (int)p->ndelta, p->d_lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
     ctx->launches++;
   }
@@ -189,7 +204,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (p->leaf_run_end[0] > p->leaf_run_begin[0]) {
       const int nr = p->leaf_run_end[0] - p->leaf_run_begin[0], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t sm = (size_t)kWarpsPerBlock * p->leaf_lb_cap * sizeof(double);
-      leaf_fused_kernel<<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[0], nr,
+      launch_k(leaf_fused_kernel, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[0], nr,
                                                            p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
                                                            p->d_scalars, p->leaf_lb_cap, 0);
       ctx->launches++;
@@ -197,7 +212,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (p->leaf_run_end[1] > p->leaf_run_begin[1]) {
       const int nr = p->leaf_run_end[1] - p->leaf_run_begin[1], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 6 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
-      leaf_point_kernel<6><<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[1], nr,
+      launch_k(leaf_point_kernel<6>, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[1], nr,
                                                               p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
                                                               p->d_scalars, p->leaf_acc_cap);
       ctx->launches++;
@@ -205,7 +220,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (p->leaf_run_end[2] > p->leaf_run_begin[2]) {
       const int nr = p->leaf_run_end[2] - p->leaf_run_begin[2], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 9 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
-      leaf_point_kernel<9><<<nb, kWarpsPerBlock * 32, sm, st>>>(t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[2], nr,
+      launch_k(leaf_point_kernel<9>, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[2], nr,
                                                               p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
                                                               p->d_scalars, p->leaf_acc_cap);
       ctx->launches++;
@@ -225,7 +240,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       PhaseScope ps(p, PH_ELIM_SMALL);
       const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t smem = (size_t)kWarpsPerBlock * p->max_small_n * p->max_small_n * sizeof(double);
-      elim_small_kernel<<<nb, kWarpsPerBlock * 32, smem, st>>>(t, p->d_lvl_small + L.small_begin, L.small_count,
+      launch_k(elim_small_kernel, dim3(nb), dim3(kWarpsPerBlock * 32), smem, st, t, p->d_lvl_small + L.small_begin, L.small_count,
                                                                p->max_small_n, p->d_scalars);
       ctx->launches++;
     }
@@ -242,25 +257,25 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       for (int K0 = 0; K0 < L.large_max_nf; K0 += kBig) {
         for (int k0 = K0; k0 < std::min(K0 + kBig, L.large_max_nf); k0 += kNB) {
           const int ncol = L.large_max_n - k0 - 1;
-          panel_kernel<<<dim3(std::max(1, (ncol + kTrsmCols - 1) / kTrsmCols), L.large_count), kTrsmCols, 0, st>>>(
+          launch_k(panel_kernel, dim3(dim3(std::max(1, (ncol + kTrsmCols - 1) / kTrsmCols), L.large_count)), dim3(kTrsmCols), 0, st, 
               t, list, k0, p->d_scalars, p->d_rdiag);
           if (!big) {
-            update_kernel<64, 4, 32><<<dim3(tiles(ncol, ncol, 64), L.large_count), 256, 0, st>>>(t, list, 0, K0, k0, p->d_rdiag);
+            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(ncol, ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 0, K0, k0, p->d_rdiag);
           } else {
             const int rows = std::min(K0 + kBig, L.large_max_nf) - k0 - 1;
-            update_kernel<64, 4, 32><<<dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count), 256, 0, st>>>(t, list, 1, K0, k0, p->d_rdiag);
+            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 1, K0, k0, p->d_rdiag);
           }
           ctx->launches += 2;
         }
         if (big) {
           const int m = L.large_max_n - K0 - 1;
-          update_kernel<128, 8, 16><<<dim3(tiles(m, m, 128), L.large_count), 256, 0, st>>>(t, list, 2, K0, 0, p->d_rdiag);
+          launch_k(update_kernel<128, 8, 16>, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, 2, K0, 0, p->d_rdiag);
           ctx->launches++;
         }
       }
       const int64_t w = L.large_max_ns + 1;
       const int gx = (int)std::min<int64_t>((w * w + 255) / 256, 4096);
-      extend_add_kernel<<<dim3(gx, L.large_count), 256, 0, st>>>(t, list);
+      launch_k(extend_add_kernel, dim3(dim3(gx, L.large_count)), dim3(256), 0, st, t, list);
       ctx->launches++;
     }
   }
@@ -272,13 +287,13 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     const LevelPlan& L = p->levels[l];
     if (L.large_count) {
       const int nblk = (L.large_max_nf + kBsRows - 1) / kBsRows;
-      backsub_large_kernel<<<dim3(nblk, L.large_count), 256, 0, st>>>(t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars,
+      launch_k(backsub_large_kernel, dim3(dim3(nblk, L.large_count)), dim3(256), 0, st, t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars,
                                                                       p->d_bs_flags, p->d_bs_flag_base, L.large_begin, 1);
       ctx->launches++;
     }
     if (L.bsmall_count) {
       const int nb = (L.bsmall_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      backsub_small_kernel<<<nb, kWarpsPerBlock * 32, 0, st>>>(t, p->d_lvl_bsmall + L.bsmall_begin, L.bsmall_count,
+      launch_k(backsub_small_kernel, dim3(nb), dim3(kWarpsPerBlock * 32), 0, st, t, p->d_lvl_bsmall + L.bsmall_begin, L.bsmall_count,
                                                                p->d_delta, p->d_scalars);
       ctx->launches++;
     }
@@ -292,7 +307,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
-    DISPATCH_TYPE(g.type, (linerr_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
+    DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
                                                                  &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1)));
     ctx->launches += 1;
     first = false;
@@ -314,7 +329,7 @@ static int enqueue_try_step(b200_problem* p) {
   cudaStream_t st = p->ctx->stream;
   {
     PhaseScope ps(p, PH_RETRACT);
-    retract_kernel<<<(int)((p->nvars + 127) / 128), 128, 0, st>>>(p->d_values, p->d_delta, p->d_val_off, p->d_var_dof,
+    launch_k(retract_kernel, dim3((int)((p->nvars + 127) / 128)), dim3(128), 0, st, p->d_values, p->d_delta, p->d_val_off, p->d_var_dof,
                                                                    p->d_var_type, (int)p->nvars, p->d_new_values);
     p->ctx->launches++;
   }
@@ -1037,7 +1052,7 @@ int b200_profile_phase_count(void) { return PH_COUNT; }
 const char* b200_profile_phase_name(int i) {
   static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
                                         "eliminate_large", "back_substitute", "linear_error", "retract", "error",
-                                        "leaf_fused", "allreduce_top"};
+                                        "leaf_fused", "allreduce_top", "linearize_small_groups"};
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {

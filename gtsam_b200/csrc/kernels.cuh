@@ -39,6 +39,21 @@ __device__ unsigned char kPairA[B200_NUM_FACTOR_TYPES][kMaxPairs];
 __device__ unsigned char kPairB[B200_NUM_FACTOR_TYPES][kMaxPairs];
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the LM try is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the
+// previous kernel is still draining; it must therefore wait here before touching anything the
+// previous kernel wrote, and it immediately lets the NEXT kernel start its own launch.  The
+// try is a chain of ~50-300 small dependent kernels: the kernel-boundary latency, not the
+// kernels, is what this hides.  No-ops when the kernel was launched without the attribute.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  cudaGridDependencySynchronize();
+  cudaTriggerProgrammaticLaunchCompletion();
+#endif
+}
+
+// ---------------------------------------------------------------------------
 // block reduction helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -84,6 +99,7 @@ __device__ __forceinline__ void finish_sum(double block_value, double* partials,
 
 // out[0] (+)= sum(partials[0..n)) in a fixed order => bitwise reproducible
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int n, double* out, int accumulate) {
+  pdl_sync();
   __shared__ double sh[32];
   double s = 0;
   for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
@@ -95,7 +111,8 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 // linearize
 // ---------------------------------------------------------------------------
 template <int TYPE>
-__global__ void __launch_bounds__(128) linearize_kernel(GroupView g, EvalCtx c) {
+__global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linearize_kernel(GroupView g, EvalCtx c) {
+  pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +134,7 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupView g, EvalCtx c) 
 template <int TYPE>
 __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, double* partials, unsigned* counter,
                                                     double* out, int accumulate) {
+  pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
   __shared__ double sh[32];
@@ -142,6 +160,7 @@ template <int TYPE>
 __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* __restrict__ delta,
                                                      const int* __restrict__ var_dof, double* p0, double* p1,
                                                      unsigned* counters, double* out0, double* out1, int accumulate) {
+  pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
   __shared__ double sh[32];
@@ -205,6 +224,7 @@ __device__ __forceinline__ void add_block(double* __restrict__ Mf, int ld, int s
 
 template <int TYPE>
 __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) {
+  pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +254,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) 
 // hessianDiagonal: gtsam/linear/JacobianFactor.cpp:516-541
 template <int TYPE>
 __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __restrict__ var_dof, double* hdiag) {
+  pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2 };
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,6 +275,7 @@ __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __re
 __global__ void damp_kernel(double* arena, const int64_t* __restrict__ diag_index, int n,
                             const double* __restrict__ lambda_ptr, const double* __restrict__ hdiag, double min_diag,
                             double max_diag) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double lambda = *lambda_ptr;   // device resident: the launch sequence is lambda independent (CUDA graph)
@@ -282,6 +304,7 @@ __device__ __forceinline__ int dexp(double x) {
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_n, Scalars* sc) {
+  pdl_sync();
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerBlock + warp;
@@ -369,6 +392,7 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
                   int nruns, const int* __restrict__ fac_ptr, const int2* __restrict__ fac,
                   const double* __restrict__ lambda_ptr, const double* __restrict__ hdiag, double min_diag,
                   double max_diag, Scalars* sc, int lb_cap, int acc_cap) {
+  pdl_sync();
   extern __shared__ double leaf_sm[];
   const double lambda = *lambda_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -507,6 +531,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 leaf_point_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr, int nruns,
                   const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
                   const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int acc_cap) {
+  pdl_sync();
   constexpr int FS = 5 * DC + 2;   // per factor: S' (3 x DC), A_c (2 x DC), b (2)
   extern __shared__ double leaf_sm[];
   const double lambda = *lambda_ptr;
@@ -704,6 +729,7 @@ constexpr int kTrsmCols = 128;
 
 __global__ void __launch_bounds__(kTrsmCols)
 panel_kernel(TreeView t, const int* __restrict__ list, int k0, Scalars* sc, double* __restrict__ rdiag) {
+  pdl_sync();
   __shared__ double Dg[kNB][kNB + 1];
   __shared__ int bad;
   const int c = list[blockIdx.y];
@@ -796,6 +822,7 @@ constexpr int kBig = 128;
 template <int TILE, int RB, int kKC>
 __global__ void __launch_bounds__(256)
 update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0, const double* __restrict__ rdiag) {
+  pdl_sync();
   __shared__ double Pi[kKC][TILE + 1];
   __shared__ double Pj[kKC][TILE + 1];
   const int c = list[blockIdx.y];
@@ -865,6 +892,7 @@ update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0
 }
 
 __global__ void __launch_bounds__(256) extend_add_kernel(TreeView t, const int* __restrict__ list) {
+  pdl_sync();
   const int c = list[blockIdx.y];
   const int p = t.parent[c];
   if (p < 0) return;
@@ -889,6 +917,7 @@ __global__ void __launch_bounds__(256) extend_add_kernel(TreeView t, const int* 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double* delta, Scalars* sc) {
+  pdl_sync();
   __shared__ double xs[kWarpsPerBlock][kSmallMaxN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerBlock + warp;
@@ -945,6 +974,7 @@ constexpr int kBsRows = 64;
 __global__ void __launch_bounds__(256)
 backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc, int* flags,
                      const int* __restrict__ flag_base, int list_begin, int epoch) {
+  pdl_sync();
   __shared__ double part[4][kBsRows];
   __shared__ double rhs[kBsRows];
   __shared__ double Dg[3][32][33];   // [0]: rows 0..31 diag, [1]: rows 32..63 diag, [2]: coupling rows 0..31 x cols 32..63
@@ -1030,6 +1060,7 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
 __global__ void retract_kernel(const double* __restrict__ values, const double* __restrict__ delta,
                                const int* __restrict__ val_off, const int* __restrict__ var_dof,
                                const int* __restrict__ var_type, int nvars, double* __restrict__ out) {
+  pdl_sync();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvars) return;
   const double* x = values + val_off[v];
