@@ -12,6 +12,9 @@
  * Variable id i <-> gtsam::Key i (plain integers), so Key order == id order.
  */
 #include "problem_io.hpp"
+#include <gtsam/slam/dataset.h>
+#include <gtsam/sfm/SfmData.h>
+#include <gtsam/inference/Symbol.h>
 
 /* ---- named-array output container ---------------------------------------- */
 struct Out {
@@ -335,6 +338,47 @@ static int cmd_balfile(const std::string& path, const std::string& outp, int mod
   return 0;
 }
 
+/* Convert a g2o 3D pose graph through the reference's own loader (gtsam/slam/dataset.cpp:922-944)
+ * into a problem file, with the prior of examples/Pose3SLAMExample_g2o.cpp:42-49 and the
+ * COLAMD ordering GaussNewtonOptimizer would compute. */
+static int cmd_g2ofile(const std::string& path, const std::string& outp) {
+  auto [graph, initial] = readG2o(path, true);
+  auto priorModel = noiseModel::Diagonal::Variances((Vector(6) << 1e-6, 1e-6, 1e-6, 1e-4, 1e-4, 1e-4).finished());
+  const Key firstKey = initial->keys().front();
+  graph->addPrior(firstKey, Pose3(), priorModel);
+  Prob p;
+  std::map<Key, int64_t> id;
+  for (const auto& kv : *initial) { id[kv.key] = (int64_t)id.size(); }
+  p.nvars = (int64_t)id.size();
+  p.var_type.assign(p.nvars, 0);
+  for (const auto& kv : *initial) {
+    double x[12];
+    putpose(initial->at<Pose3>(kv.key), x);
+    p.values.insert(p.values.end(), x, x + 12);
+  }
+  Group gb; gb.type = 0; gb.noise_kind = 3; gb.per_factor = 1; gb.has_cal = 0; gb.gi0 = 0; gb.count = 0;
+  for (const auto& f : *graph) {
+    auto b = std::dynamic_pointer_cast<BetweenFactor<Pose3>>(f);
+    if (!b) continue;
+    gb.keys.push_back(id[b->key1()]); gb.keys.push_back(id[b->key2()]);
+    double x[12];
+    putpose(b->measured(), x);
+    gb.meas.insert(gb.meas.end(), x, x + 12);
+    const Matrix R = std::dynamic_pointer_cast<noiseModel::Gaussian>(b->noiseModel())->R();
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) gb.noise.push_back(R(r, c));
+    gb.count++;
+  }
+  Group gp; gp.type = 1; gp.noise_kind = 2; gp.per_factor = 0; gp.has_cal = 0; gp.count = 1; gp.gi0 = gb.count;
+  gp.keys = {id[firstKey]};
+  { double x[12]; putpose(Pose3(), x); gp.meas.assign(x, x + 12); }
+  for (double v : {1e-6, 1e-6, 1e-6, 1e-4, 1e-4, 1e-4}) gp.noise.push_back(std::sqrt(v));
+  p.groups = {gb, gp};
+  Ordering ord = Ordering::Colamd(*graph);
+  for (Key k : ord) p.ordering.push_back(id[k]);
+  save(p, outp);
+  return 0;
+}
+
 /* known-answer vectors for the geometry primitives, incl. near-0 / near-pi */
 static int cmd_kat(const std::string& outp) {
   std::mt19937 rng(123);
@@ -388,6 +432,7 @@ int main(int argc, char** argv) {
   if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));
   if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);
   if (cmd == "kat" && argc >= 3) return cmd_kat(argv[2]);
+  if (cmd == "g2ofile" && argc >= 4) return cmd_g2ofile(argv[2], argv[3]);
   if (cmd == "balfile" && argc >= 4) return cmd_balfile(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 0);
   fprintf(stderr, "bad arguments\n");
   return 2;

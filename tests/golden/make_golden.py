@@ -52,6 +52,28 @@ def main():
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
     emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2)
     emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
+    # ---- input formats: synthetic text files written by gtsam_b200.io, parsed by the
+    # REFERENCE's loaders (readG2o / SfmData::FromBalFile) into *.prob.bin; tests compare our readers with them
+    import numpy as np
+    from gtsam_b200 import io, problem as Pm
+    ddir = os.path.join(HERE, "data")
+    os.makedirs(ddir, exist_ok=True)
+    sp = datasets.sphere(layers=4, per_ring=6, seed=21, noise="gaussian")
+    R = sp.groups[0].noise.reshape(-1, 6, 6)
+    info = np.einsum("nki,nkj->nij", R, R)
+    g2o_txt = os.path.join(ddir, "synthetic_sphere.g2o")
+    io.write_g2o_3d(g2o_txt, sp.values.reshape(-1, 12), sp.groups[0].keys, sp.groups[0].meas, info)
+    subprocess.check_call([H, "g2ofile", g2o_txt, os.path.join(HERE, "synthetic_sphere_g2o.prob.bin")])
+    bl = datasets.make("bal_tiny", camera_model="bundler", seed=9)
+    nc = int((bl.var_type == Pm.VAR_CAM_BUNDLER).sum())
+    bal_txt = os.path.join(ddir, "synthetic_bal.txt")
+    io.write_bal(bal_txt, bl.values[:nc * 17].reshape(nc, 17), bl.values[nc * 17:].reshape(-1, 3),
+                 bl.groups[0].keys[:, 0], bl.groups[0].keys[:, 1] - nc, bl.groups[0].meas)
+    subprocess.check_call([H, "balfile", bal_txt, os.path.join(HERE, "synthetic_bal.prob.bin"), "1"])
+    # the reference's own example data through its own parser: Pose3SLAMExample_g2o on pose3example.txt
+    p3 = os.path.join(HERE, "pose3example.prob.bin")
+    subprocess.check_call([H, "g2ofile", os.path.join(REF_DATA, "pose3example.txt"), p3])
+    emit("pose3example", Pm.Problem.load(p3), lm_iters=10, gn_iters=5)
     # the reference's own end-to-end golden: tests/testGeneralSFMFactorB.cpp:44-63 (0.0199833 +- 1e-5)
     from gtsam_b200.problem import Problem
     with tempfile.TemporaryDirectory() as td:
