@@ -45,7 +45,7 @@ static int upload(T** dst, const std::vector<T>& v, cudaStream_t st) { return up
 static GroupView view(const b200_problem::Group& g) {
   GroupView v;
   v.type = g.type; v.noise_kind = g.noise_kind; v.per_factor = g.per_factor; v.noise_size = g.noise_size;
-  v.count = (int)g.count; v.keys = g.d_keys; v.meas = g.d_meas; v.noise = g.d_noise; v.cal_index = g.d_cal;
+  v.count = (int)g.count; v.keys = g.d_keys; v.meas = g.d_meas; v.noise = g.d_noise; v.cal_index = g.d_cal; v.body = g.d_body;
   v.J = g.d_J; v.scat = g.d_scat;
   return v;
 }
@@ -627,7 +627,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
   for (auto& g : p->groups) {
-    cudaFree(g.d_keys); cudaFree(g.d_meas); cudaFree(g.d_noise); cudaFree(g.d_cal); cudaFree(g.d_J); cudaFree(g.d_scat);
+    cudaFree(g.d_keys); cudaFree(g.d_meas); cudaFree(g.d_noise); cudaFree(g.d_cal); cudaFree(g.d_body); cudaFree(g.d_J); cudaFree(g.d_scat);
   }
   cudaFree(p->d_values); cudaFree(p->d_new_values); cudaFree(p->d_delta); cudaFree(p->d_hdiag);
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
@@ -808,6 +808,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     if (s.noise_per_factor) UP(upload(&g.d_noise, hnoise, st));
     else UP(upload(&g.d_noise, s.noise, (size_t)g.noise_size, st));
     if (!hcal.empty()) UP(upload(&g.d_cal, hcal, st));
+    if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.body_P_sensor) UP(upload(&g.d_body, s.body_P_sensor, 12, st));
     B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)nl * g.d * g.ncols) * sizeof(double)));
   }
   // ---- junction tree tables ----

@@ -31,6 +31,7 @@ struct GroupView {
   const double* meas;      // AoS, MEAS doubles per factor
   const double* noise;     // shared payload or per-factor AoS
   const int* cal_index;    // may be null
+  const double* body;      // body_P_sensor (12 doubles) of a projection group, or null
   double* J;               // SoA: J[e * count + f], e = r + c*D (column-major element order)
   const int4* scat;        // (clique, slot0, slot1, unused) per factor
 };
@@ -93,6 +94,7 @@ struct b200_problem {
     double* d_meas = nullptr;
     double* d_noise = nullptr;
     int* d_cal = nullptr;
+    double* d_body = nullptr;
     double* d_J = nullptr;
     int4* d_scat = nullptr;
     int64_t n_nonleaf = 0;   // factors NOT owned by a fused leaf clique

@@ -34,7 +34,7 @@ template <int TYPE, bool WITH_J> struct Eval;
 //   hx = p1^-1 p2;  r = Logmap(measured^-1 hx);  H1 = -Ad(hx^-1);  H2 = I.
 template <bool WITH_J> struct Eval<B200_FACTOR_BETWEEN_POSE3, WITH_J> {
   static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int k1, const double* __restrict__ z, int,
-                                             double* M) {
+                                             const double*, double* M) {
     enum { NC = 13 };
     const Pose x1 = load_pose(c.values + c.val_off[k0]);
     const Pose x2 = load_pose(c.values + c.val_off[k1]);
@@ -67,7 +67,7 @@ template <bool WITH_J> struct Eval<B200_FACTOR_BETWEEN_POSE3, WITH_J> {
 
 // PriorFactor<Pose3>::evaluateError — gtsam/nonlinear/PriorFactor.h:98-102: r = -Local(x, prior), H = I
 template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POSE3, WITH_J> {
-  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, double* M) {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, const double*, double* M) {
     enum { NC = 7 };
     const Pose x = load_pose(c.values + c.val_off[k0]);
     const Pose pz = load_pose(z);
@@ -85,7 +85,7 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POSE3, WITH_J> {
 };
 
 template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POINT3, WITH_J> {
-  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, double* M) {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, const double*, double* M) {
     enum { NC = 4 };
     const double* x = c.values + c.val_off[k0];
 #pragma unroll
@@ -102,7 +102,7 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POINT3, WITH_J> {
 // PriorFactor<PinholeCamera<Cal3Bundler>>: Local = [pose local ; (f,k1,k2) difference]
 // (gtsam/geometry/PinholeCamera.h:208-213, gtsam/geometry/Cal3Bundler.h:145-152)
 template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_CAM_BUNDLER, WITH_J> {
-  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, double* M) {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, const double*, double* M) {
     enum { NC = 10 };
     const double* xv = c.values + c.val_off[k0];
     const Pose x = load_pose(xv);
@@ -128,9 +128,14 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_CAM_BUNDLER, WITH_J> {
 // (gtsam/geometry/Cal3_S2.cpp:44-51).  Cheirality: H = 0, r = (2fx, 2fx).
 template <bool WITH_J> struct Eval<B200_FACTOR_PROJECTION_CAL3S2, WITH_J> {
   static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int k1, const double* __restrict__ z, int cal,
-                                             double* M) {
+                                             const double* __restrict__ body, double* M) {
     enum { NC = 10 };
-    const Pose T = load_pose(c.values + c.val_off[k0]);
+    Pose T = load_pose(c.values + c.val_off[k0]);
+    Pose S;
+    if (body) {   // camera = pose.compose(body_P_sensor, H0): gtsam/slam/ProjectionFactor.h:141-151
+      S = load_pose(body);
+      T = compose(T, S);
+    }
     const double* pp = c.values + c.val_off[k1];
     const double p[3] = {pp[0], pp[1], pp[2]};
     const double* K = c.cal + 5 * cal;
@@ -151,6 +156,22 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PROJECTION_CAL3S2, WITH_J> {
           M[6 + j] = fx * Dq[j] + s * Dq[3 + j];
           M[NC + 6 + j] = 0.0 * Dq[j] + fy * Dq[3 + j];
         }
+        if (body) {   // H1 <- H1 * H0 with H0 = Ad(body_P_sensor^-1) = [R 0; [t]x R, R] (gtsam/base/Lie.h compose)
+          const Pose Si = inverse(S);
+          const Mat3 A = mul(hat(Si.t[0], Si.t[1], Si.t[2]), Si.R);
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            double h[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) h[j] = M[r * NC + j];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              M[r * NC + j] = h[0] * Si.R.m[j] + h[1] * Si.R.m[3 + j] + h[2] * Si.R.m[6 + j] +
+                              h[3] * A.m[j] + h[4] * A.m[3 + j] + h[5] * A.m[6 + j];
+              M[r * NC + 3 + j] = h[3] * Si.R.m[j] + h[4] * Si.R.m[3 + j] + h[5] * Si.R.m[6 + j];
+            }
+          }
+        }
       }
     } else {
       M[9] = -2.0 * fx;
@@ -168,7 +189,7 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PROJECTION_CAL3S2, WITH_J> {
 // (gtsam/geometry/PinholeCamera.h:230-247); Cal3Bundler::uncalibrate
 // (gtsam/geometry/Cal3Bundler.cpp:66-92).  Cheirality: H = 0, b = 0.
 template <bool WITH_J> struct Eval<B200_FACTOR_SFM_BUNDLER, WITH_J> {
-  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int k1, const double* __restrict__ z, int, double* M) {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int k1, const double* __restrict__ z, int, const double*, double* M) {
     enum { NC = 13 };
     const double* cv = c.values + c.val_off[k0];
     const Pose T = load_pose(cv);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linea
   if (f >= g.count) return;
   const int2 k = g.keys[f];
   double M[D * NC];
-  Eval<TYPE, true>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, M);
+  Eval<TYPE, true>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, g.body, M);
   whiten<D, NC, 0>(M, g.noise_kind, g.noise + (g.per_factor ? (size_t)f * g.noise_size : 0));
   double* J = g.J + f;
 #pragma unroll
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
     const int2 k = g.keys[f];
     double M[D * NC];
-    Eval<TYPE, false>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, M);
+    Eval<TYPE, false>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, g.body, M);
     whiten<D, NC, NC - 1>(M, g.noise_kind, g.noise + (g.per_factor ? (size_t)f * g.noise_size : 0));
     double s = 0;
 #pragma unroll

@@ -151,7 +151,7 @@ def lookat_pose(eye, target, up):
 
 
 def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibility: str = "scattered",
-        camera_model: str = "cal3_s2", seed: int = 42, pixel_sigma: float = 1.0) -> P.Problem:
+        camera_model: str = "cal3_s2", seed: int = 42, pixel_sigma: float = 1.0, body_sensor: bool = False) -> P.Problem:
     rng = np.random.default_rng(seed)
     th = 2 * np.pi * np.arange(ncams) / ncams
     eye = np.stack([20 * np.cos(th), 20 * np.sin(th), 2 * np.sin(3 * th)], -1)
@@ -181,10 +181,21 @@ def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibili
     if camera_model == "cal3_s2":
         K = np.array([[500.0, 500.0, 0.0, 320.0, 240.0]])
         z = np.stack([K[0, 0] * pn[:, 0] + K[0, 2] * pn[:, 1] + K[0, 3], K[0, 1] * pn[:, 1] + K[0, 4]], -1) + noise
+        body = None
+        Rpri, tpri = Rc[:2], tc[:2]
+        if body_sensor:
+            # the variables are BODY poses; the camera sits at body * body_P_sensor
+            # (GenericProjectionFactor's optional argument, gtsam/slam/ProjectionFactor.h:141-151)
+            Rs, ts = se3_exp(np.array([0.05, -0.1, 0.2, 0.3, -0.2, 0.1]))
+            Rsi, tsi = Rs.T, -Rs.T @ ts
+            R0, t0 = pose_compose(R0, t0, Rsi, tsi)
+            Rpri, tpri = pose_compose(Rpri, tpri, Rsi, tsi)
+            body = pack_pose(Rs, ts)
         cams = pack_pose(R0, t0)
         var_type = np.concatenate([np.full(ncams, P.VAR_POSE3), np.full(npoints, P.VAR_POINT3)])
-        proj = P.FactorGroup(P.FACTOR_PROJECTION_CAL3S2, keys, z, P.NOISE_ISOTROPIC, np.array([pixel_sigma]))
-        prior = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0], [1]]), pack_pose(Rc[:2], tc[:2]),
+        proj = P.FactorGroup(P.FACTOR_PROJECTION_CAL3S2, keys, z, P.NOISE_ISOTROPIC, np.array([pixel_sigma]),
+                             body_P_sensor=body)
+        prior = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0], [1]]), pack_pose(Rpri, tpri),
                               P.NOISE_ISOTROPIC, np.array([0.1]))
         groups, cal = [proj, prior], K
     elif camera_model == "bundler":

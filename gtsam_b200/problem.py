@@ -49,7 +49,8 @@ class CFactorGroup(C.Structure):
     _fields_ = [("type", C.c_int32), ("noise_kind", C.c_int32), ("noise_per_factor", C.c_int32),
                 ("reserved", C.c_int32), ("count", C.c_int64), ("graph_index0", C.c_int64),
                 ("keys", C.POINTER(C.c_int64)), ("meas", C.POINTER(C.c_double)),
-                ("noise", C.POINTER(C.c_double)), ("cal_index", C.POINTER(C.c_int32))]
+                ("noise", C.POINTER(C.c_double)), ("cal_index", C.POINTER(C.c_int32)),
+                ("body_P_sensor", C.POINTER(C.c_double))]
 
 
 class CProblemDesc(C.Structure):
@@ -97,6 +98,7 @@ class FactorGroup:
     noise: Optional[np.ndarray] = None  # shared (payload,) or per-factor (count, payload)
     cal_index: Optional[np.ndarray] = None
     graph_index0: int = -1
+    body_P_sensor: Optional[np.ndarray] = None   # (12,) Pose3 shared by the group (projection factors)
 
     def __post_init__(self):
         ar, ms = FACTOR_ARITY[self.type], FACTOR_MEAS[self.type]
@@ -111,6 +113,8 @@ class FactorGroup:
             assert self.noise.size in (pay, pay * self.count), "noise payload size"
         if self.cal_index is not None:
             self.cal_index = np.ascontiguousarray(self.cal_index, dtype=np.int32)
+        if self.body_P_sensor is not None:
+            self.body_P_sensor = np.ascontiguousarray(self.body_P_sensor, dtype=np.float64).reshape(12)
 
     @property
     def count(self) -> int:
@@ -187,6 +191,7 @@ class Problem:
             garr[i].meas = _ptr(g.meas, C.c_double)
             garr[i].noise = _ptr(g.noise, C.c_double)
             garr[i].cal_index = _ptr(g.cal_index, C.c_int32)
+            garr[i].body_P_sensor = _ptr(g.body_P_sensor, C.c_double)
         d = CProblemDesc()
         d.nvars = self.nvars
         d.var_type = _ptr(self.var_type, C.c_int32)
@@ -214,13 +219,16 @@ class Problem:
             f.write(struct.pack("<q", len(self.groups)))
             for g in self.groups:
                 f.write(struct.pack("<iiiiqq", g.type, g.noise_kind, g.noise_per_factor,
-                                    int(g.cal_index is not None), g.count, g.graph_index0))
+                                    int(g.cal_index is not None) | (2 if g.body_P_sensor is not None else 0),
+                                    g.count, g.graph_index0))
                 f.write(g.keys.tobytes())
                 f.write(g.meas.tobytes())
                 f.write(struct.pack("<q", g.noise.size))
                 f.write(g.noise.tobytes())
                 if g.cal_index is not None:
                     f.write(g.cal_index.tobytes())
+                if g.body_P_sensor is not None:
+                    f.write(g.body_P_sensor.tobytes())
 
     @classmethod
     def load(cls, path: str) -> "Problem":
@@ -256,6 +264,7 @@ class Problem:
             meas = arr(np.float64, cnt * FACTOR_MEAS[t])
             (nn,) = rd("<q")
             noise = arr(np.float64, nn)
-            ci = arr(np.int32, cnt) if hc else None
-            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0))
+            ci = arr(np.int32, cnt) if hc & 1 else None
+            body = arr(np.float64, 12) if hc & 2 else None
+            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0, body))
         return cls(vt, vals, order, groups, cal)

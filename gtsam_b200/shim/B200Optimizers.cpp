@@ -57,6 +57,7 @@ struct GroupBuf {
   std::vector<int64_t> keys;
   std::vector<double> meas, noise;
   std::vector<int32_t> cal;
+  std::vector<double> body;   // body_P_sensor shared by the group (empty: none)
   int64_t count = 0, gi0 = 0;
 };
 
@@ -147,6 +148,7 @@ struct DeviceState {
       std::vector<int64_t> keys;
       std::vector<double> meas;
       int32_t cal_id = 0;
+      std::vector<double> body;
       SharedNoiseModel nm;
       auto id = [&](Key k) {
         auto it = key2id.find(k);
@@ -163,7 +165,7 @@ struct DeviceState {
       } else if (auto pc = dynamic_cast<const PriorFactor<BCam>*>(f.get())) {
         type = B200_FACTOR_PRIOR_CAM_BUNDLER; keys = {id(pc->key())}; putCam(pc->prior(), meas); nm = pc->noiseModel();
       } else if (auto pj = dynamic_cast<const ProjFactor*>(f.get())) {
-        if (pj->body_P_sensor()) throw std::invalid_argument("gtsam_b200: body_P_sensor is a 'next' row");
+        if (pj->body_P_sensor()) putPose(*pj->body_P_sensor(), body);
         type = B200_FACTOR_PROJECTION_CAL3S2; keys = {id(pj->key1()), id(pj->key2())};
         meas = {pj->measured().x(), pj->measured().y()}; nm = pj->noiseModel();
         const Cal3_S2* K = pj->calibration().get();
@@ -183,8 +185,8 @@ struct DeviceState {
       }
       d = b200_factor_dim(type);
       const int kind = noiseOf(nm, d, pay);
-      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind) {
-        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos;
+      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind || groups.back().body != body) {
+        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos; g.body = body;
         groups.push_back(g);
       }
       GroupBuf& g = groups.back();
@@ -210,6 +212,7 @@ struct DeviceState {
       cg[i].reserved = 0; cg[i].count = groups[i].count; cg[i].graph_index0 = groups[i].gi0;
       cg[i].keys = groups[i].keys.data(); cg[i].meas = groups[i].meas.data(); cg[i].noise = groups[i].noise.data();
       cg[i].cal_index = groups[i].type == B200_FACTOR_PROJECTION_CAL3S2 ? groups[i].cal.data() : nullptr;
+      cg[i].body_P_sensor = groups[i].body.empty() ? nullptr : groups[i].body.data();
     }
     const std::vector<double> packed = packValues(values);
     b200_problem_desc desc;

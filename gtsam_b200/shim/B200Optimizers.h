@@ -19,7 +19,7 @@
  *
  * Supported factors (anything else => std::invalid_argument, there is no CPU fallback):
  * BetweenFactor<Pose3>, PriorFactor<Pose3|Point3|PinholeCamera<Cal3Bundler>>,
- * GenericProjectionFactor<Pose3,Point3,Cal3_S2> (no body_P_sensor),
+ * GenericProjectionFactor<Pose3,Point3,Cal3_S2> (with or without body_P_sensor),
  * GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>; noise models Unit,
  * Isotropic, Diagonal, Gaussian (Constrained / Robust => std::invalid_argument).
  */

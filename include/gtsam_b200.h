@@ -63,7 +63,7 @@ enum {
   /* PriorFactor<Point3>. key; meas 3; dim 3 */
   B200_FACTOR_PRIOR_POINT3 = 2,
   /* GenericProjectionFactor<Pose3,Point3,Cal3_S2>, gtsam/slam/ProjectionFactor.h:138-166
-     (no body_P_sensor, throwCheirality=false). keys (pose,point); meas z (2);
+     (optional group-wide body_P_sensor, throwCheirality=false). keys (pose,point); meas z (2);
      dim 2; per-factor calibration index into desc.cal (5 doubles fx fy s u0 v0) */
   B200_FACTOR_PROJECTION_CAL3S2 = 3,
   /* GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>, gtsam/slam/GeneralSFMFactor.h:127-177.
@@ -98,6 +98,9 @@ typedef struct b200_factor_group {
   const double* meas;       /* count*meas_size                                  */
   const double* noise;      /* payload: shared or count*payload_size            */
   const int32_t* cal_index; /* PROJECTION_CAL3S2 only; NULL => calibration 0    */
+  const double* body_P_sensor; /* PROJECTION_CAL3S2 only: one Pose3 (12 doubles) shared by
+                               the group = GenericProjectionFactor's body_P_sensor
+                               (gtsam/slam/ProjectionFactor.h:141-151), or NULL       */
 } b200_factor_group;
 
 typedef struct b200_problem_desc {

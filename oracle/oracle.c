@@ -383,6 +383,8 @@ typedef struct {
   double* noise;
   int noise_size;
   int32_t* cal_index;
+  int has_body;
+  double body[12]; /* body_P_sensor of the group (projection factors) */
   int d, ncols; /* rows, n1+n2+1 */
   double* J;    /* count * d * ncols, factor-major col-major [A1 A2 b] */
 } ogroup;
@@ -655,6 +657,7 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
     if (s->type == B200_FACTOR_PROJECTION_CAL3S2) {
       o->cal_index = (int32_t*)calloc((size_t)s->count + 1, sizeof(int32_t));
       if (s->cal_index) memcpy(o->cal_index, s->cal_index, (size_t)s->count * sizeof(int32_t));
+      if (s->body_P_sensor) { o->has_body = 1; memcpy(o->body, s->body_P_sensor, sizeof o->body); }
     }
     o->J = (double*)calloc((size_t)(s->count * d * o->ncols + 1), sizeof(double));
     for (int64_t i = 0; i < s->count; i++) {
@@ -753,10 +756,27 @@ static void eval_factor(const orc_problem* p, const ogroup* g, int64_t i, const 
     case B200_FACTOR_PROJECTION_CAL3S2: {
       /* gtsam/slam/ProjectionFactor.h:138-166 */
       const double* K = p->cal + 5 * (g->cal_index ? g->cal_index[i] : 0);
-      double pi[2];
-      if (project_cal3s2(x1, K, x2, pi, H1, H2)) {
+      double pi[2], cam[12];
+      const double* cpose = x1;
+      if (g->has_body) { /* camera = pose.compose(body_P_sensor, H0), ProjectionFactor.h:141-151 */
+        orc_pose3_compose(x1, g->body, cam);
+        cpose = cam;
+      }
+      if (project_cal3s2(cpose, K, x2, pi, H1, H2)) {
         r[0] = pi[0] - z[0];
         r[1] = pi[1] - z[1];
+        if (g->has_body && H1) { /* H1 = H1 * H0, H0 = body_P_sensor.inverse().AdjointMap() (Lie.h compose) */
+          double Si[12], Ad[36], T[12];
+          orc_pose3_inverse(g->body, Si);
+          orc_pose3_adjoint_map(Si, Ad);
+          for (int rr = 0; rr < 2; rr++)
+            for (int cc = 0; cc < 6; cc++) {
+              double sacc = 0;
+              for (int k = 0; k < 6; k++) sacc += H1[rr * 6 + k] * Ad[k * 6 + cc];
+              T[rr * 6 + cc] = sacc;
+            }
+          memcpy(H1, T, sizeof T);
+        }
       } else { /* cheirality: zero Jacobians, constant residual 2*fx */
         if (H1) { memset(H1, 0, 12 * sizeof(double)); memset(H2, 0, 6 * sizeof(double)); }
         r[0] = r[1] = 2.0 * K[0];

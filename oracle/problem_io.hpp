@@ -50,6 +50,7 @@ struct Group {
   std::vector<int64_t> keys;
   std::vector<double> meas, noise;
   std::vector<int32_t> cal_index;
+  std::vector<double> body;  // body_P_sensor (12) when has_cal & 2
 };
 struct Prob {
   int64_t nvars;
@@ -97,7 +98,8 @@ static Prob load(const std::string& path) {
     rd(f, &nn, 1);
     g.noise.resize(nn);
     rd(f, g.noise.data(), nn);
-    if (g.has_cal) { g.cal_index.resize(g.count); rd(f, g.cal_index.data(), g.count); }
+    if (g.has_cal & 1) { g.cal_index.resize(g.count); rd(f, g.cal_index.data(), g.count); }
+    if (g.has_cal & 2) { g.body.resize(12); rd(f, g.body.data(), 12); }
   }
   return p;
 }
@@ -170,8 +172,12 @@ static Built build(const Prob& p) {
         case 1: f = std::make_shared<PriorFactor<Pose3>>(k[0], mkpose(z), nm); break;
         case 2: f = std::make_shared<PriorFactor<Point3>>(k[0], Point3(z[0], z[1], z[2]), nm); break;
         case 3:
-          f = std::make_shared<GenericProjectionFactor<Pose3, Point3, Cal3_S2>>(
-              Point2(z[0], z[1]), nm, k[0], k[1], Ks[g.has_cal ? g.cal_index[i] : 0]);
+          if (g.has_cal & 2)
+            f = std::make_shared<GenericProjectionFactor<Pose3, Point3, Cal3_S2>>(
+                Point2(z[0], z[1]), nm, k[0], k[1], Ks[(g.has_cal & 1) ? g.cal_index[i] : 0], mkpose(g.body.data()));
+          else
+            f = std::make_shared<GenericProjectionFactor<Pose3, Point3, Cal3_S2>>(
+                Point2(z[0], z[1]), nm, k[0], k[1], Ks[(g.has_cal & 1) ? g.cal_index[i] : 0]);
           break;
         case 4: f = std::make_shared<GeneralSFMFactor<BCam, Point3>>(Point2(z[0], z[1]), nm, k[0], k[1]); break;
         case 5: f = std::make_shared<PriorFactor<BCam>>(k[0], mkcam(z), nm); break;

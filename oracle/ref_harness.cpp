@@ -281,7 +281,8 @@ static void save(const Prob& p, const std::string& path) {
     int64_t nn = (int64_t)g.noise.size();
     wr(f, &nn, 1);
     wr(f, g.noise.data(), g.noise.size());
-    if (g.has_cal) wr(f, g.cal_index.data(), g.cal_index.size());
+    if (g.has_cal & 1) wr(f, g.cal_index.data(), g.cal_index.size());
+    if (g.has_cal & 2) wr(f, g.body.data(), g.body.size());
   }
 }
 

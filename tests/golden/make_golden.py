@@ -46,6 +46,7 @@ def main():
     assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
     subprocess.check_call([H, "kat", os.path.join(HERE, "geometry_kat.bin")])
     emit("bal_tiny_s2", datasets.make("bal_tiny"))
+    emit("bal_tiny_body_sensor", datasets.make("bal_tiny", seed=13, body_sensor=True))
     emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True)
     emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"))
     emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3)
