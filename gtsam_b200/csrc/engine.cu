@@ -45,7 +45,7 @@ static int upload(T** dst, const std::vector<T>& v, cudaStream_t st) { return up
 static GroupView view(const b200_problem::Group& g) {
   GroupView v;
   v.type = g.type; v.noise_kind = g.noise_kind; v.per_factor = g.per_factor; v.noise_size = g.noise_size;
-  v.count = (int)g.count; v.keys = g.d_keys; v.meas = g.d_meas; v.noise = g.d_noise; v.cal_index = g.d_cal; v.body = g.d_body;
+  v.count = (int)g.count; v.robust_kind = g.robust_kind; v.robust_param = g.robust_param; v.keys = g.d_keys; v.meas = g.d_meas; v.noise = g.d_noise; v.cal_index = g.d_cal; v.body = g.d_body;
   v.J = g.d_J; v.scat = g.d_scat;
   return v;
 }
@@ -363,7 +363,7 @@ static int solve_status(const b200_problem* p, int64_t* fail_var) {
 
 // Validation of a problem description + the symbolic phase.  Host only: needs
 // no GPU, so it is also exposed through b200_symbolic_create for CPU tests.
-struct PackedGroup { int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas; int64_t count, gi0; };
+struct PackedGroup { int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas, robust_kind; double robust_param; int64_t count, gi0; };
 struct Packed {
   std::vector<int> val_off, var_dof, var_dim;
   std::vector<int64_t> fkey0, fkey1;
@@ -397,7 +397,12 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
     g.d = F_DIM[s.type]; g.arity = F_ARITY[s.type]; g.meas = F_MEAS[s.type];
     g.ncols = VAR_DIM[F_VT[s.type][0]] + (g.arity == 2 ? VAR_DIM[F_VT[s.type][1]] : 0) + 1;
     g.noise_size = noise_payload(s.noise_kind, g.d);
-    if (g.noise_size < 0) FAIL(B200_UNSUPPORTED_NOISE, "unsupported noise model (Constrained/Robust are out of scope)");
+    if (g.noise_size < 0) FAIL(B200_UNSUPPORTED_NOISE, "unsupported noise model (Constrained models need QR: out of scope)");
+    g.robust_kind = s.robust_kind; g.robust_param = s.robust_param;
+    if (s.robust_kind < 0 || s.robust_kind > B200_ROBUST_FAIR || (s.robust_kind && !(s.robust_param > 0)))
+      FAIL(B200_UNSUPPORTED_NOISE, "unknown robust loss or non-positive parameter");
+    if (s.robust_kind && s.type == B200_FACTOR_SFM_BUNDLER)
+      FAIL(B200_UNSUPPORTED_NOISE, "GeneralSFMFactor::linearize whitens without reweighting: Robust models are not supported on it");
     g.gi0 = s.graph_index0 < 0 ? next : s.graph_index0;
     next = g.gi0 + s.count;
     if (s.count < 0 || g.gi0 + s.count > total) FAIL(B200_INVALID_ARGUMENT, "graph_index0 out of range");
@@ -669,6 +674,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     const PackedGroup& q = pk.groups[gi];
     g.type = q.type; g.noise_kind = q.noise_kind; g.per_factor = q.per_factor; g.noise_size = q.noise_size;
     g.d = q.d; g.ncols = q.ncols; g.arity = q.arity; g.meas = q.meas; g.count = q.count; g.gi0 = q.gi0;
+    g.robust_kind = q.robust_kind; g.robust_param = q.robust_param;
   }
   p->sym = std::move(pk.sym);
   const Symbolic& S = p->sym;

@@ -27,6 +27,8 @@ void set_error(const std::string& s);
 struct GroupView {
   int type, noise_kind, per_factor, noise_size;
   int count;
+  int robust_kind;         // B200_ROBUST_*
+  double robust_param;
   const int2* keys;        // (key0, key1 or -1)
   const double* meas;      // AoS, MEAS doubles per factor
   const double* noise;     // shared payload or per-factor AoS
@@ -89,6 +91,8 @@ struct b200_problem {
   // host copies of group metadata
   struct Group {
     int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas;
+    int robust_kind = 0;
+    double robust_param = 0;
     int64_t count, gi0;
     int2* d_keys = nullptr;
     double* d_meas = nullptr;

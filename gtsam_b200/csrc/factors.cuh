@@ -268,4 +268,32 @@ __device__ __forceinline__ void whiten(double* M, int kind, const double* __rest
   }
 }
 
+// m-estimators of noiseModel::Robust (gtsam/linear/LossFunctions.cpp:146-267)
+__device__ __forceinline__ double robust_weight(int kind, double k, double distance) {
+  const double a = fabs(distance);
+  switch (kind) {
+    case B200_ROBUST_HUBER: return (a <= k) ? 1.0 : (k / a);
+    case B200_ROBUST_CAUCHY: return (k * k) / (k * k + distance * distance);
+    case B200_ROBUST_TUKEY: {
+      if (a <= k) { const double t = 1.0 - distance * distance / (k * k); return t * t; }
+      return 0.0;
+    }
+    case B200_ROBUST_FAIR: return 1.0 / (1.0 + a / k);
+  }
+  return 1.0;
+}
+__device__ __forceinline__ double robust_loss(int kind, double k, double distance) {
+  const double a = fabs(distance);
+  switch (kind) {
+    case B200_ROBUST_HUBER: return (a <= k) ? distance * distance / 2 : k * (a - (k / 2));
+    case B200_ROBUST_CAUCHY: return k * k * log1p(distance * distance / (k * k)) * 0.5;
+    case B200_ROBUST_TUKEY: {
+      if (a <= k) { const double u = 1.0 - distance * distance / (k * k); return k * k * (1 - u * u * u) / 6.0; }
+      return k * k / 6.0;
+    }
+    case B200_ROBUST_FAIR: { const double ne = a / k; return k * k * (ne - log1p(ne)); }
+  }
+  return 0.5 * distance * distance;
+}
+
 }  // namespace b200

@@ -121,6 +121,14 @@ __global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linea
   double M[D * NC];
   Eval<TYPE, true>::run(c, k.x, k.y, g.meas + (size_t)f * FT::MEAS, g.cal_index ? g.cal_index[f] : 0, g.body, M);
   whiten<D, NC, 0>(M, g.noise_kind, g.noise + (g.per_factor ? (size_t)f * g.noise_size : 0));
+  if (g.robust_kind) {   // Robust::WhitenSystem: scale A and b by sqrt(w(|b|)) (Block reweighting)
+    double nrm = 0;
+#pragma unroll
+    for (int r = 0; r < D; r++) nrm += M[r * NC + NC - 1] * M[r * NC + NC - 1];
+    const double w = sqrt(robust_weight(g.robust_kind, g.robust_param, sqrt(nrm)));
+#pragma unroll
+    for (int e = 0; e < D * NC; e++) M[e] *= w;
+  }
   double* J = g.J + f;
 #pragma unroll
   for (int cc = 0; cc < NC; cc++)
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
     double s = 0;
 #pragma unroll
     for (int r = 0; r < D; r++) s += M[r * NC + NC - 1] * M[r * NC + NC - 1];
-    acc += 0.5 * s;
+    acc += g.robust_kind ? robust_loss(g.robust_kind, g.robust_param, sqrt(s)) : 0.5 * s;
   }
   acc = block_sum<256>(acc, sh);
   finish_sum(acc, partials, counter, out, accumulate, sh);

@@ -76,7 +76,7 @@ def rot_ypr(y, p, r):
 
 # ---- config 2: sphere ------------------------------------------------------------
 def sphere(layers: int = 50, per_ring: int = 50, radius: float = 50.0, seed: int = 7,
-           ordering: str = "natural", noise: str = "diagonal") -> P.Problem:
+           ordering: str = "natural", noise: str = "diagonal", robust=None) -> P.Problem:
     rng = np.random.default_rng(seed)
     n = layers * per_ring
     idx = np.arange(n)
@@ -134,6 +134,15 @@ def sphere(layers: int = 50, per_ring: int = 50, radius: float = 50.0, seed: int
         order = np.load(path).astype(np.int64)
     else:
         raise ValueError(ordering)
+    if robust:
+        # a few gross outliers + a Huber/Cauchy/... kernel, as Pose2SLAMExample_g2o exposes for 2D
+        # (examples/Pose2SLAMExample_g2o.cpp:53-61)
+        bad = rng.choice(edges.shape[0], size=max(1, edges.shape[0] // 15), replace=False)
+        Rb, tb = se3_exp(rng.normal(size=(bad.size, 6)) * np.array([0.5] * 3 + [5.0] * 3))
+        zb = between.meas[bad]
+        Rzb, tzb = pose_compose(zb[:, :9].reshape(-1, 3, 3), zb[:, 9:], Rb, tb)
+        between.meas[bad] = pack_pose(Rzb, tzb)
+        between.robust_kind, between.robust_param = robust
     pr = P.Problem(np.full(n, P.VAR_POSE3), values, order, [between, prior], name=f"sphere{n}")
     pr.meta = dict(kind="sphere", layers=layers, per_ring=per_ring, seed=seed, gt=pack_pose(R, t), ordering=ordering)
     return pr

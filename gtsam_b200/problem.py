@@ -30,6 +30,7 @@ FACTOR_DIM = (6, 6, 3, 2, 2, 9)
 FACTOR_VAR_TYPES = ((0, 0), (0,), (1,), (0, 1), (2, 1), (2,))
 
 NOISE_UNIT, NOISE_ISOTROPIC, NOISE_DIAGONAL, NOISE_GAUSSIAN = range(4)
+ROBUST_NONE, ROBUST_HUBER, ROBUST_CAUCHY, ROBUST_TUKEY, ROBUST_FAIR = range(5)
 
 (OK, INDETERMINATE, UNSUPPORTED_FACTOR, UNSUPPORTED_NOISE, INVALID_ARGUMENT, CUDA_ERROR,
  NCCL_ERROR, NO_DEVICE) = range(8)
@@ -47,10 +48,10 @@ def factor_ncols(ftype: int) -> int:
 # ---- ctypes mirrors -----------------------------------------------------------
 class CFactorGroup(C.Structure):
     _fields_ = [("type", C.c_int32), ("noise_kind", C.c_int32), ("noise_per_factor", C.c_int32),
-                ("reserved", C.c_int32), ("count", C.c_int64), ("graph_index0", C.c_int64),
+                ("robust_kind", C.c_int32), ("count", C.c_int64), ("graph_index0", C.c_int64),
                 ("keys", C.POINTER(C.c_int64)), ("meas", C.POINTER(C.c_double)),
                 ("noise", C.POINTER(C.c_double)), ("cal_index", C.POINTER(C.c_int32)),
-                ("body_P_sensor", C.POINTER(C.c_double))]
+                ("body_P_sensor", C.POINTER(C.c_double)), ("robust_param", C.c_double)]
 
 
 class CProblemDesc(C.Structure):
@@ -99,6 +100,8 @@ class FactorGroup:
     cal_index: Optional[np.ndarray] = None
     graph_index0: int = -1
     body_P_sensor: Optional[np.ndarray] = None   # (12,) Pose3 shared by the group (projection factors)
+    robust_kind: int = 0                          # ROBUST_*: noiseModel::Robust around the noise model
+    robust_param: float = 0.0
 
     def __post_init__(self):
         ar, ms = FACTOR_ARITY[self.type], FACTOR_MEAS[self.type]
@@ -192,6 +195,8 @@ class Problem:
             garr[i].noise = _ptr(g.noise, C.c_double)
             garr[i].cal_index = _ptr(g.cal_index, C.c_int32)
             garr[i].body_P_sensor = _ptr(g.body_P_sensor, C.c_double)
+            garr[i].robust_kind = g.robust_kind
+            garr[i].robust_param = g.robust_param
         d = CProblemDesc()
         d.nvars = self.nvars
         d.var_type = _ptr(self.var_type, C.c_int32)
@@ -219,7 +224,7 @@ class Problem:
             f.write(struct.pack("<q", len(self.groups)))
             for g in self.groups:
                 f.write(struct.pack("<iiiiqq", g.type, g.noise_kind, g.noise_per_factor,
-                                    int(g.cal_index is not None) | (2 if g.body_P_sensor is not None else 0),
+                                    int(g.cal_index is not None) | (2 if g.body_P_sensor is not None else 0) | (g.robust_kind << 8),
                                     g.count, g.graph_index0))
                 f.write(g.keys.tobytes())
                 f.write(g.meas.tobytes())
@@ -229,6 +234,8 @@ class Problem:
                     f.write(g.cal_index.tobytes())
                 if g.body_P_sensor is not None:
                     f.write(g.body_P_sensor.tobytes())
+                if g.robust_kind:
+                    f.write(struct.pack("<d", g.robust_param))
 
     @classmethod
     def load(cls, path: str) -> "Problem":
@@ -266,5 +273,7 @@ class Problem:
             noise = arr(np.float64, nn)
             ci = arr(np.int32, cnt) if hc & 1 else None
             body = arr(np.float64, 12) if hc & 2 else None
-            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0, body))
+            rk = (hc >> 8) & 0xff
+            (rp,) = rd("<d") if rk else (0.0,)
+            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0, body, rk, rp))
         return cls(vt, vals, order, groups, cal)

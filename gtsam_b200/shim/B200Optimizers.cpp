@@ -54,6 +54,8 @@ static Pose3 getPose(const double* x) {
 
 struct GroupBuf {
   int type, noise_kind;
+  int robust_kind = 0;
+  double robust_param = 0;
   std::vector<int64_t> keys;
   std::vector<double> meas, noise;
   std::vector<int32_t> cal;
@@ -104,6 +106,20 @@ struct DeviceState {
   }
 
   // noise model -> (kind, payload); Constrained / Robust are rejected like an unsupported factor
+  // noiseModel::Robust = m-estimator around a base model (gtsam/linear/NoiseModel.h: Robust)
+  static SharedNoiseModel unwrapRobust(const SharedNoiseModel& nm, int* kind, double* param) {
+    *kind = B200_ROBUST_NONE; *param = 0;
+    auto rb = std::dynamic_pointer_cast<noiseModel::Robust>(nm);
+    if (!rb) return nm;
+    auto m = rb->robust();
+    if (auto h = std::dynamic_pointer_cast<noiseModel::mEstimator::Huber>(m)) { *kind = B200_ROBUST_HUBER; *param = h->modelParameter(); }
+    else if (auto c = std::dynamic_pointer_cast<noiseModel::mEstimator::Cauchy>(m)) { *kind = B200_ROBUST_CAUCHY; *param = c->modelParameter(); }
+    else if (auto t = std::dynamic_pointer_cast<noiseModel::mEstimator::Tukey>(m)) { *kind = B200_ROBUST_TUKEY; *param = t->modelParameter(); }
+    else if (auto f = std::dynamic_pointer_cast<noiseModel::mEstimator::Fair>(m)) { *kind = B200_ROBUST_FAIR; *param = f->modelParameter(); }
+    else throw std::invalid_argument("gtsam_b200: unsupported m-estimator (supported: Huber, Cauchy, Tukey, Fair)");
+    return rb->noise();
+  }
+
   static int noiseOf(const SharedNoiseModel& nm, int d, std::vector<double>& payload) {
     payload.clear();
     if (!nm || nm->isUnit()) return B200_NOISE_UNIT;
@@ -118,7 +134,7 @@ struct DeviceState {
       for (int r = 0; r < d; r++) for (int c = 0; c < d; c++) payload.push_back(R(r, c));
       return B200_NOISE_GAUSSIAN;
     }
-    throw std::invalid_argument("gtsam_b200: unsupported noise model (Robust models are a 'next' row)");
+    throw std::invalid_argument("gtsam_b200: unsupported noise model");
   }
 
   void pack(const NonlinearFactorGraph& graph, const Values& values, const Ordering& ordering) {
@@ -184,9 +200,12 @@ struct DeviceState {
                                     "GenericProjectionFactor<Pose3,Point3,Cal3_S2>, GeneralSFMFactor<SfmCamera,Point3>)");
       }
       d = b200_factor_dim(type);
-      const int kind = noiseOf(nm, d, pay);
-      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind || groups.back().body != body) {
-        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos; g.body = body;
+      int rkind; double rparam;
+      const SharedNoiseModel base = unwrapRobust(nm, &rkind, &rparam);
+      const int kind = noiseOf(base, d, pay);
+      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind || groups.back().body != body ||
+          groups.back().robust_kind != rkind || groups.back().robust_param != rparam) {
+        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos; g.body = body; g.robust_kind = rkind; g.robust_param = rparam;
         groups.push_back(g);
       }
       GroupBuf& g = groups.back();
@@ -209,7 +228,7 @@ struct DeviceState {
     for (size_t i = 0; i < groups.size(); i++) {
       cg[i].type = groups[i].type; cg[i].noise_kind = groups[i].noise_kind;
       cg[i].noise_per_factor = groups[i].noise_kind != B200_NOISE_UNIT && groups[i].count > 1;
-      cg[i].reserved = 0; cg[i].count = groups[i].count; cg[i].graph_index0 = groups[i].gi0;
+      cg[i].robust_kind = groups[i].robust_kind; cg[i].robust_param = groups[i].robust_param; cg[i].count = groups[i].count; cg[i].graph_index0 = groups[i].gi0;
       cg[i].keys = groups[i].keys.data(); cg[i].meas = groups[i].meas.data(); cg[i].noise = groups[i].noise.data();
       cg[i].cal_index = groups[i].type == B200_FACTOR_PROJECTION_CAL3S2 ? groups[i].cal.data() : nullptr;
       cg[i].body_P_sensor = groups[i].body.empty() ? nullptr : groups[i].body.data();

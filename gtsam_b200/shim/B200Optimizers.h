@@ -21,7 +21,8 @@
  * BetweenFactor<Pose3>, PriorFactor<Pose3|Point3|PinholeCamera<Cal3Bundler>>,
  * GenericProjectionFactor<Pose3,Point3,Cal3_S2> (with or without body_P_sensor),
  * GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>; noise models Unit,
- * Isotropic, Diagonal, Gaussian (Constrained / Robust => std::invalid_argument).
+ * Isotropic, Diagonal, Gaussian, and noiseModel::Robust (Huber / Cauchy / Tukey / Fair) around any
+ * of them (Constrained => std::invalid_argument).
  */
 #pragma once
 #include <gtsam/nonlinear/GaussNewtonOptimizer.h>

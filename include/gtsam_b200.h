@@ -37,7 +37,7 @@ enum {
                                   gtsam/linear/HessianFactor.cpp:476-483,
                                   gtsam/linear/linearAlgorithms-inst.h:99 */
   B200_UNSUPPORTED_FACTOR = 2, /* factor type outside the hot path          */
-  B200_UNSUPPORTED_NOISE = 3,  /* Constrained / Robust noise models          */
+  B200_UNSUPPORTED_NOISE = 3,  /* Constrained noise models (need QR)         */
   B200_INVALID_ARGUMENT = 4,   /* std::invalid_argument / ValuesKeyDoesNotExist */
   B200_CUDA_ERROR = 5,
   B200_NCCL_ERROR = 6,
@@ -83,6 +83,16 @@ enum {
                                triangular), row-major; whitened r = R r       */
 };
 
+/* m-estimators of noiseModel::Robust (gtsam/linear/LossFunctions.cpp), Block reweighting:
+ * after whitening, A and b are scaled by sqrt(w(|b|)) and the factor's error is rho(|r|). */
+enum {
+  B200_ROBUST_NONE = 0,
+  B200_ROBUST_HUBER = 1,   /* LossFunctions.cpp:179-191 */
+  B200_ROBUST_CAUCHY = 2,  /* :217-224 */
+  B200_ROBUST_TUKEY = 3,   /* :250-267 */
+  B200_ROBUST_FAIR = 4     /* :146-155 */
+};
+
 /* One homogeneous run of factors (same type, same noise kind).  Factors of a
  * group occupy consecutive positions graph_index0 .. graph_index0+count-1 of
  * the NonlinearFactorGraph (position matters for the symbolic structure:
@@ -91,7 +101,8 @@ typedef struct b200_factor_group {
   int32_t type;             /* B200_FACTOR_*                                    */
   int32_t noise_kind;       /* B200_NOISE_*                                     */
   int32_t noise_per_factor; /* 0: one shared model for the group, 1: per factor */
-  int32_t reserved;
+  int32_t robust_kind;      /* B200_ROBUST_*: noiseModel::Robust wrapped around the
+                               noise above (gtsam/linear/NoiseModel.cpp:708-733); 0 = none */
   int64_t count;
   int64_t graph_index0;     /* -1: append after the previous group              */
   const int64_t* keys;      /* count*arity variable ids                         */
@@ -101,6 +112,7 @@ typedef struct b200_factor_group {
   const double* body_P_sensor; /* PROJECTION_CAL3S2 only: one Pose3 (12 doubles) shared by
                                the group = GenericProjectionFactor's body_P_sensor
                                (gtsam/slam/ProjectionFactor.h:141-151), or NULL       */
+  double robust_param;      /* k (Huber, Cauchy) / c (Tukey, Fair)                     */
 } b200_factor_group;
 
 typedef struct b200_problem_desc {

@@ -384,6 +384,8 @@ typedef struct {
   int noise_size;
   int32_t* cal_index;
   int has_body;
+  int robust_kind;
+  double robust_param;
   double body[12]; /* body_P_sensor of the group (projection factors) */
   int d, ncols; /* rows, n1+n2+1 */
   double* J;    /* count * d * ncols, factor-major col-major [A1 A2 b] */
@@ -639,6 +641,8 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
     ogroup* o = &p->groups[g];
     if (s->type < 0 || s->type >= B200_NUM_FACTOR_TYPES) return B200_UNSUPPORTED_FACTOR;
     o->type = s->type; o->noise_kind = s->noise_kind; o->per_factor = s->noise_per_factor;
+    o->robust_kind = s->robust_kind; o->robust_param = s->robust_param;
+    if (s->robust_kind < 0 || s->robust_kind > B200_ROBUST_FAIR || (s->robust_kind && s->type == B200_FACTOR_SFM_BUNDLER)) return B200_UNSUPPORTED_NOISE;
     o->count = s->count;
     o->graph_index0 = s->graph_index0 < 0 ? next : s->graph_index0;
     next = o->graph_index0 + s->count;
@@ -830,6 +834,34 @@ static void whiten_rows(const ogroup* g, int64_t i, double* M, int ncols) {
   }
 }
 
+/* m-estimators, gtsam/linear/LossFunctions.cpp: weight(distance) and loss(distance) */
+static double robust_weight(int kind, double k, double distance) {
+  const double a = fabs(distance);
+  switch (kind) {
+    case B200_ROBUST_HUBER: return (a <= k) ? 1.0 : (k / a);
+    case B200_ROBUST_CAUCHY: return (k * k) / (k * k + distance * distance);
+    case B200_ROBUST_TUKEY: {
+      if (a <= k) { const double t = 1.0 - distance * distance / (k * k); return t * t; }
+      return 0.0;
+    }
+    case B200_ROBUST_FAIR: return 1.0 / (1.0 + a / k);
+  }
+  return 1.0;
+}
+static double robust_loss(int kind, double k, double distance) {
+  const double a = fabs(distance);
+  switch (kind) {
+    case B200_ROBUST_HUBER: return (a <= k) ? distance * distance / 2 : k * (a - (k / 2));
+    case B200_ROBUST_CAUCHY: return k * k * log1p(distance * distance / (k * k)) * 0.5;
+    case B200_ROBUST_TUKEY: {
+      if (a <= k) { const double u = 1.0 - distance * distance / (k * k); return k * k * (1 - u * u * u) / 6.0; }
+      return k * k / 6.0;
+    }
+    case B200_ROBUST_FAIR: { const double ne = a / k; return k * k * (ne - log1p(ne)); }
+  }
+  return 0.5 * distance * distance;
+}
+
 /* NonlinearFactorGraph::error, gtsam/nonlinear/NonlinearFactorGraph.cpp:170-179;
  * NoiseModelFactor::error, gtsam/nonlinear/NonlinearFactor.cpp:133-146 */
 static double graph_error(const orc_problem* p, const double* values) {
@@ -841,7 +873,8 @@ static double graph_error(const orc_problem* p, const double* values) {
     whiten_rows(g, p->fidx[gi], r, 1);
     double s = 0;
     for (int k = 0; k < g->d; k++) s += r[k] * r[k];
-    total += 0.5 * s;
+    /* Gaussian: 0.5 d^2; Robust::loss(d^2) = rho(sqrt(d^2)) (NoiseModel.h Robust::loss) */
+    total += g->robust_kind ? robust_loss(g->robust_kind, g->robust_param, sqrt(s)) : 0.5 * s;
   }
   return total;
 }
@@ -861,6 +894,14 @@ void orc_linearize(orc_problem* p) {
       whiten_rows(g, i, H1, n1);
       if (n2) whiten_rows(g, i, H2, n2);
       whiten_rows(g, i, r, 1);
+      if (g->robust_kind) { /* Robust::WhitenSystem: Base::reweight, Block mode (LossFunctions.cpp:79-106) */
+        double nrm = 0;
+        for (int k = 0; k < d; k++) nrm += r[k] * r[k];
+        const double w = sqrt(robust_weight(g->robust_kind, g->robust_param, sqrt(nrm)));
+        for (int k = 0; k < d * n1; k++) H1[k] *= w;
+        for (int k = 0; k < d * n2; k++) H2[k] *= w;
+        for (int k = 0; k < d; k++) r[k] *= w;
+      }
       double* J = g->J + i * d * g->ncols;
       for (int rr = 0; rr < d; rr++) {
         for (int c = 0; c < n1; c++) J[rr + c * d] = H1[rr * n1 + c];

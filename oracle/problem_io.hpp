@@ -51,6 +51,8 @@ struct Group {
   std::vector<double> meas, noise;
   std::vector<int32_t> cal_index;
   std::vector<double> body;  // body_P_sensor (12) when has_cal & 2
+  int robust_kind = 0;       // (has_cal >> 8) & 0xff
+  double robust_param = 0;
 };
 struct Prob {
   int64_t nvars;
@@ -100,6 +102,8 @@ static Prob load(const std::string& path) {
     rd(f, g.noise.data(), nn);
     if (g.has_cal & 1) { g.cal_index.resize(g.count); rd(f, g.cal_index.data(), g.count); }
     if (g.has_cal & 2) { g.body.resize(12); rd(f, g.body.data(), 12); }
+    g.robust_kind = (g.has_cal >> 8) & 0xff;
+    if (g.robust_kind) rd(f, &g.robust_param, 1);
   }
   return p;
 }
@@ -116,7 +120,18 @@ static void putpose(const Pose3& p, double* x) {
   x[9] = p.x(); x[10] = p.y(); x[11] = p.z();
 }
 
+static SharedNoiseModel mknoise_base(const Group& g, int64_t i);
 static SharedNoiseModel mknoise(const Group& g, int64_t i) {
+  SharedNoiseModel base = mknoise_base(g, i);
+  switch (g.robust_kind) {
+    case 1: return noiseModel::Robust::Create(noiseModel::mEstimator::Huber::Create(g.robust_param), base);
+    case 2: return noiseModel::Robust::Create(noiseModel::mEstimator::Cauchy::Create(g.robust_param), base);
+    case 3: return noiseModel::Robust::Create(noiseModel::mEstimator::Tukey::Create(g.robust_param), base);
+    case 4: return noiseModel::Robust::Create(noiseModel::mEstimator::Fair::Create(g.robust_param), base);
+    default: return base;
+  }
+}
+static SharedNoiseModel mknoise_base(const Group& g, int64_t i) {
   const int d = F_DIM[g.type];
   const int pay = g.noise_kind == 0 ? 0 : g.noise_kind == 1 ? 1 : g.noise_kind == 2 ? d : d * d;
   const double* nz = g.noise.data() + (g.per_factor ? i * pay : 0);

@@ -283,6 +283,7 @@ static void save(const Prob& p, const std::string& path) {
     wr(f, g.noise.data(), g.noise.size());
     if (g.has_cal & 1) wr(f, g.cal_index.data(), g.cal_index.size());
     if (g.has_cal & 2) wr(f, g.body.data(), g.body.size());
+    if ((g.has_cal >> 8) & 0xff) wr(f, &g.robust_param, 1);
   }
 }
 

@@ -52,6 +52,15 @@ def main():
     emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3)
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
     emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2)
+    from gtsam_b200 import problem as Pq
+    emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2)
+    emit("sphere_tiny_cauchy", datasets.sphere(layers=5, per_ring=8, seed=14, noise="gaussian", robust=(Pq.ROBUST_CAUCHY, 2.0)))
+    bt = datasets.make("bal_tiny", seed=15)
+    bt.groups[0].robust_kind, bt.groups[0].robust_param = Pq.ROBUST_TUKEY, 4.685
+    emit("bal_tiny_tukey", bt)
+    bf = datasets.make("bal_tiny", seed=16)
+    bf.groups[0].robust_kind, bf.groups[0].robust_param = Pq.ROBUST_FAIR, 1.3998
+    emit("bal_tiny_fair", bf)
     emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
     # ---- input formats: synthetic text files written by gtsam_b200.io, parsed by the
     # REFERENCE's loaders (readG2o / SfmData::FromBalFile) into *.prob.bin; tests compare our readers with them
