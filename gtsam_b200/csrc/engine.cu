@@ -363,7 +363,12 @@ static int solve_status(const b200_problem* p, int64_t* fail_var) {
 
 // Validation of a problem description + the symbolic phase.  Host only: needs
 // no GPU, so it is also exposed through b200_symbolic_create for CPU tests.
-struct PackedGroup { int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas, robust_kind; double robust_param; int64_t count, gi0; };
+struct PackedGroup {
+  int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas, robust_kind;
+  double robust_param;
+  int64_t count;
+  std::vector<int64_t> pos;   // graph position of every factor of the group
+};
 struct Packed {
   std::vector<int> val_off, var_dof, var_dim;
   std::vector<int64_t> fkey0, fkey1;
@@ -403,20 +408,27 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
       FAIL(B200_UNSUPPORTED_NOISE, "unknown robust loss or non-positive parameter");
     if (s.robust_kind && s.type == B200_FACTOR_SFM_BUNDLER)
       FAIL(B200_UNSUPPORTED_NOISE, "GeneralSFMFactor::linearize whitens without reweighting: Robust models are not supported on it");
-    g.gi0 = s.graph_index0 < 0 ? next : s.graph_index0;
-    next = g.gi0 + s.count;
-    if (s.count < 0 || g.gi0 + s.count > total) FAIL(B200_INVALID_ARGUMENT, "graph_index0 out of range");
+    if (s.count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
+    g.pos.resize(s.count);
+    if (s.graph_index) {
+      for (int64_t i = 0; i < s.count; i++) g.pos[i] = s.graph_index[i];
+    } else {
+      const int64_t gi0 = s.graph_index0 < 0 ? next : s.graph_index0;
+      for (int64_t i = 0; i < s.count; i++) g.pos[i] = gi0 + i;
+      next = gi0 + s.count;
+    }
     if (s.count > INT_MAX / 2) FAIL(B200_INVALID_ARGUMENT, "factor group too large");
     for (int64_t i = 0; i < s.count; i++) {
-      if (used[g.gi0 + i]) FAIL(B200_INVALID_ARGUMENT, "overlapping graph positions");
-      used[g.gi0 + i] = 1;
+      if (g.pos[i] < 0 || g.pos[i] >= total) FAIL(B200_INVALID_ARGUMENT, "graph position out of range");
+      if (used[g.pos[i]]) FAIL(B200_INVALID_ARGUMENT, "overlapping graph positions");
+      used[g.pos[i]] = 1;
       for (int a = 0; a < g.arity; a++) {
         const int64_t k = s.keys[i * g.arity + a];
         if (k < 0 || k >= n || d->var_type[k] != F_VT[s.type][a])
           FAIL(B200_INVALID_ARGUMENT, "factor key missing or of the wrong value type (ValuesKeyDoesNotExist / ValuesIncorrectType)");
       }
-      pk->fkey0[g.gi0 + i] = s.keys[i * g.arity];
-      if (g.arity == 2) pk->fkey1[g.gi0 + i] = s.keys[i * g.arity + 1];
+      pk->fkey0[g.pos[i]] = s.keys[i * g.arity];
+      if (g.arity == 2) pk->fkey1[g.pos[i]] = s.keys[i * g.arity + 1];
     }
     if (s.type == B200_FACTOR_PROJECTION_CAL3S2) {
       if (d->ncal < 1) FAIL(B200_INVALID_ARGUMENT, "projection factors need a calibration");
@@ -673,7 +685,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     auto& g = p->groups[gi];
     const PackedGroup& q = pk.groups[gi];
     g.type = q.type; g.noise_kind = q.noise_kind; g.per_factor = q.per_factor; g.noise_size = q.noise_size;
-    g.d = q.d; g.ncols = q.ncols; g.arity = q.arity; g.meas = q.meas; g.count = q.count; g.gi0 = q.gi0;
+    g.d = q.d; g.ncols = q.ncols; g.arity = q.arity; g.meas = q.meas; g.count = q.count; g.pos = q.pos;
     g.robust_kind = q.robust_kind; g.robust_param = q.robust_param;
   }
   p->sym = std::move(pk.sym);
@@ -724,7 +736,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     std::vector<int> cf_count(S.ncliques, 0), cf_mask(S.ncliques, 0), kind(S.ncliques, 0);
     for (int64_t gi = 0; gi < d->ngroups; gi++)
       for (int64_t i = 0; i < d->groups[gi].count; i++) {
-        const int c = S.fac_clique[p->groups[gi].gi0 + i];
+        const int c = S.fac_clique[p->groups[gi].pos[i]];
         if (fused[c]) { cf_count[c]++; cf_mask[c] |= 1 << d->groups[gi].type; }
       }
     const bool fast = !getenv("B200_NO_POINT_KERNEL");
@@ -790,7 +802,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     auto& g = p->groups[gi];
     // keep only the factors this rank owns (all of them when world == 1)
     std::vector<int64_t>& keep = g.local_index;
-    for (int64_t i = 0; i < s.count; i++) if (factor_owner[g.gi0 + i] == rank) keep.push_back(i);
+    for (int64_t i = 0; i < s.count; i++) if (factor_owner[g.pos[i]] == rank) keep.push_back(i);
     const int64_t nl = (int64_t)keep.size();
     hkeys[gi].resize(nl);
     hscat[gi].resize(nl);
@@ -798,7 +810,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     std::vector<int> hcal;
     if (s.noise_per_factor) hnoise.resize((size_t)nl * g.noise_size);
     for (int64_t li = 0; li < nl; li++) {
-      const int64_t i = keep[li], pos = g.gi0 + i;
+      const int64_t i = keep[li], pos = g.pos[i];
       hkeys[gi][li] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
       const int isleaf = fused[S.fac_clique[pos]];
       hscat[gi][li] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
@@ -847,13 +859,13 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     std::vector<int> cur(fptr.begin(), fptr.end() - 1);
     for (int64_t gi = 0; gi < d->ngroups; gi++)
       for (int64_t li = 0; li < p->groups[gi].count; li++) {
-        const int64_t pos = p->groups[gi].gi0 + p->groups[gi].local_index[li];
+        const int64_t pos = p->groups[gi].pos[p->groups[gi].local_index[li]];
         if (lpos[S.fac_clique[pos]] >= 0) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)li);
       }
     // keep graph order inside each clique (groups may interleave in the graph)
     for (int i = 0; i < p->n_fused; i++)
       std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) {
-        return p->groups[a.x].gi0 + p->groups[a.x].local_index[a.y] < p->groups[b.x].gi0 + p->groups[b.x].local_index[b.y]; });
+        return p->groups[a.x].pos[p->groups[a.x].local_index[a.y]] < p->groups[b.x].pos[p->groups[b.x].local_index[b.y]]; });
     UP(upload(&p->d_fused_list, fused_list, st));
     UP(upload(&p->d_fused_run_ptr, run_ptr, st));
     UP(upload(&p->d_fused_fac_ptr, fptr, st));

@@ -93,7 +93,8 @@ struct b200_problem {
     int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas;
     int robust_kind = 0;
     double robust_param = 0;
-    int64_t count, gi0;
+    int64_t count;
+    std::vector<int64_t> pos;          // graph position of every factor of the caller's group
     int2* d_keys = nullptr;
     double* d_meas = nullptr;
     double* d_noise = nullptr;

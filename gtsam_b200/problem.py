@@ -51,7 +51,8 @@ class CFactorGroup(C.Structure):
                 ("robust_kind", C.c_int32), ("count", C.c_int64), ("graph_index0", C.c_int64),
                 ("keys", C.POINTER(C.c_int64)), ("meas", C.POINTER(C.c_double)),
                 ("noise", C.POINTER(C.c_double)), ("cal_index", C.POINTER(C.c_int32)),
-                ("body_P_sensor", C.POINTER(C.c_double)), ("robust_param", C.c_double)]
+                ("body_P_sensor", C.POINTER(C.c_double)), ("robust_param", C.c_double),
+                ("graph_index", C.POINTER(C.c_int64))]
 
 
 class CProblemDesc(C.Structure):
@@ -102,6 +103,7 @@ class FactorGroup:
     body_P_sensor: Optional[np.ndarray] = None   # (12,) Pose3 shared by the group (projection factors)
     robust_kind: int = 0                          # ROBUST_*: noiseModel::Robust around the noise model
     robust_param: float = 0.0
+    graph_index: Optional[np.ndarray] = None      # explicit graph positions (non-consecutive factors)
 
     def __post_init__(self):
         ar, ms = FACTOR_ARITY[self.type], FACTOR_MEAS[self.type]
@@ -118,6 +120,9 @@ class FactorGroup:
             self.cal_index = np.ascontiguousarray(self.cal_index, dtype=np.int32)
         if self.body_P_sensor is not None:
             self.body_P_sensor = np.ascontiguousarray(self.body_P_sensor, dtype=np.float64).reshape(12)
+        if self.graph_index is not None:
+            self.graph_index = np.ascontiguousarray(self.graph_index, dtype=np.int64)
+            assert self.graph_index.size == self.keys.shape[0]
 
     @property
     def count(self) -> int:
@@ -146,6 +151,8 @@ class Problem:
         self.cal = np.ascontiguousarray(self.cal, dtype=np.float64).reshape(-1, 5)
         nxt = 0
         for g in self.groups:  # resolve graph positions
+            if g.graph_index is not None:
+                continue
             if g.graph_index0 < 0:
                 g.graph_index0 = nxt
             nxt = g.graph_index0 + g.count
@@ -197,6 +204,7 @@ class Problem:
             garr[i].body_P_sensor = _ptr(g.body_P_sensor, C.c_double)
             garr[i].robust_kind = g.robust_kind
             garr[i].robust_param = g.robust_param
+            garr[i].graph_index = _ptr(g.graph_index, C.c_int64)
         d = CProblemDesc()
         d.nvars = self.nvars
         d.var_type = _ptr(self.var_type, C.c_int32)
@@ -224,7 +232,7 @@ class Problem:
             f.write(struct.pack("<q", len(self.groups)))
             for g in self.groups:
                 f.write(struct.pack("<iiiiqq", g.type, g.noise_kind, g.noise_per_factor,
-                                    int(g.cal_index is not None) | (2 if g.body_P_sensor is not None else 0) | (g.robust_kind << 8),
+                                    int(g.cal_index is not None) | (2 if g.body_P_sensor is not None else 0) | (4 if g.graph_index is not None else 0) | (g.robust_kind << 8),
                                     g.count, g.graph_index0))
                 f.write(g.keys.tobytes())
                 f.write(g.meas.tobytes())
@@ -236,6 +244,8 @@ class Problem:
                     f.write(g.body_P_sensor.tobytes())
                 if g.robust_kind:
                     f.write(struct.pack("<d", g.robust_param))
+                if g.graph_index is not None:
+                    f.write(g.graph_index.tobytes())
 
     @classmethod
     def load(cls, path: str) -> "Problem":
@@ -275,5 +285,6 @@ class Problem:
             body = arr(np.float64, 12) if hc & 2 else None
             rk = (hc >> 8) & 0xff
             (rp,) = rd("<d") if rk else (0.0,)
-            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0, body, rk, rp))
+            gidx = arr(np.int64, cnt) if hc & 4 else None
+            groups.append(FactorGroup(t, keys, meas, nk, noise, ci, gi0, body, rk, rp, gidx))
         return cls(vt, vals, order, groups, cal)

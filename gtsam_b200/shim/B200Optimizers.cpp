@@ -60,7 +60,8 @@ struct GroupBuf {
   std::vector<double> meas, noise;
   std::vector<int32_t> cal;
   std::vector<double> body;   // body_P_sensor shared by the group (empty: none)
-  int64_t count = 0, gi0 = 0;
+  std::vector<int64_t> pos;   // graph position of every factor (factors of one kind need not be consecutive)
+  int64_t count = 0;
 };
 
 struct DeviceState {
@@ -203,12 +204,18 @@ struct DeviceState {
       int rkind; double rparam;
       const SharedNoiseModel base = unwrapRobust(nm, &rkind, &rparam);
       const int kind = noiseOf(base, d, pay);
-      if (groups.empty() || groups.back().type != type || groups.back().noise_kind != kind || groups.back().body != body ||
-          groups.back().robust_kind != rkind || groups.back().robust_param != rparam) {
-        GroupBuf g; g.type = type; g.noise_kind = kind; g.gi0 = pos; g.body = body; g.robust_kind = rkind; g.robust_param = rparam;
+      // bucket by (type, noise kind, robust loss, body_P_sensor): a graph that interleaves factor
+      // kinds still becomes a handful of homogeneous tables, each with explicit graph positions
+      size_t gidx = groups.size();
+      for (size_t q = 0; q < groups.size(); q++)
+        if (groups[q].type == type && groups[q].noise_kind == kind && groups[q].body == body &&
+            groups[q].robust_kind == rkind && groups[q].robust_param == rparam) { gidx = q; break; }
+      if (gidx == groups.size()) {
+        GroupBuf g; g.type = type; g.noise_kind = kind; g.body = body; g.robust_kind = rkind; g.robust_param = rparam;
         groups.push_back(g);
       }
-      GroupBuf& g = groups.back();
+      GroupBuf& g = groups[gidx];
+      g.pos.push_back(pos);
       g.keys.insert(g.keys.end(), keys.begin(), keys.end());
       g.meas.insert(g.meas.end(), meas.begin(), meas.end());
       g.noise.insert(g.noise.end(), pay.begin(), pay.end());
@@ -228,7 +235,7 @@ struct DeviceState {
     for (size_t i = 0; i < groups.size(); i++) {
       cg[i].type = groups[i].type; cg[i].noise_kind = groups[i].noise_kind;
       cg[i].noise_per_factor = groups[i].noise_kind != B200_NOISE_UNIT && groups[i].count > 1;
-      cg[i].robust_kind = groups[i].robust_kind; cg[i].robust_param = groups[i].robust_param; cg[i].count = groups[i].count; cg[i].graph_index0 = groups[i].gi0;
+      cg[i].robust_kind = groups[i].robust_kind; cg[i].robust_param = groups[i].robust_param; cg[i].count = groups[i].count; cg[i].graph_index0 = -1; cg[i].graph_index = groups[i].pos.data();
       cg[i].keys = groups[i].keys.data(); cg[i].meas = groups[i].meas.data(); cg[i].noise = groups[i].noise.data();
       cg[i].cal_index = groups[i].type == B200_FACTOR_PROJECTION_CAL3S2 ? groups[i].cal.data() : nullptr;
       cg[i].body_P_sensor = groups[i].body.empty() ? nullptr : groups[i].body.data();
@@ -298,7 +305,7 @@ GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::iterate() {
 GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::linearize() const {
   check(b200_linearize(dev_->prob), "b200_linearize");
   size_t total = 0;
-  for (auto& g : dev_->groups) total = std::max<size_t>(total, (size_t)(g.gi0 + g.count));
+  for (auto& g : dev_->groups) total += (size_t)g.count;
   std::vector<GaussianFactor::shared_ptr> out(total);
   for (size_t gi = 0; gi < dev_->groups.size(); gi++) {
     const GroupBuf& g = dev_->groups[gi];
@@ -312,8 +319,8 @@ GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::linearize() con
       Eigen::Map<const Matrix> Ab(J.data() + (size_t)i * d * ncols, d, ncols);
       const Vector b = Ab.col(ncols - 1);
       const Key k1 = dev_->id2key[g.keys[i * ar]];
-      if (ar == 1) out[g.gi0 + i] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), b);
-      else out[g.gi0 + i] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), dev_->id2key[g.keys[i * ar + 1]],
+      if (ar == 1) out[g.pos[i]] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), b);
+      else out[g.pos[i]] = std::make_shared<JacobianFactor>(k1, Matrix(Ab.leftCols(dims[0])), dev_->id2key[g.keys[i * ar + 1]],
                                                              Matrix(Ab.middleCols(dims[0], dims[1])), b);
     }
   }

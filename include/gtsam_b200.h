@@ -113,6 +113,9 @@ typedef struct b200_factor_group {
                                the group = GenericProjectionFactor's body_P_sensor
                                (gtsam/slam/ProjectionFactor.h:141-151), or NULL       */
   double robust_param;      /* k (Huber, Cauchy) / c (Tukey, Fair)                     */
+  const int64_t* graph_index; /* optional: explicit graph position of every factor of the
+                               group (count entries), for factors of one kind that are NOT
+                               consecutive in the NonlinearFactorGraph; NULL => graph_index0 + i */
 } b200_factor_group;
 
 typedef struct b200_problem_desc {

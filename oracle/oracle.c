@@ -644,8 +644,8 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
     o->robust_kind = s->robust_kind; o->robust_param = s->robust_param;
     if (s->robust_kind < 0 || s->robust_kind > B200_ROBUST_FAIR || (s->robust_kind && s->type == B200_FACTOR_SFM_BUNDLER)) return B200_UNSUPPORTED_NOISE;
     o->count = s->count;
-    o->graph_index0 = s->graph_index0 < 0 ? next : s->graph_index0;
-    next = o->graph_index0 + s->count;
+    o->graph_index0 = s->graph_index ? -1 : (s->graph_index0 < 0 ? next : s->graph_index0);
+    if (!s->graph_index) next = o->graph_index0 + s->count;
     const int ar = F_ARITY[s->type], ms = F_MEAS[s->type], d = F_DIM[s->type];
     o->d = d;
     o->ncols = VAR_DIM[F_VT[s->type][0]] + (ar == 2 ? VAR_DIM[F_VT[s->type][1]] : 0) + 1;
@@ -665,8 +665,8 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
     }
     o->J = (double*)calloc((size_t)(s->count * d * o->ncols + 1), sizeof(double));
     for (int64_t i = 0; i < s->count; i++) {
-      const int64_t gi = o->graph_index0 + i;
-      if (gi >= total || p->fgroup[gi] != -1) return B200_INVALID_ARGUMENT;
+      const int64_t gi = s->graph_index ? s->graph_index[i] : o->graph_index0 + i;
+      if (gi < 0 || gi >= total || p->fgroup[gi] != -1) return B200_INVALID_ARGUMENT;
       p->fgroup[gi] = (int32_t)g;
       p->fidx[gi] = i;
       for (int a = 0; a < ar; a++) {

@@ -51,6 +51,7 @@ struct Group {
   std::vector<double> meas, noise;
   std::vector<int32_t> cal_index;
   std::vector<double> body;  // body_P_sensor (12) when has_cal & 2
+  std::vector<int64_t> gidx; // explicit graph positions when has_cal & 4
   int robust_kind = 0;       // (has_cal >> 8) & 0xff
   double robust_param = 0;
 };
@@ -104,6 +105,7 @@ static Prob load(const std::string& path) {
     if (g.has_cal & 2) { g.body.resize(12); rd(f, g.body.data(), 12); }
     g.robust_kind = (g.has_cal >> 8) & 0xff;
     if (g.robust_kind) rd(f, &g.robust_param, 1);
+    if (g.has_cal & 4) { g.gidx.resize(g.count); rd(f, g.gidx.data(), g.count); }
   }
   return p;
 }
@@ -197,7 +199,7 @@ static Built build(const Prob& p) {
         case 4: f = std::make_shared<GeneralSFMFactor<BCam, Point3>>(Point2(z[0], z[1]), nm, k[0], k[1]); break;
         case 5: f = std::make_shared<PriorFactor<BCam>>(k[0], mkcam(z), nm); break;
       }
-      fs[g.gi0 + i] = f;
+      fs[(g.has_cal & 4) ? g.gidx[i] : g.gi0 + i] = f;
     }
   }
   for (auto& f : fs) b.graph.push_back(f);

@@ -65,8 +65,9 @@ static void dump_jacobians(const Prob& p, const GaussianFactorGraph& lin, Out& o
     const Group& g = p.groups[gi];
     std::vector<double> J;
     for (int64_t i = 0; i < g.count; i++) {
-      auto jf = std::dynamic_pointer_cast<JacobianFactor>(lin[g.gi0 + i]);
-      if (!jf) { fprintf(stderr, "factor %ld is not a JacobianFactor\n", (long)(g.gi0 + i)); exit(3); }
+      const int64_t gpos = (g.has_cal & 4) ? g.gidx[i] : g.gi0 + i;
+      auto jf = std::dynamic_pointer_cast<JacobianFactor>(lin[gpos]);
+      if (!jf) { fprintf(stderr, "factor %ld is not a JacobianFactor\n", (long)gpos); exit(3); }
       /* apply any remaining (non-unit) model so the dump is the whitened system */
       Matrix Ab = jf->augmentedJacobian();  // whitened [A b]
       /* columns are in the factor's key order, which for our factors is (key1,key2) */
@@ -284,6 +285,7 @@ static void save(const Prob& p, const std::string& path) {
     if (g.has_cal & 1) wr(f, g.cal_index.data(), g.cal_index.size());
     if (g.has_cal & 2) wr(f, g.body.data(), g.body.size());
     if ((g.has_cal >> 8) & 0xff) wr(f, &g.robust_param, 1);
+    if (g.has_cal & 4) wr(f, g.gidx.data(), g.gidx.size());
   }
 }
 

@@ -53,6 +53,7 @@ def main():
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
     emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2)
     from gtsam_b200 import problem as Pq
+    import numpy as np
     emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2)
     emit("sphere_tiny_cauchy", datasets.sphere(layers=5, per_ring=8, seed=14, noise="gaussian", robust=(Pq.ROBUST_CAUCHY, 2.0)))
     bt = datasets.make("bal_tiny", seed=15)
@@ -61,6 +62,13 @@ def main():
     bf = datasets.make("bal_tiny", seed=16)
     bf.groups[0].robust_kind, bf.groups[0].robust_param = Pq.ROBUST_FAIR, 1.3998
     emit("bal_tiny_fair", bf)
+    # factors of one kind that are NOT consecutive in the graph (explicit graph positions)
+    si = datasets.sphere(layers=5, per_ring=8, seed=17)
+    nb = si.groups[0].count
+    kpos = nb // 3
+    si.groups[0].graph_index = np.concatenate([np.arange(kpos), np.arange(kpos + 1, nb + 1)])
+    si.groups[1].graph_index = np.array([kpos])
+    emit("sphere_tiny_interleaved", si, gn_iters=2)
     emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
     # ---- input formats: synthetic text files written by gtsam_b200.io, parsed by the
     # REFERENCE's loaders (readG2o / SfmData::FromBalFile) into *.prob.bin; tests compare our readers with them

@@ -36,7 +36,8 @@ def check(r, rtol):
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="shim_parity not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("case", ["bal_tiny_s2", "bal_tiny_bundler", "sphere_small_colamd", "dubrovnik_3_7_unit"])
+@pytest.mark.parametrize("case", ["bal_tiny_s2", "bal_tiny_bundler", "sphere_small_colamd", "dubrovnik_3_7_unit", "bal_tiny_body_sensor",
+                                  "sphere_tiny_huber", "bal_tiny_tukey", "sphere_tiny_interleaved", "pose3example"])
 def test_shim_matches_stock_optimizer(case):
     r = run(os.path.join(util.GOLDEN, f"{case}.prob.bin"), 100 if case.startswith("dub") else 30, int(case in util.CERES_CASES))
     check(r, 1e-5 if case.startswith("dub") else 1e-7)
