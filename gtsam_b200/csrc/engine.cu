@@ -247,7 +247,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (L.large_count) {
       PhaseScope ps(p, PH_ELIM_LARGE);
       const int* list = p->d_lvl_large + L.large_begin;
-      const bool big = L.large_max_n >= 1024;   // big fronts: one K=128 trailing update per 128 columns
+      const bool big = L.large_max_n >= p->big_min_n;   // big fronts: one K=128 trailing update per 128 columns
       auto tiles = [](int rows, int cols, int T) {   // upper-trapezoid tile count
         const int TR = (rows + T - 1) / T, TC = (cols + T - 1) / T;
         int cnt = 0;
@@ -269,7 +269,8 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
         }
         if (big) {
           const int m = L.large_max_n - K0 - 1;
-          launch_k(update_kernel<128, 8, 16>, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, 2, K0, 0, p->d_rdiag);
+          if (p->use_dmma) launch_k(update_dmma_kernel, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, K0);
+          else launch_k(update_kernel<128, 8, 16>, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, 2, K0, 0, p->d_rdiag);
           ctx->launches++;
         }
       }
@@ -782,6 +783,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     p->leaf_lb_cap = lb; p->leaf_acc_cap = tri;
   }
   p->n_fused = (int)fused_list.size();
+  p->big_min_n = getenv("B200_BIG_MIN_N") ? atoi(getenv("B200_BIG_MIN_N")) : 1024;
+  p->use_dmma = getenv("B200_NO_DMMA") == nullptr;
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
   {

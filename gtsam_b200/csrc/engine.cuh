@@ -116,6 +116,8 @@ struct b200_problem {
   std::vector<int64_t> h_off;       // final arena offsets (fused leaves store f x n only)
   std::vector<int> h_ld;
   // fused leaf path
+  int big_min_n = 1024;   // fronts at least this large use the 128-column big-panel scheme
+  bool use_dmma = true;   // trailing update of big fronts on the FP64 tensor path (DMMA)
   int n_fused = 0, n_runs = 0, leaf_lb_cap = 1, leaf_acc_cap = 0;
   int leaf_run_begin[3] = {0, 0, 0}, leaf_run_end[3] = {0, 0, 0};  // run ranges: generic / point DC=6 / point DC=9
   int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr, *d_fused_run_ptr = nullptr;

@@ -899,6 +899,78 @@ update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0
     }
 }
 
+// (3) the same trailing update for genuinely dense big fronts on the FP64 tensor path:
+// mma.sync.aligned.m8n8k4.row.col.f64 (SASS: DMMA).  128x128 tile per CTA, 8 warps as 2x4,
+// each warp owns 64x32 = 8x4 MMA tiles (64 FP64 accumulators per thread).  Fragment layout
+// (PTX ISA, m8n8k4 .f64): A(row i = lane/4, col k = lane%4), B(row k = lane%4, col j = lane/4),
+// C/D(row i = lane/4, cols 2*(lane%4) + {0,1}).  With C -= P^T P: A[i][k] = P[k][i], B[k][j] = P[k][j],
+// both straight out of the staged row panels.  Only mode 2 (TRAIL) of update_kernel.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0) {
+  constexpr int TILE = 128, KC = 16;
+  __shared__ double Pi[KC][TILE + 4];
+  __shared__ double Pj[KC][TILE + 4];
+  pdl_sync();
+  const int c = list[blockIdx.y];
+  const int f = t.nf[c], n = f + t.ns[c] + 1;
+  if (K0 >= f) return;
+  double* M = t.arena + t.off[c];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pa = K0, pb = min(K0 + kBig, f), ia = pb;
+  if (ia >= n) return;
+  const int TC = (n - ia + TILE - 1) / TILE;
+  int rem = blockIdx.x, ti = 0;
+  while (ti < TC && rem >= TC - ti) { rem -= TC - ti; ti++; }
+  if (ti >= TC) return;
+  const int tj = ti + rem;
+  const int i0 = ia + ti * TILE, j0 = ia + tj * TILE;
+  const int wi = (warp >> 2) * 64, wj = (warp & 3) * 32;   // warp sub-tile origin inside the CTA tile
+  const int g = lane >> 2, q = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int kk = pa; kk < pb; kk += KC) {
+    for (int e = tid; e < KC * TILE; e += 256) {
+      const int p = e % KC, cc = e / KC;
+      const int gi = i0 + cc, gj = j0 + cc;
+      const bool pv = kk + p < pb;
+      Pi[p][cc] = (pv && gi < n) ? M[(kk + p) + (size_t)gi * n] : 0.0;
+      Pj[p][cc] = (pv && gj < n) ? M[(kk + p) + (size_t)gj * n] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int a = 0; a < 8; a++) af[a] = Pi[k4 + q][wi + 8 * a + g];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bf[b] = Pj[k4 + q][wj + 8 * b + g];
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int gi = i0 + wi + 8 * a + g, gj = j0 + wj + 8 * b + 2 * q + h;
+        if (gi < n && gj < n && gi <= gj) M[gi + (size_t)gj * n] -= acc[a][b][h];
+      }
+}
+
 __global__ void __launch_bounds__(256) extend_add_kernel(TreeView t, const int* __restrict__ list) {
   pdl_sync();
   const int c = list[blockIdx.y];

@@ -155,7 +155,7 @@ def _normal_equation_residual(prob, dev, lam):
     return float(np.linalg.norm(A.T @ (A @ dl - b) + lam * dl) / np.linalg.norm(g0)), A, b, dl
 
 
-@pytest.mark.parametrize("workload,lam", [("bal_c3", 1e-5), ("sphere2500", 0.0)])
+@pytest.mark.parametrize("workload,lam", [("bal_c3", 1e-5), ("sphere2500", 0.0), ("bal_1m", 1e-5)])
 def test_full_size_normal_equations(gpu_ctx, workload, lam):
     """BASELINE.json configs[2] / configs[1] at full size: delta satisfies the damped normal
     equations to 1e-9 and the reported linear errors equal 0.5|b|^2 and 0.5|A delta - b|^2."""
@@ -203,3 +203,28 @@ def test_cuda_edge_cases(gpu_ctx, name):
         lm.iterate(); orc.lm_iterate(olm)
         assert abs(lm.error() - olm.state.error) <= 1e-8 * max(1.0, olm.state.error)
         assert lm.lambda_() == olm.state.lambda_
+
+
+@pytest.mark.parametrize("no_dmma", [False, True])
+def test_big_front_scheme_matches_oracle(gpu_ctx, monkeypatch, no_dmma):
+    """Fronts >= 1024 use 128-column big panels (band updates + one K=128 trailing update, on the
+    FP64 tensor path: mma.sync m8n8k4 f64 / DMMA).  Force that scheme on mid-size fronts
+    (B200_BIG_MIN_N) so it is covered at a size the oracle finishes in seconds."""
+    monkeypatch.setenv("B200_BIG_MIN_N", "64")
+    if no_dmma:
+        monkeypatch.setenv("B200_NO_DMMA", "1")
+    for kw in (dict(layers=14, per_ring=24), dict(layers=14, per_ring=24, ordering="reverse")):
+        prob = datasets.make("sphere_tiny", **kw)
+        dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+        assert dev.symbolic_info().max_frontal_dim + dev.symbolic_info().max_separator_dim >= 256
+        dev.linearize(); orc.linearize()
+        for lam in (0.0, 1e-3):
+            st, e0, e1, _ = dev.solve(lam)
+            so, f0, f1, _ = orc.solve(lam)
+            assert st == so == 0
+            assert util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+            assert abs(e1 - f1) <= 1e-9 * f0
+        info = dev.symbolic_info()
+        a, b = dev.conditional(info.ncliques - 1), orc.conditional(info.ncliques - 1)
+        assert np.abs(a - b).max() <= 1e-7 * max(1.0, np.abs(b).max())
+        dev.close()
