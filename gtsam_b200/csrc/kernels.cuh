@@ -1,17 +1,20 @@
-// kernels.cuh — the sm_100a kernels of the hot path (FP64).
+// kernels.cuh — the sm_100a kernels of the hot path (FP64).  Reference rows of SURVEY.md §8(a):
 //
-//  linearize_kernel   a1-a7  residual + Jacobian + whitening, one thread / factor,
-//                            SoA (element-major) stores => every store coalesced
-//  error_kernel       a8     0.5*|R r|^2 block partial sums (deterministic 2-stage)
-//  assemble_kernel    a12    J^T J / J^T b / b^T b scatter-add into the owning front
-//  damp_kernel        a10    lambda*I or lambda*clip(diag H) on the diagonal
-//  hdiag_kernel       a10    hessianDiagonal
-//  elim_small_kernel  a13/14 one warp per clique: partial Cholesky in shared
-//                            memory + fused extend-add into the parent front
-//  panel_kernel, update_kernel, extend_add_kernel   a13/14 for large fronts
-//  backsub_*_kernel   a15    x_F = R^-1 (d - S x_S), level by level
-//  linerr_kernel      a16    0.5*|A delta - b|^2 and 0.5*|b|^2
-//  retract_kernel     a9     x (+) delta per variable
+//  linearize_kernel      a1-a7   residual + Jacobian + whitening (+ robust reweighting), one thread per
+//                                factor, element-major SoA stores => every store instruction coalesced
+//  error_kernel          a8      0.5*|R r|^2 or rho(|R r|); single launch, last-block reduction in index order
+//  leaf_point_kernel<DC> a10+a12+a13+a14  BAL point cliques: assemble + damp + 3x3 Cholesky + Schur update,
+//                                one lane per factor, runs of points with the same cameras share one extend-add
+//  leaf_fused_kernel     a10+a12+a13+a14  any leaf clique with a small frontal block
+//  assemble_kernel       a12     J^T J / J^T b / b^T b scatter-add into the owning non-leaf front
+//  hdiag_kernel, damp_kernel  a10  hessianDiagonal; lambda*I or lambda*clip(diag H) on the diagonal
+//  elim_small_kernel     a13/14  one warp per small non-leaf front in shared memory, fused extend-add
+//  panel_kernel          a13     32x32 diagonal Cholesky (one warp, registers + shuffles) + TRSM of the row panel
+//  update_kernel, update_dmma_kernel  a13  C -= S^T S on the upper trapezoid (FP64 FMA tiles / DMMA for big fronts)
+//  extend_add_kernel     a12     child Schur complement into the parent front
+//  backsub_small_kernel, backsub_large_kernel  a15  x_F = R^-1 (d - S x_S), level by level
+//  linerr_kernel         a16     0.5*|A delta - b|^2 and 0.5*|b|^2 in one pass
+//  retract_kernel        a9      x (+) delta per variable
 #pragma once
 #include <climits>
 
@@ -93,16 +96,6 @@ __device__ __forceinline__ void finish_sum(double block_value, double* partials,
   __threadfence();
   double s = 0;
   for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partials + i);
-  s = block_sum<256>(s, sh);
-  if (threadIdx.x == 0) *out = accumulate ? (*out + s) : s;
-}
-
-// out[0] (+)= sum(partials[0..n)) in a fixed order => bitwise reproducible
-__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n, double* out, int accumulate) {
-  pdl_sync();
-  __shared__ double sh[32];
-  double s = 0;
-  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
   s = block_sum<256>(s, sh);
   if (threadIdx.x == 0) *out = accumulate ? (*out + s) : s;
 }
