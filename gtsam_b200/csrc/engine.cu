@@ -191,7 +191,6 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   if (damped) {
     PhaseScope ps(p, PH_DAMP);
     if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
-    if (ctx->rank == 0)   // the shared top is summed over ranks: its damping priors are added once
     launch_k(damp_kernel, dim3((int)((p->ndelta + 255) / 256)), dim3(256), 0, st, p->d_arena, p->d_diag_index, (int)p->ndelta, p->d_lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
     ctx->launches++;
@@ -226,15 +225,15 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       ctx->launches++;
     }
   }
-  if (ctx->world > 1) {
-    // the one exchange step of the solve — sum the Schur complements every rank
-    // accumulated into its copy of the shared top fronts (NCCL over NVLink, in place, on-stream)
-    PhaseScope ps(p, PH_ALLREDUCE);
-    const int rc = allreduce_sum(p, p->d_arena, (size_t)p->zero_doubles);
-    if (rc) return rc;
-  }
   // ---- elimination, leaves to roots ----
   for (size_t l = 0; l < p->levels.size(); l++) {
+    if ((int)l == p->n_sub_levels && ctx->world > 1) {
+      // the one exchange step of the solve — every rank has eliminated its own subtrees
+      // into its copy of the shared top fronts; sum them (NCCL over NVLink, in place, on-stream)
+      PhaseScope ps(p, PH_ALLREDUCE);
+      const int rc = allreduce_sum(p, p->d_arena, (size_t)p->top_doubles);
+      if (rc) return rc;
+    }
     const LevelPlan& L = p->levels[l];
     if (L.small_count) {
       PhaseScope ps(p, PH_ELIM_SMALL);
@@ -446,28 +445,71 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
 }
 
 // ---- sharding plan ------------------------------------------------------
-// Which leaf cliques take the fused path, and which rank owns each of them.  Fused leaf
-// cliques (+ their factors and frontal variables) are partitioned over the ranks in clique
-// order, balanced by factor count; every other clique is the shared "top" of the tree,
-// replicated on all ranks; factors owned by top cliques belong to rank 0.
+// Which leaf cliques take the fused path; which cliques form the replicated TOP of the junction
+// tree; which rank owns every other clique.  The top T is ancestor-closed: starting from the
+// roots, the heaviest subtree root is moved into T and replaced by its children until every
+// remaining subtree is lighter than total/(4*world) (for BAL with Schur ordering T ends up being
+// the camera cliques and the subtrees the points; for nested-dissection orderings T is the top
+// separators and the subtrees the ND branches).  The remaining subtrees are assigned to ranks
+// in clique order by prefix weight (keeps neighbouring leaves, and their shared separators,
+// together).  Factors follow the clique that owns them; factors of top cliques belong to rank 0.
 static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int world, std::vector<char>* fused,
-                       std::vector<int>* clique_owner, std::vector<int>* factor_owner) {
+                       std::vector<char>* is_top, std::vector<int>* clique_owner, std::vector<int>* factor_owner) {
   const bool leaf_path = ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
-  fused->assign(S.ncliques, 0);
-  for (int64_t c = 0; c < S.ncliques; c++) {
+  const int64_t nc = S.ncliques;
+  fused->assign(nc, 0);
+  for (int64_t c = 0; c < nc; c++) {
     const int64_t nn = S.nf[c] + S.ns[c] + 1;
     if (leaf_path && S.level[c] == 0 && S.nf[c] <= kLeafMaxF && (int64_t)S.nf[c] * nn <= kLeafMaxFN) (*fused)[c] = 1;
   }
-  std::vector<int64_t> nfac(S.ncliques, 0);
-  int64_t leaf_total = 0;
-  for (int64_t pos = 0; pos < total; pos++)
-    if ((*fused)[S.fac_clique[pos]]) { nfac[S.fac_clique[pos]]++; leaf_total++; }
-  clique_owner->assign(S.ncliques, -1);
-  int64_t prefix = 0;
-  for (int64_t c = 0; c < S.ncliques; c++) {
-    if (!(*fused)[c]) continue;
-    (*clique_owner)[c] = leaf_total ? (int)std::min<int64_t>(world - 1, prefix * world / leaf_total) : 0;
-    prefix += nfac[c];
+  is_top->assign(nc, 0);
+  clique_owner->assign(nc, 0);
+  if (world > 1) {
+    std::vector<int64_t> nfac(nc, 0);
+    for (int64_t pos = 0; pos < total; pos++) nfac[S.fac_clique[pos]]++;
+    std::vector<double> w(nc, 0.0);
+    std::vector<int64_t> ch_ptr(nc + 1, 0);
+    for (int64_t c = 0; c < nc; c++) if (S.parent[c] >= 0) ch_ptr[S.parent[c] + 1]++;
+    for (int64_t c = 0; c < nc; c++) ch_ptr[c + 1] += ch_ptr[c];
+    std::vector<int64_t> ch(ch_ptr[nc]), cur(ch_ptr.begin(), ch_ptr.end() - 1);
+    for (int64_t c = 0; c < nc; c++) if (S.parent[c] >= 0) ch[cur[S.parent[c]]++] = c;
+    double sum = 0;
+    for (int64_t c = 0; c < nc; c++) {   // children have smaller ids than parents
+      const double nn = S.nf[c] + S.ns[c] + 1;
+      w[c] += nn * nn * (S.nf[c] + 1) + 200.0 * (double)nfac[c];
+      if (S.parent[c] >= 0) w[S.parent[c]] += w[c]; else sum += w[c];
+    }
+    const double target = sum / (4.0 * world);
+    std::vector<std::pair<double, int64_t>> heap;
+    for (int64_t c = 0; c < nc; c++) if (S.parent[c] < 0) heap.push_back({w[c], c});
+    std::make_heap(heap.begin(), heap.end());
+    while (!heap.empty()) {
+      const auto top = heap.front();
+      const int64_t c = top.second;
+      if (top.first <= target || ch_ptr[c + 1] == ch_ptr[c]) break;
+      std::pop_heap(heap.begin(), heap.end());
+      heap.pop_back();
+      (*is_top)[c] = 1;
+      for (int64_t q = ch_ptr[c]; q < ch_ptr[c + 1]; q++) {
+        heap.push_back({w[ch[q]], ch[q]});
+        std::push_heap(heap.begin(), heap.end());
+      }
+    }
+    std::vector<int64_t> roots;
+    double subsum = 0;
+    for (auto& e : heap) { roots.push_back(e.second); subsum += e.first; }
+    std::sort(roots.begin(), roots.end());
+    std::vector<int> assigned(nc, 0);
+    double prefix = 0;
+    for (int64_t r : roots) {
+      assigned[r] = subsum > 0 ? (int)std::min<double>(world - 1, std::floor(prefix * world / subsum)) : 0;
+      prefix += w[r];
+    }
+    for (int64_t c = nc - 1; c >= 0; c--) {
+      if ((*is_top)[c]) (*clique_owner)[c] = -1;
+      else if (S.parent[c] < 0 || (*is_top)[S.parent[c]]) (*clique_owner)[c] = assigned[c];
+      else (*clique_owner)[c] = (*clique_owner)[S.parent[c]];
+    }
   }
   factor_owner->assign(total, 0);
   for (int64_t pos = 0; pos < total; pos++) {
@@ -703,9 +745,9 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   UP(upload(&p->d_var_type, p->var_type, st));
   UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
   // ---- storage plan: fused leaf cliques keep only their f x n conditional; sharding -----
-  std::vector<char> fused;
+  std::vector<char> fused, is_top;
   std::vector<int> clique_owner, factor_owner;
-  shard_plan(S, d->ngroups, total, ctx->world, &fused, &clique_owner, &factor_owner);
+  shard_plan(S, d->ngroups, total, ctx->world, &fused, &is_top, &clique_owner, &factor_owner);
   const int rank = ctx->rank;
   std::vector<int> fused_list;   // the fused leaf cliques THIS rank owns
   for (int64_t c = 0; c < S.ncliques; c++)
@@ -789,8 +831,13 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   p->h_ld.assign(S.ncliques, 0);
   {
     int64_t o = 0;
-    for (int64_t c = 0; c < S.ncliques; c++)
-      if (!fused[c]) { const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = (int)nn; o += nn * nn; }
+    for (int pass = 0; pass < 2; pass++) {   // replicated top first: it is the all-reduced region
+      for (int64_t c = 0; c < S.ncliques; c++)
+        if (!fused[c] && (is_top[c] != 0) == (pass == 0)) {
+          const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = (int)nn; o += nn * nn;
+        }
+      if (pass == 0) p->top_doubles = o;
+    }
     p->zero_doubles = o;   // everything below is accumulated into by atomics: zeroed per solve
     for (int64_t c = 0; c < S.ncliques; c++)
       if (fused[c]) { const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = S.nf[c]; o += (int64_t)S.nf[c] * nn; }
@@ -849,7 +896,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     const int c = S.var_clique[v];
     const int64_t nn = S.nf[c] + S.ns[c] + 1;
     for (int k = 0; k < var_dim[v]; k++)
-      diag_index[var_dof[v] + k] = fused[c] ? -1 : p->h_off[c] + (S.var_slot[v] + k) * (nn + 1);
+      diag_index[var_dof[v] + k] = (fused[c] || (is_top[c] ? rank != 0 : clique_owner[c] != rank))
+                                       ? -1 : p->h_off[c] + (S.var_slot[v] + k) * (nn + 1);
   }
   UP(upload(&p->d_diag_index, diag_index, st));
   // fused leaf cliques: CSR of their factors as (group, index), graph order
@@ -875,11 +923,16 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     UP(upload(&p->d_fused_fac, ffac, st));
   }
   // ---- level plans: small (one warp per clique) / large (blocked) ----
+  // phase 0: the subtrees this rank owns, leaves to subtree roots; phase 1: the replicated top.
+  // p->levels = [phase-0 levels ..., phase-1 levels ...]; elimination walks it forwards (with the
+  // all-reduce of the top fronts between the phases), back-substitution walks it backwards.
   std::vector<int> small, large, bsmall;
-  p->levels.resize(S.nlevels);
+  p->levels.resize(2 * S.nlevels);
+  p->n_sub_levels = (int)S.nlevels;
   p->max_small_n = 1;
+  for (int phase = 0; phase < 2; phase++)
   for (int64_t l = 0; l < S.nlevels; l++) {
-    LevelPlan& L = p->levels[l];
+    LevelPlan& L = p->levels[phase * S.nlevels + l];
     L = LevelPlan();
     L.small_begin = (int)small.size();
     L.large_begin = (int)large.size();
@@ -887,9 +940,10 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
+      if (phase == 0 ? (is_top[c] || clique_owner[c] != rank) : !is_top[c]) continue;
       if (fused[c]) {
-        // eliminated by leaf_fused_kernel on the owning rank; back-substituted one warp per clique
-        if (clique_owner[c] == rank) bsmall.push_back(c);
+        // eliminated by the leaf kernels; back-substituted one warp per clique
+        bsmall.push_back(c);
       } else if (nn <= kSmallMaxN) {
         small.push_back(c);
         bsmall.push_back(c);
@@ -1149,23 +1203,23 @@ int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level) {
 }
 
 /* Host-only: the sharding plan problem creation uses at `world` ranks.
- * clique_owner[c] = owning rank of a fused leaf clique, -1 for the replicated top;
+ * clique_owner[c] = owning rank of a clique, -1 for the replicated top;
  * factor_owner[pos] = rank that linearizes the factor at graph position pos. */
 int b200_shard_plan(const b200_problem_desc* d, int world, int32_t* clique_owner, int32_t* factor_owner) {
   if (world < 1) { set_error("world < 1"); return B200_INVALID_ARGUMENT; }
   Packed pk;
   const int rc = pack_and_symbolic(d, &pk);
   if (rc) return rc;
-  std::vector<char> fused;
+  std::vector<char> fused, is_top;
   std::vector<int> co, fo;
-  shard_plan(pk.sym, d->ngroups, pk.total, world, &fused, &co, &fo);
+  shard_plan(pk.sym, d->ngroups, pk.total, world, &fused, &is_top, &co, &fo);
   for (size_t c = 0; c < co.size(); c++) clique_owner[c] = co[c];
   for (size_t i = 0; i < fo.size(); i++) factor_owner[i] = fo[i];
   return B200_OK;
 }
 
 int b200_shared_front_buffer(b200_problem* p, void** ptr, int64_t* nd) {
-  *ptr = p->d_arena; *nd = p->zero_doubles;   // the replicated top fronts = the all-reduced region
+  *ptr = p->d_arena; *nd = p->top_doubles;   // the replicated top fronts = the all-reduced region
   return B200_OK;
 }
 

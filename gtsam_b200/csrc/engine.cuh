@@ -122,6 +122,8 @@ struct b200_problem {
   int leaf_run_begin[3] = {0, 0, 0}, leaf_run_end[3] = {0, 0, 0};  // run ranges: generic / point DC=6 / point DC=9
   int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr, *d_fused_run_ptr = nullptr;
   int2* d_fused_fac = nullptr;
+  int64_t top_doubles = 0;          // [0, top_doubles) = fronts of the replicated top (all-reduced when sharded)
+  int n_sub_levels = 0;             // levels[0..n_sub_levels) = owned subtrees, the rest = the top
   int64_t arena_doubles = 0, zero_doubles = 0;  // [0, zero_doubles) = non-leaf fronts (memset per solve)
   int64_t *d_ea_ptr = nullptr, *d_didx_ptr = nullptr;
   int *d_ea_map = nullptr, *d_didx = nullptr;

@@ -291,8 +291,9 @@ int b200_get_conditional(b200_problem* prob, int64_t clique, double* out);
 /* Multi-GPU, one process per GPU.  Rank 0 calls b200_nccl_unique_id and
  * ships the 128 bytes to the other ranks (torch.distributed / MPI / a file); every rank then
  * calls b200_ctx_comm_init BEFORE b200_problem_create.  The problem description is the
- * full graph on every rank; each rank keeps the fused leaf cliques (BAL points) it owns and
- * their factors, the top of the tree is replicated.  Per solve there is ONE exchange step:
+ * full graph on every rank; the junction tree is cut into a replicated top and subtrees
+ * (BAL: the points; nested dissection: the ND branches); each rank keeps the subtrees it owns
+ * and their factors.  Per solve there is ONE exchange step:
  * an in-place ncclAllReduce (FP64 sum, NVLink) of the top fronts, plus a 2-double / 2-int
  * all-reduce of the scalars LM branches on.  b200_get_values returns this rank's view
  * (owned leaf variables + the replicated top variables are current). */
