@@ -52,9 +52,10 @@ def workload_config(prob, args):
         "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
         "cache": "working set (fronts + Jacobians) exceeds the 126 MB L2; no explicit flush",
         "parallelism": "single GPU" if args.gpus == 1 else
-        f"{args.gpus} ranks, one per GPU: points (leaf cliques) + their factors sharded by rank, camera top replicated, "
-        f"one in-place NCCL all-reduce of the top fronts per solve; weak scaling: the graph has {args.gpus}x the points of "
-        f"the 1-GPU workload and `value` counts 1-GPU-sized units (iterations/s x {args.gpus})",
+        f"{args.gpus} ranks, one per GPU: junction-tree subtrees (BAL: points) + their factors sharded by rank, top of the tree "
+        f"replicated, one in-place NCCL all-reduce of the top fronts per solve; BAL workloads scale weakly: the graph has "
+        f"{args.gpus}x the points of the 1-GPU workload and `value` counts 1-GPU-sized units (iterations/s x {args.gpus}); "
+        f"other workloads: the same graph sharded (strong scaling, value = iterations/s)",
     }
 
 
@@ -189,10 +190,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     over = {}
-    if world > 1:   # weak scaling: per-GPU points fixed, cameras fixed
+    weak = False
+    if world > 1:   # weak scaling: per-GPU points fixed, cameras fixed (BAL); other workloads: strong scaling
         base = datasets.WORKLOADS[args.workload][1]
         if "npoints" in base:
             over["npoints"] = base["npoints"] * world
+            weak = True
     prob = datasets.make(args.workload, **over)
     ctx = capi.Context(local)
     if world > 1:
@@ -261,8 +264,9 @@ def main():
 
     if rank != 0:
         return
-    value = world * args.steps / (ms * 1e-3)
-    e2e = world * args.steps / (ms_e2e * 1e-3)
+    units = world if weak else 1      # weak scaling: each iteration processes `world` 1-GPU-sized graphs
+    value = units * args.steps / (ms * 1e-3)
+    e2e = units * args.steps / (ms_e2e * 1e-3)
     info = dev.symbolic_info()
     peak, peak_src = measured_peaks()
     per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in prof.items()}
@@ -309,7 +313,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(prob, args),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_values.nbytes),
                 "d2h_bytes_per_step": int(host_values.nbytes) + 64, "ms_per_step": ms_e2e / args.steps},
