@@ -1000,6 +1000,12 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
   const double* M = t.arena + t.off[c];
   const int* di = t.didx + t.didx_ptr[c];
   double* x = xs[warp];
+  // small triangular block staged up front (f <= 8: every BAL point): the solve below then has no
+  // dependent global load on its critical path
+  __shared__ double Rst[kWarpsPerBlock][64];
+  const bool staged = f <= 8;
+  if (staged)
+    for (int e = lane; e < f * f; e += 32) Rst[warp][e] = M[(e % f) + (size_t)(e / f) * ld];
   // rhs = d - S x_S with the lanes spread over the separator columns (coalesced: the f entries of a
   // column are contiguous and consecutive columns are adjacent), 8 rows at a time, warp-reduced
   for (int i0 = 0; i0 < f; i0 += 8) {
@@ -1021,10 +1027,10 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
   }
   __syncwarp();
   for (int i = f - 1; i >= 0; i--) {
-    if (lane == 0) x[i] = x[i] / M[i + (size_t)i * ld];
+    if (lane == 0) x[i] = x[i] / (staged ? Rst[warp][i + i * f] : M[i + (size_t)i * ld]);
     __syncwarp();
     const double xi = x[i];
-    for (int k = lane; k < i; k += 32) x[k] -= M[k + (size_t)i * ld] * xi;
+    for (int k = lane; k < i; k += 32) x[k] -= (staged ? Rst[warp][k + i * f] : M[k + (size_t)i * ld]) * xi;
     __syncwarp();
   }
   bool nan = false;
