@@ -13,6 +13,7 @@
  */
 #include "problem_io.hpp"
 #include <gtsam/slam/dataset.h>
+#include <gtsam/geometry/Pose2.h>
 #include <gtsam/sfm/SfmData.h>
 #include <gtsam/inference/Symbol.h>
 
@@ -383,6 +384,27 @@ static int cmd_g2ofile(const std::string& path, const std::string& outp) {
   return 0;
 }
 
+/* BASELINE.json configs[0]: Pose2SLAMExample_g2o on a small g2o file, CPU only (plumbing proof that
+ * the reference built by oracle/Makefile runs its own example path).  Mirrors
+ * examples/Pose2SLAMExample_g2o.cpp:46-84 with GaussNewton (as shipped) and with
+ * LevenbergMarquardt (as configs[0] names it); prints one JSON line. */
+static int cmd_pose2(const std::string& path) {
+  auto [graph, initial] = readG2o(path, false);
+  auto priorModel = noiseModel::Diagonal::Variances(Vector3(1e-6, 1e-6, 1e-8));
+  graph->addPrior(0, Pose2(), priorModel);
+  const double e0 = graph->error(*initial);
+  GaussNewtonParams gp;
+  GaussNewtonOptimizer gn(*graph, *initial, gp);
+  Values rg = gn.optimize();
+  LevenbergMarquardtOptimizer lm(*graph, *initial);
+  Values rl = lm.optimize();
+  printf("{\"file\": \"%s\", \"variables\": %zu, \"factors\": %zu, \"initial_error\": %.12g, "
+         "\"gn_final_error\": %.12g, \"gn_iterations\": %d, \"lm_final_error\": %.12g, \"lm_iterations\": %d}\n",
+         path.substr(path.find_last_of('/') + 1).c_str(), initial->size(), graph->size(), e0, graph->error(rg),
+         (int)gn.iterations(), graph->error(rl), (int)lm.iterations());
+  return 0;
+}
+
 /* known-answer vectors for the geometry primitives, incl. near-0 / near-pi */
 static int cmd_kat(const std::string& outp) {
   std::mt19937 rng(123);
@@ -436,6 +458,7 @@ int main(int argc, char** argv) {
   if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));
   if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);
   if (cmd == "kat" && argc >= 3) return cmd_kat(argv[2]);
+  if (cmd == "pose2" && argc >= 3) return cmd_pose2(argv[2]);
   if (cmd == "g2ofile" && argc >= 4) return cmd_g2ofile(argv[2], argv[3]);
   if (cmd == "balfile" && argc >= 4) return cmd_balfile(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 0);
   fprintf(stderr, "bad arguments\n");

@@ -92,6 +92,9 @@ def main():
     p3 = os.path.join(HERE, "pose3example.prob.bin")
     subprocess.check_call([H, "g2ofile", os.path.join(REF_DATA, "pose3example.txt"), p3])
     emit("pose3example", Pm.Problem.load(p3), lm_iters=10, gn_iters=5)
+    # BASELINE.json configs[0] (CPU plumbing): the reference's Pose2 g2o example path
+    with open(os.path.join(HERE, "config1_pose2slam_g2o.json"), "w") as f:
+        f.write(subprocess.check_output([H, "pose2", os.path.join(REF_DATA, "noisyToyGraph.txt")]).decode())
     # the reference's own end-to-end golden: tests/testGeneralSFMFactorB.cpp:44-63 (0.0199833 +- 1e-5)
     from gtsam_b200.problem import Problem
     with tempfile.TemporaryDirectory() as td:

@@ -161,3 +161,15 @@ def test_cheirality_semantics():
     op = O.OracleProblem(prob)
     op.linearize()
     assert np.all(op.get_jacobians(0) == 0) and op.error() == 0.0
+
+
+def test_config1_reference_plumbing_record():
+    """BASELINE.json configs[0]: Pose2SLAMExample_g2o on noisyToyGraph.txt with the reference built
+    by oracle/Makefile (CPU, no GPU): the recorded run (tests/golden/config1_pose2slam_g2o.json,
+    `ref_harness pose2`) reproduces BASELINE.md §2: 0.391637509949 -> 0.0685034664998 in 3 GN iterations."""
+    import json
+    import os
+    rec = json.load(open(os.path.join(util.GOLDEN, "config1_pose2slam_g2o.json")))
+    assert abs(rec["initial_error"] - 0.391637509949) < 1e-11
+    assert abs(rec["gn_final_error"] - 0.0685034664998) < 1e-11 and rec["gn_iterations"] == 3
+    assert abs(rec["lm_final_error"] - rec["gn_final_error"]) < 1e-6
