@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_synchronize", "b200_profile_enable", "b200_profile_phase_count", "b200_profile_phase_name",
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
-    "b200_shard_plan",
+    "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state",
 ]
 
 
@@ -91,6 +91,10 @@ def lib():
         L.b200_lm_get_state.argtypes = [vp, C.POINTER(P.CLMState)]
         L.b200_lm_reset.argtypes = [vp]
         L.b200_gn_iterate.argtypes = [vp, dp]
+        L.b200_dl_create.argtypes = [vp, C.c_double, C.POINTER(vp)]
+        L.b200_dl_destroy.argtypes = [vp]
+        L.b200_dl_iterate.argtypes = [vp]
+        L.b200_dl_get_state.argtypes = [vp, dp, dp, C.POINTER(C.c_int32)]
         L.b200_symbolic_info_get.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
         L.b200_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_get_conditional.argtypes = [vp, C.c_int64, dp]

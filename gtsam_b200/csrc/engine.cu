@@ -308,7 +308,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
     DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
-                                                                 &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1)));
+                                                                 &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0)));
     ctx->launches += 1;
     first = false;
   }
@@ -1377,6 +1377,145 @@ int b200_gn_iterate(b200_problem* p, double* new_error) {
   if (rc) { set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
   b200_accept_step(p);
   if (new_error) *new_error = p->h_scalars->new_error;
+  return B200_OK;
+}
+
+// ---- Dogleg ------------------------------------------------------------------------------
+int b200_dl_destroy(b200_dl* dl);
+int b200_dl_create(b200_problem* p, double delta_initial, b200_dl** out) {
+  // the sharded solve leaves each rank with its own slice of delta; Dogleg's global dot products
+  // over dx_u / dx_n are not wired for that layout
+  if (p->ctx->world > 1) { set_error("Dogleg is single-GPU: create the problem on a context without a communicator"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  b200_dl* dl = new b200_dl;
+  dl->prob = p;
+  dl->delta = delta_initial;
+  dl->iterations = 0;
+  B200_CUDA(cudaMalloc((void**)&dl->d_grad, (size_t)std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&dl->d_dxn, (size_t)std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  int rc = b200_error(p, &dl->error);
+  if (rc) { b200_dl_destroy(dl); return rc; }
+  *out = dl;
+  return B200_OK;
+}
+int b200_dl_destroy(b200_dl* dl) {
+  if (!dl) return B200_OK;
+  cudaFree(dl->d_grad); cudaFree(dl->d_dxn);
+  delete dl;
+  return B200_OK;
+}
+int b200_dl_get_state(const b200_dl* dl, double* error, double* delta, int32_t* iterations) {
+  if (error) *error = dl->error;
+  if (delta) *delta = dl->delta;
+  if (iterations) *iterations = dl->iterations;
+  return B200_OK;
+}
+
+// 0.5*|A x - bscale*b|^2 into *out
+static int enqueue_linerr_of(b200_problem* p, const double* x, double bscale, double* out) {
+  b200_ctx* ctx = p->ctx;
+  cudaStream_t st = ctx->stream;
+  bool first = true;
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
+    double* p0 = p->d_partials;
+    double* p1 = p->d_partials + p->partial_cap / 2;
+    DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), x, p->d_var_dof, p0, p1, p->d_counters + 1,
+                                    &p->d_scalars->dl_scratch, out, first ? 0 : 1, bscale)));
+    ctx->launches += 1;
+    first = false;
+  }
+  if (first) B200_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_dl_iterate(b200_dl* dl) {
+  b200_problem* p = dl->prob;
+  b200_ctx* ctx = p->ctx;
+  cudaStream_t st = ctx->stream;
+  B200_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = p->ndelta;
+  int rc = enqueue_linearize(p);
+  if (rc) return rc;
+  rc = reset_flags(p);
+  if (rc) return rc;
+  rc = set_lambda(p, 0.0);
+  if (rc) return rc;
+  rc = enqueue_solve(p, false, 0, 0, 0);     // d_delta = dx_n, lin_err0 = M(0)
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(dl->d_dxn, p->d_delta, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  // gradientAtZero and |A g|^2
+  B200_CUDA(cudaMemsetAsync(dl->d_grad, 0, (size_t)n * sizeof(double), st));
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
+    DISPATCH_TYPE(g.type, (gradient_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_var_dof, dl->d_grad)));
+    ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  dot3_kernel<<<1, 1024, 0, st>>>(dl->d_grad, dl->d_dxn, n, p->d_scalars->dl_dots);
+  ctx->launches++;
+  rc = enqueue_linerr_of(p, dl->d_grad, 0.0, &p->d_scalars->dl_half_Ag2);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  int64_t fv;
+  rc = solve_status(p, &fv);
+  if (rc) { set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
+  const Scalars* s = p->h_scalars;
+  const double gg = s->dl_dots[0], gn = s->dl_dots[1], nn = s->dl_dots[2];
+  const double step = -gg / (2.0 * s->dl_half_Ag2);          // GaussianFactorGraph.cpp:397-403
+  const double uu = step * step * gg, un = step * gn;
+  const double f_error = dl->error, M_error = s->lin_err0;
+  double delta = dl->delta, new_f = f_error;
+  bool stay = true, zero_step = false;
+  while (stay) {
+    // ComputeDoglegPoint, DoglegOptimizerImpl.cpp:25-78
+    double ca, cb;
+    const double deltaSq = delta * delta;
+    if (deltaSq < uu) { ca = std::sqrt(deltaSq / uu); cb = 0; }
+    else if (deltaSq < nn) {
+      const double a = uu - 2. * un + nn, b = 2. * (un - uu), c = uu - deltaSq;
+      const double sq = std::sqrt(b * b - 4 * a * c);
+      const double tau1 = (-b + sq) / (2. * a), tau2 = (-b - sq) / (2. * a);
+      const double eps = std::numeric_limits<double>::epsilon();
+      const double tau = (-eps <= tau1 && tau1 <= 1.0 + eps) ? tau1 : tau2;
+      ca = 1. - tau; cb = tau;
+    } else { ca = 0; cb = 1; }
+    blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dl->d_grad, dl->d_dxn, ca * step, cb, n, p->d_delta);
+    ctx->launches++;
+    B200_CUDA(cudaGetLastError());
+    rc = enqueue_try_step(p);
+    if (rc) return rc;
+    rc = enqueue_linerr_of(p, p->d_delta, 1.0, &p->d_scalars->lin_err_delta);
+    if (rc) return rc;
+    rc = fetch_scalars(p);
+    if (rc) return rc;
+    new_f = s->new_error;
+    const double new_M = s->lin_err_delta;
+    const double rho = (std::fabs(f_error - new_f) < 1e-15 || std::fabs(M_error - new_M) < 1e-15)
+                           ? 0.5 : (f_error - new_f) / (M_error - new_M);
+    if (rho >= 0.75) {
+      const double nd = std::sqrt(ca * ca * uu + 2. * ca * cb * un + cb * cb * nn);
+      delta = std::max(delta, 3.0 * nd);
+      stay = false;
+    } else if (rho >= 0.25) {
+      stay = false;
+    } else if (rho >= 0.0) {
+      if (delta > 1e-5) delta = 0.5 * delta;
+      stay = false;
+    } else {   // includes NaN
+      if (delta > 1e-5) { delta *= 0.5; stay = true; }
+      else { zero_step = true; new_f = f_error; stay = false; }
+    }
+  }
+  if (!zero_step) b200_accept_step(p);
+  else p->linearized = p->solved = false;
+  dl->error = new_f;
+  dl->delta = delta;
+  dl->iterations++;
   return B200_OK;
 }
 

@@ -60,6 +60,9 @@ struct Scalars {           // device scalars fetched once per LM try
   int fail_code;           // INT_MAX - (min clique id whose partial Cholesky failed); 0 = none
   int nan_code;            // INT_MAX - (min clique id with NaN in back-substitution); 0 = none
   int pad[2];
+  double dl_dots[3];       // Dogleg: g.g, g.dx_n, dx_n.dx_n
+  double dl_half_Ag2;      // Dogleg: 0.5*|A g|^2
+  double dl_scratch;       // second output slot of linerr_kernel when only one is wanted
 };
 
 struct LevelPlan {
@@ -154,6 +157,15 @@ struct b200_problem {
   double phase_ms[16] = {0};
   int64_t phase_calls[16] = {0};
   int max_small_n = 0;
+};
+
+struct b200_dl {
+  b200_problem* prob;
+  double delta;        // trust region radius (DoglegState::delta)
+  double error;
+  int iterations;
+  double* d_grad = nullptr;   // gradientAtZero, then scaled in the blend
+  double* d_dxn = nullptr;    // Newton point
 };
 
 struct b200_lm {

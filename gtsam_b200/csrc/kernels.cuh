@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
 template <int TYPE>
 __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* __restrict__ delta,
                                                      const int* __restrict__ var_dof, double* p0, double* p1,
-                                                     unsigned* counters, double* out0, double* out1, int accumulate) {
+                                                     unsigned* counters, double* out0, double* out1, int accumulate,
+                                                     double bscale) {
+  // bscale = 1: 0.5*|A delta - b|^2; bscale = 0: 0.5*|A delta|^2 (Dogleg's |R g|^2)
   pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* 
     const double* J = g.J + f;
     double e[D], b[D];
 #pragma unroll
-    for (int r = 0; r < D; r++) { b[r] = J[(size_t)(r + (NC - 1) * D) * g.count]; e[r] = -b[r]; }
+    for (int r = 0; r < D; r++) { b[r] = J[(size_t)(r + (NC - 1) * D) * g.count]; e[r] = -bscale * b[r]; }
     const double* d0 = delta + var_dof[k.x];
 #pragma unroll
     for (int cc = 0; cc < N1; cc++) {
@@ -198,6 +200,65 @@ __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* 
   a1 = block_sum<256>(a1, sh);
   finish_sum(a0, p0, counters, out0, accumulate, sh);
   finish_sum(a1, p1, counters + 1, out1, accumulate, sh);
+}
+
+// ---------------------------------------------------------------------------
+// Dogleg support (gtsam/linear/GaussianFactorGraph.cpp:381-407 optimizeGradientSearch,
+// gtsam/nonlinear/DoglegOptimizerImpl.cpp:25-98): gradientAtZero = -A^T b per variable,
+// the three dot products of the steepest-descent and Newton points, and the blend.
+// ---------------------------------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(256) gradient_kernel(GroupView g, const int* __restrict__ var_dof, double* grad) {
+  typedef FactorTraits<TYPE> FT;
+  enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
+    const int2 k = g.keys[f];
+    const double* J = g.J + f;
+    double b[D];
+#pragma unroll
+    for (int r = 0; r < D; r++) b[r] = J[(size_t)(r + (NC - 1) * D) * g.count];
+    double* g0 = grad + var_dof[k.x];
+#pragma unroll
+    for (int cc = 0; cc < N1; cc++) {
+      double s = 0;
+#pragma unroll
+      for (int r = 0; r < D; r++) s += J[(size_t)(r + cc * D) * g.count] * b[r];
+      atomicAdd(g0 + cc, -s);
+    }
+    if (N2 > 0) {
+      double* g1 = grad + var_dof[k.y];
+#pragma unroll
+      for (int cc = 0; cc < N2; cc++) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < D; r++) s += J[(size_t)(r + (N1 + cc) * D) * g.count] * b[r];
+        atomicAdd(g1 + cc, -s);
+      }
+    }
+  }
+}
+
+// out[0..2] = {u.u, u.n, n.n}; one block, fixed summation order
+__global__ void __launch_bounds__(1024) dot3_kernel(const double* __restrict__ u, const double* __restrict__ n, int64_t count,
+                                                    double* out) {
+  __shared__ double sh[32];
+  double a = 0, b = 0, c = 0;
+  for (int64_t i = threadIdx.x; i < count; i += 1024) {
+    const double x = u[i], y = n[i];
+    a += x * x; b += x * y; c += y * y;
+  }
+  a = block_sum<1024>(a, sh);
+  b = block_sum<1024>(b, sh);
+  c = block_sum<1024>(c, sh);
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = c; }
+}
+
+// out = ca*u + cb*n (ComputeBlend); ca == 0 / cb == 0 select the pure points exactly
+__global__ void blend_kernel(const double* __restrict__ u, const double* __restrict__ n, double ca, double cb, int64_t count,
+                             double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[i] = cb == 0.0 ? ca * u[i] : (ca == 0.0 ? cb * n[i] : ca * u[i] + cb * n[i]);
 }
 
 // ---------------------------------------------------------------------------

@@ -3,7 +3,8 @@
 Same names, argument meaning and error behaviour as
 ``gtsam::LevenbergMarquardtParams`` (gtsam/nonlinear/LevenbergMarquardtParams.h:49-141),
 ``gtsam::LevenbergMarquardtOptimizer`` (gtsam/nonlinear/LevenbergMarquardtOptimizer.h:35-120)
-and ``gtsam::GaussNewtonOptimizer`` (gtsam/nonlinear/GaussNewtonOptimizer.h), so the
+``gtsam::GaussNewtonOptimizer`` (gtsam/nonlinear/GaussNewtonOptimizer.h) and
+``gtsam::DoglegOptimizer`` (gtsam/nonlinear/DoglegOptimizer.h:33-128), so the
 parity tests read like the reference's own (tests/testNonlinearOptimizer.cpp).
 All numeric work happens in the C-ABI library on the GPU; this file holds no math.
 The C++ subclass shim a GTSAM user links instead is gtsam_b200/shim/.
@@ -159,3 +160,97 @@ class GaussNewtonOptimizer:
             raise IndeterminantLinearSystemException(-1)
         self.error_ = e
         self.iterations_ += 1
+
+    def optimize(self, params=None):
+        return _default_optimize(self, params or NonlinearOptimizerParams())
+
+
+class NonlinearOptimizerParams:
+    """gtsam::NonlinearOptimizerParams defaults (gtsam/nonlinear/NonlinearOptimizerParams.h:48-53)."""
+
+    def __init__(self):
+        self.maxIterations = 100
+        self.relativeErrorTol = 1e-5
+        self.absoluteErrorTol = 1e-5
+        self.errorTol = 0.0
+        self.iterationHook: Optional[Callable[[int, float, float], None]] = None
+
+
+GaussNewtonParams = NonlinearOptimizerParams
+
+
+def _default_optimize(opt, prm):
+    """NonlinearOptimizer::defaultOptimize(), gtsam/nonlinear/NonlinearOptimizer.cpp:62-117."""
+    currentError = opt.error()
+    if currentError <= prm.errorTol or opt.iterations() >= prm.maxIterations:
+        return opt.values()
+    newError = currentError
+    while True:
+        currentError = newError
+        opt.iterate()
+        newError = opt.error()
+        if prm.iterationHook is not None:
+            prm.iterationHook(opt.iterations(), currentError, newError)
+        if not (opt.iterations() < prm.maxIterations
+                and not checkConvergence(prm.relativeErrorTol, prm.absoluteErrorTol, prm.errorTol, currentError, newError)
+                and currentError == currentError and abs(currentError) != float("inf")):
+            break
+    return opt.values()
+
+
+class DoglegParams(NonlinearOptimizerParams):
+    """gtsam::DoglegParams (gtsam/nonlinear/DoglegOptimizer.h:33-58)."""
+
+    def __init__(self):
+        super().__init__()
+        self.deltaInitial = 1.0
+
+
+class DoglegOptimizer:
+    """Drop-in for gtsam::DoglegOptimizer (gtsam/nonlinear/DoglegOptimizer.cpp:60-121)."""
+
+    def __init__(self, ctx: Context, problem: P.Problem, params: Optional[DoglegParams] = None,
+                 device_problem: Optional[DeviceProblem] = None):
+        self.params_ = params or DoglegParams()
+        self.dp = device_problem or DeviceProblem(ctx, problem)
+        self.L = self.dp.L
+        h = C.c_void_p()
+        _check(self.L.b200_dl_create(self.dp.h, float(self.params_.deltaInitial), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.b200_dl_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _state(self):
+        e, d, it = C.c_double(), C.c_double(), C.c_int32()
+        _check(self.L.b200_dl_get_state(self.h, C.byref(e), C.byref(d), C.byref(it)))
+        return e.value, d.value, it.value
+
+    def error(self) -> float:
+        return self._state()[0]
+
+    def getDelta(self) -> float:
+        return self._state()[1]
+
+    def iterations(self) -> int:
+        return self._state()[2]
+
+    def values(self):
+        return self.dp.get_values()
+
+    def params(self) -> DoglegParams:
+        return self.params_
+
+    def iterate(self):
+        rc = self.L.b200_dl_iterate(self.h)
+        if rc == P.INDETERMINATE:
+            raise IndeterminantLinearSystemException(-1)
+        _check(rc)
+
+    def optimize(self):
+        return _default_optimize(self, self.params_)

@@ -266,6 +266,20 @@ int b200_lm_reset(b200_lm* lm);
 /* GaussNewtonOptimizer::iterate(), gtsam/nonlinear/GaussNewtonOptimizer.cpp:44-67 */
 int b200_gn_iterate(b200_problem* prob, double* new_error);
 
+/* Powell's dogleg.  b200_dl_iterate = DoglegOptimizer::iterate(),
+ * gtsam/nonlinear/DoglegOptimizer.cpp:84-121, with DoglegOptimizerImpl::Iterate in
+ * ONE_STEP_PER_ITERATION mode (gtsam/nonlinear/DoglegOptimizerImpl.h:139-258): linearize,
+ * multifrontal solve for the Newton point dx_n, steepest-descent point dx_u
+ * (GaussianFactorGraph::optimizeGradientSearch, gtsam/linear/GaussianFactorGraph.cpp:381-407),
+ * then the trust-region loop on the dogleg point.  delta_initial is DoglegParams::deltaInitial.
+ * Single-GPU only: B200_INVALID_ARGUMENT on a context with a communicator. */
+typedef struct b200_dl b200_dl;
+int b200_dl_create(b200_problem* prob, double delta_initial, b200_dl** out);
+int b200_dl_destroy(b200_dl* dl);
+int b200_dl_iterate(b200_dl* dl);
+/* error = state error, delta = trust region radius, iterations = iterate() calls so far */
+int b200_dl_get_state(const b200_dl* dl, double* error, double* delta, int32_t* iterations);
+
 /* Symbolic-phase introspection (parity of a11 against the reference's
  * junction tree).  Cliques are numbered in elimination post-order. */
 int b200_symbolic_info_get(const b200_problem* prob, b200_symbolic_info* info);

@@ -1276,6 +1276,103 @@ int orc_gn_iterate(orc_problem* p, double* new_error) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* Dogleg: DoglegOptimizer::iterate, gtsam/nonlinear/DoglegOptimizer.cpp:84-121 with
+ * DoglegOptimizerImpl::Iterate (ONE_STEP_PER_ITERATION), gtsam/nonlinear/DoglegOptimizerImpl.h:139-258,
+ * ComputeDoglegPoint / ComputeBlend, DoglegOptimizerImpl.cpp:25-98, and
+ * GaussianFactorGraph::optimizeGradientSearch, gtsam/linear/GaussianFactorGraph.cpp:381-407.
+ * The Bayes tree and the linear graph encode the same quadratic up to a constant, so gradient,
+ * |R g|^2 = |A g|^2 and error differences are evaluated on the Jacobian factors. */
+static double dot_n(const double* a, const double* b, int64_t n) { double s = 0; for (int64_t i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+
+int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io) {
+  const int64_t n = p->dof_off[p->nvars];
+  orc_linearize(p);
+  int64_t fv;
+  double e0 = 0, e1 = 0;
+  const int st = orc_solve(p, 0.0, 0, 0, 0, &e0, &e1, &fv);
+  if (st != B200_OK) return st;
+  double* dxn = (double*)malloc((size_t)n * sizeof(double));
+  double* dxu = (double*)calloc((size_t)n, sizeof(double));
+  double* dxd = (double*)malloc((size_t)n * sizeof(double));
+  memcpy(dxn, p->delta, (size_t)n * sizeof(double));
+  /* gradientAtZero = -A^T b */
+  for (int64_t gi = 0; gi < p->nfactors; gi++) {
+    const ogroup* g = &p->groups[p->fgroup[gi]];
+    const int64_t i = p->fidx[gi];
+    const int d = g->d, ar = F_ARITY[g->type];
+    const double* J = g->J + i * d * g->ncols;
+    int col = 0;
+    for (int a = 0; a < ar; a++) {
+      const int64_t v = g->keys[i * ar + a];
+      for (int c = 0; c < VAR_DIM[p->var_type[v]]; c++, col++) {
+        double s = 0;
+        for (int rr = 0; rr < d; rr++) s += J[rr + col * d] * J[rr + (g->ncols - 1) * d];
+        dxu[p->dof_off[v] + c] -= s;
+      }
+    }
+  }
+  const double gg = dot_n(dxu, dxu, n);
+  /* |A g|^2 */
+  double Ag2 = 0;
+  for (int64_t gi = 0; gi < p->nfactors; gi++) {
+    const ogroup* g = &p->groups[p->fgroup[gi]];
+    const int64_t i = p->fidx[gi];
+    const int d = g->d, ar = F_ARITY[g->type];
+    const double* J = g->J + i * d * g->ncols;
+    double e[9] = {0};
+    int col = 0;
+    for (int a = 0; a < ar; a++) {
+      const int64_t v = g->keys[i * ar + a];
+      for (int c = 0; c < VAR_DIM[p->var_type[v]]; c++, col++)
+        for (int rr = 0; rr < d; rr++) e[rr] += J[rr + col * d] * dxu[p->dof_off[v] + c];
+    }
+    for (int rr = 0; rr < d; rr++) Ag2 += e[rr] * e[rr];
+  }
+  const double step = -gg / Ag2;
+  for (int64_t k = 0; k < n; k++) dxu[k] *= step;
+  const double uu = dot_n(dxu, dxu, n), un = dot_n(dxu, dxn, n), nn = dot_n(dxn, dxn, n);
+  const double f_error = *error_io, M_error = e0;
+  double delta = *delta_io, new_f = f_error;
+  int stay = 1, zero_step = 0;
+  while (stay) {
+    /* ComputeDoglegPoint */
+    double ca, cb;
+    const double deltaSq = delta * delta;
+    if (deltaSq < uu) { ca = sqrt(deltaSq / uu); cb = 0; }
+    else if (deltaSq < nn) {
+      const double a = uu - 2. * un + nn, b = 2. * (un - uu), c = uu - delta * delta;
+      const double sq = sqrt(b * b - 4 * a * c);
+      const double tau1 = (-b + sq) / (2. * a), tau2 = (-b - sq) / (2. * a);
+      const double tau = (-DBL_EPSILON <= tau1 && tau1 <= 1.0 + DBL_EPSILON) ? tau1 : tau2;
+      ca = 1. - tau; cb = tau;
+    } else { ca = 0; cb = 1; }
+    for (int64_t k = 0; k < n; k++) dxd[k] = (cb == 0 ? ca * dxu[k] : (ca == 0 ? dxn[k] : ca * dxu[k] + cb * dxn[k]));
+    memcpy(p->delta, dxd, (size_t)n * sizeof(double));
+    new_f = orc_try_step(p);
+    const double new_M = linear_error(p, dxd);
+    const double rho = (fabs(f_error - new_f) < 1e-15 || fabs(M_error - new_M) < 1e-15) ? 0.5 : (f_error - new_f) / (M_error - new_M);
+    if (rho >= 0.75) {
+      const double nd = sqrt(dot_n(dxd, dxd, n));
+      delta = delta > 3.0 * nd ? delta : 3.0 * nd;
+      stay = 0;
+    } else if (rho >= 0.25) {
+      stay = 0;
+    } else if (rho >= 0.0) {
+      if (delta > 1e-5) delta = 0.5 * delta;
+      stay = 0;   /* ONE_STEP_PER_ITERATION */
+    } else {
+      if (delta > 1e-5) { delta *= 0.5; stay = 1; }
+      else { zero_step = 1; new_f = f_error; stay = 0; }
+    }
+  }
+  if (!zero_step) orc_accept_step(p);
+  *error_io = new_f;
+  *delta_io = delta;
+  free(dxn); free(dxu); free(dxd);
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------------------ */
 void orc_symbolic_info_get(const orc_problem* p, b200_symbolic_info* info) {
   memset(info, 0, sizeof *info);
   info->ncliques = p->ncliques;

@@ -67,6 +67,8 @@ void orc_lm_init(orc_lm* lm, orc_problem* p, const b200_lm_params* params);
 int orc_lm_iterate(orc_lm* lm);
 int orc_lm_optimize(orc_lm* lm);
 int orc_gn_iterate(orc_problem* p, double* new_error);
+/* DoglegOptimizer::iterate; error_io = state error, delta_io = trust region radius */
+int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io);
 
 /* symbolic introspection */
 void orc_symbolic_info_get(const orc_problem* p, b200_symbolic_info* info);

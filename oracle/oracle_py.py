@@ -50,6 +50,7 @@ def lib():
         L.orc_try_step.restype = C.c_double
         L.orc_accept_step.argtypes = [C.c_void_p]
         L.orc_gn_iterate.argtypes = [C.c_void_p, dp]
+        L.orc_dogleg_iterate.argtypes = [C.c_void_p, dp, dp]
         L.orc_symbolic_info_get.argtypes = [C.c_void_p, C.POINTER(P.CSymbolicInfo)]
         L.orc_get_cliques.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.orc_get_conditional.argtypes = [C.c_void_p, C.c_int64, dp]
@@ -166,6 +167,11 @@ class OracleProblem:
         e = C.c_double()
         st = self.L.orc_gn_iterate(self.h, C.byref(e))
         return st, e.value
+
+    def dogleg_iterate(self, error, delta):
+        e, d = C.c_double(error), C.c_double(delta)
+        st = self.L.orc_dogleg_iterate(self.h, C.byref(e), C.byref(d))
+        return st, e.value, d.value
 
     def symbolic_info(self):
         info = P.CSymbolicInfo()

@@ -12,6 +12,7 @@
  * Variable id i <-> gtsam::Key i (plain integers), so Key order == id order.
  */
 #include "problem_io.hpp"
+#include <gtsam/nonlinear/DoglegOptimizer.h>
 #include <gtsam/slam/dataset.h>
 #include <gtsam/geometry/Pose2.h>
 #include <gtsam/sfm/SfmData.h>
@@ -197,6 +198,22 @@ static int cmd_gn(const std::string& in, const std::string& outp, int iters) {
   for (int i = 0; i < iters; i++) { gn.iterate(); errs.push_back(gn.error()); }
   out.put("gn_errors", errs);
   out.put("final_values", pack_values(p, b, gn.values()));
+  return 0;
+}
+
+static int cmd_dogleg(const std::string& in, const std::string& outp, int iters, double delta0) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  DoglegParams params;
+  params.ordering = b.ordering;
+  params.deltaInitial = delta0;
+  DoglegOptimizer dl(b.graph, b.values, params);
+  std::vector<double> errs{dl.error()}, deltas{dl.getDelta()};
+  for (int i = 0; i < iters; i++) { dl.iterate(); errs.push_back(dl.error()); deltas.push_back(dl.getDelta()); }
+  out.put("dl_errors", errs);
+  out.put("dl_deltas", deltas);
+  out.put("final_values", pack_values(p, b, dl.values()));
   return 0;
 }
 
@@ -454,6 +471,7 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "dump" && argc >= 4) return cmd_dump(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0, argc > 5 && atoi(argv[5]));
   if (cmd == "lm" && argc >= 4) return cmd_lm(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 100, argc > 5 && atoi(argv[5]));
+  if (cmd == "dogleg" && argc >= 4) return cmd_dogleg(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 5, argc > 5 ? atof(argv[5]) : 1.0);
   if (cmd == "gn" && argc >= 4) return cmd_gn(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 3);
   if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));
   if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);

@@ -8,7 +8,7 @@ The fixtures pin the C oracle (tests/test_oracle_golden.py) and the CUDA path
 (tests/test_gpu_parity.py).  Each case stores the problem (*.prob.bin, the
 gtsam_b200.problem.Problem.save format) and the reference's outputs
 (*.dump0.bin: lambda=0; *.dump1.bin: lambda=1e-2 with diagonal damping;
-*.lm.bin: LevenbergMarquardtOptimizer trace; *.gn.bin: GaussNewton trace).
+*.lm.bin: LevenbergMarquardtOptimizer trace; *.gn.bin: GaussNewton trace; *.dl.bin: DoglegOptimizer trace).
 """
 import os
 import shutil
@@ -25,7 +25,7 @@ H = refio.HARNESS
 REF_DATA = "/root/reference/examples/Data"
 
 
-def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False):
+def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False, dl_iters=0):
     ppath = os.path.join(HERE, f"{name}.prob.bin")
     prob.save(ppath)
     subprocess.check_call([H, "dump", ppath, os.path.join(HERE, f"{name}.dump0.bin"), "0", "0"])
@@ -33,6 +33,8 @@ def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False):
     subprocess.check_call([H, "lm", ppath, os.path.join(HERE, f"{name}.lm.bin"), str(lm_iters), str(int(ceres))])
     if gn_iters:
         subprocess.check_call([H, "gn", ppath, os.path.join(HERE, f"{name}.gn.bin"), str(gn_iters)])
+    if dl_iters:   # DoglegOptimizer trace, deltaInitial = 1
+        subprocess.check_call([H, "dogleg", ppath, os.path.join(HERE, f"{name}.dl.bin"), str(dl_iters), "1.0"])
     print("wrote", name, prob.nvars, "vars", prob.nfactors, "factors")
 
 
@@ -45,13 +47,13 @@ def with_ordering(prob, kind):
 def main():
     assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
     subprocess.check_call([H, "kat", os.path.join(HERE, "geometry_kat.bin")])
-    emit("bal_tiny_s2", datasets.make("bal_tiny"))
+    emit("bal_tiny_s2", datasets.make("bal_tiny"), dl_iters=5)
     emit("bal_tiny_body_sensor", datasets.make("bal_tiny", seed=13, body_sensor=True))
     emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True)
     emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"))
-    emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3)
-    emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3)
-    emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2)
+    emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3, dl_iters=8)
+    emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3, dl_iters=8)
+    emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2, dl_iters=6)
     from gtsam_b200 import problem as Pq
     import numpy as np
     emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2)

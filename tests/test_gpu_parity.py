@@ -51,6 +51,34 @@ def test_cuda_reference_end_to_end_golden(gpu_ctx):
     assert abs(lm.error() - 0.0199833) < 1e-5
 
 
+@pytest.mark.parametrize("case", ["bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian"])
+def test_cuda_dogleg_trace(gpu_ctx, case):
+    """DoglegOptimizer trace (errors + trust-region radii) against the reference's, deltaInitial = 1."""
+    prob = util.load_case(case)
+    ref = util.golden(case, "dl")
+    dl = optimizer.DoglegOptimizer(gpu_ctx, prob)
+    errs, deltas = [dl.error()], [dl.getDelta()]
+    for _ in range(len(ref["dl_errors"]) - 1):
+        dl.iterate()
+        errs.append(dl.error())
+        deltas.append(dl.getDelta())
+    assert np.allclose(errs, ref["dl_errors"], rtol=1e-8)
+    assert np.allclose(deltas, ref["dl_deltas"], rtol=1e-7)
+    assert util.relmax(dl.values(), ref["final_values"]) <= 1e-6
+
+
+def test_cuda_dogleg_optimize_mid_size(gpu_ctx):
+    """Dogleg on a mid-size BAL problem converges to the LM optimum (size-independent property)."""
+    from gtsam_b200 import datasets
+    prob = datasets.bal(ncams=23, npoints=4000, seed=2)
+    lm = optimizer.LevenbergMarquardtOptimizer(gpu_ctx, prob)
+    lm.optimize()
+    dl = optimizer.DoglegOptimizer(gpu_ctx, prob)
+    e0 = dl.error()
+    dl.optimize()
+    assert dl.error() < e0 and abs(dl.error() - lm.error()) <= 1e-3 * max(1.0, lm.error())
+
+
 @pytest.mark.parametrize("case", ["sphere_tiny", "sphere_small_colamd"])
 def test_cuda_gn_trace(gpu_ctx, case):
     prob = util.load_case(case)

@@ -65,6 +65,27 @@ def test_oracle_gn_trace(case):
     assert np.allclose(errs, ref["gn_errors"], rtol=1e-8)
 
 
+DL_CASES = ["bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian"]
+
+
+@pytest.mark.parametrize("case", DL_CASES)
+def test_oracle_dogleg_trace(case):
+    """DoglegOptimizer::iterate trace of the reference (errors and trust-region radii, deltaInitial = 1)."""
+    prob = util.load_case(case)
+    ref = util.golden(case, "dl")
+    op = O.OracleProblem(prob)
+    e, d = op.error(), 1.0
+    errs, deltas = [e], [d]
+    for _ in range(len(ref["dl_errors"]) - 1):
+        st, e, d = op.dogleg_iterate(e, d)
+        assert st == 0
+        errs.append(e)
+        deltas.append(d)
+    assert np.allclose(errs, ref["dl_errors"], rtol=1e-8)
+    assert np.allclose(deltas, ref["dl_deltas"], rtol=1e-7)
+    assert util.relmax(op.get_values(), ref["final_values"]) <= 1e-6
+
+
 def test_geometry_known_answers():
     """Pose3/Rot3 Expmap, Logmap, AdjointMap, inverse, compose against the reference,
     including the near-zero and near-pi branches (gtsam/geometry/SO3.cpp:264-319)."""
