@@ -246,6 +246,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (L.large_count) {
       PhaseScope ps(p, PH_ELIM_LARGE);
       const int* list = p->d_lvl_large + L.large_begin;
+      const int fuse = p->fuse_ea ? 1 : 0;          // last update of a front extend-adds straight into the parent
       const bool big = L.large_max_n >= p->big_min_n;   // big fronts: one K=128 trailing update per 128 columns
       auto tiles = [](int rows, int cols, int T) {   // upper-trapezoid tile count
         const int TR = (rows + T - 1) / T, TC = (cols + T - 1) / T;
@@ -259,24 +260,26 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
           launch_k(panel_kernel, dim3(dim3(std::max(1, (ncol + kTrsmCols - 1) / kTrsmCols), L.large_count)), dim3(kTrsmCols), 0, st, 
               t, list, k0, p->d_scalars, p->d_rdiag);
           if (!big) {
-            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(ncol, ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 0, K0, k0, p->d_rdiag);
+            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(ncol, ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 0, K0, k0, p->d_rdiag, fuse);
           } else {
             const int rows = std::min(K0 + kBig, L.large_max_nf) - k0 - 1;
-            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 1, K0, k0, p->d_rdiag);
+            launch_k(update_kernel<64, 4, 32>, dim3(dim3(tiles(std::max(rows, 1), ncol, 64), L.large_count)), dim3(256), 0, st, t, list, 1, K0, k0, p->d_rdiag, fuse);
           }
           ctx->launches += 2;
         }
         if (big) {
           const int m = L.large_max_n - K0 - 1;
-          if (p->use_dmma) launch_k(update_dmma_kernel, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, K0);
-          else launch_k(update_kernel<128, 8, 16>, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, 2, K0, 0, p->d_rdiag);
+          if (p->use_dmma) launch_k(update_dmma_kernel, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, K0, fuse);
+          else launch_k(update_kernel<128, 8, 16>, dim3(dim3(tiles(m, m, 128), L.large_count)), dim3(256), 0, st, t, list, 2, K0, 0, p->d_rdiag, fuse);
           ctx->launches++;
         }
       }
-      const int64_t w = L.large_max_ns + 1;
-      const int gx = (int)std::min<int64_t>((w * w + 255) / 256, 4096);
-      launch_k(extend_add_kernel, dim3(dim3(gx, L.large_count)), dim3(256), 0, st, t, list);
-      ctx->launches++;
+      if (!fuse) {
+        const int64_t w = L.large_max_ns + 1;
+        const int gx = (int)std::min<int64_t>((w * w + 255) / 256, 4096);
+        launch_k(extend_add_kernel, dim3(dim3(gx, L.large_count)), dim3(256), 0, st, t, list);
+        ctx->launches++;
+      }
     }
   }
   // ---- back-substitution, roots to leaves ----
@@ -827,6 +830,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   p->n_fused = (int)fused_list.size();
   p->big_min_n = getenv("B200_BIG_MIN_N") ? atoi(getenv("B200_BIG_MIN_N")) : 1024;
   p->use_dmma = getenv("B200_NO_DMMA") == nullptr;
+  p->fuse_ea = getenv("B200_NO_FUSE_EA") == nullptr;
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
   {

@@ -140,6 +140,7 @@ struct b200_problem {
   cudaGraphExec_t try_graph[2] = {nullptr, nullptr};  // LM try (solve + retract + error), by diagonal flag
   double graph_min_diag = 0, graph_max_diag = 0;
   int64_t try_launches = 0;
+  bool fuse_ea = true;              // fold extend_add_kernel into each front's last update
   double* d_rdiag = nullptr;        // factored diagonal blocks published by panel_kernel
   double* d_partials = nullptr;     // block partial sums
   unsigned* d_counters = nullptr;   // tickets of the last-block reductions

@@ -883,7 +883,7 @@ constexpr int kBig = 128;
 
 template <int TILE, int RB, int kKC>
 __global__ void __launch_bounds__(256)
-update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0, const double* __restrict__ rdiag) {
+update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0, const double* __restrict__ rdiag, int fuse_ea) {
   pdl_sync();
   __shared__ double Pi[kKC][TILE + 1];
   __shared__ double Pj[kKC][TILE + 1];
@@ -944,6 +944,28 @@ update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0
     }
     __syncthreads();
   }
+  // The front's LAST update (its pivots end at pb) leaves the finished Schur complement: instead of
+  // storing it and re-reading it in a separate extend-add launch, add it straight into the parent
+  // (HessianFactor::updateHessian of the child factor, gtsam/linear/HessianFactor.cpp:348-374).
+  const int par = t.parent[c];
+  const bool to_parent = fuse_ea && mode != 1 && pb == f && par >= 0;
+  if (to_parent) {
+    double* P = t.arena + t.off[par];
+    const int pn = t.nf[par] + t.ns[par] + 1;
+    const int* map = t.ea_map + t.ea_ptr[c];
+#pragma unroll
+    for (int b = 0; b < RB; b++)
+#pragma unroll
+      for (int a = 0; a < RB; a++) {
+        const int gi = i0 + tx + 16 * a, gj = j0 + ty + 16 * b;
+        if (gi < ib && gj < n && gi <= gj) {
+          const int pi = map[gi - f], pj = map[gj - f];
+          const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+          atomicAdd(P + lo + (size_t)hi * pn, M[gi + (size_t)gj * n] - acc[a][b]);
+        }
+      }
+    return;
+  }
 #pragma unroll
   for (int b = 0; b < RB; b++)
 #pragma unroll
@@ -966,7 +988,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 }
 
 __global__ void __launch_bounds__(256)
-update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0) {
+update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0, int fuse_ea) {
   constexpr int TILE = 128, KC = 16;
   __shared__ double Pi[KC][TILE + 4];
   __shared__ double Pj[KC][TILE + 4];
@@ -1013,6 +1035,26 @@ update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0) {
         for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
     __syncthreads();
+  }
+  const int par = t.parent[c];
+  if (fuse_ea && pb == f && par >= 0) {   // last update of the front: extend-add into the parent (see update_kernel)
+    double* P = t.arena + t.off[par];
+    const int pn = t.nf[par] + t.ns[par] + 1;
+    const int* map = t.ea_map + t.ea_ptr[c];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int gi = i0 + wi + 8 * a + g, gj = j0 + wj + 8 * b + 2 * q + h;
+          if (gi < n && gj < n && gi <= gj) {
+            const int pi = map[gi - f], pj = map[gj - f];
+            const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+            atomicAdd(P + lo + (size_t)hi * pn, M[gi + (size_t)gj * n] - acc[a][b][h]);
+          }
+        }
+    return;
   }
 #pragma unroll
   for (int a = 0; a < 8; a++)
