@@ -206,7 +206,9 @@ def main():
     lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, device_problem=dev)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     L = dev.L
-    host_values = prob.values.copy()
+    # the step's host buffers are page-locked (contract: inputs come from pinned host memory)
+    host_values = torch.from_numpy(prob.values.copy()).pin_memory().numpy()
+    host_out = torch.empty(host_values.size, dtype=torch.float64).pin_memory().numpy()
     dev.save_values()
 
     def step_resident():
@@ -215,10 +217,10 @@ def main():
         lm.iterate()
 
     def step_e2e():
-        dev.set_values(host_values)             # host -> pinned -> device
+        dev.set_values(host_values)             # pinned host -> device
         capi._check(L.b200_lm_reset(lm.h))
         lm.iterate()
-        out = dev.get_values()                  # device -> host
+        out = dev.get_values(host_out)          # device -> pinned host
         return out, lm.error()
 
     def barrier():

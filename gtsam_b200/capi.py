@@ -235,8 +235,11 @@ class DeviceProblem:
         assert v.size == self.nval
         _check(self.L.b200_set_values(self.h, _dp(v)))
 
-    def get_values(self):
-        out = np.zeros(self.nval)
+    def get_values(self, out=None):
+        """Packed values; pass a page-locked float64 array as ``out`` for a direct D2H copy."""
+        if out is None:
+            out = np.empty(self.nval)
+        assert out.dtype == np.float64 and out.size == self.nval and out.flags.c_contiguous
         _check(self.L.b200_get_values(self.h, _dp(out)))
         return out
 

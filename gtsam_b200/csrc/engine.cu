@@ -208,21 +208,30 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
                                                            p->d_scalars, p->leaf_lb_cap, 0);
       ctx->launches++;
     }
-    if (p->leaf_run_end[1] > p->leaf_run_begin[1]) {
-      const int nr = p->leaf_run_end[1] - p->leaf_run_begin[1], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 6 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
-      launch_k(leaf_point_kernel<6>, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[1], nr,
-                                                              p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
-                                                              p->d_scalars, p->leaf_acc_cap);
-      ctx->launches++;
-    }
-    if (p->leaf_run_end[2] > p->leaf_run_begin[2]) {
-      const int nr = p->leaf_run_end[2] - p->leaf_run_begin[2], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      const size_t sm = (size_t)kWarpsPerBlock * (kPtMaxObs * (5 * 9 + 2) + 8 + p->leaf_acc_cap) * sizeof(double);
-      launch_k(leaf_point_kernel<9>, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[2], nr,
-                                                              p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
-                                                              p->d_scalars, p->leaf_acc_cap);
-      ctx->launches++;
+    // BAL points: per-point factorisation (8 lanes per point), then one CTA per run for the Schur complement
+    for (int kd = 1; kd <= 2; kd++) {
+      const int nr = p->leaf_run_end[kd] - p->leaf_run_begin[kd];
+      if (nr <= 0) continue;
+      const int i0 = p->leaf_pos_begin[kd], i1 = p->leaf_pos_end[kd];
+      const int nb = (int)(((int64_t)(i1 - i0) * 8 + 127) / 128);
+      const int* runs = p->d_fused_run_ptr + p->leaf_run_begin[kd];
+      // CTA shape of the Schur kernel from the widest separator of the kind: 3x3 tiles over (s+1)^2 / 2
+      const int ntd = (p->leaf_max_w[kd] + 2) / 3, ntiles = ntd * (ntd + 1) / 2;
+      const int thr = ntiles <= 96 ? 96 : 128, tpt = (ntiles + thr - 1) / thr;
+#define B200_LAUNCH_SCHUR(DC_, T_, P_)                                                                                               \
+      if (tpt == T_ && p->schur_pb == P_)                                                                                            \
+        launch_k(leaf_point_schur_kernel<DC_, T_, P_>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs,          \
+                 (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac);
+#define B200_LAUNCH_POINT(DC_)                                                                                                        \
+      launch_k(leaf_point_factor_kernel<DC_>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1,                 \
+               (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
+               p->d_scalars);                                                                                                          \
+      B200_LAUNCH_SCHUR(DC_, 1, 4) B200_LAUNCH_SCHUR(DC_, 2, 4) B200_LAUNCH_SCHUR(DC_, 3, 4)                                          \
+      B200_LAUNCH_SCHUR(DC_, 1, 6) B200_LAUNCH_SCHUR(DC_, 2, 6) B200_LAUNCH_SCHUR(DC_, 3, 6)
+      if (kd == 1) { B200_LAUNCH_POINT(6) } else { B200_LAUNCH_POINT(9) }
+#undef B200_LAUNCH_POINT
+#undef B200_LAUNCH_SCHUR
+      ctx->launches += 2;
     }
   }
   // ---- elimination, leaves to roots ----
@@ -288,16 +297,24 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   PhaseScope ps(p, PH_BACKSUB);
   for (int l = (int)p->levels.size() - 1; l >= 0; l--) {
     const LevelPlan& L = p->levels[l];
-    if (L.large_count) {
-      const int nblk = (L.large_max_nf + kBsRows - 1) / kBsRows;
-      launch_k(backsub_large_kernel, dim3(dim3(nblk, L.large_count)), dim3(256), 0, st, t, p->d_lvl_large + L.large_begin, p->d_delta, p->d_scalars,
-                                                                      p->d_bs_flags, p->d_bs_flag_base, L.large_begin, 1);
+    if (L.blarge_count) {
+      const int nblk = (L.blarge_max_nf + kBsRows - 1) / kBsRows;
+      launch_k(backsub_large_kernel, dim3(dim3(nblk, L.blarge_count)), dim3(256), 0, st, t, p->d_lvl_blarge + L.blarge_begin, p->d_delta, p->d_scalars,
+                                                                      p->d_bs_flags, p->d_bs_flag_base, L.blarge_begin, 1);
       ctx->launches++;
     }
     if (L.bsmall_count) {
       const int nb = (L.bsmall_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
       launch_k(backsub_small_kernel, dim3(nb), dim3(kWarpsPerBlock * 32), 0, st, t, p->d_lvl_bsmall + L.bsmall_begin, L.bsmall_count,
                                                                p->d_delta, p->d_scalars);
+      ctx->launches++;
+    }
+    for (int kd = 0; kd < 2; kd++) {
+      if (!L.bpoint_count[kd]) continue;
+      const int nb = (int)(((int64_t)L.bpoint_count[kd] * 8 + 127) / 128);
+      const int* lst = p->d_lvl_bpoint + L.bpoint_begin[kd];
+      if (kd == 0) launch_k(backsub_point_kernel<6>, dim3(nb), dim3(128), 0, st, t, lst, L.bpoint_count[kd], p->d_delta, p->d_scalars);
+      else launch_k(backsub_point_kernel<9>, dim3(nb), dim3(128), 0, st, t, lst, L.bpoint_count[kd], p->d_delta, p->d_scalars);
       ctx->launches++;
     }
   }
@@ -647,10 +664,6 @@ int b200_ctx_create(int device, b200_ctx** out) {
   }
   B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
-  B200_CUDA(cudaFuncSetAttribute(leaf_point_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kWarpsPerBlock * (kPtMaxObs * 32 + 8 + kLeafAccMax) * sizeof(double))));
-  B200_CUDA(cudaFuncSetAttribute(leaf_point_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kWarpsPerBlock * (kPtMaxObs * 47 + 8 + kLeafAccMax) * sizeof(double))));
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
   *out = c;
@@ -696,7 +709,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
   cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
-  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_ld);
+  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
@@ -758,6 +771,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   // group the owned fused leaves into runs that share (parent, separator variables): one warp
   // reduces a run's Schur complements in shared memory before the extend-add
   std::vector<int> run_ptr;
+  std::vector<int> leaf_kind(S.ncliques, 0);   // 0 generic, 1 / 2: BAL point clique with 6- / 9-dof cameras
   {
     auto sig_less = [&](int a, int b) {
       if (S.parent[a] != S.parent[b]) return S.parent[a] < S.parent[b];
@@ -778,8 +792,9 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       return true;
     };
     // kind 1/2: BAL point cliques (one Point3 frontal, m <= kPtMaxObs binary projection factors on
-    // distinct cameras) take leaf_point_kernel<6>/<9>; everything else the generic leaf kernel
-    std::vector<int> cf_count(S.ncliques, 0), cf_mask(S.ncliques, 0), kind(S.ncliques, 0);
+    // distinct cameras) take leaf_point_{factor,schur}_kernel<6>/<9>; everything else the generic leaf kernel
+    std::vector<int> cf_count(S.ncliques, 0), cf_mask(S.ncliques, 0);
+    std::vector<int>& kind = leaf_kind;
     for (int64_t gi = 0; gi < d->ngroups; gi++)
       for (int64_t i = 0; i < d->groups[gi].count; i++) {
         const int c = S.fac_clique[p->groups[gi].pos[i]];
@@ -798,7 +813,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
       return sig_less(a, b);
     });
     const int nfl = (int)fused_list.size();
-    int run_max_pt = getenv("B200_NO_LEAF_RUNS") ? 1 : std::max(1, std::min(64, nfl / (ctx->sm_count * 32)));
+    // long enough to amortise the per-run extend-add, short enough for >= 8 CTAs per SM
+    int run_max_pt = getenv("B200_NO_LEAF_RUNS") ? 1 : std::max(1, std::min(64, nfl / (ctx->sm_count * 8)));
     if (getenv("B200_LEAF_RUN_MAX")) run_max_pt = std::max(1, atoi(getenv("B200_LEAF_RUN_MAX")));
     run_ptr.push_back(0);
     for (int kd = 0; kd < 3; kd++) p->leaf_run_begin[kd] = p->leaf_run_end[kd] = 0;
@@ -816,6 +832,8 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
         p->leaf_run_begin[kd] = r;
         while (r < p->n_runs && kind[fused_list[run_ptr[r]]] == kd) r++;
         p->leaf_run_end[kd] = r;
+        p->leaf_pos_begin[kd] = run_ptr[p->leaf_run_begin[kd]];
+        p->leaf_pos_end[kd] = run_ptr[r];
       }
     }
     // shared memory per warp: the widest [F S d] block (generic) / packed Schur triangle (point kernels)
@@ -823,14 +841,15 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     for (int c : fused_list) {
       const int nn = S.nf[c] + S.ns[c] + 1, w = S.ns[c] + 1;
       if (kind[c] == 0) lb = std::max(lb, S.nf[c] * nn);
-      else if (w * (w + 1) / 2 <= kLeafAccMax) tri = std::max(tri, w * (w + 1) / 2);
     }
     p->leaf_lb_cap = lb; p->leaf_acc_cap = tri;
+    for (int c : fused_list) p->leaf_max_w[kind[c]] = std::max(p->leaf_max_w[kind[c]], S.ns[c] + 1);
   }
   p->n_fused = (int)fused_list.size();
   p->big_min_n = getenv("B200_BIG_MIN_N") ? atoi(getenv("B200_BIG_MIN_N")) : 1024;
   p->use_dmma = getenv("B200_NO_DMMA") == nullptr;
   p->fuse_ea = getenv("B200_NO_FUSE_EA") == nullptr;
+  p->schur_pb = (getenv("B200_SCHUR_PB") && atoi(getenv("B200_SCHUR_PB")) == 6) ? 6 : 4;
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
   {
@@ -930,7 +949,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   // phase 0: the subtrees this rank owns, leaves to subtree roots; phase 1: the replicated top.
   // p->levels = [phase-0 levels ..., phase-1 levels ...]; elimination walks it forwards (with the
   // all-reduce of the top fronts between the phases), back-substitution walks it backwards.
-  std::vector<int> small, large, bsmall;
+  std::vector<int> small, large, bsmall, blarge, bpoint;
   p->levels.resize(2 * S.nlevels);
   p->n_sub_levels = (int)S.nlevels;
   p->max_small_n = 1;
@@ -941,13 +960,16 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     L.small_begin = (int)small.size();
     L.large_begin = (int)large.size();
     L.bsmall_begin = (int)bsmall.size();
+    L.blarge_begin = (int)blarge.size();
+    std::vector<int> pts[2];
     for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
       if (phase == 0 ? (is_top[c] || clique_owner[c] != rank) : !is_top[c]) continue;
       if (fused[c]) {
-        // eliminated by the leaf kernels; back-substituted one warp per clique
-        bsmall.push_back(c);
+        // eliminated by the leaf kernels; back-substituted 8 lanes per point / one warp per clique
+        if (leaf_kind[c] > 0 && !getenv("B200_NO_POINT_BACKSUB")) pts[leaf_kind[c] - 1].push_back(c);
+        else bsmall.push_back(c);
       } else if (nn <= kSmallMaxN) {
         small.push_back(c);
         bsmall.push_back(c);
@@ -957,7 +979,17 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
         L.large_max_nf = std::max(L.large_max_nf, S.nf[c]);
         L.large_max_ns = std::max(L.large_max_ns, S.ns[c]);
         L.large_max_n = std::max(L.large_max_n, nn);
+        // back-substitution cares about the pivots only: thin fronts (<= 8 pivots: one pass of the one-warp
+        // kernel over the separator) skip the multi-CTA flag machinery
+        if (S.nf[c] <= 8) bsmall.push_back(c);
+        else { blarge.push_back(c); L.blarge_max_nf = std::max(L.blarge_max_nf, S.nf[c]); }
       }
+    }
+    L.blarge_count = (int)blarge.size() - L.blarge_begin;
+    for (int kd = 0; kd < 2; kd++) {
+      L.bpoint_begin[kd] = (int)bpoint.size();
+      L.bpoint_count[kd] = (int)pts[kd].size();
+      bpoint.insert(bpoint.end(), pts[kd].begin(), pts[kd].end());
     }
     L.small_count = (int)small.size() - L.small_begin;
     L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
@@ -966,9 +998,11 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   UP(upload(&p->d_lvl_small, small, st));
   UP(upload(&p->d_lvl_bsmall, bsmall, st));
   UP(upload(&p->d_lvl_large, large, st));
+  UP(upload(&p->d_lvl_blarge, blarge, st));
+  UP(upload(&p->d_lvl_bpoint, bpoint, st));
   {
-    std::vector<int> fbase(large.size() + 1, 0);
-    for (size_t i = 0; i < large.size(); i++) fbase[i + 1] = fbase[i] + (S.nf[large[i]] + kBsRows - 1) / kBsRows;
+    std::vector<int> fbase(blarge.size() + 1, 0);
+    for (size_t i = 0; i < blarge.size(); i++) fbase[i + 1] = fbase[i] + (S.nf[blarge[i]] + kBsRows - 1) / kBsRows;
     UP(upload(&p->d_bs_flag_base, fbase, st));
     p->n_bs_flags = fbase.back();
     B200_CUDA(cudaMalloc((void**)&p->d_bs_flags, (size_t)std::max(1, fbase.back()) * sizeof(int)));
@@ -1002,19 +1036,31 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
 int64_t b200_values_size(const b200_problem* p) { return p->nval; }
 int64_t b200_delta_size(const b200_problem* p) { return p->ndelta; }
 
+// Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied
+// directly; pageable ones go through the problem's own pinned staging buffer.
+static bool is_pinned_host(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int b200_set_values(b200_problem* p, const double* v) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
-  memcpy(p->h_pinned, v, (size_t)p->nval * sizeof(double));
-  B200_CUDA(cudaMemcpyAsync(p->d_values, p->h_pinned, (size_t)p->nval * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
-  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  const size_t bytes = (size_t)p->nval * sizeof(double);
+  const void* src = v;
+  if (!is_pinned_host(v)) { memcpy(p->h_pinned, v, bytes); src = p->h_pinned; }
+  B200_CUDA(cudaMemcpyAsync(p->d_values, src, bytes, cudaMemcpyHostToDevice, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));   // the caller may reuse its buffer on return
   p->linearized = p->solved = false;
   return B200_OK;
 }
 int b200_get_values(b200_problem* p, double* v) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
-  B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  const size_t bytes = (size_t)p->nval * sizeof(double);
+  const bool direct = is_pinned_host(v);
+  B200_CUDA(cudaMemcpyAsync(direct ? (void*)v : (void*)p->h_pinned, p->d_values, bytes, cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
-  memcpy(v, p->h_pinned, (size_t)p->nval * sizeof(double));
+  if (!direct) memcpy(v, p->h_pinned, bytes);
   return B200_OK;
 }
 

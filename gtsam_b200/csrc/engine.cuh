@@ -67,10 +67,13 @@ struct Scalars {           // device scalars fetched once per LM try
 
 struct LevelPlan {
   int small_begin, small_count;   // range in d_lvl_small (elimination, one warp per clique)
-  int bsmall_begin, bsmall_count; // range in d_lvl_bsmall (back-substitution: small + fused leaves)
+  int bsmall_begin, bsmall_count; // range in d_lvl_bsmall (back-substitution, one warp per clique: at most kSmallMaxN pivots)
   int large_begin, large_count;   // range in d_lvl_large
   int large_max_nf, large_max_n;  // over the large cliques of the level
   int large_max_ns;
+  int blarge_begin, blarge_count; // back-substitution of fronts with more than kSmallMaxN pivots (range in d_lvl_blarge)
+  int blarge_max_nf;
+  int bpoint_begin[2], bpoint_count[2];  // BAL point leaves, DC = 6 / 9 (ranges in d_lvl_bpoint)
 };
 
 }  // namespace b200
@@ -123,6 +126,9 @@ struct b200_problem {
   bool use_dmma = true;   // trailing update of big fronts on the FP64 tensor path (DMMA)
   int n_fused = 0, n_runs = 0, leaf_lb_cap = 1, leaf_acc_cap = 0;
   int leaf_run_begin[3] = {0, 0, 0}, leaf_run_end[3] = {0, 0, 0};  // run ranges: generic / point DC=6 / point DC=9
+  int schur_pb = 4;                                                 // points per staged batch of leaf_point_schur_kernel
+  int leaf_max_w[3] = {1, 1, 1};                                    // widest separator + 1 per kind
+  int leaf_pos_begin[3] = {0, 0, 0}, leaf_pos_end[3] = {0, 0, 0};  // the same ranges as positions in d_fused_list
   int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr, *d_fused_run_ptr = nullptr;
   int2* d_fused_fac = nullptr;
   int64_t top_doubles = 0;          // [0, top_doubles) = fronts of the replicated top (all-reduced when sharded)
@@ -131,7 +137,7 @@ struct b200_problem {
   int64_t *d_ea_ptr = nullptr, *d_didx_ptr = nullptr;
   int *d_ea_map = nullptr, *d_didx = nullptr;
   int64_t* d_diag_index = nullptr;  // per delta scalar: arena index of its diagonal entry
-  int *d_lvl_small = nullptr, *d_lvl_large = nullptr, *d_lvl_bsmall = nullptr;
+  int *d_lvl_small = nullptr, *d_lvl_large = nullptr, *d_lvl_bsmall = nullptr, *d_lvl_blarge = nullptr, *d_lvl_bpoint = nullptr;
   std::vector<b200::LevelPlan> levels;
   int *d_bs_flags = nullptr, *d_bs_flag_base = nullptr;  // publish flags of the multi-CTA back-substitution
   int n_bs_flags = 0;

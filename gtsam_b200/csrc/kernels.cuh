@@ -3,7 +3,7 @@
 //  linearize_kernel      a1-a7   residual + Jacobian + whitening (+ robust reweighting), one thread per
 //                                factor, element-major SoA stores => every store instruction coalesced
 //  error_kernel          a8      0.5*|R r|^2 or rho(|R r|); single launch, last-block reduction in index order
-//  leaf_point_kernel<DC> a10+a12+a13+a14  BAL point cliques: assemble + damp + 3x3 Cholesky + Schur update,
+//  leaf_point_factor_kernel<DC> + leaf_point_schur_kernel<DC>  a10+a12+a13+a14  BAL point cliques: assemble + damp + 3x3 Cholesky + Schur update,
 //                                one lane per factor, runs of points with the same cameras share one extend-add
 //  leaf_fused_kernel     a10+a12+a13+a14  any leaf clique with a small frontal block
 //  assemble_kernel       a12     J^T J / J^T b / b^T b scatter-add into the owning non-leaf front
@@ -578,201 +578,272 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
 }
 
 // ---------------------------------------------------------------------------
-// BAL fast path of the fused leaf kernel: cliques whose single frontal variable is a Point3
+// BAL fast path of the fused leaf elimination: cliques whose single frontal variable is a Point3
 // observed by m <= kPtMaxObs DISTINCT cameras through binary projection factors
-// (GenericProjectionFactor: DC = 6, GeneralSFMFactor<Cal3Bundler>: DC = 9).  Same maths and
-// same outputs as leaf_fused_kernel, but one LANE per factor does the factor work in registers
-// (no divergent index decoding), the 3x3 Cholesky is done redundantly in registers after a
-// warp all-reduce, and the Schur update is emitted as (camera pair, row) items: 6-9 outputs
-// per lane per round instead of one.
+// (GenericProjectionFactor: DC = 6, GeneralSFMFactor<Cal3Bundler>: DC = 9).  Same maths and same
+// outputs as leaf_fused_kernel, split into a per-point and a per-run kernel:
+//
+//  leaf_point_factor_kernel  8 lanes per point (one LANE per factor): assemble H_pp / g_p, damp,
+//      3x3 Cholesky in registers, S' = R^-T H_pc, d' = R^-T g_p; writes the compact conditional
+//      [R S' d'] (3 x n).  50k points = 12.5k warps, nothing sequential: latency is hidden by
+//      occupancy instead of being paid per point.
+//  leaf_point_schur_kernel   one CTA per RUN of points seen by the same cameras.  The run's Schur
+//      complement  sum_p ( [A_c b]^T [A_c b] - [S' d']^T [S' d'] )  is a small SYRK (K = 3 per
+//      point, N = s + 1): 3x3 register tiles over the (s+1)^2 upper triangle, operands staged in
+//      shared memory 8 points at a time, ONE extend-add (FP64 atomics) per run into the parent.
 // ---------------------------------------------------------------------------
 constexpr int kPtMaxObs = 8;
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <int DC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-leaf_point_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr, int nruns,
-                  const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
-                  const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int acc_cap) {
+__global__ void __launch_bounds__(128)
+leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int i_begin, int i_end,
+                         const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
+                         const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc) {
   pdl_sync();
-  constexpr int FS = 5 * DC + 2;   // per factor: S' (3 x DC), A_c (2 x DC), b (2)
-  extern __shared__ double leaf_sm[];
   const double lambda = *lambda_ptr;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int run = blockIdx.x * kWarpsPerBlock + warp;
-  if (run >= nruns) return;
-  const int per_warp = kPtMaxObs * FS + 8 + acc_cap;
-  double* fs = leaf_sm + (size_t)warp * per_warp;   // factor stash
-  double* dd = fs + kPtMaxObs * FS;                 // d'[3], bb
-  double* acc = dd + 8;
-  __shared__ int tks[kWarpsPerBlock][kPtMaxObs];
-  const int r0 = run_ptr[run], r1 = run_ptr[run + 1];
-  const int c0 = list[r0];
-  const int s = t.ns[c0], w = s + 1, ntri = w * (w + 1) / 2, n = 3 + w;
-  const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
-  const int p = t.parent[c0];
-  double* P = p >= 0 ? t.arena + t.off[p] : nullptr;
-  const int pn = p >= 0 ? t.nf[p] + t.ns[p] + 1 : 0;
-  const int* map = t.ea_map + t.ea_ptr[c0];
-  const bool grouped = P && ntri <= acc_cap;
-  if (grouped)
-    for (int e = lane; e < ntri; e += 32) acc[e] = 0.0;
-  const int npairs = m * (m + 1) / 2;
-  for (int idx = r0; idx < r1; idx++) {
-    const int c = list[idx];
-    double Ac[2][DC], Ap[2][3], b[2];
-    int tk = 0;
-    double v[10];
+  const int sub = threadIdx.x & 7;
+  const int idx = i_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const bool live = idx < i_end;
+  int c = 0, m = 0, f0 = 0;
+  if (live) { c = list[idx]; f0 = fac_ptr[idx]; m = fac_ptr[idx + 1] - f0; }
+  double Ac[2][DC], Ap[2][3], b[2];
+  int tk = 0;
+  double v[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) v[i] = 0.0;
-    if (lane < m) {
-      const int2 gf = fac[fac_ptr[idx] + lane];
-      const GroupView& g = gt.g[gf.x];
-      const size_t cnt = (size_t)g.count;
-      const double* J = g.J + gf.y;
-      tk = g.scat[gf.y].y - 3;
+  for (int i = 0; i < 10; i++) v[i] = 0.0;
+  if (sub < m) {
+    const int2 gf = fac[f0 + sub];
+    const GroupView& g = gt.g[gf.x];
+    const size_t cnt = (size_t)g.count;
+    const double* J = g.J + gf.y;
+    tk = g.scat[gf.y].y - 3;
 #pragma unroll
-      for (int cc = 0; cc < DC; cc++) { Ac[0][cc] = J[(size_t)(2 * cc) * cnt]; Ac[1][cc] = J[(size_t)(2 * cc + 1) * cnt]; }
+    for (int cc = 0; cc < DC; cc++) { Ac[0][cc] = J[(size_t)(2 * cc) * cnt]; Ac[1][cc] = J[(size_t)(2 * cc + 1) * cnt]; }
 #pragma unroll
-      for (int j = 0; j < 3; j++) { Ap[0][j] = J[(size_t)(2 * (DC + j)) * cnt]; Ap[1][j] = J[(size_t)(2 * (DC + j) + 1) * cnt]; }
-      b[0] = J[(size_t)(2 * (DC + 3)) * cnt]; b[1] = J[(size_t)(2 * (DC + 3) + 1) * cnt];
-      v[0] = Ap[0][0] * Ap[0][0] + Ap[1][0] * Ap[1][0];
-      v[1] = Ap[0][0] * Ap[0][1] + Ap[1][0] * Ap[1][1];
-      v[2] = Ap[0][0] * Ap[0][2] + Ap[1][0] * Ap[1][2];
-      v[3] = Ap[0][1] * Ap[0][1] + Ap[1][1] * Ap[1][1];
-      v[4] = Ap[0][1] * Ap[0][2] + Ap[1][1] * Ap[1][2];
-      v[5] = Ap[0][2] * Ap[0][2] + Ap[1][2] * Ap[1][2];
-      v[6] = Ap[0][0] * b[0] + Ap[1][0] * b[1];
-      v[7] = Ap[0][1] * b[0] + Ap[1][1] * b[1];
-      v[8] = Ap[0][2] * b[0] + Ap[1][2] * b[1];
-      v[9] = b[0] * b[0] + b[1] * b[1];
+    for (int j = 0; j < 3; j++) { Ap[0][j] = J[(size_t)(2 * (DC + j)) * cnt]; Ap[1][j] = J[(size_t)(2 * (DC + j) + 1) * cnt]; }
+    b[0] = J[(size_t)(2 * (DC + 3)) * cnt]; b[1] = J[(size_t)(2 * (DC + 3) + 1) * cnt];
+    v[0] = Ap[0][0] * Ap[0][0] + Ap[1][0] * Ap[1][0];
+    v[1] = Ap[0][0] * Ap[0][1] + Ap[1][0] * Ap[1][1];
+    v[2] = Ap[0][0] * Ap[0][2] + Ap[1][0] * Ap[1][2];
+    v[3] = Ap[0][1] * Ap[0][1] + Ap[1][1] * Ap[1][1];
+    v[4] = Ap[0][1] * Ap[0][2] + Ap[1][1] * Ap[1][2];
+    v[5] = Ap[0][2] * Ap[0][2] + Ap[1][2] * Ap[1][2];
+    v[6] = Ap[0][0] * b[0] + Ap[1][0] * b[1];
+    v[7] = Ap[0][1] * b[0] + Ap[1][1] * b[1];
+    v[8] = Ap[0][2] * b[0] + Ap[1][2] * b[1];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  if (lambda > 0) {
+    const double sl = 1.0 / (1.0 / sqrt(lambda));
+    double a2[3] = {1.0, 1.0, 1.0};
+    if (hdiag && live) {
+      const int* di = t.didx + t.didx_ptr[c];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { const double sq = sqrt(fmin(fmax(hdiag[di[i]], min_diag), max_diag)); a2[i] = sq * sq; }
     }
-#pragma unroll
-    for (int i = 0; i < 10; i++)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-    if (lambda > 0) {
-      const double sl = 1.0 / (1.0 / sqrt(lambda));
-      double a2[3] = {1.0, 1.0, 1.0};
-      if (hdiag) {
-        const int* di = t.didx + t.didx_ptr[c];
-#pragma unroll
-        for (int i = 0; i < 3; i++) { const double sq = sqrt(fmin(fmax(hdiag[di[i]], min_diag), max_diag)); a2[i] = sq * sq; }
-      }
-      v[0] += (sl * sl) * a2[0]; v[3] += (sl * sl) * a2[1]; v[5] += (sl * sl) * a2[2];
-    }
-    // 3x3 partial Cholesky in registers (every lane, identical): gtsam/base/cholesky.cpp:107-158
-    // (rsqrt + multiplies instead of sqrt + divides: same result to ~1 ulp per operation, a third of the latency)
-    bool ok = v[0] > 0.0;
-    const double i00 = rsqrt(v[0]);
-    const double r00 = v[0] * i00;
-    const double r01 = v[1] * i00, r02 = v[2] * i00;
-    const double p11 = v[3] - r01 * r01;
-    ok = ok && p11 > 0.0;
-    const double i11 = rsqrt(p11);
-    const double r11 = p11 * i11;
-    const double r12 = (v[4] - r01 * r02) * i11;
-    const double p22 = v[5] - r02 * r02 - r12 * r12;
-    ok = ok && p22 > 0.0;
-    const double i22 = rsqrt(p22);
-    const double r22 = p22 * i22;
-    if (!(dexp(r11) - dexp(r22) < 12)) ok = false;
-    if (!ok && lane == 0) atomicMax(&sc->fail_code, INT_MAX - c);
+    v[0] += (sl * sl) * a2[0]; v[3] += (sl * sl) * a2[1]; v[5] += (sl * sl) * a2[2];
+  }
+  // 3x3 partial Cholesky in registers (every lane of the point, identical): gtsam/base/cholesky.cpp:107-158
+  // (rsqrt + multiplies instead of sqrt + divides: same result to ~1 ulp per operation, a third of the latency)
+  bool ok = v[0] > 0.0;
+  const double i00 = rsqrt(v[0]);
+  const double r00 = v[0] * i00;
+  const double r01 = v[1] * i00, r02 = v[2] * i00;
+  const double p11 = v[3] - r01 * r01;
+  ok = ok && p11 > 0.0;
+  const double i11 = rsqrt(p11);
+  const double r11 = p11 * i11;
+  const double r12 = (v[4] - r01 * r02) * i11;
+  const double p22 = v[5] - r02 * r02 - r12 * r12;
+  ok = ok && p22 > 0.0;
+  const double i22 = rsqrt(p22);
+  const double r22 = p22 * i22;
+  if (!(dexp(r11) - dexp(r22) < 12)) ok = false;
+  if (!live) return;
+  if (!ok && sub == 0) atomicMax(&sc->fail_code, INT_MAX - c);
+  const int n = 3 + t.ns[c] + 1;
+  double* M = t.arena + t.off[c];   // compact conditional [R S' d'], column-major 3 x n
+  if (sub == 0) {
     const double d0 = v[6] * i00;
     const double d1 = (v[7] - r01 * d0) * i11;
     const double d2 = (v[8] - r02 * d0 - r12 * d1) * i22;
-    double* M = t.arena + t.off[c];   // compact conditional [R S' d'], column-major 3 x n
-    if (lane == 0) {
-      M[0] = r00; M[1] = 0.0; M[2] = 0.0;
-      M[3] = r01; M[4] = r11; M[5] = 0.0;
-      M[6] = r02; M[7] = r12; M[8] = r22;
-      M[3 * (n - 1)] = d0; M[3 * (n - 1) + 1] = d1; M[3 * (n - 1) + 2] = d2;
-      dd[0] = d0; dd[1] = d1; dd[2] = d2; dd[3] = v[9];
-    }
-    if (lane < m) {
-      double* F = fs + lane * FS;
-      double* Mc = M + 3 * (3 + tk);
+    M[0] = r00; M[1] = 0.0; M[2] = 0.0;
+    M[3] = r01; M[4] = r11; M[5] = 0.0;
+    M[6] = r02; M[7] = r12; M[8] = r22;
+    M[3 * (n - 1)] = d0; M[3 * (n - 1) + 1] = d1; M[3 * (n - 1) + 2] = d2;
+  }
+  if (sub < m) {
+    double* Mc = M + 3 * (3 + tk);
 #pragma unroll
-      for (int cc = 0; cc < DC; cc++) {
-        const double w0 = Ap[0][0] * Ac[0][cc] + Ap[1][0] * Ac[1][cc];
-        const double w1 = Ap[0][1] * Ac[0][cc] + Ap[1][1] * Ac[1][cc];
-        const double w2 = Ap[0][2] * Ac[0][cc] + Ap[1][2] * Ac[1][cc];
-        const double s0 = w0 * i00;
-        const double s1 = (w1 - r01 * s0) * i11;
-        const double s2 = (w2 - r02 * s0 - r12 * s1) * i22;
-        Mc[3 * cc] = s0; Mc[3 * cc + 1] = s1; Mc[3 * cc + 2] = s2;
-        F[cc] = s0; F[DC + cc] = s1; F[2 * DC + cc] = s2;
-        F[3 * DC + cc] = Ac[0][cc]; F[4 * DC + cc] = Ac[1][cc];
-      }
-      F[5 * DC] = b[0]; F[5 * DC + 1] = b[1];
-      tks[warp][lane] = tk;
+    for (int cc = 0; cc < DC; cc++) {
+      const double w0 = Ap[0][0] * Ac[0][cc] + Ap[1][0] * Ac[1][cc];
+      const double w1 = Ap[0][1] * Ac[0][cc] + Ap[1][1] * Ac[1][cc];
+      const double w2 = Ap[0][2] * Ac[0][cc] + Ap[1][2] * Ac[1][cc];
+      const double s0 = w0 * i00;
+      const double s1 = (w1 - r01 * s0) * i11;
+      const double s2 = (w2 - r02 * s0 - r12 * s1) * i22;
+      Mc[3 * cc] = s0; Mc[3 * cc + 1] = s1; Mc[3 * cc + 2] = s2;
     }
-    __syncwarp();
-    if (P) {
-      // (A) camera-pair blocks: item = (pair (k<=l), row r of the k block) -> DC outputs
-      const int nitems = npairs * DC;
-      for (int q = lane; q < nitems; q += 32) {
-        const int pr = q / DC, r = q - pr * DC;
-        int kk = 0, rem = pr;
-        while (rem >= m - kk) { rem -= m - kk; kk++; }
-        const int ll = kk + rem;
-        const double* Fk = fs + kk * FS;
-        const double* Fl = fs + ll * FS;
-        const double sk0 = Fk[r], sk1 = Fk[DC + r], sk2 = Fk[2 * DC + r];
-        const double ak0 = Fk[3 * DC + r], ak1 = Fk[4 * DC + r];
-        const int ti = tks[warp][kk] + r, tl0 = tks[warp][ll];
+  }
+}
+
+template <int DC, int TPT, int PB>   // TPT: 3x3 tiles per thread = ceil(tiles of the widest separator / blockDim); PB: points per staged batch (<= 8)
+__global__ void __launch_bounds__(128)
+leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
+                        const int* __restrict__ fac_ptr, const int2* __restrict__ fac) {
+  pdl_sync();
+  constexpr int NTMAX = (kPtMaxObs * DC + 1 + 2) / 3; // 3-wide tiles along the widest separator (+ rhs column)
+  constexpr int WP = NTMAX * 3;
+  constexpr int AW = 2 * DC + 2;                      // per factor: A_c (2 x DC, column-major) and b (2)
+  __shared__ double sS[2][PB][3 * WP];                // [S' d'] as stored: entry (r, col) at 3*col + r
+  __shared__ double sA[2][PB][kPtMaxObs][AW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = blockDim.x, nwarp = nthr >> 5;   // 96 or 128 threads: no idle warp on the common 6-camera point
+  const int r0 = run_ptr[blockIdx.x], r1 = run_ptr[blockIdx.x + 1];
+  const int c0 = list[r0];
+  const int p = t.parent[c0];
+  if (p < 0) return;
+  const int s = t.ns[c0], w = s + 1;
+  const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
+  const int nt = (w + 2) / 3, ts = s / 3;   // s = m*DC is a multiple of 3: the rhs column is entry 0 of tile ts
+  int ti[TPT], tj[TPT];
+  double acc[TPT][3][3];
 #pragma unroll
-        for (int cc = 0; cc < DC; cc++) {
-          if (kk == ll && cc < r) continue;
-          double val = -(sk0 * Fl[cc] + sk1 * Fl[DC + cc] + sk2 * Fl[2 * DC + cc]);
-          if (kk == ll) val += ak0 * Fl[3 * DC + cc] + ak1 * Fl[4 * DC + cc];
-          const int tj = tl0 + cc;
-          const int i = ti < tj ? ti : tj, j = ti < tj ? tj : ti;
-          if (grouped) {
-            acc[j * (j + 1) / 2 + i] += val;
-          } else {
-            const int a = map[i], bq = map[j];
-            const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
-            atomicAdd(P + lo + (size_t)hi * pn, val);
+  for (int u = 0; u < TPT; u++) {
+    int e = tid + nthr * u, a = 0;
+    while (a < nt && e >= nt - a) { e -= nt - a; a++; }
+    ti[u] = a < nt ? a : -1;
+    tj[u] = a + e;
+#pragma unroll
+    for (int x = 0; x < 3; x++)
+#pragma unroll
+      for (int y = 0; y < 3; y++) acc[u][x][y] = 0.0;
+  }
+  for (int e = tid; e < 2 * PB * (3 * WP - 3 * w); e += nthr) {   // zero padding behind the rhs column, written once
+    const int pt = e / (3 * WP - 3 * w);
+    (&sS[0][0][0])[(size_t)pt * 3 * WP + 3 * w + (e - pt * (3 * WP - 3 * w))] = 0.0;
+  }
+  // Software pipeline: the operands of batch b+1 stream into the other buffer (cp.async) while batch b
+  // is multiplied, and the (dependent) index loads of batch b+2 are in flight behind them.
+  const double* srcS[3];       // [S' d'] of the points this warp copies (points warp, warp + nwarp, ... of a batch)
+  const double* srcJ = nullptr;  // this thread's factor (point tid>>3, factor tid&7), staged by camera slot
+  size_t cntJ = 0;
+  int slotJ = -1;
+  auto load_idx = [&](int b0) {
+    const int nb = min(PB, r1 - b0);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const int pt = warp + nwarp * q;
+      srcS[q] = pt < nb ? t.arena + t.off[list[b0 + pt]] + 9 : nullptr;
+    }
+    const int pt = tid >> 3, fi = tid & 7;
+    slotJ = -1;
+    if (pt < nb && fi < m) {
+      const int2 gf = fac[fac_ptr[b0 + pt] + fi];
+      const GroupView& g = gt.g[gf.x];
+      cntJ = (size_t)g.count;
+      srcJ = g.J + gf.y;
+      slotJ = (g.scat[gf.y].y - 3) / DC;
+    }
+  };
+  auto issue = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      if (srcS[q])
+        for (int e = lane; e < 3 * w; e += 32) cp_async8(&sS[buf][warp + nwarp * q][e], srcS[q] + e);
+    if (slotJ >= 0) {
+      double* dst = sA[buf][tid >> 3][slotJ];
+#pragma unroll
+      for (int el = 0; el < 2 * DC; el++) cp_async8(dst + el, srcJ + (size_t)el * cntJ);
+      cp_async8(dst + 2 * DC, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
+      cp_async8(dst + 2 * DC + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
+    }
+    cp_async_commit();
+  };
+  load_idx(r0);
+  issue(0);
+  load_idx(r0 + PB);
+  int buf = 0;
+  for (int b0 = r0; b0 < r1; b0 += PB, buf ^= 1) {
+    const int nbp = min(PB, r1 - b0);
+    if (b0 + PB < r1) {
+      issue(buf ^ 1);
+      load_idx(b0 + 2 * PB);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < TPT; u++) {
+      if (ti[u] < 0) continue;
+      const int i0 = 3 * ti[u], j0 = 3 * tj[u];
+      const int ci = i0 / DC, cj = j0 / DC;
+      const int oi = i0 - ci * DC, oj = j0 - cj * DC;
+      for (int pt = 0; pt < nbp; pt++) {
+        const double* Si = sS[buf][pt] + 3 * i0;
+        const double* Sj = sS[buf][pt] + 3 * j0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          double si[3], sj[3];
+#pragma unroll
+          for (int x = 0; x < 3; x++) { si[x] = Si[3 * x + r]; sj[x] = Sj[3 * x + r]; }
+#pragma unroll
+          for (int x = 0; x < 3; x++)
+#pragma unroll
+            for (int y = 0; y < 3; y++) acc[u][x][y] -= si[x] * sj[y];
+        }
+        if (tj[u] < ts) {
+          if (ci == cj) {   // both inside one camera's block: A_c^T A_c
+            const double* A = sA[buf][pt][ci];
+#pragma unroll
+            for (int x = 0; x < 3; x++)
+#pragma unroll
+              for (int y = 0; y < 3; y++)
+                acc[u][x][y] += A[2 * (oi + x)] * A[2 * (oj + y)] + A[2 * (oi + x) + 1] * A[2 * (oj + y) + 1];
+          }
+        } else if (ti[u] < ts) {   // rhs column: A_c^T b
+          const double* A = sA[buf][pt][ci];
+#pragma unroll
+          for (int x = 0; x < 3; x++) acc[u][x][0] += A[2 * (oi + x)] * A[2 * DC] + A[2 * (oi + x) + 1] * A[2 * DC + 1];
+        } else {                   // constant term: b^T b
+          for (int fi = 0; fi < m; fi++) {
+            const double* A = sA[buf][pt][fi];
+            acc[u][0][0] += A[2 * DC] * A[2 * DC] + A[2 * DC + 1] * A[2 * DC + 1];
           }
         }
       }
-      // (B) rhs column (tk + r, s) and (C) the constant term (s, s)
-      for (int q = lane; q < m * DC + 1; q += 32) {
-        double val;
-        int i;
-        if (q < m * DC) {
-          const int kk = q / DC, r = q - kk * DC;
-          const double* Fk = fs + kk * FS;
-          val = Fk[3 * DC + r] * Fk[5 * DC] + Fk[4 * DC + r] * Fk[5 * DC + 1] -
-                (Fk[r] * dd[0] + Fk[DC + r] * dd[1] + Fk[2 * DC + r] * dd[2]);
-          i = tks[warp][kk] + r;
-        } else {
-          val = dd[3] - (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
-          i = s;
-        }
-        if (grouped) {
-          acc[s * (s + 1) / 2 + i] += val;
-        } else {
-          const int a = map[i], bq = map[s];
-          const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
-          atomicAdd(P + lo + (size_t)hi * pn, val);
-        }
-      }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (grouped) {
-    int i, j;
-    tri_decode(lane, i, j);
-    for (int e = lane; e < ntri; e += 32) {
-      if (e != lane) {
-        i += 32;
-        while (i > j) { i -= j + 1; j++; }
+  // one extend-add per run (HessianFactor::updateHessian of the leaf's separator factor)
+  double* P = t.arena + t.off[p];
+  const int pn = t.nf[p] + t.ns[p] + 1;
+  const int* map = t.ea_map + t.ea_ptr[c0];
+#pragma unroll
+  for (int u = 0; u < TPT; u++) {
+    if (ti[u] < 0) continue;
+#pragma unroll
+    for (int x = 0; x < 3; x++)
+#pragma unroll
+      for (int y = 0; y < 3; y++) {
+        const int i = 3 * ti[u] + x, j = 3 * tj[u] + y;
+        if (i <= j && j < w) {
+          const int a = map[i], bq = map[j];
+          const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+          atomicAdd(P + lo + (size_t)hi * pn, acc[u][x][y]);
+        }
       }
-      const int a = map[i], b = map[j];
-      const int lo = a < b ? a : b, hi = a < b ? b : a;
-      atomicAdd(P + lo + (size_t)hi * pn, acc[e]);
-    }
   }
 }
 
@@ -1152,6 +1223,49 @@ backsub_small_kernel(TreeView t, const int* __restrict__ list, int count, double
 // 64x64 diagonal block as two 32x32 warp-shuffle solves, and publishes.  The critical path per
 // block is one flag hop + one 64-column GEMV + the in-block solve; everything else overlaps.
 constexpr int kBsRows = 64;
+
+// BAL point leaves (compact conditional [R S' d'], 3 x n): 8 lanes per point, lane k multiplies
+// camera k's 3 x DC block of S' with that camera's slice of delta, an 8-lane shuffle reduction
+// gives d' - S' x_S, lane 0 solves the 3 x 3 triangle.  ~1/20 of the instructions of the generic
+// one-warp-per-clique kernel on the same cliques.
+template <int DC>
+__global__ void __launch_bounds__(128)
+backsub_point_kernel(TreeView t, const int* __restrict__ list, int count, double* delta, Scalars* sc) {
+  pdl_sync();
+  const int sub = threadIdx.x & 7;
+  const int idx = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const bool live = idx < count;
+  const int c = live ? list[idx] : list[0];
+  const int s = t.ns[c];
+  const int m = live ? s / DC : 0;
+  const double* M = t.arena + t.off[c];
+  const int* di = t.didx + t.didx_ptr[c];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (sub < m) {
+    const double* xs = delta + di[3 + DC * sub];   // a variable's dofs are contiguous in delta
+    const double* S = M + 3 * (3 + DC * sub);
+#pragma unroll
+    for (int cc = 0; cc < DC; cc++) {
+      const double x = xs[cc];
+      a0 += S[3 * cc] * x; a1 += S[3 * cc + 1] * x; a2 += S[3 * cc + 2] * x;
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (live && sub == 0) {
+    const double* d = M + 3 * (3 + s);
+    const double x2 = (d[2] - a2) / M[8];
+    const double x1 = ((d[1] - a1) - M[7] * x2) / M[4];
+    const double x0 = (((d[0] - a0) - M[6] * x2) - M[3] * x1) / M[0];
+    double* xo = delta + di[0];
+    xo[0] = x0; xo[1] = x1; xo[2] = x2;
+    if (isnan(x0) || isnan(x1) || isnan(x2)) atomicMax(&sc->nan_code, INT_MAX - c);
+  }
+}
 
 __global__ void __launch_bounds__(256)
 backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc, int* flags,

@@ -67,6 +67,24 @@ def test_cuda_dogleg_trace(gpu_ctx, case):
     assert util.relmax(dl.values(), ref["final_values"]) <= 1e-6
 
 
+def test_pinned_host_buffers_copy_directly(gpu_ctx):
+    """b200_set_values / b200_get_values with page-locked caller buffers (direct DMA) == pageable path."""
+    import torch
+    prob = util.load_case("bal_tiny_s2")
+    dp = capi.DeviceProblem(gpu_ctx, prob)
+    e0 = dp.error()
+    pinned = torch.from_numpy(prob.values.copy()).pin_memory().numpy()
+    pinned += 1e-3
+    dp.set_values(pinned)
+    e1 = dp.error()
+    dp.set_values(np.array(pinned))            # pageable copy of the same numbers
+    assert dp.error() == e1 and e1 != e0
+    out = torch.empty(pinned.size, dtype=torch.float64).pin_memory().numpy()
+    assert dp.get_values(out) is out
+    assert np.array_equal(out, pinned) and np.array_equal(dp.get_values(), pinned)
+    dp.close()
+
+
 def test_cuda_dogleg_optimize_mid_size(gpu_ctx):
     """Dogleg on a mid-size BAL problem converges to the LM optimum (size-independent property)."""
     from gtsam_b200 import datasets
