@@ -981,7 +981,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
         L.large_max_n = std::max(L.large_max_n, nn);
         // back-substitution cares about the pivots only: thin fronts (<= 8 pivots: one pass of the one-warp
         // kernel over the separator) skip the multi-CTA flag machinery
-        if (S.nf[c] <= 8) bsmall.push_back(c);
+        if (S.nf[c] <= 8 && !getenv("B200_NO_THIN_BACKSUB")) bsmall.push_back(c);
         else { blarge.push_back(c); L.blarge_max_nf = std::max(L.blarge_max_nf, S.nf[c]); }
       }
     }
