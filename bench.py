@@ -282,10 +282,13 @@ def main():
         "eliminate_small": 2 * info.front_bytes,                 # read each front, write [R S d] + Schur update
         "eliminate_large": 2 * info.front_bytes,
         "leaf_fused": jac_bytes + info.front_bytes,              # read [A|b] of the leaf factors, write [R S d]
+        # Schur SYRK of the point leaves: read [S' d'] (3 x DC per factor + 3 per point) and [A_c b] (2 x DC + 2 per factor)
+        "leaf_schur": schur_bytes(prob),
     }
     tries = max(1.0, per_step["leaf_fused"][1] if per_step["leaf_fused"][1] else per_step["back_substitute"][1])
     # phases that are ONE kernel launch (per group): the candidates for "the dominant kernel"
-    single = {"linearize": "linearize_kernel", "leaf_fused": "leaf_point_kernel / leaf_fused_kernel",
+    single = {"linearize": "linearize_kernel", "leaf_fused": "leaf_point_factor_kernel / leaf_fused_kernel",
+              "leaf_schur": "leaf_point_schur_kernel",
               "memset_fronts": "memset", "assemble": "assemble_kernel", "linear_error": "linerr_kernel", "error": "error_kernel"}
     dom = max(single, key=lambda k: per_step[k][0])
     traffic = {}
@@ -341,6 +344,18 @@ def main():
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def schur_bytes(prob):
+    """Algorithmic bytes of leaf_point_schur_kernel: read [S' d'] (3 x DC per factor + 3 per point) and
+    [A_c b] (2 x DC + 2 per factor); the run's extend-add output is negligible."""
+    from gtsam_b200 import problem as P
+    total = 24 * int((prob.var_type == P.VAR_POINT3).sum())
+    for g in prob.groups:
+        if g.type in (P.FACTOR_PROJECTION_CAL3S2, P.FACTOR_SFM_BUNDLER):
+            dc = P.factor_ncols(g.type) - 4       # camera dofs: ncols = DC + 3 + 1
+            total += g.count * 8 * (3 * dc + 2 * dc + 2)
+    return total
 
 
 def P_ncols(g):
