@@ -74,7 +74,7 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
-             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_LINEARIZE_MINOR, PH_COUNT };
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_LINEARIZE_MINOR, PH_LEAF_SCHUR, PH_COUNT };
 struct PhaseScope {
   b200_problem* p; int ph; size_t idx; bool on;
   PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
@@ -208,30 +208,42 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
                                                            p->d_scalars, p->leaf_lb_cap, 0);
       ctx->launches++;
     }
-    // BAL points: per-point factorisation (8 lanes per point), then one CTA per run for the Schur complement
+    // BAL points: per-point factorisation (8 lanes per point) ...
     for (int kd = 1; kd <= 2; kd++) {
-      const int nr = p->leaf_run_end[kd] - p->leaf_run_begin[kd];
-      if (nr <= 0) continue;
+      if (p->leaf_run_end[kd] <= p->leaf_run_begin[kd]) continue;
       const int i0 = p->leaf_pos_begin[kd], i1 = p->leaf_pos_end[kd];
       const int nb = (int)(((int64_t)(i1 - i0) * 8 + 127) / 128);
-      const int* runs = p->d_fused_run_ptr + p->leaf_run_begin[kd];
-      // CTA shape of the Schur kernel from the widest separator of the kind: 3x3 tiles over (s+1)^2 / 2
-      const int ntd = (p->leaf_max_w[kd] + 2) / 3, ntiles = ntd * (ntd + 1) / 2;
-      const int thr = ntiles <= 96 ? 96 : 128, tpt = (ntiles + thr - 1) / thr;
-#define B200_LAUNCH_SCHUR(DC_, T_, P_)                                                                                               \
-      if (tpt == T_ && p->schur_pb == P_)                                                                                            \
-        launch_k(leaf_point_schur_kernel<DC_, T_, P_>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs,          \
-                 (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac);
 #define B200_LAUNCH_POINT(DC_)                                                                                                        \
       launch_k(leaf_point_factor_kernel<DC_>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1,                 \
                (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
-               p->d_scalars);                                                                                                          \
-      B200_LAUNCH_SCHUR(DC_, 1, 4) B200_LAUNCH_SCHUR(DC_, 2, 4) B200_LAUNCH_SCHUR(DC_, 3, 4)                                          \
-      B200_LAUNCH_SCHUR(DC_, 1, 6) B200_LAUNCH_SCHUR(DC_, 2, 6) B200_LAUNCH_SCHUR(DC_, 3, 6)
+               p->d_scalars);
       if (kd == 1) { B200_LAUNCH_POINT(6) } else { B200_LAUNCH_POINT(9) }
 #undef B200_LAUNCH_POINT
+      ctx->launches++;
+    }
+  }
+  if (p->n_fused) {
+    // ... then one CTA per run of points with the same cameras for the Schur complement
+    PhaseScope ps(p, PH_LEAF_SCHUR);
+    GroupTable gt;
+    for (size_t gi = 0; gi < p->groups.size(); gi++) gt.g[gi] = view(p->groups[gi]);
+    for (int kd = 1; kd <= 2; kd++) {
+      const int nr = p->leaf_run_end[kd] - p->leaf_run_begin[kd];
+      if (nr <= 0) continue;
+      const int* runs = p->d_fused_run_ptr + p->leaf_run_begin[kd];
+      // CTA shape from the widest separator of the kind: 3x3 tiles over (s+1)^2 / 2
+      const int ntd = (p->leaf_max_w[kd] + 2) / 3, ntiles = ntd * (ntd + 1) / 2;
+      const int thr = ntiles <= 96 ? 96 : 128, tpt = (ntiles + thr - 1) / thr;
+#define B200_LAUNCH_SCHUR(DC_, T_, P_)                                                                                               \
+      if (kd == (DC_ == 6 ? 1 : 2) && tpt == T_ && p->schur_pb == P_)                                                                \
+        launch_k(leaf_point_schur_kernel<DC_, T_, P_>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs,          \
+                 (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac);
+      B200_LAUNCH_SCHUR(6, 1, 4) B200_LAUNCH_SCHUR(6, 2, 4) B200_LAUNCH_SCHUR(6, 3, 4)
+      B200_LAUNCH_SCHUR(6, 1, 6) B200_LAUNCH_SCHUR(6, 2, 6) B200_LAUNCH_SCHUR(6, 3, 6)
+      B200_LAUNCH_SCHUR(9, 1, 4) B200_LAUNCH_SCHUR(9, 2, 4) B200_LAUNCH_SCHUR(9, 3, 4)
+      B200_LAUNCH_SCHUR(9, 1, 6) B200_LAUNCH_SCHUR(9, 2, 6) B200_LAUNCH_SCHUR(9, 3, 6)
 #undef B200_LAUNCH_SCHUR
-      ctx->launches += 2;
+      ctx->launches++;
     }
   }
   // ---- elimination, leaves to roots ----
@@ -1179,7 +1191,7 @@ int b200_profile_phase_count(void) { return PH_COUNT; }
 const char* b200_profile_phase_name(int i) {
   static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
                                         "eliminate_large", "back_substitute", "linear_error", "retract", "error",
-                                        "leaf_fused", "allreduce_top", "linearize_small_groups"};
+                                        "leaf_fused", "allreduce_top", "linearize_small_groups", "leaf_schur"};
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {
