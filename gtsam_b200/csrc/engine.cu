@@ -991,10 +991,10 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
         L.large_max_nf = std::max(L.large_max_nf, S.nf[c]);
         L.large_max_ns = std::max(L.large_max_ns, S.ns[c]);
         L.large_max_n = std::max(L.large_max_n, nn);
-        // back-substitution cares about the pivots only: thin fronts (<= 8 pivots, moderate separator: one pass of
-        // the one-warp kernel) skip the multi-CTA flag machinery (bal_c3 0.150 -> 0.114 ms; wider separators are
-        // faster with 256 threads: sphere2500 0.85 vs 0.90 ms)
-        if (S.nf[c] <= 8 && S.ns[c] <= 320 && !getenv("B200_NO_THIN_BACKSUB")) bsmall.push_back(c);
+        // back-substitution cares about the pivots only: thin fronts (<= 8 pivots: one pass of the one-warp kernel
+        // over the separator) skip the multi-CTA flag machinery (back-substitution: bal_c3 0.150 -> 0.114 ms,
+        // bal_c4 2.7 -> 2.0 ms, sphere2500 0.85 -> 0.90 ms)
+        if (S.nf[c] <= 8 && !getenv("B200_NO_THIN_BACKSUB")) bsmall.push_back(c);
         else { blarge.push_back(c); L.blarge_max_nf = std::max(L.blarge_max_nf, S.nf[c]); }
       }
     }
