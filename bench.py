@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="bal_c3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -63,7 +63,7 @@ def workload_config(prob, args):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -81,7 +81,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts):
+        import datetime
+        try:
+            return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def stop(self, region=None):
+        """region = (epoch start, epoch end) of the timed loop: only samples taken inside it count (a short
+        region may hold none: then all samples of the run, warm-up included, are used and `in_region` is 0)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,8 +100,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = self.rows
+        in_region = 0
+        if region is not None:
+            inside = [r for r in rows if len(r) > 7 and self._epoch(r[7]) is not None
+                      and region[0] - 0.02 <= self._epoch(r[7]) <= region[1] + 0.02]
+            in_region = len(inside)
+            if inside:
+                rows = inside
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -101,7 +119,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "in_region": in_region, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -235,12 +253,14 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count()
         t0 = time.perf_counter()
+        timed.region = [time.time(), None]
         ev0.record(stream)
         for _ in range(steps):
             fn()
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
+        timed.region[1] = time.time()
         ms = ev0.elapsed_time(ev1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -252,7 +272,7 @@ def main():
     if rank == 0:
         sampler.start()
     ms, wall, launches = timed(step_resident, args.steps, max(3, args.warmup))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tuple(timed.region)) if rank == 0 else None
     ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, 1)
 
     # phase profile (separate pass; event records add ~1 us per phase)
