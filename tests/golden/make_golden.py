@@ -48,15 +48,15 @@ def main():
     assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
     subprocess.check_call([H, "kat", os.path.join(HERE, "geometry_kat.bin")])
     emit("bal_tiny_s2", datasets.make("bal_tiny"), dl_iters=5)
-    emit("bal_tiny_body_sensor", datasets.make("bal_tiny", seed=13, body_sensor=True))
-    emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True)
-    emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"))
+    emit("bal_tiny_body_sensor", datasets.make("bal_tiny", seed=13, body_sensor=True), dl_iters=5)
+    emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True, dl_iters=5)
+    emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"), dl_iters=5)
     emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3, dl_iters=8)
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3, dl_iters=8)
     emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2, dl_iters=6)
     from gtsam_b200 import problem as Pq
     import numpy as np
-    emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2)
+    emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2, dl_iters=6)
     emit("sphere_tiny_cauchy", datasets.sphere(layers=5, per_ring=8, seed=14, noise="gaussian", robust=(Pq.ROBUST_CAUCHY, 2.0)))
     bt = datasets.make("bal_tiny", seed=15)
     bt.groups[0].robust_kind, bt.groups[0].robust_param = Pq.ROBUST_TUKEY, 4.685

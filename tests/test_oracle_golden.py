@@ -65,7 +65,8 @@ def test_oracle_gn_trace(case):
     assert np.allclose(errs, ref["gn_errors"], rtol=1e-8)
 
 
-DL_CASES = ["bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian"]
+DL_CASES = ["bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian",
+            "sphere_tiny_huber", "bal_tiny_bundler", "bal_tiny_body_sensor", "bal_tiny_colamd"]
 
 
 @pytest.mark.parametrize("case", DL_CASES)
