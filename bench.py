@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--workload", default="bal_c3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush-l2", action="store_true", help="time the K steps back to back with L2 left warm")
     return ap.parse_args()
 
 
@@ -50,7 +51,8 @@ def workload_config(prob, args):
         "factor_types": sorted({int(g.type) for g in prob.groups}),
         "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else prob.meta.get("ordering", "natural"),
         "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
-        "cache": "working set (fronts + Jacobians) exceeds the 126 MB L2; no explicit flush",
+        "cache": ("L2 left warm between iterations (--no-flush-l2)" if getattr(args, "no_flush_l2", False) else
+                  "L2 flushed between timed iterations: 256 MiB memset on the stream, outside the per-iteration CUDA-event pairs"),
         "parallelism": "single GPU" if args.gpus == 1 else
         f"{args.gpus} ranks, one per GPU: junction-tree subtrees (BAL: points) + their factors sharded by rank, top of the tree "
         f"replicated, one in-place NCCL all-reduce of the top fronts per solve; BAL workloads scale weakly: the graph has "
@@ -246,22 +248,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    # L2 flush between timed iterations: the working set of bal_c3 (Jacobians 48 MB + fronts 52 MB + tables) is about
+    # the size of the 126 MB L2, so each iteration is timed on its own (event pair on the library's stream) and a
+    # 256 MiB memset on the same stream evicts L2 in between, outside the event pairs.
+    flush_buf = None if args.no_flush_l2 else torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local))
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush_buf.zero_()
+
+    def timed(fn, steps, warmup, flush=True):
         for _ in range(warmup):
             fn()
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush = flush and flush_buf is not None
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps if flush else 1)]
         l0 = ctx.launch_count()
         t0 = time.perf_counter()
         timed.region = [time.time(), None]
-        ev0.record(stream)
-        for _ in range(steps):
-            fn()
-        ev1.record(stream)
+        if flush:
+            for a, b in pairs:
+                flush_l2()
+                a.record(stream)
+                fn()
+                b.record(stream)
+        else:
+            pairs[0][0].record(stream)
+            for _ in range(steps):
+                fn()
+            pairs[0][1].record(stream)
         barrier()
         wall = time.perf_counter() - t0
         timed.region[1] = time.time()
-        ms = ev0.elapsed_time(ev1)
+        ms = sum(a.elapsed_time(b) for a, b in pairs)
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,6 +293,7 @@ def main():
     ms, wall, launches = timed(step_resident, args.steps, max(3, args.warmup))
     clocks = sampler.stop(tuple(timed.region)) if rank == 0 else None
     ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_warm, _, _ = timed(step_resident, args.steps, 1, flush=False)   # information only: L2 left warm between iterations
 
     # phase profile (separate pass; event records add ~1 us per phase)
     dev.profile_enable(True)
@@ -343,6 +363,8 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_values.nbytes),
                 "d2h_bytes_per_step": int(host_values.nbytes) + 64, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
+        "warm_l2": {"ms_per_step": ms_warm / args.steps, "value": units * args.steps / (ms_warm * 1e-3),
+                    "note": "same K steps back to back without the L2 flush (information only)"},
         "roofline": roof(dom) or roof("linearize"),
         "roofline_linearize": roof("linearize"),
         "large_fronts": large,

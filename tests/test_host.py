@@ -153,3 +153,26 @@ def test_symbolic_edge_cases_match_oracle(built, name):
     assert np.array_equal(sv, osv) and np.array_equal(par, opar)
     if name == "priors_only":
         assert info.ncliques == 4 and np.all(par == -1) and info.nlevels == 1
+
+
+def test_bench_clock_sampler_region_filter():
+    """bench.py keeps only the nvidia-smi samples whose timestamp falls inside the timed region."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    t0 = bench.ClockSampler._epoch("2026/09/22 23:12:01.000")
+    assert t0 is not None and bench.ClockSampler._epoch("garbage") is None
+
+    class _P:
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+    s.proc = _P()
+    s.rows = [["1000", "1965", "300", "Not Active", "Not Active", "Not Active", "Not Active", "2026/09/22 23:12:00.500"],
+              ["1965", "1965", "700", "Not Active", "Not Active", "Not Active", "Active", "2026/09/22 23:12:01.100"],
+              ["1950", "1965", "700", "Not Active", "Not Active", "Not Active", "Not Active", "2026/09/22 23:12:01.200"],
+              ["900", "1965", "200", "Not Active", "Not Active", "Not Active", "Not Active", "2026/09/22 23:12:02.500"]]
+    out = s.stop((t0 + 0.05, t0 + 0.25))
+    assert out["in_region"] == 2 and out["samples"] == 2 and out["sm_mhz"] in (1950.0, 1965.0)
+    assert out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965.0
