@@ -1133,6 +1133,88 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
   return status;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Marginals (groundwork for the device path).  The reference computes
+ * Marginals::marginalCovariance(j) = marginalInformation(j)^-1 with marginalInformation taken from
+ * bayesTree_.marginalFactor(j, EliminatePreferCholesky) (gtsam/nonlinear/Marginals.cpp:118-154,
+ * gtsam/inference/BayesTree-inst.h:287-318).  The marginal information of x_j under the Gaussian
+ * N(H^-1 g, H^-1) of the linearised graph is the inverse of the (j, j) block of H^-1, so the
+ * covariance is that block itself: the columns H^-1 e_k, k in dofs(j), obtained from the multifrontal
+ * factor H = U^T U whose rows [R S] are the stored conditionals (forward solve U^T y = e_k in
+ * elimination order, back-substitution U x = y as linearAlgorithms-inst.h:50-117). */
+static void clique_fs(const orc_problem* p, int64_t c, int64_t* f, int64_t* s) {
+  *f = 0; *s = 0;
+  for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) *f += VAR_DIM[p->var_type[p->front_vars[q]]];
+  for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) *s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+}
+
+/* x = H^-1 g with the factorisation left by the last successful orc_solve (its damping included) */
+void orc_solve_rhs(const orc_problem* p, const double* g, double* x) {
+  const int64_t ntot = p->dof_off[p->nvars], nc = p->ncliques;
+  double* y = (double*)malloc((size_t)ntot * sizeof(double));
+  memcpy(y, g, (size_t)ntot * sizeof(double));
+  int64_t* idx = (int64_t*)malloc((size_t)(ntot + 1) * sizeof(int64_t));
+  for (int64_t c = 0; c < nc; c++) {   /* U^T y = g */
+    int64_t f, s;
+    clique_fs(p, c, &f, &s);
+    const double* C = p->cond + p->cond_off[c];
+    int64_t k = 0;
+    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++)
+      for (int t = 0; t < VAR_DIM[p->var_type[p->front_vars[q]]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
+    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++)
+      for (int t = 0; t < VAR_DIM[p->var_type[p->sep_vars[q]]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
+    for (int64_t i = 0; i < f; i++) {
+      double sum = y[idx[i]];
+      for (int64_t kk = 0; kk < i; kk++) sum -= C[kk + i * f] * y[idx[kk]];
+      y[idx[i]] = sum / C[i + i * f];
+    }
+    for (int64_t col = f; col < f + s; col++) {
+      double sum = 0;
+      for (int64_t i = 0; i < f; i++) sum += C[i + col * f] * y[idx[i]];
+      y[idx[col]] -= sum;
+    }
+  }
+  for (int64_t c = nc - 1; c >= 0; c--) {   /* U x = y */
+    int64_t f, s;
+    clique_fs(p, c, &f, &s);
+    const double* C = p->cond + p->cond_off[c];
+    int64_t k = 0;
+    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++)
+      for (int t = 0; t < VAR_DIM[p->var_type[p->front_vars[q]]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
+    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++)
+      for (int t = 0; t < VAR_DIM[p->var_type[p->sep_vars[q]]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
+    for (int64_t i = f - 1; i >= 0; i--) {
+      double sum = y[idx[i]];
+      for (int64_t col = f; col < f + s; col++) sum -= C[i + col * f] * x[idx[col]];
+      for (int64_t j = i + 1; j < f; j++) sum -= C[i + j * f] * x[idx[j]];
+      x[idx[i]] = sum / C[i + i * f];
+    }
+  }
+  free(idx);
+  free(y);
+}
+
+/* out: d x d column-major covariance of variable `var` at the current values */
+int orc_marginal_covariance(orc_problem* p, int64_t var, double* out) {
+  const int64_t ntot = p->dof_off[p->nvars];
+  const int d = VAR_DIM[p->var_type[var]];
+  orc_linearize(p);
+  int64_t fv;
+  const int st = orc_solve(p, 0.0, 0, 0, 0, 0, 0, &fv);
+  if (st != B200_OK) return st;
+  double* g = (double*)calloc((size_t)ntot, sizeof(double));
+  double* x = (double*)calloc((size_t)ntot, sizeof(double));
+  for (int k = 0; k < d; k++) {
+    g[p->dof_off[var] + k] = 1.0;
+    orc_solve_rhs(p, g, x);
+    g[p->dof_off[var] + k] = 0.0;
+    for (int i = 0; i < d; i++) out[i + k * d] = x[p->dof_off[var] + i];
+  }
+  free(g);
+  free(x);
+  return B200_OK;
+}
+
 void orc_get_delta(const orc_problem* p, double* out) { memcpy(out, p->delta, (size_t)p->dof_off[p->nvars] * sizeof(double)); }
 
 void orc_get_conditional(const orc_problem* p, int64_t c, double* out) {

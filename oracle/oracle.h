@@ -70,6 +70,11 @@ int orc_gn_iterate(orc_problem* p, double* new_error);
 /* DoglegOptimizer::iterate; error_io = state error, delta_io = trust region radius */
 int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io);
 
+/* Marginals::marginalCovariance (gtsam/nonlinear/Marginals.cpp:118-154): d x d column-major block of H^-1 */
+int orc_marginal_covariance(orc_problem* p, int64_t var, double* out);
+/* x = H^-1 g with the factorisation left by the last successful orc_solve */
+void orc_solve_rhs(const orc_problem* p, const double* g, double* x);
+
 /* symbolic introspection */
 void orc_symbolic_info_get(const orc_problem* p, b200_symbolic_info* info);
 void orc_get_cliques(const orc_problem* p, int64_t* frontal_ptr, int64_t* frontal_vars,

@@ -51,6 +51,8 @@ def lib():
         L.orc_accept_step.argtypes = [C.c_void_p]
         L.orc_gn_iterate.argtypes = [C.c_void_p, dp]
         L.orc_dogleg_iterate.argtypes = [C.c_void_p, dp, dp]
+        L.orc_marginal_covariance.argtypes = [C.c_void_p, C.c_int64, dp]
+        L.orc_solve_rhs.argtypes = [C.c_void_p, dp, dp]
         L.orc_symbolic_info_get.argtypes = [C.c_void_p, C.POINTER(P.CSymbolicInfo)]
         L.orc_get_cliques.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.orc_get_conditional.argtypes = [C.c_void_p, C.c_int64, dp]
@@ -172,6 +174,18 @@ class OracleProblem:
         e, d = C.c_double(error), C.c_double(delta)
         st = self.L.orc_dogleg_iterate(self.h, C.byref(e), C.byref(d))
         return st, e.value, d.value
+
+    def marginal_covariance(self, var):
+        d = P.VAR_DIM[int(self.prob.var_type[var])]
+        out = np.zeros(d * d)
+        st = self.L.orc_marginal_covariance(self.h, int(var), _dp(out))
+        return st, out.reshape(d, d).T   # column-major -> (row, col)
+
+    def solve_rhs(self, g):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        x = np.zeros(self.ndelta)
+        self.L.orc_solve_rhs(self.h, _dp(g), _dp(x))
+        return x
 
     def symbolic_info(self):
         info = P.CSymbolicInfo()

@@ -13,6 +13,7 @@
  */
 #include "problem_io.hpp"
 #include <gtsam/nonlinear/DoglegOptimizer.h>
+#include <gtsam/nonlinear/Marginals.h>
 #include <gtsam/slam/dataset.h>
 #include <gtsam/geometry/Pose2.h>
 #include <gtsam/sfm/SfmData.h>
@@ -198,6 +199,21 @@ static int cmd_gn(const std::string& in, const std::string& outp, int iters) {
   for (int i = 0; i < iters; i++) { gn.iterate(); errs.push_back(gn.error()); }
   out.put("gn_errors", errs);
   out.put("final_values", pack_values(p, b, gn.values()));
+  return 0;
+}
+
+static int cmd_marginals(const std::string& in, const std::string& outp) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  Marginals marginals(b.graph, b.values, b.ordering, Marginals::CHOLESKY);
+  std::vector<double> cov;
+  for (int64_t v = 0; v < p.nvars; v++) {
+    const Matrix S = marginals.marginalCovariance(Key(v));
+    for (int j = 0; j < S.cols(); j++)
+      for (int i = 0; i < S.rows(); i++) cov.push_back(S(i, j));   // column-major per variable, variables in id order
+  }
+  out.put("marg_cov", cov);
   return 0;
 }
 
@@ -471,6 +487,7 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "dump" && argc >= 4) return cmd_dump(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0, argc > 5 && atoi(argv[5]));
   if (cmd == "lm" && argc >= 4) return cmd_lm(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 100, argc > 5 && atoi(argv[5]));
+  if (cmd == "marginals" && argc >= 4) return cmd_marginals(argv[2], argv[3]);
   if (cmd == "dogleg" && argc >= 4) return cmd_dogleg(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 5, argc > 5 ? atof(argv[5]) : 1.0);
   if (cmd == "gn" && argc >= 4) return cmd_gn(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 3);
   if (cmd == "time" && argc >= 3) return cmd_time(argv[2], argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 1, argc > 5 && atoi(argv[5]));

@@ -8,7 +8,7 @@ The fixtures pin the C oracle (tests/test_oracle_golden.py) and the CUDA path
 (tests/test_gpu_parity.py).  Each case stores the problem (*.prob.bin, the
 gtsam_b200.problem.Problem.save format) and the reference's outputs
 (*.dump0.bin: lambda=0; *.dump1.bin: lambda=1e-2 with diagonal damping;
-*.lm.bin: LevenbergMarquardtOptimizer trace; *.gn.bin: GaussNewton trace; *.dl.bin: DoglegOptimizer trace).
+*.lm.bin: LevenbergMarquardtOptimizer trace; *.gn.bin: GaussNewton trace; *.dl.bin: DoglegOptimizer trace; *.marg.bin: Marginals covariances).
 """
 import os
 import shutil
@@ -25,7 +25,7 @@ H = refio.HARNESS
 REF_DATA = "/root/reference/examples/Data"
 
 
-def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False, dl_iters=0):
+def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False, dl_iters=0, marg=False):
     ppath = os.path.join(HERE, f"{name}.prob.bin")
     prob.save(ppath)
     subprocess.check_call([H, "dump", ppath, os.path.join(HERE, f"{name}.dump0.bin"), "0", "0"])
@@ -35,6 +35,8 @@ def emit(name, prob, lm_iters=30, gn_iters=0, ceres=False, dl_iters=0):
         subprocess.check_call([H, "gn", ppath, os.path.join(HERE, f"{name}.gn.bin"), str(gn_iters)])
     if dl_iters:   # DoglegOptimizer trace, deltaInitial = 1
         subprocess.check_call([H, "dogleg", ppath, os.path.join(HERE, f"{name}.dl.bin"), str(dl_iters), "1.0"])
+    if marg:       # Marginals::marginalCovariance of every variable
+        subprocess.check_call([H, "marginals", ppath, os.path.join(HERE, f"{name}.marg.bin")])
     print("wrote", name, prob.nvars, "vars", prob.nfactors, "factors")
 
 
@@ -47,13 +49,13 @@ def with_ordering(prob, kind):
 def main():
     assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
     subprocess.check_call([H, "kat", os.path.join(HERE, "geometry_kat.bin")])
-    emit("bal_tiny_s2", datasets.make("bal_tiny"), dl_iters=5)
+    emit("bal_tiny_s2", datasets.make("bal_tiny"), dl_iters=5, marg=True)
     emit("bal_tiny_body_sensor", datasets.make("bal_tiny", seed=13, body_sensor=True), dl_iters=5)
-    emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True, dl_iters=5)
+    emit("bal_tiny_bundler", datasets.make("bal_tiny", camera_model="bundler"), ceres=True, dl_iters=5, marg=True)
     emit("bal_tiny_colamd", with_ordering(datasets.make("bal_tiny", seed=5), "colamd"), dl_iters=5)
-    emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3, dl_iters=8)
+    emit("sphere_tiny", datasets.make("sphere_tiny"), gn_iters=3, dl_iters=8, marg=True)
     emit("sphere_small_colamd", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=3), "colamd"), gn_iters=3, dl_iters=8)
-    emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2, dl_iters=6)
+    emit("sphere_tiny_gaussian", datasets.sphere(layers=5, per_ring=8, seed=11, noise="gaussian"), gn_iters=2, dl_iters=6, marg=True)
     from gtsam_b200 import problem as Pq
     import numpy as np
     emit("sphere_tiny_huber", datasets.sphere(layers=5, per_ring=8, seed=12, robust=(Pq.ROBUST_HUBER, 1.345)), gn_iters=2, dl_iters=6)

@@ -87,6 +87,49 @@ def test_oracle_dogleg_trace(case):
     assert util.relmax(op.get_values(), ref["final_values"]) <= 1e-6
 
 
+@pytest.mark.parametrize("case", ["bal_tiny_s2", "sphere_tiny", "sphere_tiny_gaussian", "bal_tiny_bundler"])
+def test_oracle_marginal_covariances(case):
+    """Marginals::marginalCovariance of every variable (gtsam/nonlinear/Marginals.cpp:118-154) against the
+    unmodified reference (ref_harness marginals): groundwork for the device path of SURVEY 8f rank 3."""
+    prob = util.load_case(case)
+    ref = util.golden(case, "marg")["marg_cov"]
+    op = O.OracleProblem(prob)
+    off = 0
+    for v in range(prob.nvars):
+        d = P.VAR_DIM[int(prob.var_type[v])]
+        st, S = op.marginal_covariance(v)
+        assert st == 0
+        R = ref[off:off + d * d].reshape(d, d).T
+        off += d * d
+        assert np.abs(S - R).max() <= 1e-8 * np.abs(R).max()
+        assert np.allclose(S, S.T, rtol=1e-9, atol=1e-12 * np.abs(S).max())
+    assert off == ref.size
+
+
+def test_oracle_solve_rhs_reproduces_delta():
+    """H^-1 (A^T b) through the stored conditionals == the solve's own back-substituted delta."""
+    prob = util.load_case("sphere_small_colamd")
+    op = O.OracleProblem(prob)
+    op.linearize()
+    st, _, _, _ = op.solve(0.0)
+    assert st == 0
+    delta = op.get_delta()
+    g = np.zeros(op.ndelta)
+    dof = prob.dof_offsets()
+    for gi, grp in enumerate(prob.groups):
+        J = op.get_jacobians(gi)                       # (count, d, ncols), last column b
+        for f in range(grp.count):
+            col = 0
+            for v in grp.keys[f]:
+                if v < 0:
+                    continue
+                dv = P.VAR_DIM[int(prob.var_type[v])]
+                g[dof[v]:dof[v] + dv] += J[f, :, col:col + dv].T @ J[f, :, -1]
+                col += dv
+    x = op.solve_rhs(g)
+    assert np.linalg.norm(x - delta) <= 1e-9 * np.linalg.norm(delta)
+
+
 def test_geometry_known_answers():
     """Pose3/Rot3 Expmap, Logmap, AdjointMap, inverse, compose against the reference,
     including the near-zero and near-pi branches (gtsam/geometry/SO3.cpp:264-319)."""
