@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_synchronize", "b200_profile_enable", "b200_profile_phase_count", "b200_profile_phase_name",
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
-    "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state",
+    "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         L.b200_lm_get_state.argtypes = [vp, C.POINTER(P.CLMState)]
         L.b200_lm_reset.argtypes = [vp]
         L.b200_gn_iterate.argtypes = [vp, dp]
+        L.b200_marginal_covariance.argtypes = [vp, C.c_int64, dp]
         L.b200_dl_create.argtypes = [vp, C.c_double, C.POINTER(vp)]
         L.b200_dl_destroy.argtypes = [vp]
         L.b200_dl_iterate.argtypes = [vp]
@@ -284,6 +285,16 @@ class DeviceProblem:
 
     def accept_step(self):
         _check(self.L.b200_accept_step(self.h))
+
+    def marginal_covariance(self, var: int):
+        """(d, d) covariance of variable `var` at the current values (Marginals::marginalCovariance)."""
+        d = P.VAR_DIM[int(self.prob.var_type[var])]
+        out = np.zeros(d * d)
+        rc = self.L.b200_marginal_covariance(self.h, int(var), _dp(out))
+        if rc == P.INDETERMINATE:
+            raise IndeterminantLinearSystemException(-1)
+        _check(rc)
+        return out.reshape(d, d).T      # column-major -> [row, col]
 
     def gn_iterate(self):
         e = C.c_double()

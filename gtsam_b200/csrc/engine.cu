@@ -354,6 +354,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   }
   p->solved = true;
   p->factored = true;
+  p->marg_ready = !damped;   // an undamped factor of H at the current values: what Marginals needs
   return B200_OK;
 }
 
@@ -633,6 +634,7 @@ static int launch_try(b200_problem* p, int diagonal, double min_diag, double max
   B200_CUDA(cudaGraphLaunch(p->try_graph[key], p->ctx->stream));
   p->ctx->launches += p->try_launches;
   p->solved = p->factored = true;
+  p->marg_ready = false;     // the LM try factors the damped system
   return B200_OK;
 }
 
@@ -721,7 +723,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
   cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
-  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
+  cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_marg_work); cudaFree(p->d_marg_path); cudaFree(p->d_marg_out); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
@@ -1064,7 +1066,7 @@ int b200_set_values(b200_problem* p, const double* v) {
   if (!is_pinned_host(v)) { memcpy(p->h_pinned, v, bytes); src = p->h_pinned; }
   B200_CUDA(cudaMemcpyAsync(p->d_values, src, bytes, cudaMemcpyHostToDevice, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));   // the caller may reuse its buffer on return
-  p->linearized = p->solved = false;
+  p->linearized = p->solved = p->marg_ready = false;
   return B200_OK;
 }
 int b200_get_values(b200_problem* p, double* v) {
@@ -1131,7 +1133,9 @@ int b200_solve(b200_problem* p, double lambda, int diagonal, double min_diag, do
   if (rc) return rc;
   if (e0) *e0 = p->h_scalars->lin_err0;
   if (e1) *e1 = p->h_scalars->lin_err_delta;
-  return solve_status(p, fail_var);
+  rc = solve_status(p, fail_var);
+  if (rc) p->marg_ready = false;   // a failed factorisation is no basis for marginals
+  return rc;
 }
 
 int b200_get_delta(b200_problem* p, double* out) {
@@ -1157,7 +1161,7 @@ int b200_accept_step(b200_problem* p) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
   // copy, not pointer swap: the captured CUDA graph of the LM try has the buffer roles baked in
   B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_new_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
-  p->linearized = p->solved = false;
+  p->linearized = p->solved = p->marg_ready = false;
   return B200_OK;
 }
 
@@ -1172,7 +1176,7 @@ int b200_restore_values(b200_problem* p) {
   if (!p->d_saved_values) { set_error("b200_restore_values before b200_save_values"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_saved_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
-  p->linearized = p->solved = false;
+  p->linearized = p->solved = p->marg_ready = false;
   return B200_OK;
 }
 int b200_synchronize(b200_problem* p) {
@@ -1443,6 +1447,52 @@ int b200_gn_iterate(b200_problem* p, double* new_error) {
   return B200_OK;
 }
 
+// ---- Marginals ---------------------------------------------------------------------------
+int b200_marginal_covariance(b200_problem* p, int64_t var, double* out) {
+  b200_ctx* ctx = p->ctx;
+  if (ctx->world > 1) { set_error("marginals are single-GPU: create the problem on a context without a communicator"); return B200_INVALID_ARGUMENT; }
+  if (var < 0 || var >= p->nvars) { set_error("b200_marginal_covariance: variable id out of range"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!p->marg_ready) {   // linearize at the current values and factor the undamped system once
+    int rc = enqueue_linearize(p);
+    if (rc) return rc;
+    rc = reset_flags(p);
+    if (rc) return rc;
+    rc = set_lambda(p, 0.0);
+    if (rc) return rc;
+    rc = enqueue_solve(p, false, 0, 0, 0);
+    if (rc) return rc;
+    rc = fetch_scalars(p);
+    if (rc) return rc;
+    int64_t fv;
+    rc = solve_status(p, &fv);
+    if (rc) { p->marg_ready = false; set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
+  }
+  const Symbolic& S = p->sym;
+  std::vector<int> path;
+  for (int c = S.var_clique[var]; c >= 0; c = S.parent[c]) {
+    if (S.nf[c] > kMargMaxF) { set_error("b200_marginal_covariance: a clique on the path has more than 4096 pivots"); return B200_INVALID_ARGUMENT; }
+    path.push_back(c);
+  }
+  const int d = (int)(S.var_dof[var + 1] - S.var_dof[var]);
+  if (!p->d_marg_work) {
+    B200_CUDA(cudaMalloc((void**)&p->d_marg_work, (size_t)9 * std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+    B200_CUDA(cudaMalloc((void**)&p->d_marg_path, (size_t)std::max<int64_t>(1, S.ncliques) * sizeof(int)));
+    B200_CUDA(cudaMalloc((void**)&p->d_marg_out, 81 * sizeof(double)));
+  }
+  B200_CUDA(cudaMemcpyAsync(p->d_marg_path, path.data(), path.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaStreamSynchronize(st));   // `path` is pageable and dies with this call
+  marginal_path_kernel<<<d, 256, 0, st>>>(tview(p), p->d_marg_path, (int)path.size(), (int)S.var_dof[var], d, p->d_marg_work,
+                                          p->ndelta, p->d_marg_out);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_marg_out, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, p->h_pinned, (size_t)d * d * sizeof(double));
+  return B200_OK;
+}
+
 // ---- Dogleg ------------------------------------------------------------------------------
 int b200_dl_destroy(b200_dl* dl);
 int b200_dl_create(b200_problem* p, double delta_initial, b200_dl** out) {
@@ -1575,7 +1625,7 @@ int b200_dl_iterate(b200_dl* dl) {
     }
   }
   if (!zero_step) b200_accept_step(p);
-  else p->linearized = p->solved = false;
+  else p->linearized = p->solved = p->marg_ready = false;
   dl->error = new_f;
   dl->delta = delta;
   dl->iterations++;

@@ -155,6 +155,10 @@ struct b200_problem {
   b200::Scalars* h_scalars = nullptr;  // pinned
   double* h_pinned = nullptr;          // pinned staging for values
   bool linearized = false, solved = false, factored = false;
+  bool marg_ready = false;          // the fronts hold the UNDAMPED factor of H at the current values
+  double* d_marg_work = nullptr;    // Marginals: one scratch vector per covariance column
+  int* d_marg_path = nullptr;
+  double* d_marg_out = nullptr;
   double* d_saved_values = nullptr;
   // phase timers
   bool profile = false;

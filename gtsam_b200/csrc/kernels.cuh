@@ -1351,6 +1351,78 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
 }
 
 // ---------------------------------------------------------------------------
+// Marginals::marginalCovariance (gtsam/nonlinear/Marginals.cpp:118-154): the (j, j) block of H^-1 from the
+// factor already on the device.  H = U^T U with the rows [R S] of U stored per clique, so column k of the
+// block is x = U^-1 U^-T e_k restricted to variable j.  e_k lives in j's clique, the forward solve
+// U^T y = e_k only touches the cliques on the path from there to the root, and x_j only depends on that
+// same path: one CTA per column walks the path up (y_F = R^-T g_F, g_S -= S^T y_F) and down
+// (x_F = R^-1 (y_F - S x_S)).  work: one scratch vector of ndelta doubles per column.
+// ---------------------------------------------------------------------------
+constexpr int kMargMaxF = 4096;   // pivots of one clique staged in shared memory
+
+__global__ void __launch_bounds__(256)
+marginal_path_kernel(TreeView t, const int* __restrict__ path, int npath, int dof0, int d, double* __restrict__ work,
+                     int64_t ndelta, double* __restrict__ out) {
+  __shared__ double yv[kMargMaxF];
+  const int kcol = blockIdx.x, tid = threadIdx.x;
+  double* w = work + (size_t)kcol * ndelta;
+  // zero the entries this walk can touch (frontals of the path cliques cover their separators too), then e_k
+  for (int q = 0; q < npath; q++) {
+    const int c = path[q];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < t.nf[c]; i += 256) w[di[i]] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) w[dof0 + kcol] = 1.0;
+  __syncthreads();
+  for (int q = 0; q < npath; q++) {   // U^T y = e_k, leaf-side clique first
+    const int c = path[q];
+    const int f = t.nf[c], s = t.ns[c], ld = t.ld[c];
+    const double* M = t.arena + t.off[c];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < f; i += 256) yv[i] = w[di[i]];
+    __syncthreads();
+    for (int i = 0; i < f; i++) {
+      if (tid == 0) yv[i] = yv[i] / M[i + (size_t)i * ld];
+      __syncthreads();
+      const double yi = yv[i];
+      for (int j = i + 1 + tid; j < f; j += 256) yv[j] -= M[i + (size_t)j * ld] * yi;
+      __syncthreads();
+    }
+    for (int i = tid; i < f; i += 256) w[di[i]] = yv[i];
+    for (int j = tid; j < s; j += 256) {
+      const double* col = M + (size_t)(f + j) * ld;
+      double acc = 0.0;
+      for (int i = 0; i < f; i++) acc += col[i] * yv[i];
+      w[di[f + j]] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int q = npath - 1; q >= 0; q--) {   // U x = y, root first
+    const int c = path[q];
+    const int f = t.nf[c], s = t.ns[c], ld = t.ld[c];
+    const double* M = t.arena + t.off[c];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < f; i += 256) {
+      double acc = w[di[i]];
+      for (int j = 0; j < s; j++) acc -= M[i + (size_t)(f + j) * ld] * w[di[f + j]];
+      yv[i] = acc;
+    }
+    __syncthreads();
+    for (int i = f - 1; i >= 0; i--) {
+      if (tid == 0) yv[i] = yv[i] / M[i + (size_t)i * ld];
+      __syncthreads();
+      const double xi = yv[i];
+      for (int r = tid; r < i; r += 256) yv[r] -= M[r + (size_t)i * ld] * xi;
+      __syncthreads();
+    }
+    for (int i = tid; i < f; i += 256) w[di[i]] = yv[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < d; i += 256) out[i + kcol * d] = w[dof0 + i];
+}
+
+// ---------------------------------------------------------------------------
 // retract: Values::retract (gtsam/nonlinear/Values.cpp:52-63)
 // ---------------------------------------------------------------------------
 __global__ void retract_kernel(const double* __restrict__ values, const double* __restrict__ delta,

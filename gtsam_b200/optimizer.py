@@ -4,7 +4,8 @@ Same names, argument meaning and error behaviour as
 ``gtsam::LevenbergMarquardtParams`` (gtsam/nonlinear/LevenbergMarquardtParams.h:49-141),
 ``gtsam::LevenbergMarquardtOptimizer`` (gtsam/nonlinear/LevenbergMarquardtOptimizer.h:35-120)
 ``gtsam::GaussNewtonOptimizer`` (gtsam/nonlinear/GaussNewtonOptimizer.h) and
-``gtsam::DoglegOptimizer`` (gtsam/nonlinear/DoglegOptimizer.h:33-128), so the
+``gtsam::DoglegOptimizer`` (gtsam/nonlinear/DoglegOptimizer.h:33-128), ``gtsam::Marginals``
+(gtsam/nonlinear/Marginals.h:31-100), so the
 parity tests read like the reference's own (tests/testNonlinearOptimizer.cpp).
 All numeric work happens in the C-ABI library on the GPU; this file holds no math.
 The C++ subclass shim a GTSAM user links instead is gtsam_b200/shim/.
@@ -254,3 +255,18 @@ class DoglegOptimizer:
 
     def optimize(self):
         return _default_optimize(self, self.params_)
+
+
+class Marginals:
+    """gtsam::Marginals(graph, solution) for the CHOLESKY factorization (gtsam/nonlinear/Marginals.h:31-100):
+    ``marginalCovariance`` / ``marginalInformation`` of one variable at the problem's current values."""
+
+    def __init__(self, ctx: Context, problem: P.Problem, device_problem: Optional[DeviceProblem] = None):
+        self.dp = device_problem or DeviceProblem(ctx, problem)
+
+    def marginalCovariance(self, variable: int):
+        return self.dp.marginal_covariance(variable)
+
+    def marginalInformation(self, variable: int):
+        import numpy as np
+        return np.linalg.inv(self.marginalCovariance(variable))

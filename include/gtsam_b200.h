@@ -266,6 +266,13 @@ int b200_lm_reset(b200_lm* lm);
 /* GaussNewtonOptimizer::iterate(), gtsam/nonlinear/GaussNewtonOptimizer.cpp:44-67 */
 int b200_gn_iterate(b200_problem* prob, double* new_error);
 
+/* Marginals::marginalCovariance(key), gtsam/nonlinear/Marginals.cpp:118-154: the covariance of one variable under
+ * the Gaussian of the graph linearised at the current values = the (var, var) block of (A^T A)^-1.  out: d x d
+ * doubles, column-major, d = tangent dimension of the variable.  The first call after the values changed (or after
+ * a damped solve) linearizes and factors the undamped system (B200_INDETERMINATE if that fails); further calls reuse
+ * the factor and only walk the clique path from the variable to the root.  Single-GPU only. */
+int b200_marginal_covariance(b200_problem* prob, int64_t var, double* out);
+
 /* Powell's dogleg.  b200_dl_iterate = DoglegOptimizer::iterate(),
  * gtsam/nonlinear/DoglegOptimizer.cpp:84-121, with DoglegOptimizerImpl::Iterate in
  * ONE_STEP_PER_ITERATION mode (gtsam/nonlinear/DoglegOptimizerImpl.h:139-258): linearize,
