@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_synchronize", "b200_profile_enable", "b200_profile_phase_count", "b200_profile_phase_name",
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
-    "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance",
+    "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.b200_lm_reset.argtypes = [vp]
         L.b200_gn_iterate.argtypes = [vp, dp]
         L.b200_marginal_covariance.argtypes = [vp, C.c_int64, dp]
+        L.b200_joint_marginal_covariance.argtypes = [vp, ip, C.c_int64, dp]
         L.b200_dl_create.argtypes = [vp, C.c_double, C.POINTER(vp)]
         L.b200_dl_destroy.argtypes = [vp]
         L.b200_dl_iterate.argtypes = [vp]
@@ -295,6 +296,17 @@ class DeviceProblem:
             raise IndeterminantLinearSystemException(-1)
         _check(rc)
         return out.reshape(d, d).T      # column-major -> [row, col]
+
+    def joint_marginal_covariance(self, variables):
+        """(D, D) joint covariance, blocks in ascending variable order (Marginals::jointMarginalCovariance)."""
+        vs = np.array(sorted(int(v) for v in variables), dtype=np.int64)
+        D = int(sum(P.VAR_DIM[int(self.prob.var_type[v])] for v in vs))
+        out = np.zeros(D * D)
+        rc = self.L.b200_joint_marginal_covariance(self.h, _ip(vs), len(vs), _dp(out))
+        if rc == P.INDETERMINATE:
+            raise IndeterminantLinearSystemException(-1)
+        _check(rc)
+        return out.reshape(D, D).T
 
     def gn_iterate(self):
         e = C.c_double()

@@ -1448,27 +1448,32 @@ int b200_gn_iterate(b200_problem* p, double* new_error) {
 }
 
 // ---- Marginals ---------------------------------------------------------------------------
+// the undamped factor of H at the current values, computed once and reused until the values change
+static int prepare_marginals(b200_problem* p) {
+  if (p->marg_ready) return B200_OK;
+  int rc = enqueue_linearize(p);
+  if (rc) return rc;
+  rc = reset_flags(p);
+  if (rc) return rc;
+  rc = set_lambda(p, 0.0);
+  if (rc) return rc;
+  rc = enqueue_solve(p, false, 0, 0, 0);
+  if (rc) return rc;
+  rc = fetch_scalars(p);
+  if (rc) return rc;
+  int64_t fv;
+  rc = solve_status(p, &fv);
+  if (rc) { p->marg_ready = false; set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
+  return B200_OK;
+}
+
 int b200_marginal_covariance(b200_problem* p, int64_t var, double* out) {
   b200_ctx* ctx = p->ctx;
   if (ctx->world > 1) { set_error("marginals are single-GPU: create the problem on a context without a communicator"); return B200_INVALID_ARGUMENT; }
   if (var < 0 || var >= p->nvars) { set_error("b200_marginal_covariance: variable id out of range"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  if (!p->marg_ready) {   // linearize at the current values and factor the undamped system once
-    int rc = enqueue_linearize(p);
-    if (rc) return rc;
-    rc = reset_flags(p);
-    if (rc) return rc;
-    rc = set_lambda(p, 0.0);
-    if (rc) return rc;
-    rc = enqueue_solve(p, false, 0, 0, 0);
-    if (rc) return rc;
-    rc = fetch_scalars(p);
-    if (rc) return rc;
-    int64_t fv;
-    rc = solve_status(p, &fv);
-    if (rc) { p->marg_ready = false; set_error("indeterminate linear system near variable " + std::to_string(fv)); return rc; }
-  }
+  { const int rc = prepare_marginals(p); if (rc) return rc; }
   const Symbolic& S = p->sym;
   std::vector<int> path;
   for (int c = S.var_clique[var]; c >= 0; c = S.parent[c]) {
@@ -1490,6 +1495,52 @@ int b200_marginal_covariance(b200_problem* p, int64_t var, double* out) {
   B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_marg_out, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
   memcpy(out, p->h_pinned, (size_t)d * d * sizeof(double));
+  return B200_OK;
+}
+
+int b200_joint_marginal_covariance(b200_problem* p, const int64_t* vars, int64_t nv, double* out) {
+  b200_ctx* ctx = p->ctx;
+  if (ctx->world > 1) { set_error("marginals are single-GPU: create the problem on a context without a communicator"); return B200_INVALID_ARGUMENT; }
+  if (nv <= 0) { set_error("b200_joint_marginal_covariance: no variables"); return B200_INVALID_ARGUMENT; }
+  const Symbolic& S = p->sym;
+  std::vector<int> dofs;
+  for (int64_t a = 0; a < nv; a++) {
+    if (vars[a] < 0 || vars[a] >= p->nvars || (a > 0 && vars[a] <= vars[a - 1])) {
+      set_error("b200_joint_marginal_covariance: variable ids must be in range, distinct and ascending");
+      return B200_INVALID_ARGUMENT;
+    }
+    for (int64_t q = S.var_dof[vars[a]]; q < S.var_dof[vars[a] + 1]; q++) dofs.push_back((int)q);
+  }
+  const int D = (int)dofs.size();
+  if (D > 128) { set_error("b200_joint_marginal_covariance: more than 128 scalar dimensions requested"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  { const int rc = prepare_marginals(p); if (rc) return rc; }
+  std::vector<char> on(S.ncliques, 0);
+  for (int64_t a = 0; a < nv; a++)
+    for (int c = S.var_clique[vars[a]]; c >= 0 && !on[c]; c = S.parent[c]) {
+      if (S.nf[c] > kMargMaxF) { set_error("b200_joint_marginal_covariance: a clique on the path has more than 4096 pivots"); return B200_INVALID_ARGUMENT; }
+      on[c] = 1;
+    }
+  std::vector<int> path;
+  for (int c = 0; c < (int)S.ncliques; c++)
+    if (on[c]) path.push_back(c);   // ascending clique id = elimination order
+  double *d_work = nullptr, *d_out = nullptr;
+  int *d_path = nullptr, *d_dofs = nullptr;
+  B200_CUDA(cudaMalloc((void**)&d_work, (size_t)D * std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&d_out, (size_t)D * D * sizeof(double)));
+  B200_CUDA(cudaMalloc((void**)&d_path, path.size() * sizeof(int)));
+  B200_CUDA(cudaMalloc((void**)&d_dofs, (size_t)D * sizeof(int)));
+  B200_CUDA(cudaMemcpyAsync(d_path, path.data(), path.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(d_dofs, dofs.data(), (size_t)D * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  marginal_joint_kernel<<<D, 256, 0, st>>>(tview(p), d_path, (int)path.size(), d_dofs, D, d_work, p->ndelta, d_out);
+  ctx->launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(d_work); cudaFree(d_out); cudaFree(d_path); cudaFree(d_dofs);
+  if (ce != cudaSuccess) { set_error(std::string("b200_joint_marginal_covariance: ") + cudaGetErrorString(ce)); return B200_CUDA_ERROR; }
   return B200_OK;
 }
 

@@ -1422,6 +1422,70 @@ marginal_path_kernel(TreeView t, const int* __restrict__ path, int npath, int do
   for (int i = tid; i < d; i += 256) out[i + kcol * d] = w[dof0 + i];
 }
 
+// Marginals::jointMarginalCovariance: the same walk over the UNION of the variables' clique paths (ascending
+// clique id = elimination order: parents have larger ids), one CTA per column of the D x D joint matrix;
+// dofs[] lists the delta indices of the requested variables in sorted-variable order.
+__global__ void __launch_bounds__(256)
+marginal_joint_kernel(TreeView t, const int* __restrict__ path, int npath, const int* __restrict__ dofs, int D,
+                      double* __restrict__ work, int64_t ndelta, double* __restrict__ out) {
+  __shared__ double yv[kMargMaxF];
+  const int kcol = blockIdx.x, tid = threadIdx.x;
+  double* w = work + (size_t)kcol * ndelta;
+  for (int q = 0; q < npath; q++) {
+    const int c = path[q];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < t.nf[c]; i += 256) w[di[i]] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) w[dofs[kcol]] = 1.0;
+  __syncthreads();
+  for (int q = 0; q < npath; q++) {   // U^T y = e_k in elimination order
+    const int c = path[q];
+    const int f = t.nf[c], s = t.ns[c], ld = t.ld[c];
+    const double* M = t.arena + t.off[c];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < f; i += 256) yv[i] = w[di[i]];
+    __syncthreads();
+    for (int i = 0; i < f; i++) {
+      if (tid == 0) yv[i] = yv[i] / M[i + (size_t)i * ld];
+      __syncthreads();
+      const double yi = yv[i];
+      for (int j = i + 1 + tid; j < f; j += 256) yv[j] -= M[i + (size_t)j * ld] * yi;
+      __syncthreads();
+    }
+    for (int i = tid; i < f; i += 256) w[di[i]] = yv[i];
+    for (int j = tid; j < s; j += 256) {
+      const double* col = M + (size_t)(f + j) * ld;
+      double acc = 0.0;
+      for (int i = 0; i < f; i++) acc += col[i] * yv[i];
+      w[di[f + j]] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int q = npath - 1; q >= 0; q--) {   // U x = y, roots first
+    const int c = path[q];
+    const int f = t.nf[c], s = t.ns[c], ld = t.ld[c];
+    const double* M = t.arena + t.off[c];
+    const int* di = t.didx + t.didx_ptr[c];
+    for (int i = tid; i < f; i += 256) {
+      double acc = w[di[i]];
+      for (int j = 0; j < s; j++) acc -= M[i + (size_t)(f + j) * ld] * w[di[f + j]];
+      yv[i] = acc;
+    }
+    __syncthreads();
+    for (int i = f - 1; i >= 0; i--) {
+      if (tid == 0) yv[i] = yv[i] / M[i + (size_t)i * ld];
+      __syncthreads();
+      const double xi = yv[i];
+      for (int r = tid; r < i; r += 256) yv[r] -= M[r + (size_t)i * ld] * xi;
+      __syncthreads();
+    }
+    for (int i = tid; i < f; i += 256) w[di[i]] = yv[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < D; i += 256) out[i + (size_t)kcol * D] = w[dofs[i]];
+}
+
 // ---------------------------------------------------------------------------
 // retract: Values::retract (gtsam/nonlinear/Values.cpp:52-63)
 // ---------------------------------------------------------------------------

@@ -270,3 +270,32 @@ class Marginals:
     def marginalInformation(self, variable: int):
         import numpy as np
         return np.linalg.inv(self.marginalCovariance(variable))
+
+    def jointMarginalCovariance(self, variables) -> "JointMarginal":
+        vs = sorted(int(v) for v in variables)
+        dims = [P.VAR_DIM[int(self.dp.prob.var_type[v])] for v in vs]
+        return JointMarginal(self.dp.joint_marginal_covariance(vs), vs, dims)
+
+
+class JointMarginal:
+    """gtsam::JointMarginal (gtsam/nonlinear/Marginals.h:135-185): blocks addressed by variable, keys sorted."""
+
+    def __init__(self, full, keys, dims):
+        self._full, self._keys = full, list(keys)
+        self._off = {}
+        o = 0
+        for k, d in zip(keys, dims):
+            self._off[k] = (o, o + d)
+            o += d
+
+    def fullMatrix(self):
+        return self._full
+
+    def keys(self):
+        return list(self._keys)
+
+    def at(self, i: int, j: int):
+        (a, b), (c, d) = self._off[int(i)], self._off[int(j)]
+        return self._full[a:b, c:d]
+
+    __call__ = at

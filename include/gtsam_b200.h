@@ -272,6 +272,10 @@ int b200_gn_iterate(b200_problem* prob, double* new_error);
  * a damped solve) linearizes and factors the undamped system (B200_INDETERMINATE if that fails); further calls reuse
  * the factor and only walk the clique path from the variable to the root.  Single-GPU only. */
 int b200_marginal_covariance(b200_problem* prob, int64_t var, double* out);
+/* Marginals::jointMarginalCovariance(keys).fullMatrix(), gtsam/nonlinear/Marginals.cpp:128-190: vars are distinct
+ * variable ids in ASCENDING order (the reference returns the blocks in sorted-key order as well); out: D x D doubles,
+ * column-major, D = sum of their tangent dimensions (<= 128). */
+int b200_joint_marginal_covariance(b200_problem* prob, const int64_t* vars, int64_t nvars, double* out);
 
 /* Powell's dogleg.  b200_dl_iterate = DoglegOptimizer::iterate(),
  * gtsam/nonlinear/DoglegOptimizer.cpp:84-121, with DoglegOptimizerImpl::Iterate in

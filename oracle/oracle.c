@@ -1215,6 +1215,34 @@ int orc_marginal_covariance(orc_problem* p, int64_t var, double* out) {
   return B200_OK;
 }
 
+/* Marginals::jointMarginalCovariance (gtsam/nonlinear/Marginals.cpp:128-190): the covariance of several
+ * variables, blocks in sorted-key order = the rows/columns of H^-1 picked at those variables' dofs.
+ * vars must be sorted ascending and distinct; out: D x D column-major, D = sum of their dims. */
+int orc_joint_marginal_covariance(orc_problem* p, const int64_t* vars, int64_t nv, double* out) {
+  const int64_t ntot = p->dof_off[p->nvars];
+  int64_t D = 0;
+  for (int64_t a = 0; a < nv; a++) D += VAR_DIM[p->var_type[vars[a]]];
+  orc_linearize(p);
+  int64_t fv;
+  const int st = orc_solve(p, 0.0, 0, 0, 0, 0, 0, &fv);
+  if (st != B200_OK) return st;
+  double* g = (double*)calloc((size_t)ntot, sizeof(double));
+  double* x = (double*)calloc((size_t)ntot, sizeof(double));
+  int64_t col = 0;
+  for (int64_t a = 0; a < nv; a++)
+    for (int k = 0; k < VAR_DIM[p->var_type[vars[a]]]; k++, col++) {
+      g[p->dof_off[vars[a]] + k] = 1.0;
+      orc_solve_rhs(p, g, x);
+      g[p->dof_off[vars[a]] + k] = 0.0;
+      int64_t row = 0;
+      for (int64_t b = 0; b < nv; b++)
+        for (int i = 0; i < VAR_DIM[p->var_type[vars[b]]]; i++, row++) out[row + col * D] = x[p->dof_off[vars[b]] + i];
+    }
+  free(g);
+  free(x);
+  return B200_OK;
+}
+
 void orc_get_delta(const orc_problem* p, double* out) { memcpy(out, p->delta, (size_t)p->dof_off[p->nvars] * sizeof(double)); }
 
 void orc_get_conditional(const orc_problem* p, int64_t c, double* out) {

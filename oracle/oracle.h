@@ -72,6 +72,8 @@ int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io);
 
 /* Marginals::marginalCovariance (gtsam/nonlinear/Marginals.cpp:118-154): d x d column-major block of H^-1 */
 int orc_marginal_covariance(orc_problem* p, int64_t var, double* out);
+/* Marginals::jointMarginalCovariance: vars sorted ascending; out D x D column-major, blocks in that order */
+int orc_joint_marginal_covariance(orc_problem* p, const int64_t* vars, int64_t nv, double* out);
 /* x = H^-1 g with the factorisation left by the last successful orc_solve */
 void orc_solve_rhs(const orc_problem* p, const double* g, double* x);
 

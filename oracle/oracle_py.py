@@ -53,6 +53,7 @@ def lib():
         L.orc_dogleg_iterate.argtypes = [C.c_void_p, dp, dp]
         L.orc_marginal_covariance.argtypes = [C.c_void_p, C.c_int64, dp]
         L.orc_solve_rhs.argtypes = [C.c_void_p, dp, dp]
+        L.orc_joint_marginal_covariance.argtypes = [C.c_void_p, ip, C.c_int64, dp]
         L.orc_symbolic_info_get.argtypes = [C.c_void_p, C.POINTER(P.CSymbolicInfo)]
         L.orc_get_cliques.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.orc_get_conditional.argtypes = [C.c_void_p, C.c_int64, dp]
@@ -180,6 +181,13 @@ class OracleProblem:
         out = np.zeros(d * d)
         st = self.L.orc_marginal_covariance(self.h, int(var), _dp(out))
         return st, out.reshape(d, d).T   # column-major -> (row, col)
+
+    def joint_marginal_covariance(self, variables):
+        vs = np.array(sorted(int(v) for v in variables), dtype=np.int64)
+        D = int(sum(P.VAR_DIM[int(self.prob.var_type[v])] for v in vs))
+        out = np.zeros(D * D)
+        st = self.L.orc_joint_marginal_covariance(self.h, _ip(vs), len(vs), _dp(out))
+        return st, out.reshape(D, D).T
 
     def solve_rhs(self, g):
         g = np.ascontiguousarray(g, dtype=np.float64)

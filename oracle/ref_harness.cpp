@@ -217,6 +217,22 @@ static int cmd_marginals(const std::string& in, const std::string& outp) {
   return 0;
 }
 
+static int cmd_jointmarg(const std::string& in, const std::string& outp, int argc, char** argv) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  Marginals marginals(b.graph, b.values, b.ordering, Marginals::CHOLESKY);
+  KeyVector keys;
+  for (int i = 4; i < argc; i++) keys.push_back(Key(atoll(argv[i])));
+  const JointMarginal joint = marginals.jointMarginalCovariance(keys);
+  const Matrix F = joint.fullMatrix();   // blocks in sorted-key order (Marginals.cpp:176-188)
+  std::vector<double> cov;
+  for (int j = 0; j < F.cols(); j++)
+    for (int i = 0; i < F.rows(); i++) cov.push_back(F(i, j));
+  out.put("joint_cov", cov);
+  return 0;
+}
+
 static int cmd_dogleg(const std::string& in, const std::string& outp, int iters, double delta0) {
   Prob p = load(in);
   Built b = build(p);
@@ -487,6 +503,7 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "dump" && argc >= 4) return cmd_dump(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0, argc > 5 && atoi(argv[5]));
   if (cmd == "lm" && argc >= 4) return cmd_lm(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 100, argc > 5 && atoi(argv[5]));
+  if (cmd == "jointmarg" && argc >= 5) return cmd_jointmarg(argv[2], argv[3], argc, argv);
   if (cmd == "marginals" && argc >= 4) return cmd_marginals(argv[2], argv[3]);
   if (cmd == "dogleg" && argc >= 4) return cmd_dogleg(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 5, argc > 5 ? atof(argv[5]) : 1.0);
   if (cmd == "gn" && argc >= 4) return cmd_gn(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 3);

@@ -99,6 +99,13 @@ def main():
     # BASELINE.json configs[0] (CPU plumbing): the reference's Pose2 g2o example path
     with open(os.path.join(HERE, "config1_pose2slam_g2o.json"), "w") as f:
         f.write(subprocess.check_output([H, "pose2", os.path.join(REF_DATA, "noisyToyGraph.txt")]).decode())
+    # joint marginals of a few variable sets (Marginals::jointMarginalCovariance)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import util as _util
+    for case, sets in _util.JOINT_SETS.items():
+        for i, vs in enumerate(sets):
+            subprocess.check_call([H, "jointmarg", os.path.join(HERE, f"{case}.prob.bin"), os.path.join(HERE, f"{case}.joint{i}.bin")]
+                                  + [str(v) for v in vs])
     # the reference's own end-to-end golden: tests/testGeneralSFMFactorB.cpp:44-63 (0.0199833 +- 1e-5)
     from gtsam_b200.problem import Problem
     with tempfile.TemporaryDirectory() as td:

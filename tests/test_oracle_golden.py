@@ -106,6 +106,20 @@ def test_oracle_marginal_covariances(case):
     assert off == ref.size
 
 
+@pytest.mark.parametrize("case", sorted(util.JOINT_SETS))
+def test_oracle_joint_marginal_covariances(case):
+    """Marginals::jointMarginalCovariance (two variables: BayesTree::joint; three: marginalMultifrontalBayesTree;
+    gtsam/nonlinear/Marginals.cpp:128-190), full matrix in sorted-key order, against the unmodified reference."""
+    prob = util.load_case(case)
+    op = O.OracleProblem(prob)
+    for i, vs in enumerate(util.JOINT_SETS[case]):
+        ref = util.golden(case, f"joint{i}")["joint_cov"]
+        st, S = op.joint_marginal_covariance(vs)
+        assert st == 0
+        R = ref.reshape(S.shape).T
+        assert np.abs(S - R).max() <= 1e-8 * np.abs(R).max()
+
+
 def test_oracle_solve_rhs_reproduces_delta():
     """H^-1 (A^T b) through the stored conditionals == the solve's own back-substituted delta."""
     prob = util.load_case("sphere_small_colamd")

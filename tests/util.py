@@ -151,3 +151,8 @@ def edge_case_problems():
                                                      P.FactorGroup(pg.type, pg.keys, pg.meas, pg.noise_kind, pg.noise)], b.cal)
     out["single_observation_points"] = b
     return out
+
+
+# variable sets of the joint-marginal fixtures (tests/golden/<case>.joint<i>.bin, written by make_golden.py)
+JOINT_SETS = {"bal_tiny_s2": [[0, 1], [3, 40], [2, 9, 55]], "sphere_tiny": [[0, 39], [5, 6, 7]],
+              "bal_tiny_bundler": [[1, 30], [0, 4, 69]]}
