@@ -354,6 +354,45 @@ GaussianFactorGraph::shared_ptr B200GaussNewtonOptimizer::iterate() {
   return GaussianFactorGraph::shared_ptr();
 }
 
+// ---- Marginals ----------------------------------------------------------------------------
+B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution, const Ordering& ordering)
+    : dev_(std::make_shared<DeviceState>()) {
+  dev_->pack(graph, solution, ordering);
+}
+B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution)
+    : B200Marginals(graph, solution, Ordering::Colamd(graph)) {}
+
+Matrix B200Marginals::marginalCovariance(Key variable) const {
+  const auto it = dev_->key2id.find(variable);
+  if (it == dev_->key2id.end()) throw ValuesKeyDoesNotExist("B200Marginals::marginalCovariance", variable);
+  const int64_t v = it->second;
+  const int d = (int)(dev_->dof_off[v + 1] - dev_->dof_off[v]);
+  Matrix S(d, d);   // Eigen default: column-major, as the C-ABI writes it
+  const int rc = b200_marginal_covariance(dev_->prob, v, S.data());
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variable);
+  check(rc, "b200_marginal_covariance");
+  return S;
+}
+
+Matrix B200Marginals::marginalInformation(Key variable) const { return marginalCovariance(variable).inverse(); }
+
+Matrix B200Marginals::jointMarginalCovariance(const KeyVector& variables) const {
+  std::vector<int64_t> ids;
+  for (Key k : variables) {
+    const auto it = dev_->key2id.find(k);
+    if (it == dev_->key2id.end()) throw ValuesKeyDoesNotExist("B200Marginals::jointMarginalCovariance", k);
+    ids.push_back(it->second);
+  }
+  std::sort(ids.begin(), ids.end());   // ids are the ranks of the Keys: sorted ids == sorted keys
+  int64_t D = 0;
+  for (int64_t v : ids) D += dev_->dof_off[v + 1] - dev_->dof_off[v];
+  Matrix S(D, D);
+  const int rc = b200_joint_marginal_covariance(dev_->prob, ids.data(), (int64_t)ids.size(), S.data());
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variables.front());
+  check(rc, "b200_joint_marginal_covariance");
+  return S;
+}
+
 VectorValues solveOnDevice(const NonlinearFactorGraph& graph, const Values& values, const Ordering& ordering, double lambda) {
   DeviceState dev;
   dev.pack(graph, values, ordering);

@@ -27,6 +27,7 @@
 #pragma once
 #include <gtsam/nonlinear/GaussNewtonOptimizer.h>
 #include <gtsam/nonlinear/LevenbergMarquardtOptimizer.h>
+#include <gtsam/nonlinear/Marginals.h>
 
 #include <memory>
 
@@ -66,6 +67,26 @@ class B200GaussNewtonOptimizer : public gtsam::GaussNewtonOptimizer {
 
  private:
   void init();
+  std::shared_ptr<DeviceState> dev_;
+};
+
+/// Drop-in for gtsam::Marginals (gtsam/nonlinear/Marginals.h:31-100, CHOLESKY factorization): covariances of the
+/// graph linearised at `solution`, from the multifrontal factor kept on the device (one linearize + solve at
+/// construction of the first query; each query walks the clique path(s) from the variable(s) to the root).
+class B200Marginals {
+ public:
+  B200Marginals(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& solution, const gtsam::Ordering& ordering);
+  /// ordering = Ordering::Colamd(graph), as gtsam::Marginals(graph, solution) computes it (Marginals.cpp:30-36)
+  B200Marginals(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& solution);
+  /// Marginals::marginalCovariance, gtsam/nonlinear/Marginals.cpp:118-126
+  gtsam::Matrix marginalCovariance(gtsam::Key variable) const;
+  /// Marginals::marginalInformation, gtsam/nonlinear/Marginals.cpp:128-154
+  gtsam::Matrix marginalInformation(gtsam::Key variable) const;
+  /// JointMarginal::fullMatrix() of Marginals::jointMarginalCovariance: blocks in sorted-key order
+  /// (gtsam::JointMarginal's constructor is private to gtsam::Marginals, hence the plain matrix)
+  gtsam::Matrix jointMarginalCovariance(const gtsam::KeyVector& variables) const;
+
+ private:
   std::shared_ptr<DeviceState> dev_;
 };
 
