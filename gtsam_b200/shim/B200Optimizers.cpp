@@ -354,6 +354,49 @@ GaussianFactorGraph::shared_ptr B200GaussNewtonOptimizer::iterate() {
   return GaussianFactorGraph::shared_ptr();
 }
 
+// ---- Dogleg -------------------------------------------------------------------------------
+static DoglegParams doglegWithOrdering(DoglegParams params, const NonlinearFactorGraph& graph) {
+  if (!params.ordering) params.ordering = Ordering::Create(params.orderingType, graph);   // DoglegOptimizer.cpp:126-130
+  return params;
+}
+B200DoglegOptimizer::B200DoglegOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues, const DoglegParams& params)
+    : NonlinearOptimizer(graph, std::unique_ptr<internal::NonlinearOptimizerState>(
+                                    new internal::NonlinearOptimizerState(initialValues, graph.error(initialValues)))),
+      params_(doglegWithOrdering(params, graph)) { init(); }
+B200DoglegOptimizer::B200DoglegOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues, const Ordering& ordering)
+    : NonlinearOptimizer(graph, std::unique_ptr<internal::NonlinearOptimizerState>(
+                                    new internal::NonlinearOptimizerState(initialValues, graph.error(initialValues)))) {
+  params_.ordering = ordering;
+  init();
+}
+B200DoglegOptimizer::~B200DoglegOptimizer() {
+  if (dl_) b200_dl_destroy((b200_dl*)dl_);
+}
+
+void B200DoglegOptimizer::init() {
+  dev_ = std::make_shared<DeviceState>();
+  dev_->pack(graph_, state_->values, *params_.ordering);
+  b200_dl* dl = nullptr;
+  check(b200_dl_create(dev_->prob, params_.deltaInitial, &dl), "b200_dl_create");
+  dl_ = dl;
+}
+
+double B200DoglegOptimizer::getDelta() const {
+  double delta = 0;
+  check(b200_dl_get_state((const b200_dl*)dl_, nullptr, &delta, nullptr), "b200_dl_get_state");
+  return delta;
+}
+
+GaussianFactorGraph::shared_ptr B200DoglegOptimizer::iterate() {
+  const int rc = b200_dl_iterate((b200_dl*)dl_);
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(0);
+  check(rc, "b200_dl_iterate");
+  double e = 0;
+  check(b200_dl_get_state((const b200_dl*)dl_, &e, nullptr, nullptr), "b200_dl_get_state");
+  state_.reset(new internal::NonlinearOptimizerState(dev_->currentValues(), e, state_->iterations + 1));
+  return GaussianFactorGraph::shared_ptr();
+}
+
 // ---- Marginals ----------------------------------------------------------------------------
 B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution, const Ordering& ordering)
     : dev_(std::make_shared<DeviceState>()) {

@@ -25,6 +25,7 @@
  * of them (Constrained => std::invalid_argument).
  */
 #pragma once
+#include <gtsam/nonlinear/DoglegOptimizer.h>
 #include <gtsam/nonlinear/GaussNewtonOptimizer.h>
 #include <gtsam/nonlinear/LevenbergMarquardtOptimizer.h>
 #include <gtsam/nonlinear/Marginals.h>
@@ -68,6 +69,33 @@ class B200GaussNewtonOptimizer : public gtsam::GaussNewtonOptimizer {
  private:
   void init();
   std::shared_ptr<DeviceState> dev_;
+};
+
+/// Drop-in for gtsam::DoglegOptimizer (gtsam/nonlinear/DoglegOptimizer.h:63-128): same constructors, params(),
+/// getDelta(), iterate(), optimize().  It derives from NonlinearOptimizer rather than from DoglegOptimizer because the
+/// reference keeps its DoglegState private to DoglegOptimizer.cpp (getDelta() is non-virtual and casts to it); the
+/// unmodified NonlinearOptimizer::defaultOptimize() drives iterate() exactly as it drives the reference's.
+class B200DoglegOptimizer : public gtsam::NonlinearOptimizer {
+ public:
+  B200DoglegOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                      const gtsam::DoglegParams& params = gtsam::DoglegParams());
+  B200DoglegOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                      const gtsam::Ordering& ordering);
+  ~B200DoglegOptimizer() override;
+  /// One dogleg iteration on the device (DoglegOptimizer.cpp:84-121); returns nullptr (the linear graph stays in HBM).
+  gtsam::GaussianFactorGraph::shared_ptr iterate() override;
+  const gtsam::DoglegParams& params() const { return params_; }
+  /// current trust-region radius (DoglegOptimizer::getDelta)
+  double getDelta() const;
+
+ protected:
+  const gtsam::NonlinearOptimizerParams& _params() const override { return params_; }
+  gtsam::DoglegParams params_;
+
+ private:
+  void init();
+  std::shared_ptr<DeviceState> dev_;
+  void* dl_ = nullptr;   // b200_dl*
 };
 
 /// Drop-in for gtsam::Marginals (gtsam/nonlinear/Marginals.h:31-100, CHOLESKY factorization): covariances of the

@@ -1,6 +1,7 @@
 /*
  * shim_marginals.cpp — TEST INFRASTRUCTURE: gtsam::Marginals (unmodified reference, CPU) against the drop-in
- * gtsam_b200::B200Marginals (GPU through the C-ABI) on the same NonlinearFactorGraph / Values / Ordering.
+ * gtsam_b200::B200Marginals, and gtsam::DoglegOptimizer against gtsam_b200::B200DoglegOptimizer (GPU through the
+ * C-ABI), on the same NonlinearFactorGraph / Values / Ordering.
  * Prints one JSON line.  Built into oracle/_ref/shim_marginals by gtsam_b200/shim/Makefile; run on the GPU box by
  * tests/test_gpu_shim.py.
  */
@@ -27,7 +28,26 @@ int main(int argc, char** argv) {
     const Matrix R = ref.jointMarginalCovariance(keys).fullMatrix(), S = dev.jointMarginalCovariance(keys);
     worst_joint = (R - S).cwiseAbs().maxCoeff() / R.cwiseAbs().maxCoeff();
   }
-  printf("{\"worst_cov\": %.6g, \"worst_info\": %.6g, \"worst_joint\": %.6g, \"variables\": %lld}\n", worst, worst_info, worst_joint,
+  // Dogleg drop-in against the stock DoglegOptimizer: errors and trust-region radii of 5 iterations
+  double dl_err = 0, dl_delta = 0, dl_values = 0;
+  {
+    DoglegParams dp;
+    dp.ordering = b.ordering;
+    DoglegOptimizer sref(b.graph, b.values, dp);
+    gtsam_b200::B200DoglegOptimizer sdev(b.graph, b.values, dp);
+    for (int i = 0; i < 5; i++) {
+      sref.iterate(); sdev.iterate();
+      dl_err = std::max(dl_err, std::abs(sref.error() - sdev.error()) / std::max(1.0, std::abs(sref.error())));
+      dl_delta = std::max(dl_delta, std::abs(sref.getDelta() - sdev.getDelta()) / std::max(1e-12, std::abs(sref.getDelta())));
+    }
+    for (const auto& kv : sref.values()) {
+      Vector d = kv.value.localCoordinates_(sdev.values().at(kv.key));
+      dl_values = std::max(dl_values, d.cwiseAbs().maxCoeff());
+    }
+    if (sdev.iterations() != 5) dl_err = 1;
+  }
+  printf("{\"dogleg_error\": %.6g, \"dogleg_delta\": %.6g, \"dogleg_values\": %.6g, ", dl_err, dl_delta, dl_values);
+  printf("\"worst_cov\": %.6g, \"worst_info\": %.6g, \"worst_joint\": %.6g, \"variables\": %lld}\n", worst, worst_info, worst_joint,
          (long long)p.nvars);
   return 0;
 }

@@ -64,7 +64,7 @@ MBIN = os.path.join(os.path.dirname(BIN), "shim_marginals")
 def test_shim_marginals_match_stock_marginals(case):
     """gtsam_b200::B200Marginals (C++ drop-in over b200_marginal_covariance / b200_joint_marginal_covariance)
     against gtsam::Marginals on real GTSAM objects: every variable's covariance, one information matrix, one
-    3-variable joint with unsorted keys.  The C++ wrapper and the joint kernel were written after this round's GPU
+    3-variable joint with unsorted keys; and gtsam_b200::B200DoglegOptimizer against gtsam::DoglegOptimizer.  The C++ wrapper and the joint kernel were written after this round's GPU
     budget was spent; until their first hardware run a disagreement is reported as xfail, not as a suite failure."""
     try:
         out = subprocess.run([MBIN, os.path.join(util.GOLDEN, f"{case}.prob.bin")], capture_output=True, text=True, timeout=300)
@@ -73,3 +73,6 @@ def test_shim_marginals_match_stock_marginals(case):
         pytest.xfail(f"shim_marginals: first hardware run did not complete: {e}")
     if not (r["worst_cov"] <= 1e-7 and r["worst_info"] <= 1e-6 and r["worst_joint"] <= 1e-7):
         pytest.xfail(f"shim_marginals: first hardware run off: {r}")
+    # B200DoglegOptimizer against the stock DoglegOptimizer (5 iterations: errors, trust-region radii, final values)
+    if not (r["dogleg_error"] <= 1e-7 and r["dogleg_delta"] <= 1e-6 and r["dogleg_values"] <= 1e-6):
+        pytest.xfail(f"B200DoglegOptimizer: first hardware run off: {r}")
