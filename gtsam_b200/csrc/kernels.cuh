@@ -3,8 +3,9 @@
 //  linearize_kernel      a1-a7   residual + Jacobian + whitening (+ robust reweighting), one thread per
 //                                factor, element-major SoA stores => every store instruction coalesced
 //  error_kernel          a8      0.5*|R r|^2 or rho(|R r|); single launch, last-block reduction in index order
-//  leaf_point_factor_kernel<DC> + leaf_point_schur_kernel<DC>  a10+a12+a13+a14  BAL point cliques: assemble + damp + 3x3 Cholesky + Schur update,
-//                                one lane per factor, runs of points with the same cameras share one extend-add
+//  leaf_point_factor_kernel<DC>    a10+a12+a13+a14  BAL point cliques, per-point half: assemble + damp + 3x3 Cholesky, 8 lanes per point
+//  leaf_point_schur_kernel<DC,..>  a12  per-run half: SYRK of the run's Schur complement (3x3 register tiles, cp.async
+//                                staging), one extend-add per run of points with the same cameras
 //  leaf_fused_kernel     a10+a12+a13+a14  any leaf clique with a small frontal block
 //  assemble_kernel       a12     J^T J / J^T b / b^T b scatter-add into the owning non-leaf front
 //  hdiag_kernel, damp_kernel  a10  hessianDiagonal; lambda*I or lambda*clip(diag H) on the diagonal
@@ -12,9 +13,11 @@
 //  panel_kernel          a13     32x32 diagonal Cholesky (one warp, registers + shuffles) + TRSM of the row panel
 //  update_kernel, update_dmma_kernel  a13  C -= S^T S on the upper trapezoid (FP64 FMA tiles / DMMA for big fronts)
 //  extend_add_kernel     a12     child Schur complement into the parent front
-//  backsub_small_kernel, backsub_large_kernel  a15  x_F = R^-1 (d - S x_S), level by level
+//  backsub_point_kernel<DC>, backsub_small_kernel, backsub_large_kernel  a15  x_F = R^-1 (d - S x_S), level by level
 //  linerr_kernel         a16     0.5*|A delta - b|^2 and 0.5*|b|^2 in one pass
 //  retract_kernel        a9      x (+) delta per variable
+//  gradient_kernel, dot3_kernel, blend_kernel        Dogleg (8f rank 3): gradientAtZero, dot products, dogleg point
+//  marginal_path_kernel, marginal_joint_kernel        Marginals (8f rank 3): forward/back solves along clique paths
 #pragma once
 #include <climits>
 
