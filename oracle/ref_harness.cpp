@@ -14,6 +14,7 @@
 #include "problem_io.hpp"
 #include <gtsam/nonlinear/DoglegOptimizer.h>
 #include <gtsam/nonlinear/Marginals.h>
+#include <gtsam/nonlinear/GncOptimizer.h>
 #include <gtsam/slam/dataset.h>
 #include <gtsam/geometry/Pose2.h>
 #include <gtsam/sfm/SfmData.h>
@@ -214,6 +215,24 @@ static int cmd_marginals(const std::string& in, const std::string& outp) {
       for (int i = 0; i < S.rows(); i++) cov.push_back(S(i, j));   // column-major per variable, variables in id order
   }
   out.put("marg_cov", cov);
+  return 0;
+}
+
+static int cmd_gnc(const std::string& in, const std::string& outp, int loss) {
+  Prob p = load(in);
+  Built b = build(p);
+  Out out(outp);
+  LevenbergMarquardtParams lmp;
+  lmp.ordering = b.ordering;
+  GncParams<LevenbergMarquardtParams> gp(lmp);
+  gp.lossType = loss ? GncLossType::TLS : GncLossType::GM;
+  GncOptimizer<GncParams<LevenbergMarquardtParams>> gnc(b.graph, b.values, gp);
+  const Values result = gnc.optimize();
+  const Vector w = gnc.getWeights(), th = gnc.getInlierCostThresholds();
+  out.put("gnc_weights", std::vector<double>(w.data(), w.data() + w.size()));
+  out.put("gnc_barcsq", std::vector<double>(th.data(), th.data() + th.size()));
+  out.put("final_values", pack_values(p, b, result));
+  out.put("final_error", std::vector<double>{b.graph.error(result)});
   return 0;
 }
 
@@ -503,6 +522,7 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "dump" && argc >= 4) return cmd_dump(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0, argc > 5 && atoi(argv[5]));
   if (cmd == "lm" && argc >= 4) return cmd_lm(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 100, argc > 5 && atoi(argv[5]));
+  if (cmd == "gnc" && argc >= 5) return cmd_gnc(argv[2], argv[3], atoi(argv[4]));
   if (cmd == "jointmarg" && argc >= 5) return cmd_jointmarg(argv[2], argv[3], argc, argv);
   if (cmd == "marginals" && argc >= 4) return cmd_marginals(argv[2], argv[3]);
   if (cmd == "dogleg" && argc >= 4) return cmd_dogleg(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 5, argc > 5 ? atof(argv[5]) : 1.0);

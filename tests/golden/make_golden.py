@@ -99,6 +99,22 @@ def main():
     # BASELINE.json configs[0] (CPU plumbing): the reference's Pose2 g2o example path
     with open(os.path.join(HERE, "config1_pose2slam_g2o.json"), "w") as f:
         f.write(subprocess.check_output([H, "pose2", os.path.join(REF_DATA, "noisyToyGraph.txt")]).decode())
+    # GncOptimizer<GncParams<LevenbergMarquardtParams>> on graphs with injected outliers (TLS and GM)
+    rng = np.random.default_rng(5)
+    so = datasets.sphere(layers=5, per_ring=8, seed=31)
+    for i in rng.choice(np.arange(so.groups[0].count), size=4, replace=False):
+        mm = so.groups[0].meas[i].copy()
+        mm[9:12] += rng.normal(0, 8.0, 3)
+        mm[:9] = mm[:9].reshape(3, 3)[[1, 2, 0]].ravel()
+        so.groups[0].meas[i] = mm
+    so.save(os.path.join(HERE, "sphere_tiny_outliers.prob.bin"))
+    bo = datasets.make("bal_tiny", seed=41)
+    jdx = rng.choice(np.arange(bo.groups[0].count), size=6, replace=False)
+    bo.groups[0].meas[jdx] += rng.normal(0, 60.0, (6, 2))
+    bo.save(os.path.join(HERE, "bal_tiny_outliers.prob.bin"))
+    for case in ("sphere_tiny_outliers", "bal_tiny_outliers"):
+        for loss, nm in ((1, "tls"), (0, "gm")):
+            subprocess.check_call([H, "gnc", os.path.join(HERE, f"{case}.prob.bin"), os.path.join(HERE, f"{case}.gnc_{nm}.bin"), str(loss)])
     # joint marginals of a few variable sets (Marginals::jointMarginalCovariance)
     sys.path.insert(0, os.path.dirname(HERE))
     import util as _util

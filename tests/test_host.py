@@ -176,3 +176,42 @@ def test_bench_clock_sampler_region_filter():
     out = s.stop((t0 + 0.05, t0 + 0.25))
     assert out["in_region"] == 2 and out["samples"] == 2 and out["sm_mhz"] in (1950.0, 1965.0)
     assert out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965.0
+
+
+@pytest.mark.parametrize("case", ["sphere_tiny_outliers", "bal_tiny_outliers"])
+@pytest.mark.parametrize("loss", ["tls", "gm"])
+def test_gnc_host_logic_matches_reference(case, loss):
+    """gtsam_b200.gnc.GncOptimizer (host control logic of gtsam::GncOptimizer, GncOptimizer.h:184-468: weights,
+    weighted graph, mu schedule, convergence tests, chi-squared thresholds) driven by the CPU oracle as numeric backend,
+    against the unmodified reference's GncOptimizer<GncParams<LevenbergMarquardtParams>> on graphs with injected
+    outliers: identical weights and solution after 25-35 GNC iterations."""
+    import util
+    from gtsam_b200 import gnc
+    prob = util.load_case(case)
+    ref = util.golden(case, f"gnc_{loss}")
+    prm = gnc.GncParams()
+    prm.lossType = gnc.TLS if loss == "tls" else gnc.GM
+    opt = gnc.GncOptimizer(None, prob, prm, backend=util.OracleGncBackend(prm.baseOptimizerParams))
+    res = opt.optimize()
+    assert np.abs(opt.getInlierCostThresholds() - ref["gnc_barcsq"]).max() <= 1e-9
+    assert np.abs(opt.getWeights() - ref["gnc_weights"]).max() <= 1e-6
+    assert util.relmax(res, ref["final_values"]) <= 1e-7
+    assert len(opt.mu_history) > 5 and (opt.getWeights() < 0.5).sum() >= 4     # the injected outliers were rejected
+
+
+def test_gnc_weighted_problem_payloads():
+    """makeWeightedGraph on this library's noise payloads: sigma / sigmas scale by 1/sqrt(w), R by sqrt(w), w = 0 -> inf."""
+    import util
+    from gtsam_b200 import gnc, problem as Pm
+    prob = util.load_case("sphere_tiny_gaussian")
+    w = np.linspace(0.0, 1.0, prob.nfactors)
+    pw = gnc.weighted_problem(prob, w)
+    for g, h in zip(prob.groups, pw.groups):
+        d = Pm.FACTOR_DIM[g.type]
+        ww = w[gnc.graph_positions(g)]
+        if g.noise_kind == Pm.NOISE_GAUSSIAN:
+            assert np.allclose(h.noise.reshape(g.count, d * d), np.broadcast_to(g.noise.reshape(-1, d * d), (g.count, d * d)) * np.sqrt(ww)[:, None])
+        elif g.noise_kind == Pm.NOISE_DIAGONAL:
+            with np.errstate(divide="ignore"):
+                assert np.allclose(h.noise.reshape(g.count, d), np.broadcast_to(g.noise.reshape(-1, d), (g.count, d)) / np.sqrt(ww)[:, None])
+    assert pw.nfactors == prob.nfactors and np.array_equal(pw.values, prob.values)

@@ -156,3 +156,30 @@ def edge_case_problems():
 # variable sets of the joint-marginal fixtures (tests/golden/<case>.joint<i>.bin, written by make_golden.py)
 JOINT_SETS = {"bal_tiny_s2": [[0, 1], [3, 40], [2, 9, 55]], "sphere_tiny": [[0, 39], [5, 6, 7]],
               "bal_tiny_bundler": [[1, 30], [0, 4, 69]]}
+
+
+class OracleGncBackend:
+    """Numeric backend of gtsam_b200.gnc.GncOptimizer on the CPU oracle: lets the CPU tests check the GNC HOST LOGIC
+    (the product's control code) against traces of the unmodified reference without a GPU."""
+
+    def __init__(self, lm_params):
+        self.lm_params = lm_params
+
+    def factor_errors(self, prob, values):
+        from gtsam_b200 import gnc
+        from oracle import oracle_py as O
+        op = O.OracleProblem(prob)
+        op.set_values(values)
+        op.linearize()
+        out = np.zeros(prob.nfactors)
+        for gi, g in enumerate(prob.groups):
+            b = op.get_jacobians(gi)[:, :, -1]
+            out[gnc.graph_positions(g)] = 0.5 * np.sum(b * b, axis=1)
+        return out
+
+    def optimize(self, prob_w):
+        from oracle import oracle_py as O
+        op = O.OracleProblem(prob_w)
+        lm = op.lm(self.lm_params._c)
+        op.lm_optimize(lm)
+        return op.get_values(), lm.state.error
