@@ -71,6 +71,16 @@ class B200GaussNewtonOptimizer : public gtsam::GaussNewtonOptimizer {
   std::shared_ptr<DeviceState> dev_;
 };
 
+/// Parameter type that names the device LM as its optimizer, so the reference's own templates pick it up:
+///     gtsam::GncOptimizer<gtsam::GncParams<gtsam_b200::B200LevenbergMarquardtParams>> gnc(graph, initial, params);
+/// runs graduated non-convexity (gtsam/nonlinear/GncOptimizer.h:184-268) with every weighted LM solve on the B200
+/// (BaseOptimizer = GncParameters::OptimizerType, GncOptimizer.h:47, GncParams.h:44).
+struct B200LevenbergMarquardtParams : public gtsam::LevenbergMarquardtParams {
+  typedef B200LevenbergMarquardtOptimizer OptimizerType;
+  B200LevenbergMarquardtParams() = default;
+  B200LevenbergMarquardtParams(const gtsam::LevenbergMarquardtParams& p) : gtsam::LevenbergMarquardtParams(p) {}
+};
+
 /// Drop-in for gtsam::DoglegOptimizer (gtsam/nonlinear/DoglegOptimizer.h:63-128): same constructors, params(),
 /// getDelta(), iterate(), optimize().  It derives from NonlinearOptimizer rather than from DoglegOptimizer because the
 /// reference keeps its DoglegState private to DoglegOptimizer.cpp (getDelta() is non-virtual and casts to it); the

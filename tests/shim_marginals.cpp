@@ -8,8 +8,10 @@
 #include "../oracle/problem_io.hpp"
 #include "../gtsam_b200/shim/B200Optimizers.h"
 
+#include <gtsam/nonlinear/GncOptimizer.h>
+
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: shim_marginals problem.bin\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: shim_marginals problem.bin [run_gnc]\n"); return 2; }
   Prob p = load(argv[1]);
   Built b = build(p);
   Marginals ref(b.graph, b.values, b.ordering, Marginals::CHOLESKY);
@@ -46,7 +48,23 @@ int main(int argc, char** argv) {
     }
     if (sdev.iterations() != 5) dl_err = 1;
   }
-  printf("{\"dogleg_error\": %.6g, \"dogleg_delta\": %.6g, \"dogleg_values\": %.6g, ", dl_err, dl_delta, dl_values);
+  // the reference's own GncOptimizer template with the device LM plugged in through the params type
+  double gnc_w = -1, gnc_v = -1;
+  if (argc > 2 && atoi(argv[2])) {
+    LevenbergMarquardtParams lmp;
+    lmp.ordering = b.ordering;
+    GncParams<LevenbergMarquardtParams> gp(lmp);
+    GncOptimizer<GncParams<LevenbergMarquardtParams>> gref(b.graph, b.values, gp);
+    const Values rref = gref.optimize();
+    GncParams<gtsam_b200::B200LevenbergMarquardtParams> gd{gtsam_b200::B200LevenbergMarquardtParams(lmp)};
+    GncOptimizer<GncParams<gtsam_b200::B200LevenbergMarquardtParams>> gdev(b.graph, b.values, gd);
+    const Values rdev = gdev.optimize();
+    gnc_w = (gref.getWeights() - gdev.getWeights()).cwiseAbs().maxCoeff();
+    gnc_v = 0;
+    for (const auto& kv : rref) gnc_v = std::max(gnc_v, kv.value.localCoordinates_(rdev.at(kv.key)).cwiseAbs().maxCoeff());
+  }
+  printf("{\"gnc_weights\": %.6g, \"gnc_values\": %.6g, ", gnc_w, gnc_v);
+  printf("\"dogleg_error\": %.6g, \"dogleg_delta\": %.6g, \"dogleg_values\": %.6g, ", dl_err, dl_delta, dl_values);
   printf("\"worst_cov\": %.6g, \"worst_info\": %.6g, \"worst_joint\": %.6g, \"variables\": %lld}\n", worst, worst_info, worst_joint,
          (long long)p.nvars);
   return 0;
