@@ -49,6 +49,13 @@ static GroupView view(const b200_problem::Group& g) {
   v.J = g.d_J; v.scat = g.d_scat;
   return v;
 }
+static JacobianView jview(const b200_problem::Group& g) {
+  JacobianView v;
+  v.count = (int)g.count; v.rows = g.d; v.arity = g.arity; v.ncols = g.ncols;
+  for (int a = 0; a < B200_JACOBIAN_MAX_ARITY + 2; a++) v.col0[a] = g.col0[a];
+  v.keys = g.d_jkeys; v.slots = g.d_jslots; v.clique = g.d_jclique; v.J = g.d_J;
+  return v;
+}
 static TreeView tview(const b200_problem* p) {
   TreeView t;
   t.arena = p->d_arena; t.off = p->d_off; t.nf = p->d_nf; t.ns = p->d_ns; t.parent = p->d_parent; t.ld = p->d_ld;
@@ -142,6 +149,7 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
 }
 
 static int enqueue_linearize(b200_problem* p) {
+  if (p->linear) return B200_OK;   // a linear problem is its own linearization (b200_linear_create / b200_linear_update)
   cudaStream_t st = p->ctx->stream;
   for (auto& g : p->groups) {
     if (!g.count) continue;
@@ -162,7 +170,8 @@ static int enqueue_hdiag(b200_problem* p) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = (int)((g.count + 127) / 128);
-    DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag)));
+    if (g.type == B200_FACTOR_JACOBIAN) launch_k(hdiag_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, p->d_hdiag);
+    else DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag)));
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
@@ -184,7 +193,8 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     for (auto& g : p->groups) {
       if (!g.n_nonleaf) continue;   // every factor of the group is owned by a fused leaf clique
       const int nb = (int)((g.count + 127) / 128);
-      DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), t)));
+      if (g.type == B200_FACTOR_JACOBIAN) launch_k(assemble_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), t);
+      else DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), t)));
       ctx->launches++;
     }
   }
@@ -339,6 +349,10 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
+    if (g.type == B200_FACTOR_JACOBIAN)
+      launch_k(linerr_jacobian_kernel, dim3(nb), dim3(256), 0, st, jview(g), (const double*)p->d_delta, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1,
+               &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0);
+    else
     DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
                                                                  &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0)));
     ctx->launches += 1;
@@ -397,18 +411,40 @@ static int solve_status(const b200_problem* p, int64_t* fail_var) {
 // Validation of a problem description + the symbolic phase.  Host only: needs
 // no GPU, so it is also exposed through b200_symbolic_create for CPU tests.
 struct PackedGroup {
-  int type, noise_kind, per_factor, noise_size, d, ncols, arity, meas, robust_kind;
-  double robust_param;
+  int type, noise_kind = 0, per_factor = 0, noise_size = 0, d, ncols, arity, meas = 0, robust_kind = 0;
+  double robust_param = 0;
   int64_t count;
   std::vector<int64_t> pos;   // graph position of every factor of the group
+  int dims[B200_JACOBIAN_MAX_ARITY] = {0};   // block widths (groups of a linear problem)
 };
 struct Packed {
   std::vector<int> val_off, var_dof, var_dim;
-  std::vector<int64_t> fkey0, fkey1;
+  std::vector<int64_t> fptr, fkeys;   // CSR of the keys of every factor by graph position
   std::vector<PackedGroup> groups;
   int64_t total = 0;
   Symbolic sym;
 };
+// graph positions of a group (explicit list, or a consecutive run) + overlap / range checks
+static int resolve_positions(int64_t count, const int64_t* graph_index, int64_t graph_index0, int64_t total, int64_t* next,
+                             std::vector<char>* used, std::vector<int64_t>* pos) {
+  if (count < 0) { set_error("negative factor count"); return B200_INVALID_ARGUMENT; }
+  if (count > INT_MAX / 2) { set_error("factor group too large"); return B200_INVALID_ARGUMENT; }
+  pos->resize(count);
+  if (graph_index) {
+    for (int64_t i = 0; i < count; i++) (*pos)[i] = graph_index[i];
+  } else {
+    const int64_t gi0 = graph_index0 < 0 ? *next : graph_index0;
+    for (int64_t i = 0; i < count; i++) (*pos)[i] = gi0 + i;
+    *next = gi0 + count;
+  }
+  for (int64_t i = 0; i < count; i++) {
+    const int64_t q = (*pos)[i];
+    if (q < 0 || q >= total) { set_error("graph position out of range"); return B200_INVALID_ARGUMENT; }
+    if ((*used)[q]) { set_error("overlapping graph positions"); return B200_INVALID_ARGUMENT; }
+    (*used)[q] = 1;
+  }
+  return B200_OK;
+}
 static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
 #define FAIL(code, msg) do { set_error(msg); return code; } while (0)
   if (!d || d->nvars < 0 || d->ngroups < 0) FAIL(B200_INVALID_ARGUMENT, "bad problem description");
@@ -422,15 +458,26 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
     pk->var_dof[v + 1] = pk->var_dof[v] + VAR_DIM[t];
   }
   int64_t total = 0, next = 0;
-  for (int64_t g = 0; g < d->ngroups; g++) total += d->groups[g].count;
+  for (int64_t g = 0; g < d->ngroups; g++) {
+    if (d->groups[g].count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
+    total += d->groups[g].count;
+  }
   pk->total = total;
-  pk->fkey0.assign(total, -1); pk->fkey1.assign(total, -1);
   std::vector<char> used(total, 0);
   pk->groups.resize(d->ngroups);
+  pk->fptr.assign(total + 1, 0);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {   // pass 1: graph positions and arities -> CSR offsets
+    const b200_factor_group& s = d->groups[gi];
+    if (s.type < 0 || s.type >= B200_NUM_FACTOR_TYPES) FAIL(B200_UNSUPPORTED_FACTOR, "unsupported factor type");
+    const int rc = resolve_positions(s.count, s.graph_index, s.graph_index0, total, &next, &used, &pk->groups[gi].pos);
+    if (rc) return rc;
+    for (int64_t i = 0; i < s.count; i++) pk->fptr[pk->groups[gi].pos[i] + 1] = F_ARITY[s.type];
+  }
+  for (int64_t i = 0; i < total; i++) pk->fptr[i + 1] += pk->fptr[i];
+  pk->fkeys.assign(pk->fptr[total], -1);
   for (int64_t gi = 0; gi < d->ngroups; gi++) {
     const b200_factor_group& s = d->groups[gi];
     PackedGroup& g = pk->groups[gi];
-    if (s.type < 0 || s.type >= B200_NUM_FACTOR_TYPES) FAIL(B200_UNSUPPORTED_FACTOR, "unsupported factor type");
     g.type = s.type; g.noise_kind = s.noise_kind; g.per_factor = s.noise_per_factor; g.count = s.count;
     g.d = F_DIM[s.type]; g.arity = F_ARITY[s.type]; g.meas = F_MEAS[s.type];
     g.ncols = VAR_DIM[F_VT[s.type][0]] + (g.arity == 2 ? VAR_DIM[F_VT[s.type][1]] : 0) + 1;
@@ -441,27 +488,13 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
       FAIL(B200_UNSUPPORTED_NOISE, "unknown robust loss or non-positive parameter");
     if (s.robust_kind && s.type == B200_FACTOR_SFM_BUNDLER)
       FAIL(B200_UNSUPPORTED_NOISE, "GeneralSFMFactor::linearize whitens without reweighting: Robust models are not supported on it");
-    if (s.count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
-    g.pos.resize(s.count);
-    if (s.graph_index) {
-      for (int64_t i = 0; i < s.count; i++) g.pos[i] = s.graph_index[i];
-    } else {
-      const int64_t gi0 = s.graph_index0 < 0 ? next : s.graph_index0;
-      for (int64_t i = 0; i < s.count; i++) g.pos[i] = gi0 + i;
-      next = gi0 + s.count;
-    }
-    if (s.count > INT_MAX / 2) FAIL(B200_INVALID_ARGUMENT, "factor group too large");
     for (int64_t i = 0; i < s.count; i++) {
-      if (g.pos[i] < 0 || g.pos[i] >= total) FAIL(B200_INVALID_ARGUMENT, "graph position out of range");
-      if (used[g.pos[i]]) FAIL(B200_INVALID_ARGUMENT, "overlapping graph positions");
-      used[g.pos[i]] = 1;
       for (int a = 0; a < g.arity; a++) {
         const int64_t k = s.keys[i * g.arity + a];
         if (k < 0 || k >= n || d->var_type[k] != F_VT[s.type][a])
           FAIL(B200_INVALID_ARGUMENT, "factor key missing or of the wrong value type (ValuesKeyDoesNotExist / ValuesIncorrectType)");
+        pk->fkeys[pk->fptr[g.pos[i]] + a] = k;
       }
-      pk->fkey0[g.pos[i]] = s.keys[i * g.arity];
-      if (g.arity == 2) pk->fkey1[g.pos[i]] = s.keys[i * g.arity + 1];
     }
     if (s.type == B200_FACTOR_PROJECTION_CAL3S2) {
       if (d->ncal < 1) FAIL(B200_INVALID_ARGUMENT, "projection factors need a calibration");
@@ -471,7 +504,65 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
     }
   }
   const char* serr = "";
-  if (!build_symbolic(n, pk->var_dim.data(), d->ordering, total, pk->fkey0.data(), pk->fkey1.data(), &pk->sym, &serr))
+  if (!build_symbolic(n, pk->var_dim.data(), d->ordering, total, pk->fptr.data(), pk->fkeys.data(), &pk->sym, &serr))
+    FAIL(B200_INVALID_ARGUMENT, serr);
+  return B200_OK;
+}
+
+// The same for a linear description (b200_linear_create): JacobianFactor groups of any arity.
+static int pack_linear(const b200_linear_desc* d, Packed* pk) {
+  if (!d || d->nvars < 0 || d->ngroups < 0) FAIL(B200_INVALID_ARGUMENT, "bad linear description");
+  const int64_t n = d->nvars;
+  pk->val_off.assign(n + 1, 0); pk->var_dof.assign(n + 1, 0); pk->var_dim.assign(n, 0);
+  for (int64_t v = 0; v < n; v++) {
+    if (d->var_dim[v] < 1) FAIL(B200_INVALID_ARGUMENT, "variable dimension < 1");
+    pk->var_dim[v] = d->var_dim[v];
+    if ((int64_t)pk->var_dof[v] + d->var_dim[v] > INT_MAX / 2) FAIL(B200_INVALID_ARGUMENT, "total dimension too large");
+    pk->var_dof[v + 1] = pk->var_dof[v] + d->var_dim[v];
+  }
+  int64_t total = 0, next = 0;
+  for (int64_t g = 0; g < d->ngroups; g++) {
+    if (d->groups[g].count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
+    total += d->groups[g].count;
+  }
+  pk->total = total;
+  std::vector<char> used(total, 0);
+  pk->groups.resize(d->ngroups);
+  pk->fptr.assign(total + 1, 0);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+    const b200_jacobian_group& s = d->groups[gi];
+    PackedGroup& g = pk->groups[gi];
+    if (s.arity < 1 || s.arity > B200_JACOBIAN_MAX_ARITY) FAIL(B200_UNSUPPORTED_FACTOR, "JacobianFactor arity outside 1..B200_JACOBIAN_MAX_ARITY");
+    if (s.rows < 0) FAIL(B200_INVALID_ARGUMENT, "negative row count");
+    g.type = B200_FACTOR_JACOBIAN; g.d = s.rows; g.arity = s.arity; g.count = s.count;
+    g.ncols = 1;
+    for (int a = 0; a < s.arity; a++) {
+      if (s.dims[a] < 1) FAIL(B200_INVALID_ARGUMENT, "block width < 1");
+      g.dims[a] = s.dims[a];
+      g.ncols += s.dims[a];
+    }
+    const int rc = resolve_positions(s.count, s.graph_index, s.graph_index0, total, &next, &used, &g.pos);
+    if (rc) return rc;
+    for (int64_t i = 0; i < s.count; i++) pk->fptr[g.pos[i] + 1] = s.arity;
+    if (s.sigmas)
+      for (int64_t i = 0; i < s.count * s.rows; i++)
+        if (!(s.sigmas[i] > 0)) FAIL(B200_UNSUPPORTED_NOISE, "sigma <= 0: Constrained noise models need QR elimination (out of scope)");
+  }
+  for (int64_t i = 0; i < total; i++) pk->fptr[i + 1] += pk->fptr[i];
+  pk->fkeys.assign(pk->fptr[total], -1);
+  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+    const b200_jacobian_group& s = d->groups[gi];
+    const PackedGroup& g = pk->groups[gi];
+    for (int64_t i = 0; i < s.count; i++)
+      for (int a = 0; a < s.arity; a++) {
+        const int64_t k = s.keys[i * s.arity + a];
+        if (k < 0 || k >= n) FAIL(B200_INVALID_ARGUMENT, "JacobianFactor key out of range");
+        if (d->var_dim[k] != s.dims[a]) FAIL(B200_INVALID_ARGUMENT, "JacobianFactor block width differs from the variable's dimension");
+        pk->fkeys[pk->fptr[g.pos[i]] + a] = k;
+      }
+  }
+  const char* serr = "";
+  if (!build_symbolic(n, pk->var_dim.data(), d->ordering, total, pk->fptr.data(), pk->fkeys.data(), &pk->sym, &serr))
     FAIL(B200_INVALID_ARGUMENT, serr);
 #undef FAIL
   return B200_OK;
@@ -487,8 +578,10 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
 // in clique order by prefix weight (keeps neighbouring leaves, and their shared separators,
 // together).  Factors follow the clique that owns them; factors of top cliques belong to rank 0.
 static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int world, std::vector<char>* fused,
-                       std::vector<char>* is_top, std::vector<int>* clique_owner, std::vector<int>* factor_owner) {
-  const bool leaf_path = ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
+                       std::vector<char>* is_top, std::vector<int>* clique_owner, std::vector<int>* factor_owner,
+                       bool allow_leaf = true) {
+  // the fused leaf kernels evaluate typed factor groups: never for the JacobianFactor groups of a linear problem
+  const bool leaf_path = allow_leaf && ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
   const int64_t nc = S.ncliques;
   fused->assign(nc, 0);
   for (int64_t c = 0; c < nc; c++) {
@@ -718,6 +811,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaStreamSynchronize(p->ctx->stream);
   for (auto& g : p->groups) {
     cudaFree(g.d_keys); cudaFree(g.d_meas); cudaFree(g.d_noise); cudaFree(g.d_cal); cudaFree(g.d_body); cudaFree(g.d_J); cudaFree(g.d_scat);
+    cudaFree(g.d_jkeys); cudaFree(g.d_jslots); cudaFree(g.d_jclique);
   }
   cudaFree(p->d_values); cudaFree(p->d_new_values); cudaFree(p->d_delta); cudaFree(p->d_hdiag);
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
@@ -735,49 +829,61 @@ int b200_problem_destroy(b200_problem* p) {
   return B200_OK;
 }
 
-int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem** out) {
-  if (!ctx || !d || !out) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const double* Ab, const double* sigmas);
+
+// Problem creation, shared by the two descriptions: `d` (nonlinear graph + Values, b200_problem_create) or
+// `ld` (JacobianFactors, b200_linear_create); exactly one of them is non-null.
+static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_linear_desc* ld, b200_problem** out) {
+  if (!ctx || (!d && !ld) || !out) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  if (ld && ctx->world > 1) { set_error("linear problems are single-GPU: create them on a context without a communicator"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   b200_problem* p = new b200_problem();
   p->ctx = ctx;
+  p->linear = ld != nullptr;
 #define FAIL(code, msg) do { set_error(msg); b200_problem_destroy(p); return code; } while (0)
   Packed pk;
   {
-    const int rc = pack_and_symbolic(d, &pk);
+    const int rc = d ? pack_and_symbolic(d, &pk) : pack_linear(ld, &pk);
     if (rc) { b200_problem_destroy(p); return rc; }
   }
-  const int64_t n = d->nvars;
+  const int64_t n = d ? d->nvars : ld->nvars;
+  const int64_t ngroups = d ? d->ngroups : ld->ngroups;
   const int64_t total = pk.total;
   p->nvars = n; p->nval = pk.val_off[n]; p->ndelta = pk.var_dof[n]; p->nfactors = total;
-  p->var_type.assign(d->var_type, d->var_type + n);
+  if (d) p->var_type.assign(d->var_type, d->var_type + n);
   std::vector<int>&val_off = pk.val_off, &var_dof = pk.var_dof, &var_dim = pk.var_dim;
-  std::vector<int64_t>&fkey0 = pk.fkey0, &fkey1 = pk.fkey1;
-  p->groups.resize(d->ngroups);
-  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+  std::vector<int64_t>&fptr = pk.fptr, &fkeys = pk.fkeys;
+  p->groups.resize(ngroups);
+  for (int64_t gi = 0; gi < ngroups; gi++) {
     auto& g = p->groups[gi];
     const PackedGroup& q = pk.groups[gi];
     g.type = q.type; g.noise_kind = q.noise_kind; g.per_factor = q.per_factor; g.noise_size = q.noise_size;
     g.d = q.d; g.ncols = q.ncols; g.arity = q.arity; g.meas = q.meas; g.count = q.count; g.pos = q.pos;
     g.robust_kind = q.robust_kind; g.robust_param = q.robust_param;
+    g.col0[0] = 0;
+    for (int a = 0; a < B200_JACOBIAN_MAX_ARITY; a++) g.col0[a + 1] = g.col0[a] + (a < q.arity ? q.dims[a] : 0);
+    g.col0[q.arity + 1] = g.col0[q.arity] + 1;   // the rhs column closes the list
   }
   p->sym = std::move(pk.sym);
   const Symbolic& S = p->sym;
 #define UP(call) do { int rc_ = (call); if (rc_) { b200_problem_destroy(p); return rc_; } } while (0)
   // ---- values & variable tables ----
-  UP(upload(&p->d_values, d->values, (size_t)p->nval, st));
-  B200_CUDA(cudaMalloc((void**)&p->d_new_values, std::max<int64_t>(1, p->nval) * sizeof(double)));
+  if (d) {
+    UP(upload(&p->d_values, d->values, (size_t)p->nval, st));
+    B200_CUDA(cudaMalloc((void**)&p->d_new_values, std::max<int64_t>(1, p->nval) * sizeof(double)));
+    UP(upload(&p->d_val_off, val_off, st));
+    UP(upload(&p->d_var_type, p->var_type, st));
+    UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
+  }
   B200_CUDA(cudaMalloc((void**)&p->d_delta, std::max<int64_t>(1, p->ndelta) * sizeof(double)));
   B200_CUDA(cudaMemsetAsync(p->d_delta, 0, std::max<int64_t>(1, p->ndelta) * sizeof(double), st));
   B200_CUDA(cudaMalloc((void**)&p->d_hdiag, std::max<int64_t>(1, p->ndelta) * sizeof(double)));
-  UP(upload(&p->d_val_off, val_off, st));
   UP(upload(&p->d_var_dof, var_dof, st));
-  UP(upload(&p->d_var_type, p->var_type, st));
-  UP(upload(&p->d_cal, d->cal, (size_t)d->ncal * 5, st));
   // ---- storage plan: fused leaf cliques keep only their f x n conditional; sharding -----
   std::vector<char> fused, is_top;
   std::vector<int> clique_owner, factor_owner;
-  shard_plan(S, d->ngroups, total, ctx->world, &fused, &is_top, &clique_owner, &factor_owner);
+  shard_plan(S, ngroups, total, ctx->world, &fused, &is_top, &clique_owner, &factor_owner, /*allow_leaf=*/d != nullptr);
   const int rank = ctx->rank;
   std::vector<int> fused_list;   // the fused leaf cliques THIS rank owns
   for (int64_t c = 0; c < S.ncliques; c++)
@@ -809,7 +915,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     // distinct cameras) take leaf_point_{factor,schur}_kernel<6>/<9>; everything else the generic leaf kernel
     std::vector<int> cf_count(S.ncliques, 0), cf_mask(S.ncliques, 0);
     std::vector<int>& kind = leaf_kind;
-    for (int64_t gi = 0; gi < d->ngroups; gi++)
+    for (int64_t gi = 0; d && gi < d->ngroups; gi++)
       for (int64_t i = 0; i < d->groups[gi].count; i++) {
         const int c = S.fac_clique[p->groups[gi].pos[i]];
         if (fused[c]) { cf_count[c]++; cf_mask[c] |= 1 << d->groups[gi].type; }
@@ -882,9 +988,31 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     p->h_off[S.ncliques] = o;
   }
   // ---- factor tables ----
-  std::vector<std::vector<int2>> hkeys(d->ngroups);
-  std::vector<std::vector<int4>> hscat(d->ngroups);
-  for (int64_t gi = 0; gi < d->ngroups; gi++) {
+  std::vector<std::vector<int2>> hkeys(ngroups);
+  std::vector<std::vector<int4>> hscat(ngroups);
+  for (int64_t gi = 0; ld && gi < ngroups; gi++) {
+    // JacobianFactor groups: keys, owning clique and front slot of every key, then the whitened [A|b] (SoA)
+    const b200_jacobian_group& s = ld->groups[gi];
+    auto& g = p->groups[gi];
+    std::vector<int> jkeys((size_t)s.count * s.arity), jslots((size_t)s.count * s.arity), jclique((size_t)s.count);
+    g.local_index.resize(s.count);
+    for (int64_t i = 0; i < s.count; i++) {
+      const int64_t pos = g.pos[i];
+      g.local_index[i] = i;
+      jclique[i] = S.fac_clique[pos];
+      for (int a = 0; a < s.arity; a++) {
+        jkeys[(size_t)i * s.arity + a] = (int)fkeys[fptr[pos] + a];
+        jslots[(size_t)i * s.arity + a] = S.fac_slots[fptr[pos] + a];
+      }
+    }
+    g.n_nonleaf = s.count;
+    UP(upload(&g.d_jkeys, jkeys, st));
+    UP(upload(&g.d_jslots, jslots, st));
+    UP(upload(&g.d_jclique, jclique, st));
+    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)s.count * g.d * g.ncols) * sizeof(double)));
+    UP(upload_jacobian_group(p, g, s.Ab, s.sigmas));
+  }
+  for (int64_t gi = 0; d && gi < ngroups; gi++) {
     const b200_factor_group& s = d->groups[gi];
     auto& g = p->groups[gi];
     // keep only the factors this rank owns (all of them when world == 1)
@@ -898,7 +1026,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     if (s.noise_per_factor) hnoise.resize((size_t)nl * g.noise_size);
     for (int64_t li = 0; li < nl; li++) {
       const int64_t i = keep[li], pos = g.pos[i];
-      hkeys[gi][li] = make_int2((int)fkey0[pos], (int)fkey1[pos]);
+      hkeys[gi][li] = make_int2((int)fkeys[fptr[pos]], g.arity == 2 ? (int)fkeys[fptr[pos] + 1] : -1);
       const int isleaf = fused[S.fac_clique[pos]];
       hscat[gi][li] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
       if (!isleaf) g.n_nonleaf++;
@@ -945,7 +1073,7 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
     for (int i = 0; i < p->n_fused; i++) fptr[i + 1] += fptr[i];
     std::vector<int2> ffac(fptr[p->n_fused]);
     std::vector<int> cur(fptr.begin(), fptr.end() - 1);
-    for (int64_t gi = 0; gi < d->ngroups; gi++)
+    for (int64_t gi = 0; gi < ngroups; gi++)
       for (int64_t li = 0; li < p->groups[gi].count; li++) {
         const int64_t pos = p->groups[gi].pos[p->groups[gi].local_index[li]];
         if (lpos[S.fac_clique[pos]] >= 0) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)li);
@@ -1040,12 +1168,58 @@ int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem*
   B200_CUDA(cudaMalloc((void**)&p->d_lambda, sizeof(double)));
   B200_CUDA(cudaMemsetAsync(p->d_lambda, 0, sizeof(double), st));
   B200_CUDA(cudaMallocHost((void**)&p->h_lambda, sizeof(double)));
-  B200_CUDA(cudaMallocHost((void**)&p->h_pinned, std::max<int64_t>(1, std::max(p->nval, p->ndelta)) * sizeof(double)));
+  B200_CUDA(cudaMallocHost((void**)&p->h_pinned, std::max<int64_t>(81, std::max(p->nval, p->ndelta)) * sizeof(double)));   // >= 9 x 9: one marginal covariance
   B200_CUDA(cudaStreamSynchronize(st));
 #undef FAIL
 #undef UP
+  p->linearized = p->linear;   // a linear problem IS its linearization
   *out = p;
   return B200_OK;
+}
+
+// [A|b] blocks as the caller holds them (factor-major, column-major blocks) -> staging buffer -> whitened SoA
+static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const double* Ab, const double* sigmas) {
+  cudaStream_t st = p->ctx->stream;
+  const size_t per = (size_t)g.d * g.ncols, nel = per * (size_t)g.count;
+  if (!nel) return B200_OK;
+  if (!Ab) { set_error("JacobianFactor group without [A|b] data"); return B200_INVALID_ARGUMENT; }
+  double *d_stage = nullptr, *d_sig = nullptr;
+  B200_CUDA(cudaMalloc((void**)&d_stage, nel * sizeof(double)));
+  cudaError_t ce = cudaMemcpyAsync(d_stage, Ab, nel * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && sigmas) {
+    ce = cudaMalloc((void**)&d_sig, (size_t)g.count * g.d * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_sig, sigmas, (size_t)g.count * g.d * sizeof(double), cudaMemcpyHostToDevice, st);
+  }
+  if (ce == cudaSuccess) {
+    const int nb = (int)std::min<int64_t>(((int64_t)nel + 255) / 256, (int64_t)p->ctx->sm_count * 16);
+    jacobian_load_kernel<<<nb, 256, 0, st>>>(d_stage, d_sig, g.d, g.ncols, (int)g.count, g.d_J);
+    p->ctx->launches++;
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // the caller's buffers and the staging copies die with this call
+  cudaFree(d_stage); cudaFree(d_sig);
+  if (ce != cudaSuccess) { set_error(std::string("upload_jacobian_group: ") + cudaGetErrorString(ce)); return B200_CUDA_ERROR; }
+  return B200_OK;
+}
+
+int b200_problem_create(b200_ctx* ctx, const b200_problem_desc* d, b200_problem** out) {
+  if (!d) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  return create_problem(ctx, d, nullptr, out);
+}
+int b200_linear_create(b200_ctx* ctx, const b200_linear_desc* d, b200_problem** out) {
+  if (!d) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  return create_problem(ctx, nullptr, d, out);
+}
+int b200_linear_update(b200_problem* p, int64_t gi, const double* Ab, const double* sigmas) {
+  if (!p || !p->linear) { set_error("b200_linear_update: not a linear problem"); return B200_INVALID_ARGUMENT; }
+  if (gi < 0 || gi >= (int64_t)p->groups.size()) { set_error("group out of range"); return B200_INVALID_ARGUMENT; }
+  auto& g = p->groups[gi];
+  if (sigmas)
+    for (int64_t i = 0; i < g.count * g.d; i++)
+      if (!(sigmas[i] > 0)) { set_error("sigma <= 0: Constrained noise models need QR elimination (out of scope)"); return B200_UNSUPPORTED_NOISE; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  p->solved = p->factored = p->marg_ready = false;
+  return upload_jacobian_group(p, g, Ab, sigmas);
 }
 
 int64_t b200_values_size(const b200_problem* p) { return p->nval; }
@@ -1060,6 +1234,7 @@ static bool is_pinned_host(const void* ptr) {
 }
 
 int b200_set_values(b200_problem* p, const double* v) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   const size_t bytes = (size_t)p->nval * sizeof(double);
   const void* src = v;
@@ -1070,6 +1245,7 @@ int b200_set_values(b200_problem* p, const double* v) {
   return B200_OK;
 }
 int b200_get_values(b200_problem* p, double* v) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   const size_t bytes = (size_t)p->nval * sizeof(double);
   const bool direct = is_pinned_host(v);
@@ -1080,6 +1256,7 @@ int b200_get_values(b200_problem* p, double* v) {
 }
 
 int b200_error(b200_problem* p, double* err) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   int rc = enqueue_error(p, p->d_values, &p->d_scalars->error);
   if (rc) return rc;
@@ -1090,6 +1267,7 @@ int b200_error(b200_problem* p, double* err) {
 }
 
 int b200_linearize(b200_problem* p) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   return enqueue_linearize(p);
 }
@@ -1147,6 +1325,7 @@ int b200_get_delta(b200_problem* p, double* out) {
 }
 
 int b200_try_step(b200_problem* p, double* new_error) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   if (!p->solved) { set_error("b200_try_step before b200_solve"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   int rc = enqueue_try_step(p);
@@ -1158,6 +1337,7 @@ int b200_try_step(b200_problem* p, double* new_error) {
 }
 
 int b200_accept_step(b200_problem* p) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   // copy, not pointer swap: the captured CUDA graph of the LM try has the buffer roles baked in
   B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_new_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
@@ -1167,12 +1347,14 @@ int b200_accept_step(b200_problem* p) {
 
 /* device-side snapshot / restore of Values (benchmarks: reset without host traffic) */
 int b200_save_values(b200_problem* p) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   if (!p->d_saved_values) B200_CUDA(cudaMalloc((void**)&p->d_saved_values, std::max<int64_t>(1, p->nval) * sizeof(double)));
   B200_CUDA(cudaMemcpyAsync(p->d_saved_values, p->d_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
   return B200_OK;
 }
 int b200_restore_values(b200_problem* p) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   if (!p->d_saved_values) { set_error("b200_restore_values before b200_save_values"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   B200_CUDA(cudaMemcpyAsync(p->d_values, p->d_saved_values, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
@@ -1238,6 +1420,16 @@ struct b200_symbolic { Symbolic sym; int64_t ndelta; };
 int b200_symbolic_create(const b200_problem_desc* d, b200_symbolic** out) {
   Packed pk;
   const int rc = pack_and_symbolic(d, &pk);
+  if (rc) return rc;
+  b200_symbolic* s = new b200_symbolic();
+  s->ndelta = pk.var_dof[d->nvars];
+  s->sym = std::move(pk.sym);
+  *out = s;
+  return B200_OK;
+}
+int b200_linear_symbolic_create(const b200_linear_desc* d, b200_symbolic** out) {
+  Packed pk;
+  const int rc = pack_linear(d, &pk);
   if (rc) return rc;
   b200_symbolic* s = new b200_symbolic();
   s->ndelta = pk.var_dof[d->nvars];
@@ -1318,6 +1510,7 @@ int b200_lm_reset(b200_lm* lm) {
   return B200_OK;
 }
 int b200_lm_create(b200_problem* p, const b200_lm_params* params, b200_lm** out) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   b200_lm* lm = new b200_lm();
   lm->prob = p;
   lm->params = *params;
@@ -1426,6 +1619,7 @@ int b200_lm_optimize(b200_lm* lm) {
 
 /* GaussNewtonOptimizer::iterate, gtsam/nonlinear/GaussNewtonOptimizer.cpp:44-67 */
 int b200_gn_iterate(b200_problem* p, double* new_error) {
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   int rc = enqueue_linearize(p);
   if (rc) return rc;
@@ -1481,6 +1675,7 @@ int b200_marginal_covariance(b200_problem* p, int64_t var, double* out) {
     path.push_back(c);
   }
   const int d = (int)(S.var_dof[var + 1] - S.var_dof[var]);
+  if (d > 9) { set_error("b200_marginal_covariance: variable dimension > 9 (use b200_joint_marginal_covariance)"); return B200_INVALID_ARGUMENT; }
   if (!p->d_marg_work) {
     B200_CUDA(cudaMalloc((void**)&p->d_marg_work, (size_t)9 * std::max<int64_t>(1, p->ndelta) * sizeof(double)));
     B200_CUDA(cudaMalloc((void**)&p->d_marg_path, (size_t)std::max<int64_t>(1, S.ncliques) * sizeof(int)));
@@ -1550,6 +1745,7 @@ int b200_dl_create(b200_problem* p, double delta_initial, b200_dl** out) {
   // the sharded solve leaves each rank with its own slice of delta; Dogleg's global dot products
   // over dx_u / dx_n are not wired for that layout
   if (p->ctx->world > 1) { set_error("Dogleg is single-GPU: create the problem on a context without a communicator"); return B200_INVALID_ARGUMENT; }
+  if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   b200_dl* dl = new b200_dl;
   dl->prob = p;

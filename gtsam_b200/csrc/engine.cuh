@@ -38,6 +38,17 @@ struct GroupView {
   const int4* scat;        // (clique, slot0, slot1, unused) per factor
 };
 
+// Device-side view of one JacobianFactor group of a linear problem (b200_linear_create): factors of any
+// arity and block widths, [A1 .. Ak b] stored like the typed groups (element-major SoA).
+struct JacobianView {
+  int count, rows, arity, ncols;            // ncols = sum of the block widths + 1
+  int col0[B200_JACOBIAN_MAX_ARITY + 2];    // first column of block a; col0[arity] = the rhs column, col0[arity+1] = ncols
+  const int* keys;                          // count*arity variable ids
+  const int* slots;                         // count*arity scalar slots of the keys in the owning clique's front
+  const int* clique;                        // count: owning clique
+  double* J;                                // J[e * count + f], e = r + c*rows
+};
+
 // Device-side view of the junction tree + frontal arena.
 struct TreeView {
   double* arena;           // all fronts, each (nf+ns+1)^2 col-major, upper triangle used
@@ -91,6 +102,7 @@ struct b200_ctx {
 
 struct b200_problem {
   b200_ctx* ctx = nullptr;
+  bool linear = false;     // created by b200_linear_create: JacobianFactor groups, no Values
   b200::Symbolic sym;
   int64_t nvars = 0, nfactors = 0, nval = 0, ndelta = 0;
   std::vector<int> var_type;
@@ -108,6 +120,8 @@ struct b200_problem {
     double* d_body = nullptr;
     double* d_J = nullptr;
     int4* d_scat = nullptr;
+    int col0[B200_JACOBIAN_MAX_ARITY + 2] = {0};   // JacobianFactor groups: first column of every block
+    int *d_jkeys = nullptr, *d_jslots = nullptr, *d_jclique = nullptr;   // JacobianFactor groups (see JacobianView)
     int64_t n_nonleaf = 0;   // factors NOT owned by a fused leaf clique
     std::vector<int64_t> local_index;  // index in the caller's group of every factor kept on this rank
   };

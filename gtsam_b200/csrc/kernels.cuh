@@ -16,6 +16,9 @@
 //  backsub_point_kernel<DC>, backsub_small_kernel, backsub_large_kernel  a15  x_F = R^-1 (d - S x_S), level by level
 //  linerr_kernel         a16     0.5*|A delta - b|^2 and 0.5*|b|^2 in one pass
 //  retract_kernel        a9      x (+) delta per variable
+//  jacobian_load_kernel, assemble_jacobian_kernel, hdiag_jacobian_kernel, linerr_jacobian_kernel
+//                                a12/a10/a16 for the JacobianFactor groups (any arity / block widths) of a linear problem
+//                                (GaussianFactorGraph::optimize level, b200_linear_create)
 //  gradient_kernel, dot3_kernel, blend_kernel        Dogleg (8f rank 3): gradientAtZero, dot products, dogleg point
 //  marginal_path_kernel, marginal_joint_kernel        Marginals (8f rank 3): forward/back solves along clique paths
 #pragma once
@@ -334,6 +337,105 @@ __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __re
     const int idx = cc < N1 ? var_dof[k.x] + cc : var_dof[k.y] + (cc - N1);
     atomicAdd(hdiag + idx, s);
   }
+}
+
+// ---------------------------------------------------------------------------
+// GaussianFactorGraph level (b200_linear_create): JacobianFactors of any arity and block widths
+// (gtsam/linear/JacobianFactor.h:93-103).  Runtime shapes, one thread per factor, the same
+// element-major SoA as the typed groups, so a warp's loads of one element are one segment.
+// ---------------------------------------------------------------------------
+// [A|b] blocks as the caller holds them (factor-major, column-major blocks = JacobianFactor::matrixObject())
+// -> SoA, whitened by the Diagonal model's inverse sigmas (JacobianFactor::whiten, JacobianFactor.cpp:743-750;
+// noiseModel::Diagonal::WhitenInPlace multiplies row r by invsigmas[r] = 1/sigmas[r])
+__global__ void __launch_bounds__(256) jacobian_load_kernel(const double* __restrict__ Ab, const double* __restrict__ sigmas,
+                                                            int rows, int ncols, int count, double* __restrict__ J) {
+  const int64_t per = (int64_t)rows * ncols, total = per * count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / count, f = i - e * count;   // consecutive threads -> consecutive factors: coalesced stores
+    double x = Ab[f * per + e];
+    if (sigmas) x *= 1.0 / sigmas[f * rows + e % rows];
+    J[i] = x;
+  }
+}
+
+// JacobianFactor::updateHessian (gtsam/linear/JacobianFactor.cpp:563-598): info(I,J) += A_i^T A_j over the
+// blocks i <= j of [A1 .. Ak b], into the upper triangle of the owning clique's front
+__global__ void __launch_bounds__(128) assemble_jacobian_kernel(JacobianView g, TreeView t) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const int c = g.clique[f];
+  double* Mf = t.arena + t.off[c];
+  const int ld = t.nf[c] + t.ns[c] + 1;
+  const double* J = g.J + f;
+  const int m = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int a = 0; a <= g.arity; a++) {
+    const int sa = a < g.arity ? g.slots[(size_t)f * g.arity + a] : ld - 1;   // block `arity` is the rhs column
+    for (int ca = g.col0[a]; ca < g.col0[a + 1]; ca++) {
+      const int i = sa + (ca - g.col0[a]);
+      for (int b = a; b <= g.arity; b++) {
+        const int sb = b < g.arity ? g.slots[(size_t)f * g.arity + b] : ld - 1;
+        for (int cb = (b == a ? ca : g.col0[b]); cb < g.col0[b + 1]; cb++) {   // diagonal block: upper part only
+          const int j = sb + (cb - g.col0[b]);
+          double s = 0;
+          for (int r = 0; r < m; r++) s += J[(size_t)(r + ca * m) * cnt] * J[(size_t)(r + cb * m) * cnt];
+          const int lo = i < j ? i : j, hi = i < j ? j : i;
+          atomicAdd(Mf + lo + (size_t)hi * ld, s);
+        }
+      }
+    }
+  }
+}
+
+// JacobianFactor::hessianDiagonalAdd, gtsam/linear/JacobianFactor.cpp:516-541
+__global__ void __launch_bounds__(128) hdiag_jacobian_kernel(JacobianView g, const int* __restrict__ var_dof, double* hdiag) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const double* J = g.J + f;
+  const int m = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int a = 0; a < g.arity; a++) {
+    const int base = var_dof[g.keys[(size_t)f * g.arity + a]];
+    for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) {
+      double s = 0;
+      for (int r = 0; r < m; r++) { const double x = J[(size_t)(r + cc * m) * cnt]; s += x * x; }
+      atomicAdd(hdiag + base + (cc - g.col0[a]), s);
+    }
+  }
+}
+
+// JacobianFactor::error (gtsam/linear/JacobianFactor.cpp:479-491): 0.5*|A x - bscale*b|^2 and 0.5*|b|^2
+__global__ void __launch_bounds__(256) linerr_jacobian_kernel(JacobianView g, const double* __restrict__ delta,
+                                                              const int* __restrict__ var_dof, double* p0, double* p1,
+                                                              unsigned* counters, double* out0, double* out1, int accumulate,
+                                                              double bscale) {
+  pdl_sync();
+  __shared__ double sh[32];
+  double a0 = 0, a1 = 0;
+  const int m = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
+    const double* J = g.J + f;
+    double s0 = 0, s1 = 0;
+    for (int r = 0; r < m; r++) {
+      const double b = J[(size_t)(r + g.col0[g.arity] * m) * cnt];
+      double e = -bscale * b;
+      for (int a = 0; a < g.arity; a++) {
+        const double* d = delta + var_dof[g.keys[(size_t)f * g.arity + a]];
+        for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) e += J[(size_t)(r + cc * m) * cnt] * d[cc - g.col0[a]];
+      }
+      s0 += b * b;
+      s1 += e * e;
+    }
+    a0 += 0.5 * s0;
+    a1 += 0.5 * s1;
+  }
+  a0 = block_sum<256>(a0, sh);
+  a1 = block_sum<256>(a1, sh);
+  finish_sum(a0, p0, counters, out0, accumulate, sh);
+  finish_sum(a1, p1, counters + 1, out1, accumulate, sh);
 }
 
 // damping priors of buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)

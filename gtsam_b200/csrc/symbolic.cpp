@@ -7,7 +7,7 @@
 namespace b200 {
 
 bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int64_t m,
-                    const int64_t* fkey0, const int64_t* fkey1, Symbolic* S, const char** err) {
+                    const int64_t* fptr, const int64_t* fkeys, Symbolic* S, const char** err) {
   S->nvars = n;
   S->var_dim.assign(var_dim, var_dim + n);
   S->var_dof.assign(n + 1, 0);
@@ -21,18 +21,19 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   // ---- variable index (CSR, factor positions ascending per variable) ----------
   std::vector<int64_t> vi_ptr(n + 1, 0);
   for (int64_t i = 0; i < m; i++) {
-    if (fkey0[i] < 0 || fkey0[i] >= n || fkey1[i] >= n) { *err = "factor key out of range"; return false; }
-    vi_ptr[fkey0[i] + 1]++;
-    if (fkey1[i] >= 0) vi_ptr[fkey1[i] + 1]++;
+    if (fptr[i + 1] <= fptr[i]) { *err = "factor without keys"; return false; }
+    for (int64_t q = fptr[i]; q < fptr[i + 1]; q++) {
+      if (fkeys[q] < 0 || fkeys[q] >= n) { *err = "factor key out of range"; return false; }
+      for (int64_t r = fptr[i]; r < q; r++) if (fkeys[r] == fkeys[q]) { *err = "factor lists a key twice"; return false; }
+      vi_ptr[fkeys[q] + 1]++;
+    }
   }
   for (int64_t v = 0; v < n; v++) vi_ptr[v + 1] += vi_ptr[v];
   std::vector<int64_t> vi(vi_ptr[n]);
   {
     std::vector<int64_t> cur(vi_ptr.begin(), vi_ptr.end() - 1);
-    for (int64_t i = 0; i < m; i++) {
-      vi[cur[fkey0[i]]++] = i;
-      if (fkey1[i] >= 0) vi[cur[fkey1[i]]++] = i;
-    }
+    for (int64_t i = 0; i < m; i++)
+      for (int64_t q = fptr[i]; q < fptr[i + 1]; q++) vi[cur[fkeys[q]]++] = i;
   }
   // ---- elimination tree with path compression ----------------------------------
   std::vector<int64_t> eparent(n, -1), anc(n, -1), prevCol(m, -1), node_of_factor(m, -1);
@@ -71,7 +72,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   }
   // ---- symbolic elimination: separator (as positions) of every etree node -------
   std::vector<int64_t> sep_off(n + 1, 0), sep_pool;
-  sep_pool.reserve((size_t)(2 * m + n));
+  sep_pool.reserve((size_t)(fptr[m] + n));
   std::vector<int64_t> mark(n, -1);
   std::vector<std::vector<int64_t>> cfront(n);  // frontal positions of the cluster headed by j
   std::vector<char> alive(n, 1);
@@ -80,10 +81,8 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     const size_t s0 = sep_pool.size();
     for (int64_t q = nf_ptr[j]; q < nf_ptr[j + 1]; q++) {
       const int64_t i = nfac[q];
-      const int64_t ks[2] = {fkey0[i], fkey1[i]};
-      for (int a = 0; a < 2; a++) {
-        if (ks[a] < 0) continue;
-        const int64_t pj = pos[ks[a]];
+      for (int64_t a = fptr[i]; a < fptr[i + 1]; a++) {
+        const int64_t pj = pos[fkeys[a]];
         if (pj != j && mark[pj] != j) { mark[pj] = j; sep_pool.push_back(pj); }
       }
     }
@@ -178,6 +177,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   // ---- scatter maps ------------------------------------------------------------------
   // factors by owning clique
   S->fac_clique.assign(m, -1); S->fac_slot0.assign(m, -1); S->fac_slot1.assign(m, -1);
+  S->fac_slots.assign(fptr[m], -1);
   std::vector<int64_t> cf_ptr(nc + 1, 0);
   for (int64_t i = 0; i < m; i++) {
     S->fac_clique[i] = (int)clique_of_node[node_of_factor[i]];
@@ -224,9 +224,12 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     const int nn = k + 1;
     for (int64_t q = cf_ptr[c]; q < cf_ptr[c + 1]; q++) {
       const int64_t i = cf[q];
-      S->fac_slot0[i] = slot[fkey0[i]];
-      if (fkey1[i] >= 0) S->fac_slot1[i] = slot[fkey1[i]];
-      if (S->fac_slot0[i] < 0 || (fkey1[i] >= 0 && S->fac_slot1[i] < 0)) { *err = "internal: factor variable not in owning clique"; return false; }
+      for (int64_t a = fptr[i]; a < fptr[i + 1]; a++) {
+        S->fac_slots[a] = slot[fkeys[a]];
+        if (S->fac_slots[a] < 0) { *err = "internal: factor variable not in owning clique"; return false; }
+      }
+      S->fac_slot0[i] = S->fac_slots[fptr[i]];
+      if (fptr[i + 1] - fptr[i] >= 2) S->fac_slot1[i] = S->fac_slots[fptr[i] + 1];
     }
     for (int64_t q = ch_ptr[c]; q < ch_ptr[c + 1]; q++) {
       const int64_t cc = ch[q];

@@ -34,14 +34,16 @@ struct Symbolic {
   std::vector<int> var_clique, var_slot;  // owning clique + scalar slot of each variable
   std::vector<int> fac_clique;        // per graph position: owning clique
   std::vector<int> fac_slot0, fac_slot1;  // scalar slots of key 0 / key 1 in that clique (-1 if unary)
+  std::vector<int> fac_slots;         // the same for every key of every factor, laid out like fkeys (n-ary factors)
   int64_t arena_doubles = 0;
   int64_t max_nf = 0, max_ns = 0;
   double flops = 0;
 };
 
-// fkey0/fkey1: variable ids of every factor by graph position (fkey1 = -1 for
-// unary factors).  Returns false (and fills err) on invalid input.
+// fptr (nfactors+1) / fkeys: CSR of the variable ids of every factor by graph position, in the
+// factor's own key order (any arity >= 1, as a JacobianFactor has).  Returns false (and fills err)
+// on invalid input.
 bool build_symbolic(int64_t nvars, const int* var_dim, const int64_t* ordering, int64_t nfactors,
-                    const int64_t* fkey0, const int64_t* fkey1, Symbolic* out, const char** err);
+                    const int64_t* fptr, const int64_t* fkeys, Symbolic* out, const char** err);
 
 }  // namespace b200

@@ -71,7 +71,10 @@ enum {
   B200_FACTOR_SFM_BUNDLER = 4,
   /* PriorFactor<PinholeCamera<Cal3Bundler>>. key; meas 17; dim 9 */
   B200_FACTOR_PRIOR_CAM_BUNDLER = 5,
-  B200_NUM_FACTOR_TYPES = 6
+  B200_NUM_FACTOR_TYPES = 6,
+  /* internal tag of the groups of a linear problem (b200_linear_create); never valid in a
+     b200_factor_group */
+  B200_FACTOR_JACOBIAN = 6
 };
 
 /* ---- noise models (gtsam/linear/NoiseModel.cpp:83-130,163-238,322-340,646-675) */
@@ -291,6 +294,53 @@ int b200_dl_iterate(b200_dl* dl);
 /* error = state error, delta = trust region radius, iterations = iterate() calls so far */
 int b200_dl_get_state(const b200_dl* dl, double* error, double* delta, int32_t* iterations);
 
+/* ---- GaussianFactorGraph level -----------------------------------------------------------
+ * The same multifrontal solve on an ALREADY LINEARIZED graph: what
+ * GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky)
+ * (gtsam/linear/GaussianFactorGraph.cpp:316-319 -> EliminateableFactorGraph-inst.h:123-146 ->
+ * HessianFactor.cpp:516-536 -> linearAlgorithms-inst.h:50-117) does for a graph of JacobianFactors
+ * of any arity and any block widths (gtsam/linear/JacobianFactor.h:93-103), i.e. rows a11-a16 of the
+ * hot path without a1-a9.  The handle is a b200_problem: b200_solve (lambda = 0, or > 0 for
+ * buildDampedSystem's priors), b200_get_delta, b200_hessian_diagonal, b200_get_conditional,
+ * b200_symbolic_info_get / b200_get_cliques, b200_marginal_covariance and
+ * b200_joint_marginal_covariance work on it; the calls that need Values (b200_error, b200_linearize,
+ * b200_try_step, b200_lm_*, b200_gn_iterate, b200_dl_*) return B200_INVALID_ARGUMENT.
+ * Single GPU (a context without a communicator). */
+#define B200_JACOBIAN_MAX_ARITY 8
+/* One run of JacobianFactors with the same shape (rows, arity, block widths). */
+typedef struct b200_jacobian_group {
+  int32_t rows;             /* rows of [A1 .. Ak b]                                   */
+  int32_t arity;            /* k, 1 .. B200_JACOBIAN_MAX_ARITY                         */
+  const int32_t* dims;      /* k block widths; must equal var_dim of the keyed variables */
+  int64_t count;
+  int64_t graph_index0;     /* -1: append after the previous group                     */
+  const int64_t* graph_index; /* optional explicit graph positions (count), else NULL  */
+  const int64_t* keys;      /* count*arity variable ids, in the factor's key order    */
+  const double* Ab;         /* count blocks, each rows x (sum(dims)+1) COLUMN-MAJOR =
+                               JacobianFactor::matrixObject() (VerticalBlockMatrix, b last) */
+  const double* sigmas;     /* NULL: unit model (or already whitened); else count*rows Diagonal
+                               sigmas: row r of [A|b] is divided by sigmas[r]
+                               (JacobianFactor::whiten, gtsam/linear/JacobianFactor.cpp:743-757, as updateHessian :563-598 does).
+                               Constrained models (sigma == 0) are rejected: B200_UNSUPPORTED_NOISE */
+} b200_jacobian_group;
+
+typedef struct b200_linear_desc {
+  int64_t nvars;
+  const int32_t* var_dim;   /* nvars: tangent dimension of every variable (>= 1)       */
+  const int64_t* ordering;  /* nvars: elimination order (variable ids)                 */
+  int64_t ngroups;
+  const b200_jacobian_group* groups;
+} b200_linear_desc;
+
+/* Pack + symbolic phase + upload of the whitened [A|b] blocks (whitening is a kernel). */
+int b200_linear_create(b200_ctx* ctx, const b200_linear_desc* desc, b200_problem** prob);
+/* New numbers, same structure (the next linearization of the same graph): re-uploads group
+ * `group`'s [A|b] (and sigmas, NULL = unit); the symbolic phase and all tables are reused. */
+int b200_linear_update(b200_problem* prob, int64_t group, const double* Ab, const double* sigmas);
+/* Host-only symbolic phase of a linear description (CPU tests of a11 on n-ary factors). */
+typedef struct b200_symbolic b200_symbolic;
+int b200_linear_symbolic_create(const b200_linear_desc* desc, b200_symbolic** out);
+
 /* Symbolic-phase introspection (parity of a11 against the reference's
  * junction tree).  Cliques are numbered in elimination post-order. */
 int b200_symbolic_info_get(const b200_problem* prob, b200_symbolic_info* info);
@@ -301,7 +351,6 @@ int b200_get_cliques(const b200_problem* prob, int64_t* frontal_ptr, int64_t* fr
 
 /* Host-only symbolic phase (no GPU needed): the same junction tree
  * b200_problem_create builds, for inspection and CPU-side tests of a11. */
-typedef struct b200_symbolic b200_symbolic;
 int b200_symbolic_create(const b200_problem_desc* desc, b200_symbolic** out);
 int b200_symbolic_destroy(b200_symbolic* s);
 int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info);
