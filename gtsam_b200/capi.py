@@ -32,6 +32,7 @@ EXPORTS = [
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
+    "b200_linear_create", "b200_linear_update", "b200_linear_symbolic_create",
 ]
 
 
@@ -114,6 +115,11 @@ def lib():
         L.b200_symbolic_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(vp)]
         L.b200_symbolic_destroy.argtypes = [vp]
         L.b200_symbolic_get_info.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
+        from . import linear as LN
+        L.b200_linear_create.argtypes = [vp, C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
+        L.b200_linear_update.argtypes = [vp, C.c_int64, dp, dp]
+        L.b200_linear_symbolic_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
+        L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         _LIB = L
     return _LIB
 
@@ -289,7 +295,7 @@ class DeviceProblem:
 
     def marginal_covariance(self, var: int):
         """(d, d) covariance of variable `var` at the current values (Marginals::marginalCovariance)."""
-        d = P.VAR_DIM[int(self.prob.var_type[var])]
+        d = int(self.prob.var_dims[var])
         out = np.zeros(d * d)
         rc = self.L.b200_marginal_covariance(self.h, int(var), _dp(out))
         if rc == P.INDETERMINATE:
@@ -300,7 +306,7 @@ class DeviceProblem:
     def joint_marginal_covariance(self, variables):
         """(D, D) joint covariance, blocks in ascending variable order (Marginals::jointMarginalCovariance)."""
         vs = np.array(sorted(int(v) for v in variables), dtype=np.int64)
-        D = int(sum(P.VAR_DIM[int(self.prob.var_type[v])] for v in vs))
+        D = int(sum(int(self.prob.var_dims[v]) for v in vs))
         out = np.zeros(D * D)
         rc = self.L.b200_joint_marginal_covariance(self.h, _ip(vs), len(vs), _dp(out))
         if rc == P.INDETERMINATE:
@@ -332,9 +338,63 @@ class DeviceProblem:
 
     def conditional(self, c: int):
         fp, fv, sp, sv, _ = self.cliques()
-        dims = np.asarray(P.VAR_DIM)[self.prob.var_type]
+        dims = self.prob.var_dims
         f = int(dims[fv[fp[c]:fp[c + 1]]].sum())
         s = int(dims[sv[sp[c]:sp[c + 1]]].sum())
         out = np.zeros(f * (f + s + 1))
         _check(self.L.b200_get_conditional(self.h, c, _dp(out)))
         return out.reshape(f + s + 1, f).T
+
+
+class LinearDeviceProblem(DeviceProblem):
+    """Device-resident GaussianFactorGraph (b200_linear_create): JacobianFactor groups of any arity.
+    solve / get_delta / hessian_diagonal / cliques / conditional / marginal covariances as on
+    DeviceProblem; the calls that need Values raise (status B200_INVALID_ARGUMENT)."""
+
+    def __init__(self, ctx: Context, lprob):
+        self.ctx, self.prob, self.L = ctx, lprob, ctx.L
+        desc, keep = lprob.c_desc()
+        h = C.c_void_p()
+        _check(self.L.b200_linear_create(ctx.h, C.byref(desc), C.byref(h)))
+        del keep
+        self.h = h
+        self.nval = 0
+        self.ndelta = int(self.L.b200_delta_size(h))
+        ctx._problems.add(self)
+
+    def update(self, group: int, Ab, sigmas=None):
+        """New numbers for one group, same structure (b200_linear_update)."""
+        g = self.prob.groups[group]
+        Ab = np.ascontiguousarray(Ab, dtype=np.float64)
+        assert Ab.size == g.count * g.rows * g.ncols
+        sp = None
+        if sigmas is not None:
+            sigmas = np.ascontiguousarray(sigmas, dtype=np.float64)
+            assert sigmas.size == g.count * g.rows
+            sp = _dp(sigmas)
+        _check(self.L.b200_linear_update(self.h, group, _dp(Ab), sp))
+
+    def get_jacobians(self, group: int):
+        """(count, rows, ncols) whitened [A|b] as stored on the device."""
+        g = self.prob.groups[group]
+        out = np.zeros(g.count * g.rows * g.ncols)
+        _check(self.L.b200_get_jacobians(self.h, group, _dp(out)))
+        return out.reshape(g.count, g.ncols, g.rows).transpose(0, 2, 1)
+
+
+def linear_symbolic(lprob):
+    """Host-only junction tree of a linear problem: (frontal_ptr, frontal_vars, separator_ptr, separator_vars, parent)."""
+    L = lib()
+    desc, keep = lprob.c_desc()
+    h = C.c_void_p()
+    _check(L.b200_linear_symbolic_create(C.byref(desc), C.byref(h)))
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info(h, C.byref(info))
+    fp = np.zeros(info.ncliques + 1, dtype=np.int64)
+    sp = np.zeros(info.ncliques + 1, dtype=np.int64)
+    fv = np.zeros(max(1, info.frontal_list_len), dtype=np.int64)
+    sv = np.zeros(max(1, info.separator_list_len), dtype=np.int64)
+    par = np.zeros(max(1, info.ncliques), dtype=np.int64)
+    L.b200_symbolic_get_cliques(h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par))
+    L.b200_symbolic_destroy(h)
+    return fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques]

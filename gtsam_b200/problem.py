@@ -166,6 +166,11 @@ class Problem:
     def nfactors(self) -> int:
         return sum(g.count for g in self.groups)
 
+    @property
+    def var_dims(self) -> np.ndarray:
+        """Tangent dimension of every variable."""
+        return np.asarray(VAR_DIM)[self.var_type]
+
     def val_offsets(self) -> np.ndarray:
         st = np.asarray(VAR_STORAGE)[self.var_type]
         return np.concatenate([[0], np.cumsum(st)]).astype(np.int64)

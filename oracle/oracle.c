@@ -388,11 +388,14 @@ typedef struct {
   double robust_param;
   double body[12]; /* body_P_sensor of the group (projection factors) */
   int d, ncols; /* rows, n1+n2+1 */
+  int arity;    /* keys per factor (typed groups: F_ARITY; JacobianFactor groups: any, <= B200_JACOBIAN_MAX_ARITY) */
   double* J;    /* count * d * ncols, factor-major col-major [A1 A2 b] */
 } ogroup;
 
 struct orc_problem {
   int64_t nvars;
+  int linear;        /* created by orc_linear_create: JacobianFactor groups, no Values */
+  int32_t* var_dim;  /* tangent dimension of every variable */
   int32_t* var_type;
   int64_t *val_off, *dof_off;
   double *values, *new_values, *delta;
@@ -433,7 +436,7 @@ static int cmp_i64_int(const void* a, const void* b) { return (int)cmp_i64(a, b)
 
 static void factor_keys(const orc_problem* p, int64_t gi, const int64_t** keys, int* arity) {
   const ogroup* g = &p->groups[p->fgroup[gi]];
-  *arity = F_ARITY[g->type];
+  *arity = g->arity;
   *keys = g->keys + p->fidx[gi] * (*arity);
 }
 
@@ -587,8 +590,8 @@ static void symbolic(orc_problem* p) {
   p->cond_off = (int64_t*)calloc((size_t)nc + 1, sizeof(int64_t));
   for (c = 0; c < nc; c++) {
     int64_t f = 0, s = 0;
-    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += VAR_DIM[p->var_type[p->front_vars[q]]];
-    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += p->var_dim[p->front_vars[q]];
+    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += p->var_dim[p->sep_vars[q]];
     p->cond_off[c + 1] = p->cond_off[c] + f * (f + s + 1);
   }
   p->cond = (double*)calloc((size_t)(p->cond_off[nc] ? p->cond_off[nc] : 1), sizeof(double));
@@ -605,13 +608,15 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
   const int64_t n = desc->nvars;
   p->nvars = n;
   p->var_type = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+  p->var_dim = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
   memcpy(p->var_type, desc->var_type, (size_t)n * sizeof(int32_t));
   p->val_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
   p->dof_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
   for (int64_t v = 0; v < n; v++) {
     if (p->var_type[v] < 0 || p->var_type[v] > 2) return B200_INVALID_ARGUMENT;
     p->val_off[v + 1] = p->val_off[v] + VAR_STORAGE[p->var_type[v]];
-    p->dof_off[v + 1] = p->dof_off[v] + VAR_DIM[p->var_type[v]];
+    p->var_dim[v] = VAR_DIM[p->var_type[v]];
+    p->dof_off[v + 1] = p->dof_off[v] + p->var_dim[v];
   }
   p->values = (double*)malloc((size_t)p->val_off[n] * sizeof(double));
   p->new_values = (double*)malloc((size_t)p->val_off[n] * sizeof(double));
@@ -648,6 +653,7 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
     if (!s->graph_index) next = o->graph_index0 + s->count;
     const int ar = F_ARITY[s->type], ms = F_MEAS[s->type], d = F_DIM[s->type];
     o->d = d;
+    o->arity = ar;
     o->ncols = VAR_DIM[F_VT[s->type][0]] + (ar == 2 ? VAR_DIM[F_VT[s->type][1]] : 0) + 1;
     o->noise_size = noise_payload(s->noise_kind, d);
     if (o->noise_size < 0) return B200_UNSUPPORTED_NOISE;
@@ -680,13 +686,104 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
   return B200_OK;
 }
 
+/* ---- GaussianFactorGraph level: a graph of JacobianFactors of any arity and block widths
+ * (gtsam/linear/JacobianFactor.h:93-103) solved by GaussianFactorGraph::optimize(ordering,
+ * EliminatePreferCholesky) (gtsam/linear/GaussianFactorGraph.cpp:316-319).  The factors are stored
+ * whitened, as JacobianFactor::updateHessian uses them (JacobianFactor.cpp:563-598 -> whiten() :743-750,
+ * noiseModel::Diagonal::WhitenInPlace: row r times invsigmas[r] = 1/sigmas[r]). */
+static void whiten_jacobian_group(ogroup* o, const double* Ab, const double* sigmas) {
+  const int64_t per = (int64_t)o->d * o->ncols;
+  for (int64_t i = 0; i < o->count; i++)
+    for (int64_t e = 0; e < per; e++) {
+      double x = Ab[i * per + e];
+      if (sigmas) x *= 1.0 / sigmas[i * o->d + e % o->d];
+      o->J[i * per + e] = x;
+    }
+}
+
+int orc_linear_create(const b200_linear_desc* desc, orc_problem** out) {
+  orc_problem* p = (orc_problem*)calloc(1, sizeof(orc_problem));
+  const int64_t n = desc->nvars;
+  p->nvars = n;
+  p->linear = 1;
+  p->var_type = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  p->var_dim = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+  p->val_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+  p->dof_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+  for (int64_t v = 0; v < n; v++) {
+    if (desc->var_dim[v] < 1) return B200_INVALID_ARGUMENT;
+    p->var_dim[v] = desc->var_dim[v];
+    p->dof_off[v + 1] = p->dof_off[v] + p->var_dim[v];
+  }
+  p->values = (double*)malloc(sizeof(double));
+  p->new_values = (double*)malloc(sizeof(double));
+  p->delta = (double*)calloc((size_t)p->dof_off[n] + 1, sizeof(double));
+  p->ordering = (int64_t*)malloc((size_t)(n + 1) * sizeof(int64_t));
+  p->pos = (int64_t*)malloc((size_t)(n + 1) * sizeof(int64_t));
+  memcpy(p->ordering, desc->ordering, (size_t)n * sizeof(int64_t));
+  for (int64_t v = 0; v < n; v++) p->pos[v] = -1;
+  for (int64_t j = 0; j < n; j++) {
+    if (p->ordering[j] < 0 || p->ordering[j] >= n || p->pos[p->ordering[j]] != -1) return B200_INVALID_ARGUMENT;
+    p->pos[p->ordering[j]] = j;
+  }
+  p->cal = (double*)malloc(5 * sizeof(double));
+  p->ngroups = desc->ngroups;
+  p->groups = (ogroup*)calloc((size_t)(desc->ngroups ? desc->ngroups : 1), sizeof(ogroup));
+  int64_t next = 0, total = 0;
+  for (int64_t g = 0; g < desc->ngroups; g++) total += desc->groups[g].count;
+  p->nfactors = total;
+  p->fgroup = (int32_t*)malloc((size_t)(total ? total : 1) * sizeof(int32_t));
+  p->fidx = (int64_t*)malloc((size_t)(total ? total : 1) * sizeof(int64_t));
+  for (int64_t i = 0; i < total; i++) p->fgroup[i] = -1;
+  for (int64_t g = 0; g < desc->ngroups; g++) {
+    const b200_jacobian_group* s = &desc->groups[g];
+    ogroup* o = &p->groups[g];
+    if (s->arity < 1 || s->arity > B200_JACOBIAN_MAX_ARITY) return B200_UNSUPPORTED_FACTOR;
+    o->type = B200_FACTOR_JACOBIAN;
+    o->count = s->count;
+    o->graph_index0 = s->graph_index ? -1 : (s->graph_index0 < 0 ? next : s->graph_index0);
+    if (!s->graph_index) next = o->graph_index0 + s->count;
+    o->d = s->rows;
+    o->arity = s->arity;
+    o->ncols = 1;
+    for (int a = 0; a < s->arity; a++) o->ncols += s->dims[a];
+    o->keys = (int64_t*)malloc((size_t)(s->count * s->arity + 1) * sizeof(int64_t));
+    memcpy(o->keys, s->keys, (size_t)(s->count * s->arity) * sizeof(int64_t));
+    o->meas = 0; o->noise = 0; o->cal_index = 0;
+    o->J = (double*)calloc((size_t)(s->count * o->d * o->ncols + 1), sizeof(double));
+    if (s->sigmas)
+      for (int64_t i = 0; i < s->count * s->rows; i++)
+        if (!(s->sigmas[i] > 0)) return B200_UNSUPPORTED_NOISE; /* Constrained: needs QR */
+    whiten_jacobian_group(o, s->Ab, s->sigmas);
+    for (int64_t i = 0; i < s->count; i++) {
+      const int64_t gi = s->graph_index ? s->graph_index[i] : o->graph_index0 + i;
+      if (gi < 0 || gi >= total || p->fgroup[gi] != -1) return B200_INVALID_ARGUMENT;
+      p->fgroup[gi] = (int32_t)g;
+      p->fidx[gi] = i;
+      for (int a = 0; a < s->arity; a++) {
+        const int64_t k = o->keys[i * s->arity + a];
+        if (k < 0 || k >= n || p->var_dim[k] != s->dims[a]) return B200_INVALID_ARGUMENT;
+      }
+    }
+  }
+  symbolic(p);
+  *out = p;
+  return B200_OK;
+}
+
+int orc_linear_update(orc_problem* p, int64_t group, const double* Ab, const double* sigmas) {
+  if (!p->linear || group < 0 || group >= p->ngroups) return B200_INVALID_ARGUMENT;
+  whiten_jacobian_group(&p->groups[group], Ab, sigmas);
+  return B200_OK;
+}
+
 void orc_problem_destroy(orc_problem* p) {
   if (!p) return;
   for (int64_t g = 0; g < p->ngroups; g++) {
     ogroup* o = &p->groups[g];
     free(o->keys); free(o->meas); free(o->noise); free(o->cal_index); free(o->J);
   }
-  free(p->groups); free(p->var_type); free(p->val_off); free(p->dof_off); free(p->values);
+  free(p->groups); free(p->var_type); free(p->var_dim); free(p->val_off); free(p->dof_off); free(p->values);
   free(p->new_values); free(p->delta); free(p->ordering); free(p->pos); free(p->cal);
   free(p->fgroup); free(p->fidx); free(p->front_ptr); free(p->front_vars); free(p->sep_ptr);
   free(p->sep_vars); free(p->parent); free(p->cf_ptr); free(p->cf_list); free(p->ch_ptr);
@@ -706,7 +803,7 @@ int64_t orc_delta_size(const orc_problem* p) { return p->dof_off[p->nvars]; }
  * active.  Follows NoiseModelFactorN::unwhitenedError -> evaluateError. */
 static void eval_factor(const orc_problem* p, const ogroup* g, int64_t i, const double* values,
                         double* r, double* H1, double* H2) {
-  const int ar = F_ARITY[g->type];
+  const int ar = g->arity;
   const int64_t* keys = g->keys + i * ar;
   const double* x1 = values + p->val_off[keys[0]];
   const double* x2 = ar == 2 ? values + p->val_off[keys[1]] : 0;
@@ -883,9 +980,10 @@ double orc_error(orc_problem* p) { return graph_error(p, p->values); }
 /* NoiseModelFactor::linearize, gtsam/nonlinear/NonlinearFactor.cpp:150-182;
  * GeneralSFMFactor::linearize, gtsam/slam/GeneralSFMFactor.h:141-177 */
 void orc_linearize(orc_problem* p) {
+  if (p->linear) return; /* a linear problem is its own linearization */
   for (int64_t gidx = 0; gidx < p->ngroups; gidx++) {
     ogroup* g = &p->groups[gidx];
-    const int d = g->d, ar = F_ARITY[g->type];
+    const int d = g->d, ar = g->arity;
     const int n1 = VAR_DIM[F_VT[g->type][0]], n2 = ar == 2 ? VAR_DIM[F_VT[g->type][1]] : 0;
     for (int64_t i = 0; i < g->count; i++) {
       double r[9], H1[81], H2[36];
@@ -924,12 +1022,12 @@ void orc_hessian_diagonal(const orc_problem* p, double* out) {
   for (int64_t gi = 0; gi < p->nfactors; gi++) {
     const ogroup* g = &p->groups[p->fgroup[gi]];
     const int64_t i = p->fidx[gi];
-    const int d = g->d, ar = F_ARITY[g->type];
+    const int d = g->d, ar = g->arity;
     const double* J = g->J + i * d * g->ncols;
     int col = 0;
     for (int a = 0; a < ar; a++) {
       const int64_t v = g->keys[i * ar + a];
-      const int nv = VAR_DIM[p->var_type[v]];
+      const int nv = p->var_dim[v];
       for (int c = 0; c < nv; c++, col++) {
         double s = 0;
         for (int rr = 0; rr < d; rr++) s += J[rr + col * d] * J[rr + col * d];
@@ -946,14 +1044,14 @@ static double linear_error(const orc_problem* p, const double* delta) {
   for (int64_t gi = 0; gi < p->nfactors; gi++) {
     const ogroup* g = &p->groups[p->fgroup[gi]];
     const int64_t i = p->fidx[gi];
-    const int d = g->d, ar = F_ARITY[g->type];
+    const int d = g->d, ar = g->arity;
     const double* J = g->J + i * d * g->ncols;
-    double e[9];
+    double e[d > 0 ? d : 1];
     for (int rr = 0; rr < d; rr++) e[rr] = -J[rr + (g->ncols - 1) * d];
     int col = 0;
     for (int a = 0; a < ar; a++) {
       const int64_t v = g->keys[i * ar + a];
-      const int nv = VAR_DIM[p->var_type[v]];
+      const int nv = p->var_dim[v];
       for (int c = 0; c < nv; c++, col++) {
         const double x = delta ? delta[p->dof_off[v] + c] : 0.0;
         for (int rr = 0; rr < d; rr++) e[rr] += J[rr + col * d] * x;
@@ -988,11 +1086,11 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
     int64_t f = 0, s = 0;
     for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) {
       slot[p->front_vars[q]] = f;
-      f += VAR_DIM[p->var_type[p->front_vars[q]]];
+      f += p->var_dim[p->front_vars[q]];
     }
     for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) {
       slot[p->sep_vars[q]] = f + s;
-      s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+      s += p->var_dim[p->sep_vars[q]];
     }
     const int64_t n = f + s + 1;
     double* M = (double*)calloc((size_t)(n * n), sizeof(double));
@@ -1002,15 +1100,15 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
       const int64_t gi = p->cf_list[q];
       const ogroup* g = &p->groups[p->fgroup[gi]];
       const int64_t i = p->fidx[gi];
-      const int d = g->d, ar = F_ARITY[g->type];
+      const int d = g->d, ar = g->arity;
       const double* J = g->J + i * d * g->ncols;
-      int64_t off[3];
-      int dim[3], col0[3];
+      int64_t off[B200_JACOBIAN_MAX_ARITY + 1];
+      int dim[B200_JACOBIAN_MAX_ARITY + 1], col0[B200_JACOBIAN_MAX_ARITY + 1];
       int col = 0;
       for (int a = 0; a < ar; a++) {
         const int64_t v = g->keys[i * ar + a];
         off[a] = slot[v];
-        dim[a] = VAR_DIM[p->var_type[v]];
+        dim[a] = p->var_dim[v];
         col0[a] = col;
         col += dim[a];
       }
@@ -1031,7 +1129,7 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
     if (lambda > 0) {
       for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) {
         const int64_t v = p->front_vars[q];
-        const int nv = VAR_DIM[p->var_type[v]];
+        const int nv = p->var_dim[v];
         for (int k = 0; k < nv; k++) {
           double a2 = 1.0;
           if (diagonal_damping) {
@@ -1051,13 +1149,13 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
     for (int64_t q = p->ch_ptr[c]; q < p->ch_ptr[c + 1]; q++) {
       const int64_t ch = p->ch_list[q];
       int64_t cs = 0;
-      for (int64_t qq = p->sep_ptr[ch]; qq < p->sep_ptr[ch + 1]; qq++) cs += VAR_DIM[p->var_type[p->sep_vars[qq]]];
+      for (int64_t qq = p->sep_ptr[ch]; qq < p->sep_ptr[ch + 1]; qq++) cs += p->var_dim[p->sep_vars[qq]];
       const int64_t cn = cs + 1;
       int64_t* map = (int64_t*)malloc((size_t)cn * sizeof(int64_t));
       int64_t k = 0;
       for (int64_t qq = p->sep_ptr[ch]; qq < p->sep_ptr[ch + 1]; qq++) {
         const int64_t v = p->sep_vars[qq];
-        for (int t = 0; t < VAR_DIM[p->var_type[v]]; t++) map[k++] = slot[v] + t;
+        for (int t = 0; t < p->var_dim[v]; t++) map[k++] = slot[v] + t;
       }
       map[k] = n - 1;
       const double* S = schur[ch];
@@ -1093,8 +1191,8 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
   /* back-substitution, pre-order: gtsam/linear/linearAlgorithms-inst.h:50-117 */
   for (int64_t c = nc - 1; c >= 0 && status == B200_OK; c--) {
     int64_t f = 0, s = 0;
-    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += VAR_DIM[p->var_type[p->front_vars[q]]];
-    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += p->var_dim[p->front_vars[q]];
+    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += p->var_dim[p->sep_vars[q]];
     const int64_t n = f + s + 1;
     const double* C = p->cond + p->cond_off[c];
     double* x = (double*)malloc((size_t)f * sizeof(double));
@@ -1102,7 +1200,7 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
     int64_t col = f;
     for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) {
       const int64_t v = p->sep_vars[q];
-      for (int t = 0; t < VAR_DIM[p->var_type[v]]; t++, col++) {
+      for (int t = 0; t < p->var_dim[v]; t++, col++) {
         const double xs = p->delta[p->dof_off[v] + t];
         for (int64_t i = 0; i < f; i++) x[i] -= C[i + col * f] * xs;
       }
@@ -1115,7 +1213,7 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
     int64_t k = 0;
     for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) {
       const int64_t v = p->front_vars[q];
-      for (int t = 0; t < VAR_DIM[p->var_type[v]]; t++, k++) {
+      for (int t = 0; t < p->var_dim[v]; t++, k++) {
         if (isnan(x[k])) {
           status = B200_INDETERMINATE;
           if (fail_var) *fail_var = p->front_vars[p->front_ptr[c]];
@@ -1144,8 +1242,8 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
  * elimination order, back-substitution U x = y as linearAlgorithms-inst.h:50-117). */
 static void clique_fs(const orc_problem* p, int64_t c, int64_t* f, int64_t* s) {
   *f = 0; *s = 0;
-  for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) *f += VAR_DIM[p->var_type[p->front_vars[q]]];
-  for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) *s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+  for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) *f += p->var_dim[p->front_vars[q]];
+  for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) *s += p->var_dim[p->sep_vars[q]];
 }
 
 /* x = H^-1 g with the factorisation left by the last successful orc_solve (its damping included) */
@@ -1160,9 +1258,9 @@ void orc_solve_rhs(const orc_problem* p, const double* g, double* x) {
     const double* C = p->cond + p->cond_off[c];
     int64_t k = 0;
     for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++)
-      for (int t = 0; t < VAR_DIM[p->var_type[p->front_vars[q]]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
+      for (int t = 0; t < p->var_dim[p->front_vars[q]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
     for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++)
-      for (int t = 0; t < VAR_DIM[p->var_type[p->sep_vars[q]]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
+      for (int t = 0; t < p->var_dim[p->sep_vars[q]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
     for (int64_t i = 0; i < f; i++) {
       double sum = y[idx[i]];
       for (int64_t kk = 0; kk < i; kk++) sum -= C[kk + i * f] * y[idx[kk]];
@@ -1180,9 +1278,9 @@ void orc_solve_rhs(const orc_problem* p, const double* g, double* x) {
     const double* C = p->cond + p->cond_off[c];
     int64_t k = 0;
     for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++)
-      for (int t = 0; t < VAR_DIM[p->var_type[p->front_vars[q]]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
+      for (int t = 0; t < p->var_dim[p->front_vars[q]]; t++) idx[k++] = p->dof_off[p->front_vars[q]] + t;
     for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++)
-      for (int t = 0; t < VAR_DIM[p->var_type[p->sep_vars[q]]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
+      for (int t = 0; t < p->var_dim[p->sep_vars[q]]; t++) idx[k++] = p->dof_off[p->sep_vars[q]] + t;
     for (int64_t i = f - 1; i >= 0; i--) {
       double sum = y[idx[i]];
       for (int64_t col = f; col < f + s; col++) sum -= C[i + col * f] * x[idx[col]];
@@ -1197,7 +1295,7 @@ void orc_solve_rhs(const orc_problem* p, const double* g, double* x) {
 /* out: d x d column-major covariance of variable `var` at the current values */
 int orc_marginal_covariance(orc_problem* p, int64_t var, double* out) {
   const int64_t ntot = p->dof_off[p->nvars];
-  const int d = VAR_DIM[p->var_type[var]];
+  const int d = p->var_dim[var];
   orc_linearize(p);
   int64_t fv;
   const int st = orc_solve(p, 0.0, 0, 0, 0, 0, 0, &fv);
@@ -1221,7 +1319,7 @@ int orc_marginal_covariance(orc_problem* p, int64_t var, double* out) {
 int orc_joint_marginal_covariance(orc_problem* p, const int64_t* vars, int64_t nv, double* out) {
   const int64_t ntot = p->dof_off[p->nvars];
   int64_t D = 0;
-  for (int64_t a = 0; a < nv; a++) D += VAR_DIM[p->var_type[vars[a]]];
+  for (int64_t a = 0; a < nv; a++) D += p->var_dim[vars[a]];
   orc_linearize(p);
   int64_t fv;
   const int st = orc_solve(p, 0.0, 0, 0, 0, 0, 0, &fv);
@@ -1230,13 +1328,13 @@ int orc_joint_marginal_covariance(orc_problem* p, const int64_t* vars, int64_t n
   double* x = (double*)calloc((size_t)ntot, sizeof(double));
   int64_t col = 0;
   for (int64_t a = 0; a < nv; a++)
-    for (int k = 0; k < VAR_DIM[p->var_type[vars[a]]]; k++, col++) {
+    for (int k = 0; k < p->var_dim[vars[a]]; k++, col++) {
       g[p->dof_off[vars[a]] + k] = 1.0;
       orc_solve_rhs(p, g, x);
       g[p->dof_off[vars[a]] + k] = 0.0;
       int64_t row = 0;
       for (int64_t b = 0; b < nv; b++)
-        for (int i = 0; i < VAR_DIM[p->var_type[vars[b]]]; i++, row++) out[row + col * D] = x[p->dof_off[vars[b]] + i];
+        for (int i = 0; i < p->var_dim[vars[b]]; i++, row++) out[row + col * D] = x[p->dof_off[vars[b]] + i];
     }
   free(g);
   free(x);
@@ -1409,12 +1507,12 @@ int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io) {
   for (int64_t gi = 0; gi < p->nfactors; gi++) {
     const ogroup* g = &p->groups[p->fgroup[gi]];
     const int64_t i = p->fidx[gi];
-    const int d = g->d, ar = F_ARITY[g->type];
+    const int d = g->d, ar = g->arity;
     const double* J = g->J + i * d * g->ncols;
     int col = 0;
     for (int a = 0; a < ar; a++) {
       const int64_t v = g->keys[i * ar + a];
-      for (int c = 0; c < VAR_DIM[p->var_type[v]]; c++, col++) {
+      for (int c = 0; c < p->var_dim[v]; c++, col++) {
         double s = 0;
         for (int rr = 0; rr < d; rr++) s += J[rr + col * d] * J[rr + (g->ncols - 1) * d];
         dxu[p->dof_off[v] + c] -= s;
@@ -1427,13 +1525,13 @@ int orc_dogleg_iterate(orc_problem* p, double* error_io, double* delta_io) {
   for (int64_t gi = 0; gi < p->nfactors; gi++) {
     const ogroup* g = &p->groups[p->fgroup[gi]];
     const int64_t i = p->fidx[gi];
-    const int d = g->d, ar = F_ARITY[g->type];
+    const int d = g->d, ar = g->arity;
     const double* J = g->J + i * d * g->ncols;
     double e[9] = {0};
     int col = 0;
     for (int a = 0; a < ar; a++) {
       const int64_t v = g->keys[i * ar + a];
-      for (int c = 0; c < VAR_DIM[p->var_type[v]]; c++, col++)
+      for (int c = 0; c < p->var_dim[v]; c++, col++)
         for (int rr = 0; rr < d; rr++) e[rr] += J[rr + col * d] * dxu[p->dof_off[v] + c];
     }
     for (int rr = 0; rr < d; rr++) Ag2 += e[rr] * e[rr];
@@ -1492,8 +1590,8 @@ void orc_symbolic_info_get(const orc_problem* p, b200_symbolic_info* info) {
   int64_t* level = (int64_t*)calloc((size_t)(p->ncliques ? p->ncliques : 1), sizeof(int64_t));
   for (int64_t c = 0; c < p->ncliques; c++) {
     int64_t f = 0, s = 0;
-    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += VAR_DIM[p->var_type[p->front_vars[q]]];
-    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += VAR_DIM[p->var_type[p->sep_vars[q]]];
+    for (int64_t q = p->front_ptr[c]; q < p->front_ptr[c + 1]; q++) f += p->var_dim[p->front_vars[q]];
+    for (int64_t q = p->sep_ptr[c]; q < p->sep_ptr[c + 1]; q++) s += p->var_dim[p->sep_vars[q]];
     if (f > info->max_frontal_dim) info->max_frontal_dim = f;
     if (s > info->max_separator_dim) info->max_separator_dim = s;
     info->factor_flops += (double)f * f * f / 3.0 + (double)f * f * s + (double)f * s * s;

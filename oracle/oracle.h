@@ -41,6 +41,10 @@ void orc_pose3_adjoint_map(const double T[12], double Ad[36]); /* row-major 6x6 
 int orc_cholesky_partial(double* ABC, int64_t n, int64_t nFrontal);
 
 int orc_problem_create(const b200_problem_desc* desc, orc_problem** out);
+/* GaussianFactorGraph level (b200_linear_create): JacobianFactors of any arity; orc_solve, orc_get_delta,
+ * orc_hessian_diagonal, orc_get_conditional, orc_get_cliques and the marginals work on the result */
+int orc_linear_create(const b200_linear_desc* desc, orc_problem** out);
+int orc_linear_update(orc_problem* p, int64_t group, const double* Ab, const double* sigmas);
 void orc_problem_destroy(orc_problem* p);
 void orc_set_values(orc_problem* p, const double* packed);
 void orc_get_values(const orc_problem* p, double* packed);

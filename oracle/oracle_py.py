@@ -32,6 +32,9 @@ def lib():
         L = C.CDLL(build())
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
         L.orc_problem_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(C.c_void_p)]
+        from gtsam_b200 import linear as LN
+        L.orc_linear_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(C.c_void_p)]
+        L.orc_linear_update.argtypes = [C.c_void_p, C.c_int64, dp, dp]
         L.orc_problem_destroy.argtypes = [C.c_void_p]
         L.orc_set_values.argtypes = [C.c_void_p, dp]
         L.orc_get_values.argtypes = [C.c_void_p, dp]
@@ -177,14 +180,14 @@ class OracleProblem:
         return st, e.value, d.value
 
     def marginal_covariance(self, var):
-        d = P.VAR_DIM[int(self.prob.var_type[var])]
+        d = int(self.prob.var_dims[var])
         out = np.zeros(d * d)
         st = self.L.orc_marginal_covariance(self.h, int(var), _dp(out))
         return st, out.reshape(d, d).T   # column-major -> (row, col)
 
     def joint_marginal_covariance(self, variables):
         vs = np.array(sorted(int(v) for v in variables), dtype=np.int64)
-        D = int(sum(P.VAR_DIM[int(self.prob.var_type[v])] for v in vs))
+        D = int(sum(int(self.prob.var_dims[v]) for v in vs))
         out = np.zeros(D * D)
         st = self.L.orc_joint_marginal_covariance(self.h, _ip(vs), len(vs), _dp(out))
         return st, out.reshape(D, D).T
@@ -212,7 +215,7 @@ class OracleProblem:
 
     def conditional(self, c):
         fp, fv, sp, sv, _ = self.cliques()
-        dims = np.asarray(P.VAR_DIM)[self.prob.var_type]
+        dims = self.prob.var_dims
         f = int(dims[fv[fp[c]:fp[c + 1]]].sum())
         s = int(dims[sv[sp[c]:sp[c + 1]]].sum())
         out = np.zeros(f * (f + s + 1))
@@ -230,3 +233,34 @@ class OracleProblem:
 
     def lm_optimize(self, lm):
         return self.L.orc_lm_optimize(C.byref(lm))
+
+
+class OracleLinearProblem(OracleProblem):
+    """CPU oracle of the GaussianFactorGraph level (orc_linear_create): same surface as
+    gtsam_b200.capi.LinearDeviceProblem."""
+
+    def __init__(self, lprob):
+        self.prob = lprob
+        self.L = lib()
+        desc, self._keep = lprob.c_desc()
+        h = C.c_void_p()
+        st = self.L.orc_linear_create(C.byref(desc), C.byref(h))
+        if st != 0:
+            raise RuntimeError(f"orc_linear_create failed: {st}")
+        self.h = h
+        self.nval = 0
+        self.ndelta = self.L.orc_delta_size(h)
+
+    def update(self, group, Ab, sigmas=None):
+        Ab = np.ascontiguousarray(Ab, dtype=np.float64)
+        sp = None
+        if sigmas is not None:
+            sigmas = np.ascontiguousarray(sigmas, dtype=np.float64)
+            sp = _dp(sigmas)
+        assert self.L.orc_linear_update(self.h, group, _dp(Ab), sp) == 0
+
+    def get_jacobians(self, group):
+        g = self.prob.groups[group]
+        out = np.zeros(g.count * g.rows * g.ncols)
+        self.L.orc_get_jacobians(self.h, group, _dp(out))
+        return out.reshape(g.count, g.ncols, g.rows).transpose(0, 2, 1)

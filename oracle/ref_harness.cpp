@@ -12,6 +12,7 @@
  * Variable id i <-> gtsam::Key i (plain integers), so Key order == id order.
  */
 #include "problem_io.hpp"
+#include "linear_io.hpp"
 #include <gtsam/nonlinear/DoglegOptimizer.h>
 #include <gtsam/nonlinear/Marginals.h>
 #include <gtsam/nonlinear/GncOptimizer.h>
@@ -473,6 +474,79 @@ static int cmd_pose2(const std::string& path) {
   return 0;
 }
 
+/* ---- GaussianFactorGraph level: the reference's own optimize() on a graph of JacobianFactors ----
+ * `linsolve in.lin out [lambda]`: GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky)
+ * (gtsam/linear/GaussianFactorGraph.cpp:316-319); with lambda > 0 the graph is first extended by the
+ * damping priors buildDampedSystem appends (LevenbergMarquardtState.h:125-156, non-diagonal case:
+ * A = I, b = 0, sigma = 1/sqrt(lambda) per variable).  Dumps delta, hessianDiagonal, the two linear
+ * errors of the UNDAMPED graph, the Bayes tree (cliques + conditionals) and the marginal covariance of
+ * every variable (inverse of the marginal information, GaussianBayesTree::marginalFactor). */
+static int cmd_linsolve(const std::string& in, const std::string& outp, double lambda) {
+  linio::LinProb lp = linio::load(in);
+  GaussianFactorGraph gfg = linio::build_graph(lp);
+  Ordering ordering = linio::build_ordering(lp);
+  Out out(outp);
+  Prob dummy;
+  dummy.nvars = lp.nvars;
+  auto pack = [&](const VectorValues& vv) {
+    std::vector<double> o;
+    for (int64_t i = 0; i < lp.nvars; i++) { const Vector& x = vv.at(Key(i)); for (int k = 0; k < x.size(); k++) o.push_back(x(k)); }
+    return o;
+  };
+  out.put("hessian_diagonal", pack(gfg.hessianDiagonal()));
+  GaussianFactorGraph sys = gfg;
+  if (lambda > 0) {
+    for (int64_t v = 0; v < lp.nvars; v++) {
+      const int d = lp.var_dim[v];
+      sys.push_back(std::make_shared<JacobianFactor>(Key(v), Matrix::Identity(d, d), Vector::Zero(d),
+                                                     noiseModel::Isotropic::Sigma(d, 1.0 / std::sqrt(lambda))));
+    }
+  }
+  int status = 0;
+  VectorValues delta;
+  try {
+    delta = sys.optimize(ordering, EliminatePreferCholesky);
+  } catch (const IndeterminantLinearSystemException& e) {
+    status = 1;
+    out.put("fail_var", std::vector<int64_t>{(int64_t)e.nearbyVariable()});
+  }
+  out.put("status", std::vector<int64_t>{status});
+  if (!status) {
+    out.put("delta", pack(delta));
+    out.put("linear_error_zero", gfg.error(VectorValues::Zero(delta)));
+    out.put("linear_error_delta", gfg.error(delta));
+    dump_tree(dummy, sys, ordering, out);
+    if (lambda == 0) {
+      auto bt = gfg.eliminateMultifrontal(ordering, EliminatePreferCholesky);
+      std::vector<double> cov;
+      for (int64_t v = 0; v < lp.nvars; v++) {
+        Matrix info = bt->marginalFactor(Key(v), EliminatePreferCholesky)->information();
+        Matrix c = info.inverse();
+        for (int cc = 0; cc < c.cols(); cc++) for (int r = 0; r < c.rows(); r++) cov.push_back(c(r, cc));
+      }
+      out.put("marginal_covariances", cov);
+    }
+  }
+  return 0;
+}
+
+/* `linearize2d file.g2o out.lin`: BASELINE.json configs[0]'s graph (Pose2 g2o + the example's prior,
+ * examples/Pose2SLAMExample_g2o.cpp:46-64) linearized by the reference at the file's initial estimate,
+ * written as a linear problem with the reference's COLAMD ordering. */
+static int cmd_linearize2d(const std::string& path, const std::string& outp) {
+  auto [graph, initial] = readG2o(path, false);
+  auto priorModel = noiseModel::Diagonal::Variances(Vector3(1e-6, 1e-6, 1e-8));
+  graph->addPrior(0, Pose2(), priorModel);
+  auto lin = graph->linearize(*initial);
+  Ordering ordering = Ordering::Colamd(*lin);
+  linio::LinProb lp;
+  if (!linio::from_graph(*lin, ordering, &lp)) { fprintf(stderr, "graph holds a non-Jacobian or constrained factor\n"); return 3; }
+  linio::save(lp, outp);
+  printf("{\"variables\": %ld, \"factors\": %ld, \"groups\": %zu, \"error\": %.12g}\n", (long)lp.nvars, (long)lp.nfactors(),
+         lp.groups.size(), graph->error(*initial));
+  return 0;
+}
+
 /* known-answer vectors for the geometry primitives, incl. near-0 / near-pi */
 static int cmd_kat(const std::string& outp) {
   std::mt19937 rng(123);
@@ -531,6 +605,8 @@ int main(int argc, char** argv) {
   if (cmd == "order" && argc >= 5) return cmd_order(argv[2], argv[3], argv[4]);
   if (cmd == "kat" && argc >= 3) return cmd_kat(argv[2]);
   if (cmd == "pose2" && argc >= 3) return cmd_pose2(argv[2]);
+  if (cmd == "linsolve" && argc >= 4) return cmd_linsolve(argv[2], argv[3], argc > 4 ? atof(argv[4]) : 0.0);
+  if (cmd == "linearize2d" && argc >= 4) return cmd_linearize2d(argv[2], argv[3]);
   if (cmd == "g2ofile" && argc >= 4) return cmd_g2ofile(argv[2], argv[3]);
   if (cmd == "balfile" && argc >= 4) return cmd_balfile(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 0);
   fprintf(stderr, "bad arguments\n");

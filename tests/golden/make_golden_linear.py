@@ -1,0 +1,129 @@
+"""Regenerates tests/golden/lin_*.{lin,out0,out1}.bin: GaussianFactorGraph-level fixtures produced by the
+UNMODIFIED reference (oracle/_ref/ref_harness linsolve / linearize2d).  Run from the repo root in the build
+container:
+
+    python tests/golden/make_golden_linear.py
+
+* lin_pose2_toy   — BASELINE.json configs[0]: examples/Data/noisyToyGraph.txt (Pose2 g2o + the example's prior)
+                    linearized BY THE REFERENCE at the file's initial estimate, COLAMD ordering.
+* lin_random_nary — random JacobianFactors of arity 1..4, rows 1..7, block widths 1/2/3/6, half of the groups with a
+                    Diagonal model (sigmas), random elimination order.
+* lin_arity8      — a few factors of the maximum supported arity (8).
+* lin_sphere_tiny, lin_bal_tiny — the reference's own linearization of the sphere_tiny / bal_tiny_s2 graphs (the
+                    whitened [A|b] of tests/golden/<case>.dump0.bin) re-posed as linear problems: must reproduce
+                    those dumps' delta.
+* lin_singular    — an under-constrained graph: the reference throws IndeterminantLinearSystemException.
+Each case stores the problem (*.lin.bin, gtsam_b200.linear.LinearProblem.save) and the reference's outputs for
+lambda = 0 (*.out0.bin: delta, hessianDiagonal, linear errors, Bayes tree + conditionals, marginal covariances) and
+lambda = 0.25 (*.out1.bin: the damped system of LevenbergMarquardtState.h:125-156).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gtsam_b200 import linear as LN, problem as P  # noqa: E402
+from oracle import refio  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+H = refio.HARNESS
+REF_DATA = "/root/reference/examples/Data"
+
+
+def emit(name, lp=None):
+    path = os.path.join(HERE, f"{name}.lin.bin")
+    if lp is not None:
+        lp.save(path)
+    subprocess.check_call([H, "linsolve", path, os.path.join(HERE, f"{name}.out0.bin"), "0"])
+    subprocess.check_call([H, "linsolve", path, os.path.join(HERE, f"{name}.out1.bin"), "0.25"])
+    lp = LN.LinearProblem.load(path)
+    print("wrote", name, lp.nvars, "vars", lp.nfactors, "factors", len(lp.groups), "groups")
+
+
+def random_nary(seed=0, nvars=40, nfac=90, max_arity=4):
+    rng = np.random.default_rng(seed)
+    var_dim = rng.choice([1, 2, 3, 6], size=nvars).astype(np.int32)
+    factors = []   # (keys, rows, has_sigma)
+    for v in range(nvars):   # a prior on every variable keeps the system well conditioned
+        factors.append(([v], int(var_dim[v]), bool(v % 2)))
+    for _ in range(nfac):
+        ar = int(rng.integers(1, max_arity + 1))
+        v0 = int(rng.integers(0, nvars))
+        near = (v0 + rng.choice(np.arange(1, 9), size=ar - 1, replace=False)) % nvars   # locality => a real tree
+        factors.append(([v0] + [int(x) for x in near], int(rng.integers(1, 8)), bool(rng.integers(0, 2))))
+    order = rng.permutation(len(factors))
+    buckets = {}
+    for pos, fi in enumerate(order):
+        keys, rows, sig = factors[fi]
+        dims = tuple(int(var_dim[k]) for k in keys)
+        b = buckets.setdefault((rows, sig) + dims, dict(keys=[], Ab=[], sig=[], pos=[]))
+        nc = sum(dims) + 1
+        A = rng.normal(size=(nc, rows))
+        if len(keys) == 1 and rows == dims[0]:
+            A[:rows, :] += 3.0 * np.eye(rows)
+        b["keys"].append(keys)
+        b["Ab"].append(A)
+        b["sig"].append(rng.uniform(0.2, 3.0, size=rows))
+        b["pos"].append(pos)
+    groups = [LN.JacobianGroup(sig[0], sig[2:], np.array(b["keys"]), np.array(b["Ab"]),
+                               np.array(b["sig"]) if sig[1] else None, graph_index=np.array(b["pos"]))
+              for sig, b in buckets.items()]
+    return LN.LinearProblem(var_dim, rng.permutation(nvars), groups)
+
+
+def arity8(seed=3):
+    rng = np.random.default_rng(seed)
+    nv = 12
+    var_dim = np.array([2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1], dtype=np.int32)
+    pri = [LN.JacobianGroup(int(d), [int(d)], np.array([[v] for v in range(nv) if var_dim[v] == d]),
+                            np.array([np.concatenate([2 * np.eye(d), rng.normal(size=(1, d))], 0) for v in range(nv) if var_dim[v] == d]))
+           for d in (1, 2, 3)]
+    keys = np.array([[0, 1, 2, 3, 4, 5, 6, 7], [3, 4, 5, 6, 7, 8, 9, 10]])
+    dims = [int(var_dim[k]) for k in keys[0]]
+    assert dims == [int(var_dim[k]) for k in keys[1]]
+    big = LN.JacobianGroup(5, dims, keys, rng.normal(size=(2, sum(dims) + 1, 5)), rng.uniform(0.5, 2.0, size=(2, 5)))
+    return LN.LinearProblem(var_dim, rng.permutation(nv), pri + [big])
+
+
+def from_typed_dump(case):
+    """The reference's linearization of a typed problem (whitened [A|b] of <case>.dump0.bin) as a linear problem."""
+    prob = P.Problem.load(os.path.join(HERE, f"{case}.prob.bin"))
+    ref = refio.read_out(os.path.join(HERE, f"{case}.dump0.bin"))
+    vd = prob.var_dims
+    groups = []
+    for gi, g in enumerate(prob.groups):
+        d, nc = P.FACTOR_DIM[g.type], P.factor_ncols(g.type)
+        dims = [int(vd[k]) for k in g.keys[0]]
+        groups.append(LN.JacobianGroup(d, dims, g.keys, ref[f"J{gi}"].reshape(g.count, nc, d), None,
+                                       graph_index0=g.graph_index0, graph_index=g.graph_index))
+    return LN.LinearProblem(vd.astype(np.int32), prob.ordering, groups)
+
+
+def singular():
+    # x0 -- x1 -- x2 chain with no prior anywhere: A^T A is rank deficient
+    rng = np.random.default_rng(9)
+    Ab = np.zeros((2, 5, 2))
+    for f in range(2):
+        Ab[f, 0:2, :] = np.eye(2)
+        Ab[f, 2:4, :] = -np.eye(2)
+        Ab[f, 4, :] = rng.normal(size=2)
+    return LN.LinearProblem(np.array([2, 2, 2], dtype=np.int32), np.array([0, 1, 2]),
+                            [LN.JacobianGroup(2, [2, 2], np.array([[0, 1], [1, 2]]), Ab)])
+
+
+def main():
+    assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    subprocess.check_call([H, "linearize2d", os.path.join(REF_DATA, "noisyToyGraph.txt"), os.path.join(HERE, "lin_pose2_toy.lin.bin")])
+    emit("lin_pose2_toy")
+    emit("lin_random_nary", random_nary())
+    emit("lin_arity8", arity8())
+    emit("lin_sphere_tiny", from_typed_dump("sphere_tiny"))
+    emit("lin_bal_tiny", from_typed_dump("bal_tiny_s2"))
+    emit("lin_singular", singular())
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,7 @@ def ref_clique_set(ref):
 
 def ref_conditionals(prob, ref):
     """{frontal tuple: [R S d] (f x n)} from a dump."""
-    dims = np.asarray(P.VAR_DIM)[prob.var_type]
+    dims = prob.var_dims
     out = {}
     fp, fv, sp, sv = (ref["clique_frontal_ptr"], ref["clique_frontal_vars"], ref["clique_separator_ptr"],
                       ref["clique_separator_vars"])
@@ -98,11 +98,15 @@ def check_against_dump(be, prob, ref, lam, diag, tol_j=1e-12, tol_delta=1e-8, to
     assert abs(ne - ref["new_error"][0]) <= 1e-8 * loose * max(1.0, abs(ref["new_error"][0]))
     be.accept_step()
     assert relmax(be.get_values(), ref["new_values"]) <= 1e-9 * loose
-    # junction tree + conditionals
+    check_tree_against_dump(be, prob, ref, loose)
+
+
+def check_tree_against_dump(be, prob, ref, loose=1.0):
+    """junction tree + conditionals [R S d] of every clique against a reference dump"""
     fp, fv_, sp, sv, par = be.cliques()
     assert clique_set(fp, fv_, sp, sv) == ref_clique_set(ref)
     rc = ref_conditionals(prob, ref)
-    dims = np.asarray(P.VAR_DIM)[prob.var_type]
+    dims = prob.var_dims
     for c in range(len(par)):
         fr = tuple(int(x) for x in fv_[fp[c]:fp[c + 1]])
         Rref, sref = rc[fr]
@@ -121,6 +125,34 @@ def check_against_dump(be, prob, ref, lam, diag, tol_j=1e-12, tol_delta=1e-8, to
         cols.append(mine.shape[1] - 1)
         scale = max(1.0, np.abs(Rref).max())
         assert np.abs(mine[:, cols] - Rref).max() <= 1e-7 * scale * loose, (c, fr)
+
+
+LINEAR_CASES = ["lin_pose2_toy", "lin_random_nary", "lin_arity8", "lin_sphere_tiny", "lin_bal_tiny", "lin_singular"]
+LINEAR_LAMBDA = {0: 0.0, 1: 0.25}   # *.out0.bin / *.out1.bin (tests/golden/make_golden_linear.py)
+
+
+def load_linear_case(name):
+    from gtsam_b200 import linear as LN
+    lp = LN.LinearProblem.load(os.path.join(GOLDEN, f"{name}.lin.bin"))
+    lp.name = name
+    return lp
+
+
+def check_linear_against_reference(be, lp, ref, lam, tol_delta=1e-9):
+    """`be` is an OracleLinearProblem or a LinearDeviceProblem: every stage of GaussianFactorGraph::optimize against
+    the reference's own run on the same JacobianFactors (ref_harness linsolve)."""
+    for gi, g in enumerate(lp.groups):     # whitening (JacobianFactor::whiten) happened at creation
+        assert relmax(be.get_jacobians(gi), g.whitened()) <= 1e-15
+    assert relmax(be.hessian_diagonal(), ref["hessian_diagonal"]) <= 1e-12
+    st, e0, e1, fv = be.solve(lam)
+    assert st == ref["status"][0], (st, ref["status"][0])
+    if st != 0:
+        assert 0 <= fv < lp.nvars
+        return
+    assert rel2(be.get_delta(), ref["delta"]) <= tol_delta
+    assert abs(e0 - ref["linear_error_zero"][0]) <= 1e-11 * abs(ref["linear_error_zero"][0])
+    assert abs(e1 - ref["linear_error_delta"][0]) <= 1e-9 * abs(ref["linear_error_zero"][0])
+    check_tree_against_dump(be, lp, ref)
 
 
 def edge_case_problems():
