@@ -448,4 +448,201 @@ VectorValues solveOnDevice(const NonlinearFactorGraph& graph, const Values& valu
   return dev.currentDelta();
 }
 
+// ---- GaussianFactorGraph level ---------------------------------------------------------------
+// JacobianFactors bucketed by shape (rows, has-model, block widths); keys -> dense ids in ascending Key order.
+struct LinGroup {
+  int rows = 0;
+  bool has_model = false;
+  std::vector<int32_t> dims;
+  std::vector<int64_t> keys, pos;
+  std::vector<double> Ab, sigmas;
+  int64_t count = 0;
+};
+struct LinearState {
+  std::vector<Key> id2key;
+  std::map<Key, int64_t> key2id;
+  std::vector<int32_t> var_dim;
+  std::vector<int64_t> dof_off;
+  std::vector<LinGroup> groups;
+  std::vector<std::vector<int>> signature;   // per graph position: (rows, has-model, key ids...)
+  b200_ctx* ctx = nullptr;
+  b200_problem* prob = nullptr;
+  int builds = 0, solves = 0;
+
+  ~LinearState() { reset(); if (ctx) b200_ctx_destroy(ctx); }
+  void reset() { if (prob) { b200_problem_destroy(prob); prob = nullptr; } }
+
+  static std::shared_ptr<JacobianFactor> asJacobian(const GaussianFactor::shared_ptr& f, size_t pos) {
+    if (!f) throw std::invalid_argument("gtsam_b200: null factor in the GaussianFactorGraph at position " + std::to_string(pos));
+    auto jf = std::dynamic_pointer_cast<JacobianFactor>(f);
+    if (!jf) throw std::invalid_argument("gtsam_b200: only JacobianFactors are supported at the linear level (position " +
+                                         std::to_string(pos) + " holds another GaussianFactor type); no CPU fallback");
+    const SharedDiagonal& m = jf->get_model();
+    if (m && m->isConstrained()) throw std::invalid_argument("gtsam_b200: Constrained noise models are out of scope (need QR)");
+    return jf;
+  }
+
+  // (rows, has-model, key ids) of every factor; false if `gfg` has another structure than the packed one
+  bool sameStructure(const GaussianFactorGraph& gfg) const {
+    if (!prob || gfg.size() != signature.size()) return false;
+    for (size_t pos = 0; pos < gfg.size(); pos++) {
+      auto jf = asJacobian(gfg[pos], pos);
+      const std::vector<int>& sig = signature[pos];
+      const SharedDiagonal& m = jf->get_model();
+      if ((int)jf->rows() != sig[0] || (int)(m && !m->isUnit()) != sig[1] || jf->size() + 2 != sig.size()) return false;
+      size_t a = 2;
+      for (auto it = jf->begin(); it != jf->end(); ++it, ++a) {
+        auto id = key2id.find(*it);
+        if (id == key2id.end() || (int)id->second != sig[a] || (int)jf->getDim(it) != var_dim[id->second]) return false;
+      }
+    }
+    return true;
+  }
+
+  // numbers of every group, in the packed order
+  void fillNumbers(const GaussianFactorGraph& gfg) {
+    for (auto& g : groups) { g.Ab.clear(); g.sigmas.clear(); }
+    for (auto& g : groups)
+      for (int64_t pos : g.pos) {
+        auto jf = std::static_pointer_cast<JacobianFactor>(gfg[(size_t)pos]);
+        const Matrix Ab = jf->augmentedJacobianUnweighted();   // [A1 .. Ak b], unwhitened; whitening is a device kernel
+        g.Ab.insert(g.Ab.end(), Ab.data(), Ab.data() + Ab.size());   // Eigen default is column-major
+        if (g.has_model) { const Vector s = jf->get_model()->sigmas(); g.sigmas.insert(g.sigmas.end(), s.data(), s.data() + s.size()); }
+      }
+  }
+
+  void build(const GaussianFactorGraph& gfg, const Ordering& ordering) {
+    reset();
+    id2key.clear(); key2id.clear(); var_dim.clear(); dof_off.assign(1, 0); groups.clear(); signature.clear();
+    std::map<Key, int> dimOf;
+    for (size_t pos = 0; pos < gfg.size(); pos++) {
+      auto jf = asJacobian(gfg[pos], pos);
+      for (auto it = jf->begin(); it != jf->end(); ++it) {
+        auto ins = dimOf.emplace(*it, (int)jf->getDim(it));
+        if (!ins.second && ins.first->second != (int)jf->getDim(it))
+          throw std::invalid_argument("gtsam_b200: variable " + DefaultKeyFormatter(*it) + " appears with two different dimensions");
+      }
+    }
+    for (auto& kv : dimOf) {   // std::map iterates in ascending Key order
+      key2id[kv.first] = (int64_t)id2key.size();
+      id2key.push_back(kv.first);
+      var_dim.push_back(kv.second);
+      dof_off.push_back(dof_off.back() + kv.second);
+    }
+    std::map<std::vector<int>, size_t> bucket;
+    for (size_t pos = 0; pos < gfg.size(); pos++) {
+      auto jf = std::static_pointer_cast<JacobianFactor>(gfg[pos]);
+      const SharedDiagonal& m = jf->get_model();
+      const bool has_model = m && !m->isUnit();
+      if (jf->size() < 1 || jf->size() > B200_JACOBIAN_MAX_ARITY)
+        throw std::invalid_argument("gtsam_b200: JacobianFactor with " + std::to_string(jf->size()) + " keys (supported: 1.." +
+                                    std::to_string(B200_JACOBIAN_MAX_ARITY) + ")");
+      std::vector<int> shape{(int)jf->rows(), (int)has_model}, sig{(int)jf->rows(), (int)has_model};
+      for (auto it = jf->begin(); it != jf->end(); ++it) { shape.push_back((int)jf->getDim(it)); sig.push_back((int)key2id.at(*it)); }
+      signature.push_back(sig);
+      auto found = bucket.find(shape);
+      if (found == bucket.end()) {
+        LinGroup g;
+        g.rows = (int)jf->rows(); g.has_model = has_model;
+        for (auto it = jf->begin(); it != jf->end(); ++it) g.dims.push_back((int32_t)jf->getDim(it));
+        groups.push_back(g);
+        found = bucket.emplace(shape, groups.size() - 1).first;
+      }
+      LinGroup& g = groups[found->second];
+      for (auto it = jf->begin(); it != jf->end(); ++it) g.keys.push_back(key2id.at(*it));
+      g.pos.push_back((int64_t)pos);
+      g.count++;
+    }
+    fillNumbers(gfg);
+    std::vector<int64_t> ord;
+    for (Key k : ordering) {
+      auto it = key2id.find(k);
+      if (it == key2id.end()) throw std::invalid_argument("gtsam_b200: ordering contains a key that is not in the graph");
+      ord.push_back(it->second);
+    }
+    if (ord.size() != id2key.size()) throw std::invalid_argument("gtsam_b200: ordering must cover every variable of the graph");
+    std::vector<b200_jacobian_group> cg(groups.size());
+    for (size_t i = 0; i < groups.size(); i++) {
+      const LinGroup& g = groups[i];
+      cg[i].rows = g.rows; cg[i].arity = (int32_t)g.dims.size(); cg[i].dims = g.dims.data(); cg[i].count = g.count;
+      cg[i].graph_index0 = -1; cg[i].graph_index = g.pos.data(); cg[i].keys = g.keys.data(); cg[i].Ab = g.Ab.data();
+      cg[i].sigmas = g.has_model ? g.sigmas.data() : nullptr;
+    }
+    b200_linear_desc desc;
+    desc.nvars = (int64_t)id2key.size(); desc.var_dim = var_dim.data(); desc.ordering = ord.data();
+    desc.ngroups = (int64_t)cg.size(); desc.groups = cg.data();
+    if (!ctx) {
+      const char* devEnv = std::getenv("B200_DEVICE");
+      check(b200_ctx_create(devEnv ? std::atoi(devEnv) : 0, &ctx), "b200_ctx_create");
+    }
+    check(b200_linear_create(ctx, &desc, &prob), "b200_linear_create");
+    builds++;
+  }
+
+  void update(const GaussianFactorGraph& gfg) {
+    fillNumbers(gfg);
+    for (size_t i = 0; i < groups.size(); i++)
+      check(b200_linear_update(prob, (int64_t)i, groups[i].Ab.data(), groups[i].has_model ? groups[i].sigmas.data() : nullptr),
+            "b200_linear_update");
+  }
+
+  VectorValues solve() {
+    double e0, e1;
+    int64_t fv = -1;
+    const int rc = b200_solve(prob, 0.0, 0, 0.0, 0.0, &e0, &e1, &fv);
+    if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(fv >= 0 ? id2key[(size_t)fv] : 0);
+    check(rc, "b200_solve");
+    solves++;
+    std::vector<double> dl((size_t)b200_delta_size(prob));
+    check(b200_get_delta(prob, dl.data()), "b200_get_delta");
+    VectorValues out;
+    for (size_t i = 0; i < id2key.size(); i++)
+      out.insert(id2key[i], Eigen::Map<const Vector>(dl.data() + dof_off[i], dof_off[i + 1] - dof_off[i]));
+    return out;
+  }
+};
+
+B200LinearSolver::B200LinearSolver(const Ordering& ordering) : ordering_(ordering), st_(std::make_shared<LinearState>()) {}
+B200LinearSolver::~B200LinearSolver() {}
+VectorValues B200LinearSolver::optimize(const GaussianFactorGraph& gfg) {
+  if (st_->sameStructure(gfg)) st_->update(gfg);
+  else st_->build(gfg, ordering_);
+  return st_->solve();
+}
+int B200LinearSolver::structureBuilds() const { return st_->builds; }
+int B200LinearSolver::solves() const { return st_->solves; }
+long long B200LinearSolver::launchCount() const { return st_->ctx ? b200_launch_count(st_->ctx) : 0; }
+
+VectorValues optimizeOnDevice(const GaussianFactorGraph& gfg, const Ordering& ordering) {
+  B200LinearSolver solver(ordering);
+  return solver.optimize(gfg);
+}
+
+static void requireMultifrontalCholesky(const NonlinearOptimizerParams& params) {
+  if (params.linearSolverType != NonlinearOptimizerParams::MULTIFRONTAL_CHOLESKY)
+    throw std::invalid_argument("gtsam_b200: the device solve() is multifrontal Cholesky "
+                                "(NonlinearOptimizerParams::MULTIFRONTAL_CHOLESKY); other linearSolverType values have no device path");
+}
+
+B200SolveLevenbergMarquardtOptimizer::B200SolveLevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                                           const LevenbergMarquardtParams& params)
+    : LevenbergMarquardtOptimizer(graph, initialValues, params) {}
+B200SolveLevenbergMarquardtOptimizer::B200SolveLevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                                           const Ordering& ordering, const LevenbergMarquardtParams& params)
+    : LevenbergMarquardtOptimizer(graph, initialValues, ordering, params) {}
+VectorValues B200SolveLevenbergMarquardtOptimizer::solve(const GaussianFactorGraph& gfg, const NonlinearOptimizerParams& params) const {
+  requireMultifrontalCholesky(params);
+  if (!solver_) solver_ = std::make_shared<B200LinearSolver>(*params.ordering);   // set by the base constructor (ensureHasOrdering)
+  return solver_->optimize(gfg);
+}
+
+B200SolveGaussNewtonOptimizer::B200SolveGaussNewtonOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                             const GaussNewtonParams& params)
+    : GaussNewtonOptimizer(graph, initialValues, params) {}
+VectorValues B200SolveGaussNewtonOptimizer::solve(const GaussianFactorGraph& gfg, const NonlinearOptimizerParams& params) const {
+  requireMultifrontalCholesky(params);
+  if (!solver_) solver_ = std::make_shared<B200LinearSolver>(*params.ordering);
+  return solver_->optimize(gfg);
+}
+
 }  // namespace gtsam_b200

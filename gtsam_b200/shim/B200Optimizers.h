@@ -128,6 +128,66 @@ class B200Marginals {
   std::shared_ptr<DeviceState> dev_;
 };
 
+/// GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky) (gtsam/linear/GaussianFactorGraph.cpp:316-319) on the
+/// device for ANY graph of JacobianFactors (any arity / block widths, Unit or Diagonal models): the
+/// "GaussianFactorGraph::optimize-level entry" of SURVEY 8b.  HessianFactors and Constrained models =>
+/// std::invalid_argument (no CPU fallback); a singular system => IndeterminantLinearSystemException as in the reference.
+gtsam::VectorValues optimizeOnDevice(const gtsam::GaussianFactorGraph& gfg, const gtsam::Ordering& ordering);
+
+struct LinearState;  // packed JacobianFactor groups + C-ABI handles
+
+/// The same, keeping the device problem: successive graphs with the SAME structure (the next linearization of one
+/// nonlinear graph, the next lambda of LM's damped system) only re-upload numbers (b200_linear_update); the symbolic
+/// phase, which the reference repeats inside every optimize() (VariableIndex + elimination tree + junction tree,
+/// gtsam/inference/EliminateableFactorGraph-inst.h:123-146), runs once.
+class B200LinearSolver {
+ public:
+  explicit B200LinearSolver(const gtsam::Ordering& ordering);
+  ~B200LinearSolver();
+  /// solve `gfg` (re-packs only if its structure differs from the previous call's)
+  gtsam::VectorValues optimize(const gtsam::GaussianFactorGraph& gfg);
+  /// how many times the structure was (re)built / how many solves reused it
+  int structureBuilds() const;
+  int solves() const;
+  long long launchCount() const;
+
+ private:
+  gtsam::Ordering ordering_;
+  std::shared_ptr<LinearState> st_;
+};
+
+/// LevenbergMarquardtOptimizer whose linear-solve seam
+///     virtual VectorValues NonlinearOptimizer::solve(const GaussianFactorGraph&, const NonlinearOptimizerParams&) const
+/// (gtsam/nonlinear/NonlinearOptimizer.h:128-130, called by tryLambda at LevenbergMarquardtOptimizer.cpp:156) runs on the
+/// device.  linearize(), the damped system, retract and error stay the reference's own host code, so this variant
+/// accepts ANY factor type GTSAM can linearize (e.g. the Pose2 graph of BASELINE configs[0]); use
+/// B200LevenbergMarquardtOptimizer when all factors are of the device-resident kinds.
+/// Requires linearSolverType MULTIFRONTAL_CHOLESKY (the default); anything else => std::invalid_argument.
+class B200SolveLevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimizer {
+ public:
+  B200SolveLevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                       const gtsam::LevenbergMarquardtParams& params = gtsam::LevenbergMarquardtParams());
+  B200SolveLevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                       const gtsam::Ordering& ordering,
+                                       const gtsam::LevenbergMarquardtParams& params = gtsam::LevenbergMarquardtParams());
+  gtsam::VectorValues solve(const gtsam::GaussianFactorGraph& gfg, const gtsam::NonlinearOptimizerParams& params) const override;
+  const B200LinearSolver& linearSolver() const { return *solver_; }
+
+ private:
+  mutable std::shared_ptr<B200LinearSolver> solver_;
+};
+
+/// The same seam on GaussNewtonOptimizer (GaussNewtonOptimizer.cpp:54).
+class B200SolveGaussNewtonOptimizer : public gtsam::GaussNewtonOptimizer {
+ public:
+  B200SolveGaussNewtonOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                const gtsam::GaussNewtonParams& params = gtsam::GaussNewtonParams());
+  gtsam::VectorValues solve(const gtsam::GaussianFactorGraph& gfg, const gtsam::NonlinearOptimizerParams& params) const override;
+
+ private:
+  mutable std::shared_ptr<B200LinearSolver> solver_;
+};
+
 /// GaussianFactorGraph::optimize-level entry for the nonlinear graph at `values`:
 /// one undamped (lambda = 0) or damped linearize + multifrontal solve on the device.
 gtsam::VectorValues solveOnDevice(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& values,

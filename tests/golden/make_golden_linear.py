@@ -6,6 +6,9 @@ container:
 
 * lin_pose2_toy   — BASELINE.json configs[0]: examples/Data/noisyToyGraph.txt (Pose2 g2o + the example's prior)
                     linearized BY THE REFERENCE at the file's initial estimate, COLAMD ordering.
+* lin_pose2_synth — the same for tests/golden/data/synthetic_pose2.g2o (40 poses on a ring, odometry + loop closures,
+                    written by synthetic_pose2() below); pose2_synth_reference.json records the reference's
+                    Pose2SLAMExample_g2o path (GN as shipped, LM as configs[0] names it) on that file.
 * lin_random_nary — random JacobianFactors of arity 1..4, rows 1..7, block widths 1/2/3/6, half of the groups with a
                     Diagonal model (sigmas), random elimination order.
 * lin_arity8      — a few factors of the maximum supported arity (8).
@@ -102,6 +105,31 @@ def from_typed_dump(case):
     return LN.LinearProblem(vd.astype(np.int32), prob.ordering, groups)
 
 
+def synthetic_pose2(path, n=40, seed=21):
+    """A Pose2 g2o file in the format of examples/Data/noisyToyGraph.txt (VERTEX_SE2 / EDGE_SE2 with the upper
+    triangle of the information matrix): n poses on a ring expressed in the frame of pose 0 (the example pins pose 0
+    at the origin), odometry + two families of loop closures."""
+    rng = np.random.default_rng(seed)
+    th = 2 * np.pi * np.arange(n) / n
+    ring = np.stack([10 * np.cos(th), 10 * np.sin(th), th + np.pi / 2], -1)
+
+    def between(a, b):
+        c, s = np.cos(a[2]), np.sin(a[2])
+        d = b[:2] - a[:2]
+        return np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1], (b[2] - a[2] + np.pi) % (2 * np.pi) - np.pi])
+
+    gt = np.array([between(ring[0], p) for p in ring])
+    init = gt + rng.normal(size=gt.shape) * np.array([0.3, 0.3, 0.05])
+    init[0] = 0
+    edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 7) % n) for i in range(0, n, 3)] + [(i, (i + 19) % n) for i in range(1, n, 5)]
+    lines = ["VERTEX_SE2 %d %.9f %.9f %.9f" % (i, *init[i]) for i in range(n)]
+    for (i, j) in edges:
+        z = between(gt[i], gt[j]) + rng.normal(size=3) * np.array([0.05, 0.05, 0.01])
+        lines.append("EDGE_SE2 %d %d %.9f %.9f %.9f 400 0 0 400 0 10000" % (i, j, *z))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 def singular():
     # x0 -- x1 -- x2 chain with no prior anywhere: A^T A is rank deficient
     rng = np.random.default_rng(9)
@@ -118,6 +146,12 @@ def main():
     assert refio.have_ref(), "build oracle/_ref first: make -C oracle ref"
     subprocess.check_call([H, "linearize2d", os.path.join(REF_DATA, "noisyToyGraph.txt"), os.path.join(HERE, "lin_pose2_toy.lin.bin")])
     emit("lin_pose2_toy")
+    g2o = os.path.join(HERE, "data", "synthetic_pose2.g2o")
+    synthetic_pose2(g2o)
+    subprocess.check_call([H, "linearize2d", g2o, os.path.join(HERE, "lin_pose2_synth.lin.bin")])
+    emit("lin_pose2_synth")
+    with open(os.path.join(HERE, "pose2_synth_reference.json"), "w") as f:
+        f.write(subprocess.check_output([H, "pose2", g2o]).decode().strip().splitlines()[-1] + "\n")
     emit("lin_random_nary", random_nary())
     emit("lin_arity8", arity8())
     emit("lin_sphere_tiny", from_typed_dump("sphere_tiny"))
