@@ -465,6 +465,9 @@ struct LinearState {
   std::vector<int64_t> dof_off;
   std::vector<LinGroup> groups;
   std::vector<std::vector<int>> signature;   // per graph position: (rows, has-model, key ids...)
+  std::vector<int64_t> ord;
+  std::vector<b200_jacobian_group> cg;
+  b200_linear_desc desc;
   b200_ctx* ctx = nullptr;
   b200_problem* prob = nullptr;
   int builds = 0, solves = 0;
@@ -511,8 +514,8 @@ struct LinearState {
       }
   }
 
-  void build(const GaussianFactorGraph& gfg, const Ordering& ordering) {
-    reset();
+  // the C-ABI description of `gfg` (b200_linear_desc over this object's own buffers)
+  void pack(const GaussianFactorGraph& gfg, const Ordering& ordering) {
     id2key.clear(); key2id.clear(); var_dim.clear(); dof_off.assign(1, 0); groups.clear(); signature.clear();
     std::map<Key, int> dimOf;
     for (size_t pos = 0; pos < gfg.size(); pos++) {
@@ -554,23 +557,27 @@ struct LinearState {
       g.count++;
     }
     fillNumbers(gfg);
-    std::vector<int64_t> ord;
+    ord.clear();
     for (Key k : ordering) {
       auto it = key2id.find(k);
       if (it == key2id.end()) throw std::invalid_argument("gtsam_b200: ordering contains a key that is not in the graph");
       ord.push_back(it->second);
     }
     if (ord.size() != id2key.size()) throw std::invalid_argument("gtsam_b200: ordering must cover every variable of the graph");
-    std::vector<b200_jacobian_group> cg(groups.size());
+    cg.assign(groups.size(), b200_jacobian_group());
     for (size_t i = 0; i < groups.size(); i++) {
       const LinGroup& g = groups[i];
       cg[i].rows = g.rows; cg[i].arity = (int32_t)g.dims.size(); cg[i].dims = g.dims.data(); cg[i].count = g.count;
       cg[i].graph_index0 = -1; cg[i].graph_index = g.pos.data(); cg[i].keys = g.keys.data(); cg[i].Ab = g.Ab.data();
       cg[i].sigmas = g.has_model ? g.sigmas.data() : nullptr;
     }
-    b200_linear_desc desc;
     desc.nvars = (int64_t)id2key.size(); desc.var_dim = var_dim.data(); desc.ordering = ord.data();
     desc.ngroups = (int64_t)cg.size(); desc.groups = cg.data();
+  }
+
+  void build(const GaussianFactorGraph& gfg, const Ordering& ordering) {
+    reset();
+    pack(gfg, ordering);
     if (!ctx) {
       const char* devEnv = std::getenv("B200_DEVICE");
       check(b200_ctx_create(devEnv ? std::atoi(devEnv) : 0, &ctx), "b200_ctx_create");
@@ -616,6 +623,27 @@ long long B200LinearSolver::launchCount() const { return st_->ctx ? b200_launch_
 VectorValues optimizeOnDevice(const GaussianFactorGraph& gfg, const Ordering& ordering) {
   B200LinearSolver solver(ordering);
   return solver.optimize(gfg);
+}
+
+std::vector<std::pair<KeyVector, KeyVector>> symbolicOnHost(const GaussianFactorGraph& gfg, const Ordering& ordering) {
+  LinearState st;
+  st.pack(gfg, ordering);
+  b200_symbolic* sym = nullptr;
+  check(b200_linear_symbolic_create(&st.desc, &sym), "b200_linear_symbolic_create");
+  b200_symbolic_info info;
+  b200_symbolic_get_info(sym, &info);
+  std::vector<int64_t> fp(info.ncliques + 1), sp(info.ncliques + 1), fv(std::max<int64_t>(1, info.frontal_list_len)),
+      sv(std::max<int64_t>(1, info.separator_list_len)), par(std::max<int64_t>(1, info.ncliques));
+  b200_symbolic_get_cliques(sym, fp.data(), fv.data(), sp.data(), sv.data(), par.data());
+  b200_symbolic_destroy(sym);
+  std::vector<std::pair<KeyVector, KeyVector>> out;
+  for (int64_t c = 0; c < info.ncliques; c++) {
+    KeyVector f, s;
+    for (int64_t q = fp[c]; q < fp[c + 1]; q++) f.push_back(st.id2key[(size_t)fv[q]]);
+    for (int64_t q = sp[c]; q < sp[c + 1]; q++) s.push_back(st.id2key[(size_t)sv[q]]);
+    out.emplace_back(f, s);
+  }
+  return out;
 }
 
 static void requireMultifrontalCholesky(const NonlinearOptimizerParams& params) {

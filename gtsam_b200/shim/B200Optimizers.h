@@ -134,6 +134,12 @@ class B200Marginals {
 /// std::invalid_argument (no CPU fallback); a singular system => IndeterminantLinearSystemException as in the reference.
 gtsam::VectorValues optimizeOnDevice(const gtsam::GaussianFactorGraph& gfg, const gtsam::Ordering& ordering);
 
+/// Host-only (needs no GPU): packs `gfg` exactly as optimizeOnDevice does and runs the library's symbolic phase;
+/// returns (frontal keys, separator keys) of every clique in elimination order — the cliques the reference's
+/// eliminateMultifrontal(ordering) builds.  For inspection and CPU-side tests of the packing.
+std::vector<std::pair<gtsam::KeyVector, gtsam::KeyVector>> symbolicOnHost(const gtsam::GaussianFactorGraph& gfg,
+                                                                           const gtsam::Ordering& ordering);
+
 struct LinearState;  // packed JacobianFactor groups + C-ABI handles
 
 /// The same, keeping the device problem: successive graphs with the SAME structure (the next linearization of one

@@ -6,6 +6,9 @@
  *       gtsam::GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky)   (reference, CPU)
  *       gtsam_b200::optimizeOnDevice(gfg, ordering)                               (GPU through the C-ABI)
  *       + B200LinearSolver reused on a perturbed copy of the graph (same structure => numbers only)
+ *   shim_linear hostpack <problem.lin.bin>     (no GPU needed)
+ *       the shim's packing of the GaussianFactorGraph + the library's host symbolic phase vs the cliques of the
+ *       reference's eliminateMultifrontal
  *   shim_linear pose2 <file.g2o> [maxit]
  *       BASELINE.json configs[0]: the Pose2 g2o graph + the example's prior (examples/Pose2SLAMExample_g2o.cpp:46-64);
  *       stock gtsam::LevenbergMarquardtOptimizer vs gtsam_b200::B200SolveLevenbergMarquardtOptimizer (solve() seam on
@@ -17,6 +20,7 @@
 #include "../gtsam_b200/shim/B200Optimizers.h"
 
 #include <gtsam/geometry/Pose2.h>
+#include <gtsam/linear/GaussianBayesTree.h>
 #include <gtsam/linear/linearExceptions.h>
 #include <gtsam/slam/dataset.h>
 
@@ -68,6 +72,35 @@ static int cmd_graph(const std::string& path) {
   }
   printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, "
          "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, builds, solves, launches);
+  return 0;
+}
+
+/* host only: the shim's packing + the library's symbolic phase against the reference's Bayes tree */
+static int cmd_hostpack(const std::string& path) {
+  linio::LinProb lp = linio::load(path);
+  GaussianFactorGraph gfg = linio::build_graph(lp);
+  Ordering ordering = linio::build_ordering(lp);
+  auto mine = gtsam_b200::symbolicOnHost(gfg, ordering);
+  typedef std::pair<std::vector<Key>, std::vector<Key>> CS;
+  std::vector<CS> a, b;
+  for (auto& c : mine) { CS x(std::vector<Key>(c.first.begin(), c.first.end()), std::vector<Key>(c.second.begin(), c.second.end())); std::sort(x.second.begin(), x.second.end()); a.push_back(x); }
+  GaussianFactorGraph sys = gfg;
+  for (int64_t v = 0; v < lp.nvars; v++) {   // damping priors keep a singular fixture eliminable; they do not change the structure
+    const int d = lp.var_dim[v];
+    sys.push_back(std::make_shared<JacobianFactor>(Key(v), Matrix::Identity(d, d), Vector::Zero(d)));
+  }
+  auto bt = sys.eliminateMultifrontal(ordering, EliminatePreferCholesky);
+  std::vector<GaussianBayesTree::sharedClique> stack(bt->roots().begin(), bt->roots().end());
+  while (!stack.empty()) {
+    auto c = stack.back(); stack.pop_back();
+    auto cond = c->conditional();
+    CS x(std::vector<Key>(cond->beginFrontals(), cond->endFrontals()), std::vector<Key>(cond->beginParents(), cond->endParents()));
+    std::sort(x.second.begin(), x.second.end());
+    b.push_back(x);
+    for (auto& ch : c->children) stack.push_back(ch);
+  }
+  std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+  printf("{\"cliques\": %zu, \"reference_cliques\": %zu, \"equal\": %d}\n", a.size(), b.size(), (int)(a == b));
   return 0;
 }
 
@@ -123,6 +156,7 @@ static int cmd_pose2(const std::string& path, int maxit) {
 
 int main(int argc, char** argv) {
   if (argc >= 3 && std::string(argv[1]) == "graph") return cmd_graph(argv[2]);
+  if (argc >= 3 && std::string(argv[1]) == "hostpack") return cmd_hostpack(argv[2]);
   if (argc >= 3 && std::string(argv[1]) == "pose2") return cmd_pose2(argv[2], argc > 3 ? atoi(argv[3]) : 30);
   fprintf(stderr, "usage: shim_linear graph problem.lin.bin | pose2 file.g2o [maxit]\n");
   return 2;

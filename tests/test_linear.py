@@ -133,3 +133,19 @@ def test_linear_description_is_validated(built):
     assert status(lambda q: q.groups[3].keys.__setitem__((0, 1), int(q.groups[3].keys[0, 0]))) == P.INVALID_ARGUMENT   # dims / duplicate
     assert status(lambda q: q.var_dim.__setitem__(0, 5)) == P.INVALID_ARGUMENT                        # block width mismatch
     assert status(lambda q: q.ordering.__setitem__(0, int(q.ordering[1]))) == P.INVALID_ARGUMENT      # not a permutation
+
+
+SHIM_LINEAR = __import__("os").path.join(__import__("os").path.dirname(util.GOLDEN), "..", "oracle", "_ref", "shim_linear")
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(SHIM_LINEAR), reason="shim_linear not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", util.LINEAR_CASES)
+def test_cpp_shim_packs_a_gaussian_factor_graph_like_the_reference(case):
+    """C++ drop-in, host side only: gtsam_b200::symbolicOnHost packs a real gtsam::GaussianFactorGraph exactly as
+    optimizeOnDevice does (ids by ascending Key, groups by shape, explicit graph positions) and runs the library's
+    symbolic phase; the cliques equal those of the reference's eliminateMultifrontal."""
+    import json
+    import subprocess
+    out = subprocess.check_output([SHIM_LINEAR, "hostpack", __import__("os").path.join(util.GOLDEN, f"{case}.lin.bin")], timeout=120)
+    r = json.loads(out.decode().strip().splitlines()[-1])
+    assert r["equal"] == 1 and r["cliques"] == r["reference_cliques"] > 0
