@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush-l2", action="store_true", help="time the K steps back to back with L2 left warm")
+    ap.add_argument("--jacobian-fp32", action="store_true",
+                    help="BASELINE configs[4]'s precision mix: whitened Jacobians stored as floats (FP32 linearize output), FP64 solve")
     return ap.parse_args()
 
 
@@ -51,6 +53,7 @@ def workload_config(prob, args):
         "factor_types": sorted({int(g.type) for g in prob.groups}),
         "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else prob.meta.get("ordering", "natural"),
         "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
+        "jacobian_storage": "fp32 (b200_set_jacobian_precision: FP64 evaluation, float [A|b], FP64 solve)" if getattr(args, "jacobian_fp32", False) else "fp64",
         "cache": ("L2 left warm between iterations (--no-flush-l2)" if getattr(args, "no_flush_l2", False) else
                   "L2 flushed between timed iterations: 256 MiB memset on the stream, outside the per-iteration CUDA-event pairs"),
         "parallelism": "single GPU" if args.gpus == 1 else
@@ -223,6 +226,9 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
     dev = capi.DeviceProblem(ctx, prob)
+    if args.jacobian_fp32:
+        dev.set_jacobian_precision(True)
+    jb = 4 if args.jacobian_fp32 else 8
     lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, device_problem=dev)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     L = dev.L
@@ -313,8 +319,8 @@ def main():
     peak, peak_src = measured_peaks()
     per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in prof.items()}
     # algorithmic bytes per step of the HBM-bound phases
-    lin_bytes = prob.linearize_bytes()
-    jac_bytes = sum(g.count * 8 * P_ncols(g) for g in prob.groups)
+    lin_bytes = prob.linearize_bytes(jb)
+    jac_bytes = sum(g.count * jb * P_ncols(g) for g in prob.groups)
     alg_bytes = {
         "linearize": lin_bytes,                                  # 184 B/projection factor + Values
         "memset_fronts": info.front_bytes,
@@ -323,7 +329,7 @@ def main():
         "eliminate_large": 2 * info.front_bytes,
         "leaf_fused": jac_bytes + info.front_bytes,              # read [A|b] of the leaf factors, write [R S d]
         # Schur SYRK of the point leaves: read [S' d'] (3 x DC per factor + 3 per point) and [A_c b] (2 x DC + 2 per factor)
-        "leaf_schur": schur_bytes(prob),
+        "leaf_schur": schur_bytes(prob, jb),
     }
     tries = max(1.0, per_step["leaf_fused"][1] if per_step["leaf_fused"][1] else per_step["back_substitute"][1])
     # phases that are ONE kernel launch (per group): the candidates for "the dominant kernel"
@@ -359,7 +365,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(prob, args),
+        "vs_baseline": None, "dtype": "f32 Jacobians + f64 solve" if args.jacobian_fp32 else "f64", "data": "synthetic", "config": workload_config(prob, args),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_values.nbytes),
                 "d2h_bytes_per_step": int(host_values.nbytes) + 64, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -388,15 +394,15 @@ def main():
         dist.destroy_process_group()
 
 
-def schur_bytes(prob):
-    """Algorithmic bytes of leaf_point_schur_kernel: read [S' d'] (3 x DC per factor + 3 per point) and
-    [A_c b] (2 x DC + 2 per factor); the run's extend-add output is negligible."""
+def schur_bytes(prob, jb=8):
+    """Algorithmic bytes of leaf_point_schur_kernel: read [S' d'] (3 x DC per factor + 3 per point, FP64) and
+    [A_c b] (2 x DC + 2 per factor, jb bytes each); the run's extend-add output is negligible."""
     from gtsam_b200 import problem as P
     total = 24 * int((prob.var_type == P.VAR_POINT3).sum())
     for g in prob.groups:
         if g.type in (P.FACTOR_PROJECTION_CAL3S2, P.FACTOR_SFM_BUNDLER):
             dc = P.factor_ncols(g.type) - 4       # camera dofs: ncols = DC + 3 + 1
-            total += g.count * 8 * (3 * dc + 2 * dc + 2)
+            total += g.count * (8 * 3 * dc + jb * (2 * dc + 2))
     return total
 
 

@@ -33,6 +33,7 @@ EXPORTS = [
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
     "b200_linear_create", "b200_linear_update", "b200_linear_symbolic_create",
+    "b200_set_jacobian_precision", "b200_get_jacobian_precision",
 ]
 
 
@@ -115,6 +116,8 @@ def lib():
         L.b200_symbolic_create.argtypes = [C.POINTER(P.CProblemDesc), C.POINTER(vp)]
         L.b200_symbolic_destroy.argtypes = [vp]
         L.b200_symbolic_get_info.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
+        L.b200_set_jacobian_precision.argtypes = [vp, C.c_int]
+        L.b200_get_jacobian_precision.argtypes = [vp]
         from . import linear as LN
         L.b200_linear_create.argtypes = [vp, C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_linear_update.argtypes = [vp, C.c_int64, dp, dp]
@@ -258,6 +261,10 @@ class DeviceProblem:
 
     def linearize(self):
         _check(self.L.b200_linearize(self.h))
+
+    def set_jacobian_precision(self, fp32: bool):
+        """FP32 storage of the whitened Jacobians ("FP32 linearize + FP64 solve", BASELINE configs[4])."""
+        _check(self.L.b200_set_jacobian_precision(self.h, int(fp32)))
 
     def get_jacobians(self, group: int):
         g = self.prob.groups[group]

@@ -78,6 +78,13 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
     case B200_FACTOR_PRIOR_CAM_BUNDLER: { constexpr int TY = B200_FACTOR_PRIOR_CAM_BUNDLER; STMT; break; } \
   }
 
+// storage type of the whitened Jacobians (b200_set_jacobian_precision): JT = float or double inside the statement
+#define DISPATCH_JT(P, ...)                                   \
+  do {                                                        \
+    if ((P)->jac_f32) { typedef float JT; __VA_ARGS__; }      \
+    else { typedef double JT; __VA_ARGS__; }                  \
+  } while (0)
+
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
@@ -156,7 +163,7 @@ static int enqueue_linearize(b200_problem* p) {
     // tiny groups (a handful of priors) are pure launch latency: timed apart from the bandwidth kernels
     PhaseScope ps(p, g.count >= 4096 ? PH_LINEARIZE : PH_LINEARIZE_MINOR);
     const int nb = (int)((g.count + 127) / 128);
-    DISPATCH_TYPE(g.type, (launch_k(linearize_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values))));
+    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linearize_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values)))));
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
@@ -171,7 +178,7 @@ static int enqueue_hdiag(b200_problem* p) {
     if (!g.count) continue;
     const int nb = (int)((g.count + 127) / 128);
     if (g.type == B200_FACTOR_JACOBIAN) launch_k(hdiag_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, p->d_hdiag);
-    else DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag)));
+    else DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag))));
     p->ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
@@ -194,7 +201,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (!g.n_nonleaf) continue;   // every factor of the group is owned by a fused leaf clique
       const int nb = (int)((g.count + 127) / 128);
       if (g.type == B200_FACTOR_JACOBIAN) launch_k(assemble_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), t);
-      else DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY>, dim3(nb), dim3(128), 0, st, view(g), t)));
+      else DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), t))));
       ctx->launches++;
     }
   }
@@ -213,9 +220,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (p->leaf_run_end[0] > p->leaf_run_begin[0]) {
       const int nr = p->leaf_run_end[0] - p->leaf_run_begin[0], nb = (nr + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const size_t sm = (size_t)kWarpsPerBlock * p->leaf_lb_cap * sizeof(double);
-      launch_k(leaf_fused_kernel, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[0], nr,
+      DISPATCH_JT(p, launch_k(leaf_fused_kernel<JT>, dim3(nb), dim3(kWarpsPerBlock * 32), sm, st, t, gt, p->d_fused_list, p->d_fused_run_ptr + p->leaf_run_begin[0], nr,
                                                            p->d_fused_fac_ptr, p->d_fused_fac, p->d_lambda, hd, min_diag, max_diag,
-                                                           p->d_scalars, p->leaf_lb_cap, 0);
+                                                           p->d_scalars, p->leaf_lb_cap, 0));
       ctx->launches++;
     }
     // BAL points: per-point factorisation (8 lanes per point) ...
@@ -224,9 +231,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       const int i0 = p->leaf_pos_begin[kd], i1 = p->leaf_pos_end[kd];
       const int nb = (int)(((int64_t)(i1 - i0) * 8 + 127) / 128);
 #define B200_LAUNCH_POINT(DC_)                                                                                                        \
-      launch_k(leaf_point_factor_kernel<DC_>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1,                 \
+      DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1, \
                (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
-               p->d_scalars);
+               p->d_scalars));
       if (kd == 1) { B200_LAUNCH_POINT(6) } else { B200_LAUNCH_POINT(9) }
 #undef B200_LAUNCH_POINT
       ctx->launches++;
@@ -246,8 +253,8 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       const int thr = ntiles <= 96 ? 96 : 128, tpt = (ntiles + thr - 1) / thr;
 #define B200_LAUNCH_SCHUR(DC_, T_, P_)                                                                                               \
       if (kd == (DC_ == 6 ? 1 : 2) && tpt == T_ && p->schur_pb == P_)                                                                \
-        launch_k(leaf_point_schur_kernel<DC_, T_, P_>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs,          \
-                 (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac);
+        DISPATCH_JT(p, launch_k(leaf_point_schur_kernel<DC_, T_, P_, JT>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs, \
+                 (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac));
       B200_LAUNCH_SCHUR(6, 1, 4) B200_LAUNCH_SCHUR(6, 2, 4) B200_LAUNCH_SCHUR(6, 3, 4)
       B200_LAUNCH_SCHUR(6, 1, 6) B200_LAUNCH_SCHUR(6, 2, 6) B200_LAUNCH_SCHUR(6, 3, 6)
       B200_LAUNCH_SCHUR(9, 1, 4) B200_LAUNCH_SCHUR(9, 2, 4) B200_LAUNCH_SCHUR(9, 3, 4)
@@ -353,8 +360,8 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       launch_k(linerr_jacobian_kernel, dim3(nb), dim3(256), 0, st, jview(g), (const double*)p->d_delta, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1,
                &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0);
     else
-    DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
-                                                                 &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0)));
+    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
+                                                                 &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0))));
     ctx->launches += 1;
     first = false;
   }
@@ -769,7 +776,9 @@ int b200_ctx_create(int device, b200_ctx** out) {
     B200_CUDA(cudaMemcpyToSymbol(kPairA, pa, sizeof pa));
     B200_CUDA(cudaMemcpyToSymbol(kPairB, pb, sizeof pb));
   }
-  B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
+  B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
@@ -1278,6 +1287,14 @@ int b200_get_jacobians(b200_problem* p, int64_t gi, double* out) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
   auto& g = p->groups[gi];
   const size_t per = (size_t)g.d * g.ncols;
+  if (p->jac_f32) {   // stored as floats (b200_set_jacobian_precision): widened for the caller
+    std::vector<float> soa(per * g.count);
+    B200_CUDA(cudaMemcpyAsync(soa.data(), g.d_J, soa.size() * sizeof(float), cudaMemcpyDeviceToHost, p->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    for (int64_t f = 0; f < g.count; f++)
+      for (size_t e = 0; e < per; e++) out[f * per + e] = (double)soa[e * g.count + f];
+    return B200_OK;
+  }
   std::vector<double> soa(per * g.count);
   B200_CUDA(cudaMemcpyAsync(soa.data(), g.d_J, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
@@ -1285,6 +1302,27 @@ int b200_get_jacobians(b200_problem* p, int64_t gi, double* out) {
     for (size_t e = 0; e < per; e++) out[f * per + e] = soa[e * g.count + f];
   return B200_OK;
 }
+
+/* "FP32 linearize + FP64 solve" (BASELINE configs[4]): store the whitened Jacobians as floats. */
+int b200_set_jacobian_precision(b200_problem* p, int fp32) {
+  if (!p) { set_error("null problem"); return B200_INVALID_ARGUMENT; }
+  if (p->linear) { set_error("b200_set_jacobian_precision: a linear problem holds the caller's FP64 [A|b]"); return B200_INVALID_ARGUMENT; }
+  const bool want = fp32 != 0;
+  if (want == p->jac_f32) return B200_OK;
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  for (auto& g : p->groups) {   // re-allocate at the new element size (the old contents are a stale linearization anyway)
+    cudaFree(g.d_J);
+    g.d_J = nullptr;
+    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)g.count * g.d * g.ncols) * (want ? sizeof(float) : sizeof(double))));
+  }
+  for (int i = 0; i < 2; i++)   // the captured LM try has the buffers and kernel instantiations baked in
+    if (p->try_graph[i]) { cudaGraphExecDestroy(p->try_graph[i]); p->try_graph[i] = nullptr; }
+  p->jac_f32 = want;
+  p->linearized = p->solved = p->factored = p->marg_ready = false;
+  return B200_OK;
+}
+int b200_get_jacobian_precision(const b200_problem* p) { return p && p->jac_f32 ? 1 : 0; }
 
 int b200_hessian_diagonal(b200_problem* p, double* out) {
   if (!p->linearized) { set_error("b200_hessian_diagonal before b200_linearize"); return B200_INVALID_ARGUMENT; }
@@ -1781,8 +1819,8 @@ static int enqueue_linerr_of(b200_problem* p, const double* x, double bscale, do
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
-    DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY>, dim3(nb), dim3(256), 0, st, view(g), x, p->d_var_dof, p0, p1, p->d_counters + 1,
-                                    &p->d_scalars->dl_scratch, out, first ? 0 : 1, bscale)));
+    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), x, p->d_var_dof, p0, p1, p->d_counters + 1,
+                                    &p->d_scalars->dl_scratch, out, first ? 0 : 1, bscale))));
     ctx->launches += 1;
     first = false;
   }
@@ -1811,7 +1849,7 @@ int b200_dl_iterate(b200_dl* dl) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
-    DISPATCH_TYPE(g.type, (gradient_kernel<TY><<<nb, 256, 0, st>>>(view(g), p->d_var_dof, dl->d_grad)));
+    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (gradient_kernel<TY, JT><<<nb, 256, 0, st>>>(view(g), p->d_var_dof, dl->d_grad))));
     ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());

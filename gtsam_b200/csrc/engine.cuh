@@ -34,7 +34,8 @@ struct GroupView {
   const double* noise;     // shared payload or per-factor AoS
   const int* cal_index;    // may be null
   const double* body;      // body_P_sensor (12 doubles) of a projection group, or null
-  double* J;               // SoA: J[e * count + f], e = r + c*D (column-major element order)
+  double* J;               // SoA: J[e * count + f], e = r + c*D (column-major element order); holds floats in the
+                           // FP32-storage mode (the kernels' JT template parameter says which)
   const int4* scat;        // (clique, slot0, slot1, unused) per factor
 };
 
@@ -103,6 +104,7 @@ struct b200_ctx {
 struct b200_problem {
   b200_ctx* ctx = nullptr;
   bool linear = false;     // created by b200_linear_create: JacobianFactor groups, no Values
+  bool jac_f32 = false;    // whitened Jacobians stored as floats (b200_set_jacobian_precision): "FP32 linearize + FP64 solve"
   b200::Symbolic sym;
   int64_t nvars = 0, nfactors = 0, nval = 0, ndelta = 0;
   std::vector<int> var_type;

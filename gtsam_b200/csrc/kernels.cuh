@@ -109,7 +109,10 @@ __device__ __forceinline__ void finish_sum(double block_value, double* partials,
 // ---------------------------------------------------------------------------
 // linearize
 // ---------------------------------------------------------------------------
-template <int TYPE>
+// JT = storage type of the whitened Jacobians: double, or float for the "FP32 linearize + FP64 solve" mode of
+// BASELINE configs[4] (b200_set_jacobian_precision): the math stays FP64 in registers, the element-major SoA holds
+// floats (half the HBM traffic of the two bandwidth-bound phases); every consumer widens back to FP64 on load.
+template <int TYPE, typename JT = double>
 __global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linearize_kernel(GroupView g, EvalCtx c) {
   pdl_sync();
   typedef FactorTraits<TYPE> FT;
@@ -128,11 +131,11 @@ __global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linea
 #pragma unroll
     for (int e = 0; e < D * NC; e++) M[e] *= w;
   }
-  double* J = g.J + f;
+  JT* J = reinterpret_cast<JT*>(g.J) + f;
 #pragma unroll
   for (int cc = 0; cc < NC; cc++)
 #pragma unroll
-    for (int r = 0; r < D; r++) J[(size_t)(r + cc * D) * g.count] = M[r * NC + cc];
+    for (int r = 0; r < D; r++) J[(size_t)(r + cc * D) * g.count] = (JT)M[r * NC + cc];
 }
 
 // ---------------------------------------------------------------------------
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) error_kernel(GroupView g, EvalCtx c, doub
 // ---------------------------------------------------------------------------
 // linear error on the undamped linearization
 // ---------------------------------------------------------------------------
-template <int TYPE>
+template <int TYPE, typename JT = double>
 __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* __restrict__ delta,
                                                      const int* __restrict__ var_dof, double* p0, double* p1,
                                                      unsigned* counters, double* out0, double* out1, int accumulate,
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* 
   double a0 = 0, a1 = 0;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
     const int2 k = g.keys[f];
-    const double* J = g.J + f;
+    const JT* J = reinterpret_cast<const JT*>(g.J) + f;
     double e[D], b[D];
 #pragma unroll
     for (int r = 0; r < D; r++) { b[r] = J[(size_t)(r + (NC - 1) * D) * g.count]; e[r] = -bscale * b[r]; }
@@ -213,13 +216,13 @@ __global__ void __launch_bounds__(256) linerr_kernel(GroupView g, const double* 
 // gtsam/nonlinear/DoglegOptimizerImpl.cpp:25-98): gradientAtZero = -A^T b per variable,
 // the three dot products of the steepest-descent and Newton points, and the blend.
 // ---------------------------------------------------------------------------
-template <int TYPE>
+template <int TYPE, typename JT = double>
 __global__ void __launch_bounds__(256) gradient_kernel(GroupView g, const int* __restrict__ var_dof, double* grad) {
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, N1 = FT::N1, N2 = FT::N2, NC = N1 + N2 + 1 };
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
     const int2 k = g.keys[f];
-    const double* J = g.J + f;
+    const JT* J = reinterpret_cast<const JT*>(g.J) + f;
     double b[D];
 #pragma unroll
     for (int r = 0; r < D; r++) b[r] = J[(size_t)(r + (NC - 1) * D) * g.count];
@@ -290,7 +293,7 @@ __device__ __forceinline__ void add_block(double* __restrict__ Mf, int ld, int s
     }
 }
 
-template <int TYPE>
+template <int TYPE, typename JT = double>
 __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) {
   pdl_sync();
   typedef FactorTraits<TYPE> FT;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) 
   const int4 sc = g.scat[f];
   if (sc.w) return;   // owned by a fused leaf clique: handled by leaf_fused_kernel
   double Jl[D * NC];  // column-major
-  const double* J = g.J + f;
+  const JT* J = reinterpret_cast<const JT*>(g.J) + f;
 #pragma unroll
   for (int e = 0; e < D * NC; e++) Jl[e] = J[(size_t)e * g.count];
   double* Mf = t.arena + t.off[sc.x];
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(GroupView g, TreeView t) 
 }
 
 // hessianDiagonal: gtsam/linear/JacobianFactor.cpp:516-541
-template <int TYPE>
+template <int TYPE, typename JT = double>
 __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __restrict__ var_dof, double* hdiag) {
   pdl_sync();
   typedef FactorTraits<TYPE> FT;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(128) hdiag_kernel(GroupView g, const int* __re
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= g.count) return;
   const int2 k = g.keys[f];
-  const double* J = g.J + f;
+  const JT* J = reinterpret_cast<const JT*>(g.J) + f;
 #pragma unroll
   for (int cc = 0; cc < N1 + N2; cc++) {
     double s = 0;
@@ -554,6 +557,7 @@ __device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
 // (lane-private accumulators, no conflicts) and extend-added once per run, which divides the
 // number of FP64 atomics into the top fronts by the run length.  A run of length 1 whose
 // separator is too wide for the accumulators falls back to direct atomics.
+template <typename JT = double>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
                   int nruns, const int* __restrict__ fac_ptr, const int2* __restrict__ fac,
@@ -587,15 +591,15 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
       const GroupView& g = gt.g[gf.x];
       const int D = kFD[g.type], N1 = kFN1[g.type], N2 = kFN2[g.type], NC = N1 + N2 + 1;
       const int4 scat = g.scat[gf.y];
-      const double* J = g.J + gf.y;
+      const JT* J = reinterpret_cast<const JT*>(g.J) + gf.y;
       const int NP = NC * (NC + 1) / 2;
       const size_t cnt = (size_t)g.count;
       for (int pi = lane; pi < NP; pi += 32) {
         const int ca = __ldg(&kPairA[g.type][pi]), cb = __ldg(&kPairB[g.type][pi]);
-        const double* Ja = J + (size_t)(ca * D) * cnt;
-        const double* Jb = J + (size_t)(cb * D) * cnt;
+        const JT* Ja = J + (size_t)(ca * D) * cnt;
+        const JT* Jb = J + (size_t)(cb * D) * cnt;
         double dot = 0;
-        for (int r = 0; r < D; r++) dot += Ja[r * cnt] * Jb[r * cnt];
+        for (int r = 0; r < D; r++) dot += (double)Ja[r * cnt] * (double)Jb[r * cnt];
         int I = ca < N1 ? scat.y + ca : (ca < N1 + N2 ? scat.z + (ca - N1) : n - 1);
         int Jx = cb < N1 ? scat.y + cb : (cb < N1 + N2 ? scat.z + (cb - N1) : n - 1);
         if (I > Jx) { const int tmp = I; I = Jx; Jx = tmp; }
@@ -703,10 +707,15 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_el(double* d, const double* s) { cp_async8(d, s); }
+__device__ __forceinline__ void cp_async_el(float* d, const float* s) { cp_async4(d, s); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int DC>
+template <int DC, typename JT = double>
 __global__ void __launch_bounds__(128)
 leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int i_begin, int i_end,
                          const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
@@ -727,7 +736,7 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
     const int2 gf = fac[f0 + sub];
     const GroupView& g = gt.g[gf.x];
     const size_t cnt = (size_t)g.count;
-    const double* J = g.J + gf.y;
+    const JT* J = reinterpret_cast<const JT*>(g.J) + gf.y;
     tk = g.scat[gf.y].y - 3;
 #pragma unroll
     for (int cc = 0; cc < DC; cc++) { Ac[0][cc] = J[(size_t)(2 * cc) * cnt]; Ac[1][cc] = J[(size_t)(2 * cc + 1) * cnt]; }
@@ -802,7 +811,7 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
   }
 }
 
-template <int DC, int TPT, int PB>   // TPT: 3x3 tiles per thread = ceil(tiles of the widest separator / blockDim); PB: points per staged batch (<= 8)
+template <int DC, int TPT, int PB, typename JT = double>   // TPT: 3x3 tiles per thread = ceil(tiles of the widest separator / blockDim); PB: points per staged batch (<= 8)
 __global__ void __launch_bounds__(128)
 leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
                         const int* __restrict__ fac_ptr, const int2* __restrict__ fac) {
@@ -811,7 +820,7 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
   constexpr int WP = NTMAX * 3;
   constexpr int AW = 2 * DC + 2;                      // per factor: A_c (2 x DC, column-major) and b (2)
   __shared__ double sS[2][PB][3 * WP];                // [S' d'] as stored: entry (r, col) at 3*col + r
-  __shared__ double sA[2][PB][kPtMaxObs][AW];
+  __shared__ JT sA[2][PB][kPtMaxObs][AW];            // staged in the Jacobians' storage type, widened on use
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthr = blockDim.x, nwarp = nthr >> 5;   // 96 or 128 threads: no idle warp on the common 6-camera point
   const int r0 = run_ptr[blockIdx.x], r1 = run_ptr[blockIdx.x + 1];
@@ -841,7 +850,7 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
   // Software pipeline: the operands of batch b+1 stream into the other buffer (cp.async) while batch b
   // is multiplied, and the (dependent) index loads of batch b+2 are in flight behind them.
   const double* srcS[3];       // [S' d'] of the points this warp copies (points warp, warp + nwarp, ... of a batch)
-  const double* srcJ = nullptr;  // this thread's factor (point tid>>3, factor tid&7), staged by camera slot
+  const JT* srcJ = nullptr;    // this thread's factor (point tid>>3, factor tid&7), staged by camera slot
   size_t cntJ = 0;
   int slotJ = -1;
   auto load_idx = [&](int b0) {
@@ -857,7 +866,7 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
       const int2 gf = fac[fac_ptr[b0 + pt] + fi];
       const GroupView& g = gt.g[gf.x];
       cntJ = (size_t)g.count;
-      srcJ = g.J + gf.y;
+      srcJ = reinterpret_cast<const JT*>(g.J) + gf.y;
       slotJ = (g.scat[gf.y].y - 3) / DC;
     }
   };
@@ -867,11 +876,11 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
       if (srcS[q])
         for (int e = lane; e < 3 * w; e += 32) cp_async8(&sS[buf][warp + nwarp * q][e], srcS[q] + e);
     if (slotJ >= 0) {
-      double* dst = sA[buf][tid >> 3][slotJ];
+      JT* dst = sA[buf][tid >> 3][slotJ];
 #pragma unroll
-      for (int el = 0; el < 2 * DC; el++) cp_async8(dst + el, srcJ + (size_t)el * cntJ);
-      cp_async8(dst + 2 * DC, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
-      cp_async8(dst + 2 * DC + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
+      for (int el = 0; el < 2 * DC; el++) cp_async_el(dst + el, srcJ + (size_t)el * cntJ);
+      cp_async_el(dst + 2 * DC, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
+      cp_async_el(dst + 2 * DC + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
     }
     cp_async_commit();
   };
@@ -910,21 +919,21 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
         }
         if (tj[u] < ts) {
           if (ci == cj) {   // both inside one camera's block: A_c^T A_c
-            const double* A = sA[buf][pt][ci];
+            const JT* A = sA[buf][pt][ci];
 #pragma unroll
             for (int x = 0; x < 3; x++)
 #pragma unroll
               for (int y = 0; y < 3; y++)
-                acc[u][x][y] += A[2 * (oi + x)] * A[2 * (oj + y)] + A[2 * (oi + x) + 1] * A[2 * (oj + y) + 1];
+                acc[u][x][y] += (double)A[2 * (oi + x)] * (double)A[2 * (oj + y)] + (double)A[2 * (oi + x) + 1] * (double)A[2 * (oj + y) + 1];
           }
         } else if (ti[u] < ts) {   // rhs column: A_c^T b
-          const double* A = sA[buf][pt][ci];
+          const JT* A = sA[buf][pt][ci];
 #pragma unroll
-          for (int x = 0; x < 3; x++) acc[u][x][0] += A[2 * (oi + x)] * A[2 * DC] + A[2 * (oi + x) + 1] * A[2 * DC + 1];
+          for (int x = 0; x < 3; x++) acc[u][x][0] += (double)A[2 * (oi + x)] * (double)A[2 * DC] + (double)A[2 * (oi + x) + 1] * (double)A[2 * DC + 1];
         } else {                   // constant term: b^T b
           for (int fi = 0; fi < m; fi++) {
-            const double* A = sA[buf][pt][fi];
-            acc[u][0][0] += A[2 * DC] * A[2 * DC] + A[2 * DC + 1] * A[2 * DC + 1];
+            const JT* A = sA[buf][pt][fi];
+            acc[u][0][0] += (double)A[2 * DC] * (double)A[2 * DC] + (double)A[2 * DC + 1] * (double)A[2 * DC + 1];
           }
         }
       }

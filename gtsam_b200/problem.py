@@ -179,14 +179,15 @@ class Problem:
         st = np.asarray(VAR_DIM)[self.var_type]
         return np.concatenate([[0], np.cumsum(st)]).astype(np.int64)
 
-    def linearize_bytes(self) -> int:
+    def linearize_bytes(self, jac_elem_bytes: int = 8) -> int:
         """Algorithmic bytes of one linearize pass, materialised-[A|b] definition
         (SURVEY.md §8d): per factor = measurement + 2 x int32 ids (+ noise payload
-        when per-factor) in, whitened [A1 A2 b] out; plus one pass over Values."""
+        when per-factor) in, whitened [A1 A2 b] out; plus one pass over Values.
+        jac_elem_bytes = 4 in the FP32-storage mode (b200_set_jacobian_precision)."""
         total = int(self.values.size) * 8
         for g in self.groups:
             d = FACTOR_DIM[g.type]
-            per = FACTOR_MEAS[g.type] * 8 + 4 * FACTOR_ARITY[g.type] + d * factor_ncols(g.type) * 8
+            per = FACTOR_MEAS[g.type] * 8 + 4 * FACTOR_ARITY[g.type] + d * factor_ncols(g.type) * jac_elem_bytes
             if g.noise_per_factor:
                 per += noise_payload(g.noise_kind, d) * 8
             total += per * g.count

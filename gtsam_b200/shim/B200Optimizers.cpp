@@ -330,6 +330,7 @@ GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::linearize() con
 }
 
 long long B200LevenbergMarquardtOptimizer::launchCount() const { return b200_launch_count(dev_->ctx); }
+void B200LevenbergMarquardtOptimizer::setJacobianFp32(bool on) { check(b200_set_jacobian_precision(dev_->prob, on ? 1 : 0), "b200_set_jacobian_precision"); }
 
 // ---- Gauss-Newton ------------------------------------------------------------------
 B200GaussNewtonOptimizer::B200GaussNewtonOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,

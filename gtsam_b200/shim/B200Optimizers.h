@@ -51,6 +51,9 @@ class B200LevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimize
   gtsam::GaussianFactorGraph::shared_ptr linearize() const override;
   /// kernels launched so far (evidence that the device path ran)
   long long launchCount() const;
+  /// true: the "FP32 linearize + FP64 solve" mode of BASELINE configs[4] (whitened Jacobians kept as floats,
+  /// b200_set_jacobian_precision); false (default): the reference's FP64 arithmetic throughout
+  void setJacobianFp32(bool on);
 
  private:
   void init();

@@ -216,6 +216,15 @@ int b200_linearize(b200_problem* prob);
  * a column-major d x (n1 + n2 + 1) block [A1 A2 b] like VerticalBlockMatrix. */
 int b200_get_jacobians(b200_problem* prob, int64_t group, double* out);
 
+/* Precision of the stored linearization: 0 (default) = FP64, the reference's arithmetic; 1 = the
+ * "FP32 linearize + FP64 solve" mode of BASELINE.json configs[4]: residuals and Jacobians are still evaluated in
+ * FP64 registers but the whitened [A1 A2 b] blocks are rounded to and kept as floats (half the HBM traffic of
+ * linearize and of every pass over the Jacobians); assembly, the multifrontal Cholesky, back-substitution, retract
+ * and the nonlinear error stay FP64.  Parity in this mode is the FP32 protocol of SURVEY 8(c): [A|b] rel <= 1e-5,
+ * final error rel <= 1e-5.  Call it any time: it invalidates the current linearization.  Not for linear problems. */
+int b200_set_jacobian_precision(b200_problem* prob, int fp32);
+int b200_get_jacobian_precision(const b200_problem* prob);
+
 /* GaussianFactorGraph::hessianDiagonal(), gtsam/linear/GaussianFactorGraph.cpp:279-287.
  * out: delta_size doubles, variable-id order. */
 int b200_hessian_diagonal(b200_problem* prob, double* out);

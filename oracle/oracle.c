@@ -395,6 +395,7 @@ typedef struct {
 struct orc_problem {
   int64_t nvars;
   int linear;        /* created by orc_linear_create: JacobianFactor groups, no Values */
+  int jac_f32;       /* the "FP32 linearize + FP64 solve" mode: the whitened [A|b] are rounded to float after linearize */
   int32_t* var_dim;  /* tangent dimension of every variable */
   int32_t* var_type;
   int64_t *val_off, *dof_off;
@@ -1006,9 +1007,13 @@ void orc_linearize(orc_problem* p) {
         for (int c = 0; c < n2; c++) J[rr + (n1 + c) * d] = H2[rr * n2 + c];
         J[rr + (n1 + n2) * d] = r[rr];
       }
+      if (p->jac_f32) /* storage precision of the device's FP32 mode: evaluated in FP64, kept as floats */
+        for (int e = 0; e < d * g->ncols; e++) J[e] = (double)(float)J[e];
     }
   }
 }
+
+void orc_set_jacobian_fp32(orc_problem* p, int on) { p->jac_f32 = on != 0; }
 
 void orc_get_jacobians(const orc_problem* p, int64_t group, double* out) {
   const ogroup* g = &p->groups[group];

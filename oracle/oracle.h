@@ -53,6 +53,8 @@ int64_t orc_delta_size(const orc_problem* p);
 
 double orc_error(orc_problem* p);
 void orc_linearize(orc_problem* p);
+/* mirror of b200_set_jacobian_precision: round the whitened [A|b] to float after every linearize */
+void orc_set_jacobian_fp32(orc_problem* p, int on);
 void orc_get_jacobians(const orc_problem* p, int64_t group, double* out);
 void orc_hessian_diagonal(const orc_problem* p, double* out);
 int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_diagonal,

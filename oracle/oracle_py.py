@@ -45,6 +45,7 @@ def lib():
         L.orc_error.argtypes = [C.c_void_p]
         L.orc_error.restype = C.c_double
         L.orc_linearize.argtypes = [C.c_void_p]
+        L.orc_set_jacobian_fp32.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_jacobians.argtypes = [C.c_void_p, C.c_int64, dp]
         L.orc_hessian_diagonal.argtypes = [C.c_void_p, dp]
         L.orc_solve.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp, ip]
@@ -138,6 +139,9 @@ class OracleProblem:
 
     def linearize(self):
         self.L.orc_linearize(self.h)
+
+    def set_jacobian_precision(self, fp32: bool):
+        self.L.orc_set_jacobian_fp32(self.h, int(fp32))
 
     def get_jacobians(self, group):
         g = self.prob.groups[group]
