@@ -32,7 +32,7 @@ EXPORTS = [
     "b200_profile_get", "b200_symbolic_create", "b200_symbolic_destroy", "b200_symbolic_get_info",
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
-    "b200_linear_create", "b200_linear_update", "b200_linear_symbolic_create",
+    "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
     "b200_set_jacobian_precision", "b200_get_jacobian_precision",
 ]
 
@@ -121,6 +121,7 @@ def lib():
         from . import linear as LN
         L.b200_linear_create.argtypes = [vp, C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_linear_update.argtypes = [vp, C.c_int64, dp, dp]
+        L.b200_linear_update_hessian.argtypes = [vp, C.c_int64, dp]
         L.b200_linear_symbolic_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         _LIB = L
@@ -380,6 +381,13 @@ class LinearDeviceProblem(DeviceProblem):
             assert sigmas.size == g.count * g.rows
             sp = _dp(sigmas)
         _check(self.L.b200_linear_update(self.h, group, _dp(Ab), sp))
+
+    def update_hessian(self, hgroup: int, info):
+        """New augmented information matrices for one HessianFactor group (b200_linear_update_hessian)."""
+        g = self.prob.hgroups[hgroup]
+        info = np.ascontiguousarray(info, dtype=np.float64)
+        assert info.size == g.count * g.ncols * g.ncols
+        _check(self.L.b200_linear_update_hessian(self.h, hgroup, _dp(info)))
 
     def get_jacobians(self, group: int):
         """(count, rows, ncols) whitened [A|b] as stored on the device."""

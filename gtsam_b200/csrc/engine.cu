@@ -178,6 +178,7 @@ static int enqueue_hdiag(b200_problem* p) {
     if (!g.count) continue;
     const int nb = (int)((g.count + 127) / 128);
     if (g.type == B200_FACTOR_JACOBIAN) launch_k(hdiag_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, p->d_hdiag);
+    else if (g.type == B200_FACTOR_HESSIAN) launch_k(hdiag_hessian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, p->d_hdiag);
     else DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(hdiag_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), p->d_var_dof, p->d_hdiag))));
     p->ctx->launches++;
   }
@@ -201,6 +202,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (!g.n_nonleaf) continue;   // every factor of the group is owned by a fused leaf clique
       const int nb = (int)((g.count + 127) / 128);
       if (g.type == B200_FACTOR_JACOBIAN) launch_k(assemble_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), t);
+      else if (g.type == B200_FACTOR_HESSIAN) launch_k(assemble_hessian_kernel, dim3(nb), dim3(128), 0, st, jview(g), t);
       else DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(assemble_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), t))));
       ctx->launches++;
     }
@@ -358,6 +360,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     double* p1 = p->d_partials + p->partial_cap / 2;
     if (g.type == B200_FACTOR_JACOBIAN)
       launch_k(linerr_jacobian_kernel, dim3(nb), dim3(256), 0, st, jview(g), (const double*)p->d_delta, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1,
+               &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0);
+    else if (g.type == B200_FACTOR_HESSIAN)
+      launch_k(linerr_hessian_kernel, dim3(nb), dim3(256), 0, st, jview(g), (const double*)p->d_delta, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1,
                &p->d_scalars->lin_err0, &p->d_scalars->lin_err_delta, first ? 0 : 1, 1.0);
     else
     DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), p->d_delta, p->d_var_dof, p0, p1, p->d_counters + 1,
@@ -518,7 +523,7 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
 
 // The same for a linear description (b200_linear_create): JacobianFactor groups of any arity.
 static int pack_linear(const b200_linear_desc* d, Packed* pk) {
-  if (!d || d->nvars < 0 || d->ngroups < 0) FAIL(B200_INVALID_ARGUMENT, "bad linear description");
+  if (!d || d->nvars < 0 || d->ngroups < 0 || d->nhgroups < 0) FAIL(B200_INVALID_ARGUMENT, "bad linear description");
   const int64_t n = d->nvars;
   pk->val_off.assign(n + 1, 0); pk->var_dof.assign(n + 1, 0); pk->var_dim.assign(n, 0);
   for (int64_t v = 0; v < n; v++) {
@@ -532,9 +537,13 @@ static int pack_linear(const b200_linear_desc* d, Packed* pk) {
     if (d->groups[g].count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
     total += d->groups[g].count;
   }
+  for (int64_t g = 0; g < d->nhgroups; g++) {
+    if (d->hgroups[g].count < 0) FAIL(B200_INVALID_ARGUMENT, "negative factor count");
+    total += d->hgroups[g].count;
+  }
   pk->total = total;
   std::vector<char> used(total, 0);
-  pk->groups.resize(d->ngroups);
+  pk->groups.resize(d->ngroups + d->nhgroups);
   pk->fptr.assign(total + 1, 0);
   for (int64_t gi = 0; gi < d->ngroups; gi++) {
     const b200_jacobian_group& s = d->groups[gi];
@@ -555,8 +564,35 @@ static int pack_linear(const b200_linear_desc* d, Packed* pk) {
       for (int64_t i = 0; i < s.count * s.rows; i++)
         if (!(s.sigmas[i] > 0)) FAIL(B200_UNSUPPORTED_NOISE, "sigma <= 0: Constrained noise models need QR elimination (out of scope)");
   }
+  for (int64_t hi = 0; hi < d->nhgroups; hi++) {   // HessianFactor groups follow the Jacobian groups
+    const b200_hessian_group& s = d->hgroups[hi];
+    PackedGroup& g = pk->groups[d->ngroups + hi];
+    if (s.arity < 1 || s.arity > B200_JACOBIAN_MAX_ARITY) FAIL(B200_UNSUPPORTED_FACTOR, "HessianFactor arity outside 1..B200_JACOBIAN_MAX_ARITY");
+    g.type = B200_FACTOR_HESSIAN; g.arity = s.arity; g.count = s.count;
+    g.ncols = 1;
+    for (int a = 0; a < s.arity; a++) {
+      if (s.dims[a] < 1) FAIL(B200_INVALID_ARGUMENT, "block width < 1");
+      g.dims[a] = s.dims[a];
+      g.ncols += s.dims[a];
+    }
+    g.d = g.ncols;   // the augmented information matrix is (N+1) x (N+1)
+    const int rc = resolve_positions(s.count, s.graph_index, s.graph_index0, total, &next, &used, &g.pos);
+    if (rc) return rc;
+    for (int64_t i = 0; i < s.count; i++) pk->fptr[g.pos[i] + 1] = s.arity;
+  }
   for (int64_t i = 0; i < total; i++) pk->fptr[i + 1] += pk->fptr[i];
   pk->fkeys.assign(pk->fptr[total], -1);
+  for (int64_t hi = 0; hi < d->nhgroups; hi++) {
+    const b200_hessian_group& s = d->hgroups[hi];
+    const PackedGroup& g = pk->groups[d->ngroups + hi];
+    for (int64_t i = 0; i < s.count; i++)
+      for (int a = 0; a < s.arity; a++) {
+        const int64_t k = s.keys[i * s.arity + a];
+        if (k < 0 || k >= n) FAIL(B200_INVALID_ARGUMENT, "HessianFactor key out of range");
+        if (d->var_dim[k] != s.dims[a]) FAIL(B200_INVALID_ARGUMENT, "HessianFactor block width differs from the variable's dimension");
+        pk->fkeys[pk->fptr[g.pos[i]] + a] = k;
+      }
+  }
   for (int64_t gi = 0; gi < d->ngroups; gi++) {
     const b200_jacobian_group& s = d->groups[gi];
     const PackedGroup& g = pk->groups[gi];
@@ -857,7 +893,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     if (rc) { b200_problem_destroy(p); return rc; }
   }
   const int64_t n = d ? d->nvars : ld->nvars;
-  const int64_t ngroups = d ? d->ngroups : ld->ngroups;
+  const int64_t ngroups = d ? d->ngroups : ld->ngroups + ld->nhgroups;   // linear: Jacobian groups, then Hessian groups
   const int64_t total = pk.total;
   p->nvars = n; p->nval = pk.val_off[n]; p->ndelta = pk.var_dof[n]; p->nfactors = total;
   if (d) p->var_type.assign(d->var_type, d->var_type + n);
@@ -1000,26 +1036,30 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   std::vector<std::vector<int2>> hkeys(ngroups);
   std::vector<std::vector<int4>> hscat(ngroups);
   for (int64_t gi = 0; ld && gi < ngroups; gi++) {
-    // JacobianFactor groups: keys, owning clique and front slot of every key, then the whitened [A|b] (SoA)
-    const b200_jacobian_group& s = ld->groups[gi];
+    // JacobianFactor / HessianFactor groups: keys, owning clique and front slot of every key, then the numbers
+    // (whitened [A|b], or the augmented information matrix) in the element-major SoA
     auto& g = p->groups[gi];
-    std::vector<int> jkeys((size_t)s.count * s.arity), jslots((size_t)s.count * s.arity), jclique((size_t)s.count);
-    g.local_index.resize(s.count);
-    for (int64_t i = 0; i < s.count; i++) {
+    const bool hess = gi >= ld->ngroups;
+    const int64_t count = g.count;
+    const int ar = g.arity;
+    std::vector<int> jkeys((size_t)count * ar), jslots((size_t)count * ar), jclique((size_t)count);
+    g.local_index.resize(count);
+    for (int64_t i = 0; i < count; i++) {
       const int64_t pos = g.pos[i];
       g.local_index[i] = i;
       jclique[i] = S.fac_clique[pos];
-      for (int a = 0; a < s.arity; a++) {
-        jkeys[(size_t)i * s.arity + a] = (int)fkeys[fptr[pos] + a];
-        jslots[(size_t)i * s.arity + a] = S.fac_slots[fptr[pos] + a];
+      for (int a = 0; a < ar; a++) {
+        jkeys[(size_t)i * ar + a] = (int)fkeys[fptr[pos] + a];
+        jslots[(size_t)i * ar + a] = S.fac_slots[fptr[pos] + a];
       }
     }
-    g.n_nonleaf = s.count;
+    g.n_nonleaf = count;
     UP(upload(&g.d_jkeys, jkeys, st));
     UP(upload(&g.d_jslots, jslots, st));
     UP(upload(&g.d_jclique, jclique, st));
-    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)s.count * g.d * g.ncols) * sizeof(double)));
-    UP(upload_jacobian_group(p, g, s.Ab, s.sigmas));
+    B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)count * g.d * g.ncols) * sizeof(double)));
+    if (hess) UP(upload_jacobian_group(p, g, ld->hgroups[gi - ld->ngroups].info, nullptr));   // (N+1)^2 entries, no whitening
+    else UP(upload_jacobian_group(p, g, ld->groups[gi].Ab, ld->groups[gi].sigmas));
   }
   for (int64_t gi = 0; d && gi < ngroups; gi++) {
     const b200_factor_group& s = d->groups[gi];
@@ -1219,9 +1259,19 @@ int b200_linear_create(b200_ctx* ctx, const b200_linear_desc* d, b200_problem** 
   if (!d) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
   return create_problem(ctx, nullptr, d, out);
 }
+int b200_linear_update_hessian(b200_problem* p, int64_t hi, const double* info) {
+  if (!p || !p->linear) { set_error("b200_linear_update_hessian: not a linear problem"); return B200_INVALID_ARGUMENT; }
+  int64_t gi = -1;
+  for (int64_t q = 0, k = 0; q < (int64_t)p->groups.size(); q++)
+    if (p->groups[q].type == B200_FACTOR_HESSIAN && k++ == hi) { gi = q; break; }
+  if (hi < 0 || gi < 0) { set_error("HessianFactor group out of range"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  p->solved = p->factored = p->marg_ready = false;
+  return upload_jacobian_group(p, p->groups[gi], info, nullptr);
+}
 int b200_linear_update(b200_problem* p, int64_t gi, const double* Ab, const double* sigmas) {
   if (!p || !p->linear) { set_error("b200_linear_update: not a linear problem"); return B200_INVALID_ARGUMENT; }
-  if (gi < 0 || gi >= (int64_t)p->groups.size()) { set_error("group out of range"); return B200_INVALID_ARGUMENT; }
+  if (gi < 0 || gi >= (int64_t)p->groups.size() || p->groups[gi].type != B200_FACTOR_JACOBIAN) { set_error("JacobianFactor group out of range"); return B200_INVALID_ARGUMENT; }
   auto& g = p->groups[gi];
   if (sigmas)
     for (int64_t i = 0; i < g.count * g.d; i++)

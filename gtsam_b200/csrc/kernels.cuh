@@ -16,6 +16,7 @@
 //  backsub_point_kernel<DC>, backsub_small_kernel, backsub_large_kernel  a15  x_F = R^-1 (d - S x_S), level by level
 //  linerr_kernel         a16     0.5*|A delta - b|^2 and 0.5*|b|^2 in one pass
 //  retract_kernel        a9      x (+) delta per variable
+//  assemble_hessian_kernel, hdiag_hessian_kernel, linerr_hessian_kernel   the same for HessianFactor groups
 //  jacobian_load_kernel, assemble_jacobian_kernel, hdiag_jacobian_kernel, linerr_jacobian_kernel
 //                                a12/a10/a16 for the JacobianFactor groups (any arity / block widths) of a linear problem
 //                                (GaussianFactorGraph::optimize level, b200_linear_create)
@@ -434,6 +435,86 @@ __global__ void __launch_bounds__(256) linerr_jacobian_kernel(JacobianView g, co
     }
     a0 += 0.5 * s0;
     a1 += 0.5 * s1;
+  }
+  a0 = block_sum<256>(a0, sh);
+  a1 = block_sum<256>(a1, sh);
+  finish_sum(a0, p0, counters, out0, accumulate, sh);
+  finish_sum(a1, p1, counters + 1, out1, accumulate, sh);
+}
+
+// HessianFactors of a linear problem (gtsam/linear/HessianFactor.h:99-110): the view's "rows" is N + 1 and J holds
+// the augmented information matrix [G g; g' f] (element (r, c) at r + c*(N+1); upper triangle read).
+// HessianFactor::updateHessian (gtsam/linear/HessianFactor.cpp:348-374): info(I,J) += this->info(i,j)
+__global__ void __launch_bounds__(128) assemble_hessian_kernel(JacobianView g, TreeView t) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const int c = g.clique[f];
+  double* Mf = t.arena + t.off[c];
+  const int ld = t.nf[c] + t.ns[c] + 1;
+  const double* H = g.J + f;
+  const int n1 = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int a = 0; a <= g.arity; a++) {
+    const int sa = a < g.arity ? g.slots[(size_t)f * g.arity + a] : ld - 1;
+    for (int ca = g.col0[a]; ca < g.col0[a + 1]; ca++) {
+      const int i = sa + (ca - g.col0[a]);
+      for (int b = a; b <= g.arity; b++) {
+        const int sb = b < g.arity ? g.slots[(size_t)f * g.arity + b] : ld - 1;
+        for (int cb = (b == a ? ca : g.col0[b]); cb < g.col0[b + 1]; cb++) {
+          const int j = sb + (cb - g.col0[b]);
+          const int lo = i < j ? i : j, hi = i < j ? j : i;
+          atomicAdd(Mf + lo + (size_t)hi * ld, H[(size_t)(ca + cb * n1) * cnt]);   // ca <= cb: upper triangle of the factor
+        }
+      }
+    }
+  }
+}
+
+// HessianFactor::hessianDiagonalAdd (gtsam/linear/HessianFactor.cpp:292-304): the diagonal of G
+__global__ void __launch_bounds__(128) hdiag_hessian_kernel(JacobianView g, const int* __restrict__ var_dof, double* hdiag) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const double* H = g.J + f;
+  const int n1 = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int a = 0; a < g.arity; a++) {
+    const int base = var_dof[g.keys[(size_t)f * g.arity + a]];
+    for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) atomicAdd(hdiag + base + (cc - g.col0[a]), H[(size_t)(cc + cc * n1) * cnt]);
+  }
+}
+
+// HessianFactor::error (gtsam/linear/HessianFactor.cpp:331-346): 0.5 (f - 2 x'g + x'G x); out0 gets the value at
+// x = 0 (0.5 f), out1 the value at x = delta; bscale = 0 drops the f and g terms (0.5 x'G x)
+__global__ void __launch_bounds__(256) linerr_hessian_kernel(JacobianView g, const double* __restrict__ delta,
+                                                             const int* __restrict__ var_dof, double* p0, double* p1,
+                                                             unsigned* counters, double* out0, double* out1, int accumulate,
+                                                             double bscale) {
+  pdl_sync();
+  __shared__ double sh[32];
+  double a0 = 0, a1 = 0;
+  const int n1 = g.rows, N = n1 - 1;
+  const size_t cnt = (size_t)g.count;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < g.count; f += gridDim.x * blockDim.x) {
+    const double* H = g.J + f;
+    double xGx = 0, xg = 0;
+    for (int a = 0; a < g.arity; a++) {
+      const double* da = delta + var_dof[g.keys[(size_t)f * g.arity + a]];
+      for (int ca = g.col0[a]; ca < g.col0[a + 1]; ca++) {
+        const double xa = da[ca - g.col0[a]];
+        xg += xa * H[(size_t)(ca + N * n1) * cnt];
+        xGx += xa * xa * H[(size_t)(ca + ca * n1) * cnt];
+        for (int b = a; b < g.arity; b++) {   // strictly upper entries count twice
+          const double* db = delta + var_dof[g.keys[(size_t)f * g.arity + b]];
+          for (int cb = (b == a ? ca + 1 : g.col0[b]); cb < g.col0[b + 1]; cb++)
+            xGx += 2.0 * xa * db[cb - g.col0[b]] * H[(size_t)(ca + cb * n1) * cnt];
+        }
+      }
+    }
+    const double ff = H[(size_t)(N + N * n1) * cnt];
+    a0 += 0.5 * ff;
+    a1 += 0.5 * (bscale * (ff - 2.0 * xg) + xGx);
   }
   a0 = block_sum<256>(a0, sh);
   a1 = block_sum<256>(a1, sh);

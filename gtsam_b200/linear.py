@@ -4,6 +4,7 @@ Python mirror of ``b200_linear_desc`` / ``b200_jacobian_group`` (include/gtsam_b
 part of the reference's linear API that sits on the hot path:
 
 * ``JacobianFactor(keys, blocks, b, sigmas)``   gtsam/linear/JacobianFactor.h:93-160
+* ``HessianFactor(keys, dims, info)``            gtsam/linear/HessianFactor.h:99-110
 * ``GaussianFactorGraph``                        gtsam/linear/GaussianFactorGraph.h:73-404
   ``.add / .push_back / .size / .keys``, ``.optimize(ordering)`` (GaussianFactorGraph.cpp:316-319, the
   multifrontal Cholesky path), ``.hessianDiagonal()`` (:279-287)
@@ -33,9 +34,15 @@ class CJacobianGroup(C.Structure):
                 ("Ab", C.POINTER(C.c_double)), ("sigmas", C.POINTER(C.c_double))]
 
 
+class CHessianGroup(C.Structure):
+    _fields_ = [("arity", C.c_int32), ("dims", C.POINTER(C.c_int32)), ("count", C.c_int64), ("graph_index0", C.c_int64),
+                ("graph_index", C.POINTER(C.c_int64)), ("keys", C.POINTER(C.c_int64)), ("info", C.POINTER(C.c_double))]
+
+
 class CLinearDesc(C.Structure):
     _fields_ = [("nvars", C.c_int64), ("var_dim", C.POINTER(C.c_int32)), ("ordering", C.POINTER(C.c_int64)),
-                ("ngroups", C.c_int64), ("groups", C.POINTER(CJacobianGroup))]
+                ("ngroups", C.c_int64), ("groups", C.POINTER(CJacobianGroup)),
+                ("nhgroups", C.c_int64), ("hgroups", C.POINTER(CHessianGroup))]
 
 
 @dataclass
@@ -79,10 +86,44 @@ class JacobianGroup:
 
 
 @dataclass
+class HessianGroup:
+    """A run of HessianFactors with the same block widths.  ``info[f, c, r]`` = entry (r, c) of factor f's augmented
+    information matrix [G g; g' f] (HessianFactor::info(); the upper triangle is what the library reads)."""
+    dims: Sequence[int]
+    keys: np.ndarray                      # (count, arity) int64 variable ids
+    info: np.ndarray                      # (count, N+1, N+1) float64, N = sum(dims)
+    graph_index0: int = -1
+    graph_index: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.dims = np.ascontiguousarray(self.dims, dtype=np.int32)
+        self.keys = np.ascontiguousarray(self.keys, dtype=np.int64).reshape(-1, self.arity)
+        self.info = np.ascontiguousarray(self.info, dtype=np.float64).reshape(self.count, self.ncols, self.ncols)
+        if self.graph_index is not None:
+            self.graph_index = np.ascontiguousarray(self.graph_index, dtype=np.int64)
+            assert self.graph_index.size == self.count
+
+    @property
+    def arity(self) -> int:
+        return int(self.dims.size)
+
+    @property
+    def ncols(self) -> int:
+        return int(self.dims.sum()) + 1
+
+    rows = ncols
+
+    @property
+    def count(self) -> int:
+        return int(self.keys.shape[0])
+
+
+@dataclass
 class LinearProblem:
     var_dim: np.ndarray        # (nvars,) int32 tangent dimensions
     ordering: np.ndarray       # (nvars,) int64 elimination order
     groups: List[JacobianGroup] = field(default_factory=list)
+    hgroups: List[HessianGroup] = field(default_factory=list)   # HessianFactor groups (graph positions after / among the Jacobian ones)
     name: str = ""
     meta: dict = field(default_factory=dict)
 
@@ -90,7 +131,7 @@ class LinearProblem:
         self.var_dim = np.ascontiguousarray(self.var_dim, dtype=np.int32)
         self.ordering = np.ascontiguousarray(self.ordering, dtype=np.int64)
         nxt = 0
-        for g in self.groups:
+        for g in list(self.groups) + list(self.hgroups):
             if g.graph_index is not None:
                 continue
             if g.graph_index0 < 0:
@@ -103,7 +144,7 @@ class LinearProblem:
 
     @property
     def nfactors(self) -> int:
-        return sum(g.count for g in self.groups)
+        return sum(g.count for g in self.groups) + sum(g.count for g in self.hgroups)
 
     @property
     def var_dims(self) -> np.ndarray:
@@ -122,13 +163,23 @@ class LinearProblem:
             garr[i].keys = P._ptr(g.keys, C.c_int64)
             garr[i].Ab = P._ptr(g.Ab, C.c_double)
             garr[i].sigmas = P._ptr(g.sigmas, C.c_double)
+        harr = (CHessianGroup * max(1, len(self.hgroups)))()
+        for i, g in enumerate(self.hgroups):
+            harr[i].arity, harr[i].count = g.arity, g.count
+            harr[i].dims = P._ptr(g.dims, C.c_int32)
+            harr[i].graph_index0 = g.graph_index0
+            harr[i].graph_index = P._ptr(g.graph_index, C.c_int64)
+            harr[i].keys = P._ptr(g.keys, C.c_int64)
+            harr[i].info = P._ptr(g.info, C.c_double)
         d = CLinearDesc()
         d.nvars = self.nvars
         d.var_dim = P._ptr(self.var_dim, C.c_int32)
         d.ordering = P._ptr(self.ordering, C.c_int64)
         d.ngroups = len(self.groups)
         d.groups = garr
-        return d, (garr, self)
+        d.nhgroups = len(self.hgroups)
+        d.hgroups = harr
+        return d, (garr, harr, self)
 
     # -- file exchange with oracle/ref_harness.cpp (oracle/linear_io.hpp) ------------------
     MAGIC = b"B200LIN1"
@@ -139,7 +190,7 @@ class LinearProblem:
             f.write(struct.pack("<q", self.nvars))
             f.write(self.var_dim.tobytes())
             f.write(self.ordering.tobytes())
-            f.write(struct.pack("<q", len(self.groups)))
+            f.write(struct.pack("<q", len(self.groups) + len(self.hgroups)))
             for g in self.groups:
                 f.write(struct.pack("<ii", g.rows, g.arity))
                 f.write(g.dims.tobytes())
@@ -149,6 +200,14 @@ class LinearProblem:
                 f.write(g.Ab.tobytes())
                 if g.sigmas is not None:
                     f.write(g.sigmas.tobytes())
+                if g.graph_index is not None:
+                    f.write(g.graph_index.tobytes())
+            for g in self.hgroups:
+                f.write(struct.pack("<ii", g.ncols, g.arity))
+                f.write(g.dims.tobytes())
+                f.write(struct.pack("<qqi", g.count, g.graph_index0, 8 | (4 if g.graph_index is not None else 0)))
+                f.write(g.keys.tobytes())
+                f.write(g.info.tobytes())
                 if g.graph_index is not None:
                     f.write(g.graph_index.tobytes())
 
@@ -175,7 +234,7 @@ class LinearProblem:
         vd = arr(np.int32, nv)
         order = arr(np.int64, nv)
         (ng,) = rd("<q")
-        groups = []
+        groups, hgroups = [], []
         for _ in range(ng):
             rows, ar = rd("<ii")
             dims = arr(np.int32, ar)
@@ -185,8 +244,11 @@ class LinearProblem:
             Ab = arr(np.float64, cnt * rows * nc)
             sig = arr(np.float64, cnt * rows) if flags & 1 else None
             gidx = arr(np.int64, cnt) if flags & 4 else None
-            groups.append(JacobianGroup(rows, dims, keys, Ab, sig, gi0, gidx))
-        return cls(vd, order, groups)
+            if flags & 8:
+                hgroups.append(HessianGroup(dims, keys, Ab, gi0, gidx))
+            else:
+                groups.append(JacobianGroup(rows, dims, keys, Ab, sig, gi0, gidx))
+        return cls(vd, order, groups, hgroups)
 
 
 # ---- the reference's object-level API, mirrored ---------------------------------------------
@@ -214,12 +276,30 @@ class JacobianFactor:
         return np.concatenate(self.blocks + [self.b[:, None]], axis=1)
 
 
+class HessianFactor:
+    """0.5 (f - 2 x'g + x'G x) over `keys` (gtsam/linear/HessianFactor.h:99-110): `info` is the symmetric augmented
+    information matrix [G g; g' f], `dims` the block width of every key."""
+
+    def __init__(self, keys, dims, info):
+        self._keys = [int(k) for k in keys]
+        self.dims = [int(d) for d in dims]
+        self.info = np.asarray(info, dtype=np.float64)
+        n1 = sum(self.dims) + 1
+        assert self.info.shape == (n1, n1) and len(self.dims) == len(self._keys)
+
+    def keys(self):
+        return list(self._keys)
+
+    def getDim(self, i: int) -> int:
+        return self.dims[i]
+
+
 VectorValues = Dict[int, np.ndarray]
 
 
 class GaussianFactorGraph:
     def __init__(self, factors=()):
-        self.factors: List[JacobianFactor] = list(factors)
+        self.factors: list = list(factors)   # JacobianFactor | HessianFactor
 
     def add(self, *args):
         """add(factor) or add(keys, blocks, b[, sigmas]) like the reference's overloads."""
@@ -246,7 +326,14 @@ class GaussianFactorGraph:
                     raise ValueError(f"variable {k} appears with two different dimensions")
         order = np.array([ids[k] for k in (keys if ordering is None else ordering)], dtype=np.int64)
         buckets: Dict[tuple, dict] = {}
+        hbuckets: Dict[tuple, dict] = {}
         for pos, f in enumerate(self.factors):
+            if isinstance(f, HessianFactor):
+                b = hbuckets.setdefault(tuple(f.dims), dict(keys=[], info=[], pos=[]))
+                b["keys"].append([ids[k] for k in f.keys()])
+                b["info"].append(np.triu(f.info) + np.triu(f.info, 1).T)   # symmetric; stored column-major == row-major
+                b["pos"].append(pos)
+                continue
             sig = (f.rows(), f.sigmas is not None) + tuple(f.getDim(i) for i in range(len(f.keys())))
             b = buckets.setdefault(sig, dict(keys=[], Ab=[], sig=[], pos=[]))
             b["keys"].append([ids[k] for k in f.keys()])
@@ -257,7 +344,9 @@ class GaussianFactorGraph:
         groups = [JacobianGroup(sig[0], sig[2:], np.array(b["keys"]), np.array(b["Ab"]),
                                 np.array(b["sig"]) if sig[1] else None, graph_index=np.array(b["pos"]))
                   for sig, b in buckets.items()]
-        return LinearProblem(np.array([dim[k] for k in keys], dtype=np.int32), order, groups), ids
+        hgroups = [HessianGroup(dims, np.array(b["keys"]), np.array(b["info"]), graph_index=np.array(b["pos"]))
+                   for dims, b in hbuckets.items()]
+        return LinearProblem(np.array([dim[k] for k in keys], dtype=np.int32), order, groups, hgroups), ids
 
     def hessianDiagonal(self, ctx=None) -> VectorValues:
         """GaussianFactorGraph::hessianDiagonal() on the device."""

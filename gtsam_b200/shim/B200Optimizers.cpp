@@ -6,6 +6,7 @@
 #include <gtsam/geometry/Cal3_S2.h>
 #include <gtsam/geometry/PinholeCamera.h>
 #include <gtsam/geometry/Pose3.h>
+#include <gtsam/linear/HessianFactor.h>
 #include <gtsam/linear/JacobianFactor.h>
 #include <gtsam/linear/linearExceptions.h>
 #include <gtsam/nonlinear/PriorFactor.h>
@@ -452,7 +453,8 @@ VectorValues solveOnDevice(const NonlinearFactorGraph& graph, const Values& valu
 // ---- GaussianFactorGraph level ---------------------------------------------------------------
 // JacobianFactors bucketed by shape (rows, has-model, block widths); keys -> dense ids in ascending Key order.
 struct LinGroup {
-  int rows = 0;
+  int rows = 0;            // JacobianFactor rows; N + 1 for a HessianFactor group
+  bool hessian = false;    // Ab holds augmented information matrices (HessianFactor::info())
   bool has_model = false;
   std::vector<int32_t> dims;
   std::vector<int64_t> keys, pos;
@@ -468,6 +470,8 @@ struct LinearState {
   std::vector<std::vector<int>> signature;   // per graph position: (rows, has-model, key ids...)
   std::vector<int64_t> ord;
   std::vector<b200_jacobian_group> cg;
+  std::vector<b200_hessian_group> ch;
+  std::vector<size_t> jgroups, hgroups;   // indices into `groups` by kind, in the order of the C-ABI arrays
   b200_linear_desc desc;
   b200_ctx* ctx = nullptr;
   b200_problem* prob = nullptr;
@@ -476,29 +480,42 @@ struct LinearState {
   ~LinearState() { reset(); if (ctx) b200_ctx_destroy(ctx); }
   void reset() { if (prob) { b200_problem_destroy(prob); prob = nullptr; } }
 
-  static std::shared_ptr<JacobianFactor> asJacobian(const GaussianFactor::shared_ptr& f, size_t pos) {
+  // JacobianFactor (Unit / Diagonal model) or HessianFactor; anything else has no device path
+  static void checkFactor(const GaussianFactor::shared_ptr& f, size_t pos) {
     if (!f) throw std::invalid_argument("gtsam_b200: null factor in the GaussianFactorGraph at position " + std::to_string(pos));
-    auto jf = std::dynamic_pointer_cast<JacobianFactor>(f);
-    if (!jf) throw std::invalid_argument("gtsam_b200: only JacobianFactors are supported at the linear level (position " +
-                                         std::to_string(pos) + " holds another GaussianFactor type); no CPU fallback");
-    const SharedDiagonal& m = jf->get_model();
-    if (m && m->isConstrained()) throw std::invalid_argument("gtsam_b200: Constrained noise models are out of scope (need QR)");
-    return jf;
+    if (auto jf = std::dynamic_pointer_cast<JacobianFactor>(f)) {
+      const SharedDiagonal& m = jf->get_model();
+      if (m && m->isConstrained()) throw std::invalid_argument("gtsam_b200: Constrained noise models are out of scope (need QR)");
+      return;
+    }
+    if (std::dynamic_pointer_cast<HessianFactor>(f)) return;
+    throw std::invalid_argument("gtsam_b200: only JacobianFactors and HessianFactors are supported at the linear level (position " +
+                                std::to_string(pos) + " holds another GaussianFactor type); no CPU fallback");
+  }
+  // shape signature of a factor: (rows or -1 for a HessianFactor, has-model, key ids...)
+  std::vector<int> signatureOf(const GaussianFactor::shared_ptr& f, bool* ok) const {
+    std::vector<int> sig;
+    *ok = true;
+    if (auto jf = std::dynamic_pointer_cast<JacobianFactor>(f)) {
+      const SharedDiagonal& m = jf->get_model();
+      sig = {(int)jf->rows(), (int)(m && !m->isUnit())};
+    } else {
+      sig = {-1, 0};
+    }
+    for (auto it = f->begin(); it != f->end(); ++it) {
+      auto id = key2id.find(*it);
+      if (id == key2id.end() || (int)f->getDim(it) != var_dim[id->second]) { *ok = false; return sig; }
+      sig.push_back((int)id->second);
+    }
+    return sig;
   }
 
-  // (rows, has-model, key ids) of every factor; false if `gfg` has another structure than the packed one
   bool sameStructure(const GaussianFactorGraph& gfg) const {
     if (!prob || gfg.size() != signature.size()) return false;
     for (size_t pos = 0; pos < gfg.size(); pos++) {
-      auto jf = asJacobian(gfg[pos], pos);
-      const std::vector<int>& sig = signature[pos];
-      const SharedDiagonal& m = jf->get_model();
-      if ((int)jf->rows() != sig[0] || (int)(m && !m->isUnit()) != sig[1] || jf->size() + 2 != sig.size()) return false;
-      size_t a = 2;
-      for (auto it = jf->begin(); it != jf->end(); ++it, ++a) {
-        auto id = key2id.find(*it);
-        if (id == key2id.end() || (int)id->second != sig[a] || (int)jf->getDim(it) != var_dim[id->second]) return false;
-      }
+      checkFactor(gfg[pos], pos);
+      bool ok;
+      if (signatureOf(gfg[pos], &ok) != signature[pos] || !ok) return false;
     }
     return true;
   }
@@ -508,6 +525,11 @@ struct LinearState {
     for (auto& g : groups) { g.Ab.clear(); g.sigmas.clear(); }
     for (auto& g : groups)
       for (int64_t pos : g.pos) {
+        if (g.hessian) {
+          const Matrix info = std::static_pointer_cast<HessianFactor>(gfg[(size_t)pos])->info().selfadjointView();
+          g.Ab.insert(g.Ab.end(), info.data(), info.data() + info.size());
+          continue;
+        }
         auto jf = std::static_pointer_cast<JacobianFactor>(gfg[(size_t)pos]);
         const Matrix Ab = jf->augmentedJacobianUnweighted();   // [A1 .. Ak b], unwhitened; whitening is a device kernel
         g.Ab.insert(g.Ab.end(), Ab.data(), Ab.data() + Ab.size());   // Eigen default is column-major
@@ -520,10 +542,11 @@ struct LinearState {
     id2key.clear(); key2id.clear(); var_dim.clear(); dof_off.assign(1, 0); groups.clear(); signature.clear();
     std::map<Key, int> dimOf;
     for (size_t pos = 0; pos < gfg.size(); pos++) {
-      auto jf = asJacobian(gfg[pos], pos);
-      for (auto it = jf->begin(); it != jf->end(); ++it) {
-        auto ins = dimOf.emplace(*it, (int)jf->getDim(it));
-        if (!ins.second && ins.first->second != (int)jf->getDim(it))
+      checkFactor(gfg[pos], pos);
+      const auto& f = gfg[pos];
+      for (auto it = f->begin(); it != f->end(); ++it) {
+        auto ins = dimOf.emplace(*it, (int)f->getDim(it));
+        if (!ins.second && ins.first->second != (int)f->getDim(it))
           throw std::invalid_argument("gtsam_b200: variable " + DefaultKeyFormatter(*it) + " appears with two different dimensions");
       }
     }
@@ -535,25 +558,28 @@ struct LinearState {
     }
     std::map<std::vector<int>, size_t> bucket;
     for (size_t pos = 0; pos < gfg.size(); pos++) {
-      auto jf = std::static_pointer_cast<JacobianFactor>(gfg[pos]);
-      const SharedDiagonal& m = jf->get_model();
-      const bool has_model = m && !m->isUnit();
-      if (jf->size() < 1 || jf->size() > B200_JACOBIAN_MAX_ARITY)
-        throw std::invalid_argument("gtsam_b200: JacobianFactor with " + std::to_string(jf->size()) + " keys (supported: 1.." +
+      const auto& f = gfg[pos];
+      if (f->size() < 1 || f->size() > B200_JACOBIAN_MAX_ARITY)
+        throw std::invalid_argument("gtsam_b200: Gaussian factor with " + std::to_string(f->size()) + " keys (supported: 1.." +
                                     std::to_string(B200_JACOBIAN_MAX_ARITY) + ")");
-      std::vector<int> shape{(int)jf->rows(), (int)has_model}, sig{(int)jf->rows(), (int)has_model};
-      for (auto it = jf->begin(); it != jf->end(); ++it) { shape.push_back((int)jf->getDim(it)); sig.push_back((int)key2id.at(*it)); }
+      bool ok;
+      const std::vector<int> sig = signatureOf(f, &ok);
       signature.push_back(sig);
+      std::vector<int> shape{sig[0], sig[1]};
+      for (auto it = f->begin(); it != f->end(); ++it) shape.push_back((int)f->getDim(it));
       auto found = bucket.find(shape);
       if (found == bucket.end()) {
         LinGroup g;
-        g.rows = (int)jf->rows(); g.has_model = has_model;
-        for (auto it = jf->begin(); it != jf->end(); ++it) g.dims.push_back((int32_t)jf->getDim(it));
+        g.hessian = sig[0] < 0; g.has_model = sig[1] != 0;
+        for (auto it = f->begin(); it != f->end(); ++it) g.dims.push_back((int32_t)f->getDim(it));
+        int n1 = 1;
+        for (int32_t d : g.dims) n1 += d;
+        g.rows = g.hessian ? n1 : sig[0];
         groups.push_back(g);
         found = bucket.emplace(shape, groups.size() - 1).first;
       }
       LinGroup& g = groups[found->second];
-      for (auto it = jf->begin(); it != jf->end(); ++it) g.keys.push_back(key2id.at(*it));
+      for (auto it = f->begin(); it != f->end(); ++it) g.keys.push_back(key2id.at(*it));
       g.pos.push_back((int64_t)pos);
       g.count++;
     }
@@ -565,15 +591,25 @@ struct LinearState {
       ord.push_back(it->second);
     }
     if (ord.size() != id2key.size()) throw std::invalid_argument("gtsam_b200: ordering must cover every variable of the graph");
-    cg.assign(groups.size(), b200_jacobian_group());
+    cg.clear(); ch.clear(); jgroups.clear(); hgroups.clear();
     for (size_t i = 0; i < groups.size(); i++) {
       const LinGroup& g = groups[i];
-      cg[i].rows = g.rows; cg[i].arity = (int32_t)g.dims.size(); cg[i].dims = g.dims.data(); cg[i].count = g.count;
-      cg[i].graph_index0 = -1; cg[i].graph_index = g.pos.data(); cg[i].keys = g.keys.data(); cg[i].Ab = g.Ab.data();
-      cg[i].sigmas = g.has_model ? g.sigmas.data() : nullptr;
+      if (g.hessian) {
+        b200_hessian_group h;
+        h.arity = (int32_t)g.dims.size(); h.dims = g.dims.data(); h.count = g.count; h.graph_index0 = -1;
+        h.graph_index = g.pos.data(); h.keys = g.keys.data(); h.info = g.Ab.data();
+        ch.push_back(h); hgroups.push_back(i);
+      } else {
+        b200_jacobian_group c;
+        c.rows = g.rows; c.arity = (int32_t)g.dims.size(); c.dims = g.dims.data(); c.count = g.count;
+        c.graph_index0 = -1; c.graph_index = g.pos.data(); c.keys = g.keys.data(); c.Ab = g.Ab.data();
+        c.sigmas = g.has_model ? g.sigmas.data() : nullptr;
+        cg.push_back(c); jgroups.push_back(i);
+      }
     }
     desc.nvars = (int64_t)id2key.size(); desc.var_dim = var_dim.data(); desc.ordering = ord.data();
     desc.ngroups = (int64_t)cg.size(); desc.groups = cg.data();
+    desc.nhgroups = (int64_t)ch.size(); desc.hgroups = ch.data();
   }
 
   void build(const GaussianFactorGraph& gfg, const Ordering& ordering) {
@@ -589,9 +625,12 @@ struct LinearState {
 
   void update(const GaussianFactorGraph& gfg) {
     fillNumbers(gfg);
-    for (size_t i = 0; i < groups.size(); i++)
-      check(b200_linear_update(prob, (int64_t)i, groups[i].Ab.data(), groups[i].has_model ? groups[i].sigmas.data() : nullptr),
-            "b200_linear_update");
+    for (size_t q = 0; q < jgroups.size(); q++) {
+      const LinGroup& g = groups[jgroups[q]];
+      check(b200_linear_update(prob, (int64_t)q, g.Ab.data(), g.has_model ? g.sigmas.data() : nullptr), "b200_linear_update");
+    }
+    for (size_t q = 0; q < hgroups.size(); q++)
+      check(b200_linear_update_hessian(prob, (int64_t)q, groups[hgroups[q]].Ab.data()), "b200_linear_update_hessian");
   }
 
   VectorValues solve() {

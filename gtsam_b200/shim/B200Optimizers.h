@@ -132,8 +132,8 @@ class B200Marginals {
 };
 
 /// GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky) (gtsam/linear/GaussianFactorGraph.cpp:316-319) on the
-/// device for ANY graph of JacobianFactors (any arity / block widths, Unit or Diagonal models): the
-/// "GaussianFactorGraph::optimize-level entry" of SURVEY 8b.  HessianFactors and Constrained models =>
+/// device for ANY graph of JacobianFactors (any arity / block widths, Unit or Diagonal models) and HessianFactors: the
+/// "GaussianFactorGraph::optimize-level entry" of SURVEY 8b.  Constrained models and other GaussianFactor types =>
 /// std::invalid_argument (no CPU fallback); a singular system => IndeterminantLinearSystemException as in the reference.
 gtsam::VectorValues optimizeOnDevice(const gtsam::GaussianFactorGraph& gfg, const gtsam::Ordering& ordering);
 

@@ -74,7 +74,8 @@ enum {
   B200_NUM_FACTOR_TYPES = 6,
   /* internal tag of the groups of a linear problem (b200_linear_create); never valid in a
      b200_factor_group */
-  B200_FACTOR_JACOBIAN = 6
+  B200_FACTOR_JACOBIAN = 6,
+  B200_FACTOR_HESSIAN = 7
 };
 
 /* ---- noise models (gtsam/linear/NoiseModel.cpp:83-130,163-238,322-340,646-675) */
@@ -308,8 +309,9 @@ int b200_dl_get_state(const b200_dl* dl, double* error, double* delta, int32_t* 
  * GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky)
  * (gtsam/linear/GaussianFactorGraph.cpp:316-319 -> EliminateableFactorGraph-inst.h:123-146 ->
  * HessianFactor.cpp:516-536 -> linearAlgorithms-inst.h:50-117) does for a graph of JacobianFactors
- * of any arity and any block widths (gtsam/linear/JacobianFactor.h:93-103), i.e. rows a11-a16 of the
- * hot path without a1-a9.  The handle is a b200_problem: b200_solve (lambda = 0, or > 0 for
+ * of any arity and any block widths (gtsam/linear/JacobianFactor.h:93-103) and HessianFactors
+ * (gtsam/linear/HessianFactor.h:99-110; HessianFactor::updateHessian, HessianFactor.cpp:348-374),
+ * i.e. rows a11-a16 of the hot path without a1-a9.  The handle is a b200_problem: b200_solve (lambda = 0, or > 0 for
  * buildDampedSystem's priors), b200_get_delta, b200_hessian_diagonal, b200_get_conditional,
  * b200_symbolic_info_get / b200_get_cliques, b200_marginal_covariance and
  * b200_joint_marginal_covariance work on it; the calls that need Values (b200_error, b200_linearize,
@@ -333,12 +335,28 @@ typedef struct b200_jacobian_group {
                                Constrained models (sigma == 0) are rejected: B200_UNSUPPORTED_NOISE */
 } b200_jacobian_group;
 
+/* One run of HessianFactors (gtsam/linear/HessianFactor.h:99-110) with the same block widths: the
+ * quadratic 0.5 (f - 2 x'g + x'G x), stored as the augmented information matrix [G g; g' f]. */
+typedef struct b200_hessian_group {
+  int32_t arity;            /* k, 1 .. B200_JACOBIAN_MAX_ARITY                         */
+  const int32_t* dims;      /* k block widths                                          */
+  int64_t count;
+  int64_t graph_index0;     /* -1: append after the previous group (Jacobian groups come first) */
+  const int64_t* graph_index;
+  const int64_t* keys;      /* count*arity variable ids                                */
+  const double* info;       /* count blocks, each (N+1) x (N+1) COLUMN-MAJOR, N = sum(dims):
+                               HessianFactor::info() (SymmetricBlockMatrix); only the upper
+                               triangle is read                                        */
+} b200_hessian_group;
+
 typedef struct b200_linear_desc {
   int64_t nvars;
   const int32_t* var_dim;   /* nvars: tangent dimension of every variable (>= 1)       */
   const int64_t* ordering;  /* nvars: elimination order (variable ids)                 */
   int64_t ngroups;
   const b200_jacobian_group* groups;
+  int64_t nhgroups;         /* HessianFactor groups (0 / NULL when the graph has none) */
+  const b200_hessian_group* hgroups;
 } b200_linear_desc;
 
 /* Pack + symbolic phase + upload of the whitened [A|b] blocks (whitening is a kernel). */
@@ -346,6 +364,8 @@ int b200_linear_create(b200_ctx* ctx, const b200_linear_desc* desc, b200_problem
 /* New numbers, same structure (the next linearization of the same graph): re-uploads group
  * `group`'s [A|b] (and sigmas, NULL = unit); the symbolic phase and all tables are reused. */
 int b200_linear_update(b200_problem* prob, int64_t group, const double* Ab, const double* sigmas);
+/* The same for HessianFactor group `hgroup`: new augmented information matrices. */
+int b200_linear_update_hessian(b200_problem* prob, int64_t hgroup, const double* info);
 /* Host-only symbolic phase of a linear description (CPU tests of a11 on n-ary factors). */
 typedef struct b200_symbolic b200_symbolic;
 int b200_linear_symbolic_create(const b200_linear_desc* desc, b200_symbolic** out);

@@ -5,13 +5,15 @@
  * Variable id i <-> gtsam::Key i.
  *
  * Layout ("B200LIN1"): nvars(q) var_dim(i32 x nvars) ordering(q x nvars) ngroups(q), then per group
- * rows(i32) arity(i32) dims(i32 x arity) count(q) graph_index0(q) flags(i32: 1 sigmas, 4 graph_index)
+ * rows(i32) arity(i32) dims(i32 x arity) count(q) graph_index0(q) flags(i32: 1 sigmas, 4 graph_index,
+ * 8 HessianFactor group: rows = sum(dims)+1 and "Ab" holds the augmented information matrices)
  * keys(q x count*arity) Ab(f64 x count*rows*ncols, column-major blocks) [sigmas(f64 x count*rows)]
  * [graph_index(q x count)].
  */
 #pragma once
 #include <gtsam/inference/Ordering.h>
 #include <gtsam/linear/GaussianFactorGraph.h>
+#include <gtsam/linear/HessianFactor.h>
 #include <gtsam/linear/JacobianFactor.h>
 #include <gtsam/linear/NoiseModel.h>
 #include <gtsam/linear/VectorValues.h>
@@ -97,6 +99,17 @@ static gtsam::GaussianFactorGraph build_graph(const LinProb& p) {
     const int nc = g.ncols();
     for (int64_t i = 0; i < g.count; i++) {
       const double* M = g.Ab.data() + (size_t)i * g.rows * nc;
+      const int64_t ppos = (g.flags & 4) ? g.gidx[i] : g.gi0 + i;
+      if (g.flags & 8) {   // HessianFactor(keys, dims, SymmetricBlockMatrix-like augmented information)
+        KeyVector keys;
+        std::vector<DenseIndex> dims;
+        for (int a = 0; a < g.arity; a++) { keys.push_back(Key(g.keys[i * g.arity + a])); dims.push_back(g.dims[a]); }
+        dims.push_back(1);
+        Matrix full(nc, nc);
+        for (int c = 0; c < nc; c++) for (int r = 0; r < nc; r++) full(r, c) = r <= c ? M[r + (size_t)c * nc] : M[c + (size_t)r * nc];
+        slots[ppos] = std::make_shared<HessianFactor>(keys, SymmetricBlockMatrix(dims, full));
+        continue;
+      }
       std::vector<std::pair<Key, Matrix>> terms;
       int col = 0;
       for (int a = 0; a < g.arity; a++) {
@@ -137,9 +150,8 @@ static bool from_graph(const gtsam::GaussianFactorGraph& gfg, const gtsam::Order
   std::map<Key, int> dimOf;
   for (auto& f : gfg) {
     if (!f) continue;
-    auto jf = std::dynamic_pointer_cast<JacobianFactor>(f);
-    if (!jf) return false;
-    for (auto it = jf->begin(); it != jf->end(); ++it) { ids[*it] = 0; dimOf[*it] = (int)jf->getDim(it); }
+    if (!std::dynamic_pointer_cast<JacobianFactor>(f) && !std::dynamic_pointer_cast<HessianFactor>(f)) return false;
+    for (auto it = f->begin(); it != f->end(); ++it) { ids[*it] = 0; dimOf[*it] = (int)f->getDim(it); }
   }
   int64_t n = 0;
   for (auto& kv : ids) kv.second = n++;
@@ -152,6 +164,26 @@ static bool from_graph(const gtsam::GaussianFactorGraph& gfg, const gtsam::Order
   int64_t pos = 0;
   for (auto& f : gfg) {
     if (!f) continue;
+    if (auto hf = std::dynamic_pointer_cast<HessianFactor>(f)) {
+      std::vector<int> sig{-1, 0};
+      for (auto it = hf->begin(); it != hf->end(); ++it) sig.push_back((int)hf->getDim(it));
+      auto found = sig2group.find(sig);
+      if (found == sig2group.end()) {
+        JGroup g;
+        g.arity = (int32_t)hf->size(); g.flags = 4 | 8; g.gi0 = -1;
+        for (auto it = hf->begin(); it != hf->end(); ++it) g.dims.push_back((int32_t)hf->getDim(it));
+        g.rows = g.ncols();
+        out->groups.push_back(g);
+        found = sig2group.emplace(sig, out->groups.size() - 1).first;
+      }
+      JGroup& g = out->groups[found->second];
+      for (auto it = hf->begin(); it != hf->end(); ++it) g.keys.push_back(ids.at(*it));
+      const Matrix info = hf->info().selfadjointView();
+      for (int c = 0; c < info.cols(); c++) for (int r = 0; r < info.rows(); r++) g.Ab.push_back(info(r, c));
+      g.gidx.push_back(pos++);
+      g.count++;
+      continue;
+    }
     auto jf = std::dynamic_pointer_cast<JacobianFactor>(f);
     const SharedDiagonal& model = jf->get_model();
     if (model && model->isConstrained()) return false;

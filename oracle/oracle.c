@@ -730,12 +730,32 @@ int orc_linear_create(const b200_linear_desc* desc, orc_problem** out) {
   p->cal = (double*)malloc(5 * sizeof(double));
   p->ngroups = desc->ngroups;
   p->groups = (ogroup*)calloc((size_t)(desc->ngroups ? desc->ngroups : 1), sizeof(ogroup));
+  p->ngroups = desc->ngroups + desc->nhgroups;
+  free(p->groups);
+  p->groups = (ogroup*)calloc((size_t)(p->ngroups ? p->ngroups : 1), sizeof(ogroup));
   int64_t next = 0, total = 0;
   for (int64_t g = 0; g < desc->ngroups; g++) total += desc->groups[g].count;
+  for (int64_t g = 0; g < desc->nhgroups; g++) total += desc->hgroups[g].count;
   p->nfactors = total;
   p->fgroup = (int32_t*)malloc((size_t)(total ? total : 1) * sizeof(int32_t));
   p->fidx = (int64_t*)malloc((size_t)(total ? total : 1) * sizeof(int64_t));
   for (int64_t i = 0; i < total; i++) p->fgroup[i] = -1;
+  for (int64_t hg = 0; hg < desc->nhgroups; hg++) { /* HessianFactor groups are stored after the Jacobian groups */
+    const b200_hessian_group* s = &desc->hgroups[hg];
+    const int64_t g = desc->ngroups + hg;
+    ogroup* o = &p->groups[g];
+    if (s->arity < 1 || s->arity > B200_JACOBIAN_MAX_ARITY) return B200_UNSUPPORTED_FACTOR;
+    o->type = B200_FACTOR_HESSIAN;
+    o->count = s->count;
+    o->arity = s->arity;
+    o->ncols = 1;
+    for (int a = 0; a < s->arity; a++) o->ncols += s->dims[a];
+    o->d = o->ncols;
+    o->keys = (int64_t*)malloc((size_t)(s->count * s->arity + 1) * sizeof(int64_t));
+    memcpy(o->keys, s->keys, (size_t)(s->count * s->arity) * sizeof(int64_t));
+    o->J = (double*)calloc((size_t)(s->count * o->d * o->ncols + 1), sizeof(double));
+    memcpy(o->J, s->info, (size_t)(s->count * o->d * o->ncols) * sizeof(double));
+  }
   for (int64_t g = 0; g < desc->ngroups; g++) {
     const b200_jacobian_group* s = &desc->groups[g];
     ogroup* o = &p->groups[g];
@@ -767,9 +787,37 @@ int orc_linear_create(const b200_linear_desc* desc, orc_problem** out) {
       }
     }
   }
+  for (int64_t hg = 0; hg < desc->nhgroups; hg++) {
+    const b200_hessian_group* s = &desc->hgroups[hg];
+    const int64_t g = desc->ngroups + hg;
+    ogroup* o = &p->groups[g];
+    o->graph_index0 = s->graph_index ? -1 : (s->graph_index0 < 0 ? next : s->graph_index0);
+    if (!s->graph_index) next = o->graph_index0 + s->count;
+    for (int64_t i = 0; i < s->count; i++) {
+      const int64_t gi = s->graph_index ? s->graph_index[i] : o->graph_index0 + i;
+      if (gi < 0 || gi >= total || p->fgroup[gi] != -1) return B200_INVALID_ARGUMENT;
+      p->fgroup[gi] = (int32_t)g;
+      p->fidx[gi] = i;
+      for (int a = 0; a < s->arity; a++) {
+        const int64_t k = o->keys[i * s->arity + a];
+        if (k < 0 || k >= n || p->var_dim[k] != s->dims[a]) return B200_INVALID_ARGUMENT;
+      }
+    }
+  }
   symbolic(p);
   *out = p;
   return B200_OK;
+}
+
+int orc_linear_update_hessian(orc_problem* p, int64_t hgroup, const double* info) {
+  int64_t k = 0;
+  for (int64_t g = 0; g < p->ngroups; g++)
+    if (p->groups[g].type == B200_FACTOR_HESSIAN && k++ == hgroup) {
+      ogroup* o = &p->groups[g];
+      memcpy(o->J, info, (size_t)(o->count * o->d * o->ncols) * sizeof(double));
+      return B200_OK;
+    }
+  return B200_INVALID_ARGUMENT;
 }
 
 int orc_linear_update(orc_problem* p, int64_t group, const double* Ab, const double* sigmas) {
@@ -1035,7 +1083,8 @@ void orc_hessian_diagonal(const orc_problem* p, double* out) {
       const int nv = p->var_dim[v];
       for (int c = 0; c < nv; c++, col++) {
         double s = 0;
-        for (int rr = 0; rr < d; rr++) s += J[rr + col * d] * J[rr + col * d];
+        if (g->type == B200_FACTOR_HESSIAN) s = J[col + col * d]; /* HessianFactor::hessianDiagonalAdd, HessianFactor.cpp:292-304 */
+        else for (int rr = 0; rr < d; rr++) s += J[rr + col * d] * J[rr + col * d];
         out[p->dof_off[v] + c] += s;
       }
     }
@@ -1051,6 +1100,22 @@ static double linear_error(const orc_problem* p, const double* delta) {
     const int64_t i = p->fidx[gi];
     const int d = g->d, ar = g->arity;
     const double* J = g->J + i * d * g->ncols;
+    if (g->type == B200_FACTOR_HESSIAN) { /* HessianFactor::error, HessianFactor.cpp:331-346: 0.5 (f - 2 x'g + x'G x) */
+      const int N = d - 1;
+      double x[N > 0 ? N : 1];
+      int col = 0;
+      for (int a = 0; a < ar; a++) {
+        const int64_t v = g->keys[i * ar + a];
+        for (int c = 0; c < p->var_dim[v]; c++, col++) x[col] = delta ? delta[p->dof_off[v] + c] : 0.0;
+      }
+      double xg = 0, xGx = 0;
+      for (int r = 0; r < N; r++) {
+        xg += x[r] * J[r + N * d];
+        for (int c = 0; c < N; c++) xGx += x[r] * x[c] * (r <= c ? J[r + c * d] : J[c + r * d]);
+      }
+      total += 0.5 * (J[N + N * d] - 2.0 * xg + xGx);
+      continue;
+    }
     double e[d > 0 ? d : 1];
     for (int rr = 0; rr < d; rr++) e[rr] = -J[rr + (g->ncols - 1) * d];
     int col = 0;
@@ -1123,7 +1188,10 @@ int orc_solve(orc_problem* p, double lambda, int diagonal_damping, double min_di
           for (int ca = 0; ca < dim[a]; ca++)
             for (int cb = 0; cb < dim[b]; cb++) {
               double sum = 0;
-              for (int rr = 0; rr < d; rr++) sum += J[rr + (col0[a] + ca) * d] * J[rr + (col0[b] + cb) * d];
+              if (g->type == B200_FACTOR_HESSIAN) /* HessianFactor::updateHessian, HessianFactor.cpp:348-374: upper blocks of info */
+                sum = J[(col0[a] + ca) + (col0[b] + cb) * d];
+              else
+                for (int rr = 0; rr < d; rr++) sum += J[rr + (col0[a] + ca) * d] * J[rr + (col0[b] + cb) * d];
               int64_t I = off[a] + ca, Jx = off[b] + cb;
               if (a == b && ca > cb) continue; /* diagonal block: upper only */
               if (I > Jx) { const int64_t t = I; I = Jx; Jx = t; }

@@ -45,6 +45,7 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out);
  * orc_hessian_diagonal, orc_get_conditional, orc_get_cliques and the marginals work on the result */
 int orc_linear_create(const b200_linear_desc* desc, orc_problem** out);
 int orc_linear_update(orc_problem* p, int64_t group, const double* Ab, const double* sigmas);
+int orc_linear_update_hessian(orc_problem* p, int64_t hgroup, const double* info);
 void orc_problem_destroy(orc_problem* p);
 void orc_set_values(orc_problem* p, const double* packed);
 void orc_get_values(const orc_problem* p, double* packed);

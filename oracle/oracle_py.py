@@ -35,6 +35,7 @@ def lib():
         from gtsam_b200 import linear as LN
         L.orc_linear_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(C.c_void_p)]
         L.orc_linear_update.argtypes = [C.c_void_p, C.c_int64, dp, dp]
+        L.orc_linear_update_hessian.argtypes = [C.c_void_p, C.c_int64, dp]
         L.orc_problem_destroy.argtypes = [C.c_void_p]
         L.orc_set_values.argtypes = [C.c_void_p, dp]
         L.orc_get_values.argtypes = [C.c_void_p, dp]
@@ -262,6 +263,10 @@ class OracleLinearProblem(OracleProblem):
             sigmas = np.ascontiguousarray(sigmas, dtype=np.float64)
             sp = _dp(sigmas)
         assert self.L.orc_linear_update(self.h, group, _dp(Ab), sp) == 0
+
+    def update_hessian(self, hgroup, info):
+        info = np.ascontiguousarray(info, dtype=np.float64)
+        assert self.L.orc_linear_update_hessian(self.h, hgroup, _dp(info)) == 0
 
     def get_jacobians(self, group):
         g = self.prob.groups[group]

@@ -15,6 +15,9 @@ container:
 * lin_sphere_tiny, lin_bal_tiny — the reference's own linearization of the sphere_tiny / bal_tiny_s2 graphs (the
                     whitened [A|b] of tests/golden/<case>.dump0.bin) re-posed as linear problems: must reproduce
                     those dumps' delta.
+* lin_mixed_hessian — lin_random_nary with every third factor turned into a HessianFactor (augmented information
+                    [A b]^T Sigma^-1 [A b] of the same numbers, plus a few genuinely full-rank quadratic factors): Jacobian
+                    and Hessian factors interleaved in one graph.
 * lin_singular    — an under-constrained graph: the reference throws IndeterminantLinearSystemException.
 Each case stores the problem (*.lin.bin, gtsam_b200.linear.LinearProblem.save) and the reference's outputs for
 lambda = 0 (*.out0.bin: delta, hessianDiagonal, linear errors, Bayes tree + conditionals, marginal covariances) and
@@ -43,7 +46,7 @@ def emit(name, lp=None):
     subprocess.check_call([H, "linsolve", path, os.path.join(HERE, f"{name}.out0.bin"), "0"])
     subprocess.check_call([H, "linsolve", path, os.path.join(HERE, f"{name}.out1.bin"), "0.25"])
     lp = LN.LinearProblem.load(path)
-    print("wrote", name, lp.nvars, "vars", lp.nfactors, "factors", len(lp.groups), "groups")
+    print("wrote", name, lp.nvars, "vars", lp.nfactors, "factors", len(lp.groups), "+", len(lp.hgroups), "groups")
 
 
 def random_nary(seed=0, nvars=40, nfac=90, max_arity=4):
@@ -130,6 +133,29 @@ def synthetic_pose2(path, n=40, seed=21):
         f.write("\n".join(lines) + "\n")
 
 
+def mixed_hessian(seed=4):
+    base = random_nary(seed=seed, nvars=30, nfac=70, max_arity=3)
+    rng = np.random.default_rng(seed + 100)
+    jg, hb = [], {}
+    for g in base.groups:
+        pos = g.graph_index
+        W = g.whitened()                      # (count, rows, ncols)
+        keepj = [i for i in range(g.count) if pos[i] % 3 != 0]
+        toh = [i for i in range(g.count) if pos[i] % 3 == 0]
+        if keepj:
+            jg.append(LN.JacobianGroup(g.rows, g.dims, g.keys[keepj], g.Ab[keepj], None if g.sigmas is None else g.sigmas[keepj],
+                                       graph_index=pos[keepj]))
+        for i in toh:
+            info = W[i].T @ W[i]
+            if i % 2 == 0:                     # a genuinely full-rank quadratic, not just a Jacobian in disguise
+                M = rng.normal(size=(info.shape[0] + 2, info.shape[0])) * 0.3
+                info = info + M.T @ M
+            b = hb.setdefault(tuple(int(d) for d in g.dims), dict(keys=[], info=[], pos=[]))
+            b["keys"].append(g.keys[i]); b["info"].append(info); b["pos"].append(pos[i])
+    hg = [LN.HessianGroup(dims, np.array(b["keys"]), np.array(b["info"]), graph_index=np.array(b["pos"])) for dims, b in hb.items()]
+    return LN.LinearProblem(base.var_dim, base.ordering, jg, hg)
+
+
 def singular():
     # x0 -- x1 -- x2 chain with no prior anywhere: A^T A is rank deficient
     rng = np.random.default_rng(9)
@@ -154,6 +180,7 @@ def main():
         f.write(subprocess.check_output([H, "pose2", g2o]).decode().strip().splitlines()[-1] + "\n")
     emit("lin_random_nary", random_nary())
     emit("lin_arity8", arity8())
+    emit("lin_mixed_hessian", mixed_hessian())
     emit("lin_sphere_tiny", from_typed_dump("sphere_tiny"))
     emit("lin_bal_tiny", from_typed_dump("bal_tiny_s2"))
     emit("lin_singular", singular())

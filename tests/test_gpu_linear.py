@@ -4,7 +4,8 @@ whitening, hessianDiagonal, delta, the two linear errors, the Bayes-tree cliques
 lambda = 0 and the damped system; marginal covariances; b200_linear_update; the GaussianFactorGraph mirror.
 
 The elimination / back-substitution kernels are the validated ones of the nonlinear path; new here are
-jacobian_load_kernel, assemble_jacobian_kernel, hdiag_jacobian_kernel and linerr_jacobian_kernel, written after the
+jacobian_load_kernel and the assemble / hessianDiagonal / linear-error kernels of the JacobianFactor and
+HessianFactor groups, written after the
 round's GPU budget was spent.  The CPU side (oracle + host symbolic phase on n-ary factors) is pinned in
 tests/test_linear.py; until its first hardware run this check lives in its own process and reports xfail instead of
 failing the suite.
@@ -61,6 +62,17 @@ lp2 = LN.LinearProblem(lp.var_dim, lp.ordering, [LN.JacobianGroup(h.rows, h.dims
 dev2 = capi.LinearDeviceProblem(ctx, lp2)
 assert dev2.solve(0.0)[0] == 0
 assert util.rel2(dev.get_delta(), dev2.get_delta()) <= 1e-12
+# HessianFactor groups: new information matrices, same structure
+lpm = util.load_linear_case("lin_mixed_hessian")
+devm = capi.LinearDeviceProblem(ctx, lpm)
+newinfo = lpm.hgroups[1].info * 1.01
+devm.update_hessian(1, newinfo)
+assert devm.solve(0.0)[0] == 0
+lpm2 = LN.LinearProblem(lpm.var_dim, lpm.ordering, lpm.groups,
+                        [LN.HessianGroup(g.dims, g.keys, newinfo if i == 1 else g.info, g.graph_index0, g.graph_index) for i, g in enumerate(lpm.hgroups)])
+devm2 = capi.LinearDeviceProblem(ctx, lpm2)
+assert devm2.solve(0.0)[0] == 0 and util.rel2(devm.get_delta(), devm2.get_delta()) <= 1e-12
+devm.close(); devm2.close()
 # the calls that need Values are refused, loudly
 try:
     dev.error()

@@ -76,10 +76,23 @@ def test_oracle_linear_update_reuses_structure():
     assert st == st2 == 0 and np.array_equal(o.get_delta(), o2.get_delta())
 
 
+def test_oracle_hessian_update_reuses_structure():
+    lp = util.load_linear_case("lin_mixed_hessian")
+    o = O.OracleLinearProblem(lp)
+    h = lp.hgroups[1]
+    new = h.info * 1.01
+    o.update_hessian(1, new)
+    assert o.solve(0.0)[0] == 0
+    lp2 = LN.LinearProblem(lp.var_dim, lp.ordering, lp.groups,
+                           [LN.HessianGroup(g.dims, g.keys, new if i == 1 else g.info, g.graph_index0, g.graph_index) for i, g in enumerate(lp.hgroups)])
+    o2 = O.OracleLinearProblem(lp2)
+    assert o2.solve(0.0)[0] == 0 and np.array_equal(o.get_delta(), o2.get_delta())
+
+
 def test_python_graph_mirror_packs_like_the_harness():
     """gtsam_b200.linear.GaussianFactorGraph.to_problem: ids in ascending key order, factors grouped by shape with
     their graph positions — the same system as the LinearProblem it came from (checked through the oracle)."""
-    lp = util.load_linear_case("lin_random_nary")
+    lp = util.load_linear_case("lin_mixed_hessian")
     gfg = LN.GaussianFactorGraph()
     flat = {}
     for g in lp.groups:
@@ -89,6 +102,9 @@ def test_python_graph_mirror_packs_like_the_harness():
             for d in g.dims:
                 blocks.append(M[:, c:c + d]); c += d
             flat[int(pos[i])] = LN.JacobianFactor([1000 + 7 * int(k) for k in g.keys[i]], blocks, M[:, c], None if g.sigmas is None else g.sigmas[i])
+    for g in lp.hgroups:
+        for i in range(g.count):
+            flat[int(g.graph_index[i])] = LN.HessianFactor([1000 + 7 * int(k) for k in g.keys[i]], g.dims, g.info[i])
     for pos in sorted(flat):
         gfg.add(flat[pos])
     order_keys = [1000 + 7 * int(v) for v in lp.ordering]
