@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush-l2", action="store_true", help="time the K steps back to back with L2 left warm")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="N > 1: auto = BAL workloads scale weakly (N x the points), others strongly; strong = the named workload "
+                         "itself sharded over the N ranks (BASELINE configs[3]/[4]: the 3M / 10M-factor graphs on 4 / 8 GPUs)")
     ap.add_argument("--jacobian-fp32", action="store_true",
                     help="BASELINE configs[4]'s precision mix: whitened Jacobians stored as floats (FP32 linearize output), FP64 solve")
     return ap.parse_args()
@@ -216,7 +219,7 @@ def main():
     weak = False
     if world > 1:   # weak scaling: per-GPU points fixed, cameras fixed (BAL); other workloads: strong scaling
         base = datasets.WORKLOADS[args.workload][1]
-        if "npoints" in base:
+        if "npoints" in base and args.scaling != "strong":
             over["npoints"] = base["npoints"] * world
             weak = True
     prob = datasets.make(args.workload, **over)
