@@ -54,7 +54,9 @@ def workload_config(prob, args):
     return {
         "workload": f"{args.workload}: {prob.name}", "factors": prob.nfactors, "variables": prob.nvars,
         "factor_types": sorted({int(g.type) for g in prob.groups}),
-        "ordering": "Schur (points, then cameras)" if prob.meta.get("kind") == "bal" else prob.meta.get("ordering", "natural"),
+        "ordering": ("Schur (points, then cameras)" if prob.meta.get("ordering", "schur") == "schur" else
+                     f"{prob.meta['ordering'].upper()} by the reference's Ordering::Create (shipped as data)") if prob.meta.get("kind") == "bal"
+        else prob.meta.get("ordering", "natural"),
         "lm_params": "LevenbergMarquardtParams::LegacyDefaults (lambda0=1e-5, factor 10)",
         "jacobian_storage": "fp32 (b200_set_jacobian_precision: FP64 evaluation, float [A|b], FP64 solve)" if getattr(args, "jacobian_fp32", False) else "fp64",
         "cache": ("L2 left warm between iterations (--no-flush-l2)" if getattr(args, "no_flush_l2", False) else
@@ -181,7 +183,8 @@ def run_reference(args):
     from gtsam_b200 import datasets
     prob = datasets.make(args.workload)
     # bounded: the reference needs 1.7 s (bal_c3) .. 40 s (bal_c4) per iterate
-    est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0, "bal_c5": 200.0, "sphere2500": 0.3}.get(args.workload, 1.0)
+    est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0, "bal_c5": 200.0, "sphere2500": 0.3,
+           "bal_1m_metis": 9.0, "bal_c4_metis": 40.0, "bal_c5_metis": 200.0}.get(args.workload, 1.0)
     steps = max(1, min(args.steps, int(150.0 / est)))
     warmup = min(args.warmup, 1 if est > 1 else 3)
     sec, info = reference_time(prob, steps, warmup)
@@ -219,7 +222,7 @@ def main():
     weak = False
     if world > 1:   # weak scaling: per-GPU points fixed, cameras fixed (BAL); other workloads: strong scaling
         base = datasets.WORKLOADS[args.workload][1]
-        if "npoints" in base and args.scaling != "strong":
+        if "npoints" in base and args.scaling != "strong" and base.get("ordering", "schur") == "schur":   # stored orderings fit one size
             over["npoints"] = base["npoints"] * world
             weak = True
     prob = datasets.make(args.workload, **over)
@@ -386,7 +389,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0}.get(args.workload, 1.0)
+            est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0, "bal_1m_metis": 9.0, "bal_c4_metis": 40.0, "bal_c5_metis": 200.0}.get(args.workload, 1.0)
             n = max(1, min(5, int(20.0 / est)))
             sec, cinfo = reference_time(prob, n, 1)
             line["cpu_baseline"] = dict(cinfo, value=1.0 / sec, unit=UNIT)

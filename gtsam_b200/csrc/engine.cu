@@ -670,9 +670,30 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
     std::sort(roots.begin(), roots.end());
     std::vector<int> assigned(nc, 0);
     double prefix = 0;
+    std::vector<double> load(world, 0.0);
     for (int64_t r : roots) {
       assigned[r] = subsum > 0 ? (int)std::min<double>(world - 1, std::floor(prefix * world / subsum)) : 0;
       prefix += w[r];
+      load[assigned[r]] += w[r];
+    }
+    // A few heavy subtrees (nested-dissection branches, camera chains) defeat the contiguous split: if
+    // longest-processing-time-first packing lowers the heaviest rank by more than 10 %, take it instead.
+    // (Many equal leaves - the BAL points of the default benchmark - stay contiguous: runs of points with
+    // the same cameras remain on one rank.)
+    {
+      std::vector<int64_t> by_w(roots);
+      std::sort(by_w.begin(), by_w.end(), [&](int64_t a, int64_t b) { return w[a] != w[b] ? w[a] > w[b] : a < b; });
+      std::vector<double> lpt_load(world, 0.0);
+      std::vector<int> lpt(nc, 0);
+      for (int64_t r : by_w) {
+        const int k = (int)(std::min_element(lpt_load.begin(), lpt_load.end()) - lpt_load.begin());
+        lpt[r] = k;
+        lpt_load[k] += w[r];
+      }
+      const double worst = *std::max_element(load.begin(), load.end());
+      const double worst_lpt = *std::max_element(lpt_load.begin(), lpt_load.end());
+      if (worst_lpt < 0.9 * worst && !getenv("B200_NO_LPT"))
+        for (int64_t r : roots) assigned[r] = lpt[r];
     }
     for (int64_t c = nc - 1; c >= 0; c--) {
       if ((*is_top)[c]) (*clique_owner)[c] = -1;

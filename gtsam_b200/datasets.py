@@ -159,8 +159,15 @@ def lookat_pose(eye, target, up):
     return np.stack([xc, yc, zc], -1), eye   # columns = camera axes
 
 
+def ordering_file(ncams, npoints, obs_per_point, visibility, seed, kind):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        f"data_bal_{ncams}c_{npoints}p_{obs_per_point}o_{visibility}_s{seed}_{kind}.npz")
+
+
 def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibility: str = "scattered",
-        camera_model: str = "cal3_s2", seed: int = 42, pixel_sigma: float = 1.0, body_sensor: bool = False) -> P.Problem:
+        camera_model: str = "cal3_s2", seed: int = 42, pixel_sigma: float = 1.0, body_sensor: bool = False,
+        ordering: str = "schur") -> P.Problem:
     rng = np.random.default_rng(seed)
     th = 2 * np.pi * np.arange(ncams) / ncams
     eye = np.stack([20 * np.cos(th), 20 * np.sin(th), 2 * np.sin(3 * th)], -1)
@@ -186,7 +193,21 @@ def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibili
     pts0 = pts + rng.normal(size=pts.shape) * 0.05
     # variable ids follow Key order: C(i) = 'c'<<56|i  <  P(j) = 'p'<<56|j
     keys = np.stack([cid, ncams + pid], -1)
-    order = np.concatenate([ncams + np.arange(npoints), np.arange(ncams)])   # Schur: points, then cameras
+    if ordering == "schur":
+        order = np.concatenate([ncams + np.arange(npoints), np.arange(ncams)])   # points, then cameras
+    elif ordering in ("metis", "colamd"):
+        # orderings are INPUTS at the boundary: produced by the reference's own Ordering::Metis / Ordering::Colamd
+        # for exactly this graph (tests/golden/make_orderings.py through oracle/ref_harness order) and shipped as data;
+        # the structure depends on every generator argument, hence the long file name
+        import os
+        path = ordering_file(ncams, npoints, obs_per_point, visibility, seed, ordering)
+        if not os.path.exists(path):
+            raise ValueError(f"no stored {ordering} ordering for this BAL graph ({path}); tests/golden/make_orderings.py writes it "
+                             "in the build container")
+        order = np.load(path)["ordering"].astype(np.int64)
+        assert order.size == ncams + npoints
+    else:
+        raise ValueError(ordering)
     if camera_model == "cal3_s2":
         K = np.array([[500.0, 500.0, 0.0, 320.0, 240.0]])
         z = np.stack([K[0, 0] * pn[:, 0] + K[0, 2] * pn[:, 1] + K[0, 3], K[0, 1] * pn[:, 1] + K[0, 4]], -1) + noise
@@ -226,7 +247,7 @@ def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibili
     pr = P.Problem(var_type, values, order, groups, cal,
                    name=f"bal_{ncams}c_{npoints}p_{visibility}_{camera_model}")
     pr.meta = dict(kind="bal", ncams=ncams, npoints=npoints, visibility=visibility,
-                   camera_model=camera_model, seed=seed)
+                   camera_model=camera_model, seed=seed, ordering=ordering)
     return pr
 
 
@@ -239,6 +260,12 @@ WORKLOADS = {
     "bal_1m": (bal, dict(ncams=300, npoints=166667)),                # north_star 1M-factor target
     "bal_c4": (bal, dict(ncams=1000, npoints=500000)),               # configs[3]: 3M factors
     "bal_c5": (bal, dict(ncams=5000, npoints=2000000, obs_per_point=5)),            # configs[4]: 10M factors (FP64 here)
+    # the same graphs eliminated in the reference's METIS nested-dissection order (what configs[3] names): all points stay
+    # leaves, fewer flops (bal_c4 6.6e9 vs 1.45e10, bal_c5 1.9e10 vs 7.5e10), 24-25 levels instead of 19 / 134, and
+    # balanced subtrees for the multi-GPU plan
+    "bal_1m_metis": (bal, dict(ncams=300, npoints=166667, ordering="metis")),
+    "bal_c4_metis": (bal, dict(ncams=1000, npoints=500000, ordering="metis")),
+    "bal_c5_metis": (bal, dict(ncams=5000, npoints=2000000, obs_per_point=5, ordering="metis")),
     "bal_tiny": (bal, dict(ncams=10, npoints=60, visibility="banded")),
     "sphere_tiny": (sphere, dict(layers=5, per_ring=8)),
 }

@@ -74,6 +74,9 @@ def main():
     si.groups[1].graph_index = np.array([kpos])
     emit("sphere_tiny_interleaved", si, gn_iters=2)
     emit("sphere_small_metis", with_ordering(datasets.sphere(layers=8, per_ring=12, seed=4), "metis"))
+    # BAL eliminated in the reference's METIS nested-dissection order (BASELINE configs[3] names METIS): camera and point
+    # cliques interleave, every point is still a leaf
+    emit("bal_small_metis", with_ordering(datasets.bal(ncams=12, npoints=300, seed=21), "metis"))
     # ---- input formats: synthetic text files written by gtsam_b200.io, parsed by the
     # REFERENCE's loaders (readG2o / SfmData::FromBalFile) into *.prob.bin; tests compare our readers with them
     import numpy as np

@@ -215,3 +215,28 @@ def test_gnc_weighted_problem_payloads():
             with np.errstate(divide="ignore"):
                 assert np.allclose(h.noise.reshape(g.count, d), np.broadcast_to(g.noise.reshape(-1, d), (g.count, d)) / np.sqrt(ww)[:, None])
     assert pw.nfactors == prob.nfactors and np.array_equal(pw.values, prob.values)
+
+
+@pytest.mark.parametrize("name,cliques,levels,max_front", [("bal_1m_metis", 166745, 18, (546, 576)), ("bal_c4_metis", 500258, 25, (1494, 1368))])
+def test_stored_metis_orderings_of_the_large_bal_workloads(built, name, cliques, levels, max_front):
+    """gtsam_b200/data_bal_*_metis.npz: the reference's own Ordering::Metis for the large BAL workloads (inputs at the
+    boundary, tests/golden/make_orderings.py).  They are permutations of the right size, every point stays a leaf clique,
+    and the junction tree has the recorded shape (BASELINE configs[3]: SURVEY 8d quotes 6.59e9 flops / max front
+    1404+1398 for the reference's METIS tree at this size)."""
+    import ctypes as C
+    from gtsam_b200 import capi, datasets, problem as P
+    prob = datasets.make(name)
+    assert np.array_equal(np.sort(prob.ordering), np.arange(prob.nvars))
+    L = capi.lib()
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    capi._check(L.b200_symbolic_create(C.byref(desc), C.byref(h)))
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info(h, C.byref(info))
+    L.b200_symbolic_destroy(h)
+    assert (info.ncliques, info.nlevels, (info.max_frontal_dim, info.max_separator_dim)) == (cliques, levels, max_front)
+    if name == "bal_c4_metis":
+        assert 6.0e9 < info.factor_flops < 7.0e9
+        co, fo = capi.shard_plan(prob, 4)      # nested-dissection branches: every rank busy, within 10 % of each other
+        per = np.bincount(fo, minlength=4)
+        assert per.min() > 0.85 * per.max()

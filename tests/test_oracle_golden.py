@@ -10,14 +10,14 @@ from gtsam_b200 import problem as P
 from oracle import oracle_py as O
 
 
-@pytest.mark.parametrize("case", util.CASES)
+@pytest.mark.parametrize("case", util.CASES + util.EXTRA_CASES)
 @pytest.mark.parametrize("kind,lam,diag", [("dump0", 0.0, 0), ("dump1", 1e-2, 1)])
 def test_oracle_matches_reference_dump(case, kind, lam, diag):
     prob = util.load_case(case)
     util.check_against_dump(O.OracleProblem(prob), prob, util.golden(case, kind), lam, diag)
 
 
-@pytest.mark.parametrize("case", util.CASES)
+@pytest.mark.parametrize("case", util.CASES + util.EXTRA_CASES)
 def test_oracle_lm_trace(case):
     """Same accept/reject sequence, lambdas and errors as LevenbergMarquardtOptimizer."""
     prob = util.load_case(case)

@@ -9,6 +9,9 @@ from oracle import refio
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["bal_tiny_s2", "bal_tiny_body_sensor", "bal_tiny_tukey", "bal_tiny_fair", "sphere_tiny_huber", "sphere_tiny_cauchy", "sphere_tiny_interleaved", "bal_tiny_bundler", "bal_tiny_colamd", "sphere_tiny", "sphere_tiny_gaussian", "sphere_small_colamd",
          "sphere_small_metis", "dubrovnik_3_7_unit", "dubrovnik_3_7_priors", "pose3example"]
+# cases added after the last hardware run of the -m gpu suite: pinned on the oracle in tests/test_oracle_golden.py, on the
+# device in tests/test_gpu_orderings.py (own process) until they have run on a B200 once
+EXTRA_CASES = ["bal_small_metis"]
 CERES_CASES = {"bal_tiny_bundler"}   # LM trace generated with LevenbergMarquardtParams::CeresDefaults
 
 
