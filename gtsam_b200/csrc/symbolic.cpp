@@ -2,7 +2,10 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 
 namespace b200 {
 
@@ -205,46 +208,72 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   }
   S->ea_map.assign(S->ea_ptr[nc], -1);
   S->didx.assign(S->didx_ptr[nc], -1);
-  std::vector<int> slot(n, -1);
-  for (int64_t c = 0; c < nc; c++) {
-    int k = 0;
-    int64_t dq = S->didx_ptr[c];
-    for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) {
-      const int64_t v = S->front_vars[q];
-      slot[v] = k;
-      for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
-      k += var_dim[v];
-    }
-    for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) {
-      const int64_t v = S->sep_vars[q];
-      slot[v] = k;
-      for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
-      k += var_dim[v];
-    }
-    const int nn = k + 1;
-    for (int64_t q = cf_ptr[c]; q < cf_ptr[c + 1]; q++) {
-      const int64_t i = cf[q];
-      for (int64_t a = fptr[i]; a < fptr[i + 1]; a++) {
-        S->fac_slots[a] = slot[fkeys[a]];
-        if (S->fac_slots[a] < 0) { *err = "internal: factor variable not in owning clique"; return false; }
+  // Every clique writes only its own ranges (its didx rows, the slots of the factors it owns, the ea_map of its
+  // children), so the cliques are processed in parallel: chunks handed out through an atomic counter, one slot[]
+  // scratch per thread.  (4.5 of the 7.3 s of this phase at 10M factors were spent here on one thread.)
+  std::atomic<int64_t> next_chunk(0);
+  std::atomic<int> failure(0);   // 1: factor variable missing, 2: child separator variable missing
+  const int64_t chunk = 2048;
+  auto worker = [&]() {
+    std::vector<int> slot(n, -1);
+    for (;;) {
+      const int64_t c0 = next_chunk.fetch_add(chunk);
+      if (c0 >= nc || failure.load()) return;
+      const int64_t c1 = std::min(nc, c0 + chunk);
+      for (int64_t c = c0; c < c1; c++) {
+        int k = 0;
+        int64_t dq = S->didx_ptr[c];
+        for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) {
+          const int64_t v = S->front_vars[q];
+          slot[v] = k;
+          for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
+          k += var_dim[v];
+        }
+        for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) {
+          const int64_t v = S->sep_vars[q];
+          slot[v] = k;
+          for (int t = 0; t < var_dim[v]; t++) S->didx[dq++] = (int)(S->var_dof[v] + t);
+          k += var_dim[v];
+        }
+        const int nn = k + 1;
+        for (int64_t q = cf_ptr[c]; q < cf_ptr[c + 1]; q++) {
+          const int64_t i = cf[q];
+          for (int64_t a = fptr[i]; a < fptr[i + 1]; a++) {
+            S->fac_slots[a] = slot[fkeys[a]];
+            if (S->fac_slots[a] < 0) failure.store(1);
+          }
+          S->fac_slot0[i] = S->fac_slots[fptr[i]];
+          if (fptr[i + 1] - fptr[i] >= 2) S->fac_slot1[i] = S->fac_slots[fptr[i] + 1];
+        }
+        for (int64_t q = ch_ptr[c]; q < ch_ptr[c + 1]; q++) {
+          const int64_t cc = ch[q];
+          int64_t e = S->ea_ptr[cc];
+          for (int64_t qq = S->sep_ptr[cc]; qq < S->sep_ptr[cc + 1]; qq++) {
+            const int64_t v = S->sep_vars[qq];
+            if (slot[v] < 0) { failure.store(2); continue; }
+            for (int t = 0; t < var_dim[v]; t++) S->ea_map[e++] = slot[v] + t;
+          }
+          S->ea_map[e < S->ea_ptr[cc + 1] ? e : S->ea_ptr[cc + 1] - 1] = nn - 1;
+        }
+        // reset scratch
+        for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) slot[S->front_vars[q]] = -1;
+        for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) slot[S->sep_vars[q]] = -1;
       }
-      S->fac_slot0[i] = S->fac_slots[fptr[i]];
-      if (fptr[i + 1] - fptr[i] >= 2) S->fac_slot1[i] = S->fac_slots[fptr[i] + 1];
     }
-    for (int64_t q = ch_ptr[c]; q < ch_ptr[c + 1]; q++) {
-      const int64_t cc = ch[q];
-      int64_t e = S->ea_ptr[cc];
-      for (int64_t qq = S->sep_ptr[cc]; qq < S->sep_ptr[cc + 1]; qq++) {
-        const int64_t v = S->sep_vars[qq];
-        if (slot[v] < 0) { *err = "internal: child separator variable not in parent clique"; return false; }
-        for (int t = 0; t < var_dim[v]; t++) S->ea_map[e++] = slot[v] + t;
-      }
-      S->ea_map[e] = nn - 1;
+  };
+  {
+    int nthreads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<int64_t>(16, (nc + chunk - 1) / chunk));
+    if (const char* e = getenv("B200_SYMBOLIC_THREADS")) nthreads = std::max(1, atoi(e));
+    if (nthreads <= 1) {
+      worker();
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+      for (auto& t : pool) t.join();
     }
-    // reset scratch
-    for (int64_t q = S->front_ptr[c]; q < S->front_ptr[c + 1]; q++) slot[S->front_vars[q]] = -1;
-    for (int64_t q = S->sep_ptr[c]; q < S->sep_ptr[c + 1]; q++) slot[S->sep_vars[q]] = -1;
   }
+  if (failure.load() == 1) { *err = "internal: factor variable not in owning clique"; return false; }
+  if (failure.load() == 2) { *err = "internal: child separator variable not in parent clique"; return false; }
   return true;
 }
 
