@@ -33,7 +33,7 @@ EXPORTS = [
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
-    "b200_set_jacobian_precision", "b200_get_jacobian_precision",
+    "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
         L.b200_linear_update_hessian.argtypes = [vp, C.c_int64, dp]
         L.b200_linear_symbolic_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
+        L.b200_symbolic_get_factor_slots.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
 
@@ -397,8 +398,9 @@ class LinearDeviceProblem(DeviceProblem):
         return out.reshape(g.count, g.ncols, g.rows).transpose(0, 2, 1)
 
 
-def linear_symbolic(lprob):
-    """Host-only junction tree of a linear problem: (frontal_ptr, frontal_vars, separator_ptr, separator_vars, parent)."""
+def linear_symbolic(lprob, with_slots=False):
+    """Host-only junction tree of a linear problem: (frontal_ptr, frontal_vars, separator_ptr, separator_vars, parent);
+    with_slots adds (owning clique per graph position, CSR pointer of the factors' keys, front slot of every key)."""
     L = lib()
     desc, keep = lprob.c_desc()
     h = C.c_void_p()
@@ -411,5 +413,15 @@ def linear_symbolic(lprob):
     sv = np.zeros(max(1, info.separator_list_len), dtype=np.int64)
     par = np.zeros(max(1, info.ncliques), dtype=np.int64)
     L.b200_symbolic_get_cliques(h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par))
+    if with_slots:
+        arity = np.zeros(lprob.nfactors, dtype=np.int64)
+        for g in list(lprob.groups) + list(lprob.hgroups):
+            pos = g.graph_index if g.graph_index is not None else g.graph_index0 + np.arange(g.count)
+            arity[pos] = g.arity
+        fptr = np.concatenate([[0], np.cumsum(arity)]).astype(np.int64)
+        clique = np.zeros(max(1, lprob.nfactors), dtype=np.int32)
+        slots = np.zeros(max(1, int(fptr[-1])), dtype=np.int32)
+        L.b200_symbolic_get_factor_slots(h, clique.ctypes.data_as(C.POINTER(C.c_int32)), slots.ctypes.data_as(C.POINTER(C.c_int32)))
     L.b200_symbolic_destroy(h)
-    return fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques]
+    out = (fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques])
+    return out + (clique[:lprob.nfactors], fptr, slots[:int(fptr[-1])]) if with_slots else out

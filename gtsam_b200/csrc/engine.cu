@@ -1565,6 +1565,11 @@ int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* fp, int64_t* fv, 
   fill_cliques(s->sym, fp, fv, sp, sv, parent);
   return B200_OK;
 }
+int b200_symbolic_get_factor_slots(const b200_symbolic* s, int32_t* clique, int32_t* slots) {
+  for (size_t i = 0; i < s->sym.fac_clique.size(); i++) clique[i] = s->sym.fac_clique[i];
+  for (size_t i = 0; i < s->sym.fac_slots.size(); i++) slots[i] = s->sym.fac_slots[i];
+  return B200_OK;
+}
 int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level) {
   for (int64_t c = 0; c < s->sym.ncliques; c++) level[c] = s->sym.level[c];
   return B200_OK;

@@ -386,6 +386,10 @@ int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info);
 int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* frontal_ptr, int64_t* frontal_vars,
                               int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
 int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level); /* ncliques */
+/* Scatter tables of the assembly (a12): owning clique of every factor by graph position (nfactors entries) and the
+ * scalar slot, in that clique's front, of every key of every factor (laid out factor after factor in graph order,
+ * each factor's keys in its own key order). */
+int b200_symbolic_get_factor_slots(const b200_symbolic* s, int32_t* clique, int32_t* slots);
 
 /* Parity of a14: the conditional [R S d] of clique c after a solve
  * (gtsam/linear/HessianFactor.cpp:459-487), nf x (nf+ns+1) column-major. */
