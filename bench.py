@@ -391,7 +391,7 @@ def main():
         try:
             est = {"bal_c3": 2.0, "bal_1m": 9.0, "bal_c4": 40.0, "bal_1m_metis": 9.0, "bal_c4_metis": 40.0, "bal_c5_metis": 200.0}.get(args.workload, 1.0)
             n = max(1, min(5, int(20.0 / est)))
-            sec, cinfo = reference_time(prob, n, 1)
+            sec, cinfo = reference_time(prob, n, 1 if est <= 10.0 else 0)   # 3M / 10M factors: 30-250 s per reference iterate
             line["cpu_baseline"] = dict(cinfo, value=1.0 / sec, unit=UNIT)
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}

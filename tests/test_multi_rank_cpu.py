@@ -91,3 +91,32 @@ def test_two_rank_partial_sums_over_gloo(built):
     for r in range(world):
         ok_err, ok_hd, covered, nleaf = out[r]
         assert ok_err and ok_hd and covered and nleaf > 0
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_shard_plan_of_a_nested_dissection_bal_graph(built, world):
+    """bal_1m_metis (the reference's METIS ordering): the few heavy nested-dissection branches make the planner fall
+    back to longest-processing-time-first packing; the plan stays valid (ancestor-closed top, one rank per subtree,
+    every factor owned once) and every rank gets a comparable share of the factors."""
+    import ctypes as C
+    prob = datasets.make("bal_1m_metis")
+    co, fo = capi.shard_plan(prob, world)
+    L = capi.lib()
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    capi._check(L.b200_symbolic_create(C.byref(desc), C.byref(h)))
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info(h, C.byref(info))
+    fp, sp = np.zeros(info.ncliques + 1, dtype=np.int64), np.zeros(info.ncliques + 1, dtype=np.int64)
+    fv, sv = np.zeros(info.frontal_list_len, dtype=np.int64), np.zeros(max(1, info.separator_list_len), dtype=np.int64)
+    par = np.zeros(info.ncliques, dtype=np.int64)
+    L.b200_symbolic_get_cliques(h, capi._ip(fp), capi._ip(fv), capi._ip(sp), capi._ip(sv), capi._ip(par))
+    L.b200_symbolic_destroy(h)
+    has_par = par >= 0
+    pc = co[par[has_par]]
+    cc = co[has_par]
+    assert np.all((pc == -1) | (pc == cc))            # a non-top parent owns its whole subtree
+    assert not np.any((cc == -1) & (pc != -1))        # the top is ancestor-closed
+    assert (co == -1).sum() >= 1 and set(np.unique(fo)) == set(range(world))
+    counts = np.bincount(fo, minlength=world)
+    assert counts.min() > 0.8 * counts.max()
