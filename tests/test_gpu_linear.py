@@ -103,7 +103,7 @@ print("LINEAR_OK", n, worst, ctx.launch_count())
 
 def test_cuda_linear_level_matches_reference_isolated():
     try:
-        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=600)
+        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=420)
     except subprocess.TimeoutExpired:
         pytest.xfail("device GaussianFactorGraph level: first hardware run timed out")
     lines = [l for l in out.stdout.splitlines() if l.startswith("LINEAR_OK")]

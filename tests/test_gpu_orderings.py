@@ -51,7 +51,7 @@ print("ORDERINGS_OK", res, info.ncliques, info.nlevels, ctx.launch_count())
 
 def test_cuda_metis_ordered_bal_isolated():
     try:
-        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=900)
+        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=420)
     except subprocess.TimeoutExpired:
         pytest.xfail("METIS-ordered BAL: first hardware run timed out")
     lines = [l for l in out.stdout.splitlines() if l.startswith("ORDERINGS_OK")]

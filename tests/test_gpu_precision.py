@@ -87,7 +87,7 @@ print("F32_OK", wj, wd, we, ctx.launch_count())
 
 def test_cuda_fp32_storage_mode_isolated():
     try:
-        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=900)
+        out = subprocess.run([sys.executable, "-c", SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=420)
     except subprocess.TimeoutExpired:
         pytest.xfail("FP32-storage mode: first hardware run timed out")
     lines = [l for l in out.stdout.splitlines() if l.startswith("F32_OK")]

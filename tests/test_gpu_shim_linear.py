@@ -21,7 +21,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "shim_linear")
 
 
 def run(*args):
-    out = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=420)
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
