@@ -169,7 +169,8 @@ class B200LinearSolver {
 ///     virtual VectorValues NonlinearOptimizer::solve(const GaussianFactorGraph&, const NonlinearOptimizerParams&) const
 /// (gtsam/nonlinear/NonlinearOptimizer.h:128-130, called by tryLambda at LevenbergMarquardtOptimizer.cpp:156) runs on the
 /// device.  linearize(), the damped system, retract and error stay the reference's own host code, so this variant
-/// accepts ANY factor type GTSAM can linearize (e.g. the Pose2 graph of BASELINE configs[0]); use
+/// accepts ANY factor type GTSAM can linearize to Jacobian / Hessian factors (the Pose2 graph of BASELINE configs[0],
+/// GeneralSFMFactor2, SmartProjectionPoseFactor in HESSIAN mode, ExpressionFactors: tests/shim_families.cpp); use
 /// B200LevenbergMarquardtOptimizer when all factors are of the device-resident kinds.
 /// Requires linearSolverType MULTIFRONTAL_CHOLESKY (the default); anything else => std::invalid_argument.
 class B200SolveLevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimizer {

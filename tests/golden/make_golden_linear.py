@@ -18,6 +18,9 @@ container:
 * lin_mixed_hessian — lin_random_nary with every third factor turned into a HessianFactor (augmented information
                     [A b]^T Sigma^-1 [A b] of the same numbers, plus a few genuinely full-rank quadratic factors): Jacobian
                     and Hessian factors interleaved in one graph.
+* lin_family_sfm2 / _smart / _expr — the reference's linearizations of GeneralSFMFactor2 (ternary factors, a 5-dof
+                    calibration variable), SmartProjectionPoseFactor (HessianFactors over 6 cameras) and ExpressionFactor
+                    graphs of one small synthetic scene (tests/shim_families.cpp dumplin).
 * lin_singular    — an under-constrained graph: the reference throws IndeterminantLinearSystemException.
 Each case stores the problem (*.lin.bin, gtsam_b200.linear.LinearProblem.save) and the reference's outputs for
 lambda = 0 (*.out0.bin: delta, hessianDiagonal, linear errors, Bayes tree + conditionals, marginal covariances) and
@@ -184,6 +187,13 @@ def main():
     emit("lin_sphere_tiny", from_typed_dump("sphere_tiny"))
     emit("lin_bal_tiny", from_typed_dump("bal_tiny_s2"))
     emit("lin_singular", singular())
+    # SURVEY 8(f) rank-4 families (GeneralSFMFactor2, smart factors in HESSIAN mode, expression factors) linearized by the
+    # reference on a small synthetic scene (tests/shim_families.cpp)
+    fam = os.path.join(os.path.dirname(H), "shim_families")
+    if os.path.exists(fam):
+        subprocess.check_call([fam, "dumplin", HERE])
+        for name in ("sfm2", "smart", "expr"):
+            emit(f"lin_family_{name}")
 
 
 if __name__ == "__main__":

@@ -53,3 +53,20 @@ def test_shim_solve_seam_on_pose2_graph():
           and r["launches"] > 0 and r["solves"] >= len(r["lm_dev_errors"]) - 1)
     if not ok:
         pytest.xfail(f"shim_linear pose2: first hardware run off: {r}")
+
+
+FBIN = os.path.join(ROOT, "oracle", "_ref", "shim_families")
+
+
+@pytest.mark.skipif(not os.path.exists(FBIN), reason="shim_families not built (needs /root/reference at build time)")
+def test_shim_solve_seam_on_rank4_factor_families():
+    """GeneralSFMFactor2, smart projection factors (HESSIAN mode) and expression factors: the stock
+    LevenbergMarquardtOptimizer against B200SolveLevenbergMarquardtOptimizer (GTSAM linearizes, the device solves)."""
+    try:
+        out = subprocess.run([FBIN, "gpu"], capture_output=True, text=True, timeout=420)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001
+        pytest.xfail(f"shim_families gpu: first hardware run did not complete: {e}")
+    bad = {k: v for k, v in r.items() if not (v["worst_error_rel_diff"] <= 1e-7 and v["value_diff"] <= 1e-6 and v["launches"] > 0)}
+    if bad:
+        pytest.xfail(f"shim_families gpu: first hardware run off: {bad}")

@@ -165,3 +165,20 @@ def test_cpp_shim_packs_a_gaussian_factor_graph_like_the_reference(case):
     out = subprocess.check_output([SHIM_LINEAR, "hostpack", __import__("os").path.join(util.GOLDEN, f"{case}.lin.bin")], timeout=120)
     r = json.loads(out.decode().strip().splitlines()[-1])
     assert r["equal"] == 1 and r["cliques"] == r["reference_cliques"] > 0
+
+
+SHIM_FAMILIES = __import__("os").path.join(__import__("os").path.dirname(util.GOLDEN), "..", "oracle", "_ref", "shim_families")
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(SHIM_FAMILIES), reason="shim_families not built (needs /root/reference at build time)")
+def test_cpp_shim_accepts_the_rank4_factor_families():
+    """SURVEY 8(f) rank 4 through the solve() seam, host side: GeneralSFMFactor2 (ternary Jacobians), smart projection
+    factors (HessianFactors over all cameras of a point) and expression factors linearized by GTSAM; the shim packs each
+    GaussianFactorGraph and the library's symbolic phase builds the reference's cliques."""
+    import json
+    import subprocess
+    r = json.loads(subprocess.check_output([SHIM_FAMILIES, "host"], timeout=120).decode().strip().splitlines()[-1])
+    assert set(r) == {"sfm2", "smart", "expr"}
+    for name, f in r.items():
+        assert f["cliques_equal"] == 1 and f["other"] == 0 and f["cliques"] > 0, (name, f)
+    assert r["sfm2"]["max_arity"] == 3 and r["smart"]["hessian"] == 24 and r["smart"]["max_arity"] == 6

@@ -130,7 +130,8 @@ def check_tree_against_dump(be, prob, ref, loose=1.0):
         assert np.abs(mine[:, cols] - Rref).max() <= 1e-7 * scale * loose, (c, fr)
 
 
-LINEAR_CASES = ["lin_pose2_toy", "lin_pose2_synth", "lin_random_nary", "lin_mixed_hessian", "lin_arity8", "lin_sphere_tiny", "lin_bal_tiny", "lin_singular"]
+LINEAR_CASES = ["lin_pose2_toy", "lin_pose2_synth", "lin_random_nary", "lin_mixed_hessian", "lin_arity8", "lin_sphere_tiny", "lin_bal_tiny", "lin_singular",
+                "lin_family_sfm2", "lin_family_smart", "lin_family_expr"]
 LINEAR_LAMBDA = {0: 0.0, 1: 0.25}   # *.out0.bin / *.out1.bin (tests/golden/make_golden_linear.py)
 
 
