@@ -686,6 +686,52 @@ std::vector<std::pair<KeyVector, KeyVector>> symbolicOnHost(const GaussianFactor
   return out;
 }
 
+GaussianBayesTree::shared_ptr bayesTreeFromTables(const std::vector<KeyVector>& frontals, const std::vector<KeyVector>& separators,
+                                                  const std::vector<int64_t>& parent, const std::vector<Matrix>& conditionals,
+                                                  const std::map<Key, int>& dims) {
+  const size_t nc = frontals.size();
+  if (separators.size() != nc || parent.size() != nc || conditionals.size() != nc)
+    throw std::invalid_argument("gtsam_b200::bayesTreeFromTables: table sizes differ");
+  auto bt = std::make_shared<GaussianBayesTree>();
+  std::vector<GaussianBayesTree::sharedClique> cliques(nc);
+  for (size_t k = nc; k-- > 0;) {   // top down: parents have larger indices than their children
+    KeyVector keys(frontals[k]);
+    keys.insert(keys.end(), separators[k].begin(), separators[k].end());
+    std::vector<DenseIndex> bd;
+    for (Key key : keys) bd.push_back(dims.at(key));
+    bd.push_back(1);
+    auto cond = std::make_shared<GaussianConditional>(keys, frontals[k].size(), VerticalBlockMatrix(bd, conditionals[k]));
+    cliques[k] = std::make_shared<GaussianBayesTreeClique>(cond);
+    if (parent[k] >= 0 && (size_t)parent[k] <= k) throw std::invalid_argument("gtsam_b200::bayesTreeFromTables: a parent must follow its children");
+    bt->addClique(cliques[k], parent[k] >= 0 ? cliques[(size_t)parent[k]] : GaussianBayesTree::sharedClique());
+  }
+  return bt;
+}
+
+GaussianBayesTree::shared_ptr eliminateMultifrontalOnDevice(const GaussianFactorGraph& gfg, const Ordering& ordering) {
+  LinearState st;
+  st.build(gfg, ordering);
+  st.solve();   // eliminates every clique (and back-substitutes); throws IndeterminantLinearSystemException like the reference
+  b200_symbolic_info info;
+  check(b200_symbolic_info_get(st.prob, &info), "b200_symbolic_info_get");
+  std::vector<int64_t> fp(info.ncliques + 1), sp(info.ncliques + 1), fv(std::max<int64_t>(1, info.frontal_list_len)),
+      sv(std::max<int64_t>(1, info.separator_list_len)), par(std::max<int64_t>(1, info.ncliques));
+  check(b200_get_cliques(st.prob, fp.data(), fv.data(), sp.data(), sv.data(), par.data()), "b200_get_cliques");
+  std::vector<KeyVector> F(info.ncliques), S(info.ncliques);
+  std::vector<Matrix> C(info.ncliques);
+  std::map<Key, int> dims;
+  for (size_t i = 0; i < st.id2key.size(); i++) dims[st.id2key[i]] = st.var_dim[i];
+  par.resize(info.ncliques);
+  for (int64_t c = 0; c < info.ncliques; c++) {
+    int f = 0, s = 0;
+    for (int64_t q = fp[c]; q < fp[c + 1]; q++) { F[c].push_back(st.id2key[(size_t)fv[q]]); f += st.var_dim[(size_t)fv[q]]; }
+    for (int64_t q = sp[c]; q < sp[c + 1]; q++) { S[c].push_back(st.id2key[(size_t)sv[q]]); s += st.var_dim[(size_t)sv[q]]; }
+    C[c].resize(f, f + s + 1);   // Eigen default is column-major, as b200_get_conditional writes it
+    check(b200_get_conditional(st.prob, c, C[c].data()), "b200_get_conditional");
+  }
+  return bayesTreeFromTables(F, S, par, C, dims);
+}
+
 static void requireMultifrontalCholesky(const NonlinearOptimizerParams& params) {
   if (params.linearSolverType != NonlinearOptimizerParams::MULTIFRONTAL_CHOLESKY)
     throw std::invalid_argument("gtsam_b200: the device solve() is multifrontal Cholesky "

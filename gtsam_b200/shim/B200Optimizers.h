@@ -30,7 +30,11 @@
 #include <gtsam/nonlinear/LevenbergMarquardtOptimizer.h>
 #include <gtsam/nonlinear/Marginals.h>
 
+#include <gtsam/linear/GaussianBayesTree.h>
+
+#include <map>
 #include <memory>
+#include <vector>
 
 namespace gtsam_b200 {
 
@@ -142,6 +146,20 @@ gtsam::VectorValues optimizeOnDevice(const gtsam::GaussianFactorGraph& gfg, cons
 /// eliminateMultifrontal(ordering) builds.  For inspection and CPU-side tests of the packing.
 std::vector<std::pair<gtsam::KeyVector, gtsam::KeyVector>> symbolicOnHost(const gtsam::GaussianFactorGraph& gfg,
                                                                            const gtsam::Ordering& ordering);
+
+/// GaussianFactorGraph::eliminateMultifrontal(ordering, EliminatePreferCholesky)
+/// (gtsam/inference/EliminateableFactorGraph-inst.h:123-146) on the device: the junction tree is eliminated there and the
+/// result comes back as a real gtsam::GaussianBayesTree (one GaussianConditional [R S d] per clique), so everything the
+/// reference offers on a Bayes tree (optimize(), determinant(), marginalFactor(), ...) works on it.
+gtsam::GaussianBayesTree::shared_ptr eliminateMultifrontalOnDevice(const gtsam::GaussianFactorGraph& gfg, const gtsam::Ordering& ordering);
+
+/// Host-only helper (needs no GPU): the GaussianBayesTree of flat clique tables — frontal / separator keys and parent
+/// index of every clique (children before parents, -1 for roots) and its conditional [R S d] as an f x (f+s+1) matrix with
+/// the columns in frontals-then-separators order.  It is what eliminateMultifrontalOnDevice calls on the device's output.
+gtsam::GaussianBayesTree::shared_ptr bayesTreeFromTables(const std::vector<gtsam::KeyVector>& frontals,
+                                                         const std::vector<gtsam::KeyVector>& separators,
+                                                         const std::vector<int64_t>& parent, const std::vector<gtsam::Matrix>& conditionals,
+                                                         const std::map<gtsam::Key, int>& dims);
 
 struct LinearState;  // packed JacobianFactor groups + C-ABI handles
 

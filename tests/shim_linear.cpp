@@ -6,6 +6,7 @@
  *       gtsam::GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky)   (reference, CPU)
  *       gtsam_b200::optimizeOnDevice(gfg, ordering)                               (GPU through the C-ABI)
  *       + B200LinearSolver reused on a perturbed copy of the graph (same structure => numbers only)
+ *   shim_linear bayestree <problem.lin.bin>    (no GPU needed) gtsam_b200::bayesTreeFromTables round trip on the reference's tree
  *   shim_linear hostpack <problem.lin.bin>     (no GPU needed)
  *       the shim's packing of the GaussianFactorGraph + the library's host symbolic phase vs the cliques of the
  *       reference's eliminateMultifrontal
@@ -46,7 +47,7 @@ static int cmd_graph(const std::string& path) {
   VectorValues ref, dev;
   try { ref = gfg.optimize(ordering, EliminatePreferCholesky); } catch (const IndeterminantLinearSystemException&) { ref_status = 1; }
   try { dev = gtsam_b200::optimizeOnDevice(gfg, ordering); } catch (const IndeterminantLinearSystemException&) { dev_status = 1; }
-  double d0 = -1, d1 = -1;
+  double d0 = -1, d1 = -1, dbt = -1;
   int builds = 0, solves = 0;
   long long launches = 0;
   if (!ref_status && !dev_status) {
@@ -69,9 +70,14 @@ static int cmd_graph(const std::string& path) {
     const VectorValues dev2 = solver.optimize(g2);
     d1 = relDiff(dev2, g2.optimize(ordering, EliminatePreferCholesky));
     builds = solver.structureBuilds(); solves = solver.solves(); launches = solver.launchCount();
+    // the device's elimination result as a real GaussianBayesTree
+    auto bt = gtsam_b200::eliminateMultifrontalOnDevice(gfg, ordering);
+    auto btr = gfg.eliminateMultifrontal(ordering, EliminatePreferCholesky);
+    dbt = std::max(relDiff(bt->optimize(), ref), std::fabs(bt->logDeterminant() - btr->logDeterminant()) / std::max(1.0, std::fabs(btr->logDeterminant())));
+    if (bt->size() != btr->size()) dbt = 1e300;
   }
-  printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, "
-         "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, builds, solves, launches);
+  printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, \"bayes_tree_diff\": %.6g, "
+         "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, dbt, builds, solves, launches);
   return 0;
 }
 
@@ -101,6 +107,43 @@ static int cmd_hostpack(const std::string& path) {
   }
   std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
   printf("{\"cliques\": %zu, \"reference_cliques\": %zu, \"equal\": %d}\n", a.size(), b.size(), (int)(a == b));
+  return 0;
+}
+
+/* host only: gtsam_b200::bayesTreeFromTables on tables extracted from the REFERENCE's own Bayes tree must give a tree with
+ * the same solution, determinant and clique count (round trip of what eliminateMultifrontalOnDevice does with the device's output) */
+static int cmd_bayestree(const std::string& path) {
+  linio::LinProb lp = linio::load(path);
+  GaussianFactorGraph gfg = linio::build_graph(lp);
+  for (int64_t v = 0; v < lp.nvars; v++) {   // keeps the singular fixture eliminable
+    const int d = lp.var_dim[v];
+    gfg.push_back(std::make_shared<JacobianFactor>(Key(v), Matrix::Identity(d, d), Vector::Zero(d)));
+  }
+  Ordering ordering = linio::build_ordering(lp);
+  auto ref = gfg.eliminateMultifrontal(ordering, EliminatePreferCholesky);
+  // flatten: children before parents
+  std::vector<GaussianBayesTree::sharedClique> order;
+  std::vector<GaussianBayesTree::sharedClique> stack(ref->roots().begin(), ref->roots().end());
+  while (!stack.empty()) { auto c = stack.back(); stack.pop_back(); order.push_back(c); for (auto& ch : c->children) stack.push_back(ch); }
+  std::reverse(order.begin(), order.end());
+  std::map<const GaussianBayesTreeClique*, int64_t> index;
+  for (size_t i = 0; i < order.size(); i++) index[order[i].get()] = (int64_t)i;
+  std::vector<KeyVector> F, S;
+  std::vector<int64_t> par;
+  std::vector<Matrix> C;
+  std::map<Key, int> dims;
+  for (int64_t v = 0; v < lp.nvars; v++) dims[Key(v)] = lp.var_dim[v];
+  for (auto& c : order) {
+    auto cond = c->conditional();
+    F.emplace_back(cond->beginFrontals(), cond->endFrontals());
+    S.emplace_back(cond->beginParents(), cond->endParents());
+    C.push_back(cond->augmentedJacobian());
+    par.push_back(c->parent() ? index.at(c->parent().get()) : -1);
+  }
+  auto mine = gtsam_b200::bayesTreeFromTables(F, S, par, C, dims);
+  const double d = relDiff(mine->optimize(), ref->optimize());
+  printf("{\"cliques\": %zu, \"reference_cliques\": %zu, \"optimize_rel_diff\": %.6g, \"log_determinant_diff\": %.6g}\n", mine->size(), ref->size(), d,
+         std::fabs(mine->logDeterminant() - ref->logDeterminant()));
   return 0;
 }
 
@@ -157,6 +200,7 @@ static int cmd_pose2(const std::string& path, int maxit) {
 int main(int argc, char** argv) {
   if (argc >= 3 && std::string(argv[1]) == "graph") return cmd_graph(argv[2]);
   if (argc >= 3 && std::string(argv[1]) == "hostpack") return cmd_hostpack(argv[2]);
+  if (argc >= 3 && std::string(argv[1]) == "bayestree") return cmd_bayestree(argv[2]);
   if (argc >= 3 && std::string(argv[1]) == "pose2") return cmd_pose2(argv[2], argc > 3 ? atoi(argv[3]) : 30);
   fprintf(stderr, "usage: shim_linear graph problem.lin.bin | pose2 file.g2o [maxit]\n");
   return 2;

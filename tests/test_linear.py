@@ -182,3 +182,16 @@ def test_cpp_shim_accepts_the_rank4_factor_families():
     for name, f in r.items():
         assert f["cliques_equal"] == 1 and f["other"] == 0 and f["cliques"] > 0, (name, f)
     assert r["sfm2"]["max_arity"] == 3 and r["smart"]["hessian"] == 24 and r["smart"]["max_arity"] == 6
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(SHIM_LINEAR), reason="shim_linear not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", ["lin_pose2_toy", "lin_random_nary", "lin_mixed_hessian", "lin_family_smart", "lin_bal_tiny"])
+def test_cpp_shim_builds_a_real_bayes_tree_from_flat_tables(case):
+    """gtsam_b200::bayesTreeFromTables (what eliminateMultifrontalOnDevice calls on the device's cliques + conditionals),
+    fed with tables extracted from the reference's own GaussianBayesTree: same clique count, optimize() and
+    log-determinant."""
+    import json
+    import subprocess
+    out = subprocess.check_output([SHIM_LINEAR, "bayestree", __import__("os").path.join(util.GOLDEN, f"{case}.lin.bin")], timeout=120)
+    r = json.loads(out.decode().strip().splitlines()[-1])
+    assert r["cliques"] == r["reference_cliques"] > 0 and r["optimize_rel_diff"] <= 1e-14 and r["log_determinant_diff"] <= 1e-10
