@@ -399,45 +399,6 @@ GaussianFactorGraph::shared_ptr B200DoglegOptimizer::iterate() {
   return GaussianFactorGraph::shared_ptr();
 }
 
-// ---- Marginals ----------------------------------------------------------------------------
-B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution, const Ordering& ordering)
-    : dev_(std::make_shared<DeviceState>()) {
-  dev_->pack(graph, solution, ordering);
-}
-B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution)
-    : B200Marginals(graph, solution, Ordering::Colamd(graph)) {}
-
-Matrix B200Marginals::marginalCovariance(Key variable) const {
-  const auto it = dev_->key2id.find(variable);
-  if (it == dev_->key2id.end()) throw ValuesKeyDoesNotExist("B200Marginals::marginalCovariance", variable);
-  const int64_t v = it->second;
-  const int d = (int)(dev_->dof_off[v + 1] - dev_->dof_off[v]);
-  Matrix S(d, d);   // Eigen default: column-major, as the C-ABI writes it
-  const int rc = b200_marginal_covariance(dev_->prob, v, S.data());
-  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variable);
-  check(rc, "b200_marginal_covariance");
-  return S;
-}
-
-Matrix B200Marginals::marginalInformation(Key variable) const { return marginalCovariance(variable).inverse(); }
-
-Matrix B200Marginals::jointMarginalCovariance(const KeyVector& variables) const {
-  std::vector<int64_t> ids;
-  for (Key k : variables) {
-    const auto it = dev_->key2id.find(k);
-    if (it == dev_->key2id.end()) throw ValuesKeyDoesNotExist("B200Marginals::jointMarginalCovariance", k);
-    ids.push_back(it->second);
-  }
-  std::sort(ids.begin(), ids.end());   // ids are the ranks of the Keys: sorted ids == sorted keys
-  int64_t D = 0;
-  for (int64_t v : ids) D += dev_->dof_off[v + 1] - dev_->dof_off[v];
-  Matrix S(D, D);
-  const int rc = b200_joint_marginal_covariance(dev_->prob, ids.data(), (int64_t)ids.size(), S.data());
-  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variables.front());
-  check(rc, "b200_joint_marginal_covariance");
-  return S;
-}
-
 VectorValues solveOnDevice(const NonlinearFactorGraph& graph, const Values& values, const Ordering& ordering, double lambda) {
   DeviceState dev;
   dev.pack(graph, values, ordering);
@@ -648,6 +609,55 @@ struct LinearState {
     return out;
   }
 };
+
+// ---- Marginals ----------------------------------------------------------------------------
+B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution, const Ordering& ordering)
+    : dev_(std::make_shared<DeviceState>()) {
+  dev_->pack(graph, solution, ordering);
+}
+B200Marginals::B200Marginals(const NonlinearFactorGraph& graph, const Values& solution)
+    : B200Marginals(graph, solution, Ordering::Colamd(graph)) {}
+B200Marginals::B200Marginals(const GaussianFactorGraph& graph, const Ordering& ordering) : lin_(std::make_shared<LinearState>()) {
+  lin_->build(graph, ordering);
+}
+B200Marginals::B200Marginals(const GaussianFactorGraph& graph) : B200Marginals(graph, Ordering::Colamd(graph)) {}
+
+// (problem handle, id of a key, tangent dimension of an id) of whichever description this object holds
+static b200_problem* margProb(const std::shared_ptr<DeviceState>& d, const std::shared_ptr<LinearState>& l) { return d ? d->prob : l->prob; }
+static int64_t margId(const std::shared_ptr<DeviceState>& d, const std::shared_ptr<LinearState>& l, Key k, const char* who) {
+  const std::map<Key, int64_t>& m = d ? d->key2id : l->key2id;
+  const auto it = m.find(k);
+  if (it == m.end()) throw ValuesKeyDoesNotExist(who, k);
+  return it->second;
+}
+static int margDim(const std::shared_ptr<DeviceState>& d, const std::shared_ptr<LinearState>& l, int64_t v) {
+  return d ? (int)(d->dof_off[v + 1] - d->dof_off[v]) : (int)l->var_dim[(size_t)v];
+}
+
+Matrix B200Marginals::marginalCovariance(Key variable) const {
+  const int64_t v = margId(dev_, lin_, variable, "B200Marginals::marginalCovariance");
+  const int d = margDim(dev_, lin_, v);
+  Matrix S(d, d);   // Eigen default: column-major, as the C-ABI writes it
+  const int rc = b200_marginal_covariance(margProb(dev_, lin_), v, S.data());
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variable);
+  check(rc, "b200_marginal_covariance");
+  return S;
+}
+
+Matrix B200Marginals::marginalInformation(Key variable) const { return marginalCovariance(variable).inverse(); }
+
+Matrix B200Marginals::jointMarginalCovariance(const KeyVector& variables) const {
+  std::vector<int64_t> ids;
+  for (Key k : variables) ids.push_back(margId(dev_, lin_, k, "B200Marginals::jointMarginalCovariance"));
+  std::sort(ids.begin(), ids.end());   // ids are the ranks of the Keys: sorted ids == sorted keys
+  int64_t D = 0;
+  for (int64_t v : ids) D += margDim(dev_, lin_, v);
+  Matrix S(D, D);
+  const int rc = b200_joint_marginal_covariance(margProb(dev_, lin_), ids.data(), (int64_t)ids.size(), S.data());
+  if (rc == B200_INDETERMINATE) throw IndeterminantLinearSystemException(variables.front());
+  check(rc, "b200_joint_marginal_covariance");
+  return S;
+}
 
 B200LinearSolver::B200LinearSolver(const Ordering& ordering) : ordering_(ordering), st_(std::make_shared<LinearState>()) {}
 B200LinearSolver::~B200LinearSolver() {}

@@ -39,6 +39,7 @@
 namespace gtsam_b200 {
 
 struct DeviceState;  // packed problem + C-ABI handles
+struct LinearState;  // packed JacobianFactor / HessianFactor groups + C-ABI handles
 
 class B200LevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimizer {
  public:
@@ -123,6 +124,9 @@ class B200Marginals {
   B200Marginals(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& solution, const gtsam::Ordering& ordering);
   /// ordering = Ordering::Colamd(graph), as gtsam::Marginals(graph, solution) computes it (Marginals.cpp:30-36)
   B200Marginals(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& solution);
+  /// the linear constructors of gtsam::Marginals (Marginals.h:60-76): an already linear graph of Jacobian / Hessian factors
+  B200Marginals(const gtsam::GaussianFactorGraph& graph, const gtsam::Ordering& ordering);
+  explicit B200Marginals(const gtsam::GaussianFactorGraph& graph);
   /// Marginals::marginalCovariance, gtsam/nonlinear/Marginals.cpp:118-126
   gtsam::Matrix marginalCovariance(gtsam::Key variable) const;
   /// Marginals::marginalInformation, gtsam/nonlinear/Marginals.cpp:128-154
@@ -132,7 +136,8 @@ class B200Marginals {
   gtsam::Matrix jointMarginalCovariance(const gtsam::KeyVector& variables) const;
 
  private:
-  std::shared_ptr<DeviceState> dev_;
+  std::shared_ptr<DeviceState> dev_;     // nonlinear graph + Values ...
+  std::shared_ptr<LinearState> lin_;     // ... or a GaussianFactorGraph
 };
 
 /// GaussianFactorGraph::optimize(ordering, EliminatePreferCholesky) (gtsam/linear/GaussianFactorGraph.cpp:316-319) on the
@@ -160,8 +165,6 @@ gtsam::GaussianBayesTree::shared_ptr bayesTreeFromTables(const std::vector<gtsam
                                                          const std::vector<gtsam::KeyVector>& separators,
                                                          const std::vector<int64_t>& parent, const std::vector<gtsam::Matrix>& conditionals,
                                                          const std::map<gtsam::Key, int>& dims);
-
-struct LinearState;  // packed JacobianFactor groups + C-ABI handles
 
 /// The same, keeping the device problem: successive graphs with the SAME structure (the next linearization of one
 /// nonlinear graph, the next lambda of LM's damped system) only re-upload numbers (b200_linear_update); the symbolic

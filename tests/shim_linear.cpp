@@ -47,7 +47,7 @@ static int cmd_graph(const std::string& path) {
   VectorValues ref, dev;
   try { ref = gfg.optimize(ordering, EliminatePreferCholesky); } catch (const IndeterminantLinearSystemException&) { ref_status = 1; }
   try { dev = gtsam_b200::optimizeOnDevice(gfg, ordering); } catch (const IndeterminantLinearSystemException&) { dev_status = 1; }
-  double d0 = -1, d1 = -1, dbt = -1;
+  double d0 = -1, d1 = -1, dbt = -1, dmarg = -1;
   int builds = 0, solves = 0;
   long long launches = 0;
   if (!ref_status && !dev_status) {
@@ -75,9 +75,18 @@ static int cmd_graph(const std::string& path) {
     auto btr = gfg.eliminateMultifrontal(ordering, EliminatePreferCholesky);
     dbt = std::max(relDiff(bt->optimize(), ref), std::fabs(bt->logDeterminant() - btr->logDeterminant()) / std::max(1.0, std::fabs(btr->logDeterminant())));
     if (bt->size() != btr->size()) dbt = 1e300;
+    // gtsam_b200::B200Marginals over the linear graph vs the marginals of the reference's Bayes tree
+    gtsam_b200::B200Marginals marg(gfg, ordering);
+    dmarg = 0;
+    int taken = 0;
+    for (Key k : gfg.keys()) {
+      if (lp.var_dim[k] > 9 || taken++ >= 4) continue;
+      const Matrix R = btr->marginalFactor(k, EliminatePreferCholesky)->information().inverse();
+      dmarg = std::max(dmarg, (marg.marginalCovariance(k) - R).cwiseAbs().maxCoeff() / R.cwiseAbs().maxCoeff());
+    }
   }
-  printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, \"bayes_tree_diff\": %.6g, "
-         "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, dbt, builds, solves, launches);
+  printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, \"bayes_tree_diff\": %.6g, \"marginals_diff\": %.6g, "
+         "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, dbt, dmarg, builds, solves, launches);
   return 0;
 }
 
