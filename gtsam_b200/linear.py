@@ -7,7 +7,7 @@ part of the reference's linear API that sits on the hot path:
 * ``HessianFactor(keys, dims, info)``            gtsam/linear/HessianFactor.h:99-110
 * ``GaussianFactorGraph``                        gtsam/linear/GaussianFactorGraph.h:73-404
   ``.add / .push_back / .size / .keys``, ``.optimize(ordering)`` (GaussianFactorGraph.cpp:316-319, the
-  multifrontal Cholesky path), ``.hessianDiagonal()`` (:279-287)
+  multifrontal Cholesky path), ``.eliminateMultifrontal(ordering)``, ``.hessianDiagonal()`` (:279-287)
 * ``VectorValues`` is a plain ``dict`` key -> 1-D array (gtsam/linear/VectorValues.h:77-78).
 
 Factors of any arity and any block widths.  The numbers live in ``LinearProblem`` (flat groups of
@@ -359,6 +359,29 @@ class GaussianFactorGraph:
             h, off = dev.hessian_diagonal(), lp.dof_offsets()
             dev.close()
             return {k: h[off[i]:off[i + 1]].copy() for k, i in ids.items()}
+        finally:
+            if own:
+                ctx.close()
+
+    def eliminateMultifrontal(self, ordering=None, ctx=None):
+        """GaussianFactorGraph::eliminateMultifrontal(ordering, EliminatePreferCholesky) on the device: the Bayes tree as a
+        list of cliques in elimination order, each ``(frontal keys, separator keys, parent index or -1, [R S d])`` with
+        ``[R S d]`` an f x (f+s+1) array (columns: frontals, separators in ascending key order, rhs)."""
+        from . import capi
+        own = ctx is None
+        ctx = ctx or capi.Context(0)
+        try:
+            lp, ids = self.to_problem(ordering)
+            key_of = {i: k for k, i in ids.items()}
+            dev = capi.LinearDeviceProblem(ctx, lp)
+            st, _, _, fv = dev.solve(0.0)
+            if st == P.INDETERMINATE:
+                raise capi.IndeterminantLinearSystemException(key_of.get(int(fv), -1))
+            fp, fvars, sp, svars, par = dev.cliques()
+            out = [([key_of[int(v)] for v in fvars[fp[c]:fp[c + 1]]], [key_of[int(v)] for v in svars[sp[c]:sp[c + 1]]], int(par[c]),
+                    dev.conditional(c)) for c in range(len(par))]
+            dev.close()
+            return out
         finally:
             if own:
                 ctx.close()
