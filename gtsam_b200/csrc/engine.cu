@@ -1503,13 +1503,12 @@ int b200_symbolic_info_get(const b200_problem* p, b200_symbolic_info* info) {
   info->factor_flops = S.flops; info->front_bytes = p->arena_doubles * 8;
   return B200_OK;
 }
+static void copy_i64(int64_t* dst, const std::vector<int64_t>& v) {   // an empty vector's data() may be null
+  if (!v.empty()) memcpy(dst, v.data(), v.size() * sizeof(int64_t));
+}
 int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
   const Symbolic& S = p->sym;
-  memcpy(fp, S.front_ptr.data(), S.front_ptr.size() * sizeof(int64_t));
-  memcpy(fv, S.front_vars.data(), S.front_vars.size() * sizeof(int64_t));
-  memcpy(sp, S.sep_ptr.data(), S.sep_ptr.size() * sizeof(int64_t));
-  memcpy(sv, S.sep_vars.data(), S.sep_vars.size() * sizeof(int64_t));
-  memcpy(parent, S.parent.data(), S.parent.size() * sizeof(int64_t));
+  copy_i64(fp, S.front_ptr); copy_i64(fv, S.front_vars); copy_i64(sp, S.sep_ptr); copy_i64(sv, S.sep_vars); copy_i64(parent, S.parent);
   return B200_OK;
 }
 /* conditional [R S d] of clique c after a solve: nf x (nf+ns+1) column-major */
@@ -1554,11 +1553,7 @@ static void fill_info(const Symbolic& S, int64_t ndelta, b200_symbolic_info* inf
   info->factor_flops = S.flops; info->front_bytes = S.arena_doubles * 8;
 }
 static void fill_cliques(const Symbolic& S, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
-  memcpy(fp, S.front_ptr.data(), S.front_ptr.size() * sizeof(int64_t));
-  memcpy(fv, S.front_vars.data(), S.front_vars.size() * sizeof(int64_t));
-  memcpy(sp, S.sep_ptr.data(), S.sep_ptr.size() * sizeof(int64_t));
-  memcpy(sv, S.sep_vars.data(), S.sep_vars.size() * sizeof(int64_t));
-  memcpy(parent, S.parent.data(), S.parent.size() * sizeof(int64_t));
+  copy_i64(fp, S.front_ptr); copy_i64(fv, S.front_vars); copy_i64(sp, S.sep_ptr); copy_i64(sv, S.sep_vars); copy_i64(parent, S.parent);
 }
 int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info) { fill_info(s->sym, s->ndelta, info); return B200_OK; }
 int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
