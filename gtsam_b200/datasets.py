@@ -251,6 +251,33 @@ def bal(ncams: int = 100, npoints: int = 50000, obs_per_point: int = 6, visibili
     return pr
 
 
+# ---- config 1 family: planar pose graphs ----------------------------------------------------------
+def pose2_ring(n: int = 40, seed: int = 21, ordering: str = "natural") -> P.Problem:
+    """A Pose2 pose graph of the kind Pose2SLAMExample_g2o reads (BASELINE configs[0]): n poses on a ring expressed in
+    the frame of pose 0, BetweenFactor<Pose2> odometry + two families of loop closures with the information
+    diag(400, 400, 10000), and the example's prior on pose 0 (examples/Pose2SLAMExample_g2o.cpp:62-64)."""
+    rng = np.random.default_rng(seed)
+    th = 2 * np.pi * np.arange(n) / n
+    ring = np.stack([10 * np.cos(th), 10 * np.sin(th), th + np.pi / 2], -1)
+
+    def between(a, b):
+        c, s = np.cos(a[2]), np.sin(a[2])
+        d = b[:2] - a[:2]
+        return np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1], (b[2] - a[2] + np.pi) % (2 * np.pi) - np.pi])
+
+    gt = np.array([between(ring[0], q) for q in ring])
+    init = gt + rng.normal(size=gt.shape) * np.array([0.3, 0.3, 0.05])
+    init[0] = 0
+    edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 7) % n) for i in range(0, n, 3)] + [(i, (i + 19) % n) for i in range(1, n, 5)]
+    z = np.array([between(gt[i], gt[j]) + rng.normal(size=3) * np.array([0.05, 0.05, 0.01]) for i, j in edges])
+    btw = P.FactorGroup(P.FACTOR_BETWEEN_POSE2, np.array(edges), z, P.NOISE_DIAGONAL, 1.0 / np.sqrt(np.array([400.0, 400.0, 10000.0])))
+    pri = P.FactorGroup(P.FACTOR_PRIOR_POSE2, np.array([[0]]), np.zeros((1, 3)), P.NOISE_DIAGONAL, np.sqrt(np.array([1e-6, 1e-6, 1e-8])))
+    order = np.arange(n) if ordering == "natural" else np.arange(n)[::-1].copy()
+    pr = P.Problem(np.full(n, P.VAR_POSE2), init.ravel(), order, [btw, pri], name=f"pose2_ring{n}")
+    pr.meta = dict(kind="pose2", n=n, seed=seed, ordering=ordering)
+    return pr
+
+
 WORKLOADS = {
     # name: (builder, kwargs) — BASELINE.json configs
     "sphere2500": (sphere, dict(layers=50, per_ring=50, ordering="colamd")),   # configs[1]: 2.5k Pose3 / 9.8k Between, COLAMD
@@ -268,6 +295,7 @@ WORKLOADS = {
     "bal_c5_metis": (bal, dict(ncams=5000, npoints=2000000, obs_per_point=5, ordering="metis")),
     "bal_tiny": (bal, dict(ncams=10, npoints=60, visibility="banded")),
     "sphere_tiny": (sphere, dict(layers=5, per_ring=8)),
+    "pose2_ring": (pose2_ring, dict(n=40)),                          # configs[0]'s factor family (planar pose graph)
 }
 
 

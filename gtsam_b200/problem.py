@@ -18,16 +18,16 @@ from typing import List, Optional
 import numpy as np
 
 # ---- enums (include/gtsam_b200.h) -------------------------------------------
-VAR_POSE3, VAR_POINT3, VAR_CAM_BUNDLER = 0, 1, 2
-VAR_STORAGE = (12, 3, 17)
-VAR_DIM = (6, 3, 9)
+VAR_POSE3, VAR_POINT3, VAR_CAM_BUNDLER, VAR_POSE2 = 0, 1, 2, 3
+VAR_STORAGE = (12, 3, 17, 3)
+VAR_DIM = (6, 3, 9, 3)
 
 (FACTOR_BETWEEN_POSE3, FACTOR_PRIOR_POSE3, FACTOR_PRIOR_POINT3, FACTOR_PROJECTION_CAL3S2,
- FACTOR_SFM_BUNDLER, FACTOR_PRIOR_CAM_BUNDLER) = range(6)
-FACTOR_ARITY = (2, 1, 1, 2, 2, 1)
-FACTOR_MEAS = (12, 12, 3, 2, 2, 17)
-FACTOR_DIM = (6, 6, 3, 2, 2, 9)
-FACTOR_VAR_TYPES = ((0, 0), (0,), (1,), (0, 1), (2, 1), (2,))
+ FACTOR_SFM_BUNDLER, FACTOR_PRIOR_CAM_BUNDLER, FACTOR_BETWEEN_POSE2, FACTOR_PRIOR_POSE2) = range(8)
+FACTOR_ARITY = (2, 1, 1, 2, 2, 1, 2, 1)
+FACTOR_MEAS = (12, 12, 3, 2, 2, 17, 3, 3)
+FACTOR_DIM = (6, 6, 3, 2, 2, 9, 3, 3)
+FACTOR_VAR_TYPES = ((0, 0), (0,), (1,), (0, 1), (2, 1), (2,), (3, 3), (3,))
 
 NOISE_UNIT, NOISE_ISOTROPIC, NOISE_DIAGONAL, NOISE_GAUSSIAN = range(4)
 ROBUST_NONE, ROBUST_HUBER, ROBUST_CAUCHY, ROBUST_TUKEY, ROBUST_FAIR = range(5)

@@ -48,9 +48,13 @@ enum {
 enum {
   B200_VAR_POSE3 = 0,       /* gtsam::Pose3; storage 12 (R row-major, t); dim 6 */
   B200_VAR_POINT3 = 1,      /* gtsam::Point3; storage 3; dim 3                  */
-  B200_VAR_CAM_BUNDLER = 2  /* PinholeCamera<Cal3Bundler>; storage 17 =
+  B200_VAR_CAM_BUNDLER = 2, /* PinholeCamera<Cal3Bundler>; storage 17 =
                                R(9) t(3) f k1 k2 u0 v0; dim 9 = pose(6)+f,k1,k2
                                (gtsam/geometry/PinholeCamera.h:199-205)         */
+  B200_VAR_POSE2 = 3,       /* gtsam::Pose2; storage 3 = x y theta; dim 3, tangent order (x, y, theta);
+                               retract / localCoordinates are the first-order chart the reference uses
+                               unless GTSAM_SLOW_BUT_CORRECT_EXPMAP (gtsam/geometry/Pose2.cpp:99-122)  */
+  B200_NUM_VAR_TYPES = 4
 };
 
 /* ---- factor types --------------------------------------------------------- */
@@ -71,11 +75,17 @@ enum {
   B200_FACTOR_SFM_BUNDLER = 4,
   /* PriorFactor<PinholeCamera<Cal3Bundler>>. key; meas 17; dim 9 */
   B200_FACTOR_PRIOR_CAM_BUNDLER = 5,
-  B200_NUM_FACTOR_TYPES = 6,
-  /* internal tag of the groups of a linear problem (b200_linear_create); never valid in a
+  /* BetweenFactor<Pose2> (the EDGE_SE2 lines of a g2o file, BASELINE configs[0]'s factor family),
+     gtsam/slam/BetweenFactor.h:111-124 with gtsam/base/Lie.h:63-69 (between) and the Pose2 chart.
+     keys (p1,p2); meas = measured Pose2 (x y theta); residual dim 3 */
+  B200_FACTOR_BETWEEN_POSE2 = 6,
+  /* PriorFactor<Pose2>. key; meas 3; dim 3 */
+  B200_FACTOR_PRIOR_POSE2 = 7,
+  B200_NUM_FACTOR_TYPES = 8,
+  /* internal tags of the groups of a linear problem (b200_linear_create); never valid in a
      b200_factor_group */
-  B200_FACTOR_JACOBIAN = 6,
-  B200_FACTOR_HESSIAN = 7
+  B200_FACTOR_JACOBIAN = 100,
+  B200_FACTOR_HESSIAN = 101
 };
 
 /* ---- noise models (gtsam/linear/NoiseModel.cpp:83-130,163-238,322-340,646-675) */

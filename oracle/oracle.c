@@ -25,15 +25,16 @@
 /* ------------------------------------------------------------------------ */
 /* static layout tables (mirror include/gtsam_b200.h)                        */
 /* ------------------------------------------------------------------------ */
-static const int VAR_STORAGE[3] = {12, 3, 17};
-static const int VAR_DIM[3] = {6, 3, 9};
-static const int F_ARITY[B200_NUM_FACTOR_TYPES] = {2, 1, 1, 2, 2, 1};
-static const int F_MEAS[B200_NUM_FACTOR_TYPES] = {12, 12, 3, 2, 2, 17};
-static const int F_DIM[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
+static const int VAR_STORAGE[B200_NUM_VAR_TYPES] = {12, 3, 17, 3};
+static const int VAR_DIM[B200_NUM_VAR_TYPES] = {6, 3, 9, 3};
+static const int F_ARITY[B200_NUM_FACTOR_TYPES] = {2, 1, 1, 2, 2, 1, 2, 1};
+static const int F_MEAS[B200_NUM_FACTOR_TYPES] = {12, 12, 3, 2, 2, 17, 3, 3};
+static const int F_DIM[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9, 3, 3};
 static const int F_VT[B200_NUM_FACTOR_TYPES][2] = {
     {B200_VAR_POSE3, B200_VAR_POSE3},       {B200_VAR_POSE3, -1},
     {B200_VAR_POINT3, -1},                  {B200_VAR_POSE3, B200_VAR_POINT3},
-    {B200_VAR_CAM_BUNDLER, B200_VAR_POINT3}, {B200_VAR_CAM_BUNDLER, -1}};
+    {B200_VAR_CAM_BUNDLER, B200_VAR_POINT3}, {B200_VAR_CAM_BUNDLER, -1},
+    {B200_VAR_POSE2, B200_VAR_POSE2},       {B200_VAR_POSE2, -1}};
 
 /* ------------------------------------------------------------------------ */
 /* small dense helpers (3x3 row-major)                                       */
@@ -614,7 +615,7 @@ int orc_problem_create(const b200_problem_desc* desc, orc_problem** out) {
   p->val_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
   p->dof_off = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
   for (int64_t v = 0; v < n; v++) {
-    if (p->var_type[v] < 0 || p->var_type[v] > 2) return B200_INVALID_ARGUMENT;
+    if (p->var_type[v] < 0 || p->var_type[v] >= B200_NUM_VAR_TYPES) return B200_INVALID_ARGUMENT;
     p->val_off[v + 1] = p->val_off[v] + VAR_STORAGE[p->var_type[v]];
     p->var_dim[v] = VAR_DIM[p->var_type[v]];
     p->dof_off[v + 1] = p->dof_off[v] + p->var_dim[v];
@@ -848,6 +849,26 @@ int64_t orc_delta_size(const orc_problem* p) { return p->dof_off[p->nvars]; }
 /* ------------------------------------------------------------------------ */
 /* per-factor unwhitened residual r and Jacobians (row-major d x n_i)        */
 /* ------------------------------------------------------------------------ */
+/* ---- Pose2 = (x, y, theta), tangent (x, y, theta) ---------------------------------------------
+ * between(a, b) = a^-1 b: Pose2::inverse (gtsam/geometry/Pose2.cpp:201-203) then operator*
+ * (Pose2.h:131-133; Rot2::operator* goes through fromCosSin -> normalize, Rot2.cpp:27-30,56-64);
+ * theta() = atan2(s, c) (Rot2.h:186-188). */
+static void rot2_normalize(double* c, double* s) {
+  double scale = (*c) * (*c) + (*s) * (*s);
+  if (fabs(scale - 1.0) > 1e-10) { scale = 1 / sqrt(scale); *c *= scale; *s *= scale; }
+}
+/* out = (x, y, c, s) of a^-1 b */
+static void pose2_between(const double a[3], const double b[3], double out[4]) {
+  const double ca = cos(a[2]), sa = sin(a[2]), cb = cos(b[2]), sb = sin(b[2]);
+  /* a^-1 = (R_a^T, unrotate(-t_a)) */
+  const double ix = ca * (-a[0]) + sa * (-a[1]), iy = -sa * (-a[0]) + ca * (-a[1]);
+  double c = ca * cb - (-sa) * sb, s = (-sa) * cb + ca * sb;
+  rot2_normalize(&c, &s);
+  out[0] = ix + (ca * b[0] + sa * b[1]);   /* t = t_inv + R_a^T t_b */
+  out[1] = iy + (-sa * b[0] + ca * b[1]);
+  out[2] = c; out[3] = s;
+}
+
 /* Returns r (d) and, if H1, the Jacobians.  `active` semantics: all factors
  * active.  Follows NoiseModelFactorN::unwhitenedError -> evaluateError. */
 static void eval_factor(const orc_problem* p, const ogroup* g, int64_t i, const double* values,
@@ -880,6 +901,37 @@ static void eval_factor(const orc_problem* p, const ogroup* g, int64_t i, const 
       if (H1) {
         memset(H1, 0, 36 * sizeof(double));
         for (int k = 0; k < 6; k++) H1[7 * k] = 1.0;
+      }
+      break;
+    }
+    case B200_FACTOR_BETWEEN_POSE2: {
+      /* gtsam/slam/BetweenFactor.h:111-124 (fast variant): hx = between(p1, p2) with H1 = -AdjointMap(hx^-1), H2 = I
+         (gtsam/base/Lie.h:63-69, Pose2::AdjointMap gtsam/geometry/Pose2.cpp:127-135); r = Local(measured, hx) =
+         (x, y, theta) of measured^-1 hx (Pose2::ChartAtOrigin::Local, Pose2.cpp:111-122) */
+      double hx[4], d[4];
+      pose2_between(x1, x2, hx);
+      const double hxp[3] = {hx[0], hx[1], atan2(hx[3], hx[2])};
+      pose2_between(z, hxp, d);
+      r[0] = d[0]; r[1] = d[1]; r[2] = atan2(d[3], d[2]);
+      if (H1) {
+        /* hx^-1 = (R^T, unrotate(-t)): c' = c, s' = -s, (x', y') = R^T (-t) */
+        const double c = hx[2], s = hx[3];
+        const double xi = c * (-hx[0]) + s * (-hx[1]), yi = -s * (-hx[0]) + c * (-hx[1]);
+        const double Ad[9] = {c, s, yi, -s, c, -xi, 0, 0, 1};   /* AdjointMap of (c, -s, xi, yi): [[c', -s', y'],[s', c', -x'],[0,0,1]] */
+        for (int k = 0; k < 9; k++) H1[k] = -Ad[k];
+        memset(H2, 0, 9 * sizeof(double));
+        for (int k = 0; k < 3; k++) H2[4 * k] = 1.0;
+      }
+      break;
+    }
+    case B200_FACTOR_PRIOR_POSE2: {
+      /* gtsam/nonlinear/PriorFactor.h:98-102: -Local(x, prior), H = I */
+      double d[4];
+      pose2_between(x1, z, d);
+      r[0] = -d[0]; r[1] = -d[1]; r[2] = -atan2(d[3], d[2]);
+      if (H1) {
+        memset(H1, 0, 9 * sizeof(double));
+        for (int k = 0; k < 3; k++) H1[4 * k] = 1.0;
       }
       break;
     }
@@ -1429,6 +1481,16 @@ static void retract_all(const orc_problem* p, const double* values, const double
     switch (p->var_type[v]) {
       case B200_VAR_POSE3: pose3_retract(x, d, y); break;
       case B200_VAR_POINT3: for (int k = 0; k < 3; k++) y[k] = x[k] + d[k]; break;
+      case B200_VAR_POSE2: {
+        /* x * ChartAtOrigin::Retract(d) = x * Pose2(d0, d1, d2) (gtsam/geometry/Pose2.cpp:99-109, Pose2.h:131-133) */
+        const double c = cos(x[2]), s = sin(x[2]), cd = cos(d[2]), sd = sin(d[2]);
+        double cn = c * cd - s * sd, sn = s * cd + c * sd;
+        rot2_normalize(&cn, &sn);
+        y[0] = x[0] + (c * d[0] - s * d[1]);
+        y[1] = x[1] + (s * d[0] + c * d[1]);
+        y[2] = atan2(sn, cn);
+        break;
+      }
       case B200_VAR_CAM_BUNDLER:
         /* PinholeCamera::retract, gtsam/geometry/PinholeCamera.h:199-205;
            Cal3Bundler::retract: (f,k1,k2) + d, u0 v0 kept */

@@ -9,6 +9,7 @@
 #include <gtsam/geometry/Cal3_S2.h>
 #include <gtsam/geometry/PinholeCamera.h>
 #include <gtsam/geometry/Point3.h>
+#include <gtsam/geometry/Pose2.h>
 #include <gtsam/geometry/Pose3.h>
 #include <gtsam/inference/Ordering.h>
 #include <gtsam/linear/GaussianBayesTree.h>
@@ -39,10 +40,10 @@
 using namespace gtsam;
 typedef PinholeCamera<Cal3Bundler> BCam;
 
-static const int VAR_STORAGE[3] = {12, 3, 17};
-static const int F_ARITY[6] = {2, 1, 1, 2, 2, 1};
-static const int F_MEAS[6] = {12, 12, 3, 2, 2, 17};
-static const int F_DIM[6] = {6, 6, 3, 2, 2, 9};
+static const int VAR_STORAGE[4] = {12, 3, 17, 3};
+static const int F_ARITY[8] = {2, 1, 1, 2, 2, 1, 2, 1};
+static const int F_MEAS[8] = {12, 12, 3, 2, 2, 17, 3, 3};
+static const int F_DIM[8] = {6, 6, 3, 2, 2, 9, 3, 3};
 
 struct Group {
   int32_t type, noise_kind, per_factor, has_cal;
@@ -166,6 +167,7 @@ static Built build(const Prob& p) {
       case 0: b.values.insert(Key(v), mkpose(x)); break;
       case 1: b.values.insert(Key(v), Point3(x[0], x[1], x[2])); break;
       case 2: b.values.insert(Key(v), mkcam(x)); break;
+      case 3: b.values.insert(Key(v), Pose2(x[0], x[1], x[2])); break;
     }
   }
   for (int64_t j = 0; j < p.nvars; j++) b.ordering.push_back(Key(p.ordering[j]));
@@ -198,6 +200,8 @@ static Built build(const Prob& p) {
           break;
         case 4: f = std::make_shared<GeneralSFMFactor<BCam, Point3>>(Point2(z[0], z[1]), nm, k[0], k[1]); break;
         case 5: f = std::make_shared<PriorFactor<BCam>>(k[0], mkcam(z), nm); break;
+        case 6: f = std::make_shared<BetweenFactor<Pose2>>(k[0], k[1], Pose2(z[0], z[1], z[2]), nm); break;
+        case 7: f = std::make_shared<PriorFactor<Pose2>>(k[0], Pose2(z[0], z[1], z[2]), nm); break;
       }
       fs[(g.has_cal & 4) ? g.gidx[i] : g.gi0 + i] = f;
     }

@@ -50,6 +50,7 @@ static std::vector<double> pack_values(const Prob& p, const Built& b, const Valu
         x[15] = c.calibration().px(); x[16] = c.calibration().py();
         break;
       }
+      case 3: { const Pose2& q = v.at<Pose2>(i); x[0] = q.x(); x[1] = q.y(); x[2] = q.theta(); break; }
     }
   }
   return out;

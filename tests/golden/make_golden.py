@@ -77,6 +77,9 @@ def main():
     # BAL eliminated in the reference's METIS nested-dissection order (BASELINE configs[3] names METIS): camera and point
     # cliques interleave, every point is still a leaf
     emit("bal_small_metis", with_ordering(datasets.bal(ncams=12, npoints=300, seed=21), "metis"))
+    # BASELINE configs[0]'s factor family: planar pose graphs (BetweenFactor<Pose2> + PriorFactor<Pose2>)
+    emit("pose2_ring", datasets.pose2_ring(n=40), gn_iters=4, dl_iters=6, marg=True)
+    emit("pose2_ring_colamd", with_ordering(datasets.pose2_ring(n=60, seed=5), "colamd"), gn_iters=4)
     # ---- input formats: synthetic text files written by gtsam_b200.io, parsed by the
     # REFERENCE's loaders (readG2o / SfmData::FromBalFile) into *.prob.bin; tests compare our readers with them
     import numpy as np

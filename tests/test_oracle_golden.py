@@ -52,7 +52,7 @@ def test_oracle_reference_end_to_end_golden():
     assert abs(lm.state.error - 0.0199833) < 1e-5
 
 
-@pytest.mark.parametrize("case", ["sphere_tiny", "sphere_small_colamd"])
+@pytest.mark.parametrize("case", ["sphere_tiny", "sphere_small_colamd", "pose2_ring", "pose2_ring_colamd"])
 def test_oracle_gn_trace(case):
     prob = util.load_case(case)
     ref = util.golden(case, "gn")
@@ -65,7 +65,7 @@ def test_oracle_gn_trace(case):
     assert np.allclose(errs, ref["gn_errors"], rtol=1e-8)
 
 
-DL_CASES = ["bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian",
+DL_CASES = ["pose2_ring", "bal_tiny_s2", "sphere_tiny", "sphere_small_colamd", "sphere_tiny_gaussian",
             "sphere_tiny_huber", "bal_tiny_bundler", "bal_tiny_body_sensor", "bal_tiny_colamd"]
 
 
@@ -87,7 +87,7 @@ def test_oracle_dogleg_trace(case):
     assert util.relmax(op.get_values(), ref["final_values"]) <= 1e-6
 
 
-@pytest.mark.parametrize("case", ["bal_tiny_s2", "sphere_tiny", "sphere_tiny_gaussian", "bal_tiny_bundler"])
+@pytest.mark.parametrize("case", ["bal_tiny_s2", "sphere_tiny", "sphere_tiny_gaussian", "bal_tiny_bundler", "pose2_ring"])
 def test_oracle_marginal_covariances(case):
     """Marginals::marginalCovariance of every variable (gtsam/nonlinear/Marginals.cpp:118-154) against the
     unmodified reference (ref_harness marginals): groundwork for the device path of SURVEY 8f rank 3."""

@@ -11,7 +11,7 @@ CASES = ["bal_tiny_s2", "bal_tiny_body_sensor", "bal_tiny_tukey", "bal_tiny_fair
          "sphere_small_metis", "dubrovnik_3_7_unit", "dubrovnik_3_7_priors", "pose3example"]
 # cases added after the last hardware run of the -m gpu suite: pinned on the oracle in tests/test_oracle_golden.py, on the
 # device in tests/test_gpu_orderings.py (own process) until they have run on a B200 once
-EXTRA_CASES = ["bal_small_metis"]
+EXTRA_CASES = ["bal_small_metis", "pose2_ring", "pose2_ring_colamd"]
 CERES_CASES = {"bal_tiny_bundler"}   # LM trace generated with LevenbergMarquardtParams::CeresDefaults
 
 
