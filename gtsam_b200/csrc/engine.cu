@@ -16,12 +16,12 @@ namespace b200 {
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 
-static const int VAR_STORAGE[3] = {12, 3, 17};
-static const int VAR_DIM[3] = {6, 3, 9};
-static const int F_ARITY[B200_NUM_FACTOR_TYPES] = {2, 1, 1, 2, 2, 1};
-static const int F_MEAS[B200_NUM_FACTOR_TYPES] = {12, 12, 3, 2, 2, 17};
-static const int F_DIM[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
-static const int F_VT[B200_NUM_FACTOR_TYPES][2] = {{0, 0}, {0, -1}, {1, -1}, {0, 1}, {2, 1}, {2, -1}};
+static const int VAR_STORAGE[B200_NUM_VAR_TYPES] = {12, 3, 17, 3};
+static const int VAR_DIM[B200_NUM_VAR_TYPES] = {6, 3, 9, 3};
+static const int F_ARITY[B200_NUM_FACTOR_TYPES] = {2, 1, 1, 2, 2, 1, 2, 1};
+static const int F_MEAS[B200_NUM_FACTOR_TYPES] = {12, 12, 3, 2, 2, 17, 3, 3};
+static const int F_DIM[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9, 3, 3};
+static const int F_VT[B200_NUM_FACTOR_TYPES][2] = {{0, 0}, {0, -1}, {1, -1}, {0, 1}, {2, 1}, {2, -1}, {3, 3}, {3, -1}};
 
 static int noise_payload(int kind, int d) {
   switch (kind) {
@@ -76,6 +76,8 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
     case B200_FACTOR_PROJECTION_CAL3S2: { constexpr int TY = B200_FACTOR_PROJECTION_CAL3S2; STMT; break; } \
     case B200_FACTOR_SFM_BUNDLER: { constexpr int TY = B200_FACTOR_SFM_BUNDLER; STMT; break; }             \
     case B200_FACTOR_PRIOR_CAM_BUNDLER: { constexpr int TY = B200_FACTOR_PRIOR_CAM_BUNDLER; STMT; break; } \
+    case B200_FACTOR_BETWEEN_POSE2: { constexpr int TY = B200_FACTOR_BETWEEN_POSE2; STMT; break; }         \
+    case B200_FACTOR_PRIOR_POSE2: { constexpr int TY = B200_FACTOR_PRIOR_POSE2; STMT; break; }             \
   }
 
 // storage type of the whitened Jacobians (b200_set_jacobian_precision): JT = float or double inside the statement
@@ -464,7 +466,7 @@ static int pack_and_symbolic(const b200_problem_desc* d, Packed* pk) {
   pk->val_off.assign(n + 1, 0); pk->var_dof.assign(n + 1, 0); pk->var_dim.assign(n, 0);
   for (int64_t v = 0; v < n; v++) {
     const int t = d->var_type[v];
-    if (t < 0 || t > 2) FAIL(B200_INVALID_ARGUMENT, "unknown variable type");
+    if (t < 0 || t >= B200_NUM_VAR_TYPES) FAIL(B200_INVALID_ARGUMENT, "unknown variable type");
     pk->var_dim[v] = VAR_DIM[t];
     pk->val_off[v + 1] = pk->val_off[v] + VAR_STORAGE[t];
     pk->var_dof[v + 1] = pk->var_dof[v] + VAR_DIM[t];
@@ -802,8 +804,8 @@ using namespace b200;
 // ---------------------------------------------------------------------------
 extern "C" {
 
-int b200_var_storage(int32_t t) { return (t >= 0 && t < 3) ? VAR_STORAGE[t] : -1; }
-int b200_var_dim(int32_t t) { return (t >= 0 && t < 3) ? VAR_DIM[t] : -1; }
+int b200_var_storage(int32_t t) { return (t >= 0 && t < B200_NUM_VAR_TYPES) ? VAR_STORAGE[t] : -1; }
+int b200_var_dim(int32_t t) { return (t >= 0 && t < B200_NUM_VAR_TYPES) ? VAR_DIM[t] : -1; }
 int b200_factor_arity(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_ARITY[t] : -1; }
 int b200_factor_meas_size(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_MEAS[t] : -1; }
 int b200_factor_dim(int32_t t) { return (t >= 0 && t < B200_NUM_FACTOR_TYPES) ? F_DIM[t] : -1; }

@@ -19,6 +19,8 @@ template <> struct FactorTraits<B200_FACTOR_PRIOR_POINT3> { enum { D = 3, N1 = 3
 template <> struct FactorTraits<B200_FACTOR_PROJECTION_CAL3S2> { enum { D = 2, N1 = 6, N2 = 3, ARITY = 2, MEAS = 2 }; };
 template <> struct FactorTraits<B200_FACTOR_SFM_BUNDLER> { enum { D = 2, N1 = 9, N2 = 3, ARITY = 2, MEAS = 2 }; };
 template <> struct FactorTraits<B200_FACTOR_PRIOR_CAM_BUNDLER> { enum { D = 9, N1 = 9, N2 = 0, ARITY = 1, MEAS = 17 }; };
+template <> struct FactorTraits<B200_FACTOR_BETWEEN_POSE2> { enum { D = 3, N1 = 3, N2 = 3, ARITY = 2, MEAS = 3 }; };
+template <> struct FactorTraits<B200_FACTOR_PRIOR_POSE2> { enum { D = 3, N1 = 3, N2 = 0, ARITY = 1, MEAS = 3 }; };
 
 // Everything a factor evaluator may read.
 struct EvalCtx {
@@ -80,6 +82,70 @@ template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POSE3, WITH_J> {
       for (int i = 0; i < 6; i++)
 #pragma unroll
         for (int j = 0; j < 6; j++) M[i * NC + j] = (i == j) ? 1.0 : 0.0;
+    }
+  }
+};
+
+// ---- Pose2 = (x, y, theta), tangent (x, y, theta): BASELINE configs[0]'s factor family ---------------------------
+// between(a, b) = a^-1 b as Pose2::inverse (gtsam/geometry/Pose2.cpp:201-203) followed by operator* (Pose2.h:131-133;
+// Rot2::operator* normalizes through fromCosSin, Rot2.cpp:27-30,56-64); theta() = atan2(s, c) (Rot2.h:186-188).
+struct P2 { double x, y, c, s; };
+__device__ __forceinline__ P2 load_pose2(const double* __restrict__ v) {
+  P2 p;
+  p.x = v[0]; p.y = v[1];
+  sincos(v[2], &p.s, &p.c);
+  return p;
+}
+__device__ __forceinline__ void rot2_normalize(double& c, double& s) {
+  double scale = c * c + s * s;
+  if (fabs(scale - 1.0) > 1e-10) { scale = 1.0 / sqrt(scale); c *= scale; s *= scale; }
+}
+__device__ __forceinline__ P2 between2(const P2& a, const P2& b) {
+  P2 g;
+  const double ix = a.c * (-a.x) + a.s * (-a.y), iy = -a.s * (-a.x) + a.c * (-a.y);   // unrotate(-t_a)
+  g.c = a.c * b.c + a.s * b.s;
+  g.s = -a.s * b.c + a.c * b.s;
+  rot2_normalize(g.c, g.s);
+  g.x = ix + (a.c * b.x + a.s * b.y);
+  g.y = iy + (-a.s * b.x + a.c * b.y);
+  return g;
+}
+
+// BetweenFactor<Pose2>::evaluateError — gtsam/slam/BetweenFactor.h:111-124 (fast variant):
+//   hx = between(p1, p2), H1 = -AdjointMap(hx^-1), H2 = I (gtsam/base/Lie.h:63-69, Pose2::AdjointMap Pose2.cpp:127-135);
+//   r = Local(measured, hx) = (x, y, theta) of measured^-1 hx (Pose2::ChartAtOrigin::Local, Pose2.cpp:111-122)
+template <bool WITH_J> struct Eval<B200_FACTOR_BETWEEN_POSE2, WITH_J> {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int k1, const double* __restrict__ z, int,
+                                             const double*, double* M) {
+    enum { NC = 7 };
+    const P2 hx = between2(load_pose2(c.values + c.val_off[k0]), load_pose2(c.values + c.val_off[k1]));
+    const P2 d = between2(load_pose2(z), hx);
+    M[0 * NC + 6] = -d.x; M[1 * NC + 6] = -d.y; M[2 * NC + 6] = -atan2(d.s, d.c);   // b = -r
+    if (WITH_J) {
+      // hx^-1 = (c, -s, unrotate(-t)); AdjointMap(p) = [[c, -s, y], [s, c, -x], [0, 0, 1]]
+      const double xi = hx.c * (-hx.x) + hx.s * (-hx.y), yi = -hx.s * (-hx.x) + hx.c * (-hx.y);
+      M[0 * NC + 0] = -hx.c; M[0 * NC + 1] = -hx.s; M[0 * NC + 2] = -yi;
+      M[1 * NC + 0] = hx.s;  M[1 * NC + 1] = -hx.c; M[1 * NC + 2] = xi;
+      M[2 * NC + 0] = -0.0;  M[2 * NC + 1] = -0.0;  M[2 * NC + 2] = -1.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[i * NC + 3 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  }
+};
+
+// PriorFactor<Pose2>::evaluateError — gtsam/nonlinear/PriorFactor.h:98-102: r = -Local(x, prior), H = I
+template <bool WITH_J> struct Eval<B200_FACTOR_PRIOR_POSE2, WITH_J> {
+  static __device__ __forceinline__ void run(const EvalCtx& c, int k0, int, const double* __restrict__ z, int, const double*, double* M) {
+    enum { NC = 4 };
+    const P2 d = between2(load_pose2(c.values + c.val_off[k0]), load_pose2(z));
+    M[0 * NC + 3] = d.x; M[1 * NC + 3] = d.y; M[2 * NC + 3] = atan2(d.s, d.c);   // b = -r = Local(x, prior)
+    if (WITH_J) {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[i * NC + j] = (i == j) ? 1.0 : 0.0;
     }
   }
 };

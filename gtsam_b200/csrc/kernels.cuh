@@ -39,9 +39,9 @@ constexpr int kLeafMaxFN = 768;  // doubles of [F S d] staged per warp in shared
 constexpr int kMaxGroups = 8;    // factor groups addressable by the fused leaf kernel
 
 struct GroupTable { GroupView g[kMaxGroups]; };
-__constant__ int kFD[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9};
-__constant__ int kFN1[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 6, 9, 9};
-__constant__ int kFN2[B200_NUM_FACTOR_TYPES] = {6, 0, 0, 3, 3, 0};
+__constant__ int kFD[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 2, 2, 9, 3, 3};
+__constant__ int kFN1[B200_NUM_FACTOR_TYPES] = {6, 6, 3, 6, 9, 9, 3, 3};
+__constant__ int kFN2[B200_NUM_FACTOR_TYPES] = {6, 0, 0, 3, 3, 0, 3, 0};
 // column pairs (ca <= cb) of a factor's [A1 A2 b] block, per factor type (filled at ctx creation)
 constexpr int kMaxPairs = 96;   // 13*14/2 = 91
 // (global memory, read through L1: the index differs per lane, which would serialise in the constant cache)
@@ -1696,6 +1696,16 @@ __global__ void retract_kernel(const double* __restrict__ values, const double* 
   const int ty = var_type[v];
   if (ty == B200_VAR_POINT3) {
     y[0] = x[0] + d[0]; y[1] = x[1] + d[1]; y[2] = x[2] + d[2];
+  } else if (ty == B200_VAR_POSE2) {
+    // x * ChartAtOrigin::Retract(d) = x * Pose2(d0, d1, d2) (gtsam/geometry/Pose2.cpp:99-109, Pose2.h:131-133)
+    double s, c, sd, cd;
+    sincos(x[2], &s, &c);
+    sincos(d[2], &sd, &cd);
+    double cn = c * cd - s * sd, sn = s * cd + c * sd;
+    rot2_normalize(cn, sn);
+    y[0] = x[0] + (c * d[0] - s * d[1]);
+    y[1] = x[1] + (s * d[0] + c * d[1]);
+    y[2] = atan2(sn, cn);
   } else {
     double xi[6];
 #pragma unroll

@@ -5,6 +5,7 @@
 #include <gtsam/geometry/Cal3Bundler.h>
 #include <gtsam/geometry/Cal3_S2.h>
 #include <gtsam/geometry/PinholeCamera.h>
+#include <gtsam/geometry/Pose2.h>
 #include <gtsam/geometry/Pose3.h>
 #include <gtsam/linear/HessianFactor.h>
 #include <gtsam/linear/JacobianFactor.h>
@@ -89,6 +90,7 @@ struct DeviceState {
       if (auto p = dynamic_cast<const GenericValue<Pose3>*>(&v)) putPose(p->value(), out);
       else if (auto q = dynamic_cast<const GenericValue<Point3>*>(&v)) { out.push_back(q->value().x()); out.push_back(q->value().y()); out.push_back(q->value().z()); }
       else if (auto c = dynamic_cast<const GenericValue<BCam>*>(&v)) putCam(c->value(), out);
+      else if (auto p2 = dynamic_cast<const GenericValue<Pose2>*>(&v)) { out.push_back(p2->value().x()); out.push_back(p2->value().y()); out.push_back(p2->value().theta()); }
       else throw std::invalid_argument("gtsam_b200: unsupported Value type for key " + DefaultKeyFormatter(k));
     }
     return out;
@@ -102,6 +104,7 @@ struct DeviceState {
         case B200_VAR_POSE3: out.insert(id2key[i], getPose(v)); break;
         case B200_VAR_POINT3: out.insert(id2key[i], Point3(v[0], v[1], v[2])); break;
         case B200_VAR_CAM_BUNDLER: out.insert(id2key[i], BCam(getPose(v), Cal3Bundler(v[12], v[13], v[14], v[15], v[16]))); break;
+        case B200_VAR_POSE2: out.insert(id2key[i], Pose2(v[0], v[1], v[2])); break;
       }
     }
     return out;
@@ -152,6 +155,7 @@ struct DeviceState {
       if (dynamic_cast<const GenericValue<Pose3>*>(&v)) t = B200_VAR_POSE3;
       else if (dynamic_cast<const GenericValue<Point3>*>(&v)) t = B200_VAR_POINT3;
       else if (dynamic_cast<const GenericValue<BCam>*>(&v)) t = B200_VAR_CAM_BUNDLER;
+      else if (dynamic_cast<const GenericValue<Pose2>*>(&v)) t = B200_VAR_POSE2;
       else throw std::invalid_argument("gtsam_b200: unsupported Value type for key " + DefaultKeyFormatter(k));
       var_type.push_back(t);
       val_off.push_back(val_off.back() + b200_var_storage(t));
@@ -175,6 +179,12 @@ struct DeviceState {
       };
       if (auto b = dynamic_cast<const BetweenFactor<Pose3>*>(f.get())) {
         type = B200_FACTOR_BETWEEN_POSE3; keys = {id(b->key1()), id(b->key2())}; putPose(b->measured(), meas); nm = b->noiseModel();
+      } else if (auto b2 = dynamic_cast<const BetweenFactor<Pose2>*>(f.get())) {
+        type = B200_FACTOR_BETWEEN_POSE2; keys = {id(b2->key1()), id(b2->key2())};
+        meas = {b2->measured().x(), b2->measured().y(), b2->measured().theta()}; nm = b2->noiseModel();
+      } else if (auto q2 = dynamic_cast<const PriorFactor<Pose2>*>(f.get())) {
+        type = B200_FACTOR_PRIOR_POSE2; keys = {id(q2->key())};
+        meas = {q2->prior().x(), q2->prior().y(), q2->prior().theta()}; nm = q2->noiseModel();
       } else if (auto p3 = dynamic_cast<const PriorFactor<Pose3>*>(f.get())) {
         type = B200_FACTOR_PRIOR_POSE3; keys = {id(p3->key())}; putPose(p3->prior(), meas); nm = p3->noiseModel();
       } else if (auto pp = dynamic_cast<const PriorFactor<Point3>*>(f.get())) {
@@ -198,7 +208,7 @@ struct DeviceState {
         meas = {sf->measured().x(), sf->measured().y()}; nm = sf->noiseModel();
       } else {
         throw std::invalid_argument("gtsam_b200: unsupported factor type at graph position " + std::to_string(pos) +
-                                    " (no CPU fallback; supported: Between<Pose3>, Prior<Pose3|Point3|SfmCamera>, "
+                                    " (no CPU fallback; supported: Between<Pose3|Pose2>, Prior<Pose3|Pose2|Point3|SfmCamera>, "
                                     "GenericProjectionFactor<Pose3,Point3,Cal3_S2>, GeneralSFMFactor<SfmCamera,Point3>)");
       }
       d = b200_factor_dim(type);

@@ -18,7 +18,7 @@
  * the unmodified base-class loop (NonlinearOptimizer::defaultOptimize) drives iterate().
  *
  * Supported factors (anything else => std::invalid_argument, there is no CPU fallback):
- * BetweenFactor<Pose3>, PriorFactor<Pose3|Point3|PinholeCamera<Cal3Bundler>>,
+ * BetweenFactor<Pose3|Pose2>, PriorFactor<Pose3|Pose2|Point3|PinholeCamera<Cal3Bundler>>,
  * GenericProjectionFactor<Pose3,Point3,Cal3_S2> (with or without body_P_sensor),
  * GeneralSFMFactor<PinholeCamera<Cal3Bundler>,Point3>; noise models Unit,
  * Isotropic, Diagonal, Gaussian, and noiseModel::Robust (Huber / Cauchy / Tukey / Fair) around any

