@@ -120,6 +120,18 @@ static void resolve_profile(b200_problem* p) {  // call after a stream sync
 
 // Kernel launch with the programmatic-dependent-launch attribute (see pdl_sync in kernels.cuh).
 static const bool g_use_pdl = getenv("B200_NO_PDL") == nullptr;
+#ifdef B200_EMULATE
+// test-only host emulation build (tests/emu/cuda_emu_full.h): a launch runs the kernel's blocks one after the other
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+  // ascending blockIdx.x is dependency-safe: backsub_large_kernel's row blocks only wait (flags) on lower block ids
+  b200_emu::run(grid, block, smem, false, [&]() { kernel(KArgs(args)...); });
+}
+template <typename... KArgs, typename... Args>
+static void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_k(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
+#else
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -131,6 +143,14 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.numAttrs = g_use_pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+// a plain launch (what kernel<<<grid, block, smem, st>>>(args...) does): no programmatic dependent launch
+template <typename... KArgs, typename... Args>
+static void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 static int allreduce_sum(b200_problem* p, double* buf, size_t n);
 static int allreduce_max_int(b200_problem* p, int* buf, size_t n);
@@ -835,12 +855,14 @@ int b200_ctx_create(int device, b200_ctx** out) {
     B200_CUDA(cudaMemcpyToSymbol(kPairA, pa, sizeof pa));
     B200_CUDA(cudaMemcpyToSymbol(kPairB, pb, sizeof pb));
   }
+#ifndef B200_EMULATE   // (no shared-memory limit to raise in the host emulation build)
   B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
   B200_CUDA(cudaFuncSetAttribute(leaf_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * (kLeafMaxFN + kLeafAccMax) * sizeof(double))));
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
+#endif
   *out = c;
   return B200_OK;
 }
@@ -1264,7 +1286,7 @@ static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const 
   }
   if (ce == cudaSuccess) {
     const int nb = (int)std::min<int64_t>(((int64_t)nel + 255) / 256, (int64_t)p->ctx->sm_count * 16);
-    jacobian_load_kernel<<<nb, 256, 0, st>>>(d_stage, d_sig, g.d, g.ncols, (int)g.count, g.d_J);
+    launch_plain(jacobian_load_kernel, dim3(nb), dim3(256), 0, st, (const double*)d_stage, (const double*)d_sig, g.d, g.ncols, (int)g.count, g.d_J);
     p->ctx->launches++;
     ce = cudaGetLastError();
   }
@@ -1794,8 +1816,8 @@ int b200_marginal_covariance(b200_problem* p, int64_t var, double* out) {
   }
   B200_CUDA(cudaMemcpyAsync(p->d_marg_path, path.data(), path.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   B200_CUDA(cudaStreamSynchronize(st));   // `path` is pageable and dies with this call
-  marginal_path_kernel<<<d, 256, 0, st>>>(tview(p), p->d_marg_path, (int)path.size(), (int)S.var_dof[var], d, p->d_marg_work,
-                                          p->ndelta, p->d_marg_out);
+  launch_plain(marginal_path_kernel, dim3(d), dim3(256), 0, st, tview(p), (const int*)p->d_marg_path, (int)path.size(), (int)S.var_dof[var], d,
+               p->d_marg_work, p->ndelta, p->d_marg_out);
   ctx->launches++;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_marg_out, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1840,7 +1862,8 @@ int b200_joint_marginal_covariance(b200_problem* p, const int64_t* vars, int64_t
   B200_CUDA(cudaMemcpyAsync(d_path, path.data(), path.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   B200_CUDA(cudaMemcpyAsync(d_dofs, dofs.data(), (size_t)D * sizeof(int), cudaMemcpyHostToDevice, st));
   B200_CUDA(cudaStreamSynchronize(st));
-  marginal_joint_kernel<<<D, 256, 0, st>>>(tview(p), d_path, (int)path.size(), d_dofs, D, d_work, p->ndelta, d_out);
+  launch_plain(marginal_joint_kernel, dim3(D), dim3(256), 0, st, tview(p), (const int*)d_path, (int)path.size(), (const int*)d_dofs, D, d_work,
+               p->ndelta, d_out);
   ctx->launches++;
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -1922,11 +1945,11 @@ int b200_dl_iterate(b200_dl* dl) {
   for (auto& g : p->groups) {
     if (!g.count) continue;
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
-    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (gradient_kernel<TY, JT><<<nb, 256, 0, st>>>(view(g), p->d_var_dof, dl->d_grad))));
+    DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_plain(gradient_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), (const int*)p->d_var_dof, dl->d_grad))));
     ctx->launches++;
   }
   B200_CUDA(cudaGetLastError());
-  dot3_kernel<<<1, 1024, 0, st>>>(dl->d_grad, dl->d_dxn, n, p->d_scalars->dl_dots);
+  launch_plain(dot3_kernel, dim3(1), dim3(1024), 0, st, (const double*)dl->d_grad, (const double*)dl->d_dxn, n, p->d_scalars->dl_dots);
   ctx->launches++;
   rc = enqueue_linerr_of(p, dl->d_grad, 0.0, &p->d_scalars->dl_half_Ag2);
   if (rc) return rc;
@@ -1955,7 +1978,7 @@ int b200_dl_iterate(b200_dl* dl) {
       const double tau = (-eps <= tau1 && tau1 <= 1.0 + eps) ? tau1 : tau2;
       ca = 1. - tau; cb = tau;
     } else { ca = 0; cb = 1; }
-    blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dl->d_grad, dl->d_dxn, ca * step, cb, n, p->d_delta);
+    launch_plain(blend_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const double*)dl->d_grad, (const double*)dl->d_dxn, ca * step, cb, n, p->d_delta);
     ctx->launches++;
     B200_CUDA(cudaGetLastError());
     rc = enqueue_try_step(p);

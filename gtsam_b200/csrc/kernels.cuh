@@ -26,6 +26,12 @@
 #include <climits>
 
 #include "engine.cuh"
+#ifdef B200_EMULATE
+#include "cuda_emu_full.h"   // tests/emu: host model of the CUDA execution for the test-only emulation build
+#define B200_DYN_SMEM(T, name) T* name = (T*)b200_emu::dyn_smem()
+#else
+#define B200_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
 #include "factors.cuh"
 
 namespace b200 {
@@ -556,7 +562,7 @@ __device__ __forceinline__ int dexp(double x) {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 elim_small_kernel(TreeView t, const int* __restrict__ list, int count, int smem_n, Scalars* sc) {
   pdl_sync();
-  extern __shared__ double smem[];
+  B200_DYN_SMEM(double, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerBlock + warp;
   if (idx >= count) return;
@@ -645,7 +651,7 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
                   const double* __restrict__ lambda_ptr, const double* __restrict__ hdiag, double min_diag,
                   double max_diag, Scalars* sc, int lb_cap, int acc_cap) {
   pdl_sync();
-  extern __shared__ double leaf_sm[];
+  B200_DYN_SMEM(double, leaf_sm);
   const double lambda = *lambda_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int run = blockIdx.x * kWarpsPerBlock + warp;
@@ -784,6 +790,11 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
 // ---------------------------------------------------------------------------
 constexpr int kPtMaxObs = 8;
 
+#ifdef B200_EMULATE   // host emulation build: the asynchronous copy is a plain copy
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async_commit() {}
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
@@ -791,10 +802,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
+#endif
 __device__ __forceinline__ void cp_async_el(double* d, const double* s) { cp_async8(d, s); }
 __device__ __forceinline__ void cp_async_el(float* d, const float* s) { cp_async4(d, s); }
+#ifdef B200_EMULATE
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
 
 template <int DC, typename JT = double>
 __global__ void __launch_bounds__(128)
@@ -1247,11 +1264,23 @@ update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0
 // (PTX ISA, m8n8k4 .f64): A(row i = lane/4, col k = lane%4), B(row k = lane%4, col j = lane/4),
 // C/D(row i = lane/4, cols 2*(lane%4) + {0,1}).  With C -= P^T P: A[i][k] = P[k][i], B[k][j] = P[k][j],
 // both straight out of the staged row panels.  Only mode 2 (TRAIL) of update_kernel.
+#ifdef B200_EMULATE   // host emulation build: the fragment layout above spelled out with warp exchanges
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
+  for (int k = 0; k < 4; k++) {
+    const double ak = __shfl_sync(0xffffffffu, a, 4 * i + k);
+    const double b0 = __shfl_sync(0xffffffffu, b, 4 * j0 + k), b1 = __shfl_sync(0xffffffffu, b, 4 * (j0 + 1) + k);
+    d0 += ak * b0;
+    d1 += ak * b1;
+  }
+}
+#else
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
+#endif
 
 __global__ void __launch_bounds__(256)
 update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0, int fuse_ea) {

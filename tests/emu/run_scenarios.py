@@ -1,0 +1,142 @@
+"""Scenarios run against the HOST-EMULATION build of the whole library (tests/test_library_emulation.py starts this file
+in its own process: `python run_scenarios.py <libgtsam_b200_emu.so> <scenario>...`).  TEST INFRASTRUCTURE."""
+import os
+import sys
+import time
+
+os.environ["B200_NO_GRAPH"] = "1"      # CUDA graphs are not emulated: eager launches
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from gtsam_b200 import capi  # noqa: E402
+
+capi.LIB_PATH = sys.argv[1]
+import numpy as np  # noqa: E402
+import util  # noqa: E402
+from gtsam_b200 import linear as LN, optimizer, problem as P  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+ctx = capi.Context(0)
+
+
+def typed(case):
+    prob = util.load_case(case)
+    for kind, lam, diag in (("dump0", 0.0, 0), ("dump1", 1e-2, 1)):
+        dev = capi.DeviceProblem(ctx, prob)
+        util.check_against_dump(dev, prob, util.golden(case, kind), lam, diag)
+        dev.close()
+    # LM to convergence: same error / lambda sequence as the reference
+    ref = util.golden(case, "lm")
+    prm = optimizer.LevenbergMarquardtParams.CeresDefaults() if case in util.CERES_CASES else optimizer.LevenbergMarquardtParams()
+    lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, prm)
+    errs = [lm.error()]
+    for _ in range(len(ref["lm_errors"]) - 1):
+        lm.iterate()
+        errs.append(lm.error())
+    # (dubrovnik-3-7: cond(H) ~ 1e15 at the first lambdas -> trajectories agree to ~1e-6 only, as in tests/test_oracle_golden.py)
+    assert np.allclose(errs, ref["lm_errors"], rtol=1e-5 if case.startswith("dub") else 1e-7, atol=1e-10), (errs, ref["lm_errors"])
+    assert abs(lm.lambda_() - ref["lm_lambdas"][-1]) <= 1e-12 * ref["lm_lambdas"][-1]
+
+
+def fp32(case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "dump0")
+    dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+    dev.linearize()
+    st64 = dev.solve(0.0)[0]
+    d64, j64 = dev.get_delta(), dev.get_jacobians(0)
+    dev.set_jacobian_precision(True); orc.set_jacobian_precision(True)
+    dev.linearize(); orc.linearize()
+    for gi in range(len(prob.groups)):
+        J = dev.get_jacobians(gi)
+        assert np.array_equal(J, J.astype(np.float32).astype(np.float64))
+        assert util.relmax(J, orc.get_jacobians(gi)) <= 1e-6 and util.relmax(J, util.ref_jacobians(prob, ref, gi)) <= 1e-6
+    assert util.relmax(dev.hessian_diagonal(), orc.hessian_diagonal()) <= 1e-6
+    st, e0, e1, _ = dev.solve(1e-2, True)
+    so, f0, f1, _ = orc.solve(1e-2, True)
+    assert st == so == 0 and util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-5
+    assert abs(e0 - f0) <= 1e-6 * f0 and abs(e1 - f1) <= 1e-5 * f0
+    dev.set_jacobian_precision(False)
+    dev.linearize()
+    assert dev.solve(0.0)[0] == st64 and np.array_equal(dev.get_jacobians(0), j64)
+    assert st64 != 0 or util.rel2(dev.get_delta(), d64) <= 1e-10     # (assembly uses FP64 atomics: not bitwise reproducible on a GPU)
+    # LM with float Jacobians reaches the FP64 reference's optimum (FP32 protocol)
+    dev.set_jacobian_precision(True)
+    prm = optimizer.LevenbergMarquardtParams.CeresDefaults() if case in util.CERES_CASES else optimizer.LevenbergMarquardtParams()
+    lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, prm, device_problem=dev)
+    lm.optimize()
+    r = util.golden(case, "lm")["lm_errors"][-1]
+    assert abs(lm.error() - r) <= 1e-5 * r, (lm.error(), r)
+
+
+def linear(case):
+    lp = util.load_linear_case(case)
+    for which, lam in util.LINEAR_LAMBDA.items():
+        dev = capi.LinearDeviceProblem(ctx, lp)
+        util.check_linear_against_reference(dev, lp, util.golden(case, "out%d" % which), lam)
+        dev.close()
+
+
+def marginals(case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "marg")["marg_cov"]
+    m = optimizer.Marginals(ctx, prob)
+    off = 0
+    for v in range(prob.nvars):
+        d = int(prob.var_dims[v])
+        R = ref[off:off + d * d].reshape(d, d).T
+        off += d * d
+        if v % 5 == 0:
+            assert np.abs(m.marginalCovariance(v) - R).max() <= 1e-7 * np.abs(R).max(), v
+    for k, vs in enumerate(util.JOINT_SETS.get(case, [])):
+        J = m.jointMarginalCovariance(vs).fullMatrix()
+        R = util.golden(case, f"joint{k}")["joint_cov"].reshape(J.shape).T
+        assert np.abs(J - R).max() <= 1e-7 * np.abs(R).max(), vs
+
+
+def dogleg(case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "dl")
+    dl = optimizer.DoglegOptimizer(ctx, prob)
+    errs = [dl.error()]
+    for _ in range(min(3, len(ref["dl_errors"]) - 1)):
+        dl.iterate()
+        errs.append(dl.error())
+    assert np.allclose(errs, ref["dl_errors"][:len(errs)], rtol=1e-7), (errs, ref["dl_errors"][:len(errs)])
+
+
+def gn(case):
+    prob = util.load_case(case)
+    ref = util.golden(case, "gn")
+    dev = capi.DeviceProblem(ctx, prob)
+    errs = [dev.error()]
+    for _ in range(2):
+        st, e = dev.gn_iterate()
+        assert st == 0
+        errs.append(e)
+    assert np.allclose(errs, ref["gn_errors"][:3], rtol=1e-7), (errs, ref["gn_errors"][:3])
+
+
+def linear_mirror(_):
+    gfg = LN.GaussianFactorGraph()
+    gfg.add([5], [2 * np.eye(2)], np.ones(2))
+    gfg.add([5, 9], [np.eye(2), -np.eye(2)], np.array([1.0, 2.0]))
+    gfg.add([9], [np.eye(2)], np.zeros(2), np.array([0.5, 0.5]))
+    x = gfg.optimize([5, 9], ctx)
+    A = np.zeros((6, 4)); b = np.zeros(6)
+    A[0:2, 0:2] = 2 * np.eye(2); b[0:2] = 1
+    A[2:4, 0:2] = np.eye(2); A[2:4, 2:4] = -np.eye(2); b[2:4] = [1, 2]
+    A[4:6, 2:4] = 2 * np.eye(2)
+    sol = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.allclose(np.concatenate([x[5], x[9]]), sol, atol=1e-12)
+    bt = gfg.eliminateMultifrontal([5, 9], ctx)
+    assert len(bt) >= 1 and bt[-1][2] == -1
+
+
+SCEN = dict(typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
+for arg in sys.argv[2:]:
+    kind, case = arg.split(":")
+    t = time.time()
+    SCEN[kind](case)
+    print("EMU_OK %s %.1fs" % (arg, time.time() - t), flush=True)
+print("EMU_LAUNCHES", ctx.launch_count())

@@ -1,7 +1,7 @@
 """The "FP32 linearize + FP64 solve" mode on the device (b200_set_jacobian_precision, BASELINE.json configs[4]):
 the float instantiations of the linearize / assemble / hessianDiagonal / linear-error / leaf kernels against the
 oracle's restatement of the mode and against the FP64 reference at the FP32 protocol of SURVEY 8(c) ([A|b] rel <= 1e-5,
-final error rel <= 1e-5); switching back restores the FP64 results bit for bit; a mid-size BAL problem exercises the
+final error rel <= 1e-5); switching back restores the FP64 Jacobians bit for bit; a mid-size BAL problem exercises the
 point-leaf kernels (cp.async staging of float operands) and the CUDA graph of the LM try.
 
 The default (FP64) instantiations are unchanged by the templating (identical SASS before / after, checked when it was
@@ -50,7 +50,8 @@ for case in util.CASES:
     dev.set_jacobian_precision(False)
     dev.linearize()
     assert dev.solve(0.0)[0] == st64 and np.array_equal(dev.get_jacobians(0), j64), case
-    assert st64 != 0 or np.array_equal(dev.get_delta(), d64), case     # (an indeterminate undamped system leaves no delta)
+    # (an indeterminate undamped system leaves no delta; assembly adds with FP64 atomics, so delta is reproducible to rounding only)
+    assert st64 != 0 or util.rel2(dev.get_delta(), d64) <= 1e-10, case
     dev.close()
     # LM to convergence with float Jacobians vs the FP64 reference's optimum
     prm = optimizer.LevenbergMarquardtParams.CeresDefaults() if case in util.CERES_CASES else optimizer.LevenbergMarquardtParams()
