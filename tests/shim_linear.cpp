@@ -22,6 +22,7 @@
 
 #include <gtsam/geometry/Pose2.h>
 #include <gtsam/linear/GaussianBayesTree.h>
+#include <gtsam/linear/HessianFactor.h>
 #include <gtsam/linear/linearExceptions.h>
 #include <gtsam/slam/dataset.h>
 
@@ -58,6 +59,16 @@ static int cmd_graph(const std::string& path) {
     std::normal_distribution<double> N(0, 1);
     for (const auto& f : gfg) {
       auto jf = std::dynamic_pointer_cast<JacobianFactor>(f);
+      if (!jf) {   // a HessianFactor: scale its information a little (same structure, new numbers)
+        auto hf = std::dynamic_pointer_cast<HessianFactor>(f);
+        Matrix info = hf->info().selfadjointView();
+        info *= 1.0 + 0.01 * std::fabs(N(rng));
+        std::vector<DenseIndex> dims;
+        for (auto it = hf->begin(); it != hf->end(); ++it) dims.push_back(hf->getDim(it));
+        dims.push_back(1);
+        g2.push_back(std::make_shared<HessianFactor>(hf->keys(), SymmetricBlockMatrix(dims, info)));
+        continue;
+      }
       Matrix Ab = jf->augmentedJacobianUnweighted();
       for (int c = 0; c < Ab.cols(); c++) for (int r = 0; r < Ab.rows(); r++) Ab(r, c) += 0.01 * N(rng);
       std::vector<std::pair<Key, Matrix>> terms;
