@@ -4,7 +4,7 @@
 //
 //  * a launch runs the blocks of the grid one after the other (x fastest; ascending block ids are dependency-safe for
 //    the one kernel whose blocks wait on each other through flags), and inside a block every CUDA thread is a FIBER
-//    (ucontext) of one host thread, scheduled round-robin: it runs until it finishes or reaches a barrier;
+//    (its own stack, a 20-instruction context switch) of one host thread, scheduled round-robin: it runs until it finishes or reaches a barrier;
 //    __syncthreads() is a block-wide barrier, __syncwarp() and the __shfl_*_sync exchanges a per-warp barrier, so
 //    warp-synchronous code runs with its real data flow; a thread that returns drops out of both barriers (as exited
 //    threads do on the device).  Deterministic: the same schedule, hence the same atomic order, every run;
@@ -37,11 +37,42 @@
 #define __launch_bounds__(...)
 #define __restrict__
 
-// ---- cooperative scheduling: every CUDA thread of the running block is a fiber (ucontext) of ONE host thread -----------
-#include <ucontext.h>
+// ---- cooperative scheduling: every CUDA thread of the running block is a fiber of ONE host thread -----------
+// (a hand-written x86-64 context switch: swapcontext() saves and restores the signal mask with two system calls per
+// switch, and a kernel with one barrier per pivot switches millions of times)
 namespace b200_emu {
+struct Ctx { void* rsp = nullptr; };
+extern "C" void b200_emu_switch(Ctx* from, Ctx* to);
+asm(R"(
+.text
+.globl b200_emu_switch
+.type b200_emu_switch,@function
+b200_emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  subq $8, %rsp
+  stmxcsr (%rsp)
+  fnstcw 4(%rsp)
+  movq %rsp, (%rdi)
+  movq (%rsi), %rsp
+  ldmxcsr (%rsp)
+  fldcw 4(%rsp)
+  addq $8, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size b200_emu_switch, .-b200_emu_switch
+)");
 struct Fiber {
-  ucontext_t ctx;
+  Ctx ctx;
   uint3 tid;
   bool done = false;
   uint64_t xbuf = 0;     // 64-bit exchange slot (warp shuffles)
@@ -49,7 +80,7 @@ struct Fiber {
 struct Sched {
   std::vector<Fiber> fibers;
   std::vector<char> stacks;
-  ucontext_t main;
+  Ctx main;
   unsigned nt = 0, cur = 0;
   int block_alive = 0, block_arrived = 0;
   unsigned block_gen = 0;
@@ -60,7 +91,7 @@ struct Sched {
   void* entry_arg = nullptr;
 };
 inline Sched& sched() { static Sched s; return s; }
-inline void yield() { Sched& s = sched(); swapcontext(&s.fibers[s.cur].ctx, &s.main); }
+inline void yield() { Sched& s = sched(); b200_emu_switch(&s.fibers[s.cur].ctx, &s.main); }
 inline void block_sync() {
   Sched& s = sched();
   const unsigned g = s.block_gen;
@@ -82,7 +113,8 @@ inline void fiber_main() {
   s.block_alive--; s.warp_alive[w]--;
   if (s.block_alive > 0 && s.block_arrived == s.block_alive) { s.block_gen++; s.block_arrived = 0; }
   if (s.warp_alive[w] > 0 && s.warp_arrived[w] == s.warp_alive[w]) { s.warp_gen[w]++; s.warp_arrived[w] = 0; }
-  swapcontext(&f.ctx, &s.main);
+  b200_emu_switch(&f.ctx, &s.main);   // never resumed
+  __builtin_trap();
 }
 }  // namespace b200_emu
 
@@ -154,11 +186,16 @@ static void run(dim3 grid, dim3 block, size_t smem, bool descending_x, F&& fn) {
           Fiber& f = s.fibers[t];
           f.done = false; f.tid.x = t; f.tid.y = 0; f.tid.z = 0;
           s.warp_alive[t >> 5]++;
-          getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = s.stacks.data() + (size_t)t * kStack;
-          f.ctx.uc_stack.ss_size = kStack;
-          f.ctx.uc_link = &s.main;
-          makecontext(&f.ctx, (void (*)())fiber_main, 0);
+          // initial frame: what b200_emu_switch pops (mxcsr / x87 control word, six callee-saved registers) and the
+          // address it returns to; the stack pointer after that `ret` is 8 modulo 16, as at any function entry
+          uintptr_t top = (uintptr_t)(s.stacks.data() + (size_t)(t + 1) * kStack);
+          top &= ~(uintptr_t)15;
+          uint64_t* sp = (uint64_t*)(top - 72);
+          sp[0] = 0x037F00001F80ull;        // mxcsr = 0x1F80 (bytes 0-3), x87 control word = 0x037F (bytes 4-5)
+          for (int q = 1; q <= 6; q++) sp[q] = 0;
+          sp[7] = (uint64_t)(uintptr_t)(void (*)())fiber_main;
+          sp[8] = 0;
+          f.ctx.rsp = sp;
         }
         unsigned remaining = nt;
         while (remaining) {      // round robin: a fiber runs until it finishes or has to wait at a barrier
@@ -166,7 +203,7 @@ static void run(dim3 grid, dim3 block, size_t smem, bool descending_x, F&& fn) {
           for (unsigned t = 0; t < nt; t++) {
             if (s.fibers[t].done) continue;
             s.cur = t;
-            swapcontext(&s.main, &s.fibers[t].ctx);
+            b200_emu_switch(&s.main, &s.fibers[t].ctx);
             if (!s.fibers[t].done) remaining++;
           }
         }

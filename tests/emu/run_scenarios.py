@@ -133,7 +133,22 @@ def linear_mirror(_):
     assert len(bt) >= 1 and bt[-1][2] == -1
 
 
-SCEN = dict(typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
+def gnc_scenario(case):
+    """gtsam_b200.gnc.GncOptimizer with the device backend against the reference's GncOptimizer (TLS and GM)."""
+    from gtsam_b200 import gnc
+    prob = util.load_case(case)
+    for loss in ("tls", "gm"):
+        ref = util.golden(case, "gnc_" + loss)
+        prm = gnc.GncParams()
+        prm.lossType = gnc.TLS if loss == "tls" else gnc.GM
+        opt = gnc.GncOptimizer(ctx, prob, prm)
+        res = opt.optimize()
+        opt.backend.close()
+        assert float(np.abs(opt.getWeights() - ref["gnc_weights"]).max()) <= 1e-4
+        assert util.relmax(res, ref["final_values"]) <= 1e-5
+
+
+SCEN = dict(gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
 for arg in sys.argv[2:]:
     kind, case = arg.split(":")
     t = time.time()

@@ -169,109 +169,6 @@ def test_linear_kernels_emulated_on_host(emu, case, built):
     assert abs(e1.value - 0.5 * x @ Hglob @ x) <= 1e-10 * abs(e0.value)
 
 
-# ---- the marginal kernels (block-cooperative: real __syncthreads, no shuffles) in lockstep emulation ----------------
-MARG_WRAPPERS = r"""
-extern "C" {
-static TreeView mktree2(double* arena, const int64_t* off, const int* nf, const int* ns, const int* ld, const int64_t* didx_ptr, const int* didx) {
-  TreeView t;
-  memset(&t, 0, sizeof t);
-  t.arena = arena; t.off = off; t.nf = nf; t.ns = ns; t.ld = ld; t.didx_ptr = didx_ptr; t.didx = didx;
-  return t;
-}
-void emu_marginal_path(double* arena, const int64_t* off, const int* nf, const int* ns, const int* ld, const int64_t* didx_ptr, const int* didx,
-                       const int* path, int npath, int dof0, int d, double* work, int64_t ndelta, double* out) {
-  TreeView t = mktree2(arena, off, nf, ns, ld, didx_ptr, didx);
-  EMU_LAUNCH_LOCKSTEP(marginal_path_kernel, d, 256, t, path, npath, dof0, d, work, ndelta, out);
-}
-void emu_marginal_joint(double* arena, const int64_t* off, const int* nf, const int* ns, const int* ld, const int64_t* didx_ptr, const int* didx,
-                        const int* path, int npath, const int* dofs, int D, double* work, int64_t ndelta, double* out) {
-  TreeView t = mktree2(arena, off, nf, ns, ld, didx_ptr, didx);
-  EMU_LAUNCH_LOCKSTEP(marginal_joint_kernel, D, 256, t, path, npath, dofs, D, work, ndelta, out);
-}
-}
-"""
-
-
-@pytest.fixture(scope="module")
-def emu_marg():
-    kern = open(os.path.join(ROOT, "gtsam_b200", "csrc", "kernels.cuh")).read()
-    eng = open(os.path.join(ROOT, "gtsam_b200", "csrc", "engine.cuh")).read()
-    src = '#include "cuda_emu_lockstep.h"\n' + _extract(eng, r"^struct TreeView \{")
-    src += "constexpr int kMargMaxF = 4096;\n"
-    for k in ("marginal_path_kernel", "marginal_joint_kernel"):
-        src += _extract(kern, r"^__global__ void __launch_bounds__\(256\)\n" + k + r"\(")
-    src += MARG_WRAPPERS
-    td = tempfile.mkdtemp()
-    cpp, so = os.path.join(td, "emu_marg.cpp"), os.path.join(td, "libemu_marg.so")
-    open(cpp, "w").write(src)
-    subprocess.check_call(["g++", "-O1", "-std=c++20", "-w", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
-    return C.CDLL(so)
-
-
-@pytest.mark.parametrize("case", ["bal_tiny_s2", "sphere_tiny"])
-def test_marginal_kernels_emulated_on_host(emu_marg, case):
-    """marginal_path_kernel (validated on the B200) and marginal_joint_kernel (first hardware run pending), verbatim, in
-    lockstep emulation on the oracle's conditionals [R S d]: single-variable covariances and the joint covariances of
-    the golden variable sets against the unmodified reference's Marginals."""
-    prob = util.load_case(case)
-    orc = O.OracleProblem(prob)
-    orc.linearize()
-    assert orc.solve(0.0)[0] == 0
-    fp, fv, sp, sv, par = orc.cliques()
-    dims = prob.var_dims.astype(np.int64)
-    dof = prob.dof_offsets()
-    nc, ndelta = len(par), int(dof[-1])
-    nf = np.array([dims[fv[fp[c]:fp[c + 1]]].sum() for c in range(nc)], dtype=np.int32)
-    ns = np.array([dims[sv[sp[c]:sp[c + 1]]].sum() for c in range(nc)], dtype=np.int32)
-    ld = nf.copy()                                  # compact conditional storage, as for fused leaves: f x (f+s+1), ld = f
-    off = np.concatenate([[0], np.cumsum(nf.astype(np.int64) * (nf + ns + 1))]).astype(np.int64)
-    arena = np.concatenate([orc.conditional(c).T.ravel() for c in range(nc)])     # (f, n) -> column-major
-    didx_ptr = np.concatenate([[0], np.cumsum(nf + ns)]).astype(np.int64)
-    didx = np.concatenate([np.concatenate([np.arange(dof[v], dof[v + 1]) for v in list(fv[fp[c]:fp[c + 1]]) + list(sv[sp[c]:sp[c + 1]])])
-                           for c in range(nc)]).astype(np.int32)
-    var_clique = np.zeros(prob.nvars, dtype=np.int64)
-    for c in range(nc):
-        var_clique[fv[fp[c]:fp[c + 1]]] = c
-    i64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))   # noqa: E731
-    tree = (_dp(arena), i64(off), _ip32(nf), _ip32(ns), _ip32(ld), i64(didx_ptr), _ip32(didx))
-    # single variables vs the reference's Marginals::marginalCovariance
-    ref = util.golden(case, "marg")["marg_cov"]
-    o = 0
-    for v in range(prob.nvars):
-        d = int(dims[v])
-        R = ref[o:o + d * d].reshape(d, d).T
-        o += d * d
-        if v not in (0, prob.nvars // 2, prob.nvars - 1):   # three variables keep the 256-thread emulation quick
-            continue
-        path = []
-        c = int(var_clique[v])
-        while c >= 0:
-            path.append(c); c = int(par[c])
-        path = np.array(path, dtype=np.int32)
-        work, out = np.zeros(d * ndelta), np.zeros(d * d)
-        emu_marg.emu_marginal_path(*tree, _ip32(path), len(path), int(dof[v]), d, _dp(work), C.c_int64(ndelta), _dp(out))
-        S = out.reshape(d, d).T
-        assert np.abs(S - R).max() <= 1e-8 * np.abs(R).max(), v
-    # joint sets vs Marginals::jointMarginalCovariance (tests/golden/<case>.joint<i>.bin)
-    for k, vs in enumerate(util.JOINT_SETS[case]):
-        vs = sorted(vs)
-        on = np.zeros(nc, dtype=bool)
-        for v in vs:
-            c = int(var_clique[v])
-            while c >= 0 and not on[c]:
-                on[c] = True; c = int(par[c])
-        path = np.nonzero(on)[0].astype(np.int32)
-        dofs = np.concatenate([np.arange(dof[v], dof[v + 1]) for v in vs]).astype(np.int32)
-        D = len(dofs)
-        work, out = np.zeros(D * ndelta), np.zeros(D * D)
-        emu_marg.emu_marginal_joint(*tree, _ip32(path), len(path), _ip32(dofs), D, _dp(work), C.c_int64(ndelta), _dp(out))
-        S = out.reshape(D, D).T
-        g = util.golden(case, f"joint{k}")
-        R = next(iter(g.values())) if len(g) == 1 else g.get("joint_cov", g.get("cov"))
-        R = np.asarray(R).reshape(D, D).T
-        assert np.abs(S - R).max() <= 1e-8 * np.abs(R).max(), vs
-
-
 # ---- the factor evaluators: linearize_kernel<TYPE, JT> and error_kernel<TYPE>, verbatim, with the product's own
 # ---- factors.cuh / geometry.cuh compiled for the host ----------------------------------------------------------------
 EVAL_WRAPPERS = r"""

@@ -2,8 +2,7 @@
 level) driven against the HOST-EMULATION build of the library (tests/test_library_emulation.py): the parity drivers that
 tests/test_gpu_shim*.py run on the B200 are started here with LD_PRELOAD=libgtsam_b200_emu.so, so the b200_* symbols
 resolve to the emulated library, and held to the same thresholds — real GTSAM objects on both sides, the stock optimizer
-as the reference.  (The reference's own GncOptimizer template over B200LevenbergMarquardtParams was run once this way:
-weights identical, values to 4e-14 after 12 minutes of emulation — too slow to keep here.)"""
+as the reference.  """
 import json
 import os
 import subprocess
@@ -12,39 +11,19 @@ import numpy as np
 import pytest
 
 import util
-from test_library_emulation import emu_lib  # noqa: F401  (fixture: builds tests/emu/_build/libgtsam_b200_emu.so)
+from test_library_emulation import emu_jobs, emu_lib  # noqa: F401  (fixtures: build the emulated library, start every emulation job at once)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "shim_parity")), reason="shim drivers not built (need /root/reference at build time)")
 
 
-def start(lib, *args):
-    env = dict(os.environ, LD_PRELOAD=lib, B200_NO_GRAPH="1")
-    return subprocess.Popen([os.path.join(REF, args[0])] + [str(a) for a in args[1:]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
-
-
-def finish(p):
-    out, err = p.communicate(timeout=900)
-    assert p.returncode == 0, err[-600:]
-    return json.loads(out.strip().splitlines()[-1])
-
-
-def test_cpp_drop_ins_against_the_emulated_library(emu_lib):  # noqa: F811
-    g = util.GOLDEN
-    jobs = {
-        "lm_bal": start(emu_lib, "shim_parity", os.path.join(g, "bal_tiny_s2.prob.bin"), 30, 0),
-        "lm_bundler": start(emu_lib, "shim_parity", os.path.join(g, "bal_tiny_bundler.prob.bin"), 30, 1),
-        "lm_pose2": start(emu_lib, "shim_parity", os.path.join(g, "pose2_ring_colamd.prob.bin"), 30, 0),
-        "lm_huber": start(emu_lib, "shim_parity", os.path.join(g, "sphere_tiny_huber.prob.bin"), 30, 0),
-        "marg": start(emu_lib, "shim_marginals", os.path.join(g, "bal_tiny_s2.prob.bin")),
-        "lin_nary": start(emu_lib, "shim_linear", "graph", os.path.join(g, "lin_random_nary.lin.bin")),
-        "lin_hess": start(emu_lib, "shim_linear", "graph", os.path.join(g, "lin_mixed_hessian.lin.bin")),
-        "lin_sing": start(emu_lib, "shim_linear", "graph", os.path.join(g, "lin_singular.lin.bin")),
-        "pose2": start(emu_lib, "shim_linear", "pose2", os.path.join(g, "data", "synthetic_pose2.g2o"), 30),
-        "families": start(emu_lib, "shim_families", "gpu"),
-    }
-    r = {k: finish(p) for k, p in jobs.items()}
+def test_cpp_drop_ins_against_the_emulated_library(emu_jobs):  # noqa: F811
+    r = {}
+    for k in ("lm_bal", "lm_bundler", "lm_pose2", "lm_huber", "marg", "lin_nary", "lin_hess", "lin_sing", "pose2", "families", "gnc"):
+        rc, out, err = emu_jobs["shim_" + k]
+        assert rc == 0, (k, err[-600:])
+        r[k] = json.loads(out.strip().splitlines()[-1])
     for k in ("lm_bal", "lm_bundler", "lm_pose2", "lm_huber"):      # B200LevenbergMarquardtOptimizer vs the stock optimizer
         x = r[k]
         assert x["launches"] > 0 and len(x["dev_errors"]) == len(x["ref_errors"])
@@ -62,5 +41,7 @@ def test_cpp_drop_ins_against_the_emulated_library(emu_lib):  # noqa: F811
     p2 = r["pose2"]                                                   # the solve() seam on a Pose2 graph
     assert np.allclose(p2["lm_dev_errors"], p2["lm_ref_errors"], rtol=1e-8) and np.allclose(p2["gn_dev_errors"], p2["gn_ref_errors"], rtol=1e-8)
     assert p2["lm_value_diff"] <= 1e-7 and p2["gn_value_diff"] <= 1e-7 and p2["lm_dev_inner"] == p2["lm_ref_inner"] and p2["structure_builds"] == 1
+    # the reference's own GncOptimizer template instantiated with B200LevenbergMarquardtParams vs the stock instantiation
+    assert 0 <= r["gnc"]["gnc_weights"] <= 1e-4 and 0 <= r["gnc"]["gnc_values"] <= 1e-5
     for name, x in r["families"].items():                             # GeneralSFMFactor2, smart factors, expression factors
         assert x["worst_error_rel_diff"] <= 1e-7 and x["value_diff"] <= 1e-6 and x["launches"] > 0 and x["builds"] == 1, (name, x)
