@@ -148,7 +148,73 @@ def gnc_scenario(case):
         assert util.relmax(res, ref["final_values"]) <= 1e-5
 
 
-SCEN = dict(gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
+def edge(_):
+    """tests/test_gpu_parity.py::test_cuda_edge_cases + API misuse: forests, empty groups, rank-deficient leaves, calls in
+    the wrong order, calls that need Values on a linear problem."""
+    for name, prob in util.edge_case_problems().items():
+        dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+        assert abs(dev.error() - orc.error()) <= 1e-12 * max(1.0, orc.error())
+        dev.linearize(); orc.linearize()
+        for lam in (0.0, 1e-3):
+            st, e0, e1, _ = dev.solve(lam)
+            so, f0, f1, _ = orc.solve(lam)
+            assert st == so, (name, lam, st, so)
+            if st == 0:
+                assert util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+                assert abs(e1 - f1) <= 1e-9 * max(1.0, f0)
+        lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, device_problem=dev)
+        olm = orc.lm(lm.params()._c)
+        for _ in range(3):
+            lm.iterate(); orc.lm_iterate(olm)
+            assert abs(lm.error() - olm.state.error) <= 1e-8 * max(1.0, olm.state.error)
+            assert lm.lambda_() == olm.state.lambda_
+        del lm
+        dev.close()
+    prob = util.load_case("bal_tiny_s2")
+    dev = capi.DeviceProblem(ctx, prob)
+    for call in (lambda: dev.solve(0.0), lambda: dev.hessian_diagonal(), lambda: dev.get_jacobians(0), lambda: dev.try_step()):
+        try:
+            call()
+            raise SystemExit("a call before b200_linearize / b200_solve was accepted")
+        except capi.B200Error as e:
+            assert e.code == P.INVALID_ARGUMENT
+    dev.close()
+    lp = util.load_linear_case("lin_arity8")
+    ldev = capi.LinearDeviceProblem(ctx, lp)
+    for call in (lambda: ldev.error(), lambda: ldev.linearize(), lambda: ldev.try_step(), lambda: ldev.set_jacobian_precision(True),
+                 lambda: optimizer.LevenbergMarquardtOptimizer(ctx, lp, device_problem=ldev)):
+        try:
+            call()
+            raise SystemExit("a call that needs Values was accepted on a linear problem")
+        except capi.B200Error as e:
+            assert e.code == P.INVALID_ARGUMENT
+    ldev.close()
+
+
+def bigfront(_):
+    """tests/test_gpu_parity.py::test_big_front_scheme_matches_oracle: the 128-column big-panel scheme with the DMMA
+    trailing update (emulated fragment layout) and with the FP64-FMA tile kernel, forced onto mid-size fronts."""
+    from gtsam_b200 import datasets
+    for no_dmma in (False, True):
+        os.environ["B200_BIG_MIN_N"] = "64"
+        if no_dmma:
+            os.environ["B200_NO_DMMA"] = "1"
+        prob = datasets.make("sphere_tiny", layers=10, per_ring=16)
+        dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+        info = dev.symbolic_info()
+        assert info.max_frontal_dim + info.max_separator_dim >= 128
+        dev.linearize(); orc.linearize()
+        for lam in (0.0, 1e-3):
+            st, e0, e1, _ = dev.solve(lam)
+            so, f0, f1, _ = orc.solve(lam)
+            assert st == so == 0 and util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8 and abs(e1 - f1) <= 1e-9 * f0
+        a, b = dev.conditional(info.ncliques - 1), orc.conditional(info.ncliques - 1)
+        assert np.abs(a - b).max() <= 1e-7 * max(1.0, np.abs(b).max())
+        dev.close()
+    os.environ.pop("B200_BIG_MIN_N", None); os.environ.pop("B200_NO_DMMA", None)
+
+
+SCEN = dict(edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
 for arg in sys.argv[2:]:
     kind, case = arg.split(":")
     t = time.time()
