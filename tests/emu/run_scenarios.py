@@ -214,7 +214,36 @@ def bigfront(_):
     os.environ.pop("B200_BIG_MIN_N", None); os.environ.pop("B200_NO_DMMA", None)
 
 
-SCEN = dict(edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
+def midsize(model):
+    """A BAL problem large enough for long runs of points with the same cameras (several staged batches per CTA in
+    leaf_point_schur_kernel, both buffers of the software pipeline in use), FP64 and FP32 storage, against the oracle in
+    the same mode; then two LM iterations."""
+    from gtsam_b200 import datasets
+    model, _, obs = model.partition("@")     # e.g. bundler@8: 8 observations per point -> 3 tiles per thread in the Schur kernel
+    prob = datasets.make("bal_tiny", ncams=12, npoints=1500 if not obs else 400, visibility="banded", camera_model=model,
+                         obs_per_point=int(obs or 6))
+    for f32, pb in ((False, 4), (True, 4), (False, 6), (True, 6)):
+        # (run length is sized from the SM count; at this size it would be 1, so it is forced)
+        os.environ["B200_LEAF_RUN_MAX"] = "24"; os.environ["B200_SCHUR_PB"] = str(pb)
+        dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+        os.environ.pop("B200_LEAF_RUN_MAX"); os.environ.pop("B200_SCHUR_PB")
+        dev.set_jacobian_precision(f32); orc.set_jacobian_precision(f32)
+        dev.linearize(); orc.linearize()
+        for lam, diag in ((1e-3, False), (1e-2, True)):
+            st, e0, e1, _ = dev.solve(lam, diag)
+            so, f0, f1, _ = orc.solve(lam, diag)
+            assert st == so == 0 and util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-6, (f32, lam)   # additive 1e-3 damping: cond ~1e8
+            assert abs(e1 - f1) <= 1e-6 * f0
+        lm = optimizer.LevenbergMarquardtOptimizer(ctx, prob, optimizer.LevenbergMarquardtParams.CeresDefaults(), device_problem=dev)
+        olm = orc.lm(lm.params()._c)
+        for _ in range(2):
+            lm.iterate(); orc.lm_iterate(olm)
+            assert abs(lm.error() - olm.state.error) <= 1e-6 * olm.state.error
+        del lm
+        dev.close()
+
+
+SCEN = dict(midsize=midsize, edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
 for arg in sys.argv[2:]:
     kind, case = arg.split(":")
     t = time.time()
