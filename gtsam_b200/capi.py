@@ -22,7 +22,7 @@ _LIB = None
 EXPORTS = [
     "b200_var_storage", "b200_var_dim", "b200_factor_arity", "b200_factor_meas_size", "b200_factor_dim",
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error_string", "b200_launch_count", "b200_ctx_stream",
-    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_get_values", "b200_values_size",
+    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_set_group_noise", "b200_get_values", "b200_values_size",
     "b200_delta_size", "b200_error", "b200_linearize", "b200_get_jacobians", "b200_hessian_diagonal",
     "b200_solve", "b200_get_delta", "b200_try_step", "b200_accept_step", "b200_lm_params_legacy",
     "b200_lm_params_ceres", "b200_lm_create", "b200_lm_destroy", "b200_lm_iterate", "b200_lm_optimize",
@@ -71,6 +71,7 @@ def lib():
         L.b200_problem_create.argtypes = [vp, C.POINTER(P.CProblemDesc), C.POINTER(vp)]
         L.b200_problem_destroy.argtypes = [vp]
         L.b200_set_values.argtypes = [vp, dp]
+        L.b200_set_group_noise.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp]
         L.b200_get_values.argtypes = [vp, dp]
         L.b200_values_size.argtypes = [vp]
         L.b200_values_size.restype = C.c_int64
@@ -247,6 +248,17 @@ class DeviceProblem:
         v = np.ascontiguousarray(v, dtype=np.float64)
         assert v.size == self.nval
         _check(self.L.b200_set_values(self.h, _dp(v)))
+
+    def set_group_noise(self, gi: int, noise_kind: int, noise):
+        """New noise model(s) on factor group ``gi`` (shared payload, or one per factor), as GncOptimizer's
+        makeWeightedGraph does between outer iterations; the robust loss of the group is kept."""
+        g = self.prob.groups[gi]
+        pay = P.noise_payload(noise_kind, P.FACTOR_DIM[g.type])
+        noise = np.zeros(0) if noise is None else np.ascontiguousarray(noise, dtype=np.float64).ravel()
+        if noise.size not in (pay, pay * g.count):
+            raise ValueError("noise payload size")
+        per = int(pay > 0 and noise.size == pay * g.count and g.count > 1)
+        _check(self.L.b200_set_group_noise(self.h, C.c_int64(gi), noise_kind, per, _dp(noise) if noise.size else None))
 
     def get_values(self, out=None):
         """Packed values; pass a page-locked float64 array as ``out`` for a direct D2H copy."""

@@ -1348,6 +1348,39 @@ int b200_set_values(b200_problem* p, const double* v) {
   p->linearized = p->solved = p->marg_ready = false;
   return B200_OK;
 }
+/* New noise models on an existing group: GncOptimizer::makeWeightedGraph (gtsam/nonlinear/GncOptimizer.h:391-411)
+ * between outer iterations, without the symbolic phase and the uploads of a new problem. */
+int b200_set_group_noise(b200_problem* p, int64_t group, int32_t noise_kind, int32_t noise_per_factor, const double* noise) {
+  if (!p) { set_error("null problem"); return B200_INVALID_ARGUMENT; }
+  if (p->linear) { set_error("b200_set_group_noise: a linear problem carries its sigmas in b200_linear_update"); return B200_INVALID_ARGUMENT; }
+  if (group < 0 || group >= (int64_t)p->groups.size()) { set_error("b200_set_group_noise: group index out of range"); return B200_INVALID_ARGUMENT; }
+  auto& g = p->groups[group];
+  const int payload = noise_payload(noise_kind, g.d);
+  if (payload < 0) { set_error("unsupported noise model (Constrained models need QR: out of scope)"); return B200_UNSUPPORTED_NOISE; }
+  if (payload > 0 && !noise) { set_error("b200_set_group_noise: null noise payload"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  std::vector<double> h;
+  if (noise_per_factor) {   // this rank's factors only (all of them when world == 1)
+    h.resize((size_t)g.count * payload);
+    for (int64_t li = 0; li < g.count; li++)
+      memcpy(h.data() + (size_t)li * payload, noise + (size_t)g.local_index[li] * payload, (size_t)payload * sizeof(double));
+  } else {
+    h.assign(noise, noise + payload);
+  }
+  double* fresh = nullptr;
+  int rc = upload(&fresh, h, p->ctx->stream);
+  if (rc) return rc;
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));   // h goes out of scope
+  cudaFree(g.d_noise);
+  g.d_noise = fresh;
+  g.noise_kind = noise_kind; g.per_factor = noise_per_factor ? 1 : 0; g.noise_size = payload;
+  for (int i = 0; i < 2; i++)   // the captured LM try has the group views baked in
+    if (p->try_graph[i]) { cudaGraphExecDestroy(p->try_graph[i]); p->try_graph[i] = nullptr; }
+  p->linearized = p->solved = p->factored = p->marg_ready = false;
+  return B200_OK;
+}
+
 int b200_get_values(b200_problem* p, double* v) {
   if (p->linear) { set_error("this call needs Values: not available on a linear problem (b200_linear_create)"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));

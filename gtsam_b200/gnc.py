@@ -110,7 +110,8 @@ class DeviceBackend:
 
     def __init__(self, ctx: Context, lm_params: LevenbergMarquardtParams):
         self.ctx, self.lm_params = ctx, lm_params
-        self._eval = None
+        self._eval = self._dp = None
+        self._dp_sig = None
 
     def factor_errors(self, prob: P.Problem, values: np.ndarray) -> np.ndarray:
         """nfg_[k]->error(values) for every factor, graph order: 0.5 * |whitened residual|^2 = 0.5 * |b|^2 of
@@ -126,19 +127,31 @@ class DeviceBackend:
         return out
 
     def optimize(self, prob_w: P.Problem):
-        """BaseOptimizer(graph_w, state_, params).optimize(); returns (values, graph_w.error(values))."""
-        dp = DeviceProblem(self.ctx, prob_w)
+        """BaseOptimizer(graph_w, state_, params).optimize(); returns (values, graph_w.error(values)).
+        The weighted graphs of one GNC run differ in their noise payloads and initial values only: the device
+        problem (symbolic phase, keys, measurements) is built once and re-weighted through b200_set_group_noise."""
+        sig = [g.keys for g in prob_w.groups]      # weighted_problem() shares the structural arrays (held: ids stay unique)
+        if self._dp is None or len(sig) != len(self._dp_sig) or any(a is not b for a, b in zip(sig, self._dp_sig)):
+            if self._dp is not None:
+                self._dp.close()
+            self._dp, self._dp_sig = DeviceProblem(self.ctx, prob_w), sig
+        else:
+            for gi, g in enumerate(prob_w.groups):
+                self._dp.set_group_noise(gi, g.noise_kind, g.noise)
+            self._dp.set_values(prob_w.values)
+        dp = self._dp
+        dp.prob = prob_w
         lm = LevenbergMarquardtOptimizer(self.ctx, prob_w, self.lm_params, device_problem=dp)
         lm.optimize()
         values, cost = dp.get_values(), lm.error()
         del lm
-        dp.close()
         return values, cost
 
     def close(self):
-        if self._eval is not None:
-            self._eval.close()
-            self._eval = None
+        for h in (self._eval, self._dp):
+            if h is not None:
+                h.close()
+        self._eval = self._dp = None
 
 
 class GncOptimizer:

@@ -215,6 +215,13 @@ int b200_problem_destroy(b200_problem* prob);
 int b200_set_values(b200_problem* prob, const double* packed_values);
 int b200_get_values(b200_problem* prob, double* packed_values);
 int64_t b200_values_size(const b200_problem* prob); /* doubles in packed values */
+/* Replace the noise model(s) of factor group `group` (index into desc.groups) in place: `noise` is laid out like
+ * b200_factor_group::noise for (noise_kind, noise_per_factor); the group's robust loss is kept.  This is what
+ * GncOptimizer::makeWeightedGraph (gtsam/nonlinear/GncOptimizer.h:391-411) does to the graph between outer
+ * iterations, without a new symbolic phase.  Invalidates the linearization; b200_lm / b200_dl handles created on
+ * the problem before the call hold a stale error: create new ones. */
+int b200_set_group_noise(b200_problem* prob, int64_t group, int32_t noise_kind, int32_t noise_per_factor, const double* noise);
+
 int64_t b200_delta_size(const b200_problem* prob);  /* total tangent dim        */
 
 /* NonlinearFactorGraph::error(values), gtsam/nonlinear/NonlinearFactorGraph.cpp:170-179 */

@@ -146,6 +146,29 @@ def gnc_scenario(case):
         opt.backend.close()
         assert float(np.abs(opt.getWeights() - ref["gnc_weights"]).max()) <= 1e-4
         assert util.relmax(res, ref["final_values"]) <= 1e-5
+    # b200_set_group_noise == a problem created with that noise (bitwise: same kernels, same inputs, no atomics in linearize)
+    base = gnc.strip_robust(prob)
+    w = np.random.default_rng(5).uniform(0.0, 1.0, base.nfactors)
+    w[::7] = 0.0
+    pw = gnc.weighted_problem(base, w)
+    fresh, upd = capi.DeviceProblem(ctx, pw), capi.DeviceProblem(ctx, base)
+    upd.linearize(); upd.solve(1e-3)
+    for gi, g in enumerate(pw.groups):
+        upd.set_group_noise(gi, g.noise_kind, g.noise)
+    try:
+        upd.solve(1e-3)
+        raise AssertionError("solve on a stale linearization")
+    except capi.B200Error:
+        pass
+    fresh.linearize(); upd.linearize()
+    for gi in range(len(pw.groups)):
+        assert np.array_equal(fresh.get_jacobians(gi), upd.get_jacobians(gi))
+    assert fresh.solve(1e-3, True)[0] == upd.solve(1e-3, True)[0] == 0
+    assert util.rel2(fresh.get_delta(), upd.get_delta()) <= 1e-10
+    assert upd.L.b200_set_group_noise(upd.h, 99, P.NOISE_UNIT, 0, None) == 4
+    assert upd.L.b200_set_group_noise(upd.h, 0, 77, 0, None) == 3
+    assert upd.L.b200_set_group_noise(upd.h, 0, P.NOISE_DIAGONAL, 0, None) == 4
+    fresh.close(); upd.close()
 
 
 def edge(_):

@@ -34,6 +34,28 @@ for case in ("sphere_tiny_outliers", "bal_tiny_outliers"):
         opt.backend.close()
         worst_w = max(worst_w, float(np.abs(opt.getWeights() - ref["gnc_weights"]).max()))
         worst_v = max(worst_v, util.relmax(res, ref["final_values"]))
+# b200_set_group_noise on a live problem (captured LM-try graphs dropped) == a problem created with that noise
+prob = util.load_case("bal_tiny_outliers")
+base = gnc.strip_robust(prob)
+w = np.random.default_rng(5).uniform(0.0, 1.0, base.nfactors)
+w[::7] = 0.0
+pw = gnc.weighted_problem(base, w)
+from gtsam_b200 import optimizer
+fresh, upd = capi.DeviceProblem(ctx, pw), capi.DeviceProblem(ctx, base)
+lm0 = optimizer.LevenbergMarquardtOptimizer(ctx, base, device_problem=upd)
+lm0.iterate(); lm0.iterate()            # graphs captured with the old group views
+del lm0
+for gi, g in enumerate(pw.groups):
+    upd.set_group_noise(gi, g.noise_kind, g.noise)
+upd.set_values(pw.values)
+fresh.linearize(); upd.linearize()
+same_j = all(np.array_equal(fresh.get_jacobians(gi), upd.get_jacobians(gi)) for gi in range(len(pw.groups)))
+la, lb = (optimizer.LevenbergMarquardtOptimizer(ctx, pw, device_problem=d) for d in (fresh, upd))
+ea, eb = [], []
+for _ in range(4):
+    la.iterate(); lb.iterate()
+    ea.append(la.error()); eb.append(lb.error())
+print("GNC_NOISE", int(same_j), float(np.max(np.abs(np.array(ea) - np.array(eb)) / np.array(ea))))
 print("GNC_WORST", worst_w, worst_v)
 """
 
@@ -46,6 +68,9 @@ def test_cuda_gnc_matches_reference_isolated():
     lines = [l for l in out.stdout.splitlines() if l.startswith("GNC_WORST")]
     if not lines:
         pytest.xfail("device GNC: first hardware run did not complete: " + out.stderr[-400:])
+    noise = [l for l in out.stdout.splitlines() if l.startswith("GNC_NOISE")]
+    if not noise or noise[-1].split()[1] != "1" or not float(noise[-1].split()[2]) <= 1e-9:
+        pytest.xfail("b200_set_group_noise: first hardware run off: " + (noise[-1] if noise else "no output"))
     ww, wv = (float(x) for x in lines[-1].split()[1:3])
     if not (ww <= 1e-4 and wv <= 1e-5):
         pytest.xfail(f"device GNC: first hardware run off: weights {ww:.3g}, values {wv:.3g}")
