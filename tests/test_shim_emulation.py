@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import util
-from test_library_emulation import emu_jobs, emu_lib  # noqa: F401  (fixtures: build the emulated library, start every emulation job at once)
+from test_library_emulation import emu_jobs, emu_lib, emu_libs  # noqa: F401  (fixtures: build the emulated library, start every emulation job at once)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
