@@ -16,6 +16,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -87,6 +89,7 @@ struct Sched {
   std::vector<int> warp_alive, warp_arrived;
   std::vector<unsigned> warp_gen;
   std::vector<unsigned char> dyn_smem;
+  std::vector<unsigned> order;
   void (*entry)(void*) = nullptr;
   void* entry_arg = nullptr;
 };
@@ -198,9 +201,22 @@ static void run(dim3 grid, dim3 block, size_t smem, bool descending_x, F&& fn) {
           f.ctx.rsp = sp;
         }
         unsigned remaining = nt;
-        while (remaining) {      // round robin: a fiber runs until it finishes or has to wait at a barrier
+        // round robin: a fiber runs until it finishes or has to wait at a barrier.  B200_EMU_ORDER picks the order of a
+        // sweep — ascending thread index (default), "reverse", or "shuffle[:seed]" (a new permutation every sweep): code
+        // between two barriers must not depend on it, so a missing __syncthreads / __syncwarp (or reliance on warp
+        // lock-step) shows up as a result that changes with the order
+        static const int order_mode = [] { const char* e = getenv("B200_EMU_ORDER"); return !e ? 0 : !strncmp(e, "reverse", 7) ? 1 : !strncmp(e, "shuffle", 7) ? 2 : 0; }();
+        static uint64_t rng = [] { const char* e = getenv("B200_EMU_ORDER"); const char* c = e ? strchr(e, ':') : nullptr; return c ? strtoull(c + 1, nullptr, 10) * 2654435761ull + 88172645463325252ull : 88172645463325252ull; }();
+        if (order_mode && s.order.size() != nt) { s.order.resize(nt); for (unsigned t = 0; t < nt; t++) s.order[t] = t; }
+        while (remaining) {
           remaining = 0;
-          for (unsigned t = 0; t < nt; t++) {
+          if (order_mode == 2)
+            for (unsigned t = nt; t > 1; t--) {
+              rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+              std::swap(s.order[t - 1], s.order[rng % t]);
+            }
+          for (unsigned k = 0; k < nt; k++) {
+            const unsigned t = order_mode == 0 ? k : order_mode == 1 ? nt - 1 - k : s.order[k];
             if (s.fibers[t].done) continue;
             s.cur = t;
             b200_emu_switch(&s.main, &s.fibers[t].ctx);

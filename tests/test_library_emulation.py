@@ -14,7 +14,10 @@ processes (tests/emu/run_scenarios.py).
 
 The scenario groups run against an AddressSanitizer build of the same sources when libasan is present: device memory is
 the host heap there, so an out-of-bounds access of any kernel (global or shared memory) or of the host code is a test
-failure — the part of compute-sanitizer's memcheck that does not need the GPU."""
+failure — the part of compute-sanitizer's memcheck that does not need the GPU.  They also run with the threads of a
+block scheduled in a freshly shuffled order between barriers (B200_EMU_ORDER, tests/emu/cuda_emu_full.h): a missing
+__syncthreads / __syncwarp, or reliance on warp lock-step, changes results with the order — the emulator's stand-in for
+racecheck.  All scenarios pass in ascending, reverse and shuffled order."""
 import os
 import subprocess
 import sys
@@ -85,7 +88,10 @@ def emu_jobs(emu_libs):
     solve, the C++ parity drivers of tests/test_shim_emulation.py): about 12 CPU-minutes, 2-3 minutes on 8 cores."""
     jobs = {}
     emu_lib, asan_lib, asan_rt = emu_libs
-    genv = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LD_PRELOAD=asan_rt) if asan_lib else None
+    # threads of a block run in a freshly shuffled order between barriers (the sharded and C++ jobs below: ascending order)
+    genv = dict(os.environ, B200_EMU_ORDER="shuffle:1")
+    if asan_lib:
+        genv.update(ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LD_PRELOAD=asan_rt)
     for i, g in enumerate(GROUPS):
         jobs["group%d" % i] = subprocess.Popen([sys.executable, os.path.join(EMU, "run_scenarios.py"), asan_lib or emu_lib] + g,
                                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=genv)
