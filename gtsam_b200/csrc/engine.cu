@@ -925,7 +925,6 @@ static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const 
 // `ld` (JacobianFactors, b200_linear_create); exactly one of them is non-null.
 static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_linear_desc* ld, b200_problem** out) {
   if (!ctx || (!d && !ld) || !out) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
-  if (ld && ctx->world > 1) { set_error("linear problems are single-GPU: create them on a context without a communicator"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   b200_problem* p = new b200_problem();
@@ -1085,17 +1084,19 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     // (whitened [A|b], or the augmented information matrix) in the element-major SoA
     auto& g = p->groups[gi];
     const bool hess = gi >= ld->ngroups;
-    const int64_t count = g.count;
     const int ar = g.arity;
+    // keep only the factors this rank owns (all of them when world == 1): SURVEY 8(e), as for the typed groups below
+    g.full_count = g.count;
+    for (int64_t i = 0; i < g.full_count; i++) if (factor_owner[g.pos[i]] == rank) g.local_index.push_back(i);
+    const int64_t count = (int64_t)g.local_index.size();
+    g.count = count;
     std::vector<int> jkeys((size_t)count * ar), jslots((size_t)count * ar), jclique((size_t)count);
-    g.local_index.resize(count);
-    for (int64_t i = 0; i < count; i++) {
-      const int64_t pos = g.pos[i];
-      g.local_index[i] = i;
-      jclique[i] = S.fac_clique[pos];
+    for (int64_t li = 0; li < count; li++) {
+      const int64_t pos = g.pos[g.local_index[li]];
+      jclique[li] = S.fac_clique[pos];
       for (int a = 0; a < ar; a++) {
-        jkeys[(size_t)i * ar + a] = (int)fkeys[fptr[pos] + a];
-        jslots[(size_t)i * ar + a] = S.fac_slots[fptr[pos] + a];
+        jkeys[(size_t)li * ar + a] = (int)fkeys[fptr[pos] + a];
+        jslots[(size_t)li * ar + a] = S.fac_slots[fptr[pos] + a];
       }
     }
     g.n_nonleaf = count;
@@ -1277,6 +1278,17 @@ static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const 
   const size_t per = (size_t)g.d * g.ncols, nel = per * (size_t)g.count;
   if (!nel) return B200_OK;
   if (!Ab) { set_error("JacobianFactor group without [A|b] data"); return B200_INVALID_ARGUMENT; }
+  std::vector<double> own_Ab, own_sig;   // sharded: the caller passes the whole group, this rank stages its own factors
+  if (g.count != g.full_count) {
+    own_Ab.resize(nel);
+    for (int64_t li = 0; li < g.count; li++) memcpy(own_Ab.data() + (size_t)li * per, Ab + (size_t)g.local_index[li] * per, per * sizeof(double));
+    Ab = own_Ab.data();
+    if (sigmas) {
+      own_sig.resize((size_t)g.count * g.d);
+      for (int64_t li = 0; li < g.count; li++) memcpy(own_sig.data() + (size_t)li * g.d, sigmas + (size_t)g.local_index[li] * g.d, (size_t)g.d * sizeof(double));
+      sigmas = own_sig.data();
+    }
+  }
   double *d_stage = nullptr, *d_sig = nullptr;
   B200_CUDA(cudaMalloc((void**)&d_stage, nel * sizeof(double)));
   cudaError_t ce = cudaMemcpyAsync(d_stage, Ab, nel * sizeof(double), cudaMemcpyHostToDevice, st);
@@ -1319,7 +1331,7 @@ int b200_linear_update(b200_problem* p, int64_t gi, const double* Ab, const doub
   if (gi < 0 || gi >= (int64_t)p->groups.size() || p->groups[gi].type != B200_FACTOR_JACOBIAN) { set_error("JacobianFactor group out of range"); return B200_INVALID_ARGUMENT; }
   auto& g = p->groups[gi];
   if (sigmas)
-    for (int64_t i = 0; i < g.count * g.d; i++)
+    for (int64_t i = 0; i < g.full_count * g.d; i++)
       if (!(sigmas[i] > 0)) { set_error("sigma <= 0: Constrained noise models need QR elimination (out of scope)"); return B200_UNSUPPORTED_NOISE; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
   p->solved = p->factored = p->marg_ready = false;

@@ -126,6 +126,7 @@ struct b200_problem {
     int *d_jkeys = nullptr, *d_jslots = nullptr, *d_jclique = nullptr;   // JacobianFactor groups (see JacobianView)
     int64_t n_nonleaf = 0;   // factors NOT owned by a fused leaf clique
     std::vector<int64_t> local_index;  // index in the caller's group of every factor kept on this rank
+    int64_t full_count = 0;            // linear groups: the caller's factor count (count = this rank's share)
   };
   std::vector<Group> groups;
   // device state

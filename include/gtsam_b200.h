@@ -333,7 +333,9 @@ int b200_dl_get_state(const b200_dl* dl, double* error, double* delta, int32_t* 
  * b200_symbolic_info_get / b200_get_cliques, b200_marginal_covariance and
  * b200_joint_marginal_covariance work on it; the calls that need Values (b200_error, b200_linearize,
  * b200_try_step, b200_lm_*, b200_gn_iterate, b200_dl_*) return B200_INVALID_ARGUMENT.
- * Single GPU (a context without a communicator). */
+ * On a context with a communicator the factors are split by owning subtree exactly like the typed groups
+ * (SURVEY 8e): every rank passes the WHOLE description (and whole groups to b200_linear_update*) and keeps its
+ * share; b200_get_delta returns the rank's own view (zeros elsewhere), as for a sharded b200_problem. */
 #define B200_JACOBIAN_MAX_ARITY 8
 /* One run of JacobianFactors with the same shape (rows, arity, block widths). */
 typedef struct b200_jacobian_group {

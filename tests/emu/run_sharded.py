@@ -54,5 +54,32 @@ for prob in cases:
     del lm_sh, lm_solo
     sh.close(); solo.close()
     print("rank", rank, prob.name, "ok" if ok else "MISMATCH", "owned cliques", int((co == rank).sum()), "top", int((co == -1).sum()), flush=True)
+# the GaussianFactorGraph level, sharded the same way: JacobianFactor / HessianFactor groups split by owning subtree
+for name in ("lin_sphere_tiny", "lin_bal_tiny", "lin_random_nary", "lin_mixed_hessian", "lin_arity8"):
+    lp = util.load_linear_case(name)
+    sh, solo = capi.LinearDeviceProblem(ctx, lp), capi.LinearDeviceProblem(solo_ctx, lp)
+    rng = np.random.default_rng(11)
+    for rnd in range(2):
+        if rnd == 1:    # new numbers, same structure: every rank is handed the whole group and stages its own share
+            for gi, g in enumerate(lp.groups):
+                Ab = np.asarray(g.Ab, dtype=np.float64) * (1.0 + 0.05 * rng.standard_normal(np.asarray(g.Ab).shape))
+                for d in (sh, solo):
+                    d.update(gi, Ab, g.sigmas)
+            for hi, g in enumerate(lp.hgroups):
+                info = np.asarray(g.info, dtype=np.float64).copy()
+                info.reshape(g.count, g.ncols, g.ncols)[:, -1, :] *= 1.05     # rhs row / column and the constant
+                info.reshape(g.count, g.ncols, g.ncols)[:, :-1, -1] *= 1.05
+                for d in (sh, solo):
+                    d.update_hessian(hi, info)
+        ok &= util.relmax(sh.hessian_diagonal(), solo.hessian_diagonal()) <= 1e-12
+        for lam, diag in ((0.25, False), (1e-2, True)):
+            st, a0, a1, _ = sh.solve(lam, diag)
+            so, b0, b1, _ = solo.solve(lam, diag)
+            ok &= st == so == 0 and abs(a0 - b0) <= 1e-12 * max(1.0, b0) and abs(a1 - b1) <= 1e-9 * max(1.0, b0)
+            d_sh, d_solo = sh.get_delta(), solo.get_delta()
+            mine = d_sh != 0      # delta of the variables this rank owns or shares (the rest stays zero)
+            ok &= bool(mine.any()) and np.linalg.norm(d_sh[mine] - d_solo[mine]) <= 1e-7 * np.linalg.norm(d_solo[mine])
+    sh.close(); solo.close()
+    print("rank", rank, name, "ok" if ok else "MISMATCH", "delta entries here", int(mine.sum()), "of", mine.size, flush=True)
 print("SHARDED_OK" if ok else "SHARDED_MISMATCH", rank, world, flush=True)
 sys.exit(0 if ok else 1)

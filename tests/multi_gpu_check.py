@@ -62,6 +62,30 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_OK" if flag.item() == 1 else "MULTI_GPU_MISMATCH", "world", world)
+    # the GaussianFactorGraph level sharded the same way (written after the last 2-GPU run: reported on its own line,
+    # it does not change the verdict above until it has run on hardware once)
+    lin_ok = True
+    try:
+        import util
+        for name in ("lin_sphere_tiny", "lin_bal_tiny", "lin_random_nary", "lin_mixed_hessian"):
+            lp = util.load_linear_case(name)
+            sh, solo = capi.LinearDeviceProblem(ctx, lp), capi.LinearDeviceProblem(solo_ctx, lp)
+            lin_ok &= util.relmax(sh.hessian_diagonal(), solo.hessian_diagonal()) <= 1e-12
+            for lam, diag in ((0.25, False), (1e-2, True)):
+                st, a0, a1, _ = sh.solve(lam, diag)
+                so, b0, b1, _ = solo.solve(lam, diag)
+                lin_ok &= st == so == 0 and abs(a0 - b0) <= 1e-12 * max(1.0, b0) and abs(a1 - b1) <= 1e-9 * max(1.0, b0)
+                d_sh, d_solo = sh.get_delta(), solo.get_delta()
+                mine = d_sh != 0
+                lin_ok &= bool(mine.any()) and np.linalg.norm(d_sh[mine] - d_solo[mine]) <= 1e-7 * np.linalg.norm(d_solo[mine])
+            sh.close(); solo.close()
+    except Exception as e:     # noqa: BLE001
+        lin_ok = False
+        print("rank", rank, "linear sharded check raised:", repr(e))
+    lflag = torch.tensor([int(bool(lin_ok))], device="cuda")
+    dist.all_reduce(lflag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_LINEAR_OK" if lflag.item() == 1 else "MULTI_GPU_LINEAR_MISMATCH", "world", world)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
 
