@@ -791,8 +791,9 @@ leaf_fused_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const
 constexpr int kPtMaxObs = 8;
 
 #ifdef B200_EMULATE   // host emulation build: the asynchronous copy is a plain copy
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) { *smem_dst = *gsrc; }
+// (cp.async needs both addresses aligned to the copy size: checked here, the hardware would fault)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { if (((uintptr_t)smem_dst | (uintptr_t)gsrc) & 7) __builtin_trap(); *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) { if (((uintptr_t)smem_dst | (uintptr_t)gsrc) & 3) __builtin_trap(); *smem_dst = *gsrc; }
 __device__ __forceinline__ void cp_async_commit() {}
 #else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
