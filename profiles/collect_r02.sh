@@ -25,6 +25,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --c
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"linearize_kernel|leaf_point_factor" -s 4 -c 4 -o gpurun_out/linearize_leaf_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"linearize_kernel|leaf_point_factor|leaf_point_schur" -s 4 -c 6 -o gpurun_out/f32_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --jacobian-fp32 > /dev/null 2>&1
 ls -la gpurun_out
-# Multi-GPU follow-up (separate call, gpurun --gpus 8):
+# Multi-GPU follow-up (separate calls).  gpurun --gpus 2: sharded typed AND linear problems vs the same problems alone
+# (prints MULTI_GPU_OK and, for the GaussianFactorGraph level sharded after round 1's budget, MULTI_GPU_LINEAR_OK):
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29510 tests/multi_gpu_check.py
+# gpurun --gpus 8:
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
 #       bench.py --gpus 8 --workload bal_c5_metis --scaling strong --jacobian-fp32 --steps 50 --no-cpu-baseline
