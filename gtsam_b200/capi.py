@@ -22,7 +22,7 @@ _LIB = None
 EXPORTS = [
     "b200_var_storage", "b200_var_dim", "b200_factor_arity", "b200_factor_meas_size", "b200_factor_dim",
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error_string", "b200_launch_count", "b200_ctx_stream",
-    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_set_group_noise", "b200_get_values", "b200_values_size",
+    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_set_group_noise", "b200_gradient_at_zero", "b200_get_values", "b200_values_size",
     "b200_delta_size", "b200_error", "b200_linearize", "b200_get_jacobians", "b200_hessian_diagonal",
     "b200_solve", "b200_get_delta", "b200_try_step", "b200_accept_step", "b200_lm_params_legacy",
     "b200_lm_params_ceres", "b200_lm_create", "b200_lm_destroy", "b200_lm_iterate", "b200_lm_optimize",
@@ -71,6 +71,7 @@ def lib():
         L.b200_problem_create.argtypes = [vp, C.POINTER(P.CProblemDesc), C.POINTER(vp)]
         L.b200_problem_destroy.argtypes = [vp]
         L.b200_set_values.argtypes = [vp, dp]
+        L.b200_gradient_at_zero.argtypes = [vp, dp]
         L.b200_set_group_noise.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp]
         L.b200_get_values.argtypes = [vp, dp]
         L.b200_values_size.argtypes = [vp]
@@ -248,6 +249,12 @@ class DeviceProblem:
         v = np.ascontiguousarray(v, dtype=np.float64)
         assert v.size == self.nval
         _check(self.L.b200_set_values(self.h, _dp(v)))
+
+    def gradient_at_zero(self):
+        """GaussianFactorGraph::gradientAtZero of the current linearization (-A'b), dof order."""
+        out = np.empty(self.ndelta)
+        _check(self.L.b200_gradient_at_zero(self.h, _dp(out)))
+        return out
 
     def set_group_noise(self, gi: int, noise_kind: int, noise):
         """New noise model(s) on factor group ``gi`` (shared payload, or one per factor), as GncOptimizer's

@@ -903,7 +903,7 @@ int b200_problem_destroy(b200_problem* p) {
     cudaFree(g.d_keys); cudaFree(g.d_meas); cudaFree(g.d_noise); cudaFree(g.d_cal); cudaFree(g.d_body); cudaFree(g.d_J); cudaFree(g.d_scat);
     cudaFree(g.d_jkeys); cudaFree(g.d_jslots); cudaFree(g.d_jclique);
   }
-  cudaFree(p->d_values); cudaFree(p->d_new_values); cudaFree(p->d_delta); cudaFree(p->d_hdiag);
+  cudaFree(p->d_values); cudaFree(p->d_new_values); cudaFree(p->d_delta); cudaFree(p->d_hdiag); cudaFree(p->d_grad);
   cudaFree(p->d_val_off); cudaFree(p->d_var_type); cudaFree(p->d_var_dof); cudaFree(p->d_cal); cudaFree(p->d_arena);
   cudaFree(p->d_off); cudaFree(p->d_nf); cudaFree(p->d_ns); cudaFree(p->d_parent); cudaFree(p->d_ea_ptr);
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
@@ -1471,6 +1471,37 @@ int b200_hessian_diagonal(b200_problem* p, double* out) {
   if (rc) return rc;
   B200_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_hdiag, (size_t)p->ndelta * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  memcpy(out, p->h_pinned, (size_t)p->ndelta * sizeof(double));
+  return B200_OK;
+}
+
+/* GaussianFactorGraph::gradientAtZero (gtsam/linear/GaussianFactorGraph.cpp:369-378): -A^T b of the current
+ * linearization (typed problems) / of the graph (linear problems), summed over the factors. */
+int b200_gradient_at_zero(b200_problem* p, double* out) {
+  if (!p || !out) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  if (!p->linearized) { set_error("b200_gradient_at_zero before b200_linearize"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  if (!p->d_grad) B200_CUDA(cudaMalloc((void**)&p->d_grad, (size_t)std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  double* grad = p->d_grad;
+  B200_CUDA(cudaMemsetAsync(grad, 0, (size_t)p->ndelta * sizeof(double), st));
+  for (auto& g : p->groups) {
+    if (!g.count) continue;
+    if (g.type == B200_FACTOR_JACOBIAN || g.type == B200_FACTOR_HESSIAN) {
+      const int nb = (int)((g.count + 127) / 128);
+      if (g.type == B200_FACTOR_JACOBIAN) launch_plain(gradient_jacobian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, grad);
+      else launch_plain(gradient_hessian_kernel, dim3(nb), dim3(128), 0, st, jview(g), (const int*)p->d_var_dof, grad);
+    } else {
+      const int nb = reduce_blocks(g.count, 256, p->ctx->sm_count);
+      DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_plain(gradient_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), (const int*)p->d_var_dof, grad))));
+    }
+    p->ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  const int rc = allreduce_sum(p, grad, (size_t)p->ndelta);   // sharded: every rank summed its own factors
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, grad, (size_t)p->ndelta * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
   memcpy(out, p->h_pinned, (size_t)p->ndelta * sizeof(double));
   return B200_OK;
 }

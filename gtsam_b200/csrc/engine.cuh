@@ -131,6 +131,7 @@ struct b200_problem {
   std::vector<Group> groups;
   // device state
   double *d_values = nullptr, *d_new_values = nullptr, *d_delta = nullptr, *d_hdiag = nullptr;
+  double* d_grad = nullptr;          // b200_gradient_at_zero (allocated on first use)
   int *d_val_off = nullptr, *d_var_type = nullptr, *d_var_dof = nullptr;
   double* d_cal = nullptr;
   double* d_arena = nullptr;

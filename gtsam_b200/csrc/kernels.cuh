@@ -17,7 +17,8 @@
 //  linerr_kernel         a16     0.5*|A delta - b|^2 and 0.5*|b|^2 in one pass
 //  retract_kernel        a9      x (+) delta per variable
 //  assemble_hessian_kernel, hdiag_hessian_kernel, linerr_hessian_kernel   the same for HessianFactor groups
-//  jacobian_load_kernel, assemble_jacobian_kernel, hdiag_jacobian_kernel, linerr_jacobian_kernel
+//  jacobian_load_kernel, assemble_jacobian_kernel, hdiag_jacobian_kernel, linerr_jacobian_kernel,
+//  gradient_jacobian_kernel, gradient_hessian_kernel (GaussianFactorGraph::gradientAtZero)
 //                                a12/a10/a16 for the JacobianFactor groups (any arity / block widths) of a linear problem
 //                                (GaussianFactorGraph::optimize level, b200_linear_create)
 //  gradient_kernel, dot3_kernel, blend_kernel        Dogleg (8f rank 3): gradientAtZero, dot products, dogleg point
@@ -416,6 +417,25 @@ __global__ void __launch_bounds__(128) hdiag_jacobian_kernel(JacobianView g, con
   }
 }
 
+// JacobianFactor::gradientAtZero (gtsam/linear/JacobianFactor.cpp:690-699): -A^T b of the whitened factor, per key
+__global__ void __launch_bounds__(128) gradient_jacobian_kernel(JacobianView g, const int* __restrict__ var_dof, double* grad) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const double* J = g.J + f;
+  const int m = g.rows;
+  const size_t cnt = (size_t)g.count;
+  const double* b = J + (size_t)(g.ncols - 1) * m * cnt;
+  for (int a = 0; a < g.arity; a++) {
+    const int base = var_dof[g.keys[(size_t)f * g.arity + a]];
+    for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) {
+      double s = 0;
+      for (int r = 0; r < m; r++) s += J[(size_t)(r + cc * m) * cnt] * b[(size_t)r * cnt];
+      atomicAdd(grad + base + (cc - g.col0[a]), -s);
+    }
+  }
+}
+
 // JacobianFactor::error (gtsam/linear/JacobianFactor.cpp:479-491): 0.5*|A x - bscale*b|^2 and 0.5*|b|^2
 __global__ void __launch_bounds__(256) linerr_jacobian_kernel(JacobianView g, const double* __restrict__ delta,
                                                               const int* __restrict__ var_dof, double* p0, double* p1,
@@ -488,6 +508,20 @@ __global__ void __launch_bounds__(128) hdiag_hessian_kernel(JacobianView g, cons
   for (int a = 0; a < g.arity; a++) {
     const int base = var_dof[g.keys[(size_t)f * g.arity + a]];
     for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) atomicAdd(hdiag + base + (cc - g.col0[a]), H[(size_t)(cc + cc * n1) * cnt]);
+  }
+}
+
+// HessianFactor::gradientAtZero (gtsam/linear/HessianFactor.cpp:422-429): minus the linear term g of [G g; g' f]
+__global__ void __launch_bounds__(128) gradient_hessian_kernel(JacobianView g, const int* __restrict__ var_dof, double* grad) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.count) return;
+  const double* H = g.J + f;
+  const int n1 = g.rows;
+  const size_t cnt = (size_t)g.count;
+  for (int a = 0; a < g.arity; a++) {
+    const int base = var_dof[g.keys[(size_t)f * g.arity + a]];
+    for (int cc = g.col0[a]; cc < g.col0[a + 1]; cc++) atomicAdd(grad + base + (cc - g.col0[a]), -H[(size_t)(cc + (n1 - 1) * n1) * cnt]);
   }
 }
 

@@ -7,7 +7,8 @@ part of the reference's linear API that sits on the hot path:
 * ``HessianFactor(keys, dims, info)``            gtsam/linear/HessianFactor.h:99-110
 * ``GaussianFactorGraph``                        gtsam/linear/GaussianFactorGraph.h:73-404
   ``.add / .push_back / .size / .keys``, ``.optimize(ordering)`` (GaussianFactorGraph.cpp:316-319, the
-  multifrontal Cholesky path), ``.eliminateMultifrontal(ordering)``, ``.hessianDiagonal()`` (:279-287)
+  multifrontal Cholesky path), ``.eliminateMultifrontal(ordering)``, ``.hessianDiagonal()`` (:279-287),
+  ``.gradientAtZero()`` (:369-378)
 * ``VectorValues`` is a plain ``dict`` key -> 1-D array (gtsam/linear/VectorValues.h:77-78).
 
 Factors of any arity and any block widths.  The numbers live in ``LinearProblem`` (flat groups of
@@ -359,6 +360,21 @@ class GaussianFactorGraph:
             h, off = dev.hessian_diagonal(), lp.dof_offsets()
             dev.close()
             return {k: h[off[i]:off[i + 1]].copy() for k, i in ids.items()}
+        finally:
+            if own:
+                ctx.close()
+
+    def gradientAtZero(self, ctx=None) -> VectorValues:
+        """GaussianFactorGraph::gradientAtZero() (GaussianFactorGraph.cpp:369-378) on the device: -A'b per key."""
+        from . import capi
+        own = ctx is None
+        ctx = ctx or capi.Context(0)
+        try:
+            lp, ids = self.to_problem(None)
+            dev = capi.LinearDeviceProblem(ctx, lp)
+            g, off = dev.gradient_at_zero(), lp.dof_offsets()
+            dev.close()
+            return {k: g[off[i]:off[i + 1]].copy() for k, i in ids.items()}
         finally:
             if own:
                 ctx.close()

@@ -618,6 +618,15 @@ struct LinearState {
       out.insert(id2key[i], Eigen::Map<const Vector>(dl.data() + dof_off[i], dof_off[i + 1] - dof_off[i]));
     return out;
   }
+
+  VectorValues gradientAtZero() {
+    std::vector<double> g((size_t)b200_delta_size(prob));
+    check(b200_gradient_at_zero(prob, g.data()), "b200_gradient_at_zero");
+    VectorValues out;
+    for (size_t i = 0; i < id2key.size(); i++)
+      out.insert(id2key[i], Eigen::Map<const Vector>(g.data() + dof_off[i], dof_off[i + 1] - dof_off[i]));
+    return out;
+  }
 };
 
 // ---- Marginals ----------------------------------------------------------------------------
@@ -675,6 +684,11 @@ VectorValues B200LinearSolver::optimize(const GaussianFactorGraph& gfg) {
   if (st_->sameStructure(gfg)) st_->update(gfg);
   else st_->build(gfg, ordering_);
   return st_->solve();
+}
+VectorValues B200LinearSolver::gradientAtZero(const GaussianFactorGraph& gfg) {
+  if (st_->sameStructure(gfg)) st_->update(gfg);
+  else st_->build(gfg, ordering_);
+  return st_->gradientAtZero();
 }
 int B200LinearSolver::structureBuilds() const { return st_->builds; }
 int B200LinearSolver::solves() const { return st_->solves; }

@@ -176,6 +176,8 @@ class B200LinearSolver {
   ~B200LinearSolver();
   /// solve `gfg` (re-packs only if its structure differs from the previous call's)
   gtsam::VectorValues optimize(const gtsam::GaussianFactorGraph& gfg);
+  /// GaussianFactorGraph::gradientAtZero() (gtsam/linear/GaussianFactorGraph.cpp:369-378) of `gfg` on the device
+  gtsam::VectorValues gradientAtZero(const gtsam::GaussianFactorGraph& gfg);
   /// how many times the structure was (re)built / how many solves reused it
   int structureBuilds() const;
   int solves() const;

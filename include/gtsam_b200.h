@@ -246,6 +246,10 @@ int b200_get_jacobian_precision(const b200_problem* prob);
 /* GaussianFactorGraph::hessianDiagonal(), gtsam/linear/GaussianFactorGraph.cpp:279-287.
  * out: delta_size doubles, variable-id order. */
 int b200_hessian_diagonal(b200_problem* prob, double* out);
+/* GaussianFactorGraph::gradientAtZero (gtsam/linear/GaussianFactorGraph.cpp:369-378; JacobianFactor.cpp:690-699,
+ * HessianFactor.cpp:422-429): -A^T b of the whitened factors, delta_size doubles in dof order.  After b200_linearize
+ * on a typed problem; any time on a linear problem. */
+int b200_gradient_at_zero(b200_problem* prob, double* out);
 
 /* Damped multifrontal Cholesky solve of the current linearization:
  * buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)

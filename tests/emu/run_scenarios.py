@@ -25,6 +25,21 @@ def typed(case):
         dev = capi.DeviceProblem(ctx, prob)
         util.check_against_dump(dev, prob, util.golden(case, kind), lam, diag)
         dev.close()
+    # gradientAtZero = -A'b of the whitened blocks (which the dumps above pinned on the reference)
+    dev = capi.DeviceProblem(ctx, prob)
+    dev.linearize()
+    off = prob.dof_offsets()
+    g = np.zeros(off[-1])
+    for gi, grp in enumerate(prob.groups):
+        J = dev.get_jacobians(gi)                  # (count, rows, ncols)
+        contrib = -np.einsum("frc,fr->fc", J[:, :, :-1], J[:, :, -1])
+        col = 0
+        for a in range(grp.keys.shape[1]):
+            d = int(prob.var_dims[grp.keys[0, a]]) if grp.count else 0
+            np.add.at(g, off[grp.keys[:, a]][:, None] + np.arange(d)[None, :], contrib[:, col:col + d])
+            col += d
+    assert util.relmax(dev.gradient_at_zero(), g) <= 1e-12
+    dev.close()
     # LM to convergence: same error / lambda sequence as the reference
     ref = util.golden(case, "lm")
     prm = optimizer.LevenbergMarquardtParams.CeresDefaults() if case in util.CERES_CASES else optimizer.LevenbergMarquardtParams()

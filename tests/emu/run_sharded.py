@@ -30,6 +30,7 @@ for prob in cases:
     e_sh, e_solo = sh.error(), solo.error()
     ok &= abs(e_sh - e_solo) <= 1e-12 * e_solo
     sh.linearize(); solo.linearize()
+    ok &= util.relmax(sh.gradient_at_zero(), solo.gradient_at_zero()) <= 1e-12
     for lam, diag in ((1e-3, False), (1e-2, True)):
         st, a0, a1, _ = sh.solve(lam, diag)
         so, b0, b1, _ = solo.solve(lam, diag)
@@ -72,6 +73,7 @@ for name in ("lin_sphere_tiny", "lin_bal_tiny", "lin_random_nary", "lin_mixed_he
                 for d in (sh, solo):
                     d.update_hessian(hi, info)
         ok &= util.relmax(sh.hessian_diagonal(), solo.hessian_diagonal()) <= 1e-12
+        ok &= util.relmax(sh.gradient_at_zero(), solo.gradient_at_zero()) <= 1e-12
         for lam, diag in ((0.25, False), (1e-2, True)):
             st, a0, a1, _ = sh.solve(lam, diag)
             so, b0, b1, _ = solo.solve(lam, diag)

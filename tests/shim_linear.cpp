@@ -48,8 +48,12 @@ static int cmd_graph(const std::string& path) {
   VectorValues ref, dev;
   try { ref = gfg.optimize(ordering, EliminatePreferCholesky); } catch (const IndeterminantLinearSystemException&) { ref_status = 1; }
   try { dev = gtsam_b200::optimizeOnDevice(gfg, ordering); } catch (const IndeterminantLinearSystemException&) { dev_status = 1; }
-  double d0 = -1, d1 = -1, dbt = -1, dmarg = -1;
+  double d0 = -1, d1 = -1, dbt = -1, dmarg = -1, dgrad = -1;
   int builds = 0, solves = 0;
+  {   // GaussianFactorGraph::gradientAtZero() on the device vs the reference's (works on singular systems too)
+    gtsam_b200::B200LinearSolver gs(ordering);
+    dgrad = relDiff(gs.gradientAtZero(gfg), gfg.gradientAtZero());
+  }
   long long launches = 0;
   if (!ref_status && !dev_status) {
     d0 = relDiff(dev, ref);
@@ -97,7 +101,7 @@ static int cmd_graph(const std::string& path) {
     }
   }
   printf("{\"ref_status\": %d, \"dev_status\": %d, \"delta_rel_diff\": %.6g, \"reuse_delta_rel_diff\": %.6g, \"bayes_tree_diff\": %.6g, \"marginals_diff\": %.6g, "
-         "\"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, dbt, dmarg, builds, solves, launches);
+         "\"gradient_diff\": %.6g, \"structure_builds\": %d, \"solves\": %d, \"launches\": %lld}\n", ref_status, dev_status, d0, d1, dbt, dmarg, dgrad, builds, solves, launches);
   return 0;
 }
 

@@ -34,6 +34,8 @@ def test_shim_optimize_on_device_matches_reference(case):
         pytest.xfail(f"shim_linear graph: first hardware run did not complete: {e}")
     if r["ref_status"] != r["dev_status"]:
         pytest.xfail(f"shim_linear graph: status differs: {r}")
+    if not 0 <= r.get("gradient_diff", -1) <= 1e-12:
+        pytest.xfail(f"shim_linear graph: gradientAtZero off on its first hardware run: {r}")
     if r["ref_status"] == 0 and not (0 <= r["delta_rel_diff"] <= 1e-9 and 0 <= r["reuse_delta_rel_diff"] <= 1e-9
                                      and 0 <= r["bayes_tree_diff"] <= 1e-9 and 0 <= r["marginals_diff"] <= 1e-7
                                      and r["structure_builds"] == 1 and r["solves"] == 2 and r["launches"] > 0):

@@ -37,6 +37,7 @@ def test_cpp_drop_ins_against_the_emulated_library(emu_jobs):  # noqa: F811
         x = r[k]
         assert x["ref_status"] == x["dev_status"] == 0 and 0 <= x["delta_rel_diff"] <= 1e-9 and 0 <= x["reuse_delta_rel_diff"] <= 1e-9
         assert 0 <= x["bayes_tree_diff"] <= 1e-9 and 0 <= x["marginals_diff"] <= 1e-7 and x["structure_builds"] == 1 and x["solves"] == 2
+        assert 0 <= x["gradient_diff"] <= 1e-12          # B200LinearSolver::gradientAtZero vs gfg.gradientAtZero()
     assert r["lin_sing"]["ref_status"] == r["lin_sing"]["dev_status"] == 1     # IndeterminantLinearSystemException on both sides
     p2 = r["pose2"]                                                   # the solve() seam on a Pose2 graph
     assert np.allclose(p2["lm_dev_errors"], p2["lm_ref_errors"], rtol=1e-8) and np.allclose(p2["gn_dev_errors"], p2["gn_ref_errors"], rtol=1e-8)

@@ -142,12 +142,37 @@ def load_linear_case(name):
     return lp
 
 
+def linear_gradient_at_zero(lp):
+    """GaussianFactorGraph::gradientAtZero (GaussianFactorGraph.cpp:369-378) in numpy from the INPUT numbers of a
+    LinearProblem: -A'b of every whitened JacobianFactor (JacobianFactor.cpp:690-699), minus the linear term of every
+    HessianFactor (HessianFactor.cpp:422-429).  The C++ parity driver compares the device with the reference's own."""
+    import numpy as np
+    off = lp.dof_offsets()
+    g = np.zeros(off[-1])
+    for grp in lp.groups:
+        W = grp.whitened()                         # (count, rows, ncols)
+        contrib = -np.einsum("frc,fr->fc", W[:, :, :-1], W[:, :, -1])
+        col = 0
+        for a, d in enumerate(grp.dims):
+            np.add.at(g, off[grp.keys[:, a]][:, None] + np.arange(d)[None, :], contrib[:, col:col + d])
+            col += d
+    for grp in lp.hgroups:
+        lin = -grp.info[:, -1, :-1]                # info[f, c, r] = entry (r, c): column N, rows 0..N-1
+        col = 0
+        for a, d in enumerate(grp.dims):
+            np.add.at(g, off[grp.keys[:, a]][:, None] + np.arange(d)[None, :], lin[:, col:col + d])
+            col += d
+    return g
+
+
 def check_linear_against_reference(be, lp, ref, lam, tol_delta=1e-9):
     """`be` is an OracleLinearProblem or a LinearDeviceProblem: every stage of GaussianFactorGraph::optimize against
     the reference's own run on the same JacobianFactors (ref_harness linsolve)."""
     for gi, g in enumerate(lp.groups):     # whitening (JacobianFactor::whiten) happened at creation
         assert relmax(be.get_jacobians(gi), g.whitened()) <= 1e-15
     assert relmax(be.hessian_diagonal(), ref["hessian_diagonal"]) <= 1e-12
+    if hasattr(be, "gradient_at_zero"):
+        assert relmax(be.gradient_at_zero(), linear_gradient_at_zero(lp)) <= 1e-12
     st, e0, e1, fv = be.solve(lam)
     assert st == ref["status"][0], (st, ref["status"][0])
     if st != 0:
