@@ -22,7 +22,7 @@ _LIB = None
 EXPORTS = [
     "b200_var_storage", "b200_var_dim", "b200_factor_arity", "b200_factor_meas_size", "b200_factor_dim",
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error_string", "b200_launch_count", "b200_ctx_stream",
-    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_set_group_noise", "b200_gradient_at_zero", "b200_get_values", "b200_values_size",
+    "b200_problem_create", "b200_problem_destroy", "b200_set_values", "b200_set_group_noise", "b200_gradient_at_zero", "b200_linear_graph_error", "b200_get_values", "b200_values_size",
     "b200_delta_size", "b200_error", "b200_linearize", "b200_get_jacobians", "b200_hessian_diagonal",
     "b200_solve", "b200_get_delta", "b200_try_step", "b200_accept_step", "b200_lm_params_legacy",
     "b200_lm_params_ceres", "b200_lm_create", "b200_lm_destroy", "b200_lm_iterate", "b200_lm_optimize",
@@ -72,6 +72,7 @@ def lib():
         L.b200_problem_destroy.argtypes = [vp]
         L.b200_set_values.argtypes = [vp, dp]
         L.b200_gradient_at_zero.argtypes = [vp, dp]
+        L.b200_linear_graph_error.argtypes = [vp, dp, dp]
         L.b200_set_group_noise.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp]
         L.b200_get_values.argtypes = [vp, dp]
         L.b200_values_size.argtypes = [vp]
@@ -255,6 +256,14 @@ class DeviceProblem:
         out = np.empty(self.ndelta)
         _check(self.L.b200_gradient_at_zero(self.h, _dp(out)))
         return out
+
+    def linear_graph_error(self, x):
+        """GaussianFactorGraph::error(x) of the current linearization / of a linear problem's graph; x in dof order."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.ndelta
+        e = C.c_double()
+        _check(self.L.b200_linear_graph_error(self.h, _dp(x), C.cast(C.byref(e), C.POINTER(C.c_double))))
+        return e.value
 
     def set_group_noise(self, gi: int, noise_kind: int, noise):
         """New noise model(s) on factor group ``gi`` (shared payload, or one per factor), as GncOptimizer's

@@ -1506,6 +1506,27 @@ int b200_gradient_at_zero(b200_problem* p, double* out) {
   return B200_OK;
 }
 
+static int enqueue_linerr_of(b200_problem* p, const double* x, double bscale, double* out);
+/* GaussianFactorGraph::error(x) (gtsam/linear/GaussianFactorGraph.cpp:71-78): sum of 0.5 |A x - b|^2 (JacobianFactor.cpp:479-491)
+ * and 0.5 (f - 2 x'g + x'G x) (HessianFactor.cpp:331-346) at the caller's x. */
+int b200_linear_graph_error(b200_problem* p, const double* x, double* err) {
+  if (!p || !x || !err) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  if (!p->linearized) { set_error("b200_linear_graph_error before b200_linearize"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  if (!p->d_grad) B200_CUDA(cudaMalloc((void**)&p->d_grad, (size_t)std::max<int64_t>(1, p->ndelta) * sizeof(double)));
+  memcpy(p->h_pinned, x, (size_t)p->ndelta * sizeof(double));
+  B200_CUDA(cudaMemcpyAsync(p->d_grad, p->h_pinned, (size_t)p->ndelta * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = enqueue_linerr_of(p, p->d_grad, 1.0, &p->d_scalars->graph_err);
+  if (rc) return rc;
+  rc = allreduce_sum(p, &p->d_scalars->graph_err, 1);   // sharded: every rank summed its own factors
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(p->h_pinned, &p->d_scalars->graph_err, sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  *err = p->h_pinned[0];
+  return B200_OK;
+}
+
 int b200_solve(b200_problem* p, double lambda, int diagonal, double min_diag, double max_diag, double* e0, double* e1,
                int64_t* fail_var) {
   if (!p->linearized) { set_error("b200_solve before b200_linearize"); return B200_INVALID_ARGUMENT; }
@@ -1991,6 +2012,13 @@ static int enqueue_linerr_of(b200_problem* p, const double* x, double bscale, do
     const int nb = reduce_blocks(g.count, 256, ctx->sm_count);
     double* p0 = p->d_partials;
     double* p1 = p->d_partials + p->partial_cap / 2;
+    if (g.type == B200_FACTOR_JACOBIAN)
+      launch_k(linerr_jacobian_kernel, dim3(nb), dim3(256), 0, st, jview(g), x, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1, &p->d_scalars->dl_scratch, out,
+               first ? 0 : 1, bscale);
+    else if (g.type == B200_FACTOR_HESSIAN)
+      launch_k(linerr_hessian_kernel, dim3(nb), dim3(256), 0, st, jview(g), x, (const int*)p->d_var_dof, p0, p1, p->d_counters + 1, &p->d_scalars->dl_scratch, out,
+               first ? 0 : 1, bscale);
+    else
     DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linerr_kernel<TY, JT>, dim3(nb), dim3(256), 0, st, view(g), x, p->d_var_dof, p0, p1, p->d_counters + 1,
                                     &p->d_scalars->dl_scratch, out, first ? 0 : 1, bscale))));
     ctx->launches += 1;

@@ -75,6 +75,7 @@ struct Scalars {           // device scalars fetched once per LM try
   double dl_dots[3];       // Dogleg: g.g, g.dx_n, dx_n.dx_n
   double dl_half_Ag2;      // Dogleg: 0.5*|A g|^2
   double dl_scratch;       // second output slot of linerr_kernel when only one is wanted
+  double graph_err;        // b200_linear_graph_error: GaussianFactorGraph::error(x)
 };
 
 struct LevelPlan {

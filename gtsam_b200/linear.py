@@ -8,7 +8,7 @@ part of the reference's linear API that sits on the hot path:
 * ``GaussianFactorGraph``                        gtsam/linear/GaussianFactorGraph.h:73-404
   ``.add / .push_back / .size / .keys``, ``.optimize(ordering)`` (GaussianFactorGraph.cpp:316-319, the
   multifrontal Cholesky path), ``.eliminateMultifrontal(ordering)``, ``.hessianDiagonal()`` (:279-287),
-  ``.gradientAtZero()`` (:369-378)
+  ``.gradientAtZero()`` (:369-378), ``.error(x)`` (:71-78)
 * ``VectorValues`` is a plain ``dict`` key -> 1-D array (gtsam/linear/VectorValues.h:77-78).
 
 Factors of any arity and any block widths.  The numbers live in ``LinearProblem`` (flat groups of
@@ -360,6 +360,25 @@ class GaussianFactorGraph:
             h, off = dev.hessian_diagonal(), lp.dof_offsets()
             dev.close()
             return {k: h[off[i]:off[i + 1]].copy() for k, i in ids.items()}
+        finally:
+            if own:
+                ctx.close()
+
+    def error(self, x: VectorValues, ctx=None) -> float:
+        """GaussianFactorGraph::error(x) (GaussianFactorGraph.cpp:71-78) on the device."""
+        from . import capi
+        own = ctx is None
+        ctx = ctx or capi.Context(0)
+        try:
+            lp, ids = self.to_problem(None)
+            off = lp.dof_offsets()
+            v = np.zeros(off[-1])
+            for k, i in ids.items():
+                v[off[i]:off[i + 1]] = np.asarray(x[k], dtype=np.float64)
+            dev = capi.LinearDeviceProblem(ctx, lp)
+            e = dev.linear_graph_error(v)
+            dev.close()
+            return e
         finally:
             if own:
                 ctx.close()

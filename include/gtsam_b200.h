@@ -250,6 +250,9 @@ int b200_hessian_diagonal(b200_problem* prob, double* out);
  * HessianFactor.cpp:422-429): -A^T b of the whitened factors, delta_size doubles in dof order.  After b200_linearize
  * on a typed problem; any time on a linear problem. */
 int b200_gradient_at_zero(b200_problem* prob, double* out);
+/* GaussianFactorGraph::error(x) (gtsam/linear/GaussianFactorGraph.cpp:71-78) at the caller's x (delta_size doubles, dof
+ * order): of the graph of a linear problem, or of the current linearization of a typed one. */
+int b200_linear_graph_error(b200_problem* prob, const double* x, double* error);
 
 /* Damped multifrontal Cholesky solve of the current linearization:
  * buildDampedSystem (gtsam/nonlinear/internal/LevenbergMarquardtState.h:125-156)

@@ -146,6 +146,11 @@ def linear_mirror(_):
     assert np.allclose(np.concatenate([x[5], x[9]]), sol, atol=1e-12)
     bt = gfg.eliminateMultifrontal([5, 9], ctx)
     assert len(bt) >= 1 and bt[-1][2] == -1
+    g = gfg.gradientAtZero(ctx)
+    assert np.allclose(np.concatenate([g[5], g[9]]), -A.T @ b, atol=1e-12)
+    xt = {5: np.array([0.3, -0.2]), 9: np.array([1.5, 0.25])}
+    r = A @ np.concatenate([xt[5], xt[9]]) - b
+    assert abs(gfg.error(xt, ctx) - 0.5 * r @ r) <= 1e-12
 
 
 def gnc_scenario(case):

@@ -74,6 +74,8 @@ for name in ("lin_sphere_tiny", "lin_bal_tiny", "lin_random_nary", "lin_mixed_he
                     d.update_hessian(hi, info)
         ok &= util.relmax(sh.hessian_diagonal(), solo.hessian_diagonal()) <= 1e-12
         ok &= util.relmax(sh.gradient_at_zero(), solo.gradient_at_zero()) <= 1e-12
+        xr = rng.standard_normal(sh.ndelta)
+        ok &= abs(sh.linear_graph_error(xr) - solo.linear_graph_error(xr)) <= 1e-12 * solo.linear_graph_error(xr)
         for lam, diag in ((0.25, False), (1e-2, True)):
             st, a0, a1, _ = sh.solve(lam, diag)
             so, b0, b1, _ = solo.solve(lam, diag)

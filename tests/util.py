@@ -181,6 +181,10 @@ def check_linear_against_reference(be, lp, ref, lam, tol_delta=1e-9):
     assert rel2(be.get_delta(), ref["delta"]) <= tol_delta
     assert abs(e0 - ref["linear_error_zero"][0]) <= 1e-11 * abs(ref["linear_error_zero"][0])
     assert abs(e1 - ref["linear_error_delta"][0]) <= 1e-9 * abs(ref["linear_error_zero"][0])
+    if hasattr(be, "linear_graph_error"):   # GaussianFactorGraph::error(x) vs the reference's gfg.error(0), gfg.error(delta)
+        import numpy as np
+        assert abs(be.linear_graph_error(np.zeros(be.ndelta)) - ref["linear_error_zero"][0]) <= 1e-11 * abs(ref["linear_error_zero"][0])
+        assert abs(be.linear_graph_error(be.get_delta()) - ref["linear_error_delta"][0]) <= 1e-9 * abs(ref["linear_error_zero"][0])
     check_tree_against_dump(be, lp, ref)
 
 
