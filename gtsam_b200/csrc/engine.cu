@@ -125,6 +125,7 @@ static const bool g_use_pdl = getenv("B200_NO_PDL") == nullptr;
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
   // ascending blockIdx.x is dependency-safe: backsub_large_kernel's row blocks only wait (flags) on lower block ids
+  b200_emu::count_launch((const void*)kernel);   // B200_EMU_TRACE_FILE: which kernels the scenarios reach
   b200_emu::run(grid, block, smem, false, [&]() { kernel(KArgs(args)...); });
 }
 template <typename... KArgs, typename... Args>
@@ -279,8 +280,10 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (kd == (DC_ == 6 ? 1 : 2) && tpt == T_ && p->schur_pb == P_)                                                                \
         DISPATCH_JT(p, launch_k(leaf_point_schur_kernel<DC_, T_, P_, JT>, dim3(nr), dim3(thr), 0, st, t, gt, (const int*)p->d_fused_list, runs, \
                  (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac));
-      B200_LAUNCH_SCHUR(6, 1, 4) B200_LAUNCH_SCHUR(6, 2, 4) B200_LAUNCH_SCHUR(6, 3, 4)
-      B200_LAUNCH_SCHUR(6, 1, 6) B200_LAUNCH_SCHUR(6, 2, 6) B200_LAUNCH_SCHUR(6, 3, 6)
+      // (6-dof cameras: at most kPtMaxObs * 6 + 1 = 49 columns = 153 tiles = 2 per thread; 9-dof: 73 columns = 325 tiles = 3)
+      if (tpt > (kd == 1 ? 2 : 3)) { set_error("leaf_point_schur_kernel: separator wider than the compiled tile counts"); return B200_CUDA_ERROR; }
+      B200_LAUNCH_SCHUR(6, 1, 4) B200_LAUNCH_SCHUR(6, 2, 4)
+      B200_LAUNCH_SCHUR(6, 1, 6) B200_LAUNCH_SCHUR(6, 2, 6)
       B200_LAUNCH_SCHUR(9, 1, 4) B200_LAUNCH_SCHUR(9, 2, 4) B200_LAUNCH_SCHUR(9, 3, 4)
       B200_LAUNCH_SCHUR(9, 1, 6) B200_LAUNCH_SCHUR(9, 2, 6) B200_LAUNCH_SCHUR(9, 3, 6)
 #undef B200_LAUNCH_SCHUR

@@ -16,7 +16,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
+#include <map>
 #include <utility>
 #include <cstring>
 #include <type_traits>
@@ -225,5 +228,27 @@ static void run(dim3 grid, dim3 block, size_t smem, bool descending_x, F&& fn) {
         }
       }
 }
+inline std::map<const void*, long>*& counts_ptr() { static std::map<const void*, long>* p = nullptr; return p; }
 inline void* dyn_smem() { return sched().dyn_smem.data(); }
+// kernel coverage of the emulated scenarios: with B200_EMU_TRACE_FILE set, every process appends "<mangled name> <launches>"
+// lines at exit (tests/emu/kernel_coverage.py compares them with the kernels of the GPU build)
+inline void count_launch(const void* fn) {
+  static const char* path = getenv("B200_EMU_TRACE_FILE");
+  if (!path) return;
+  static std::map<const void*, long>* counts = [] {
+    auto* m = new std::map<const void*, long>();
+    atexit([] {
+      FILE* f = fopen(getenv("B200_EMU_TRACE_FILE"), "a");
+      if (!f) return;
+      for (auto& kv : *counts_ptr()) {
+        Dl_info info;
+        fprintf(f, "%s %ld\n", dladdr(kv.first, &info) && info.dli_sname ? info.dli_sname : "?", kv.second);
+      }
+      fclose(f);
+    });
+    return m;
+  }();
+  counts_ptr() = counts;
+  (*counts)[fn]++;
+}
 }  // namespace b200_emu

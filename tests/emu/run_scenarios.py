@@ -263,7 +263,7 @@ def midsize(model):
     the same mode; then two LM iterations."""
     from gtsam_b200 import datasets
     model, _, obs = model.partition("@")     # e.g. bundler@8: 8 observations per point -> 3 tiles per thread in the Schur kernel
-    prob = datasets.make("bal_tiny", ncams=12, npoints=1500 if not obs else 400, visibility="banded", camera_model=model,
+    prob = datasets.make("bal_tiny", ncams=30, npoints=1500 if not obs else 400, visibility="banded", camera_model=model,   # (30 cameras: the band (start + 3k) mod n holds distinct cameras)
                          obs_per_point=int(obs or 6))
     for f32, pb in ((False, 4), (True, 4), (False, 6), (True, 6)):
         # (run length is sized from the SM count; at this size it would be 1, so it is forced)
@@ -286,7 +286,48 @@ def midsize(model):
         dev.close()
 
 
-SCEN = dict(midsize=midsize, edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
+def coverage(_):
+    """Kernel instantiations no fixture reaches (tests/emu/kernel_coverage.py): PriorFactor<Point3> outside the fused
+    leaves (points ordered LAST, so their cliques are interior), Dogleg with FP32 Jacobian storage on every factor family
+    (gradient_kernel<T, float>), the separate extend-add of the large fronts (B200_NO_FUSE_EA)."""
+    from gtsam_b200 import datasets
+    b = datasets.make("bal_tiny", ncams=8, npoints=40, visibility="scattered")
+    pts = np.where(b.var_type == P.VAR_POINT3)[0][:10]
+    off = b.val_offsets()
+    meas = np.stack([b.values[off[v]:off[v] + 3] + 0.01 for v in pts])
+    pri = P.FactorGroup(P.FACTOR_PRIOR_POINT3, pts[:, None], meas, P.NOISE_DIAGONAL, np.array([0.1, 0.2, 0.3]))
+    cams_first = np.concatenate([np.where(b.var_type != P.VAR_POINT3)[0], np.where(b.var_type == P.VAR_POINT3)[0]])
+    pp = P.Problem(b.var_type, b.values, cams_first, list(b.groups) + [pri], cal=b.cal)
+    cases = [pp, util.load_case("sphere_tiny"), util.load_case("bal_tiny_s2"), util.load_case("bal_tiny_bundler"), util.load_case("pose2_ring")]
+    for prob in cases:
+        for f32 in (False, True):
+            dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+            dev.set_jacobian_precision(f32); orc.set_jacobian_precision(f32)
+            dev.linearize(); orc.linearize()
+            assert util.relmax(dev.hessian_diagonal(), orc.hessian_diagonal()) <= 1e-12
+            st, e0, e1, _ = dev.solve(1e-2, True)
+            so, f0, f1, _ = orc.solve(1e-2, True)
+            assert st == so == 0 and util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+            assert abs(e0 - f0) <= 1e-11 * f0 and abs(e1 - f1) <= 1e-9 * f0
+            dl = optimizer.DoglegOptimizer(ctx, prob, device_problem=dev)
+            err, rad = orc.error(), 1.0
+            for _ in range(3):
+                dl.iterate()
+                so, err, rad = orc.dogleg_iterate(err, rad)
+                assert so == 0 and abs(dl.error() - err) <= 1e-7 * err and abs(dl.getDelta() - rad) <= 1e-9 * rad, (prob.name, f32, dl.error(), err, dl.getDelta(), rad)
+            del dl
+            dev.close()
+    os.environ["B200_NO_FUSE_EA"] = "1"
+    try:
+        prob = util.load_case("sphere_small_colamd")
+        dev = capi.DeviceProblem(ctx, prob)
+        util.check_against_dump(dev, prob, util.golden("sphere_small_colamd", "dump1"), 1e-2, 1)
+        dev.close()
+    finally:
+        os.environ.pop("B200_NO_FUSE_EA")
+
+
+SCEN = dict(coverage=coverage, midsize=midsize, edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)
 for arg in sys.argv[2:]:
     kind, case = arg.split(":")
     t = time.time()

@@ -38,11 +38,12 @@ GROUPS = [
     ["typed:sphere_small_colamd", "typed:sphere_tiny_cauchy"],
     ["typed:sphere_small_metis", "typed:sphere_tiny_huber", "typed:dubrovnik_3_7_unit", "typed:dubrovnik_3_7_priors"],
     # FP32-storage mode (float instantiations, cp.async staging of floats in the point-leaf Schur kernel)
-    ["fp32:bal_tiny_s2", "fp32:bal_tiny_bundler", "fp32:bal_small_metis", "fp32:sphere_tiny_gaussian", "fp32:pose2_ring",
+    ["fp32:bal_tiny_s2", "fp32:bal_tiny_bundler", "fp32:bal_small_metis", "fp32:sphere_tiny_gaussian", "fp32:pose2_ring", "fp32:pose2_ring_colamd",
      "marginals:bal_tiny_s2", "marginals:sphere_tiny", "marginals:bal_tiny_bundler", "marginals:pose2_ring"],
     # degenerate shapes + API misuse; the big-panel scheme (DMMA fragment layout emulated) forced onto mid-size fronts
     # ... and long runs of points per CTA (several cp.async batches, both batch sizes, 2 and 3 tiles per thread) in both storage modes
-    ["edge:x", "midsize:cal3_s2", "midsize:bundler", "midsize:bundler@8", "midsize:cal3_s2@10", "bigfront:x"],
+    # coverage: instantiations no fixture reaches (tests/emu/kernel_coverage.py lists what is left)
+    ["edge:x", "coverage:x", "midsize:cal3_s2", "midsize:bundler", "midsize:bundler@8", "midsize:cal3_s2@8", "midsize:bundler@4", "bigfront:x"],
     # the GaussianFactorGraph level, Dogleg, Gauss-Newton
     ["linear:" + c for c in ("lin_pose2_toy", "lin_pose2_synth", "lin_random_nary", "lin_mixed_hessian", "lin_arity8", "lin_sphere_tiny",
                              "lin_bal_tiny", "lin_singular", "lin_family_sfm2", "lin_family_smart", "lin_family_expr")] +
@@ -89,7 +90,10 @@ def emu_jobs(emu_libs):
     jobs = {}
     emu_lib, asan_lib, asan_rt = emu_libs
     # threads of a block run in a freshly shuffled order between barriers (the sharded and C++ jobs below: ascending order)
-    genv = dict(os.environ, B200_EMU_ORDER="shuffle:1")
+    trace = os.path.join(os.path.dirname(emu_lib), "kernel_trace_%d.txt" % os.getpid())   # B200_EMU_TRACE_FILE: kernel launch counts
+    if os.path.exists(trace):
+        os.unlink(trace)
+    genv = dict(os.environ, B200_EMU_ORDER="shuffle:1", B200_EMU_TRACE_FILE=trace)
     if asan_lib:
         genv.update(ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LD_PRELOAD=asan_rt)
     for i, g in enumerate(GROUPS):
@@ -100,7 +104,7 @@ def emu_jobs(emu_libs):
     src = os.path.join(EMU, "fake_nccl.cpp")
     if not os.path.exists(nccl) or os.path.getmtime(nccl) < os.path.getmtime(src):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", src, "-o", nccl, "-lrt", "-pthread"])
-    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(emu_lib) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(emu_lib) + ":" + os.environ.get("LD_LIBRARY_PATH", ""), B200_EMU_TRACE_FILE=trace)
     for world in SHARDED_WORLDS:
         uid = (b"/b200emu_pytest_%d_%d" % (os.getpid(), world)).ljust(128, b"\0").hex()
         for r in range(world):
@@ -134,6 +138,7 @@ def emu_jobs(emu_libs):
         except subprocess.TimeoutExpired:
             p.kill()
             results[k] = (-999, "", "timeout")
+    results["kernel_trace"] = trace
     return results
 
 
@@ -145,6 +150,29 @@ def test_whole_library_in_host_emulation(emu_jobs):
         if rc != 0 or done != g:
             failures.append((g, done, err[-800:]))
     assert not failures, failures
+
+
+def test_every_kernel_of_the_gpu_build_is_reached(emu_jobs):
+    """Every __global__ function compiled into libgtsam_b200.so (all template instantiations) is launched by at least one
+    emulated scenario that checks its results against the reference / the oracle — no kernel ships unexercised."""
+    import re
+    lib = os.path.join(ROOT, "gtsam_b200", "libgtsam_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+
+    def names(lines):
+        out = set()
+        for l in lines:
+            m = re.search(r"(b200::[a-z0-9_]*_kernel(?:<[^(]*>)?)\(", l)
+            if m and "__device_stub" not in l and "__wrapper" not in l:
+                out.add(m.group(1))
+        return out
+    built = names(subprocess.run(["nm", "-C", "--defined-only", lib], capture_output=True, text=True).stdout.splitlines())
+    assert len(built) > 100
+    mangled = [l.rsplit(" ", 1)[0] for l in open(emu_jobs["kernel_trace"])]
+    reached = names(subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.splitlines())
+    os.unlink(emu_jobs["kernel_trace"])
+    assert not sorted(built - reached), sorted(built - reached)
 
 
 @pytest.mark.parametrize("world", SHARDED_WORLDS)
