@@ -213,7 +213,29 @@ def edge(_):
             assert lm.lambda_() == olm.state.lambda_
         del lm
         dev.close()
+    # values snapshot / restore around a rejected step, the phase timers (what bench.py reads), joint-marginal argument checks
     prob = util.load_case("bal_tiny_s2")
+    dev = capi.DeviceProblem(ctx, prob)
+    dev.profile_enable(True)
+    v0 = dev.get_values()
+    dev.save_values()
+    dev.linearize(); dev.solve(1e-3); dev.try_step(); dev.accept_step()
+    assert not np.array_equal(dev.get_values(), v0)
+    dev.restore_values()
+    assert np.array_equal(dev.get_values(), v0)
+    dev.synchronize()
+    prof = dev.profile()
+    assert prof["linearize"][1] + prof["linearize_small_groups"][1] >= 1 and prof["back_substitute"][1] == 1 and all(ms >= 0 for ms, _ in prof.values())
+    dev.profile_enable(False)
+    dev.linearize(); dev.solve(0.0)
+    import ctypes
+    scratch = np.zeros(32 * 32)
+    for bad in ([3, 1], [1, 1], [0, prob.nvars], [-1, 2]):
+        vs = np.array(bad, dtype=np.int64)
+        rc = dev.L.b200_joint_marginal_covariance(dev.h, vs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 2,
+                                                  scratch.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert rc == P.INVALID_ARGUMENT, (bad, rc)
+    dev.close()
     dev = capi.DeviceProblem(ctx, prob)
     for call in (lambda: dev.solve(0.0), lambda: dev.hessian_diagonal(), lambda: dev.get_jacobians(0), lambda: dev.try_step()):
         try:
@@ -317,6 +339,27 @@ def coverage(_):
                 assert so == 0 and abs(dl.error() - err) <= 1e-7 * err and abs(dl.getDelta() - rad) <= 1e-9 * rad, (prob.name, f32, dl.error(), err, dl.getDelta(), rad)
             del dl
             dev.close()
+    # Dogleg with an oversized trust region: rejected and shrunk steps (the rho < 0.25 and rho < 0 branches)
+    shrunk = 0
+    for name in ("sphere_tiny", "bal_tiny_s2", "pose3example"):
+        prob = util.load_case(name)
+        prm = optimizer.DoglegParams()
+        prm.deltaInitial = 1e4
+        dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+        dl = optimizer.DoglegOptimizer(ctx, prob, prm, device_problem=dev)
+        err, rad = orc.error(), 1e4
+        for _ in range(6):
+            dl.iterate()
+            prev = err
+            so, err, rad2 = orc.dogleg_iterate(err, rad)
+            if abs(prev - err) <= 1e-9 * err:
+                break       # converged: the sign of rho is round-off from here on (in the reference too)
+            shrunk += rad2 < rad
+            rad = rad2
+            assert so == 0 and abs(dl.error() - err) <= 1e-7 * err and abs(dl.getDelta() - rad) <= 1e-9 * rad, (name, dl.error(), err, dl.getDelta(), rad)
+        del dl
+        dev.close()
+    assert shrunk >= 1
     os.environ["B200_NO_FUSE_EA"] = "1"
     try:
         prob = util.load_case("sphere_small_colamd")
