@@ -339,6 +339,38 @@ def coverage(_):
                 assert so == 0 and abs(dl.error() - err) <= 1e-7 * err and abs(dl.getDelta() - rad) <= 1e-9 * rad, (prob.name, f32, dl.error(), err, dl.getDelta(), rad)
             del dl
             dev.close()
+    # Rot3::Logmap next to pi (gtsam/geometry/SO3.cpp:264-319, one branch per dominant axis) in Between / Prior residuals and
+    # their Jacobians; points behind the camera (CheiralityException: zero Jacobians, residual 2 fx) for both camera models
+    eye = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
+    for axis in ([1, 0, 0], [0, 1, 0], [0, 0, 1], [0.5, 0.6, 0.62], [0.7, 0.1, 0.7]):
+        w = np.asarray(axis, dtype=float)
+        w = w / np.linalg.norm(w) * (np.pi - 2e-4)
+        R, t = datasets.se3_exp(np.concatenate([w, [0.3, -0.2, 0.1]])[None, :])
+        meas = datasets.pack_pose(R, t)
+        btw = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, np.array([[0, 1]]), meas, P.NOISE_DIAGONAL, np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))
+        pri = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0]]), meas, P.NOISE_ISOTROPIC, np.array([0.5]))
+        prob = P.Problem(np.array([P.VAR_POSE3, P.VAR_POSE3]), np.concatenate([eye, eye + 1e-3 * np.arange(12)]), np.array([0, 1]), [btw, pri])
+        dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
+        assert abs(dev.error() - orc.error()) <= 1e-12 * orc.error()
+        dev.linearize(); orc.linearize()
+        for gi in range(2):
+            assert util.relmax(dev.get_jacobians(gi), orc.get_jacobians(gi)) <= 1e-9, (axis, gi)
+        dev.close()
+    K = np.array([[500.0, 500.0, 0.0, 320.0, 240.0]])
+    behind = np.concatenate([eye, [0.1, 0.2, -3.0]])
+    prob = P.Problem(np.array([P.VAR_POSE3, P.VAR_POINT3]), behind, np.array([1, 0]),
+                     [P.FactorGroup(P.FACTOR_PROJECTION_CAL3S2, np.array([[0, 1]]), np.array([[1.0, 2.0]]), P.NOISE_UNIT)], K)
+    cam = np.concatenate([eye, [500.0, 0.01, 0.001, 0.0, 0.0]])
+    prob_b = P.Problem(np.array([P.VAR_CAM_BUNDLER, P.VAR_POINT3]), np.concatenate([cam, [0.1, 0.2, -3.0]]), np.array([1, 0]),
+                       [P.FactorGroup(P.FACTOR_SFM_BUNDLER, np.array([[0, 1]]), np.array([[1.0, 2.0]]), P.NOISE_UNIT)])
+    for pr in (prob, prob_b):
+        dev, orc = capi.DeviceProblem(ctx, pr), O.OracleProblem(pr)
+        # GenericProjectionFactor: residual 2 fx per row (ProjectionFactor.h:156-165); GeneralSFMFactor: zero residual (GeneralSFMFactor.h:132-141)
+        assert dev.error() == orc.error() == (1e6 if pr is prob else 0.0)
+        dev.linearize(); orc.linearize()
+        J = dev.get_jacobians(0)
+        assert np.all(J[:, :, :-1] == 0) and np.array_equal(J, orc.get_jacobians(0))
+        dev.close()
     # Dogleg with an oversized trust region: rejected and shrunk steps (the rho < 0.25 and rho < 0 branches)
     shrunk = 0
     for name in ("sphere_tiny", "bal_tiny_s2", "pose3example"):
