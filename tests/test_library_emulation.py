@@ -89,7 +89,7 @@ def emu_jobs(emu_libs):
     solve, the C++ parity drivers of tests/test_shim_emulation.py): about 12 CPU-minutes, 2-3 minutes on 8 cores."""
     jobs = {}
     emu_lib, asan_lib, asan_rt = emu_libs
-    # threads of a block run in a freshly shuffled order between barriers (the sharded and C++ jobs below: ascending order)
+    # threads of a block run in a freshly shuffled order between barriers (the sharded jobs below: descending, the C++ jobs: ascending)
     trace = os.path.join(os.path.dirname(emu_lib), "kernel_trace_%d.txt" % os.getpid())   # B200_EMU_TRACE_FILE: kernel launch counts
     if os.path.exists(trace):
         os.unlink(trace)
@@ -104,7 +104,8 @@ def emu_jobs(emu_libs):
     src = os.path.join(EMU, "fake_nccl.cpp")
     if not os.path.exists(nccl) or os.path.getmtime(nccl) < os.path.getmtime(src):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", src, "-o", nccl, "-lrt", "-pthread"])
-    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(emu_lib) + ":" + os.environ.get("LD_LIBRARY_PATH", ""), B200_EMU_TRACE_FILE=trace)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(emu_lib) + ":" + os.environ.get("LD_LIBRARY_PATH", ""), B200_EMU_TRACE_FILE=trace,
+               B200_EMU_ORDER="reverse")     # the ranks run their threads in descending order between barriers
     for world in SHARDED_WORLDS:
         uid = (b"/b200emu_pytest_%d_%d" % (os.getpid(), world)).ljust(128, b"\0").hex()
         for r in range(world):
