@@ -3,8 +3,7 @@
     python tests/emu/kernel_coverage.py        (after tests/test_library_emulation.py has built tests/emu/_build/)
 
 Runs every scenario group of tests/test_library_emulation.py plus one sharded world with B200_EMU_TRACE_FILE set and
-compares the traced kernel names with the entry functions ptxas reported for the sm_100a build
-(gtsam_b200/csrc/build.log).  Prints the kernels never launched in emulation."""
+compares the traced kernel names with the kernel symbols of the sm_100a build (gtsam_b200/libgtsam_b200.so).  Prints the kernels never launched in emulation."""
 import importlib.util
 import os
 import re
@@ -41,8 +40,10 @@ def main():
         counts[name] = counts.get(name, 0) + int(n)
     os.unlink(trace)
     reached = dict(zip(demangle(list(counts)), counts.values()))
-    log = open(os.path.join(ROOT, "gtsam_b200", "csrc", "build.log")).read()
-    built = sorted(set(demangle(re.findall(r"Compiling entry function '([^']+)'", log))))
+    # the __global__ functions of the GPU build = the host-side kernel symbols of libgtsam_b200.so
+    syms = subprocess.run(["nm", "--defined-only", os.path.join(ROOT, "gtsam_b200", "libgtsam_b200.so")], capture_output=True, text=True).stdout
+    built = sorted({n for n in demangle([l.split()[-1] for l in syms.splitlines() if l.split()[-1].startswith("_ZN4b200")])
+                    if re.match(r"b200::[a-z0-9_]*_kernel(<.*>)?$", n)})
     missing = [k for k in built if k not in reached]
     print("job exit codes:", rcs)
     print(f"{len(built)} kernels in the sm_100a build, {len(built) - len(missing)} launched in emulation, {len(missing)} never:")
