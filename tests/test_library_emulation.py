@@ -91,8 +91,9 @@ def emu_jobs(emu_libs):
     emu_lib, asan_lib, asan_rt = emu_libs
     # threads of a block run in a freshly shuffled order between barriers (the sharded jobs below: descending, the C++ jobs: ascending)
     trace = os.path.join(os.path.dirname(emu_lib), "kernel_trace_%d.txt" % os.getpid())   # B200_EMU_TRACE_FILE: kernel launch counts
-    if os.path.exists(trace):
-        os.unlink(trace)
+    for f in os.listdir(os.path.dirname(emu_lib)):      # traces of earlier runs (this one's included)
+        if f.startswith("kernel_trace_"):
+            os.unlink(os.path.join(os.path.dirname(emu_lib), f))
     genv = dict(os.environ, B200_EMU_ORDER="shuffle:1", B200_EMU_TRACE_FILE=trace)
     if asan_lib:
         genv.update(ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LD_PRELOAD=asan_rt)
@@ -172,7 +173,6 @@ def test_every_kernel_of_the_gpu_build_is_reached(emu_jobs):
     assert len(built) > 100
     mangled = [l.rsplit(" ", 1)[0] for l in open(emu_jobs["kernel_trace"])]
     reached = names(subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.splitlines())
-    os.unlink(emu_jobs["kernel_trace"])
     assert not sorted(built - reached), sorted(built - reached)
 
 
