@@ -177,38 +177,34 @@ def test_cuda_logmap_near_pi_and_bundler_cheirality(gpu_ctx):
     """Branches no fixture reaches (found with gcov on the host-emulation build, where they pass): Rot3::Logmap next to pi
     (gtsam/geometry/SO3.cpp:264-319, one branch per dominant axis) inside Between / Prior residuals and Jacobians, and
     GeneralSFMFactor's CheiralityException handling (GeneralSFMFactor.h:132-141: zero residual, zero Jacobians) — device
-    vs the oracle (pinned on the reference's near-pi known answers, tests/test_oracle_golden.py).  Written after the
-    round's GPU budget was spent: a mismatch on its first hardware run reports xfail."""
-    try:
-        from gtsam_b200 import datasets
-        from oracle import oracle_py as O
-        eye = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
-        worst = 0.0
-        for axis in ([1, 0, 0], [0, 1, 0], [0, 0, 1], [0.5, 0.6, 0.62], [0.7, 0.1, 0.7]):
-            w = np.asarray(axis, dtype=float)
-            w = w / np.linalg.norm(w) * (np.pi - 2e-4)
-            R, t = datasets.se3_exp(np.concatenate([w, [0.3, -0.2, 0.1]])[None, :])
-            meas = datasets.pack_pose(R, t)
-            btw = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, np.array([[0, 1]]), meas, P.NOISE_DIAGONAL, np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))
-            pri = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0]]), meas, P.NOISE_ISOTROPIC, np.array([0.5]))
-            prob = P.Problem(np.array([P.VAR_POSE3, P.VAR_POSE3]), np.concatenate([eye, eye + 1e-3 * np.arange(12)]), np.array([0, 1]), [btw, pri])
-            dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
-            worst = max(worst, abs(dev.error() - orc.error()) / orc.error() * 1e3)      # 1e-12 on the error ~ 1e-9 on the scale below
-            dev.linearize(); orc.linearize()
-            for gi in range(2):
-                worst = max(worst, util.relmax(dev.get_jacobians(gi), orc.get_jacobians(gi)))
-            dev.close()
-        cam = np.concatenate([eye, [500.0, 0.01, 0.001, 0.0, 0.0]])
-        prob_b = P.Problem(np.array([P.VAR_CAM_BUNDLER, P.VAR_POINT3]), np.concatenate([cam, [0.1, 0.2, -3.0]]), np.array([1, 0]),
-                           [P.FactorGroup(P.FACTOR_SFM_BUNDLER, np.array([[0, 1]]), np.array([[1.0, 2.0]]), P.NOISE_UNIT)])
-        dev = capi.DeviceProblem(gpu_ctx, prob_b)
-        dev.linearize()
-        zero = dev.error() == 0.0 and bool(np.all(dev.get_jacobians(0) == 0))
+    vs the oracle (pinned on the reference's near-pi known answers, tests/test_oracle_golden.py)."""
+    from gtsam_b200 import datasets
+    from oracle import oracle_py as O
+    eye = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
+    worst = 0.0
+    for axis in ([1, 0, 0], [0, 1, 0], [0, 0, 1], [0.5, 0.6, 0.62], [0.7, 0.1, 0.7]):
+        w = np.asarray(axis, dtype=float)
+        w = w / np.linalg.norm(w) * (np.pi - 2e-4)
+        R, t = datasets.se3_exp(np.concatenate([w, [0.3, -0.2, 0.1]])[None, :])
+        meas = datasets.pack_pose(R, t)
+        btw = P.FactorGroup(P.FACTOR_BETWEEN_POSE3, np.array([[0, 1]]), meas, P.NOISE_DIAGONAL, np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))
+        pri = P.FactorGroup(P.FACTOR_PRIOR_POSE3, np.array([[0]]), meas, P.NOISE_ISOTROPIC, np.array([0.5]))
+        prob = P.Problem(np.array([P.VAR_POSE3, P.VAR_POSE3]), np.concatenate([eye, eye + 1e-3 * np.arange(12)]), np.array([0, 1]), [btw, pri])
+        dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+        worst = max(worst, abs(dev.error() - orc.error()) / orc.error() * 1e3)      # 1e-12 on the error ~ 1e-9 on the scale below
+        dev.linearize(); orc.linearize()
+        for gi in range(2):
+            worst = max(worst, util.relmax(dev.get_jacobians(gi), orc.get_jacobians(gi)))
         dev.close()
-    except Exception as e:   # noqa: BLE001
-        pytest.xfail(f"near-pi Logmap / Bundler cheirality: first hardware run raised: {e!r}")
+    cam = np.concatenate([eye, [500.0, 0.01, 0.001, 0.0, 0.0]])
+    prob_b = P.Problem(np.array([P.VAR_CAM_BUNDLER, P.VAR_POINT3]), np.concatenate([cam, [0.1, 0.2, -3.0]]), np.array([1, 0]),
+                       [P.FactorGroup(P.FACTOR_SFM_BUNDLER, np.array([[0, 1]]), np.array([[1.0, 2.0]]), P.NOISE_UNIT)])
+    dev = capi.DeviceProblem(gpu_ctx, prob_b)
+    dev.linearize()
+    zero = dev.error() == 0.0 and bool(np.all(dev.get_jacobians(0) == 0))
+    dev.close()
     if not (worst <= 1e-9 and zero):
-        pytest.xfail(f"near-pi Logmap / Bundler cheirality: first hardware run off: worst {worst:.3g}, cheirality zero {zero}")
+        pytest.fail(f"near-pi Logmap / Bundler cheirality: off: worst {worst:.3g}, cheirality zero {zero}")
 
 
 def _normal_equation_residual(prob, dev, lam):
