@@ -34,6 +34,7 @@ EXPORTS = [
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
     "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
+    "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode",
 ]
 
 
@@ -127,6 +128,8 @@ def lib():
         L.b200_linear_update_hessian.argtypes = [vp, C.c_int64, dp]
         L.b200_linear_symbolic_create.argtypes = [C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
+        L.b200_symbolic_get_supernodes.argtypes = [vp, ip, ip, ip, ip, ip]
+        L.b200_symbolic_get_clique_supernode.argtypes = [vp, C.POINTER(C.c_int32)]
         L.b200_symbolic_get_factor_slots.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
@@ -373,6 +376,17 @@ class DeviceProblem:
         _check(self.L.b200_get_cliques(self.h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par)))
         return fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques]
 
+    def supernodes(self):
+        """The supernodes the device eliminates (the reference's cliques after relaxed amalgamation)."""
+        info = self.symbolic_info()
+        fp = np.zeros(info.supernodes + 1, dtype=np.int64)
+        sp = np.zeros(info.supernodes + 1, dtype=np.int64)
+        fv = np.zeros(max(1, info.supernode_frontal_list_len), dtype=np.int64)
+        sv = np.zeros(max(1, info.supernode_separator_list_len), dtype=np.int64)
+        par = np.zeros(max(1, info.supernodes), dtype=np.int64)
+        _check(self.L.b200_get_supernodes(self.h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par)))
+        return fp, fv[:info.supernode_frontal_list_len], sp, sv[:info.supernode_separator_list_len], par[:info.supernodes]
+
     def conditional(self, c: int):
         fp, fv, sp, sv, _ = self.cliques()
         dims = self.prob.var_dims
@@ -427,20 +441,24 @@ class LinearDeviceProblem(DeviceProblem):
 
 
 def linear_symbolic(lprob, with_slots=False):
-    """Host-only junction tree of a linear problem: (frontal_ptr, frontal_vars, separator_ptr, separator_vars, parent);
-    with_slots adds (owning clique per graph position, CSR pointer of the factors' keys, front slot of every key)."""
+    """Host-only junction tree of a linear problem: (frontal_ptr, frontal_vars, separator_ptr, separator_vars, parent)
+    of the reference's cliques; with_slots returns the SUPERNODES instead (what the device eliminates: the cliques
+    after relaxed amalgamation) plus (owning supernode per graph position, CSR pointer of the factors' keys, front slot
+    of every key)."""
     L = lib()
     desc, keep = lprob.c_desc()
     h = C.c_void_p()
     _check(L.b200_linear_symbolic_create(C.byref(desc), C.byref(h)))
     info = P.CSymbolicInfo()
     L.b200_symbolic_get_info(h, C.byref(info))
-    fp = np.zeros(info.ncliques + 1, dtype=np.int64)
-    sp = np.zeros(info.ncliques + 1, dtype=np.int64)
-    fv = np.zeros(max(1, info.frontal_list_len), dtype=np.int64)
-    sv = np.zeros(max(1, info.separator_list_len), dtype=np.int64)
-    par = np.zeros(max(1, info.ncliques), dtype=np.int64)
-    L.b200_symbolic_get_cliques(h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par))
+    nc, nfl, nsl = ((info.supernodes, info.supernode_frontal_list_len, info.supernode_separator_list_len) if with_slots
+                    else (info.ncliques, info.frontal_list_len, info.separator_list_len))
+    fp = np.zeros(nc + 1, dtype=np.int64)
+    sp = np.zeros(nc + 1, dtype=np.int64)
+    fv = np.zeros(max(1, nfl), dtype=np.int64)
+    sv = np.zeros(max(1, nsl), dtype=np.int64)
+    par = np.zeros(max(1, nc), dtype=np.int64)
+    (L.b200_symbolic_get_supernodes if with_slots else L.b200_symbolic_get_cliques)(h, _ip(fp), _ip(fv), _ip(sp), _ip(sv), _ip(par))
     if with_slots:
         arity = np.zeros(lprob.nfactors, dtype=np.int64)
         for g in list(lprob.groups) + list(lprob.hgroups):
@@ -451,5 +469,5 @@ def linear_symbolic(lprob, with_slots=False):
         slots = np.zeros(max(1, int(fptr[-1])), dtype=np.int32)
         L.b200_symbolic_get_factor_slots(h, clique.ctypes.data_as(C.POINTER(C.c_int32)), slots.ctypes.data_as(C.POINTER(C.c_int32)))
     L.b200_symbolic_destroy(h)
-    out = (fp, fv[:info.frontal_list_len], sp, sv[:info.separator_list_len], par[:info.ncliques])
+    out = (fp, fv[:nfl], sp, sv[:nsl], par[:nc])
     return out + (clique[:lprob.nfactors], fptr, slots[:int(fptr[-1])]) if with_slots else out

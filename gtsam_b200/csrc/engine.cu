@@ -218,6 +218,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   {
     PhaseScope ps(p, PH_MEMSET);
     if (p->zero_doubles) B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->zero_doubles * sizeof(double), st));
+    if (p->df_sync_ints) B200_CUDA(cudaMemsetAsync(p->d_df_sync, 0, (size_t)p->df_sync_ints * sizeof(int), st));
   }
   {
     PhaseScope ps(p, PH_ASSEMBLE);
@@ -300,6 +301,18 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (rc) return rc;
     }
     const LevelPlan& L = p->levels[l];
+    for (int ph = 0; ph < 2; ph++)
+      if ((int)l == p->df_level[ph] && p->df_ntasks[ph]) {
+        // every remaining non-leaf front of the phase, all levels, as one tile dataflow (front_df.cuh)
+        PhaseScope ps(p, PH_ELIM_LARGE);
+        DfView v;
+        v.tasks = p->d_df_tasks[ph]; v.ntasks = p->df_ntasks[ph];
+        v.ctrl = p->d_df_sync + 2 * ph; v.done = p->d_df_sync + 4; v.flags = p->d_df_sync + 4 + p->sym.ncliques;
+        v.flag_off = p->d_df_flag_off; v.expect = p->d_df_expect;
+        v.trace = ph == 0 ? p->d_df_trace : nullptr;
+        launch_k(front_df_kernel, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
+        ctx->launches++;
+      }
     if (L.small_count) {
       PhaseScope ps(p, PH_ELIM_SMALL);
       const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -421,7 +434,7 @@ static int enqueue_try_step(b200_problem* p) {
 }
 
 static int reset_flags(b200_problem* p) {
-  B200_CUDA(cudaMemsetAsync(&p->d_scalars->fail_code, 0, 2 * sizeof(int), p->ctx->stream));
+  B200_CUDA(cudaMemsetAsync(&p->d_scalars->fail_code, 0, 4 * sizeof(int), p->ctx->stream));   // fail, nan, df_abort, pad
   return B200_OK;
 }
 static int set_lambda(b200_problem* p, double lambda) {
@@ -437,6 +450,7 @@ static int fetch_scalars(b200_problem* p) {
 }
 static int solve_status(const b200_problem* p, int64_t* fail_var) {
   const Scalars* s = p->h_scalars;
+  if (s->df_abort) { set_error("front_df_kernel: a dependency wait timed out (internal scheduling error)"); return B200_CUDA_ERROR; }
   // a failed factorisation poisons everything below it: report the Cholesky failure first
   const int code = s->fail_code ? s->fail_code : s->nan_code;
   if (code == 0) { if (fail_var) *fail_var = -1; return B200_OK; }
@@ -912,6 +926,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_didx_ptr); cudaFree(p->d_ea_map); cudaFree(p->d_didx); cudaFree(p->d_diag_index);
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_marg_work); cudaFree(p->d_marg_path); cudaFree(p->d_marg_out); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
+  cudaFree(p->d_df_tasks[0]); cudaFree(p->d_df_tasks[1]); cudaFree(p->d_df_flag_off); cudaFree(p->d_df_expect); cudaFree(p->d_df_sync); cudaFree(p->d_df_trace);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
@@ -1193,6 +1208,18 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   p->levels.resize(2 * S.nlevels);
   p->n_sub_levels = (int)S.nlevels;
   p->max_small_n = 1;
+  p->use_df = getenv("B200_LEGACY_FRONTS") == nullptr;
+  // tile dataflow (front_df.cuh): per phase, from the first level that holds a front wider than kSmallMaxN upwards,
+  // every non-leaf front is a set of tiles of ONE launch; the levels below it (small fronts only) keep elim_small_kernel
+  int df_first[2] = {INT_MAX, INT_MAX};
+  std::vector<int4> df_tasks[2];
+  std::vector<int> df_flag_off(S.ncliques, 0), df_expect(S.ncliques, 0), df_tiles(S.ncliques, 0);
+  int64_t df_nflags = 0;
+  auto in_phase = [&](int phase, int c) { return phase == 0 ? (!is_top[c] && clique_owner[c] == rank) : (is_top[c] != 0); };
+  if (p->use_df)
+    for (int phase = 0; phase < 2; phase++)
+      for (int64_t c = 0; c < S.ncliques; c++)
+        if (in_phase(phase, (int)c) && !fused[c] && S.nf[c] + S.ns[c] + 1 > kSmallMaxN) df_first[phase] = std::min(df_first[phase], S.level[c]);
   for (int phase = 0; phase < 2; phase++)
   for (int64_t l = 0; l < S.nlevels; l++) {
     LevelPlan& L = p->levels[phase * S.nlevels + l];
@@ -1210,15 +1237,27 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
         // eliminated by the leaf kernels; back-substituted 8 lanes per point / one warp per clique
         if (leaf_kind[c] > 0 && !getenv("B200_NO_POINT_BACKSUB")) pts[leaf_kind[c] - 1].push_back(c);
         else bsmall.push_back(c);
-      } else if (nn <= kSmallMaxN) {
+      } else if (nn <= kSmallMaxN && l < df_first[phase]) {
         small.push_back(c);
         bsmall.push_back(c);
         p->max_small_n = std::max(p->max_small_n, nn);
       } else {
+        if (l >= df_first[phase]) {
+          // tiles (column block j, row tile r) of the upper trapezoid, ticket order: column-major (dependencies point backwards)
+          const int K = (S.nf[c] + kDfB - 1) / kDfB, NB = K + (nn - S.nf[c] + kDfB - 1) / kDfB;
+          if (p->df_level[phase] < 0) p->df_level[phase] = (int)(phase * S.nlevels + l);
+          df_flag_off[c] = (int)df_nflags;
+          df_nflags += (int64_t)K * NB;
+          for (int j = 0; j < NB; j++)
+            for (int r = 0; kDfTR * r <= j; r++) { df_tasks[phase].push_back(make_int4(c, j, r, 0)); df_tiles[c]++; }
+          if (S.parent[c] >= 0) df_expect[S.parent[c]] += df_tiles[c];
+        } else {
         large.push_back(c);
         L.large_max_nf = std::max(L.large_max_nf, S.nf[c]);
         L.large_max_ns = std::max(L.large_max_ns, S.ns[c]);
         L.large_max_n = std::max(L.large_max_n, nn);
+        }
+        if (nn <= kSmallMaxN) { bsmall.push_back(c); continue; }
         // back-substitution cares about the pivots only: thin fronts (<= 8 pivots: one pass of the one-warp kernel
         // over the separator) skip the multi-CTA flag machinery (back-substitution: bal_c3 0.150 -> 0.114 ms,
         // bal_c4 2.7 -> 2.0 ms, sphere2500 0.85 -> 0.90 ms)
@@ -1235,6 +1274,24 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     L.small_count = (int)small.size() - L.small_begin;
     L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
     L.large_count = (int)large.size() - L.large_begin;
+  }
+  if (df_nflags + S.ncliques + 4 > (int64_t)INT_MAX) FAIL(B200_INVALID_ARGUMENT, "front dataflow: flag table exceeds 2^31 entries");
+  for (int phase = 0; phase < 2; phase++) {
+    p->df_ntasks[phase] = (int)df_tasks[phase].size();
+    if (p->df_ntasks[phase]) UP(upload(&p->d_df_tasks[phase], df_tasks[phase], st));
+  }
+  if (p->df_ntasks[0] + p->df_ntasks[1]) {
+    UP(upload(&p->d_df_flag_off, df_flag_off, st));
+    UP(upload(&p->d_df_expect, df_expect, st));
+    p->df_sync_ints = 4 + S.ncliques + df_nflags;
+    B200_CUDA(cudaMalloc((void**)&p->d_df_sync, (size_t)p->df_sync_ints * sizeof(int)));
+#ifndef B200_EMULATE
+    B200_CUDA(cudaFuncSetAttribute(front_df_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDfSmemBytes));
+#endif
+    if (getenv("B200_DF_TRACE") && p->df_ntasks[0]) {
+      B200_CUDA(cudaMalloc((void**)&p->d_df_trace, (size_t)p->df_ntasks[0] * 32 * 8));
+      B200_CUDA(cudaMemsetAsync(p->d_df_trace, 0, (size_t)p->df_ntasks[0] * 32 * 8, st));
+    }
   }
   UP(upload(&p->d_lvl_small, small, st));
   UP(upload(&p->d_lvl_bsmall, bsmall, st));
@@ -1542,6 +1599,17 @@ int b200_solve(b200_problem* p, double lambda, int diagonal, double min_diag, do
   if (rc) return rc;
   rc = fetch_scalars(p);
   if (rc) return rc;
+  if (p->d_df_trace) {   // B200_DF_TRACE=<file>: per-tile globaltimer stamps of the last solve (profiling aid, phase 0 only)
+    std::vector<unsigned long long> tr((size_t)p->df_ntasks[0] * 32);
+    std::vector<int4> tk((size_t)p->df_ntasks[0]);
+    cudaMemcpy(tr.data(), p->d_df_trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(tk.data(), p->d_df_tasks[0], tk.size() * sizeof(int4), cudaMemcpyDeviceToHost);
+    if (FILE* fh = fopen(getenv("B200_DF_TRACE"), "wb")) {
+      const int64_t nt = p->df_ntasks[0];
+      fwrite(&nt, 8, 1, fh); fwrite(tk.data(), sizeof(int4), tk.size(), fh); fwrite(tr.data(), 8, tr.size(), fh);
+      fclose(fh);
+    }
+  }
   if (e0) *e0 = p->h_scalars->lin_err0;
   if (e1) *e1 = p->h_scalars->lin_err_delta;
   rc = solve_status(p, fail_var);
@@ -1619,33 +1687,78 @@ int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {
 }
 
 // ---- symbolic introspection ------------------------------------------------------
+static void fill_info(const Symbolic& S, int64_t ndelta, b200_symbolic_info* info) {
+  // the junction tree as the reference builds it (what b200_get_cliques / b200_get_conditional report) ...
+  const RefCliques& R = S.ref;
+  info->ncliques = R.ncliques; info->nlevels = R.nlevels; info->total_dim = ndelta;
+  info->max_frontal_dim = R.max_nf; info->max_separator_dim = R.max_ns;
+  info->frontal_list_len = (int64_t)R.front_vars.size(); info->separator_list_len = (int64_t)R.sep_vars.size();
+  info->factor_flops = R.flops; info->front_bytes = S.arena_doubles * 8;
+  // ... and the supernodes the device eliminates (the same cliques after relaxed amalgamation, symbolic.h)
+  info->supernodes = S.ncliques; info->supernode_levels = S.nlevels;
+  info->supernode_max_frontal_dim = S.max_nf; info->supernode_max_separator_dim = S.max_ns;
+  info->supernode_frontal_list_len = (int64_t)S.front_vars.size(); info->supernode_separator_list_len = (int64_t)S.sep_vars.size();
+  info->supernode_flops = S.flops;
+}
 int b200_symbolic_info_get(const b200_problem* p, b200_symbolic_info* info) {
-  const Symbolic& S = p->sym;
-  info->ncliques = S.ncliques; info->nlevels = S.nlevels; info->total_dim = p->ndelta;
-  info->max_frontal_dim = S.max_nf; info->max_separator_dim = S.max_ns;
-  info->frontal_list_len = (int64_t)S.front_vars.size(); info->separator_list_len = (int64_t)S.sep_vars.size();
-  info->factor_flops = S.flops; info->front_bytes = p->arena_doubles * 8;
+  fill_info(p->sym, p->ndelta, info);
+  info->front_bytes = p->arena_doubles * 8;
   return B200_OK;
 }
 static void copy_i64(int64_t* dst, const std::vector<int64_t>& v) {   // an empty vector's data() may be null
   if (!v.empty()) memcpy(dst, v.data(), v.size() * sizeof(int64_t));
 }
-int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
-  const Symbolic& S = p->sym;
+static void fill_cliques(const Symbolic& S, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  const RefCliques& R = S.ref;
+  copy_i64(fp, R.front_ptr); copy_i64(fv, R.front_vars); copy_i64(sp, R.sep_ptr); copy_i64(sv, R.sep_vars); copy_i64(parent, R.parent);
+}
+static void fill_supernodes(const Symbolic& S, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
   copy_i64(fp, S.front_ptr); copy_i64(fv, S.front_vars); copy_i64(sp, S.sep_ptr); copy_i64(sv, S.sep_vars); copy_i64(parent, S.parent);
+}
+int b200_get_cliques(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  fill_cliques(p->sym, fp, fv, sp, sv, parent);
   return B200_OK;
 }
-/* conditional [R S d] of clique c after a solve: nf x (nf+ns+1) column-major */
+int b200_get_supernodes(const b200_problem* p, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  fill_supernodes(p->sym, fp, fv, sp, sv, parent);
+  return B200_OK;
+}
+/* conditional [R S d] of (reference) clique c after a solve: nf x (nf+ns+1) column-major.  The clique's rows live in
+ * the supernode that absorbed it: its frontal rows, at the columns of its own frontals, its own separator variables
+ * (frontals or separator of the supernode) and the rhs; every other column of those rows is structurally zero. */
 int b200_get_conditional(b200_problem* p, int64_t c, double* out) {
   const Symbolic& S = p->sym;
-  if (c < 0 || c >= S.ncliques || !p->factored) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
+  const RefCliques& R = S.ref;
+  if (c < 0 || c >= R.ncliques || !p->factored) { set_error("bad clique or no solve yet"); return B200_INVALID_ARGUMENT; }
   B200_CUDA(cudaSetDevice(p->ctx->device));
-  const int64_t f = S.nf[c], nn = f + S.ns[c] + 1, ld = p->h_ld[c];
-  std::vector<double> M((size_t)(ld * nn));
-  B200_CUDA(cudaMemcpyAsync(M.data(), p->d_arena + p->h_off[c], M.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  const int64_t C = R.super[c];
+  const int64_t f = R.nf[c], nn = f + R.ns[c] + 1, ld = p->h_ld[C];
+  const int64_t NN = S.nf[C] + S.ns[C] + 1;
+  std::vector<double> M((size_t)(ld * NN));
+  B200_CUDA(cudaMemcpyAsync(M.data(), p->d_arena + p->h_off[C], M.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  // scalar slot in the supernode of every row / column of the clique
+  std::vector<int64_t> slot;
+  slot.reserve((size_t)nn);
+  auto push_var = [&](int64_t v) -> bool {
+    int64_t s0 = -1;
+    if (S.var_clique[v] == (int)C) s0 = S.var_slot[v];
+    else {
+      int64_t k = S.nf[C];
+      for (int64_t q = S.sep_ptr[C]; q < S.sep_ptr[C + 1]; q++) {
+        if (S.sep_vars[q] == v) { s0 = k; break; }
+        k += S.var_dim[S.sep_vars[q]];
+      }
+    }
+    if (s0 < 0) return false;
+    for (int t = 0; t < S.var_dim[v]; t++) slot.push_back(s0 + t);
+    return true;
+  };
+  for (int64_t q = R.front_ptr[c]; q < R.front_ptr[c + 1]; q++) if (!push_var(R.front_vars[q])) { set_error("internal: clique variable not in its supernode"); return B200_INVALID_ARGUMENT; }
+  for (int64_t q = R.sep_ptr[c]; q < R.sep_ptr[c + 1]; q++) if (!push_var(R.sep_vars[q])) { set_error("internal: clique separator not in its supernode"); return B200_INVALID_ARGUMENT; }
+  slot.push_back(NN - 1);
   for (int64_t j = 0; j < nn; j++)
-    for (int64_t i = 0; i < f; i++) out[i + j * f] = (i <= j) ? M[(size_t)(i + j * ld)] : 0.0;
+    for (int64_t i = 0; i < f; i++) out[i + j * f] = (i <= j) ? M[(size_t)(slot[i] + slot[j] * ld)] : 0.0;
   return B200_OK;
 }
 struct b200_symbolic { Symbolic sym; int64_t ndelta; };
@@ -1670,15 +1783,6 @@ int b200_linear_symbolic_create(const b200_linear_desc* d, b200_symbolic** out) 
   return B200_OK;
 }
 int b200_symbolic_destroy(b200_symbolic* s) { delete s; return B200_OK; }
-static void fill_info(const Symbolic& S, int64_t ndelta, b200_symbolic_info* info) {
-  info->ncliques = S.ncliques; info->nlevels = S.nlevels; info->total_dim = ndelta;
-  info->max_frontal_dim = S.max_nf; info->max_separator_dim = S.max_ns;
-  info->frontal_list_len = (int64_t)S.front_vars.size(); info->separator_list_len = (int64_t)S.sep_vars.size();
-  info->factor_flops = S.flops; info->front_bytes = S.arena_doubles * 8;
-}
-static void fill_cliques(const Symbolic& S, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
-  copy_i64(fp, S.front_ptr); copy_i64(fv, S.front_vars); copy_i64(sp, S.sep_ptr); copy_i64(sv, S.sep_vars); copy_i64(parent, S.parent);
-}
 int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info) { fill_info(s->sym, s->ndelta, info); return B200_OK; }
 int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
   fill_cliques(s->sym, fp, fv, sp, sv, parent);
@@ -1689,8 +1793,16 @@ int b200_symbolic_get_factor_slots(const b200_symbolic* s, int32_t* clique, int3
   for (size_t i = 0; i < s->sym.fac_slots.size(); i++) slots[i] = s->sym.fac_slots[i];
   return B200_OK;
 }
+int b200_symbolic_get_supernodes(const b200_symbolic* s, int64_t* fp, int64_t* fv, int64_t* sp, int64_t* sv, int64_t* parent) {
+  fill_supernodes(s->sym, fp, fv, sp, sv, parent);
+  return B200_OK;
+}
 int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level) {
-  for (int64_t c = 0; c < s->sym.ncliques; c++) level[c] = s->sym.level[c];
+  for (int64_t c = 0; c < s->sym.ref.ncliques; c++) level[c] = s->sym.ref.level[c];
+  return B200_OK;
+}
+int b200_symbolic_get_clique_supernode(const b200_symbolic* s, int32_t* super) {
+  for (int64_t c = 0; c < s->sym.ref.ncliques; c++) super[c] = s->sym.ref.super[c];
   return B200_OK;
 }
 
@@ -1705,7 +1817,7 @@ int b200_shard_plan(const b200_problem_desc* d, int world, int32_t* clique_owner
   std::vector<char> fused, is_top;
   std::vector<int> co, fo;
   shard_plan(pk.sym, d->ngroups, pk.total, world, &fused, &is_top, &co, &fo);
-  for (size_t c = 0; c < co.size(); c++) clique_owner[c] = co[c];
+  for (int64_t c = 0; c < pk.sym.ref.ncliques; c++) clique_owner[c] = co[pk.sym.ref.super[c]];   // per reference clique
   for (size_t i = 0; i < fo.size(); i++) factor_owner[i] = fo[i];
   return B200_OK;
 }

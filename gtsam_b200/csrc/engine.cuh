@@ -71,7 +71,8 @@ struct Scalars {           // device scalars fetched once per LM try
   double new_error;        // graph.error(newValues)
   int fail_code;           // INT_MAX - (min clique id whose partial Cholesky failed); 0 = none
   int nan_code;            // INT_MAX - (min clique id with NaN in back-substitution); 0 = none
-  int pad[2];
+  int df_abort;            // front_df_kernel: a bounded wait timed out and the launch bailed out (internal error)
+  int pad;
   double dl_dots[3];       // Dogleg: g.g, g.dx_n, dx_n.dx_n
   double dl_half_Ag2;      // Dogleg: 0.5*|A g|^2
   double dl_scratch;       // second output slot of linerr_kernel when only one is wanted
@@ -167,6 +168,15 @@ struct b200_problem {
   int64_t try_launches = 0;
   bool fuse_ea = true;              // fold extend_add_kernel into each front's last update
   double* d_rdiag = nullptr;        // factored diagonal blocks published by panel_kernel
+  // tile-dataflow elimination of the non-leaf fronts (front_df.cuh): one launch per phase (own subtrees / replicated top)
+  bool use_df = true;
+  int df_level[2] = {-1, -1};       // index in `levels` at which the launch of the phase is issued
+  int df_ntasks[2] = {0, 0};
+  int4* d_df_tasks[2] = {nullptr, nullptr};
+  int *d_df_flag_off = nullptr, *d_df_expect = nullptr;
+  int* d_df_sync = nullptr;         // [ctrl of phase 0 (2) | ctrl of phase 1 (2) | done per clique | piece flags]: zeroed per solve
+  int64_t df_sync_ints = 0;
+  unsigned long long* d_df_trace = nullptr;   // B200_DF_TRACE: 32 globaltimer stamps per tile of phase 0
   double* d_partials = nullptr;     // block partial sums
   unsigned* d_counters = nullptr;   // tickets of the last-block reductions
   int partial_cap = 0;

@@ -1418,6 +1418,10 @@ __global__ void __launch_bounds__(256) extend_add_kernel(TreeView t, const int* 
   }
 }
 
+}  // namespace b200
+#include "front_df.cuh"   // tile-dataflow partial Cholesky of all non-leaf fronts in one launch
+namespace b200 {
+
 // ---------------------------------------------------------------------------
 // back-substitution (gtsam/linear/linearAlgorithms-inst.h:50-117)
 // ---------------------------------------------------------------------------

@@ -9,8 +9,17 @@
 
 namespace b200 {
 
+AmalgOptions amalg_options_from_env() {
+  AmalgOptions o;
+  if (getenv("B200_NO_AMALGAMATE")) o.tol = -1.0;
+  if (const char* e = getenv("B200_AMALG_TOL")) o.tol = atof(e);
+  if (const char* e = getenv("B200_AMALG_SMALL")) o.small = atoi(e);
+  return o;
+}
+
 bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int64_t m,
-                    const int64_t* fptr, const int64_t* fkeys, Symbolic* S, const char** err) {
+                    const int64_t* fptr, const int64_t* fkeys, Symbolic* S, const char** err,
+                    const AmalgOptions& amalg) {
   S->nvars = n;
   S->var_dim.assign(var_dim, var_dim + n);
   S->var_dof.assign(n + 1, 0);
@@ -114,7 +123,86 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     }
     if (merged_any) std::reverse(fr.begin(), fr.end());
   }
-  // ---- clique tables --------------------------------------------------------------
+  // ---- the reference's cliques, kept for reporting (Symbolic::ref) ---------------------
+  {
+    RefCliques& R = S->ref;
+    std::vector<int64_t> rid(n, -1);
+    int64_t rc = 0;
+    for (int64_t j = 0; j < n; j++) if (alive[j]) rid[j] = rc++;
+    std::vector<int64_t> rclique_of_node(n, -1);
+    for (int64_t j = n - 1; j >= 0; j--) rclique_of_node[j] = alive[j] ? rid[j] : rclique_of_node[absorbed_into[j]];
+    R.ncliques = rc;
+    R.front_ptr.assign(rc + 1, 0); R.sep_ptr.assign(rc + 1, 0); R.parent.assign(rc, -1);
+    R.nf.assign(rc, 0); R.ns.assign(rc, 0); R.level.assign(rc, 0); R.super.assign(rc, -1);
+    R.front_vars.reserve(n);
+    for (int64_t j = 0; j < n; j++) {
+      if (!alive[j]) continue;
+      const int64_t c = rid[j];
+      int fd = 0, sd = 0;
+      for (int64_t pj : cfront[j]) { R.front_vars.push_back(ordering[pj]); fd += var_dim[ordering[pj]]; }
+      R.front_ptr[c + 1] = (int64_t)R.front_vars.size();
+      const size_t s0 = R.sep_vars.size();
+      for (int64_t q = sep_off[j]; q < sep_off[j + 1]; q++) { R.sep_vars.push_back(ordering[sep_pool[q]]); sd += var_dim[ordering[sep_pool[q]]]; }
+      std::sort(R.sep_vars.begin() + (int64_t)s0, R.sep_vars.end());   // gtsam/linear/Scatter.cpp:69-72
+      R.sep_ptr[c + 1] = (int64_t)R.sep_vars.size();
+      R.nf[c] = fd; R.ns[c] = sd;
+      if (eparent[j] != -1) R.parent[c] = rclique_of_node[eparent[j]];
+      R.max_nf = std::max<int64_t>(R.max_nf, fd); R.max_ns = std::max<int64_t>(R.max_ns, sd);
+      R.flops += (double)fd * fd * fd / 3.0 + (double)fd * fd * sd + (double)fd * sd * sd;
+    }
+    int maxlvl = 0;
+    for (int64_t c = 0; c < rc; c++) {
+      if (R.parent[c] >= 0) R.level[R.parent[c]] = std::max(R.level[R.parent[c]], R.level[c] + 1);
+      maxlvl = std::max(maxlvl, R.level[c]);
+    }
+    R.nlevels = rc ? maxlvl + 1 : 0;
+    // ---- relaxed amalgamation into supernodes (symbolic.h) -------------------------------
+    if (amalg.tol >= 0.0) {
+      std::vector<int64_t> head(rc, -1);            // head node (last frontal position) of every reference clique
+      for (int64_t j = 0; j < n; j++) if (alive[j]) head[rid[j]] = j;
+      std::vector<int64_t> into(rc), F(rc), Sd(rc);
+      for (int64_t c = 0; c < rc; c++) { into[c] = c; F[c] = R.nf[c]; Sd[c] = R.ns[c]; }
+      auto find = [&](int64_t c) { while (into[c] != c) c = into[c] = into[into[c]]; return c; };
+      bool any = false;
+      for (int64_t c = 0; c < rc; c++) {             // children have smaller ids than parents
+        if (R.parent[c] < 0) continue;
+        if (R.level[c] == 0 && R.nf[c] <= amalg.leaf_max_f) continue;   // leaves keep their own (fused) kernels
+        const int64_t p = find(R.parent[c]);
+        const int64_t width = F[p] + Sd[p], fill = width - Sd[c];
+        if ((double)fill <= amalg.tol * (double)width || F[c] + Sd[c] < amalg.small) {
+          into[c] = p; F[p] += F[c]; any = true;
+        }
+      }
+      if (any) {
+        for (int64_t c = 0; c < rc; c++) {
+          const int64_t r = find(c);
+          if (r == c) continue;
+          std::vector<int64_t>& src = cfront[head[c]];
+          std::vector<int64_t>& dst = cfront[head[r]];
+          dst.insert(dst.end(), src.begin(), src.end());
+          std::vector<int64_t>().swap(src);
+          alive[head[c]] = 0;
+        }
+        for (int64_t c = 0; c < rc; c++) if (find(c) == c) std::sort(cfront[head[c]].begin(), cfront[head[c]].end());
+        // every node follows its clique's head to the head of the supernode
+        for (int64_t j = 0; j < n; j++) {
+          const int64_t c = rclique_of_node[j], r = find(c);
+          if (r != c || !alive[j]) { if (j != head[r]) absorbed_into[j] = head[r]; }
+        }
+      }
+      for (int64_t c = 0; c < rc; c++) R.super[c] = (int)find(c);   // reference-clique id of the surviving head, renumbered below
+    } else {
+      for (int64_t c = 0; c < rc; c++) R.super[c] = (int)c;
+    }
+    // renumber R.super to supernode ids (ascending head position among the survivors)
+    {
+      std::vector<int> newid(rc, -1);
+      int k = 0;
+      for (int64_t c = 0; c < rc; c++) if (R.super[c] == (int)c) newid[c] = k++;
+      for (int64_t c = 0; c < rc; c++) R.super[c] = newid[R.super[c]];
+    }
+  }
+  // ---- clique tables (supernodes) ------------------------------------------------------
   std::vector<int64_t> cid(n, -1);
   int64_t nc = 0;
   for (int64_t j = 0; j < n; j++) if (alive[j]) cid[j] = nc++;

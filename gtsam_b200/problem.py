@@ -81,7 +81,10 @@ class CSymbolicInfo(C.Structure):
     _fields_ = [("ncliques", C.c_int64), ("nlevels", C.c_int64), ("total_dim", C.c_int64),
                 ("max_frontal_dim", C.c_int64), ("max_separator_dim", C.c_int64),
                 ("frontal_list_len", C.c_int64), ("separator_list_len", C.c_int64),
-                ("factor_flops", C.c_double), ("front_bytes", C.c_int64)]
+                ("factor_flops", C.c_double), ("front_bytes", C.c_int64),
+                ("supernodes", C.c_int64), ("supernode_levels", C.c_int64), ("supernode_max_frontal_dim", C.c_int64),
+                ("supernode_max_separator_dim", C.c_int64), ("supernode_frontal_list_len", C.c_int64),
+                ("supernode_separator_list_len", C.c_int64), ("supernode_flops", C.c_double)]
 
 
 def _ptr(a: Optional[np.ndarray], ctype):

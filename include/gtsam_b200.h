@@ -179,7 +179,19 @@ typedef struct b200_symbolic_info {
   int64_t frontal_list_len; /* sum over cliques of #frontal variables           */
   int64_t separator_list_len;
   double factor_flops;      /* sum f^3/3 + f^2 s + f s^2                        */
-  int64_t front_bytes;      /* bytes of all frontal matrices                    */
+  int64_t front_bytes;      /* bytes of all frontal matrices (of the supernodes) */
+  /* The fields above describe the junction tree exactly as the reference builds it
+   * (gtsam/inference/JunctionTree-inst.h:63-151): what b200_get_cliques and
+   * b200_get_conditional report.  The device eliminates SUPERNODES: those cliques after
+   * relaxed amalgamation (a non-leaf clique is merged into its parent when that adds few
+   * explicit zeros; same elimination order, same conditionals up to rounding). */
+  int64_t supernodes;
+  int64_t supernode_levels;
+  int64_t supernode_max_frontal_dim;
+  int64_t supernode_max_separator_dim;
+  int64_t supernode_frontal_list_len;
+  int64_t supernode_separator_list_len;
+  double supernode_flops;
 } b200_symbolic_info;
 
 typedef struct b200_ctx b200_ctx;
@@ -403,6 +415,9 @@ int b200_symbolic_info_get(const b200_problem* prob, b200_symbolic_info* info);
  * lengths from b200_symbolic_info; parent: ncliques (-1 for roots). */
 int b200_get_cliques(const b200_problem* prob, int64_t* frontal_ptr, int64_t* frontal_vars,
                      int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
+/* The supernodes the device eliminates (sizes: the supernode_* fields of b200_symbolic_info). */
+int b200_get_supernodes(const b200_problem* prob, int64_t* frontal_ptr, int64_t* frontal_vars,
+                        int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
 
 /* Host-only symbolic phase (no GPU needed): the same junction tree
  * b200_problem_create builds, for inspection and CPU-side tests of a11. */
@@ -412,8 +427,11 @@ int b200_symbolic_get_info(const b200_symbolic* s, b200_symbolic_info* info);
 int b200_symbolic_get_cliques(const b200_symbolic* s, int64_t* frontal_ptr, int64_t* frontal_vars,
                               int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
 int b200_symbolic_get_levels(const b200_symbolic* s, int32_t* level); /* ncliques */
-/* Scatter tables of the assembly (a12): owning clique of every factor by graph position (nfactors entries) and the
- * scalar slot, in that clique's front, of every key of every factor (laid out factor after factor in graph order,
+int b200_symbolic_get_supernodes(const b200_symbolic* s, int64_t* frontal_ptr, int64_t* frontal_vars,
+                                 int64_t* separator_ptr, int64_t* separator_vars, int64_t* parent);
+int b200_symbolic_get_clique_supernode(const b200_symbolic* s, int32_t* supernode); /* ncliques: supernode holding each clique */
+/* Scatter tables of the assembly (a12): owning SUPERNODE of every factor by graph position (nfactors entries) and the
+ * scalar slot, in that supernode's front, of every key of every factor (laid out factor after factor in graph order,
  * each factor's keys in its own key order). */
 int b200_symbolic_get_factor_slots(const b200_symbolic* s, int32_t* clique, int32_t* slots);
 

@@ -260,7 +260,10 @@ def bigfront(_):
     """tests/test_gpu_parity.py::test_big_front_scheme_matches_oracle: the 128-column big-panel scheme with the DMMA
     trailing update (emulated fragment layout) and with the FP64-FMA tile kernel, forced onto mid-size fronts."""
     from gtsam_b200 import datasets
-    for no_dmma in (False, True):
+    for legacy, no_dmma in ((True, False), (True, True), (False, False)):   # last: the tile dataflow (front_df_kernel), the default
+        os.environ.pop("B200_LEGACY_FRONTS", None)
+        if legacy:
+            os.environ["B200_LEGACY_FRONTS"] = "1"
         os.environ["B200_BIG_MIN_N"] = "64"
         if no_dmma:
             os.environ["B200_NO_DMMA"] = "1"
@@ -392,14 +395,14 @@ def coverage(_):
         del dl
         dev.close()
     assert shrunk >= 1
-    os.environ["B200_NO_FUSE_EA"] = "1"
+    os.environ["B200_NO_FUSE_EA"] = "1"; os.environ["B200_LEGACY_FRONTS"] = "1"   # the level-by-level panel / update chain
     try:
         prob = util.load_case("sphere_small_colamd")
         dev = capi.DeviceProblem(ctx, prob)
         util.check_against_dump(dev, prob, util.golden("sphere_small_colamd", "dump1"), 1e-2, 1)
         dev.close()
     finally:
-        os.environ.pop("B200_NO_FUSE_EA")
+        os.environ.pop("B200_NO_FUSE_EA"); os.environ.pop("B200_LEGACY_FRONTS")
 
 
 SCEN = dict(coverage=coverage, midsize=midsize, edge=edge, bigfront=bigfront, gnc=gnc_scenario, typed=typed, fp32=fp32, linear=linear, marginals=marginals, dogleg=dogleg, gn=gn, mirror=linear_mirror)

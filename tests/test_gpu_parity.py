@@ -285,12 +285,38 @@ def test_cuda_edge_cases(gpu_ctx, name):
         assert lm.lambda_() == olm.state.lambda_
 
 
+def test_tile_dataflow_fronts_match_oracle(gpu_ctx):
+    """front_df_kernel (the default): every non-leaf front of the tree factored as tiles of ONE launch (pieces published
+    through flags, Schur complements extend-added across levels inside the launch), on graphs whose fronts span several
+    128 x 32 tiles and several pivot blocks, with supernode amalgamation on: delta, linear error and the root conditional
+    against the oracle, and every reference clique's conditional read back out of its supernode."""
+    for kw in (dict(layers=14, per_ring=24), dict(layers=14, per_ring=24, ordering="reverse")):
+        prob = datasets.make("sphere_tiny", **kw)
+        dev, orc = capi.DeviceProblem(gpu_ctx, prob), O.OracleProblem(prob)
+        info = dev.symbolic_info()
+        assert info.supernode_max_frontal_dim + info.supernode_max_separator_dim >= 256 and info.supernodes < info.ncliques
+        dev.linearize(); orc.linearize()
+        for lam in (0.0, 1e-3):
+            st, e0, e1, _ = dev.solve(lam)
+            so, f0, f1, _ = orc.solve(lam)
+            assert st == so == 0
+            assert util.rel2(dev.get_delta(), orc.get_delta()) <= 1e-8
+            assert abs(e1 - f1) <= 1e-9 * f0
+        worst = 0.0
+        for c in list(range(0, info.ncliques, max(1, info.ncliques // 40))) + [info.ncliques - 1]:
+            a, b = dev.conditional(c), orc.conditional(c)
+            worst = max(worst, np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+        assert worst <= 1e-7, worst
+        dev.close()
+
+
 @pytest.mark.parametrize("no_dmma", [False, True])
 def test_big_front_scheme_matches_oracle(gpu_ctx, monkeypatch, no_dmma):
     """Fronts >= 1024 use 128-column big panels (band updates + one K=128 trailing update, on the
     FP64 tensor path: mma.sync m8n8k4 f64 / DMMA).  Force that scheme on mid-size fronts
     (B200_BIG_MIN_N) so it is covered at a size the oracle finishes in seconds."""
     monkeypatch.setenv("B200_BIG_MIN_N", "64")
+    monkeypatch.setenv("B200_LEGACY_FRONTS", "1")     # the level-by-level panel / update chain of round 1 (kept for A/B)
     if no_dmma:
         monkeypatch.setenv("B200_NO_DMMA", "1")
     for kw in (dict(layers=14, per_ring=24), dict(layers=14, per_ring=24, ordering="reverse")):

@@ -354,10 +354,11 @@ def test_typed_jacobian_consumers_emulated_on_host(emu_cons, case, f32, built):
     capi._check(L.b200_symbolic_create(C.byref(desc), C.byref(h)))
     info = P.CSymbolicInfo()
     L.b200_symbolic_get_info(h, C.byref(info))
-    fp, sp = np.zeros(info.ncliques + 1, dtype=np.int64), np.zeros(info.ncliques + 1, dtype=np.int64)
-    fv, sv = np.zeros(info.frontal_list_len, dtype=np.int64), np.zeros(max(1, info.separator_list_len), dtype=np.int64)
-    par = np.zeros(info.ncliques, dtype=np.int64)
-    L.b200_symbolic_get_cliques(h, capi._ip(fp), capi._ip(fv), capi._ip(sp), capi._ip(sv), capi._ip(par))
+    # the scatter tables address SUPERNODES (the reference's cliques after relaxed amalgamation): what the device assembles into
+    fp, sp = np.zeros(info.supernodes + 1, dtype=np.int64), np.zeros(info.supernodes + 1, dtype=np.int64)
+    fv, sv = np.zeros(info.supernode_frontal_list_len, dtype=np.int64), np.zeros(max(1, info.supernode_separator_list_len), dtype=np.int64)
+    par = np.zeros(info.supernodes, dtype=np.int64)
+    L.b200_symbolic_get_supernodes(h, capi._ip(fp), capi._ip(fv), capi._ip(sp), capi._ip(sv), capi._ip(par))
     arity = np.zeros(prob.nfactors, dtype=np.int64)
     for g in prob.groups:
         pos = g.graph_index if g.graph_index is not None else g.graph_index0 + np.arange(g.count)

@@ -55,7 +55,7 @@ GROUPS = [
 def _build(lib, extra):
     os.makedirs(os.path.dirname(lib), exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "symbolic.cpp")] + [os.path.join(EMU, "cuda_fake_runtime.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "engine.cuh", "factors.cuh", "geometry.cuh", "symbolic.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "front_df.cuh", "engine.cuh", "factors.cuh", "geometry.cuh", "symbolic.h")] + \
         [os.path.join(EMU, "cuda_emu_full.h"), os.path.join(ROOT, "include", "gtsam_b200.h")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         return subprocess.Popen(["g++", "-O1", "-std=c++20", "-w", "-fPIC", "-shared", "-DB200_EMULATE"] + extra +
