@@ -34,7 +34,7 @@ EXPORTS = [
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
     "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
-    "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode",
+    "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode", "b200_measure_fp64_peak",
 ]
 
 
@@ -130,6 +130,7 @@ def lib():
         L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_symbolic_get_supernodes.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_symbolic_get_clique_supernode.argtypes = [vp, C.POINTER(C.c_int32)]
+        L.b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200_symbolic_get_factor_slots.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
@@ -188,6 +189,12 @@ class Context:
         """Join the NCCL communicator (one process per GPU); call before creating problems."""
         _check(self.L.b200_ctx_comm_init(self.h, unique_id, rank, world))
         self.rank, self.world = rank, world
+
+    def measure_fp64_peak(self):
+        """(DMMA TFLOP/s, FMA-pipe TFLOP/s) measured on this device: roofline denominators of the dense-front kernels."""
+        a, b = C.c_double(), C.c_double()
+        _check(self.L.b200_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self) -> int:
         return int(self.L.b200_launch_count(self.h))

@@ -310,7 +310,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
         v.ctrl = p->d_df_sync + 2 * ph; v.done = p->d_df_sync + 4; v.flags = p->d_df_sync + 4 + p->sym.ncliques;
         v.flag_off = p->d_df_flag_off; v.expect = p->d_df_expect;
         v.trace = ph == 0 ? p->d_df_trace : nullptr;
-        launch_k(front_df_kernel, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
+        v.warm_ctas = getenv("B200_DF_NO_WARM") ? 0 : 3 * ctx->sm_count;
+        if (p->df_minb == 3) launch_k(front_df_kernel<3>, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
+        else launch_k(front_df_kernel<2>, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
         ctx->launches++;
       }
     if (L.small_count) {
@@ -1284,9 +1286,13 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     UP(upload(&p->d_df_flag_off, df_flag_off, st));
     UP(upload(&p->d_df_expect, df_expect, st));
     p->df_sync_ints = 4 + S.ncliques + df_nflags;
+    // latency variant (2 CTAs per SM, 252 registers) unless the tree has more tiles than that keeps busy
+    p->df_minb = (p->df_ntasks[0] + p->df_ntasks[1] > 6 * ctx->sm_count) ? 3 : 2;
+    if (const char* e = getenv("B200_DF_MINB")) p->df_minb = atoi(e) == 3 ? 3 : 2;
     B200_CUDA(cudaMalloc((void**)&p->d_df_sync, (size_t)p->df_sync_ints * sizeof(int)));
 #ifndef B200_EMULATE
-    B200_CUDA(cudaFuncSetAttribute(front_df_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDfSmemBytes));
+    B200_CUDA(cudaFuncSetAttribute(front_df_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDfSmemBytes));
+    B200_CUDA(cudaFuncSetAttribute(front_df_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDfSmemBytes));
 #endif
     if (getenv("B200_DF_TRACE") && p->df_ntasks[0]) {
       B200_CUDA(cudaMalloc((void**)&p->d_df_trace, (size_t)p->df_ntasks[0] * 32 * 8));
@@ -1672,6 +1678,35 @@ int b200_profile_enable(b200_problem* p, int on) {
   p->profile = on != 0;
   for (int i = 0; i < PH_COUNT; i++) { p->phase_ms[i] = 0; p->phase_calls[i] = 0; }
   p->ev_used = 0;
+  return B200_OK;
+}
+/* Measured FP64 peaks of this device (roofline denominators of the dense-front kernels): TFLOP/s of the DMMA path and
+ * of the FMA pipe, registers only, every SM full; best of 3 launches. */
+int b200_measure_fp64_peak(b200_ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
+  if (!ctx || !dmma_tflops || !dfma_tflops) { set_error("null argument"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  double* sink = nullptr;
+  B200_CUDA(cudaMalloc((void**)&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  double best[2] = {0, 0};
+  for (int mode = 0; mode < 2; mode++)
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, ctx->stream);
+      launch_plain(fp64_peak_kernel, dim3(blocks), dim3(256), 0, ctx->stream, iters, mode == 0 ? 1 : 0, sink);
+      cudaEventRecord(e1, ctx->stream);
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      // per warp and iteration: 16 DMMA x 512 flop, or 32 FMA x 64 flop
+      const double flop = (double)blocks * 8 * iters * (mode == 0 ? 16.0 * 512.0 : 32.0 * 64.0);
+      if (rep > 0 && ms > 0) best[mode] = std::max(best[mode], flop / (ms * 1e-3) / 1e12);
+      ctx->launches++;
+    }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  *dmma_tflops = best[0]; *dfma_tflops = best[1];
   return B200_OK;
 }
 int b200_profile_phase_count(void) { return PH_COUNT; }

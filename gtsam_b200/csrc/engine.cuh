@@ -176,6 +176,7 @@ struct b200_problem {
   int *d_df_flag_off = nullptr, *d_df_expect = nullptr;
   int* d_df_sync = nullptr;         // [ctrl of phase 0 (2) | ctrl of phase 1 (2) | done per clique | piece flags]: zeroed per solve
   int64_t df_sync_ints = 0;
+  int df_minb = 3;                  // kernel variant: resident CTAs per SM it is compiled for
   unsigned long long* d_df_trace = nullptr;   // B200_DF_TRACE: 32 globaltimer stamps per tile of phase 0
   double* d_partials = nullptr;     // block partial sums
   unsigned* d_counters = nullptr;   // tickets of the last-block reductions

@@ -34,6 +34,12 @@
 // so an L1 line can only hold final values.
 #pragma once
 
+#ifdef B200_EMULATE
+#define B200_NOINLINE
+#else
+#define B200_NOINLINE __noinline__
+#endif
+
 namespace b200 {
 
 constexpr int kDfB = 32;        // block size (rows and columns)
@@ -41,8 +47,11 @@ constexpr int kDfTR = 4;        // row blocks per tile = warps per CTA
 constexpr int kDfLd = 36;       // staged piece: [column][pivot row], 36 doubles per column (conflict-free DMMA fragments)
 constexpr int kDfThreads = 32 * kDfTR;
 constexpr int kDfSpinLimit = 1 << 21;   // x ~100 ns of back-off: ~0.3 s, then abort
-constexpr int kDfLdR = kDfB + 2;   // R_kk rows 16-byte aligned (128-bit broadcast loads in the TRSM / Cholesky)
-constexpr int kDfSmemBytes = ((1 + kDfTR) * kDfB * kDfLd + kDfB * (kDfB + 2) + kDfB * kDfLdR + kDfB) * 8;   // 63 744 B: 3 CTAs per SM
+constexpr int kDfLdR = kDfB + 2;                                   // R_kk rows 16-byte aligned
+// dynamic shared memory, in doubles: [Pc | Pr[4] | Dg 32 x 33 (+pad) | Rk 32 x 34 | invd 32 | rowbuf 2 x 32]
+constexpr int kDfOffPr = kDfB * kDfLd, kDfOffDg = (1 + kDfTR) * kDfB * kDfLd, kDfOffRk = kDfOffDg + kDfB * (kDfB + 2),
+              kDfOffInvd = kDfOffRk + kDfB * kDfLdR, kDfOffRow = kDfOffInvd + kDfB;
+constexpr int kDfSmemBytes = (kDfOffRow + 2 * kDfB) * 8;           // 64 256 B: 3 CTAs per SM
 
 struct DfView {
   const int4* tasks;       // (front, column block, row tile, unused), ticket order
@@ -53,13 +62,16 @@ struct DfView {
   int* done;               // per clique: tiles of children that finished their extend-add
   const int* expect;       // per clique: how many arrivals to wait for before loading
   unsigned long long* trace;   // B200_DF_TRACE: 32 globaltimer stamps per task (nullptr: off)
+  int warm_ctas;           // the first wave of CTAs (one per resident slot) warms the instruction caches before the grid dependency
 };
 
 #if defined(B200_EMULATE)
 #define DF_STAMP(code) do {} while (0)
+#define DF_CYC(code, cyc) do {} while (0)
 #else
 __device__ __forceinline__ unsigned long long df_now() { unsigned long long x; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(x)); return x; }
 // stamp = (event code << 56) | ns, appended to the task's row of the trace (thread 0 only)
+#define DF_CYC(code, cyc) do { if (v.trace && lane == 0 && tr_n < 32) v.trace[(size_t)s_task * 32 + tr_n++] = ((unsigned long long)(code) << 56) | ((unsigned long long)(cyc) & 0x00ffffffffffffffull); } while (0)
 #define DF_STAMP(code) do { if (v.trace && tid == 0 && tr_n < 32) v.trace[(size_t)s_task * 32 + tr_n++] = ((unsigned long long)(code) << 56) | (df_now() & 0x00ffffffffffffffull); } while (0)
 #endif
 
@@ -120,17 +132,106 @@ __device__ __forceinline__ void df_stage(double* dst, const double* M, int n, in
   }
 }
 
-__global__ void __launch_bounds__(kDfThreads, 3)
+// The two latency-critical routines of the pivot chain, each run by ONE warp on a 32 x 32 block in shared memory
+// (D[row][col], lane = column) with the block in REGISTERS while it works.  Measured alone on the B200
+// (profiles/micro/lat_bench.cu): Cholesky 6200 cycles (3.2 us), triangular solve 1870 cycles (0.95 us); dependent DFMA
+// 8 cycles, dependent 64-bit shuffle 63 cycles, dependent DMMA 26 cycles.  Two things were tried and measured worse:
+// round 1's Cholesky with one pair of shuffles per r_ki (250 instructions per pivot: 10-13 us), and versions with the
+// block left in shared memory and rolled loops (compact code, but every term a load-FMA-store chain: 15 us each).
+// The register versions are ~2500 / ~1000 fully unrolled instructions executed once per tile: inlined into the kernel
+// they ran instruction-fetch bound (17 us for the first Cholesky after an L2 flush, 4.6 us after; 4.4 us per solve), so
+// they are real functions (__noinline__: one copy of the code) and the first wave of CTAs runs both once on dummy
+// data BEFORE griddepcontrol.wait — while the previous kernel of the stream is still draining — which pulls the code
+// into L2 and into the instruction caches of every SM.
+//
+// Cholesky: the pivot comes from a per-lane running diagonal (one shuffle: the pivot chain never waits on shared
+// memory), row kk is scaled and written to shared memory once, every lane subtracts r_ki r_kj from its column with
+// r_ki read as 128-bit broadcasts.  Entries below the diagonal are never read (they accumulate garbage).  ks < 32: rows
+// and columns >= ks are padding (identity).  Returns true when a pivot was not positive.
+// (Both take the block as an OFFSET into the kernel's dynamic shared memory, not as a pointer: a pointer argument of a
+// non-inlined function is generic, its loads can neither be LDS nor be merged into 128-bit broadcasts.)
+template <int MINB>   // (one copy per kernel variant: each is compiled under that variant's register budget)
+__device__ B200_NOINLINE bool df_chol32(int d_off, int ks, int lane) {
+  B200_DYN_SMEM(double, df_smem);
+  double (*D)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + d_off);
+  double* rowbuf = df_smem + kDfOffRow;
+  double col[kDfB];
+#pragma unroll
+  for (int ii = 0; ii < kDfB; ii++)
+    col[ii] = (lane < ks && ii <= lane) ? D[ii][lane] : ((ii == lane) ? 1.0 : 0.0);
+  double dg = lane < ks ? D[lane][lane] : 1.0;
+  bool notpd = false;
+#pragma unroll
+  for (int kk = 0; kk < kDfB; kk++) {
+    const double akk = __shfl_sync(0xffffffffu, dg, kk);
+    if (kk < ks && !(akk > 0.0)) notpd = true;
+    const double rinv = rsqrt(akk);                 // one rsqrt (<= 1 ulp) instead of sqrt + divide on the pivot chain
+    const double rr = (lane == kk) ? akk * rinv : col[kk] * rinv;
+    col[kk] = rr;
+    dg -= rr * rr;                                  // the next pivots: no round trip through shared memory
+    double* rb_ = rowbuf + (kk & 1) * kDfB;
+    rb_[lane] = rr;
+    __syncwarp();
+#pragma unroll
+    for (int ii = kk + 1; ii < kDfB; ii++) col[ii] -= rb_[ii] * rr;
+  }
+#pragma unroll
+  for (int ii = 0; ii < kDfB; ii++) D[ii][lane] = (ii <= lane) ? col[ii] : 0.0;
+  __syncwarp();
+  return notpd;
+}
+
+// X = R^-T C in place (D holds C on entry, X on exit; lane = column of the piece): forward substitution, right-looking —
+// once x[qq] is final every later row takes its term, independent FMAs (the left-looking dot products are one 496-long
+// dependent chain).  Rk[row][col] = R_kk with rows 16-byte aligned (kDfLdR), invd = 1 / diag.
+template <int MINB>
+__device__ B200_NOINLINE void df_trsm32(int d_off, int lane) {
+  B200_DYN_SMEM(double, df_smem);
+  double (*D)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + d_off);
+  const double* Rk = df_smem + kDfOffRk;
+  const double* invd = df_smem + kDfOffInvd;
+  double x[kDfB];
+#pragma unroll
+  for (int p = 0; p < kDfB; p++) x[p] = D[p][lane];
+#pragma unroll
+  for (int qq = 0; qq < kDfB; qq++) {
+    x[qq] *= invd[qq];
+#pragma unroll
+    for (int p = qq + 1; p < kDfB; p++) x[p] -= Rk[qq * kDfLdR + p] * x[qq];
+  }
+#pragma unroll
+  for (int p = 0; p < kDfB; p++) D[p][lane] = x[p];
+  __syncwarp();
+}
+
+// MINB = resident CTAs per SM the variant is compiled for: 3 (168 registers: more tiles in flight, the throughput variant
+// for trees with thousands of tiles) or 2 (252 registers: the solve and the Cholesky schedule better — 3000 vs 5300 and
+// 7700 vs 8100 cycles measured in the kernel — the latency variant for small trees).
+template <int MINB>
+__global__ void __launch_bounds__(kDfThreads, MINB)
 front_df_kernel(TreeView t, DfView v, Scalars* sc) {
-  pdl_sync();
   B200_DYN_SMEM(double, df_smem);                                  // kDfSmemBytes, carved up:
   double* Pc = df_smem;                                            // column piece (k, j): the B operand, [column][pivot row]
-  double (*Pr)[kDfB * kDfLd] = (double (*)[kDfB * kDfLd])(df_smem + kDfB * kDfLd);   // row pieces (k, 4r + w): the A operands
-  double (*Dg)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + (1 + kDfTR) * kDfB * kDfLd);   // pivot rows out of the accumulators ((kDfB + 2) * kDfB reserved: keeps Rk 16-byte aligned)
-  double (*Rk)[kDfLdR] = (double (*)[kDfLdR])(df_smem + (1 + kDfTR) * kDfB * kDfLd + kDfB * (kDfB + 2));   // R_kk
-  double* invd = df_smem + (1 + kDfTR) * kDfB * kDfLd + kDfB * (kDfB + 2) + kDfB * kDfLdR;
+  double (*Pr)[kDfB * kDfLd] = (double (*)[kDfB * kDfLd])(df_smem + kDfOffPr);   // row pieces (k, 4r + w): the A operands
+  double (*Dg)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + kDfOffDg);           // pivot rows out of the accumulators
+  double* Rk = df_smem + kDfOffRk;                                 // R_kk: Rk[row * kDfLdR + col]
+  double* invd = df_smem + kDfOffInvd;
   __shared__ int s_task, s_ok;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+#ifndef B200_EMULATE
+  if (blockIdx.x < (unsigned)v.warm_ctas) {
+    // instruction-cache warm-up (see df_chol32): both routines once on an identity block, shared memory only, before
+    // the grid dependency is resolved; every warp, so that each SM sub-partition has fetched the code
+    double (*Dw)[kDfB + 1] = (double (*)[kDfB + 1])Pr[w];
+    for (int ii = 0; ii < kDfB; ii++) { Dw[ii][lane] = (ii == lane) ? 1.0 : 0.0; if (w == 0) Rk[ii * kDfLdR + lane] = (ii == lane) ? 1.0 : 0.0; }
+    if (tid < kDfB) invd[tid] = 1.0;
+    __syncthreads();
+    df_trsm32<MINB>(kDfOffPr + w * kDfB * kDfLd, lane);
+    if (w == 0) (void)df_chol32<MINB>(kDfOffPr, kDfB, lane);
+    __syncthreads();
+  }
+#endif
+  pdl_sync();
   if (tid == 0) { s_task = atomicAdd(v.ctrl, 1); s_ok = 1; }
   __syncthreads();
   if (s_task >= v.ntasks) return;
@@ -148,7 +249,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
   if (v.expect[c] > 0) {
     if (tid == 0 && !df_wait(v.done + c, v.expect[c], v.ctrl)) s_ok = 0;
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
   }
   DF_STAMP(2);    // children arrived
   // ---- this warp's block of -C into the accumulators ----
@@ -174,10 +275,10 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
   for (int k = 0; k < kend; k++) {
     const int wb = k - kDfTR * r;                         // the warp that holds pivot block k (< 0: above the tile)
     const int kb = kDfB * k, ks = min(kDfB, f - kb);      // pivot rows
+    const bool need_row = wvalid && i > k && i != j;      // this warp updates rows below the pivot block with a piece of another tile
     if (wb >= 0) {
       // ================= pivot rows live in this tile: X = R_kk^-T C, publish piece (k, j) =================
       if (tid == 0 && !df_wait(flags + k * NB + k, 1, v.ctrl)) s_ok = 0;
-      if (w > wb && wvalid && i != j && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
       if (w == wb) {
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -187,50 +288,53 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
             for (int h = 0; h < 2; h++) Dg[8 * a + g][8 * b + 2 * q + h] = -acc[a][b][h];
       }
       __syncthreads();
-      if (!s_ok) return;
+      if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
       DF_STAMP(3);
-      for (int e = tid; e < kDfB * kDfB; e += kDfThreads) {       // R_kk (upper), identity beyond the pivots
+      for (int e = tid; e < kDfB * kDfB; e += kDfThreads) {       // R_kk (upper): one batch of cp.async; zero beyond the pivots
         const int p = e & 31, x = e >> 5;
-        Rk[p][x] = (p <= x && x < ks) ? __ldcg(M + (kb + p) + (size_t)(kb + x) * n) : ((p == x) ? 1.0 : 0.0);
+        double* d = Rk + p * kDfLdR + x;
+        if (p <= x && x < ks) cp_async8(d, M + (kb + p) + (size_t)(kb + x) * n);
+        else *d = 0.0;
       }
-      if (w > wb && wvalid && i != j) df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
       cp_async_commit();
+      cp_async_wait<0>();
       __syncthreads();
-      if (tid < kDfB) invd[tid] = 1.0 / Rk[tid][tid];
+      if (tid < kDfB) invd[tid] = tid < ks ? 1.0 / Rk[tid * kDfLdR + tid] : 1.0;
       __syncthreads();
       DF_STAMP(4);
       if (w == wb) {
-        double x[kDfB];
-#pragma unroll
-        for (int p = 0; p < kDfB; p++) x[p] = (p < ks && lane < cs) ? Dg[p][lane] : 0.0;
-        // forward substitution, right-looking: once x[qq] is final every later row takes its term — independent
-        // FMAs (the left-looking dot products were one 496-long dependent chain: 2.5 us per piece on the B200)
-#pragma unroll
-        for (int qq = 0; qq < kDfB; qq++) {
-          x[qq] *= invd[qq];
-#pragma unroll
-          for (int p = qq + 1; p < kDfB; p++) x[p] -= Rk[qq][p] * x[qq];
-        }
-#pragma unroll
+        const long long c0_ = clock64();
+        df_trsm32<MINB>(kDfOffDg, lane);
+        if (wb == 0) DF_CYC(21, clock64() - c0_);   // (only warp 0 shares the trace cursor with thread 0)
+#pragma unroll 8
         for (int p = 0; p < kDfB; p++) {
-          Pc[lane * kDfLd + p] = x[p];
-          if (p < ks && lane < cs) M[(kb + p) + (size_t)(cb + lane) * n] = x[p];
+          const double xp = (p < ks && lane < cs) ? Dg[p][lane] : 0.0;
+          Pc[lane * kDfLd + p] = xp;
+          if (p < ks && lane < cs) M[(kb + p) + (size_t)(cb + lane) * n] = xp;
         }
       }
-      cp_async_wait<0>();
       __syncthreads();
       DF_STAMP(5);
       if (tid == 0) df_st_release(flags + k * NB + j, 1);   // release = fence + store
       DF_STAMP(6);
+      // only now the pieces of the other tiles (the rows below the pivot block): the TRSM above never waits for them
+      if (need_row) {
+        if (lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
+        __syncwarp();
+        df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+      }
     } else {
       // ================= pivot block above the tile: fetch the two pieces =================
       if (tid == 0 && !df_wait(flags + k * NB + j, 1, v.ctrl)) s_ok = 0;
-      if (wvalid && i != j && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
+      if (need_row && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
       __syncthreads();
-      if (!s_ok) return;
+      if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
       DF_STAMP(7);
       df_stage(Pc, M, n, kb, ks, cb, cs, tid, kDfThreads);
-      if (wvalid && i != j) df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
+      if (need_row) df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
       cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
@@ -253,70 +357,45 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
       }
     }
     __syncthreads();   // the staged pieces are overwritten by the next step
+    if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
     DF_STAMP(9);
   }
   if (diag_tile) {
+    // ================= diagonal block: Cholesky by one warp, publish R_kk =================
     const int k = j, wb = k - kDfTR * r, kb = kDfB * k, ks = min(kDfB, f - kb);
-      // ================= diagonal block: Cholesky by one warp, publish R_kk =================
-      DF_STAMP(10);
-      if (w == wb) {
+    DF_STAMP(10);
+    if (w == wb) {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int b = 0; b < 4; b++)
+        for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int h = 0; h < 2; h++) Dg[8 * a + g][8 * b + 2 * q + h] = -acc[a][b][h];
-        __syncwarp();
-        // Cholesky of the 32 x 32 block by ONE warp: lane j keeps column j in registers.  Step kk: the pivot comes from a
-        // per-lane running diagonal (one shuffle), row kk is scaled and written to shared memory once, every lane then
-        // subtracts r_ki r_kj with r_ki read as 128-bit broadcasts.  (Round 1 fetched every r_ki with its own pair of
-        // shuffles under a predicate: 250 instructions per pivot, 10-13 us per block on the B200 — the critical path
-        // of the whole solve.)  Entries below the diagonal are never read: they are left to accumulate garbage.
-        double col[kDfB];
-#pragma unroll
-        for (int ii = 0; ii < kDfB; ii++)
-          col[ii] = (lane < ks && ii <= lane) ? Dg[ii][lane] : ((ii == lane) ? 1.0 : 0.0);
-        double dg = lane < ks ? Dg[lane][lane] : 1.0;
-        double* rowbuf = &Rk[0][0];        // 2 x 32 doubles (R_kk staging is not in use in a diagonal tile)
-        bool notpd = false;
-#pragma unroll
-        for (int kk = 0; kk < kDfB; kk++) {
-          const double akk = __shfl_sync(0xffffffffu, dg, kk);
-          if (kk < ks && !(akk > 0.0)) notpd = true;
-          const double rinv = rsqrt(akk);                 // one rsqrt (<= 1 ulp) instead of sqrt + divide on the pivot chain
-          const double rr = (lane == kk) ? akk * rinv : col[kk] * rinv;
-          col[kk] = rr;
-          dg -= rr * rr;                                  // the next pivots: no round trip through shared memory
-          double* rb_ = rowbuf + (kk & 1) * kDfB;
-          rb_[lane] = rr;
-          __syncwarp();
-#pragma unroll
-          for (int ii = kk + 1; ii < kDfB; ii++) col[ii] -= rb_[ii] * rr;
+          for (int h = 0; h < 2; h++) Dg[8 * a + g][8 * b + 2 * q + h] = -acc[a][b][h];
+      __syncwarp();
+      const long long c0_ = clock64();
+      const bool notpd = df_chol32<MINB>(kDfOffDg, ks, lane);
+      if (wb == 0) DF_CYC(20, clock64() - c0_);
+      if (lane == 0) {
+        bool bad = notpd;     // (the pivots are broadcast: every lane saw the same)
+        // the reference's underconstrained test on the last two pivots (gtsam/base/cholesky.cpp:144-157)
+        if (k == K - 1) {
+          if (f >= 2) {
+            const double r2 = ks >= 2 ? Dg[ks - 2][ks - 2] : __ldcg(M + (f - 2) + (size_t)(f - 2) * n);
+            if (!(dexp(r2) - dexp(Dg[ks - 1][ks - 1]) < 12)) bad = true;
+          } else if (!(dexp(Dg[0][0]) > -12)) bad = true;
         }
-#pragma unroll
-        for (int ii = 0; ii < kDfB; ii++) Dg[ii][lane] = (ii <= lane) ? col[ii] : 0.0;
-        __syncwarp();
-        if (lane == 0) {
-          bool bad = notpd;     // (the pivots are broadcast: every lane saw the same)
-          // the reference's underconstrained test on the last two pivots (gtsam/base/cholesky.cpp:144-157)
-          if (k == K - 1) {
-            if (f >= 2) {
-              const double r2 = ks >= 2 ? Dg[ks - 2][ks - 2] : __ldcg(M + (f - 2) + (size_t)(f - 2) * n);
-              if (!(dexp(r2) - dexp(Dg[ks - 1][ks - 1]) < 12)) bad = true;
-            } else if (!(dexp(Dg[0][0]) > -12)) bad = true;
-          }
-          if (bad) atomicMax(&sc->fail_code, INT_MAX - c);
-        }
-        if (lane < ks) {
-#pragma unroll
-          for (int ii = 0; ii < kDfB; ii++)
-            if (ii <= lane) M[(kb + ii) + (size_t)(kb + lane) * n] = col[ii];
-        }
+        if (bad) atomicMax(&sc->fail_code, INT_MAX - c);
       }
-      __syncthreads();
-      DF_STAMP(11);
-      if (tid == 0) df_st_release(flags + k * NB + k, 1);
-      DF_STAMP(12);
+      if (lane < ks) {
+#pragma unroll 8
+        for (int ii = 0; ii < kDfB; ii++)
+          if (ii <= lane) M[(kb + ii) + (size_t)(kb + lane) * n] = Dg[ii][lane];
+      }
+    }
+    __syncthreads();
+    DF_STAMP(11);
+    if (tid == 0) df_st_release(flags + k * NB + k, 1);
+    DF_STAMP(12);
     // (a pivot column has no trailing rows: nothing to extend-add)
   } else if (wvalid && i >= K) {
     // ---- trailing rows: the Schur complement goes straight into the parent (or stays, for a root) ----
@@ -355,6 +434,43 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
     if (tid == 0) { __threadfence(); atomicAdd(v.done + par, 1); }
   }
   DF_STAMP(14);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Roofline denominators measured on the device the bench runs on (MEASURED_PEAKS.json holds HBM and bf16 only):
+// register-resident FP64 throughput of the tensor path (mma.sync.m8n8k4.f64, 512 flop per warp instruction) and of
+// the FMA pipe (64 flop per warp instruction), 16 independent accumulator chains per warp, every SM full.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, int use_dmma, double* sink) {
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+  double af[4], bf[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) { af[a] = 1e-3 * (threadIdx.x + a); bf[a] = 1e-3 * (blockIdx.x + a); }
+  if (use_dmma) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) { acc[a][b][0] = fma(af[a], bf[b], acc[a][b][0]); acc[a][b][1] = fma(bf[a], af[b], acc[a][b][1]); }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) s += acc[a][b][0] + acc[a][b][1];
+  if (s == 12345.678) *sink = s;   // keeps the loop alive
 }
 
 }  // namespace b200

@@ -14,6 +14,8 @@ AmalgOptions amalg_options_from_env() {
   if (getenv("B200_NO_AMALGAMATE")) o.tol = -1.0;
   if (const char* e = getenv("B200_AMALG_TOL")) o.tol = atof(e);
   if (const char* e = getenv("B200_AMALG_SMALL")) o.small = atoi(e);
+  if (const char* e = getenv("B200_AMALG_THIN_F")) o.thin_f = atoi(e);
+  if (const char* e = getenv("B200_AMALG_THIN_TOL")) o.thin_tol = atof(e);
   return o;
 }
 
@@ -169,7 +171,8 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
         if (R.level[c] == 0 && R.nf[c] <= amalg.leaf_max_f) continue;   // leaves keep their own (fused) kernels
         const int64_t p = find(R.parent[c]);
         const int64_t width = F[p] + Sd[p], fill = width - Sd[c];
-        if ((double)fill <= amalg.tol * (double)width || F[c] + Sd[c] < amalg.small) {
+        if ((double)fill <= amalg.tol * (double)width || F[c] + Sd[c] < amalg.small ||
+            (F[c] <= amalg.thin_f && (double)fill <= amalg.thin_tol * (double)width)) {
           into[c] = p; F[p] += F[c]; any = true;
         }
       }

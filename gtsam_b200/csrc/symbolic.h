@@ -55,13 +55,14 @@ struct Symbolic {
 // Relaxed supernode amalgamation (numeric tree only; the reference's cliques are kept in Symbolic::ref):
 // a non-leaf clique c is merged into its parent p when the explicit zeros this adds to c's rows,
 // (f_p + s_p - s_c) columns, are at most `amalg_tol` of the parent's width f_p + s_p, or when c is tiny
-// (f_c + s_c < amalg_small).  sep(c) is a subset of front(p) U sep(p), so the merged supernode has frontals
+// (f_c + s_c < amalg_small), or when c is thin (f_c <= thin_f pivots: a whole front life cycle — load, one pivot step,
+// extend-add, a level of the tree — for a handful of pivots) and the zeros stay below thin_tol of the width.  sep(c) is a subset of front(p) U sep(p), so the merged supernode has frontals
 // F_c U F_p (in elimination order) and the parent's separator; structurally-zero entries stay exactly 0.0
 // through the dense partial Cholesky, so every conditional [R S d] of the reference's cliques can be read
 // back out of the supernode.  amalg_tol < 0 disables (supernodes == reference cliques).  Camera chains of
 // BAL graphs (6-pivot cliques with 600-1200 separator columns, one per level) collapse into their parents:
 // bal_c4_metis 25 -> 8 levels, 899 -> 279 MB of fronts, +5 % flops.
-struct AmalgOptions { double tol = 0.15; int small = 48; int leaf_max_f = 6; };
+struct AmalgOptions { double tol = 0.15; int small = 48; int leaf_max_f = 6; int thin_f = 24; double thin_tol = 0.5; };
 AmalgOptions amalg_options_from_env();
 
 // fptr (nfactors+1) / fkeys: CSR of the variable ids of every factor by graph position, in the

