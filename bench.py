@@ -492,10 +492,12 @@ def sharded_parity(prob, dev, lm, ctx, dist, rank, local, world, jac32, st):
     import numpy as np
     import torch
     from gtsam_b200 import capi, optimizer
-    lam = 1e-5
-    dev.restore_values()
+    if os.environ.get("B200_BENCH_NO_PARITY"):
+        return None
+    lam = 1e-2          # diagonal damping (Ceres-style): well conditioned, so delta is comparable to ~1e-10; the LM iteration
+    dev.restore_values()   # compared below runs the bench's own additive lambda0 = 1e-5
     dev.linearize()
-    status, e0, e1, _ = dev.solve(lam)
+    status, e0, e1, _ = dev.solve(lam, True)
     d = torch.from_numpy(dev.get_delta()).cuda()
     hi, lo = d.clone(), d.clone()
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -509,7 +511,7 @@ def sharded_parity(prob, dev, lm, ctx, dist, rank, local, world, jac32, st):
         if jac32:
             solo.set_jacobian_precision(True)
         solo.linearize()
-        s1, f0, f1, _ = solo.solve(lam)
+        s1, f0, f1, _ = solo.solve(lam, True)
         d1 = solo.get_delta()
         slm = optimizer.LevenbergMarquardtOptimizer(solo_ctx, prob, device_problem=solo)
         # single-GPU time of the same graph: 3 warm + 5 timed iterations, CUDA events on the solo stream
@@ -529,7 +531,7 @@ def sharded_parity(prob, dev, lm, ctx, dist, rank, local, world, jac32, st):
                "linear_error_rel": abs(e1 - f1) / abs(f1), "error_after_rel": abs(st.error - slm.error()) / abs(slm.error()),
                "single_gpu_same_graph_ms_per_step": solo_ms,
                "note": "rank 0 solved the same graph unsharded (second context, no communicator) after the timed region: delta of the "
-                       "damped solve (lambda 1e-5) combined over the ranks' views, linear error, error after one LM iteration; "
+                       "damped solve (lambda 1e-2, diagonal damping) combined over the ranks' views, linear error, error after one LM iteration; "
                        "single_gpu_same_graph_ms_per_step = that unsharded problem timed warm, L2 not flushed, 5 iterations",
                "check_s": time.perf_counter() - t0}
         del slm

@@ -155,6 +155,7 @@ static void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
 
 static int allreduce_sum(b200_problem* p, double* buf, size_t n);
 static int allreduce_max_int(b200_problem* p, int* buf, size_t n);
+static int reduce_top_stage(b200_problem* p, size_t stage);
 
 static int reduce_blocks(int64_t count, int threads, int sm) {
   int64_t b = (count + threads - 1) / threads;
@@ -219,6 +220,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     PhaseScope ps(p, PH_MEMSET);
     if (p->zero_doubles) B200_CUDA(cudaMemsetAsync(p->d_arena, 0, (size_t)p->zero_doubles * sizeof(double), st));
     if (p->df_sync_ints) B200_CUDA(cudaMemsetAsync(p->d_df_sync, 0, (size_t)p->df_sync_ints * sizeof(int), st));
+    if (p->topx_doubles && p->d_topx) B200_CUDA(cudaMemsetAsync(p->d_topx, 0, (size_t)p->topx_doubles * sizeof(double), st));
   }
   {
     PhaseScope ps(p, PH_ASSEMBLE);
@@ -293,7 +295,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   }
   // ---- elimination, leaves to roots ----
   for (size_t l = 0; l < p->levels.size(); l++) {
-    if ((int)l == p->n_sub_levels && ctx->world > 1) {
+    if ((int)l == p->n_sub_levels && ctx->world > 1 && !p->top_staged) {
       // the one exchange step of the solve — every rank has eliminated its own subtrees
       // into its copy of the shared top fronts; sum them (NCCL over NVLink, in place, on-stream)
       PhaseScope ps(p, PH_ALLREDUCE);
@@ -301,20 +303,38 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (rc) return rc;
     }
     const LevelPlan& L = p->levels[l];
+    auto launch_df = [&](int slot, const int4* tasks, int ntasks, bool trace) {
+      DfView v;
+      v.tasks = tasks; v.ntasks = ntasks;
+      v.ctrl = p->d_df_sync + 2 * slot; v.done = p->d_df_sync + p->df_ctrl_ints; v.flags = v.done + p->sym.ncliques;
+      v.flag_off = p->d_df_flag_off; v.expect = p->d_df_expect;
+      v.trace = trace ? p->d_df_trace : nullptr;
+      v.warm_ctas = getenv("B200_DF_NO_WARM") ? 0 : 3 * ctx->sm_count;
+      if (p->df_minb == 3) launch_k(front_df_kernel<3>, dim3(ntasks), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
+      else launch_k(front_df_kernel<2>, dim3(ntasks), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
+      ctx->launches++;
+    };
     for (int ph = 0; ph < 2; ph++)
-      if ((int)l == p->df_level[ph] && p->df_ntasks[ph]) {
+      if ((int)l == p->df_level[ph] && p->df_ntasks[ph] && !(ph == 1 && p->top_staged)) {
         // every remaining non-leaf front of the phase, all levels, as one tile dataflow (front_df.cuh)
         PhaseScope ps(p, PH_ELIM_LARGE);
-        DfView v;
-        v.tasks = p->d_df_tasks[ph]; v.ntasks = p->df_ntasks[ph];
-        v.ctrl = p->d_df_sync + 2 * ph; v.done = p->d_df_sync + 4; v.flags = p->d_df_sync + 4 + p->sym.ncliques;
-        v.flag_off = p->d_df_flag_off; v.expect = p->d_df_expect;
-        v.trace = ph == 0 ? p->d_df_trace : nullptr;
-        v.warm_ctas = getenv("B200_DF_NO_WARM") ? 0 : 3 * ctx->sm_count;
-        if (p->df_minb == 3) launch_k(front_df_kernel<3>, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
-        else launch_k(front_df_kernel<2>, dim3(p->df_ntasks[ph]), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
-        ctx->launches++;
+        launch_df(ph, p->d_df_tasks[ph], p->df_ntasks[ph], ph == 0);
       }
+    if (p->top_staged)
+      for (size_t s = 0; s < p->ts_level.size(); s++)
+        if (p->ts_level[s] == (int)l) {
+          {
+            // SURVEY 8e, the exchange step, per top level: every rank's partial copy of the level's fronts (the Schur
+            // complements of its own subtrees and of the top fronts it owns below) is summed onto the front's owner
+            PhaseScope ps(p, PH_ALLREDUCE);
+            const int rc = reduce_top_stage(p, s);
+            if (rc) return rc;
+          }
+          if (p->ts_task_count[s]) {
+            PhaseScope ps(p, PH_ELIM_LARGE);
+            launch_df(2 + (int)s, p->d_df_tasks[1] + p->ts_task_begin[s], p->ts_task_count[s], false);
+          }
+        }
     if (L.small_count) {
       PhaseScope ps(p, PH_ELIM_SMALL);
       const int nb = (L.small_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -380,6 +400,19 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
                                                                p->d_delta, p->d_scalars);
       ctx->launches++;
     }
+    if (p->top_staged)
+      for (size_t s = 0; s < p->ts_level.size(); s++)
+        if (p->ts_level[s] == l) {
+          // the owners' solutions of this top level -> packed vector -> one small all-reduce (zeros from the others) -> delta everywhere
+          const int nfr = p->ts_begin[s + 1] - p->ts_begin[s];
+          launch_k(top_x_kernel, dim3(nfr), dim3(128), 0, st, t, (const int*)(p->d_ts_cliques + p->ts_begin[s]), (const int*)(p->d_ts_xoff + p->ts_begin[s]),
+                   (const int*)(p->d_ts_owned + p->ts_begin[s]), p->d_delta, p->d_topx, 0);
+          const int rc = allreduce_sum(p, p->d_topx + p->ts_x_begin[s], (size_t)p->ts_x_count[s]);
+          if (rc) return rc;
+          launch_k(top_x_kernel, dim3(nfr), dim3(128), 0, st, t, (const int*)(p->d_ts_cliques + p->ts_begin[s]), (const int*)(p->d_ts_xoff + p->ts_begin[s]),
+                   (const int*)(p->d_ts_owned + p->ts_begin[s]), p->d_delta, p->d_topx, 1);
+          ctx->launches += 2;
+        }
     for (int kd = 0; kd < 2; kd++) {
       if (!L.bpoint_count[kd]) continue;
       const int nb = (int)(((int64_t)L.bpoint_count[kd] * 8 + 127) / 128);
@@ -663,7 +696,7 @@ static int pack_linear(const b200_linear_desc* d, Packed* pk) {
 // together).  Factors follow the clique that owns them; factors of top cliques belong to rank 0.
 static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int world, std::vector<char>* fused,
                        std::vector<char>* is_top, std::vector<int>* clique_owner, std::vector<int>* factor_owner,
-                       bool allow_leaf = true) {
+                       bool allow_leaf = true, std::vector<int>* top_owner = nullptr) {
   // the fused leaf kernels evaluate typed factor groups: never for the JacobianFactor groups of a linear problem
   const bool leaf_path = allow_leaf && ngroups <= kMaxGroups && !getenv("B200_NO_LEAF_FUSION");
   const int64_t nc = S.ncliques;
@@ -742,6 +775,28 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
       else (*clique_owner)[c] = (*clique_owner)[S.parent[c]];
     }
   }
+  // owners of the top fronts: level by level (a level's fronts are independent), heaviest first onto the rank with the
+  // least work so far AT THAT LEVEL (what bounds a stage is its busiest owner), ties to the globally least loaded
+  if (top_owner) {
+    top_owner->assign(nc, -1);
+    if (world > 1) {
+      std::vector<double> total_load(world, 0.0);
+      for (int64_t l = 0; l < S.nlevels; l++) {
+        std::vector<int64_t> at;
+        for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) if ((*is_top)[S.lvl_cliques[q]]) at.push_back(S.lvl_cliques[q]);
+        auto wt = [&](int64_t c) { const double nn = S.nf[c] + S.ns[c] + 1; return nn * nn * (S.nf[c] + 1); };
+        std::sort(at.begin(), at.end(), [&](int64_t a, int64_t b) { return wt(a) != wt(b) ? wt(a) > wt(b) : a < b; });
+        std::vector<double> load(world, 0.0);
+        for (int64_t c : at) {
+          int best = 0;
+          for (int r = 1; r < world; r++)
+            if (load[r] < load[best] || (load[r] == load[best] && total_load[r] < total_load[best])) best = r;
+          (*top_owner)[c] = best;
+          load[best] += wt(c); total_load[best] += wt(c);
+        }
+      }
+    }
+  }
   factor_owner->assign(total, 0);
   for (int64_t pos = 0; pos < total; pos++) {
     const int o = (*clique_owner)[S.fac_clique[pos]];
@@ -755,6 +810,9 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, ncclUniqueIdBlob, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -766,6 +824,9 @@ static int nccl_load() {
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, ncclUniqueIdBlob, int))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(h, "ncclReduce");
+  g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { set_error("libnccl.so.2 lacks required symbols"); return B200_NCCL_ERROR; }
@@ -784,6 +845,19 @@ enum { kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 
 static int allreduce_sum(b200_problem* p, double* buf, size_t n) {
   if (p->ctx->world <= 1 || n == 0) return B200_OK;
   B200_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, p->ctx->comm, p->ctx->stream));
+  p->ctx->launches++;
+  return B200_OK;
+}
+// one stage of the distributed top: the ranks' partial copies of every front of the level, summed onto the front's owner
+// (ncclReduce in place; one group, so the fronts of the level travel concurrently over NVLink)
+static int reduce_top_stage(b200_problem* p, size_t s) {
+  if (!g_nccl.Reduce || !g_nccl.GroupStart || !g_nccl.GroupEnd) { set_error("libnccl.so.2 lacks ncclReduce / ncclGroupStart"); return B200_NCCL_ERROR; }
+  B200_NCCL(g_nccl.GroupStart());
+  for (int q = p->ts_begin[s]; q < p->ts_begin[s + 1]; q++) {
+    const auto& tf = p->ts_fronts[q];
+    B200_NCCL(g_nccl.Reduce(p->d_arena + tf.off, p->d_arena + tf.off, (size_t)tf.count, kNcclFloat64, kNcclSum, tf.owner, p->ctx->comm, p->ctx->stream));
+  }
+  B200_NCCL(g_nccl.GroupEnd());
   p->ctx->launches++;
   return B200_OK;
 }
@@ -929,6 +1003,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_marg_work); cudaFree(p->d_marg_path); cudaFree(p->d_marg_out); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_df_tasks[0]); cudaFree(p->d_df_tasks[1]); cudaFree(p->d_df_flag_off); cudaFree(p->d_df_expect); cudaFree(p->d_df_sync); cudaFree(p->d_df_trace);
+  cudaFree(p->d_ts_cliques); cudaFree(p->d_ts_xoff); cudaFree(p->d_ts_owned); cudaFree(p->d_topx);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
@@ -991,9 +1066,10 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   UP(upload(&p->d_var_dof, var_dof, st));
   // ---- storage plan: fused leaf cliques keep only their f x n conditional; sharding -----
   std::vector<char> fused, is_top;
-  std::vector<int> clique_owner, factor_owner;
-  shard_plan(S, ngroups, total, ctx->world, &fused, &is_top, &clique_owner, &factor_owner, /*allow_leaf=*/d != nullptr);
+  std::vector<int> clique_owner, factor_owner, top_owner;
+  shard_plan(S, ngroups, total, ctx->world, &fused, &is_top, &clique_owner, &factor_owner, /*allow_leaf=*/d != nullptr, &top_owner);
   const int rank = ctx->rank;
+  p->top_staged = ctx->world > 1 && getenv("B200_REPLICATED_TOP") == nullptr && getenv("B200_LEGACY_FRONTS") == nullptr;
   std::vector<int> fused_list;   // the fused leaf cliques THIS rank owns
   for (int64_t c = 0; c < S.ncliques; c++)
     if (fused[c] && clique_owner[c] == rank) fused_list.push_back((int)c);
@@ -1086,13 +1162,20 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     for (int pass = 0; pass < 2; pass++) {   // replicated top first: it is the all-reduced region
       for (int64_t c = 0; c < S.ncliques; c++)
         if (!fused[c] && (is_top[c] != 0) == (pass == 0)) {
-          const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = (int)nn; o += nn * nn;
+          const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_ld[c] = (int)nn;
+          // the fronts of other ranks' subtrees take no storage here (nothing on this rank ever touches them)
+          if (pass == 1 && clique_owner[c] != rank) { p->h_off[c] = 0; continue; }
+          p->h_off[c] = o; o += nn * nn;
         }
       if (pass == 0) p->top_doubles = o;
     }
     p->zero_doubles = o;   // everything below is accumulated into by atomics: zeroed per solve
     for (int64_t c = 0; c < S.ncliques; c++)
-      if (fused[c]) { const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_off[c] = o; p->h_ld[c] = S.nf[c]; o += (int64_t)S.nf[c] * nn; }
+      if (fused[c]) {
+        const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_ld[c] = S.nf[c];
+        if (clique_owner[c] != rank) { p->h_off[c] = 0; continue; }
+        p->h_off[c] = o; o += (int64_t)S.nf[c] * nn;
+      }
     p->arena_doubles = o;
     p->h_off[S.ncliques] = o;
   }
@@ -1217,11 +1300,15 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   std::vector<int4> df_tasks[2];
   std::vector<int> df_flag_off(S.ncliques, 0), df_expect(S.ncliques, 0), df_tiles(S.ncliques, 0);
   int64_t df_nflags = 0;
-  auto in_phase = [&](int phase, int c) { return phase == 0 ? (!is_top[c] && clique_owner[c] == rank) : (is_top[c] != 0); };
+  if (!p->use_df) p->top_staged = false;
+  auto in_phase = [&](int phase, int c) {
+    return phase == 0 ? (!is_top[c] && clique_owner[c] == rank) : (is_top[c] != 0 && (!p->top_staged || top_owner[c] == rank));
+  };
   if (p->use_df)
     for (int phase = 0; phase < 2; phase++)
       for (int64_t c = 0; c < S.ncliques; c++)
         if (in_phase(phase, (int)c) && !fused[c] && S.nf[c] + S.ns[c] + 1 > kSmallMaxN) df_first[phase] = std::min(df_first[phase], S.level[c]);
+  if (p->top_staged) df_first[1] = 0;     // every top front goes through its stage's reduce + dataflow launch
   for (int phase = 0; phase < 2; phase++)
   for (int64_t l = 0; l < S.nlevels; l++) {
     LevelPlan& L = p->levels[phase * S.nlevels + l];
@@ -1231,10 +1318,11 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     L.bsmall_begin = (int)bsmall.size();
     L.blarge_begin = (int)blarge.size();
     std::vector<int> pts[2];
+    const size_t stage_task_begin = df_tasks[1].size();
     for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
-      if (phase == 0 ? (is_top[c] || clique_owner[c] != rank) : !is_top[c]) continue;
+      if (!in_phase(phase, c)) continue;
       if (fused[c]) {
         // eliminated by the leaf kernels; back-substituted 8 lanes per point / one warp per clique
         if (leaf_kind[c] > 0 && !getenv("B200_NO_POINT_BACKSUB")) pts[leaf_kind[c] - 1].push_back(c);
@@ -1276,8 +1364,38 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     L.small_count = (int)small.size() - L.small_begin;
     L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
     L.large_count = (int)large.size() - L.large_begin;
+    if (phase == 1 && p->top_staged) {
+      // the stage of this top level: ALL its fronts (whoever owns them: they are reduced onto their owners), this rank's tiles
+      const int f0 = (int)p->ts_fronts.size();
+      const int64_t x0 = p->topx_doubles;
+      for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
+        const int c = S.lvl_cliques[q];
+        if (!is_top[c]) continue;
+        const int64_t nn = S.nf[c] + S.ns[c] + 1;
+        p->ts_fronts.push_back({p->h_off[c], nn * nn, top_owner[c], c});
+        p->topx_doubles += S.nf[c];
+      }
+      if ((int)p->ts_fronts.size() > f0) {
+        p->ts_level.push_back((int)(S.nlevels + l));
+        p->ts_begin.push_back(f0);
+        p->ts_task_begin.push_back((int)stage_task_begin);
+        p->ts_task_count.push_back((int)(df_tasks[1].size() - stage_task_begin));
+        p->ts_x_begin.push_back((int)x0);
+        p->ts_x_count.push_back((int)(p->topx_doubles - x0));
+      }
+    }
   }
-  if (df_nflags + S.ncliques + 4 > (int64_t)INT_MAX) FAIL(B200_INVALID_ARGUMENT, "front dataflow: flag table exceeds 2^31 entries");
+  p->ts_begin.push_back((int)p->ts_fronts.size());
+  if (p->top_staged && !p->ts_fronts.empty()) {
+    std::vector<int> tc, tx, to;
+    int64_t x = 0;
+    for (auto& tf : p->ts_fronts) { tc.push_back(tf.clique); tx.push_back((int)x); to.push_back(tf.owner == rank ? 1 : 0); x += S.nf[tf.clique]; }
+    UP(upload(&p->d_ts_cliques, tc, st));
+    UP(upload(&p->d_ts_xoff, tx, st));
+    UP(upload(&p->d_ts_owned, to, st));
+    B200_CUDA(cudaMalloc((void**)&p->d_topx, (size_t)std::max<int64_t>(1, p->topx_doubles) * sizeof(double)));
+  }
+  if (df_nflags + S.ncliques + 4 * (S.nlevels + 2) > (int64_t)INT_MAX) FAIL(B200_INVALID_ARGUMENT, "front dataflow: flag table exceeds 2^31 entries");
   for (int phase = 0; phase < 2; phase++) {
     p->df_ntasks[phase] = (int)df_tasks[phase].size();
     if (p->df_ntasks[phase]) UP(upload(&p->d_df_tasks[phase], df_tasks[phase], st));
@@ -1285,7 +1403,8 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   if (p->df_ntasks[0] + p->df_ntasks[1]) {
     UP(upload(&p->d_df_flag_off, df_flag_off, st));
     UP(upload(&p->d_df_expect, df_expect, st));
-    p->df_sync_ints = 4 + S.ncliques + df_nflags;
+    p->df_ctrl_ints = 2 * (2 + (int)S.nlevels);     // (ticket, abort) per launch: the two phases + one per stage of the top
+    p->df_sync_ints = p->df_ctrl_ints + S.ncliques + df_nflags;
     // latency variant (2 CTAs per SM, 252 registers) unless the tree has more tiles than that keeps busy
     p->df_minb = (p->df_ntasks[0] + p->df_ntasks[1] > 6 * ctx->sm_count) ? 3 : 2;
     if (const char* e = getenv("B200_DF_MINB")) p->df_minb = atoi(e) == 3 ? 3 : 2;

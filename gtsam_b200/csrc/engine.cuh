@@ -176,8 +176,20 @@ struct b200_problem {
   int *d_df_flag_off = nullptr, *d_df_expect = nullptr;
   int* d_df_sync = nullptr;         // [ctrl of phase 0 (2) | ctrl of phase 1 (2) | done per clique | piece flags]: zeroed per solve
   int64_t df_sync_ints = 0;
+  int df_ctrl_ints = 4;
   int df_minb = 3;                  // kernel variant: resident CTAs per SM it is compiled for
   unsigned long long* d_df_trace = nullptr;   // B200_DF_TRACE: 32 globaltimer stamps per tile of phase 0
+  // sharded solve, distributed top: every front of the top of the tree has an OWNER rank; per top level
+  // ("stage") the ranks' partial fronts are summed onto their owners (ncclReduce, grouped), the owners factor them
+  // (front_df_kernel over their tiles of the stage) and extend-add into their copy of the parent; back-substitution
+  // walks the stages downwards, the owners' solutions travel in a packed vector (one small all-reduce per stage)
+  bool top_staged = false;
+  struct TopFront { int64_t off, count; int owner, clique; };
+  std::vector<TopFront> ts_fronts;              // all top fronts, grouped by stage
+  std::vector<int> ts_level, ts_begin, ts_task_begin, ts_task_count, ts_x_begin, ts_x_count;   // per stage (ts_begin has nstages + 1 entries)
+  int *d_ts_cliques = nullptr, *d_ts_xoff = nullptr, *d_ts_owned = nullptr;
+  double* d_topx = nullptr;
+  int64_t topx_doubles = 0;
   double* d_partials = nullptr;     // block partial sums
   unsigned* d_counters = nullptr;   // tickets of the last-block reductions
   int partial_cap = 0;

@@ -66,6 +66,7 @@ struct DfView {
 };
 
 #if defined(B200_EMULATE)
+static inline long long clock64() { return 0; }
 #define DF_STAMP(code) do {} while (0)
 #define DF_CYC(code, cyc) do {} while (0)
 #else
@@ -434,6 +435,22 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
     if (tid == 0) { __threadfence(); atomicAdd(v.done + par, 1); }
   }
   DF_STAMP(14);
+}
+
+// Sharded solve, distributed top: the solutions of the top fronts a rank owns travel to the other ranks in a packed vector.
+// scatter = 0: topx <- delta for the fronts this rank owns (the others leave zeros); scatter = 1: delta <- topx (all fronts).
+__global__ void __launch_bounds__(128) top_x_kernel(TreeView t, const int* __restrict__ cliques, const int* __restrict__ xoff,
+                                                    const int* __restrict__ owned, double* delta, double* topx, int scatter) {
+  pdl_sync();
+  const int c = cliques[blockIdx.x];
+  if (!scatter && !owned[blockIdx.x]) return;
+  const int f = t.nf[c];
+  const int* di = t.didx + t.didx_ptr[c];
+  double* x = topx + xoff[blockIdx.x];
+  for (int i = threadIdx.x; i < f; i += 128) {
+    if (scatter) delta[di[i]] = x[i];
+    else x[i] = delta[di[i]];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -106,6 +106,19 @@ int ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int op,
   }
   return 0;
 }
+// ncclReduce: the sum lands on `root` only (the other ranks' receive buffers stay as they are) — through the all-reduce
+// path into a scratch buffer, then copied on the root.  Group calls are no-ops: every rank issues the same sequence.
+int ncclReduce(const void* send, void* recv, size_t count, int dtype, int op, int root, void* comm, void* stream) {
+  Comm* c = (Comm*)comm;
+  const size_t el = dtype == 8 ? 8 : 4;
+  char* tmp = (char*)malloc(count * el + 8);
+  const int rc = ncclAllReduce(send, tmp, count, dtype, op, comm, stream);
+  if (rc == 0 && c->rank == root) memcpy(recv, tmp, count * el);
+  free(tmp);
+  return rc;
+}
+int ncclGroupStart() { return 0; }
+int ncclGroupEnd() { return 0; }
 int ncclCommDestroy(void* comm) {
   Comm* c = (Comm*)comm;
   munmap((void*)c->h, c->bytes);
