@@ -90,7 +90,7 @@ static EvalCtx ectx(const b200_problem* p, const double* values) {
 // ---- built-in phase timers (the reference has gttic/gttoc, gtsam/base/timing.h:245-302):
 // CUDA events on the launching stream, resolved at the next host sync. -----------------
 enum Phase { PH_LINEARIZE = 0, PH_MEMSET, PH_ASSEMBLE, PH_DAMP, PH_ELIM_SMALL, PH_ELIM_LARGE, PH_BACKSUB,
-             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_LINEARIZE_MINOR, PH_LEAF_SCHUR, PH_COUNT };
+             PH_LINERR, PH_RETRACT, PH_ERROR, PH_LEAF, PH_ALLREDUCE, PH_LINEARIZE_MINOR, PH_LEAF_SCHUR, PH_TOPX, PH_COUNT };
 struct PhaseScope {
   b200_problem* p; int ph; size_t idx; bool on;
   PhaseScope(b200_problem* p_, int ph_) : p(p_), ph(ph_), idx(0), on(p_->profile) {
@@ -309,6 +309,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       v.ctrl = p->d_df_sync + 2 * slot; v.done = p->d_df_sync + p->df_ctrl_ints; v.flags = v.done + p->sym.ncliques;
       v.flag_off = p->d_df_flag_off; v.expect = p->d_df_expect;
       v.trace = trace ? p->d_df_trace : nullptr;
+      v.winv = p->d_winv; v.winv_off = p->d_winv_off;
       v.warm_ctas = getenv("B200_DF_NO_WARM") ? 0 : 3 * ctx->sm_count;
       if (p->df_minb == 3) launch_k(front_df_kernel<3>, dim3(ntasks), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
       else launch_k(front_df_kernel<2>, dim3(ntasks), dim3(kDfThreads), (size_t)kDfSmemBytes, st, t, v, p->d_scalars);
@@ -391,7 +392,8 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
     if (L.blarge_count) {
       const int nblk = (L.blarge_max_nf + kBsRows - 1) / kBsRows;
       launch_k(backsub_large_kernel, dim3(dim3(nblk, L.blarge_count)), dim3(256), 0, st, t, p->d_lvl_blarge + L.blarge_begin, p->d_delta, p->d_scalars,
-                                                                      p->d_bs_flags, p->d_bs_flag_base, L.blarge_begin, 1);
+                                                                      p->d_bs_flags, p->d_bs_flag_base, L.blarge_begin, 1,
+                                                                      (const double*)p->d_winv, (const int64_t*)p->d_winv_off);
       ctx->launches++;
     }
     if (L.bsmall_count) {
@@ -404,6 +406,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       for (size_t s = 0; s < p->ts_level.size(); s++)
         if (p->ts_level[s] == l) {
           // the owners' solutions of this top level -> packed vector -> one small all-reduce (zeros from the others) -> delta everywhere
+          PhaseScope px(p, PH_TOPX);    // (inside the back_substitute scope: counted in both)
           const int nfr = p->ts_begin[s + 1] - p->ts_begin[s];
           launch_k(top_x_kernel, dim3(nfr), dim3(128), 0, st, t, (const int*)(p->d_ts_cliques + p->ts_begin[s]), (const int*)(p->d_ts_xoff + p->ts_begin[s]),
                    (const int*)(p->d_ts_owned + p->ts_begin[s]), p->d_delta, p->d_topx, 0);
@@ -722,7 +725,10 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
       w[c] += nn * nn * (S.nf[c] + 1) + 200.0 * (double)nfac[c];
       if (S.parent[c] >= 0) w[S.parent[c]] += w[c]; else sum += w[c];
     }
-    const double target = sum / (4.0 * world);
+    // (subtrees lighter than total / (top_factor * world): a deeper top balances better, a shallower one has fewer levels —
+    //  each a communication stage of the distributed top — and less of the tree in the exchanged region)
+    static const double top_factor = getenv("B200_TOP_FACTOR") ? atof(getenv("B200_TOP_FACTOR")) : 4.0;
+    const double target = sum / (top_factor * world);
     std::vector<std::pair<double, int64_t>> heap;
     for (int64_t c = 0; c < nc; c++) if (S.parent[c] < 0) heap.push_back({w[c], c});
     std::make_heap(heap.begin(), heap.end());
@@ -851,6 +857,14 @@ static int allreduce_sum(b200_problem* p, double* buf, size_t n) {
 // one stage of the distributed top: the ranks' partial copies of every front of the level, summed onto the front's owner
 // (ncclReduce in place; one group, so the fronts of the level travel concurrently over NVLink)
 static int reduce_top_stage(b200_problem* p, size_t s) {
+  static const bool use_reduce = getenv("B200_TOP_REDUCE") != nullptr;
+  if (!use_reduce) {
+    // the level's fronts are one contiguous range of the arena: ONE all-reduce (NVLS in-switch reduction on NVSwitch: measured
+    // 2.4x faster than the grouped ncclReduce onto the owners, which moves every rank's full copy along a chain)
+    const auto& f0 = p->ts_fronts[p->ts_begin[s]];
+    const auto& f1 = p->ts_fronts[p->ts_begin[s + 1] - 1];
+    return allreduce_sum(p, p->d_arena + f0.off, (size_t)(f1.off + f1.count - f0.off));
+  }
   if (!g_nccl.Reduce || !g_nccl.GroupStart || !g_nccl.GroupEnd) { set_error("libnccl.so.2 lacks ncclReduce / ncclGroupStart"); return B200_NCCL_ERROR; }
   B200_NCCL(g_nccl.GroupStart());
   for (int q = p->ts_begin[s]; q < p->ts_begin[s + 1]; q++) {
@@ -1003,6 +1017,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_marg_work); cudaFree(p->d_marg_path); cudaFree(p->d_marg_out); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_df_tasks[0]); cudaFree(p->d_df_tasks[1]); cudaFree(p->d_df_flag_off); cudaFree(p->d_df_expect); cudaFree(p->d_df_sync); cudaFree(p->d_df_trace);
+  cudaFree(p->d_winv); cudaFree(p->d_winv_off);
   cudaFree(p->d_ts_cliques); cudaFree(p->d_ts_xoff); cudaFree(p->d_ts_owned); cudaFree(p->d_topx);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
@@ -1159,14 +1174,19 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   p->h_ld.assign(S.ncliques, 0);
   {
     int64_t o = 0;
+    std::vector<int64_t> order(S.ncliques);     // top fronts level by level: a stage of the distributed top is one contiguous range
+    for (int64_t c = 0; c < S.ncliques; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return (is_top[a] ? S.level[a] : -1) < (is_top[b] ? S.level[b] : -1); });
     for (int pass = 0; pass < 2; pass++) {   // replicated top first: it is the all-reduced region
-      for (int64_t c = 0; c < S.ncliques; c++)
+      for (int64_t oc = 0; oc < S.ncliques; oc++) {
+        const int64_t c = pass == 0 ? order[oc] : oc;
         if (!fused[c] && (is_top[c] != 0) == (pass == 0)) {
           const int64_t nn = S.nf[c] + S.ns[c] + 1; p->h_ld[c] = (int)nn;
           // the fronts of other ranks' subtrees take no storage here (nothing on this rank ever touches them)
           if (pass == 1 && clique_owner[c] != rank) { p->h_off[c] = 0; continue; }
           p->h_off[c] = o; o += nn * nn;
         }
+      }
       if (pass == 0) p->top_doubles = o;
     }
     p->zero_doubles = o;   // everything below is accumulated into by atomics: zeroed per solve
@@ -1401,6 +1421,12 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     if (p->df_ntasks[phase]) UP(upload(&p->d_df_tasks[phase], df_tasks[phase], st));
   }
   if (p->df_ntasks[0] + p->df_ntasks[1]) {
+    std::vector<int64_t> woff(S.ncliques, -1);
+    int64_t wtot = 0;
+    for (int64_t c = 0; c < S.ncliques; c++)
+      if (df_tiles[c]) { woff[c] = wtot; wtot += (int64_t)((S.nf[c] + kDfB - 1) / kDfB) * kDfB * kDfB; }
+    UP(upload(&p->d_winv_off, woff, st));
+    B200_CUDA(cudaMalloc((void**)&p->d_winv, (size_t)std::max<int64_t>(1, wtot) * sizeof(double)));
     UP(upload(&p->d_df_flag_off, df_flag_off, st));
     UP(upload(&p->d_df_expect, df_expect, st));
     p->df_ctrl_ints = 2 * (2 + (int)S.nlevels);     // (ticket, abort) per launch: the two phases + one per stage of the top
@@ -1832,7 +1858,7 @@ int b200_profile_phase_count(void) { return PH_COUNT; }
 const char* b200_profile_phase_name(int i) {
   static const char* names[PH_COUNT] = {"linearize", "memset_fronts", "assemble", "damp", "eliminate_small",
                                         "eliminate_large", "back_substitute", "linear_error", "retract", "error",
-                                        "leaf_fused", "allreduce_top", "linearize_small_groups", "leaf_schur"};
+                                        "leaf_fused", "allreduce_top", "linearize_small_groups", "leaf_schur", "backsub_exchange"};
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 int b200_profile_get(b200_problem* p, double* ms, int64_t* calls) {

@@ -183,6 +183,8 @@ struct b200_problem {
   // ("stage") the ranks' partial fronts are summed onto their owners (ncclReduce, grouped), the owners factor them
   // (front_df_kernel over their tiles of the stage) and extend-add into their copy of the parent; back-substitution
   // walks the stages downwards, the owners' solutions travel in a packed vector (one small all-reduce per stage)
+  double* d_winv = nullptr;         // W = R_kk^-1 of every factored 32 x 32 diagonal block (front_df_kernel), for back-substitution
+  int64_t* d_winv_off = nullptr;    // per clique: offset into d_winv (-1: none)
   bool top_staged = false;
   struct TopFront { int64_t off, count; int owner, clique; };
   std::vector<TopFront> ts_fronts;              // all top fronts, grouped by stage

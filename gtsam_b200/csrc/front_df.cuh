@@ -62,6 +62,8 @@ struct DfView {
   int* done;               // per clique: tiles of children that finished their extend-add
   const int* expect;       // per clique: how many arrivals to wait for before loading
   unsigned long long* trace;   // B200_DF_TRACE: 32 globaltimer stamps per task (nullptr: off)
+  double* winv;            // inverses of the factored 32 x 32 diagonal blocks (back-substitution): per front winv_off + 1024 k
+  const int64_t* winv_off;
   int warm_ctas;           // the first wave of CTAs (one per resident slot) warms the instruction caches before the grid dependency
 };
 
@@ -208,6 +210,28 @@ __device__ B200_NOINLINE void df_trsm32(int d_off, int lane) {
 // MINB = resident CTAs per SM the variant is compiled for: 3 (168 registers: more tiles in flight, the throughput variant
 // for trees with thousands of tiles) or 2 (252 registers: the solve and the Cholesky schedule better — 3000 vs 5300 and
 // 7700 vs 8100 cycles measured in the kernel — the latency variant for small trees).
+// W = R^-1 of the factored diagonal block (D holds R, upper), written to global memory column-major (wout[j * 32 + i] =
+// W[i][j]): lane = column j of W, right-looking back substitution in registers (2700 cycles measured alone).  It runs AFTER
+// the block has been published — off the pivot chain — and turns the 32 x 32 triangular solves of back-substitution
+// (32 dependent shuffle steps each) into matrix-vector products.
+template <int MINB>
+__device__ B200_NOINLINE void df_inv32(int d_off, int lane, double* wout) {
+  B200_DYN_SMEM(double, df_smem);
+  double (*D)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + d_off);
+  double s[kDfB];   // s[i] = e_j[i] - sum_{m > i} R[i][m] w[m]
+#pragma unroll
+  for (int i = 0; i < kDfB; i++) s[i] = (i == lane) ? 1.0 : 0.0;
+  const double dinv = 1.0 / D[lane][lane];
+#pragma unroll
+  for (int m = kDfB - 1; m >= 0; m--) {
+    s[m] *= __shfl_sync(0xffffffffu, dinv, m);      // w[m] (zero for m > lane)
+#pragma unroll
+    for (int i = 0; i < m; i++) s[i] -= D[i][m] * s[m];
+  }
+#pragma unroll
+  for (int i = 0; i < kDfB; i++) wout[lane * kDfB + i] = s[i];
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kDfThreads, MINB)
 front_df_kernel(TreeView t, DfView v, Scalars* sc) {
@@ -397,6 +421,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
     DF_STAMP(11);
     if (tid == 0) df_st_release(flags + k * NB + k, 1);
     DF_STAMP(12);
+    if (w == wb && v.winv) df_inv32<MINB>(kDfOffDg, lane, v.winv + v.winv_off[c] + (size_t)k * kDfB * kDfB);
     // (a pivot column has no trailing rows: nothing to extend-add)
   } else if (wvalid && i >= K) {
     // ---- trailing rows: the Schur complement goes straight into the parent (or stays, for a root) ----

@@ -1532,12 +1532,13 @@ backsub_point_kernel(TreeView t, const int* __restrict__ list, int count, double
 
 __global__ void __launch_bounds__(256)
 backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Scalars* sc, int* flags,
-                     const int* __restrict__ flag_base, int list_begin, int epoch) {
+                     const int* __restrict__ flag_base, int list_begin, int epoch,
+                     const double* __restrict__ winv, const int64_t* __restrict__ winv_off) {
   pdl_sync();
   __shared__ double part[4][kBsRows];
   __shared__ double rhs[kBsRows];
   __shared__ double Dg[3][32][33];   // [0]: rows 0..31 diag, [1]: rows 32..63 diag, [2]: coupling rows 0..31 x cols 32..63
-  __shared__ double invd[kBsRows];
+  __shared__ double invd[kBsRows];   // (with W: Dg[0] / Dg[1] hold W_lo / W_hi column-major, Dg[b][j][i] = W[i][j])
   const int c = list[blockIdx.y];
   const int f = t.nf[c], s = t.ns[c], n = f + s + 1;
   const int nblk = (f + kBsRows - 1) / kBsRows;
@@ -1548,13 +1549,20 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
   const int* di = t.didx + t.didx_ptr[c];
   int* fl = flags + flag_base[list_begin + blockIdx.y];
   const int tid = threadIdx.x, row = tid & (kBsRows - 1), q = tid >> 6, lane = tid & 31, warp = tid >> 5;
-  // stage this block's 64x64 upper-triangular diagonal block now: it overlaps with the waits below
+  // front_df_kernel left W = R_kk^-1 of every 32 x 32 diagonal block: the two triangular solves become matrix-vector products
+  const double* W = (winv && winv_off && winv_off[c] >= 0) ? winv + winv_off[c] + (size_t)(2 * rb) * 1024 : nullptr;
+  // stage this block's diagonal data now: it overlaps with the waits below
   for (int e = tid; e < 3 * 1024; e += 256) {
     const int blk = e >> 10, i = e & 31, j = (e >> 5) & 31;
-    const int gi = (blk == 1 ? 32 : 0) + i, gj = (blk == 0 ? 0 : 32) + j;
     double v = 0.0;
-    if (gi < nr && gj < nr && gi <= gj) v = M[(r0 + gi) + (size_t)(r0 + gj) * n];
-    Dg[blk][i][j] = v;
+    if (W && blk < 2) {
+      if (blk == 0 || nr > 32) v = W[(size_t)blk * 1024 + j * 32 + i];     // coalesced over i; Dg[blk][j][i] = W_blk[i][j]
+      Dg[blk][j][i] = v;
+    } else {
+      const int gi = (blk == 1 ? 32 : 0) + i, gj = (blk == 0 ? 0 : 32) + j;
+      if (gi < nr && gj < nr && gi <= gj) v = M[(r0 + gi) + (size_t)(r0 + gj) * n];
+      Dg[blk][i][j] = v;
+    }
   }
   double acc = 0.0;
   if (row < nr) {
@@ -1562,35 +1570,55 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
     for (int cc = q; cc < s; cc += 4) acc += Mr[(size_t)(f + cc) * n] * delta[di[f + cc]];
   }
   for (int jb = nblk - 1; jb > rb; jb--) {
+    // the entries of R are there before the solution is: fetch them ahead of the wait (the last wait is the pivot chain)
+    const int c0 = jb * kBsRows, c1 = min(f, c0 + kBsRows);
+    double rv[kBsRows / 4];
+#pragma unroll
+    for (int u = 0; u < kBsRows / 4; u++) {
+      const int j = c0 + q + 4 * u;
+      rv[u] = (row < nr && j < c1) ? M[(r0 + row) + (size_t)j * n] : 0.0;
+    }
     if (tid == 0) {
       int spins = 0;   // bounded: a scheduling surprise must never hang the GPU
+#ifdef B200_EMULATE
       while (atomicAdd(fl + jb, 0) != epoch && ++spins < (1 << 22)) {}
+#else
+      while (df_ld_relaxed(fl + jb) != epoch && ++spins < (1 << 22)) {}
+      df_fence_acquire();
+#endif
       if (spins >= (1 << 22)) atomicMax(&sc->nan_code, INT_MAX - c);
-      __threadfence();
     }
     __syncthreads();
-    const int c0 = jb * kBsRows, c1 = min(f, c0 + kBsRows);
-    if (row < nr) {
-      const double* Mr = M + r0 + row;
-      for (int j = c0 + q; j < c1; j += 4) acc += Mr[(size_t)j * n] * __ldcg(delta + di[j]);
+#pragma unroll
+    for (int u = 0; u < kBsRows / 4; u++) {
+      const int j = c0 + q + 4 * u;
+      if (j < c1) acc += rv[u] * __ldcg(delta + di[j]);
     }
   }
   part[q][row] = acc;
   __syncthreads();
-  if (tid < nr) {
-    rhs[tid] = M[r0 + tid + (size_t)(n - 1) * n] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
-    invd[tid] = 1.0 / Dg[tid >> 5][tid & 31][tid & 31];
+  if (tid < kBsRows) {
+    rhs[tid] = tid < nr ? M[r0 + tid + (size_t)(n - 1) * n] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) : 0.0;
+    if (!W) invd[tid] = tid < nr ? 1.0 / Dg[tid >> 5][tid & 31][tid & 31] : 1.0;
   }
   __syncthreads();
   if (warp == 0) {   // one warp: solve rows 32..63, apply the coupling block, solve rows 0..31
     for (int sb = (nr > 32 ? 1 : 0); sb >= 0; sb--) {
       const int b0 = 32 * sb, nb = min(32, nr - b0);
-      double xv = lane < nb ? rhs[b0 + lane] : 0.0;
-      for (int k = nb - 1; k >= 0; k--) {
-        const double xk = __shfl_sync(0xffffffffu, xv, k) * invd[b0 + k];
-        if (lane == k) xv = xk;
-        else if (lane < k) xv -= Dg[sb][lane][k] * xk;
+      double xv;
+      if (W) {
+        xv = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) xv += Dg[sb][j][lane] * rhs[b0 + j];   // x = W rhs (W upper: zero below the diagonal)
+      } else {
+        xv = lane < nb ? rhs[b0 + lane] : 0.0;
+        for (int k = nb - 1; k >= 0; k--) {
+          const double xk = __shfl_sync(0xffffffffu, xv, k) * invd[b0 + k];
+          if (lane == k) xv = xk;
+          else if (lane < k) xv -= Dg[sb][lane][k] * xk;
+        }
       }
+      __syncwarp();
       if (lane < nb) rhs[b0 + lane] = xv;
       __syncwarp();
       if (sb == 1) {
@@ -1608,9 +1636,13 @@ backsub_large_kernel(TreeView t, const int* __restrict__ list, double* delta, Sc
     nan = isnan(rhs[tid]);
   }
   if (nan) atomicMax(&sc->nan_code, INT_MAX - c);
-  __threadfence();
   __syncthreads();
+#ifdef B200_EMULATE
+  __threadfence();
   if (tid == 0) atomicExch(fl + rb, epoch);
+#else
+  if (tid == 0) df_st_release(fl + rb, epoch);
+#endif
 }
 
 // ---------------------------------------------------------------------------
