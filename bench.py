@@ -84,8 +84,9 @@ def workload_config(prob, workload, jac32, world, scaling, flush=True):
                   else "L2 left warm between iterations (--no-flush-l2)"),
         "parallelism": "single GPU" if world == 1 else
         f"{world} ranks, one per GPU, {scaling} scaling: junction-tree subtrees (BAL: the points and the lower camera supernodes) "
-        f"+ their factors sharded by rank, top of the tree replicated, one in-place NCCL all-reduce (FP64 sum over NVLink) of the "
-        f"top fronts per solve + one all-reduce of the LM scalars; value = iterations/s of the graph actually solved",
+        f"+ their factors sharded by rank; the top of the tree is distributed: every top front has an owner, per top level one NCCL "
+        f"all-reduce (FP64 sum over NVLink / NVSwitch) of that level's fronts, the owners factor them; back-substitution exchanges the "
+        f"owners' solutions per level; one all-reduce of the LM scalars per try; value = iterations/s of the graph actually solved",
     }
 
 
@@ -296,12 +297,29 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         capi._check(L.b200_lm_reset(lm.h))      # state <- (values, lambda0); recomputes graph.error
         lm.iterate()
 
-    def step_e2e():
-        dev.set_values(host_values)             # pinned host -> device
-        capi._check(L.b200_lm_reset(lm.h))
-        lm.iterate()
-        out = dev.get_values(host_out)          # device -> pinned host
-        return out, lm.error()
+    # sharded: a rank moves only its share (b200_values_view): in = the variables its factors touch + its cliques' and the
+    # top's frontal variables; out = the variables it owns (rank 0 reports the top); the caller stitches the N owned views
+    if world > 1:
+        idx_in, idx_own = dev.view_index(0), dev.view_index(1)
+        host_in = torch.from_numpy(np.ascontiguousarray(prob.values[idx_in])).pin_memory().numpy()
+        host_own = torch.empty(idx_own.size, dtype=torch.float64).pin_memory().numpy()
+        h2d_bytes, d2h_bytes = int(host_in.nbytes), int(host_own.nbytes) + 64
+
+        def step_e2e():
+            dev.set_values_view(host_in)            # pinned host -> device, this rank's input view
+            capi._check(L.b200_lm_reset(lm.h))
+            lm.iterate()
+            out = dev.get_values_view(host_own)     # device -> pinned host, the variables this rank owns
+            return out, lm.error()
+    else:
+        h2d_bytes, d2h_bytes = int(host_values.nbytes), int(host_values.nbytes) + 64
+
+        def step_e2e():
+            dev.set_values(host_values)             # pinned host -> device
+            capi._check(L.b200_lm_reset(lm.h))
+            lm.iterate()
+            out = dev.get_values(host_out)          # device -> pinned host
+            return out, lm.error()
 
     def barrier():
         if dist is not None:
@@ -426,8 +444,9 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
         "dtype": "f32 Jacobians + f64 solve" if jac32 else "f64",
         "config": workload_config(prob, workload, jac32, world, "weak" if weak else "strong", flush_buf is not None),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_values.nbytes),
-                "d2h_bytes_per_step": int(host_values.nbytes) + 64, "ms_per_step": ms_e2e / steps},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / steps,
+                "note": "single GPU: the whole packed Values both ways" if world == 1 else
+                "per rank (rank 0's counts): its input view up, its owned view down (b200_set_values_view / b200_get_values_view)"},
         "gpu_launches": int(launches),
         "warm_l2": {"ms_per_step": ms_warm / steps, "value": steps / (ms_warm * 1e-3),
                     "note": "same K steps back to back without the L2 flush (information only)"},

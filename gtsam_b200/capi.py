@@ -35,6 +35,7 @@ EXPORTS = [
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
     "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
     "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode", "b200_measure_fp64_peak",
+    "b200_values_view", "b200_set_values_view", "b200_get_values_view",
 ]
 
 
@@ -130,6 +131,9 @@ def lib():
         L.b200_symbolic_get_cliques.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_symbolic_get_supernodes.argtypes = [vp, ip, ip, ip, ip, ip]
         L.b200_symbolic_get_clique_supernode.argtypes = [vp, C.POINTER(C.c_int32)]
+        L.b200_values_view.argtypes = [vp, C.c_int, ip, ip, ip]
+        L.b200_set_values_view.argtypes = [vp, dp]
+        L.b200_get_values_view.argtypes = [vp, dp]
         L.b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200_symbolic_get_factor_slots.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _LIB = L
@@ -285,6 +289,32 @@ class DeviceProblem:
             raise ValueError("noise payload size")
         per = int(pay > 0 and noise.size == pay * g.count and g.count > 1)
         _check(self.L.b200_set_group_noise(self.h, C.c_int64(gi), noise_kind, per, _dp(noise) if noise.size else None))
+
+    def values_view(self, which: int):
+        """Variable ids of a values view of a (sharded) problem: 0 = what this rank needs as input, 1 = what it owns."""
+        nv, nd = C.c_int64(), C.c_int64()
+        _check(self.L.b200_values_view(self.h, which, C.byref(nv), C.byref(nd), None))
+        ids = np.zeros(max(1, nv.value), dtype=np.int64)
+        _check(self.L.b200_values_view(self.h, which, C.byref(nv), C.byref(nd), _ip(ids)))
+        return ids[:nv.value], nd.value
+
+    def view_index(self, which: int):
+        """Indices into the full packed Values of the doubles of a view (host-side gather / stitch)."""
+        ids, nd = self.values_view(which)
+        off = self.prob.val_offsets().astype(np.int64)
+        lens = off[ids + 1] - off[ids]
+        idx = np.repeat(off[ids], lens) + (np.arange(nd) - np.repeat(np.cumsum(lens) - lens, lens))
+        assert idx.size == nd
+        return idx.astype(np.int64)
+
+    def set_values_view(self, packed):
+        assert packed.dtype == np.float64 and packed.flags.c_contiguous
+        _check(self.L.b200_set_values_view(self.h, _dp(packed)))
+
+    def get_values_view(self, out):
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        _check(self.L.b200_get_values_view(self.h, _dp(out)))
+        return out
 
     def get_values(self, out=None):
         """Packed values; pass a page-locked float64 array as ``out`` for a direct D2H copy."""

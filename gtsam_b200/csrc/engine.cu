@@ -176,6 +176,7 @@ static int enqueue_error(b200_problem* p, const double* values, double* slot) {
   }
   if (first) B200_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), st));
   B200_CUDA(cudaGetLastError());
+  if (p->defer_scalar_reduce) return B200_OK;   // an LM try reduces all its scalars in one all-reduce (enqueue_try)
   return allreduce_sum(p, slot, 1);   // sharded: partial sums over the rank's own factors
 }
 
@@ -448,7 +449,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   }
   if (first) B200_CUDA(cudaMemsetAsync(&p->d_scalars->lin_err0, 0, 2 * sizeof(double), st));
   B200_CUDA(cudaGetLastError());
-  if (ctx->world > 1) {
+  if (ctx->world > 1 && !p->defer_scalar_reduce) {
     int rc = allreduce_sum(p, &p->d_scalars->lin_err0, 2);          // lin_err0, lin_err_delta are adjacent
     if (rc) return rc;
     rc = allreduce_max_int(p, &p->d_scalars->fail_code, 2);          // every rank takes the same decision
@@ -727,7 +728,8 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
     }
     // (subtrees lighter than total / (top_factor * world): a deeper top balances better, a shallower one has fewer levels —
     //  each a communication stage of the distributed top — and less of the tree in the exchanged region)
-    static const double top_factor = getenv("B200_TOP_FACTOR") ? atof(getenv("B200_TOP_FACTOR")) : 4.0;
+    // measured at 8 GPUs on the 10M-factor graph: factor 4 -> 4.57 ms per iteration, 2 -> 4.18, 1 -> 3.72
+    static const double top_factor = getenv("B200_TOP_FACTOR") ? atof(getenv("B200_TOP_FACTOR")) : 1.5;
     const double target = sum / (top_factor * world);
     std::vector<std::pair<double, int64_t>> heap;
     for (int64_t c = 0; c < nc; c++) if (S.parent[c] < 0) heap.push_back({w[c], c});
@@ -890,9 +892,23 @@ static int allreduce_max_int(b200_problem* p, int* buf, size_t n) {
 static int enqueue_try(b200_problem* p, int diagonal, double min_diag, double max_diag) {
   int rc = reset_flags(p);
   if (rc) return rc;
+  // sharded: the scalars LM branches on (two linear errors, the new error, the two failure codes) travel in ONE
+  // all-reduce at the end of the try instead of three latency-bound ones (a SUM over [3 doubles | one slot per rank
+  // for each code]; the maximum of the slots is taken on the device afterwards)
+  const bool merged = p->ctx->world > 1 && p->ctx->world <= kMaxRanksMerged && !getenv("B200_NO_MERGED_SCALARS");
+  p->defer_scalar_reduce = merged;
   rc = enqueue_solve(p, true, diagonal, min_diag, max_diag);
+  if (!rc) rc = enqueue_try_step(p);
+  p->defer_scalar_reduce = false;
+  if (rc || !merged) return rc;
+  if (!p->d_red) B200_CUDA(cudaMalloc((void**)&p->d_red, (3 + 2 * kMaxRanksMerged) * sizeof(double)));
+  cudaStream_t st = p->ctx->stream;
+  launch_k(scalars_pack_kernel, dim3(1), dim3(32), 0, st, p->d_scalars, p->d_red, p->ctx->rank, p->ctx->world, 0);
+  rc = allreduce_sum(p, p->d_red, (size_t)(3 + 2 * p->ctx->world));
   if (rc) return rc;
-  return enqueue_try_step(p);
+  launch_k(scalars_pack_kernel, dim3(1), dim3(32), 0, st, p->d_scalars, p->d_red, p->ctx->rank, p->ctx->world, 1);
+  p->ctx->launches += 2;
+  return B200_OK;
 }
 static int launch_try(b200_problem* p, int diagonal, double min_diag, double max_diag) {
   static const bool no_graph = getenv("B200_NO_GRAPH") != nullptr;
@@ -1017,7 +1033,8 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_lvl_small); cudaFree(p->d_lvl_large); cudaFree(p->d_lvl_bsmall); cudaFree(p->d_lvl_blarge); cudaFree(p->d_marg_work); cudaFree(p->d_marg_path); cudaFree(p->d_marg_out); cudaFree(p->d_lvl_bpoint); cudaFree(p->d_ld);
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_df_tasks[0]); cudaFree(p->d_df_tasks[1]); cudaFree(p->d_df_flag_off); cudaFree(p->d_df_expect); cudaFree(p->d_df_sync); cudaFree(p->d_df_trace);
-  cudaFree(p->d_winv); cudaFree(p->d_winv_off);
+  cudaFree(p->d_winv); cudaFree(p->d_winv_off); cudaFree(p->d_red);
+  cudaFree(p->d_view_idx[0]); cudaFree(p->d_view_idx[1]); cudaFree(p->d_view_buf);
   cudaFree(p->d_ts_cliques); cudaFree(p->d_ts_xoff); cudaFree(p->d_ts_owned); cudaFree(p->d_topx);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
@@ -1462,6 +1479,31 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     for (auto& L : p->levels) maxl = std::max(maxl, L.large_count);
     B200_CUDA(cudaMalloc((void**)&p->d_rdiag, (size_t)maxl * kNB * kNB * sizeof(double)));
   }
+  // ---- values views (sharded problems move only what a rank needs / owns between host and device) ----
+  if (d) {
+    std::vector<char> need(n, ctx->world == 1), own(n, ctx->world == 1);
+    if (ctx->world > 1) {
+      for (int64_t c = 0; c < S.ncliques; c++) {
+        const bool mine = is_top[c] ? true : clique_owner[c] == rank;
+        if (!mine) continue;
+        for (int64_t q = S.front_ptr[c]; q < S.front_ptr[c + 1]; q++) {
+          need[S.front_vars[q]] = 1;
+          if (!is_top[c] || rank == 0) own[S.front_vars[q]] = 1;     // the top's variables are reported by rank 0
+        }
+      }
+      for (int64_t gi = 0; gi < ngroups; gi++)
+        for (auto& k : hkeys[gi]) { need[k.x] = 1; if (k.y >= 0) need[k.y] = 1; }
+    }
+    for (int w = 0; w < 2; w++) {
+      const std::vector<char>& m = w == 0 ? need : own;
+      std::vector<int> idx;
+      for (int64_t v = 0; v < n; v++)
+        if (m[v]) { p->view_vars[w].push_back(v); for (int k = val_off[v]; k < val_off[v + 1]; k++) idx.push_back(k); }
+      p->view_doubles[w] = (int64_t)idx.size();
+      UP(upload(&p->d_view_idx[w], idx, st));
+    }
+    B200_CUDA(cudaMalloc((void**)&p->d_view_buf, (size_t)std::max<int64_t>(1, std::max(p->view_doubles[0], p->view_doubles[1])) * sizeof(double)));
+  }
   // ---- arena + scratch ----
   B200_CUDA(cudaMalloc((void**)&p->d_arena, std::max<int64_t>(1, p->arena_doubles) * sizeof(double)));
   p->partial_cap = 2 * ctx->sm_count * 8;
@@ -1601,6 +1643,43 @@ int b200_set_group_noise(b200_problem* p, int64_t group, int32_t noise_kind, int
   for (int i = 0; i < 2; i++)   // the captured LM try has the group views baked in
     if (p->try_graph[i]) { cudaGraphExecDestroy(p->try_graph[i]); p->try_graph[i] = nullptr; }
   p->linearized = p->solved = p->factored = p->marg_ready = false;
+  return B200_OK;
+}
+
+/* Views of the packed Values of a (sharded) problem: which = 0 the variables this rank needs as INPUT (every variable one of
+ * its factors touches + the frontal variables of its cliques and of the top), which = 1 the variables it OWNS (after a step
+ * their new values are current here: its own subtrees; rank 0 reports the top).  Ascending variable ids; the packed view is
+ * the storage of those variables, concatenated.  With one rank both views are all the variables. */
+int b200_values_view(const b200_problem* p, int which, int64_t* nvars, int64_t* ndoubles, int64_t* var_ids) {
+  if (!p || which < 0 || which > 1 || p->linear) { set_error("bad argument"); return B200_INVALID_ARGUMENT; }
+  if (nvars) *nvars = (int64_t)p->view_vars[which].size();
+  if (ndoubles) *ndoubles = p->view_doubles[which];
+  if (var_ids && !p->view_vars[which].empty()) memcpy(var_ids, p->view_vars[which].data(), p->view_vars[which].size() * sizeof(int64_t));
+  return B200_OK;
+}
+int b200_set_values_view(b200_problem* p, const double* packed) {
+  if (!p || p->linear || !packed) { set_error("bad argument"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  const int64_t nd = p->view_doubles[0];
+  const void* src = packed;
+  if (!is_pinned_host(packed)) { memcpy(p->h_pinned, packed, (size_t)nd * sizeof(double)); src = p->h_pinned; }
+  B200_CUDA(cudaMemcpyAsync(p->d_view_buf, src, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+  launch_plain(values_view_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, p->ctx->stream, p->d_values, p->d_view_buf, (const int*)p->d_view_idx[0], nd, 1);
+  p->ctx->launches++;
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  p->linearized = p->solved = p->marg_ready = false;
+  return B200_OK;
+}
+int b200_get_values_view(b200_problem* p, double* packed) {
+  if (!p || p->linear || !packed) { set_error("bad argument"); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  const int64_t nd = p->view_doubles[1];
+  launch_plain(values_view_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, p->ctx->stream, p->d_values, p->d_view_buf, (const int*)p->d_view_idx[1], nd, 0);
+  p->ctx->launches++;
+  const bool direct = is_pinned_host(packed);
+  B200_CUDA(cudaMemcpyAsync(direct ? (void*)packed : (void*)p->h_pinned, p->d_view_buf, (size_t)nd * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (!direct) memcpy(packed, p->h_pinned, (size_t)nd * sizeof(double));
   return B200_OK;
 }
 

@@ -185,6 +185,13 @@ struct b200_problem {
   // walks the stages downwards, the owners' solutions travel in a packed vector (one small all-reduce per stage)
   double* d_winv = nullptr;         // W = R_kk^-1 of every factored 32 x 32 diagonal block (front_df_kernel), for back-substitution
   int64_t* d_winv_off = nullptr;    // per clique: offset into d_winv (-1: none)
+  // values views of a sharded problem (b200_values_view): [0] what this rank needs as input, [1] what it owns
+  std::vector<int64_t> view_vars[2];
+  int64_t view_doubles[2] = {0, 0};
+  int* d_view_idx[2] = {nullptr, nullptr};   // per packed double: its index in the full packed Values
+  double* d_view_buf = nullptr;
+  bool defer_scalar_reduce = false; // inside an LM try: the scalar all-reduces are merged into one (enqueue_try)
+  double* d_red = nullptr;
   bool top_staged = false;
   struct TopFront { int64_t off, count; int owner, clique; };
   std::vector<TopFront> ts_fronts;              // all top fronts, grouped by stage

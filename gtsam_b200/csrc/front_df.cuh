@@ -462,6 +462,30 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
   DF_STAMP(14);
 }
 
+// packed view <-> full packed Values (b200_set_values_view / b200_get_values_view)
+__global__ void __launch_bounds__(256) values_view_kernel(double* values, double* packed, const int* __restrict__ idx, int64_t n, int to_values) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  if (to_values) values[idx[e]] = packed[e];
+  else packed[e] = values[idx[e]];
+}
+
+// Sharded LM try: [lin_err0, lin_err_delta, new_error | fail code of rank r | nan code of rank r] <-> Scalars (one SUM all-reduce).
+constexpr int kMaxRanksMerged = 16;
+__global__ void scalars_pack_kernel(Scalars* sc, double* red, int rank, int world, int unpack) {
+  pdl_sync();
+  if (threadIdx.x != 0) return;
+  if (!unpack) {
+    red[0] = sc->lin_err0; red[1] = sc->lin_err_delta; red[2] = sc->new_error;
+    for (int r = 0; r < world; r++) { red[3 + r] = r == rank ? (double)sc->fail_code : 0.0; red[3 + world + r] = r == rank ? (double)sc->nan_code : 0.0; }
+  } else {
+    sc->lin_err0 = red[0]; sc->lin_err_delta = red[1]; sc->new_error = red[2];
+    int fc = 0, nc = 0;
+    for (int r = 0; r < world; r++) { fc = max(fc, (int)red[3 + r]); nc = max(nc, (int)red[3 + world + r]); }
+    sc->fail_code = fc; sc->nan_code = nc;
+  }
+}
+
 // Sharded solve, distributed top: the solutions of the top fronts a rank owns travel to the other ranks in a packed vector.
 // scatter = 0: topx <- delta for the fronts this rank owns (the others leave zeros); scatter = 1: delta <- topx (all fronts).
 __global__ void __launch_bounds__(128) top_x_kernel(TreeView t, const int* __restrict__ cliques, const int* __restrict__ xoff,

@@ -451,6 +451,13 @@ int b200_get_conditional(b200_problem* prob, int64_t clique, double* out);
  * an in-place ncclAllReduce (FP64 sum, NVLink) of the top fronts, plus a 2-double / 2-int
  * all-reduce of the scalars LM branches on.  b200_get_values returns this rank's view
  * (owned leaf variables + the replicated top variables are current). */
+/* Sharded problems move only a rank's share of the Values between host and device: view 0 = the variables the rank needs
+ * as input (those its factors touch, the frontal variables of its cliques and of the top), view 1 = the variables it owns
+ * (its own subtrees; rank 0 reports the top) — the new values of a step are current on their owner.  var_ids (ascending,
+ * may be NULL) lists the variables; the packed view is their storage concatenated.  One rank: both views are everything. */
+int b200_values_view(const b200_problem* prob, int which, int64_t* nvars, int64_t* ndoubles, int64_t* var_ids);
+int b200_set_values_view(b200_problem* prob, const double* packed_input_view);
+int b200_get_values_view(b200_problem* prob, double* packed_owned_view);
 int b200_nccl_unique_id(void* out128);
 int b200_ctx_comm_init(b200_ctx* ctx, const void* id128, int rank, int world);
 int b200_shard_plan(const b200_problem_desc* desc, int world, int32_t* clique_owner, int32_t* factor_owner);

@@ -53,6 +53,20 @@ for prob in cases:
         ok &= abs(lm_sh.error() - lm_solo.error()) <= 1e-8 * lm_solo.error()
         ok &= lm_sh.lambda_() == lm_solo.lambda_() and lm_sh.getInnerIterations() == lm_solo.getInnerIterations()
     del lm_sh, lm_solo
+    # values views (b200_values_view): only the input view is uploaded — everything else on the device is poisoned —
+    # and after an LM iteration the owned view equals the single-GPU values of those variables
+    idx_in, idx_own = sh.view_index(0), sh.view_index(1)
+    sh.set_values(np.full(prob.values.size, np.nan))
+    sh.set_values_view(np.ascontiguousarray(prob.values[idx_in]))
+    solo.set_values(prob.values)
+    lm_sh = optimizer.LevenbergMarquardtOptimizer(ctx, prob, device_problem=sh)
+    lm_solo = optimizer.LevenbergMarquardtOptimizer(solo_ctx, prob, device_problem=solo)
+    capi._check(sh.L.b200_lm_reset(lm_sh.h)); capi._check(solo.L.b200_lm_reset(lm_solo.h))
+    lm_sh.iterate(); lm_solo.iterate()
+    ok &= abs(lm_sh.error() - lm_solo.error()) <= 1e-8 * lm_solo.error()
+    mine_v = sh.get_values_view(np.empty(idx_own.size))
+    ok &= bool(np.allclose(mine_v, solo.get_values()[idx_own], rtol=1e-6, atol=1e-6))   # (delta agrees to ~1e-7 relative, see above)
+    del lm_sh, lm_solo
     sh.close(); solo.close()
     print("rank", rank, prob.name, "ok" if ok else "MISMATCH", "owned cliques", int((co == rank).sum()), "top", int((co == -1).sum()), flush=True)
 # the GaussianFactorGraph level, sharded the same way: JacobianFactor / HessianFactor groups split by owning subtree
