@@ -193,6 +193,7 @@ static int enqueue_linearize(b200_problem* p) {
   }
   B200_CUDA(cudaGetLastError());
   p->linearized = true;
+  p->hdiag_valid = false;
   return B200_OK;
 }
 
@@ -236,7 +237,9 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
   }
   if (damped) {
     PhaseScope ps(p, PH_DAMP);
-    if (diagonal) { const int rc = enqueue_hdiag(p); if (rc) return rc; }
+    // hessianDiagonal depends on the linearization only: once per iterate() (b200_lm_iterate computes it right after
+    // linearize, as the reference does, LevenbergMarquardtOptimizer.cpp:293-299), not once per lambda try
+    if (diagonal && !p->hdiag_valid) { const int rc = enqueue_hdiag(p); if (rc) return rc; p->hdiag_valid = true; }
     launch_k(damp_kernel, dim3((int)((p->ndelta + 255) / 256)), dim3(256), 0, st, p->d_arena, p->d_diag_index, (int)p->ndelta, p->d_lambda,
                                                                 diagonal ? p->d_hdiag : nullptr, min_diag, max_diag);
     ctx->launches++;
@@ -726,10 +729,15 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
       w[c] += nn * nn * (S.nf[c] + 1) + 200.0 * (double)nfac[c];
       if (S.parent[c] >= 0) w[S.parent[c]] += w[c]; else sum += w[c];
     }
-    // (subtrees lighter than total / (top_factor * world): a deeper top balances better, a shallower one has fewer levels —
-    //  each a communication stage of the distributed top — and less of the tree in the exchanged region)
-    // measured at 8 GPUs on the 10M-factor graph: factor 4 -> 4.57 ms per iteration, 2 -> 4.18, 1 -> 3.72
-    static const double top_factor = getenv("B200_TOP_FACTOR") ? atof(getenv("B200_TOP_FACTOR")) : 1.5;
+    // Subtrees lighter than total / (top_factor * world).  A deeper top balances better; a shallower one has fewer levels —
+    // each a communication stage of the distributed top — and less of the tree in the exchanged region (measured at 8 GPUs on
+    // the 10M-factor graph: factor 4 -> 4.57 ms per iteration, 2 -> 4.18, 1.5 -> 3.98, 1 -> 3.68).  So: the shallowest top whose
+    // busiest rank stays within 20 % of the mean subtree load, deepening by 1.5x at a time (B200_TOP_FACTOR pins it).
+    std::vector<int> assigned(nc, 0);
+    const double pinned = getenv("B200_TOP_FACTOR") ? atof(getenv("B200_TOP_FACTOR")) : 0.0;
+    for (double top_factor = pinned > 0 ? pinned : 1.0;; top_factor *= 1.5) {
+    is_top->assign(nc, 0);
+    std::fill(assigned.begin(), assigned.end(), 0);
     const double target = sum / (top_factor * world);
     std::vector<std::pair<double, int64_t>> heap;
     for (int64_t c = 0; c < nc; c++) if (S.parent[c] < 0) heap.push_back({w[c], c});
@@ -750,7 +758,6 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
     double subsum = 0;
     for (auto& e : heap) { roots.push_back(e.second); subsum += e.first; }
     std::sort(roots.begin(), roots.end());
-    std::vector<int> assigned(nc, 0);
     double prefix = 0;
     std::vector<double> load(world, 0.0);
     for (int64_t r : roots) {
@@ -774,8 +781,13 @@ static void shard_plan(const Symbolic& S, int64_t ngroups, int64_t total, int wo
       }
       const double worst = *std::max_element(load.begin(), load.end());
       const double worst_lpt = *std::max_element(lpt_load.begin(), lpt_load.end());
-      if (worst_lpt < 0.9 * worst && !getenv("B200_NO_LPT"))
+      double final_worst = worst;
+      if (worst_lpt < 0.9 * worst && !getenv("B200_NO_LPT")) {
         for (int64_t r : roots) assigned[r] = lpt[r];
+        final_worst = worst_lpt;
+      }
+      if (pinned > 0 || top_factor >= 8.0 || final_worst <= 1.2 * subsum / world) break;
+    }
     }
     for (int64_t c = nc - 1; c >= 0; c--) {
       if ((*is_top)[c]) (*clique_owner)[c] = -1;
@@ -914,7 +926,7 @@ static int launch_try(b200_problem* p, int diagonal, double min_diag, double max
   static const bool no_graph = getenv("B200_NO_GRAPH") != nullptr;
   if (no_graph || p->profile || p->ctx->world > 1) return enqueue_try(p, diagonal, min_diag, max_diag);
   const int key = diagonal ? 1 : 0;
-  if (p->try_graph[key] && (p->graph_min_diag != min_diag || p->graph_max_diag != max_diag)) {
+  if (p->try_graph[key] && (p->graph_min_diag[key] != min_diag || p->graph_max_diag[key] != max_diag)) {
     cudaGraphExecDestroy(p->try_graph[key]);
     p->try_graph[key] = nullptr;
   }
@@ -929,7 +941,7 @@ static int launch_try(b200_problem* p, int diagonal, double min_diag, double max
     if (ce != cudaSuccess) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return B200_CUDA_ERROR; }
     B200_CUDA(cudaGraphInstantiate(&p->try_graph[key], graph, 0));
     cudaGraphDestroy(graph);
-    p->graph_min_diag = min_diag; p->graph_max_diag = max_diag;
+    p->graph_min_diag[key] = min_diag; p->graph_max_diag[key] = max_diag;   // the clamps are baked into THIS key's graph
     p->try_launches = p->ctx->launches - launches0;   // kernels inside one replay
     p->ctx->launches = launches0;
   }
@@ -964,6 +976,8 @@ int b200_ctx_create(int device, b200_ctx** out) {
   B200_CUDA(cudaSetDevice(device));
   b200_ctx* c = new b200_ctx();
   c->device = device;
+  // (every early return below releases the context and its stream)
+  struct Guard { b200_ctx* c; ~Guard() { if (c) { if (c->stream) cudaStreamDestroy(c->stream); delete c; } } } guard{c};
   B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   cudaDeviceProp prop;
   B200_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -986,6 +1000,7 @@ int b200_ctx_create(int device, b200_ctx** out) {
   B200_CUDA(cudaFuncSetAttribute(elim_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kWarpsPerBlock * kSmallMaxN * kSmallMaxN * sizeof(double))));
 #endif
+  guard.c = nullptr;
   *out = c;
   return B200_OK;
 }
@@ -1356,6 +1371,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     L.blarge_begin = (int)blarge.size();
     std::vector<int> pts[2];
     const size_t stage_task_begin = df_tasks[1].size();
+    const size_t level_task_begin = df_tasks[phase].size();
     for (int64_t q = S.lvl_ptr[l]; q < S.lvl_ptr[l + 1]; q++) {
       const int c = S.lvl_cliques[q];
       const int nn = S.nf[c] + S.ns[c] + 1;
@@ -1401,6 +1417,14 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     L.small_count = (int)small.size() - L.small_begin;
     L.bsmall_count = (int)bsmall.size() - L.bsmall_begin;
     L.large_count = (int)large.size() - L.large_begin;
+    // ticket order inside a level: by column block first, across ALL the level's fronts (then front, row tile).  A tile of column
+    // j has nothing to wait for once pivot step j is over, so the resident CTAs (2-3 per SM) are the columns next to every front's
+    // pivot — the tiles with work — instead of all the columns of the first few fronts parked on their dependencies while the other
+    // fronts of the level wait for a slot; columns further right start later and catch up at full rate (their pieces are all there).
+    // Dependencies still point to smaller tickets (same front: smaller column, or same column and smaller row tile; children: lower level).
+    if (!getenv("B200_DF_FRONT_ORDER"))
+    std::sort(df_tasks[phase].begin() + (int64_t)level_task_begin, df_tasks[phase].end(), [](const int4& a, const int4& b) {
+      return a.y != b.y ? a.y < b.y : (a.x != b.x ? a.x < b.x : a.z < b.z); });
     if (phase == 1 && p->top_staged) {
       // the stage of this top level: ALL its fronts (whoever owns them: they are reduced onto their owners), this rank's tiles
       const int f0 = (int)p->ts_fronts.size();
@@ -1527,6 +1551,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
 
 // [A|b] blocks as the caller holds them (factor-major, column-major blocks) -> staging buffer -> whitened SoA
 static int upload_jacobian_group(b200_problem* p, b200_problem::Group& g, const double* Ab, const double* sigmas) {
+  p->hdiag_valid = false;
   cudaStream_t st = p->ctx->stream;
   const size_t per = (size_t)g.d * g.ncols, nel = per * (size_t)g.count;
   if (!nel) return B200_OK;
@@ -2187,6 +2212,11 @@ int b200_lm_iterate(b200_lm* lm) {
   B200_CUDA(cudaSetDevice(lm->prob->ctx->device));
   int rc = enqueue_linearize(lm->prob);
   if (rc) return rc;
+  if (lm->params.diagonal_damping) {     // outside the captured try: one hessianDiagonal per linearization
+    rc = enqueue_hdiag(lm->prob);
+    if (rc) return rc;
+    lm->prob->hdiag_valid = true;
+  }
   int done = 0;
   while (!done) {
     rc = try_lambda(lm, &done);
@@ -2484,7 +2514,10 @@ int b200_dl_iterate(b200_dl* dl) {
     }
   }
   if (!zero_step) b200_accept_step(p);
-  else p->linearized = p->solved = p->marg_ready = false;
+  else {
+    B200_CUDA(cudaMemsetAsync(p->d_delta, 0, (size_t)n * sizeof(double), st));   // the reference leaves dx_d = 0 (DoglegOptimizerImpl.h:232-237)
+    p->linearized = p->solved = p->marg_ready = false;
+  }
   dl->error = new_f;
   dl->delta = delta;
   dl->iterations++;

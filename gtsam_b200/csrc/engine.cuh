@@ -164,7 +164,8 @@ struct b200_problem {
   double* d_lambda = nullptr;       // lambda of the current try (device resident)
   double* h_lambda = nullptr;       // pinned
   cudaGraphExec_t try_graph[2] = {nullptr, nullptr};  // LM try (solve + retract + error), by diagonal flag
-  double graph_min_diag = 0, graph_max_diag = 0;
+  double graph_min_diag[2] = {0, 0}, graph_max_diag[2] = {0, 0};
+  bool hdiag_valid = false;         // d_hdiag holds hessianDiagonal of the current linearization
   int64_t try_launches = 0;
   bool fuse_ea = true;              // fold extend_add_kernel into each front's last update
   double* d_rdiag = nullptr;        // factored diagonal blocks published by panel_kernel
