@@ -35,7 +35,7 @@ EXPORTS = [
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
     "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
     "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode", "b200_measure_fp64_peak",
-    "b200_values_view", "b200_set_values_view", "b200_get_values_view",
+    "b200_values_view", "b200_set_values_view", "b200_get_values_view", "b200_get_values_all",
 ]
 
 
@@ -134,6 +134,7 @@ def lib():
         L.b200_values_view.argtypes = [vp, C.c_int, ip, ip, ip]
         L.b200_set_values_view.argtypes = [vp, dp]
         L.b200_get_values_view.argtypes = [vp, dp]
+        L.b200_get_values_all.argtypes = [vp, dp]
         L.b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200_symbolic_get_factor_slots.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _LIB = L
@@ -314,6 +315,13 @@ class DeviceProblem:
     def get_values_view(self, out):
         assert out.dtype == np.float64 and out.flags.c_contiguous
         _check(self.L.b200_get_values_view(self.h, _dp(out)))
+        return out
+
+    def get_values_all(self, out=None):
+        """The whole packed Values on every rank of a sharded problem (owned views gathered by one all-reduce)."""
+        if out is None:
+            out = np.empty(self.nval)
+        _check(self.L.b200_get_values_all(self.h, _dp(out)))
         return out
 
     def get_values(self, out=None):

@@ -1049,7 +1049,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_rdiag); cudaFree(p->d_bs_flags); cudaFree(p->d_bs_flag_base);
   cudaFree(p->d_df_tasks[0]); cudaFree(p->d_df_tasks[1]); cudaFree(p->d_df_flag_off); cudaFree(p->d_df_expect); cudaFree(p->d_df_sync); cudaFree(p->d_df_trace);
   cudaFree(p->d_winv); cudaFree(p->d_winv_off); cudaFree(p->d_red);
-  cudaFree(p->d_view_idx[0]); cudaFree(p->d_view_idx[1]); cudaFree(p->d_view_buf);
+  cudaFree(p->d_view_idx[0]); cudaFree(p->d_view_idx[1]); cudaFree(p->d_view_buf); cudaFree(p->d_gather_buf);
   cudaFree(p->d_ts_cliques); cudaFree(p->d_ts_xoff); cudaFree(p->d_ts_owned); cudaFree(p->d_topx);
   cudaFree(p->d_fused_run_ptr);
   cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
@@ -1705,6 +1705,27 @@ int b200_get_values_view(b200_problem* p, double* packed) {
   B200_CUDA(cudaMemcpyAsync(direct ? (void*)packed : (void*)p->h_pinned, p->d_view_buf, (size_t)nd * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
   if (!direct) memcpy(packed, p->h_pinned, (size_t)nd * sizeof(double));
+  return B200_OK;
+}
+
+/* The whole packed Values on EVERY rank of a sharded problem (each rank owns a part of the new estimate after a step):
+ * the owned views are summed into a zeroed full-size buffer by one all-reduce.  One rank: the same as b200_get_values. */
+int b200_get_values_all(b200_problem* p, double* v) {
+  if (!p || !v || p->linear) { set_error("bad argument"); return B200_INVALID_ARGUMENT; }
+  if (p->ctx->world <= 1) return b200_get_values(p, v);
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  if (!p->d_gather_buf) B200_CUDA(cudaMalloc((void**)&p->d_gather_buf, (size_t)std::max<int64_t>(1, p->nval) * sizeof(double)));
+  B200_CUDA(cudaMemsetAsync(p->d_gather_buf, 0, (size_t)p->nval * sizeof(double), st));
+  const int64_t nd = p->view_doubles[1];
+  launch_plain(values_view_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st, p->d_values, p->d_gather_buf, (const int*)p->d_view_idx[1], nd, 2);
+  p->ctx->launches++;
+  const int rc = allreduce_sum(p, p->d_gather_buf, (size_t)p->nval);
+  if (rc) return rc;
+  const bool direct = is_pinned_host(v);
+  B200_CUDA(cudaMemcpyAsync(direct ? (void*)v : (void*)p->h_pinned, p->d_gather_buf, (size_t)p->nval * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (!direct) memcpy(v, p->h_pinned, (size_t)p->nval * sizeof(double));
   return B200_OK;
 }
 

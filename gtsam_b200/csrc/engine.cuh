@@ -191,6 +191,7 @@ struct b200_problem {
   int64_t view_doubles[2] = {0, 0};
   int* d_view_idx[2] = {nullptr, nullptr};   // per packed double: its index in the full packed Values
   double* d_view_buf = nullptr;
+  double* d_gather_buf = nullptr;            // b200_get_values_all: full-size buffer the owned views are all-reduced in
   bool defer_scalar_reduce = false; // inside an LM try: the scalar all-reduces are merged into one (enqueue_try)
   double* d_red = nullptr;
   bool top_staged = false;

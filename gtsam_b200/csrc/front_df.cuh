@@ -466,7 +466,8 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
 __global__ void __launch_bounds__(256) values_view_kernel(double* values, double* packed, const int* __restrict__ idx, int64_t n, int to_values) {
   const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (e >= n) return;
-  if (to_values) values[idx[e]] = packed[e];
+  if (to_values == 2) packed[idx[e]] = values[idx[e]];       // same position in a full-size buffer (b200_get_values_all)
+  else if (to_values) values[idx[e]] = packed[e];
   else packed[e] = values[idx[e]];
 }
 

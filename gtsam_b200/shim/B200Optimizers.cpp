@@ -76,6 +76,7 @@ struct DeviceState {
   b200_ctx* ctx = nullptr;
   b200_problem* prob = nullptr;
   b200_lm* lm = nullptr;
+  B200Communicator comm;      // world == 1: single GPU
 
   ~DeviceState() {
     if (lm) b200_lm_destroy(lm);
@@ -257,13 +258,15 @@ struct DeviceState {
     desc.ordering = ord.data(); desc.ncal = (int64_t)cal.size() / 5; desc.cal = cal.data();
     desc.ngroups = (int64_t)cg.size(); desc.groups = cg.data();
     const char* devEnv = std::getenv("B200_DEVICE");
-    check(b200_ctx_create(devEnv ? std::atoi(devEnv) : 0, &ctx), "b200_ctx_create");
+    check(b200_ctx_create(comm.world > 1 ? comm.device : (devEnv ? std::atoi(devEnv) : 0), &ctx), "b200_ctx_create");
+    if (comm.world > 1) check(b200_ctx_comm_init(ctx, comm.uniqueId.data(), comm.rank, comm.world), "b200_ctx_comm_init");
     check(b200_problem_create(ctx, &desc, &prob), "b200_problem_create");
   }
 
   Values currentValues() const {
     std::vector<double> x((size_t)b200_values_size(prob));
-    check(b200_get_values(prob, x.data()), "b200_get_values");
+    // sharded: every rank owns a part of the new estimate; b200_get_values_all gathers the whole of it on every rank
+    check(comm.world > 1 ? b200_get_values_all(prob, x.data()) : b200_get_values(prob, x.data()), "b200_get_values");
     return unpackValues(x);
   }
 
@@ -294,10 +297,21 @@ B200LevenbergMarquardtOptimizer::B200LevenbergMarquardtOptimizer(const Nonlinear
 B200LevenbergMarquardtOptimizer::B200LevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
                                                                  const Ordering& ordering, const LevenbergMarquardtParams& params)
     : LevenbergMarquardtOptimizer(graph, initialValues, ordering, params) { init(); }
+B200LevenbergMarquardtOptimizer::B200LevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initialValues,
+                                                                 const Ordering& ordering, const LevenbergMarquardtParams& params,
+                                                                 const B200Communicator& comm)
+    : LevenbergMarquardtOptimizer(graph, initialValues, ordering, params) { init(&comm); }
 B200LevenbergMarquardtOptimizer::~B200LevenbergMarquardtOptimizer() {}
 
-void B200LevenbergMarquardtOptimizer::init() {
+std::array<char, 128> B200Communicator::newUniqueId() {
+  std::array<char, 128> id{};
+  check(b200_nccl_unique_id(id.data()), "b200_nccl_unique_id");
+  return id;
+}
+
+void B200LevenbergMarquardtOptimizer::init(const B200Communicator* comm) {
   dev_ = std::make_shared<DeviceState>();
+  if (comm) dev_->comm = *comm;
   dev_->pack(graph_, state_->values, *params_.ordering);  // ordering is always set by the base ctor
   const b200_lm_params c = toC(params_);
   check(b200_lm_create(dev_->prob, &c, &dev_->lm), "b200_lm_create");
@@ -314,6 +328,7 @@ GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::iterate() {
 }
 
 GaussianFactorGraph::shared_ptr B200LevenbergMarquardtOptimizer::linearize() const {
+  if (dev_->comm.world > 1) throw std::invalid_argument("gtsam_b200: linearize() of a sharded optimizer would hold this rank's factors only");
   check(b200_linearize(dev_->prob), "b200_linearize");
   size_t total = 0;
   for (auto& g : dev_->groups) total += (size_t)g.count;

@@ -32,11 +32,23 @@
 
 #include <gtsam/linear/GaussianBayesTree.h>
 
+#include <array>
 #include <map>
 #include <memory>
 #include <vector>
 
 namespace gtsam_b200 {
+
+/// One rank of a sharded solve: one process per GPU, `world` of them.  Rank 0 draws the id
+/// (B200Communicator::newUniqueId) and ships the 128 bytes to the other ranks by whatever the application has (MPI, a
+/// file, a socket); every rank then constructs the same optimizer on the SAME graph, Values and Ordering.  The library
+/// splits the junction tree (subtrees by rank, the top distributed by owner), every rank takes the same LM decisions and
+/// values() holds the full estimate on every rank.
+struct B200Communicator {
+  int rank = 0, world = 1, device = 0;
+  std::array<char, 128> uniqueId{};
+  static std::array<char, 128> newUniqueId();
+};
 
 struct DeviceState;  // packed problem + C-ABI handles
 struct LinearState;  // packed JacobianFactor / HessianFactor groups + C-ABI handles
@@ -48,6 +60,11 @@ class B200LevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimize
   B200LevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
                                   const gtsam::Ordering& ordering,
                                   const gtsam::LevenbergMarquardtParams& params = gtsam::LevenbergMarquardtParams());
+  /// Sharded over the ranks of `comm` (same constructor arguments as gtsam/nonlinear/LevenbergMarquardtOptimizer.h:59-72
+  /// plus the communicator): iterate() / optimize() / values() / error() / lambda() behave as on one GPU.
+  B200LevenbergMarquardtOptimizer(const gtsam::NonlinearFactorGraph& graph, const gtsam::Values& initialValues,
+                                  const gtsam::Ordering& ordering, const gtsam::LevenbergMarquardtParams& params,
+                                  const B200Communicator& comm);
   ~B200LevenbergMarquardtOptimizer() override;
 
   /// One LM iteration on the device.  Returns nullptr: the linear graph stays in HBM
@@ -61,7 +78,7 @@ class B200LevenbergMarquardtOptimizer : public gtsam::LevenbergMarquardtOptimize
   void setJacobianFp32(bool on);
 
  private:
-  void init();
+  void init(const B200Communicator* comm = nullptr);
   std::shared_ptr<DeviceState> dev_;
 };
 

@@ -458,6 +458,8 @@ int b200_get_conditional(b200_problem* prob, int64_t clique, double* out);
 int b200_values_view(const b200_problem* prob, int which, int64_t* nvars, int64_t* ndoubles, int64_t* var_ids);
 int b200_set_values_view(b200_problem* prob, const double* packed_input_view);
 int b200_get_values_view(b200_problem* prob, double* packed_owned_view);
+/* The whole packed Values on every rank (the owned views gathered by one all-reduce); one rank: b200_get_values. */
+int b200_get_values_all(b200_problem* prob, double* packed);
 int b200_nccl_unique_id(void* out128);
 int b200_ctx_comm_init(b200_ctx* ctx, const void* id128, int rank, int world);
 int b200_shard_plan(const b200_problem_desc* desc, int world, int32_t* clique_owner, int32_t* factor_owner);

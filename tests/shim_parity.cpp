@@ -8,6 +8,7 @@
  */
 #include "../oracle/problem_io.hpp"
 #include "../gtsam_b200/shim/B200Optimizers.h"
+#include <unistd.h>
 
 #include <chrono>
 
@@ -47,6 +48,43 @@ int main(int argc, char** argv) {
   std::vector<double> e_ref, l_ref, e_dev, l_dev;
   std::vector<int> i_ref, i_dev;
   double t_ref = 0, t_dev = 0, maxdiff = 0;
+  // sharded mode: shim_parity problem.bin maxit ceres 0 <world> <rank> <uid file> [device]: one process per rank, the
+  // communicator id travels through a file (rank 0 writes it); every rank runs the same B200LevenbergMarquardtOptimizer
+  // constructor + the communicator and compares with the stock optimizer on the same GTSAM objects
+  if (argc > 7 && atoi(argv[5]) > 1) {
+    gtsam_b200::B200Communicator comm;
+    comm.world = atoi(argv[5]); comm.rank = atoi(argv[6]); comm.device = argc > 8 ? atoi(argv[8]) : comm.rank;
+    const std::string path = argv[7], tmp = path + ".tmp";
+    if (comm.rank == 0) {
+      comm.uniqueId = gtsam_b200::B200Communicator::newUniqueId();
+      FILE* fh = fopen(tmp.c_str(), "wb");
+      fwrite(comm.uniqueId.data(), 1, 128, fh); fclose(fh);
+      rename(tmp.c_str(), path.c_str());
+    } else {
+      FILE* fh = nullptr;
+      for (int tries = 0; tries < 60000 && !(fh = fopen(path.c_str(), "rb")); tries++) usleep(1000);
+      if (!fh || fread(comm.uniqueId.data(), 1, 128, fh) != 128) { fprintf(stderr, "no communicator id\n"); return 3; }
+      fclose(fh);
+    }
+    gtsam_b200::B200LevenbergMarquardtOptimizer sh(b.graph, b.values, b.ordering, params, comm);
+    trace(sh, maxit, e_dev, l_dev, i_dev, t_dev);
+    Values shValues = sh.values();      // the FULL estimate on every rank
+    LevenbergMarquardtOptimizer ref(b.graph, b.values, params);
+    trace(ref, maxit, e_ref, l_ref, i_ref, t_ref);
+    for (const auto& kv : ref.values()) {
+      Vector d = kv.value.localCoordinates_(shValues.at(kv.key));
+      maxdiff = std::max(maxdiff, d.cwiseAbs().maxCoeff());
+    }
+    printf("{\"world\": %d, \"rank\": %d, ", comm.world, comm.rank);
+    printv("dev_errors", e_dev); printf(", "); printv("dev_lambdas", l_dev); printf(", ");
+    printv("ref_errors", e_ref); printf(", "); printv("ref_lambdas", l_ref);
+    printf(", \"dev_inner\": [");
+    for (size_t i = 0; i < i_dev.size(); i++) printf("%s%d", i ? ", " : "", i_dev[i]);
+    printf("], \"ref_inner\": [");
+    for (size_t i = 0; i < i_ref.size(); i++) printf("%s%d", i ? ", " : "", i_ref[i]);
+    printf("], \"max_value_diff\": %.6g, \"launches\": %lld}\n", maxdiff, sh.launchCount());
+    return 0;
+  }
   gtsam_b200::B200LevenbergMarquardtOptimizer dev(b.graph, b.values, params);
   trace(dev, maxit, e_dev, l_dev, i_dev, t_dev);
   // the hook / public accessors keep working through the base class

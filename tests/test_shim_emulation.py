@@ -46,3 +46,32 @@ def test_cpp_drop_ins_against_the_emulated_library(emu_jobs):  # noqa: F811
     assert 0 <= r["gnc"]["gnc_weights"] <= 1e-4 and 0 <= r["gnc"]["gnc_values"] <= 1e-5
     for name, x in r["families"].items():                             # GeneralSFMFactor2, smart factors, expression factors
         assert x["worst_error_rel_diff"] <= 1e-7 and x["value_diff"] <= 1e-6 and x["launches"] > 0 and x["builds"] == 1, (name, x)
+
+
+def test_sharded_cpp_drop_in_against_the_emulated_library(emu_lib, tmp_path):  # noqa: F811
+    """B200LevenbergMarquardtOptimizer with a B200Communicator (multi-GPU through the C++ drop-in, one process per rank): two
+    ranks of oracle/_ref/shim_parity over the emulated library and tests/emu/fake_nccl.cpp — identical error / lambda /
+    inner-iteration traces to the stock optimizer on every rank, and values() is the FULL estimate on every rank."""
+    build = os.path.dirname(emu_lib)
+    nccl = os.path.join(build, "libnccl.so.2")
+    src = os.path.join(ROOT, "tests", "emu", "fake_nccl.cpp")
+    if not os.path.exists(nccl) or os.path.getmtime(nccl) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", src, "-o", nccl, "-lrt", "-pthread"])
+    env = dict(os.environ, LD_PRELOAD=emu_lib, B200_NO_GRAPH="1", LD_LIBRARY_PATH=build + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    for case in ("bal_tiny_s2", "sphere_small_colamd"):
+        uid = str(tmp_path / (case + ".uid"))
+        procs = [subprocess.Popen([os.path.join(REF, "shim_parity"), os.path.join(util.GOLDEN, case + ".prob.bin"), "12", "0", "0", "2", str(r), uid, "0"],   # (device 0 for both: the emulated runtime has one)
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
+        for r, p in enumerate(procs):
+            try:
+                out, err = p.communicate(timeout=300)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            assert p.returncode == 0, (case, r, err[-800:])
+            x = json.loads(out.strip().splitlines()[-1])
+            assert x["world"] == 2 and x["rank"] == r and x["launches"] > 0
+            assert len(x["dev_errors"]) == len(x["ref_errors"]) and np.allclose(x["dev_errors"], x["ref_errors"], rtol=1e-7, atol=1e-10)
+            assert np.allclose(x["dev_lambdas"], x["ref_lambdas"], rtol=1e-12) and x["dev_inner"] == x["ref_inner"]
+            assert x["max_value_diff"] <= 1e-6, (case, r, x["max_value_diff"])
