@@ -292,9 +292,14 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
     host_out = torch.empty(host_values.size, dtype=torch.float64).pin_memory().numpy()
     dev.save_values()
 
-    def step_resident():
+    # One step = one iterate().  Putting the optimizer back on the initial estimate (values restored device-side, state <-
+    # (values, lambda0, graph.error)) is the counterpart of CONSTRUCTING the optimizer, which the reference arm does before its
+    # clock starts (oracle/ref_harness.cpp cmd_time: fresh LevenbergMarquardtOptimizer, then the timed lm.iterate()): untimed here too.
+    def prepare_resident():
         dev.restore_values()                    # D2D: inputs already in HBM
         capi._check(L.b200_lm_reset(lm.h))      # state <- (values, lambda0); recomputes graph.error
+
+    def step_resident():
         lm.iterate()
 
     # sharded: a rank moves only its share (b200_values_view): in = the variables its factors touch + its cliques' and the
@@ -335,26 +340,28 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         with torch.cuda.stream(stream):
             flush_buf.zero_()
 
-    def timed(fn, steps, warmup, flush=True):
+    def timed(fn, steps, warmup, flush=True, prepare=None):
+        """Every step has its own CUDA-event pair on the library's stream; `prepare` (and the L2 flush) run between the pairs."""
         for _ in range(warmup):
+            if prepare:
+                prepare()
             fn()
         barrier()
         flush = flush and flush_buf is not None
-        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps if flush else 1)]
-        l0 = ctx.launch_count()
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        nlaunch = 0
         t0 = time.perf_counter()
         timed.region = [time.time(), None]
-        if flush:
-            for a, b in pairs:
+        for a, b in pairs:
+            if prepare:
+                prepare()
+            if flush:
                 flush_l2()
-                a.record(stream)
-                fn()
-                b.record(stream)
-        else:
-            pairs[0][0].record(stream)
-            for _ in range(steps):
-                fn()
-            pairs[0][1].record(stream)
+            l0 = ctx.launch_count()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            nlaunch += ctx.launch_count() - l0
         barrier()
         wall = time.perf_counter() - t0
         timed.region[1] = time.time()
@@ -363,24 +370,25 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, wall, ctx.launch_count() - l0
+        return ms, wall, nlaunch
 
     steps = args.steps
     sampler = ClockSampler(local)
     if rank == 0 and primary:
         sampler.start()
-    ms, wall, launches = timed(step_resident, steps, max(3, args.warmup))
+    ms, wall, launches = timed(step_resident, steps, max(3, args.warmup), prepare=prepare_resident)
     clocks = sampler.stop(tuple(timed.region)) if (rank == 0 and primary) else None
     ms_e2e, wall_e2e, _ = timed(step_e2e, steps, 1)
-    ms_warm, _, _ = timed(step_resident, steps, 1, flush=False)   # information only: L2 left warm between iterations
+    ms_warm, _, _ = timed(step_resident, steps, 1, flush=False, prepare=prepare_resident)   # information only: L2 left warm between iterations
 
     # phase profile (separate pass; event records add ~1 us per phase)
-    dev.profile_enable(True)
-    for _ in range(steps):
+    for it in range(steps):
+        prepare_resident()
+        dev.profile_enable(1 if it == 0 else 2)       # the phase timers see the timed part only (2 = resume)
         step_resident()
-    dev.synchronize()
+        dev.synchronize()
+        dev.profile_enable(0)
     prof = dev.profile()
-    dev.profile_enable(False)
     st = lm._state()
 
     parity = None

@@ -1422,9 +1422,22 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     // pivot — the tiles with work — instead of all the columns of the first few fronts parked on their dependencies while the other
     // fronts of the level wait for a slot; columns further right start later and catch up at full rate (their pieces are all there).
     // Dependencies still point to smaller tickets (same front: smaller column, or same column and smaller row tile; children: lower level).
-    if (!getenv("B200_DF_FRONT_ORDER"))
-    std::sort(df_tasks[phase].begin() + (int64_t)level_task_begin, df_tasks[phase].end(), [](const int4& a, const int4& b) {
-      return a.y != b.y ? a.y < b.y : (a.x != b.x ? a.x < b.x : a.z < b.z); });
+    if (!getenv("B200_DF_FRONT_ORDER")) {
+      // ... refined: first by the number of pivot steps the tile has to see before it is done (its `need`): a tile that needs all K
+      // steps of its front (every trailing tile of a front with few pivots and a wide separator) would otherwise sit on a slot
+      // from the first step on, busy ~20 % of the time (one 2 us update per 10 us pivot step: ncu showed the tensor pipe 11 %
+      // active with every slot taken); started late it finds its pieces ready and runs straight through.  A producer never
+      // needs more steps than its consumers (smaller-or-equal row tile and column), so the order stays dependency-safe.
+      const bool by_need = getenv("B200_DF_NO_NEED_ORDER") == nullptr;
+      auto need = [&](const int4& t) {
+        const int f = S.nf[t.x], nn = f + S.ns[t.x] + 1;
+        const int K = (f + kDfB - 1) / kDfB, NB = K + (nn - f + kDfB - 1) / kDfB;
+        return std::min(K, std::min(std::min(kDfTR * t.z + kDfTR - 1, t.y), NB - 1) + 1);
+      };
+      std::sort(df_tasks[phase].begin() + (int64_t)level_task_begin, df_tasks[phase].end(), [&](const int4& a, const int4& b) {
+        if (by_need) { const int na = need(a), nb = need(b); if (na != nb) return na < nb; }
+        return a.y != b.y ? a.y < b.y : (a.x != b.x ? a.x < b.x : a.z < b.z); });
+    }
     if (phase == 1 && p->top_staged) {
       // the stage of this top level: ALL its fronts (whoever owns them: they are reduced onto their owners), this rank's tiles
       const int f0 = (int)p->ts_fronts.size();
@@ -1946,8 +1959,10 @@ int b200_synchronize(b200_problem* p) {
 }
 int b200_profile_enable(b200_problem* p, int on) {
   p->profile = on != 0;
-  for (int i = 0; i < PH_COUNT; i++) { p->phase_ms[i] = 0; p->phase_calls[i] = 0; }
-  p->ev_used = 0;
+  if (on == 1) {    // 1: start from zero; 2: resume (the accumulated times stay); 0: pause
+    for (int i = 0; i < PH_COUNT; i++) { p->phase_ms[i] = 0; p->phase_calls[i] = 0; }
+    p->ev_used = 0;
+  }
   return B200_OK;
 }
 /* Measured FP64 peaks of this device (roofline denominators of the dense-front kernels): TFLOP/s of the DMMA path and

@@ -298,7 +298,7 @@ int b200_synchronize(b200_problem* prob);
 /* Built-in phase timers — the counterpart of the reference's gttic/gttoc call
  * tree (gtsam/base/timing.h:245-302): CUDA events on the launching stream
  * around each phase, accumulated in milliseconds. */
-int b200_profile_enable(b200_problem* prob, int on);
+int b200_profile_enable(b200_problem* prob, int on);   /* 1: start from zero, 2: resume, 0: pause */
 int b200_profile_phase_count(void);
 const char* b200_profile_phase_name(int phase);
 int b200_profile_get(b200_problem* prob, double* ms, int64_t* calls);
