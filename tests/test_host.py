@@ -240,3 +240,52 @@ def test_stored_metis_orderings_of_the_large_bal_workloads(built, name, cliques,
         co, fo = capi.shard_plan(prob, 4)      # nested-dissection branches: every rank busy (the plan balances weight =
         per = np.bincount(fo, minlength=4)     # front work + factors, so the factor counts alone differ by the camera work)
         assert per.min() > 0.6 * per.max()
+
+
+@pytest.mark.parametrize("name,kw", [("bal_tiny", dict(ncams=23, npoints=3000, visibility="scattered")), ("sphere_tiny", dict(layers=14, per_ring=24)),
+                                     ("sphere_tiny", dict(layers=10, per_ring=16, ordering="reverse")), ("bal_tiny", dict(ncams=100, npoints=5000, visibility="scattered"))])
+def test_supernodes_are_a_consistent_amalgamation_of_the_reference_cliques(built, name, kw):
+    """The device eliminates SUPERNODES (relaxed amalgamation, symbolic.h) while the API reports the reference's cliques: every
+    variable is frontal in exactly one supernode; a reference clique's frontals all live in the supernode that holds it and its
+    separator inside that supernode's frontals + separator (so its conditional can be read back by slot); a supernode's separator is
+    inside its parent's frontals + separator (extend-add is well defined); elimination order is preserved inside a supernode; and
+    the amalgamation really merges something on these graphs (fewer supernodes / levels than cliques)."""
+    import ctypes as C
+    from gtsam_b200 import capi, datasets, problem as P
+    prob = datasets.make(name, **kw)
+    L = capi.lib()
+    desc, keep = prob.c_desc()
+    h = C.c_void_p()
+    capi._check(L.b200_symbolic_create(C.byref(desc), C.byref(h)))
+    info = P.CSymbolicInfo()
+    L.b200_symbolic_get_info(h, C.byref(info))
+
+    def tables(getter, nc, nfl, nsl):
+        fp, sp = np.zeros(nc + 1, dtype=np.int64), np.zeros(nc + 1, dtype=np.int64)
+        fv, sv, par = np.zeros(max(1, nfl), dtype=np.int64), np.zeros(max(1, nsl), dtype=np.int64), np.zeros(max(1, nc), dtype=np.int64)
+        getter(h, capi._ip(fp), capi._ip(fv), capi._ip(sp), capi._ip(sv), capi._ip(par))
+        return fp, fv[:nfl], sp, sv[:nsl], par[:nc]
+    rfp, rfv, rsp, rsv, rpar = tables(L.b200_symbolic_get_cliques, info.ncliques, info.frontal_list_len, info.separator_list_len)
+    sfp, sfv, ssp, ssv, spar = tables(L.b200_symbolic_get_supernodes, info.supernodes, info.supernode_frontal_list_len, info.supernode_separator_list_len)
+    sup = np.zeros(info.ncliques, dtype=np.int32)
+    L.b200_symbolic_get_clique_supernode(h, sup.ctypes.data_as(C.POINTER(C.c_int32)))
+    L.b200_symbolic_destroy(h)
+    assert info.supernodes < info.ncliques and info.supernode_levels <= info.nlevels
+    assert np.array_equal(np.sort(sfv), np.arange(prob.nvars)) and np.array_equal(np.sort(rfv), np.arange(prob.nvars))
+    pos = np.empty(prob.nvars, dtype=np.int64)
+    pos[prob.ordering] = np.arange(prob.nvars)
+    owner = np.empty(prob.nvars, dtype=np.int64)
+    for s in range(info.supernodes):
+        fr = sfv[sfp[s]:sfp[s + 1]]
+        owner[fr] = s
+        assert np.all(np.diff(pos[fr]) > 0)                         # frontals in elimination order
+        if spar[s] >= 0:
+            p = spar[s]
+            allowed = set(sfv[sfp[p]:sfp[p + 1]]) | set(ssv[ssp[p]:ssp[p + 1]])
+            assert set(ssv[ssp[s]:ssp[s + 1]]) <= allowed
+    step = max(1, info.ncliques // 3000)
+    for c in range(0, info.ncliques, step):
+        s = sup[c]
+        assert np.all(owner[rfv[rfp[c]:rfp[c + 1]]] == s)
+        allowed = set(sfv[sfp[s]:sfp[s + 1]]) | set(ssv[ssp[s]:ssp[s + 1]])
+        assert set(rsv[rsp[c]:rsp[c + 1]]) <= allowed
