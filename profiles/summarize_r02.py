@@ -68,7 +68,7 @@ def captures(rep):
 
 
 def main():
-    print("# Round 2, final build: ncu evidence (one B200, `profiles/collect_r02b.sh`)\n")
+    print("# Round 2, final build: ncu evidence (one B200, `profiles/collect_r02c.sh`)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES with the bench's phase timers, not absolutes.\n")
     for path in sorted(glob.glob(os.path.join(D, "r02_launches_*.csv"))):
         w = os.path.basename(path)[len("r02_launches_"):-4]
