@@ -33,7 +33,7 @@ EXPORTS = [
     "b200_symbolic_get_cliques", "b200_symbolic_get_levels", "b200_nccl_unique_id", "b200_ctx_comm_init",
     "b200_shard_plan", "b200_dl_create", "b200_dl_destroy", "b200_dl_iterate", "b200_dl_get_state", "b200_marginal_covariance", "b200_joint_marginal_covariance",
     "b200_linear_create", "b200_linear_update", "b200_linear_update_hessian", "b200_linear_symbolic_create",
-    "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_symbolic_get_factor_slots",
+    "b200_set_jacobian_precision", "b200_get_jacobian_precision", "b200_set_tuning", "b200_symbolic_get_factor_slots",
     "b200_get_supernodes", "b200_symbolic_get_supernodes", "b200_symbolic_get_clique_supernode", "b200_measure_fp64_peak",
     "b200_values_view", "b200_set_values_view", "b200_get_values_view", "b200_get_values_all",
 ]
@@ -123,6 +123,7 @@ def lib():
         L.b200_symbolic_get_info.argtypes = [vp, C.POINTER(P.CSymbolicInfo)]
         L.b200_set_jacobian_precision.argtypes = [vp, C.c_int]
         L.b200_get_jacobian_precision.argtypes = [vp]
+        L.b200_set_tuning.argtypes = [vp, C.c_char_p, C.c_int64]
         from . import linear as LN
         L.b200_linear_create.argtypes = [vp, C.POINTER(LN.CLinearDesc), C.POINTER(vp)]
         L.b200_linear_update.argtypes = [vp, C.c_int64, dp, dp]
@@ -343,6 +344,10 @@ class DeviceProblem:
     def set_jacobian_precision(self, fp32: bool):
         """FP32 storage of the whitened Jacobians ("FP32 linearize + FP64 solve", BASELINE configs[4])."""
         _check(self.L.b200_set_jacobian_precision(self.h, int(fp32)))
+
+    def set_tuning(self, key: str, value: int):
+        """Kernel-variant switch of this problem (b200_set_tuning): every variant computes the same result."""
+        _check(self.L.b200_set_tuning(self.h, key.encode(), int(value)))
 
     def get_jacobians(self, group: int):
         g = self.prob.groups[group]

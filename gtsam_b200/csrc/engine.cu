@@ -280,6 +280,26 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       const int nr = p->leaf_run_end[kd] - p->leaf_run_begin[kd];
       if (nr <= 0) continue;
       const int* runs = p->d_fused_run_ptr + p->leaf_run_begin[kd];
+      if (p->schur_mma) {
+        // FP64 tensor path: 8x8 DMMA tiles over (s+1)^2 / 2, 4 warps, TPW tiles per warp from the widest separator of the kind
+        const int dc = kd == 1 ? 6 : 9, maxw = p->leaf_max_w[kd], nt8 = (maxw + 7) / 8, tpw = (nt8 * (nt8 + 1) / 2 + 3) / 4;
+        const int mmax = std::max(1, (maxw - 1) / dc);
+        const size_t jb = p->jac_f32 ? sizeof(float) : sizeof(double);
+        const size_t sm = (size_t)2 * 8 * nt8 * kSmKP * sizeof(double) + (size_t)2 * kSmPB * mmax * (2 * dc + 2) * jb;
+        bool done = false;
+#define B200_LAUNCH_SCHUR_MMA(DC_, T_)                                                                                                \
+        if (!done && dc == DC_ && tpw <= T_) {                                                                                        \
+          DISPATCH_JT(p, launch_k(leaf_point_schur_mma_kernel<DC_, T_, JT>, dim3(nr), dim3(128), sm, st, t, gt, (const int*)p->d_fused_list, runs, \
+                   (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac));                                                    \
+          done = true;                                                                                                                \
+        }
+        B200_LAUNCH_SCHUR_MMA(6, 3) B200_LAUNCH_SCHUR_MMA(6, 4) B200_LAUNCH_SCHUR_MMA(6, 7)
+        B200_LAUNCH_SCHUR_MMA(9, 3) B200_LAUNCH_SCHUR_MMA(9, 4) B200_LAUNCH_SCHUR_MMA(9, 7) B200_LAUNCH_SCHUR_MMA(9, 14)
+#undef B200_LAUNCH_SCHUR_MMA
+        if (!done) { set_error("leaf_point_schur_mma_kernel: separator wider than the compiled tile counts"); return B200_CUDA_ERROR; }
+        ctx->launches++;
+        continue;
+      }
       // CTA shape from the widest separator of the kind: 3x3 tiles over (s+1)^2 / 2
       const int ntd = (p->leaf_max_w[kd] + 2) / 3, ntiles = ntd * (ntd + 1) / 2;
       const int thr = ntiles <= 96 ? 96 : 128, tpt = (ntiles + thr - 1) / thr;
@@ -1202,6 +1222,17 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   p->use_dmma = getenv("B200_NO_DMMA") == nullptr;
   p->fuse_ea = getenv("B200_NO_FUSE_EA") == nullptr;
   p->schur_pb = (getenv("B200_SCHUR_PB") && atoi(getenv("B200_SCHUR_PB")) == 6) ? 6 : 4;
+  p->schur_mma = !(getenv("B200_SCHUR_MMA") && atoi(getenv("B200_SCHUR_MMA")) == 0);
+#ifndef B200_EMULATE
+  {   // the widest instantiations stage more than the 48 KB a kernel gets by default
+    const int optin = 200 * 1024;
+#define B200_SM_ATTR(DC_, T_)                                                                                                          \
+    B200_CUDA(cudaFuncSetAttribute(leaf_point_schur_mma_kernel<DC_, T_, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)); \
+    B200_CUDA(cudaFuncSetAttribute(leaf_point_schur_mma_kernel<DC_, T_, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    B200_SM_ATTR(6, 3) B200_SM_ATTR(6, 4) B200_SM_ATTR(6, 7) B200_SM_ATTR(9, 3) B200_SM_ATTR(9, 4) B200_SM_ATTR(9, 7) B200_SM_ATTR(9, 14)
+#undef B200_SM_ATTR
+  }
+#endif
   p->h_off.assign(S.ncliques + 1, 0);
   p->h_ld.assign(S.ncliques, 0);
   {
@@ -1812,6 +1843,22 @@ int b200_set_jacobian_precision(b200_problem* p, int fp32) {
   return B200_OK;
 }
 int b200_get_jacobian_precision(const b200_problem* p) { return p && p->jac_f32 ? 1 : 0; }
+
+/* Kernel-variant switches of one problem (A/B measurements, profiles/ab_r02.py; every variant computes the same thing). */
+int b200_set_tuning(b200_problem* p, const char* key, int64_t value) {
+  if (!p || !key) { set_error("null problem / key"); return B200_INVALID_ARGUMENT; }
+  const std::string k(key);
+  if (k == "schur_mma") p->schur_mma = value != 0;
+  else if (k == "lin_variant") p->lin_variant = (int)value;
+  else if (k == "schur_pb") p->schur_pb = value == 6 ? 6 : 4;
+  else if (k == "df_minb") p->df_minb = value == 3 ? 3 : 2;
+  else { set_error("b200_set_tuning: unknown key " + k); return B200_INVALID_ARGUMENT; }
+  B200_CUDA(cudaSetDevice(p->ctx->device));
+  B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  for (int i = 0; i < 2; i++)   // the captured LM try has the kernel instantiations baked in
+    if (p->try_graph[i]) { cudaGraphExecDestroy(p->try_graph[i]); p->try_graph[i] = nullptr; }
+  return B200_OK;
+}
 
 int b200_hessian_diagonal(b200_problem* p, double* out) {
   if (!p->linearized) { set_error("b200_hessian_diagonal before b200_linearize"); return B200_INVALID_ARGUMENT; }

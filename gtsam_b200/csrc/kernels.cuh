@@ -1094,6 +1094,189 @@ leaf_point_schur_kernel(TreeView t, GroupTable gt, const int* __restrict__ list,
   }
 }
 
+// mma.sync.aligned.m8n8k4.row.col.f64 (SASS: DMMA); fragment layout (PTX ISA): A(row i = lane/4, col k = lane%4),
+// B(row k = lane%4, col j = lane/4), C/D(row i = lane/4, cols 2*(lane%4) + {0,1}).
+#ifdef B200_EMULATE   // host emulation build: the fragment layout above spelled out with warp exchanges
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
+  for (int k = 0; k < 4; k++) {
+    const double ak = __shfl_sync(0xffffffffu, a, 4 * i + k);
+    const double b0 = __shfl_sync(0xffffffffu, b, 4 * j0 + k), b1 = __shfl_sync(0xffffffffu, b, 4 * (j0 + 1) + k);
+    d0 += ak * b0;
+    d1 += ak * b1;
+  }
+}
+#else
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// The same per-run half on the FP64 tensor path (round 2).  ncu of leaf_point_schur_kernel (profiles/r02_profile_summary.md,
+// bal_1m): 19.7k thread instructions per point for 1.7k useful FMAs, 43 % issue-active — the 3x3 register tiles spend their
+// issue slots on shared-memory loads (6 LDS.64 per 9 FMAs) and index arithmetic, not on arithmetic.  Here the run's
+// -S'^T S' is what it is, a SYRK: the [S' d'] rows of 16 points are staged TRANSPOSED ([column][k = 3 pt + r], pitch 52 doubles:
+// conflict-free fragments) and every warp multiplies its 8x8 tiles of the (s+1)^2 upper triangle with mma.sync.m8n8k4.f64
+// — one DMMA = 256 FMAs for two 8-byte shared-memory loads — while the block-diagonal A_c^T A_c, A_c^T b and b^T b terms
+// (2 FMAs per entry and point) are summed by one thread per entry.  One extend-add per run, as before.
+// ---------------------------------------------------------------------------
+constexpr int kSmPB = 16;               // points per staged batch: K = 48 rows = 12 DMMA k-steps
+constexpr int kSmKB = 3 * kSmPB;
+constexpr int kSmKP = kSmKB + 4;        // pitch of one column of S'^T: (q * 52 + g) mod 16 distinct over the 16 lanes of a half-warp
+
+template <int DC, int TPW, typename JT = double>   // TPW: 8x8 tiles per warp = ceil(tiles of the widest separator / 4)
+__global__ void __launch_bounds__(128)
+leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
+                            const int* __restrict__ fac_ptr, const int2* __restrict__ fac) {
+  pdl_sync();
+  constexpr int PB = kSmPB, KP = kSmKP, AW = 2 * DC + 2;   // per factor: A_c (2 x DC, column-major) and b (2)
+  constexpr int NE = (DC + 1) * (DC + 2) / 2;               // per camera: upper triangle of [A_c b]^T [A_c b]
+  constexpr int AV = (kPtMaxObs * NE + 127) / 128;          // those entries per thread
+  B200_DYN_SMEM(double, sm_dyn);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int r0 = run_ptr[blockIdx.x], r1 = run_ptr[blockIdx.x + 1];
+  const int c0 = list[r0];
+  const int p = t.parent[c0];
+  if (p < 0) return;
+  const int s = t.ns[c0], w = s + 1;
+  const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
+  const int NT = (w + 7) >> 3, WP = 8 * NT;
+  double* sT = sm_dyn;                                              // [2][WP][KP]: S'^T, entry (col, k = 3 pt + r)
+  JT* sA = reinterpret_cast<JT*>(sm_dyn + 2 * WP * KP);             // [2][PB][m][AW], in the Jacobians' storage type
+  // this warp's 8x8 tiles (ti <= tj) of the upper triangle, round-robin over the 4 warps
+  int ti[TPW], tj[TPW];
+  double acc[TPW][2];
+#pragma unroll
+  for (int u = 0; u < TPW; u++) {
+    int e = warp + 4 * u, a = 0;
+    while (a < NT && e >= NT - a) { e -= NT - a; a++; }
+    ti[u] = a < NT ? a : -1;
+    tj[u] = a + e;
+    acc[u][0] = acc[u][1] = 0.0;
+  }
+  // this thread's entries of the per-camera blocks: (camera slot, x <= y) with column DC = the rhs
+  int aci[AV], ax[AV], ay[AV];
+  double aacc[AV];
+#pragma unroll
+  for (int v = 0; v < AV; v++) {
+    const int e = tid + 128 * v;
+    aacc[v] = 0.0;
+    aci[v] = -1; ax[v] = ay[v] = 0;
+    if (e < m * NE) { aci[v] = e / NE; tri_decode(e - aci[v] * NE, ax[v], ay[v]); }
+  }
+  for (int e = tid; e < 2 * (WP - w) * KP; e += 128) {             // zero columns behind the rhs column, written once
+    const int b = e / ((WP - w) * KP), r = e - b * (WP - w) * KP;
+    sT[(size_t)b * WP * KP + w * KP + r] = 0.0;
+  }
+  const double* srcS[PB / 4];    // [S' d'] of the points this warp copies (points warp, warp + 4, ... of a batch)
+  const JT* srcJ = nullptr;      // this thread's factor (point tid>>3, factor tid&7), staged by camera slot
+  size_t cntJ = 0;
+  int slotJ = -1;
+  auto load_idx = [&](int b0) {
+    const int nb = min(PB, r1 - b0);
+#pragma unroll
+    for (int z = 0; z < PB / 4; z++) {
+      const int pt = warp + 4 * z;
+      srcS[z] = pt < nb ? t.arena + t.off[list[b0 + pt]] + 9 : nullptr;
+    }
+    const int pt = tid >> 3, fi = tid & 7;
+    slotJ = -1;
+    if (pt < nb && fi < m) {
+      const int2 gf = fac[fac_ptr[b0 + pt] + fi];
+      const GroupView& gv = gt.g[gf.x];
+      cntJ = (size_t)gv.count;
+      srcJ = reinterpret_cast<const JT*>(gv.J) + gf.y;
+      slotJ = (gv.scat[gf.y].y - 3) / DC;
+    }
+  };
+  auto issue = [&](int buf, int nb) {
+    double* T = sT + (size_t)buf * WP * KP;
+#pragma unroll
+    for (int z = 0; z < PB / 4; z++)
+      if (srcS[z])
+        for (int e = lane; e < 3 * w; e += 32) {
+          const int col = e / 3;
+          cp_async8(T + col * KP + 3 * (warp + 4 * z) + (e - 3 * col), srcS[z] + e);
+        }
+    if (slotJ >= 0) {
+      JT* dst = sA + ((size_t)(buf * PB + (tid >> 3)) * m + slotJ) * AW;
+#pragma unroll
+      for (int el = 0; el < 2 * DC; el++) cp_async_el(dst + el, srcJ + (size_t)el * cntJ);
+      cp_async_el(dst + 2 * DC, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
+      cp_async_el(dst + 2 * DC + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
+    }
+    cp_async_commit();
+    // a short last batch: the k rows up to the next multiple of 4 read as zero
+    const int k0 = 3 * nb, k1 = (k0 + 3) & ~3;
+    for (int e = tid; e < w * (k1 - k0); e += 128) { const int col = e / (k1 - k0); T[col * KP + k0 + (e - col * (k1 - k0))] = 0.0; }
+  };
+  load_idx(r0);
+  issue(0, min(PB, r1 - r0));
+  load_idx(r0 + PB);
+  int buf = 0;
+  for (int b0 = r0; b0 < r1; b0 += PB, buf ^= 1) {
+    const int nbp = min(PB, r1 - b0);
+    if (b0 + PB < r1) {
+      issue(buf ^ 1, min(PB, r1 - b0 - PB));
+      load_idx(b0 + 2 * PB);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* T = sT + (size_t)buf * WP * KP;
+    const int ksteps = (3 * nbp + 3) >> 2;
+    for (int k4 = 0; k4 < ksteps; k4++) {
+#pragma unroll
+      for (int u = 0; u < TPW; u++) {
+        if (ti[u] < 0) continue;      // (warp-uniform)
+        const double a = -T[(8 * ti[u] + g) * KP + 4 * k4 + q];
+        const double b = T[(8 * tj[u] + g) * KP + 4 * k4 + q];
+        dmma_m8n8k4(acc[u][0], acc[u][1], a, b);
+      }
+    }
+    const JT* Ab = sA + (size_t)buf * PB * m * AW;
+#pragma unroll
+    for (int v = 0; v < AV; v++) {
+      if (aci[v] < 0) continue;
+      const JT* A = Ab + aci[v] * AW;
+      double sum = 0.0;
+      for (int pt = 0; pt < nbp; pt++, A += m * AW)
+        sum += (double)A[2 * ax[v]] * (double)A[2 * ay[v]] + (double)A[2 * ax[v] + 1] * (double)A[2 * ay[v] + 1];
+      aacc[v] += sum;
+    }
+    __syncthreads();
+  }
+  // one extend-add per run (HessianFactor::updateHessian of the leaf's separator factor)
+  double* P = t.arena + t.off[p];
+  const int pn = t.nf[p] + t.ns[p] + 1;
+  const int* map = t.ea_map + t.ea_ptr[c0];
+#pragma unroll
+  for (int u = 0; u < TPW; u++) {
+    if (ti[u] < 0) continue;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = 8 * ti[u] + g, j = 8 * tj[u] + 2 * q + h;
+      if (i <= j && j < w) {
+        const int a = map[i], bq = map[j];
+        const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+        atomicAdd(P + lo + (size_t)hi * pn, acc[u][h]);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < AV; v++) {
+    if (aci[v] < 0) continue;
+    const int i = ax[v] < DC ? aci[v] * DC + ax[v] : s, j = ay[v] < DC ? aci[v] * DC + ay[v] : s;
+    const int a = map[i], bq = map[j];
+    const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+    atomicAdd(P + lo + (size_t)hi * pn, aacc[v]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // large fronts: blocked right-looking partial Cholesky in global memory.
 // Per panel [k0, k0+nb): (1) potrf of the nb x nb diagonal block + TRSM of the
@@ -1299,23 +1482,6 @@ update_kernel(TreeView t, const int* __restrict__ list, int mode, int K0, int k0
 // (PTX ISA, m8n8k4 .f64): A(row i = lane/4, col k = lane%4), B(row k = lane%4, col j = lane/4),
 // C/D(row i = lane/4, cols 2*(lane%4) + {0,1}).  With C -= P^T P: A[i][k] = P[k][i], B[k][j] = P[k][j],
 // both straight out of the staged row panels.  Only mode 2 (TRAIL) of update_kernel.
-#ifdef B200_EMULATE   // host emulation build: the fragment layout above spelled out with warp exchanges
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
-  for (int k = 0; k < 4; k++) {
-    const double ak = __shfl_sync(0xffffffffu, a, 4 * i + k);
-    const double b0 = __shfl_sync(0xffffffffu, b, 4 * j0 + k), b1 = __shfl_sync(0xffffffffu, b, 4 * (j0 + 1) + k);
-    d0 += ak * b0;
-    d1 += ak * b1;
-  }
-}
-#else
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-#endif
 
 __global__ void __launch_bounds__(256)
 update_dmma_kernel(TreeView t, const int* __restrict__ list, int K0, int fuse_ea) {

@@ -257,6 +257,11 @@ int b200_get_jacobians(b200_problem* prob, int64_t group, double* out);
  * final error rel <= 1e-5.  Call it any time: it invalidates the current linearization.  Not for linear problems. */
 int b200_set_jacobian_precision(b200_problem* prob, int fp32);
 int b200_get_jacobian_precision(const b200_problem* prob);
+/* Kernel-variant switches of one problem, for A/B measurements (every variant computes the same result):
+ * "schur_mma" 1 (default) = the per-run Schur complement of the BAL point leaves on the FP64 tensor path, 0 = the
+ * FMA-tile kernel; "schur_pb" 4 / 6 = its points per staged batch; "df_minb" 2 / 3 = the dense-front kernel variant;
+ * "lin_variant" = linearize_kernel variant of the projection groups.  Unknown key: B200_INVALID_ARGUMENT. */
+int b200_set_tuning(b200_problem* prob, const char* key, int64_t value);
 
 /* GaussianFactorGraph::hessianDiagonal(), gtsam/linear/GaussianFactorGraph.cpp:279-287.
  * out: delta_size doubles, variable-id order. */

@@ -292,11 +292,14 @@ def midsize(model):
     model, _, obs = model.partition("@")     # e.g. bundler@8: 8 observations per point -> 3 tiles per thread in the Schur kernel
     prob = datasets.make("bal_tiny", ncams=30, npoints=1500 if not obs else 400, visibility="banded", camera_model=model,   # (30 cameras: the band (start + 3k) mod n holds distinct cameras)
                          obs_per_point=int(obs or 6))
-    for f32, pb in ((False, 4), (True, 4), (False, 6), (True, 6)):
+    # mma = 1: the per-run Schur complement on the FP64 tensor path (leaf_point_schur_mma_kernel, 16-point batches: runs of 40
+    # points = two full batches + a short one); mma = 0: the FMA-tile kernel with 4- / 6-point batches
+    for f32, pb, mma in ((False, 4, 1), (True, 4, 1), (False, 4, 0), (True, 4, 0), (False, 6, 0), (True, 6, 0)):
         # (run length is sized from the SM count; at this size it would be 1, so it is forced)
-        os.environ["B200_LEAF_RUN_MAX"] = "24"; os.environ["B200_SCHUR_PB"] = str(pb)
+        os.environ["B200_LEAF_RUN_MAX"] = "40" if mma else "24"; os.environ["B200_SCHUR_PB"] = str(pb)
         dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
         os.environ.pop("B200_LEAF_RUN_MAX"); os.environ.pop("B200_SCHUR_PB")
+        dev.set_tuning("schur_mma", mma)
         dev.set_jacobian_precision(f32); orc.set_jacobian_precision(f32)
         dev.linearize(); orc.linearize()
         for lam, diag in ((1e-3, False), (1e-2, True)):
