@@ -188,6 +188,13 @@ static int enqueue_linearize(b200_problem* p) {
     // tiny groups (a handful of priors) are pure launch latency: timed apart from the bandwidth kernels
     PhaseScope ps(p, g.count >= 4096 ? PH_LINEARIZE : PH_LINEARIZE_MINOR);
     const int nb = (int)((g.count + 127) / 128);
+    const bool proj = g.type == B200_FACTOR_PROJECTION_CAL3S2 || g.type == B200_FACTOR_SFM_BUNDLER;
+    if (proj && p->lin_variant == 4) {        // 128-register build of the two projection evaluators (no spills, 4 CTAs per SM)
+      if (g.type == B200_FACTOR_PROJECTION_CAL3S2)
+        DISPATCH_JT(p, launch_k(linearize_kernel<B200_FACTOR_PROJECTION_CAL3S2, JT, 4>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values)));
+      else
+        DISPATCH_JT(p, launch_k(linearize_kernel<B200_FACTOR_SFM_BUNDLER, JT, 4>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values)));
+    } else
     DISPATCH_JT(p, DISPATCH_TYPE(g.type, (launch_k(linearize_kernel<TY, JT>, dim3(nb), dim3(128), 0, st, view(g), ectx(p, p->d_values)))));
     p->ctx->launches++;
   }
@@ -262,10 +269,16 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (p->leaf_run_end[kd] <= p->leaf_run_begin[kd]) continue;
       const int i0 = p->leaf_pos_begin[kd], i1 = p->leaf_pos_end[kd];
       const int nb = (int)(((int64_t)(i1 - i0) * 8 + 127) / 128);
+      const int ncap = 3 * (3 + p->leaf_max_w[kd]);     // staged variant: doubles per point in shared memory
 #define B200_LAUNCH_POINT(DC_)                                                                                                        \
-      DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1, \
+      if (p->factor_staged)                                                                                                           \
+      DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT, true>, dim3(nb), dim3(128), (size_t)16 * ncap * sizeof(double), st, t, gt, (const int*)p->d_fused_list, i0, i1, \
                (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
-               p->d_scalars));
+               p->d_scalars, ncap));                                                                                                  \
+      else                                                                                                                            \
+      DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT, false>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1, \
+               (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
+               p->d_scalars, ncap));
       if (kd == 1) { B200_LAUNCH_POINT(6) } else { B200_LAUNCH_POINT(9) }
 #undef B200_LAUNCH_POINT
       ctx->launches++;
@@ -1223,6 +1236,8 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   p->fuse_ea = getenv("B200_NO_FUSE_EA") == nullptr;
   p->schur_pb = (getenv("B200_SCHUR_PB") && atoi(getenv("B200_SCHUR_PB")) == 6) ? 6 : 4;
   p->schur_mma = !(getenv("B200_SCHUR_MMA") && atoi(getenv("B200_SCHUR_MMA")) == 0);
+  p->factor_staged = !(getenv("B200_FACTOR_STAGED") && atoi(getenv("B200_FACTOR_STAGED")) == 0);
+  if (getenv("B200_LIN_VARIANT")) p->lin_variant = atoi(getenv("B200_LIN_VARIANT"));
 #ifndef B200_EMULATE
   {   // the widest instantiations stage more than the 48 KB a kernel gets by default
     const int optin = 200 * 1024;
@@ -1491,6 +1506,74 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     }
   }
   p->ts_begin.push_back((int)p->ts_fronts.size());
+  {
+    // Ticket order across levels (B200_DF_ORDER=1; 0 = level by level): by the ESTIMATED time a tile can finish, in pivot
+    // steps — its front's start (= the latest finish of a child front) + the pivot steps it has to see; trailing-column tiles
+    // optionally B200_DF_LAG steps later (they then find their pieces ready instead of idling on a slot).  A front whose
+    // children are done early no longer waits for the tickets of the rest of its level.  Dependency-safe: a producer's key
+    // is never larger than its consumer's (same front: fewer steps, pivot columns before trailing ones; children: finish
+    // <= the parent's start), ties broken as before — and df_order_is_safe() below checks the result, whatever the order.
+    const int df_order = getenv("B200_DF_ORDER") ? atoi(getenv("B200_DF_ORDER")) : 0;
+    const int df_lag = getenv("B200_DF_LAG") ? std::max(0, atoi(getenv("B200_DF_LAG"))) : 0;
+    auto shape = [&](int c, int& K, int& NB) {
+      const int f = S.nf[c], nn = f + S.ns[c] + 1;
+      K = (f + kDfB - 1) / kDfB; NB = K + (nn - f + kDfB - 1) / kDfB;
+    };
+    auto need_of = [&](const int4& t) {
+      int K, NB; shape(t.x, K, NB);
+      return std::min(K, std::min(std::min(kDfTR * t.z + kDfTR - 1, t.y), NB - 1) + 1);
+    };
+    if (df_order >= 1) {
+      std::vector<int64_t> est(S.ncliques, 0);
+      for (int64_t c = 0; c < S.ncliques; c++) {      // children have smaller ids than parents
+        if (!df_tiles[c] || S.parent[c] < 0) continue;
+        int K, NB; shape((int)c, K, NB);
+        est[S.parent[c]] = std::max(est[S.parent[c]], est[c] + K + 1 + df_lag);
+      }
+      for (int phase = 0; phase < 2; phase++) {
+        if (phase == 1 && p->top_staged) continue;     // the staged top is launched level by level
+        auto key = [&](const int4& t) { int K, NB; shape(t.x, K, NB); return est[t.x] + need_of(t) + (t.y >= K ? df_lag : 0); };
+        std::sort(df_tasks[phase].begin(), df_tasks[phase].end(), [&](const int4& a, const int4& b) {
+          const int64_t ka = key(a), kb = key(b);
+          if (ka != kb) return ka < kb;
+          const int na = need_of(a), nb = need_of(b);
+          if (na != nb) return na < nb;
+          return a.y != b.y ? a.y < b.y : (a.x != b.x ? a.x < b.x : a.z < b.z); });
+      }
+    }
+    // every wait of front_df_kernel must point to a smaller ticket of the same launch (or to an earlier launch)
+    for (int phase = 0; phase < 2; phase++) {
+      const std::vector<int4>& T = df_tasks[phase];
+      std::vector<int64_t> first(S.ncliques, -1), base(S.ncliques, -1);   // per front: smallest ticket; offset into tk
+      std::vector<int64_t> last(S.ncliques, -1);
+      int64_t ntk = 0;
+      for (size_t i = 0; i < T.size(); i++) {
+        const int c = T[i].x;
+        if (base[c] < 0) { int K, NB; shape(c, K, NB); base[c] = ntk; ntk += (int64_t)NB * ((NB + kDfTR - 1) / kDfTR); first[c] = (int64_t)i; }
+        last[c] = (int64_t)i;
+      }
+      std::vector<int> tk((size_t)ntk, -1);             // ticket of tile (c, j, r)
+      auto slot = [&](int c, int j, int r) { int K, NB; shape(c, K, NB); return base[c] + (int64_t)j * ((NB + kDfTR - 1) / kDfTR) + r; };
+      for (size_t i = 0; i < T.size(); i++) tk[slot(T[i].x, T[i].y, T[i].z)] = (int)i;
+      bool safe = true;
+      for (size_t i = 0; i < T.size() && safe; i++) {
+        const int c = T[i].x, j = T[i].y, r = T[i].z;
+        int K, NB; shape(c, K, NB);
+        const int last_rb = std::min(std::min(kDfTR * r + kDfTR - 1, j), NB - 1);
+        for (int k = 0; k < std::min(K, last_rb + 1) && safe; k++) {
+          const int rk = k / kDfTR;
+          auto before = [&](int jj, int rr) { const int d = tk[slot(c, jj, rr)]; return (jj == j && rr == r) || (d >= 0 && d < (int)i); };
+          if (k <= j && !before(k, rk)) safe = false;                      // R_kk from the diagonal tile of column k
+          if (rk < r && !before(j, rk)) safe = false;                      // column piece (k, j)
+          for (int ib = std::max(kDfTR * r, k + 1); ib <= last_rb && safe; ib++)
+            if (ib != j && !before(ib, rk)) safe = false;                  // row piece (k, ib)
+        }
+        const int par = S.parent[c];
+        if (par >= 0 && first[par] >= 0 && first[par] < last[c]) safe = false;   // a parent's tiles wait for every tile of its children
+      }
+      if (!safe) FAIL(B200_INVALID_ARGUMENT, "front dataflow: ticket order is not dependency-safe (internal)");
+    }
+  }
   if (p->top_staged && !p->ts_fronts.empty()) {
     std::vector<int> tc, tx, to;
     int64_t x = 0;
@@ -1850,6 +1933,7 @@ int b200_set_tuning(b200_problem* p, const char* key, int64_t value) {
   const std::string k(key);
   if (k == "schur_mma") p->schur_mma = value != 0;
   else if (k == "lin_variant") p->lin_variant = (int)value;
+  else if (k == "factor_staged") p->factor_staged = value != 0;
   else if (k == "schur_pb") p->schur_pb = value == 6 ? 6 : 4;
   else if (k == "df_minb") p->df_minb = value == 3 ? 3 : 2;
   else { set_error("b200_set_tuning: unknown key " + k); return B200_INVALID_ARGUMENT; }

@@ -120,8 +120,10 @@ __device__ __forceinline__ void finish_sum(double block_value, double* partials,
 // JT = storage type of the whitened Jacobians: double, or float for the "FP32 linearize + FP64 solve" mode of
 // BASELINE configs[4] (b200_set_jacobian_precision): the math stays FP64 in registers, the element-major SoA holds
 // floats (half the HBM traffic of the two bandwidth-bound phases); every consumer widens back to FP64 on load.
-template <int TYPE, typename JT = double>
-__global__ void __launch_bounds__(128, FactorTraits<TYPE>::D <= 3 ? 8 : 2) linearize_kernel(GroupView g, EvalCtx c) {
+// MINB: resident CTAs per SM the kernel is compiled for.  The 2-row projection factors default to 8 (64 registers: ptxas
+// spills 160 bytes of the 20-entry block) — variant 4 (128 registers, no spills) is switched in by b200_set_tuning("lin_variant").
+template <int TYPE, typename JT = double, int MINB = (FactorTraits<TYPE>::D <= 3 ? 8 : 2)>
+__global__ void __launch_bounds__(128, MINB) linearize_kernel(GroupView g, EvalCtx c) {
   pdl_sync();
   typedef FactorTraits<TYPE> FT;
   enum { D = FT::D, NC = FT::N1 + FT::N2 + 1 };
@@ -848,11 +850,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
-template <int DC, typename JT = double>
+// STAGED: the conditional [R S' d'] of the warp's 4 points goes through shared memory and leaves as contiguous 256-byte
+// store instructions.  Direct (STAGED = false): every lane stores its camera's 3 x DC block 8 bytes at a time, 3 DC * 8 bytes
+// apart from its neighbour's — each 32-byte sector is written by four separate instructions (ncu, bal_1m: L2 66 % busy,
+// the top utilisation of the kernel, DRAM 50 %).  ncap = doubles reserved per point (3 x the widest n of the kind).
+template <int DC, typename JT = double, bool STAGED = false>
 __global__ void __launch_bounds__(128)
 leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int i_begin, int i_end,
                          const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
-                         const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc) {
+                         const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int ncap) {
   pdl_sync();
   const double lambda = *lambda_ptr;
   const int sub = threadIdx.x & 7;
@@ -916,11 +922,15 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
   const double i22 = rsqrt(p22);
   const double r22 = p22 * i22;
   if (!(dexp(r11) - dexp(r22) < 12)) ok = false;
-  if (!live) return;
-  if (!ok && sub == 0) atomicMax(&sc->fail_code, INT_MAX - c);
-  const int n = 3 + t.ns[c] + 1;
+  if (!STAGED && !live) return;
+  if (live && !ok && sub == 0) atomicMax(&sc->fail_code, INT_MAX - c);
+  const int n = live ? 3 + t.ns[c] + 1 : 0;
   double* M = t.arena + t.off[c];   // compact conditional [R S' d'], column-major 3 x n
-  if (sub == 0) {
+  if (STAGED) {
+    B200_DYN_SMEM(double, sm_dyn);
+    M = sm_dyn + (size_t)(threadIdx.x >> 3) * ncap;     // this point's conditional, staged
+  }
+  if (live && sub == 0) {
     const double d0 = v[6] * i00;
     const double d1 = (v[7] - r01 * d0) * i11;
     const double d2 = (v[8] - r02 * d0 - r12 * d1) * i22;
@@ -940,6 +950,19 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
       const double s1 = (w1 - r01 * s0) * i11;
       const double s2 = (w2 - r02 * s0 - r12 * s1) * i22;
       Mc[3 * cc] = s0; Mc[3 * cc + 1] = s1; Mc[3 * cc + 2] = s2;
+    }
+  }
+  if (STAGED) {
+    B200_DYN_SMEM(double, sm_dyn);
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int pt = 0; pt < 4; pt++) {
+      const int np = __shfl_sync(0xffffffffu, n, 8 * pt), cp = __shfl_sync(0xffffffffu, c, 8 * pt);
+      if (np == 0) continue;       // (warp-uniform: a point past the end of the list)
+      const double* src = sm_dyn + (size_t)((threadIdx.x >> 5) * 4 + pt) * ncap;
+      double* dst = t.arena + t.off[cp];
+      for (int e = lane; e < 3 * np; e += 32) dst[e] = src[e];
     }
   }
 }

@@ -260,7 +260,8 @@ int b200_get_jacobian_precision(const b200_problem* prob);
 /* Kernel-variant switches of one problem, for A/B measurements (every variant computes the same result):
  * "schur_mma" 1 (default) = the per-run Schur complement of the BAL point leaves on the FP64 tensor path, 0 = the
  * FMA-tile kernel; "schur_pb" 4 / 6 = its points per staged batch; "df_minb" 2 / 3 = the dense-front kernel variant;
- * "lin_variant" = linearize_kernel variant of the projection groups.  Unknown key: B200_INVALID_ARGUMENT. */
+ * "lin_variant" 0 / 4 = linearize_kernel build of the projection groups (64 / 128 registers); "factor_staged" 1 (default) / 0
+ * = leaf_point_factor_kernel stores the conditionals through shared memory / directly.  Unknown key: B200_INVALID_ARGUMENT. */
 int b200_set_tuning(b200_problem* prob, const char* key, int64_t value);
 
 /* GaussianFactorGraph::hessianDiagonal(), gtsam/linear/GaussianFactorGraph.cpp:279-287.

@@ -300,6 +300,8 @@ def midsize(model):
         dev, orc = capi.DeviceProblem(ctx, prob), O.OracleProblem(prob)
         os.environ.pop("B200_LEAF_RUN_MAX"); os.environ.pop("B200_SCHUR_PB")
         dev.set_tuning("schur_mma", mma)
+        if not mma:     # the other variants ride along: conditionals stored directly, 128-register linearize build
+            dev.set_tuning("factor_staged", 0); dev.set_tuning("lin_variant", 4)
         dev.set_jacobian_precision(f32); orc.set_jacobian_precision(f32)
         dev.linearize(); orc.linearize()
         for lam, diag in ((1e-3, False), (1e-2, True)):
@@ -400,6 +402,18 @@ def coverage(_):
         del dl
         dev.close()
     assert shrunk >= 1
+    # ticket order of the dataflow tiles across levels (B200_DF_ORDER=1, with and without lagged trailing columns): the emulator runs
+    # the CTAs in ticket order, one after the other, so a dependency that pointed forwards would time out instead of passing
+    for lag in ("0", "2", "5"):
+        os.environ["B200_DF_ORDER"] = "1"; os.environ["B200_DF_LAG"] = lag
+        try:
+            for name in ("sphere_small_colamd", "sphere_small_metis", "bal_small_metis"):
+                prob = util.load_case(name)
+                dev = capi.DeviceProblem(ctx, prob)
+                util.check_against_dump(dev, prob, util.golden(name, "dump1"), 1e-2, 1)
+                dev.close()
+        finally:
+            os.environ.pop("B200_DF_ORDER"); os.environ.pop("B200_DF_LAG")
     os.environ["B200_NO_FUSE_EA"] = "1"; os.environ["B200_LEGACY_FRONTS"] = "1"   # the level-by-level panel / update chain
     try:
         prob = util.load_case("sphere_small_colamd")

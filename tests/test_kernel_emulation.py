@@ -226,7 +226,7 @@ def emu_eval():
     src = ("#include <cuda_runtime.h>\n#undef __global__\n#undef __device__\n#undef __forceinline__\n#undef __launch_bounds__\n"
            "#undef __restrict__\n#undef __shared__\n#include \"cuda_emu_prelude.h\"\n#include \"factors.cuh\"\nusing namespace b200;\n")
     src += _extract(eng, r"^struct GroupView \{")
-    src += _extract_template(kern, r"^template <int TYPE, typename JT = double>\n__global__ void __launch_bounds__\(128, FactorTraits")
+    src += _extract_template(kern, r"^template <int TYPE, typename JT = double, int MINB = [^\n]*\n__global__ void __launch_bounds__\(128, MINB\) linearize_kernel")
     src += _extract_template(kern, r"^template <int TYPE>\n__global__ void __launch_bounds__\(256\) error_kernel\(")
     src += _extract_template(kern, r"^__global__ void retract_kernel\(")
     src += EVAL_WRAPPERS
