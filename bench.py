@@ -416,7 +416,7 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         "linear_error": jac_bytes, "error": prob.linearize_bytes(jb) - jac_bytes,
     }
     kernels = {"linearize": "linearize_kernel", "leaf_fused": "leaf_point_factor_kernel / leaf_fused_kernel",
-               "leaf_schur": "leaf_point_schur_kernel", "memset_fronts": "memset", "linear_error": "linerr_kernel",
+               "leaf_schur": "leaf_point_schur_mma_kernel (per-run Schur complement of the point leaves: 8x8 DMMA tiles)", "memset_fronts": "memset", "linear_error": "linerr_kernel",
                "error": "error_kernel", "eliminate_large": "front_df_kernel (tile dataflow: Cholesky + TRSM + DMMA rank-32 updates + extend-add of every non-leaf front, one launch)",
                "back_substitute": "backsub_large_kernel / backsub_small_kernel / backsub_point_kernel"}
     fp64 = measure.fp64_peaks
@@ -432,7 +432,7 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
             fl = model["dense_flops"]                # supernodes that go through the dense-front kernels ONLY (no leaf flops)
             ach = fl * units / (ms_phase * 1e-3) / 1e12
             return {"kernel": kernels[name], "phase": name, "bound": "tensor", "achieved": ach, "peak": fp64[0], "unit": "TFLOP/s",
-                    "frac": ach / fp64[0] if fp64[0] else None, "traffic": None,
+                    "frac": ach / fp64[0] if fp64[0] else None, "traffic": measure.traffic.get(workload, {}).get(name),
                     "peak_source": "measured live: b200_measure_fp64_peak (mma.sync.m8n8k4.f64 from registers, all SMs); MEASURED_PEAKS.json "
                                    f"has no FP64 figure; FMA pipe measured {fp64[1]:.1f} TFLOP/s",
                     "ms_per_launch": ms_phase / units, "algorithmic_flops_per_launch": fl,

@@ -294,20 +294,20 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (nr <= 0) continue;
       const int* runs = p->d_fused_run_ptr + p->leaf_run_begin[kd];
       if (p->schur_mma) {
-        // FP64 tensor path: 8x8 DMMA tiles over (s+1)^2 / 2, 4 warps, TPW tiles per warp from the widest separator of the kind
-        const int dc = kd == 1 ? 6 : 9, maxw = p->leaf_max_w[kd], nt8 = (maxw + 7) / 8, tpw = (nt8 * (nt8 + 1) / 2 + 3) / 4;
-        const int mmax = std::max(1, (maxw - 1) / dc);
+        // FP64 tensor path: 8x8 DMMA tiles over (s+1)^2 / 2 and per camera; every warp stages and multiplies its own points
+        const int dc = kd == 1 ? 6 : 9, maxw = p->leaf_max_w[kd], nt8 = (maxw + 7) / 8;
+        const int mmax = std::max(1, (maxw - 1) / dc), cp = dc < 8 ? 8 : 16;
         const size_t jb = p->jac_f32 ? sizeof(float) : sizeof(double);
-        const size_t sm = (size_t)2 * 8 * nt8 * kSmKP * sizeof(double) + (size_t)2 * kSmPB * mmax * (2 * dc + 2) * jb;
+        const size_t sm = (size_t)4 * 2 * 8 * nt8 * kSmKS * sizeof(double) + (size_t)4 * 2 * mmax * cp * kSmPA * jb;
         bool done = false;
 #define B200_LAUNCH_SCHUR_MMA(DC_, T_)                                                                                                \
-        if (!done && dc == DC_ && tpw <= T_) {                                                                                        \
+        if (!done && dc == DC_ && nt8 <= T_) {                                                                                        \
           DISPATCH_JT(p, launch_k(leaf_point_schur_mma_kernel<DC_, T_, JT>, dim3(nr), dim3(128), sm, st, t, gt, (const int*)p->d_fused_list, runs, \
                    (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac));                                                    \
           done = true;                                                                                                                \
         }
-        B200_LAUNCH_SCHUR_MMA(6, 3) B200_LAUNCH_SCHUR_MMA(6, 4) B200_LAUNCH_SCHUR_MMA(6, 7)
-        B200_LAUNCH_SCHUR_MMA(9, 3) B200_LAUNCH_SCHUR_MMA(9, 4) B200_LAUNCH_SCHUR_MMA(9, 7) B200_LAUNCH_SCHUR_MMA(9, 14)
+        B200_LAUNCH_SCHUR_MMA(6, 4) B200_LAUNCH_SCHUR_MMA(6, 5) B200_LAUNCH_SCHUR_MMA(6, 7)
+        B200_LAUNCH_SCHUR_MMA(9, 4) B200_LAUNCH_SCHUR_MMA(9, 5) B200_LAUNCH_SCHUR_MMA(9, 7) B200_LAUNCH_SCHUR_MMA(9, 10)
 #undef B200_LAUNCH_SCHUR_MMA
         if (!done) { set_error("leaf_point_schur_mma_kernel: separator wider than the compiled tile counts"); return B200_CUDA_ERROR; }
         ctx->launches++;
@@ -1244,7 +1244,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
 #define B200_SM_ATTR(DC_, T_)                                                                                                          \
     B200_CUDA(cudaFuncSetAttribute(leaf_point_schur_mma_kernel<DC_, T_, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)); \
     B200_CUDA(cudaFuncSetAttribute(leaf_point_schur_mma_kernel<DC_, T_, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    B200_SM_ATTR(6, 3) B200_SM_ATTR(6, 4) B200_SM_ATTR(6, 7) B200_SM_ATTR(9, 3) B200_SM_ATTR(9, 4) B200_SM_ATTR(9, 7) B200_SM_ATTR(9, 14)
+    B200_SM_ATTR(6, 4) B200_SM_ATTR(6, 5) B200_SM_ATTR(6, 7) B200_SM_ATTR(9, 4) B200_SM_ATTR(9, 5) B200_SM_ATTR(9, 7) B200_SM_ATTR(9, 10)
 #undef B200_SM_ATTR
   }
 #endif

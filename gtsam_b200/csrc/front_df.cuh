@@ -241,7 +241,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
   double (*Dg)[kDfB + 1] = (double (*)[kDfB + 1])(df_smem + kDfOffDg);           // pivot rows out of the accumulators
   double* Rk = df_smem + kDfOffRk;                                 // R_kk: Rk[row * kDfLdR + col]
   double* invd = df_smem + kDfOffInvd;
-  __shared__ int s_task, s_ok;
+  __shared__ int s_task, s_ok, s_ready;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
 #ifndef B200_EMULATE
   if (blockIdx.x < (unsigned)v.warm_ctas) {
@@ -257,7 +257,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
   }
 #endif
   pdl_sync();
-  if (tid == 0) { s_task = atomicAdd(v.ctrl, 1); s_ok = 1; }
+  if (tid == 0) { s_task = atomicAdd(v.ctrl, 1); s_ok = 1; s_ready = 1 << 30; }
   __syncthreads();
   if (s_task >= v.ntasks) return;
   int tr_n = 0; (void)tr_n;
@@ -289,21 +289,42 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
     for (int b = 0; b < 4; b++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
+        // branch-free: 32 independent loads in flight (an entry outside the block reads M[0] and is dropped).  With the load
+        // under its predicate the compiler kept each negation next to its load inside a branch region: 32 L2 round trips
+        // in sequence, ~7 us per tile in the trace of the 10M-factor graph (round 2).
         const int lr = 8 * a + g, lc = 8 * b + 2 * q + h;
-        double val = 0.0;
-        if (lr < rs && lc < cs && rb + lr <= cb + lc) val = -__ldcg(M + (rb + lr) + (size_t)(cb + lc) * n);
-        acc[a][b][h] = val;
+        const bool in = lr < rs && lc < cs && rb + lr <= cb + lc;
+        const double val = __ldcg(M + (in ? (size_t)(rb + lr) + (size_t)(cb + lc) * n : (size_t)0));
+        acc[a][b][h] = in ? -val : 0.0;
       }
   const int last_rb = min(min(kDfTR * r + kDfTR - 1, j), NB - 1);   // last row block of the tile
   const bool diag_tile = j < K && last_rb == j;           // holds the diagonal block of pivot column j: factored after the loop
   const int kend = min(K, last_rb + 1) - (diag_tile ? 1 : 0);
+  // One look at the flags of EVERY step (5 per step: the column piece or R_kk, one row piece per warp), all in flight at
+  // once while the loads of C above are: the steps before the first unpublished piece need no polling.  (Trace of the
+  // 10M-factor graph, round 2: half of the steps found their pieces published and still paid ~1 us of poll + fence +
+  // barrier each; a tile of a front whose chain is ahead runs straight through now.)
+  {
+    int first_missing = 1 << 30;
+    for (int e = tid; e < 5 * kend; e += kDfThreads) {
+      const int k = e / 5, which = e - 5 * k;
+      int fl = -1;
+      if (which == 0) fl = k * NB + (k - kDfTR * r >= 0 ? k : j);
+      else { const int iw = kDfTR * r + which - 1; if (iw <= j && iw < NB && iw > k && iw != j) fl = k * NB + iw; }
+      if (fl >= 0 && df_ld_relaxed(flags + fl) < 1) first_missing = min(first_missing, k);
+    }
+    if (first_missing < (1 << 30)) atomicMin(&s_ready, first_missing);
+    df_fence_acquire();
+    __syncthreads();
+  }
+  const int ready = s_ready;                              // steps k < ready: every piece this tile reads is published and visible
   for (int k = 0; k < kend; k++) {
     const int wb = k - kDfTR * r;                         // the warp that holds pivot block k (< 0: above the tile)
     const int kb = kDfB * k, ks = min(kDfB, f - kb);      // pivot rows
     const bool need_row = wvalid && i > k && i != j;      // this warp updates rows below the pivot block with a piece of another tile
     if (wb >= 0) {
       // ================= pivot rows live in this tile: X = R_kk^-T C, publish piece (k, j) =================
-      if (tid == 0 && !df_wait(flags + k * NB + k, 1, v.ctrl)) s_ok = 0;
+      if (k >= ready && tid == 0 && !df_wait(flags + k * NB + k, 1, v.ctrl)) s_ok = 0;
       if (w == wb) {
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -344,7 +365,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
       DF_STAMP(6);
       // only now the pieces of the other tiles (the rows below the pivot block): the TRSM above never waits for them
       if (need_row) {
-        if (lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
+        if (k >= ready && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
         __syncwarp();
         df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
         cp_async_commit();
@@ -353,10 +374,12 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
       }
     } else {
       // ================= pivot block above the tile: fetch the two pieces =================
-      if (tid == 0 && !df_wait(flags + k * NB + j, 1, v.ctrl)) s_ok = 0;
-      if (need_row && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
-      __syncthreads();
-      if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
+      if (k >= ready) {
+        if (tid == 0 && !df_wait(flags + k * NB + j, 1, v.ctrl)) s_ok = 0;
+        if (need_row && lane == 0 && !df_wait(flags + k * NB + i, 1, v.ctrl)) s_ok = 0;
+        __syncthreads();
+        if (!s_ok) { if (tid == 0) atomicExch(&sc->df_abort, 1); return; }
+      }
       DF_STAMP(7);
       df_stage(Pc, M, n, kb, ks, cb, cs, tid, kDfThreads);
       if (need_row) df_stage(Pr[w], M, n, kb, ks, rb, rs, lane, 32);
@@ -429,6 +452,16 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
       double* P = t.arena + t.off[par];
       const int pn = t.nf[par] + t.ns[par] + 1;
       const int* map = t.ea_map + t.ea_ptr[c];
+      // the 4 row and 8 column slots of this thread's 32 entries first (12 independent loads, one latency), then the adds
+      // back to back.  (Trace of the 10M-factor graph, round 2: with the map looked up per entry the extend-add held the
+      // slot 11 us per tile, as long as four rank-32 updates.)
+      int mr[4], mc[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; a++) mr[a] = (8 * a + g < rs) ? map[rb + 8 * a + g - f] : -1;
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) mc[b][h] = (8 * b + 2 * q + h < cs) ? map[cb + 8 * b + 2 * q + h - f] : -1;
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -437,7 +470,7 @@ front_df_kernel(TreeView t, DfView v, Scalars* sc) {
           for (int h = 0; h < 2; h++) {
             const int lr = 8 * a + g, lc = 8 * b + 2 * q + h;
             if (lr < rs && lc < cs && rb + lr <= cb + lc) {
-              const int pi = map[rb + lr - f], pj = map[cb + lc - f];
+              const int pi = mr[a], pj = mc[b][h];
               const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
               atomicAdd(P + lo + (size_t)hi * pn, -acc[a][b][h]);
             }

@@ -1141,23 +1141,31 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // The same per-run half on the FP64 tensor path (round 2).  ncu of leaf_point_schur_kernel (profiles/r02_profile_summary.md,
 // bal_1m): 19.7k thread instructions per point for 1.7k useful FMAs, 43 % issue-active — the 3x3 register tiles spend their
 // issue slots on shared-memory loads (6 LDS.64 per 9 FMAs) and index arithmetic, not on arithmetic.  Here the run's
-// -S'^T S' is what it is, a SYRK: the [S' d'] rows of 16 points are staged TRANSPOSED ([column][k = 3 pt + r], pitch 52 doubles:
-// conflict-free fragments) and every warp multiplies its 8x8 tiles of the (s+1)^2 upper triangle with mma.sync.m8n8k4.f64
-// — one DMMA = 256 FMAs for two 8-byte shared-memory loads — while the block-diagonal A_c^T A_c, A_c^T b and b^T b terms
-// (2 FMAs per entry and point) are summed by one thread per entry.  One extend-add per run, as before.
+// -S'^T S' is what it is, a SYRK, and so is every camera's [A_c b]^T [A_c b]:
+//   * every WARP runs its own pipeline over mini-batches of 4 points (the run's points are dealt round-robin to the 4
+//     warps): it stages its points' [S' d'] rows TRANSPOSED ([column][k = 3 pt + r], 12 doubles per column: conflict-free
+//     fragments, no padding) and their [A_c b] blocks ([camera][column][k = 2 pt + r]) with cp.async, double-buffered, and
+//     multiplies what it staged — no block barrier in the loop;
+//   * per k-step of 4 rows it loads ONE fragment per 8-column strip and issues mma.sync.m8n8k4.f64 for every tile pair
+//     of the upper triangle (the same fragment is the A operand, negated, and the B operand): 10 DMMAs = 2560 FMAs for
+//     4 shared-memory loads at 32 columns; the (DC+1)^2 block of a camera is one more tile (four at 9 dofs);
+//   * the four warps' partial sums are added in shared memory in a FIXED order, then one extend-add per entry and run
+//     (HessianFactor::updateHessian of the leaf's separator factor) — a run's contribution is bitwise reproducible.
 // ---------------------------------------------------------------------------
-constexpr int kSmPB = 16;               // points per staged batch: K = 48 rows = 12 DMMA k-steps
-constexpr int kSmKB = 3 * kSmPB;
-constexpr int kSmKP = kSmKB + 4;        // pitch of one column of S'^T: (q * 52 + g) mod 16 distinct over the 16 lanes of a half-warp
+constexpr int kSmMP = 4;                 // points per warp mini-batch
+constexpr int kSmKS = 3 * kSmMP;         // rows (and pitch) of a staged S'^T column: (q * 12 + g) mod 16 distinct over a half-warp
+constexpr int kSmKA = 2 * kSmMP;         // rows of a staged [A_c b]^T column; pitch 12 (doubles and floats: conflict-free)
+constexpr int kSmPA = 12;
 
-template <int DC, int TPW, typename JT = double>   // TPW: 8x8 tiles per warp = ceil(tiles of the widest separator / 4)
-__global__ void __launch_bounds__(128)
+template <int DC, int NTT, typename JT = double>   // NTT: 8-column strips of the widest separator (+ rhs column) of the kind
+__global__ void __launch_bounds__(128, (NTT <= 4 && DC == 6) ? 4 : ((NTT <= 5 && DC == 6) ? 3 : (NTT <= 7 ? 2 : 1)))
 leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
                             const int* __restrict__ fac_ptr, const int2* __restrict__ fac) {
   pdl_sync();
-  constexpr int PB = kSmPB, KP = kSmKP, AW = 2 * DC + 2;   // per factor: A_c (2 x DC, column-major) and b (2)
-  constexpr int NE = (DC + 1) * (DC + 2) / 2;               // per camera: upper triangle of [A_c b]^T [A_c b]
-  constexpr int AV = (kPtMaxObs * NE + 127) / 128;          // those entries per thread
+  constexpr int MP = kSmMP, KS = kSmKS, PA = kSmPA;
+  constexpr int CP = DC < 8 ? 8 : 16, CT = CP / 8;           // [A_c b] has DC + 1 columns: one 8x8 tile, or 2 x 2 at 9 dofs
+  constexpr int NAT = CT * (CT + 1) / 2;
+  constexpr int NI = (3 * 8 * NTT + 31) / 32;                // 8-byte copies per lane and point of [S' d']
   B200_DYN_SMEM(double, sm_dyn);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int r0 = run_ptr[blockIdx.x], r1 = run_ptr[blockIdx.x + 1];
@@ -1167,45 +1175,36 @@ leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ l
   const int s = t.ns[c0], w = s + 1;
   const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
   const int NT = (w + 7) >> 3, WP = 8 * NT;
-  double* sT = sm_dyn;                                              // [2][WP][KP]: S'^T, entry (col, k = 3 pt + r)
-  JT* sA = reinterpret_cast<JT*>(sm_dyn + 2 * WP * KP);             // [2][PB][m][AW], in the Jacobians' storage type
-  // this warp's 8x8 tiles (ti <= tj) of the upper triangle, round-robin over the 4 warps
-  int ti[TPW], tj[TPW];
-  double acc[TPW][2];
+  const int s_doubles = 2 * WP * KS;                          // per warp: S'^T, two buffers
+  const int a_elems = 2 * m * CP * PA;                        // per warp: [A_c b]^T of m cameras, two buffers, in JT
+  double* sS = sm_dyn + (size_t)warp * s_doubles;
+  JT* sA = reinterpret_cast<JT*>(sm_dyn + (size_t)4 * s_doubles) + (size_t)warp * a_elems;
+  double acc[NTT][NTT][2];                                    // tile (ti <= tj) of -S'^T S'
+  double accA[kPtMaxObs][NAT][2];                             // per camera: tiles of [A_c b]^T [A_c b]
 #pragma unroll
-  for (int u = 0; u < TPW; u++) {
-    int e = warp + 4 * u, a = 0;
-    while (a < NT && e >= NT - a) { e -= NT - a; a++; }
-    ti[u] = a < NT ? a : -1;
-    tj[u] = a + e;
-    acc[u][0] = acc[u][1] = 0.0;
-  }
-  // this thread's entries of the per-camera blocks: (camera slot, x <= y) with column DC = the rhs
-  int aci[AV], ax[AV], ay[AV];
-  double aacc[AV];
+  for (int a = 0; a < NTT; a++)
 #pragma unroll
-  for (int v = 0; v < AV; v++) {
-    const int e = tid + 128 * v;
-    aacc[v] = 0.0;
-    aci[v] = -1; ax[v] = ay[v] = 0;
-    if (e < m * NE) { aci[v] = e / NE; tri_decode(e - aci[v] * NE, ax[v], ay[v]); }
-  }
-  for (int e = tid; e < 2 * (WP - w) * KP; e += 128) {             // zero columns behind the rhs column, written once
-    const int b = e / ((WP - w) * KP), r = e - b * (WP - w) * KP;
-    sT[(size_t)b * WP * KP + w * KP + r] = 0.0;
-  }
-  const double* srcS[PB / 4];    // [S' d'] of the points this warp copies (points warp, warp + 4, ... of a batch)
-  const JT* srcJ = nullptr;      // this thread's factor (point tid>>3, factor tid&7), staged by camera slot
+    for (int b = 0; b < NTT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll
+  for (int ci = 0; ci < kPtMaxObs; ci++)
+#pragma unroll
+    for (int x = 0; x < NAT; x++) accA[ci][x][0] = accA[ci][x][1] = 0.0;
+  // padding never written by the copies: columns behind the rhs column, columns behind b
+  for (int e = lane; e < 2 * WP * KS; e += 32) { const int col = (e / KS) % WP; if (col >= w) sS[e] = 0.0; }
+  for (int e = lane; e < a_elems; e += 32) { const int col = (e / PA) % CP; if (col > DC || e % PA >= kSmKA) sA[e] = (JT)0; }
+  int soff[NI];                                                // destination of this lane's copies, per point + 3 pt
+#pragma unroll
+  for (int i = 0; i < NI; i++) { const int e = lane + 32 * i, col = e / 3; soff[i] = e < 3 * w ? col * KS + (e - 3 * col) : -1; }
+  const int npts = r1 - r0, nmb = (npts + MP - 1) / MP;       // mini-batches of the run; this warp takes warp, warp + 4, ...
+  const double* srcS[MP];
+  const JT* srcJ = nullptr;      // this lane's factor (point lane>>3 of the mini-batch, factor lane&7), staged by camera slot
   size_t cntJ = 0;
   int slotJ = -1;
-  auto load_idx = [&](int b0) {
-    const int nb = min(PB, r1 - b0);
+  auto load_idx = [&](int mb) {
+    const int b0 = r0 + MP * mb, nb = min(MP, r1 - b0);
 #pragma unroll
-    for (int z = 0; z < PB / 4; z++) {
-      const int pt = warp + 4 * z;
-      srcS[z] = pt < nb ? t.arena + t.off[list[b0 + pt]] + 9 : nullptr;
-    }
-    const int pt = tid >> 3, fi = tid & 7;
+    for (int z = 0; z < MP; z++) srcS[z] = z < nb ? t.arena + t.off[list[b0 + z]] + 9 : nullptr;
+    const int pt = lane >> 3, fi = lane & 7;
     slotJ = -1;
     if (pt < nb && fi < m) {
       const int2 gf = fac[fac_ptr[b0 + pt] + fi];
@@ -1216,60 +1215,112 @@ leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ l
     }
   };
   auto issue = [&](int buf, int nb) {
-    double* T = sT + (size_t)buf * WP * KP;
+    double* S = sS + buf * WP * KS;
+    JT* A = sA + buf * m * CP * PA;
 #pragma unroll
-    for (int z = 0; z < PB / 4; z++)
-      if (srcS[z])
-        for (int e = lane; e < 3 * w; e += 32) {
-          const int col = e / 3;
-          cp_async8(T + col * KP + 3 * (warp + 4 * z) + (e - 3 * col), srcS[z] + e);
-        }
+    for (int z = 0; z < MP; z++)
+      if (srcS[z]) {
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+          if (soff[i] >= 0) cp_async8(S + soff[i] + 3 * z, srcS[z] + lane + 32 * i);
+      }
     if (slotJ >= 0) {
-      JT* dst = sA + ((size_t)(buf * PB + (tid >> 3)) * m + slotJ) * AW;
+      JT* dst = A + slotJ * CP * PA + 2 * (lane >> 3);
 #pragma unroll
-      for (int el = 0; el < 2 * DC; el++) cp_async_el(dst + el, srcJ + (size_t)el * cntJ);
-      cp_async_el(dst + 2 * DC, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
-      cp_async_el(dst + 2 * DC + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
+      for (int cc = 0; cc < DC; cc++) {
+        cp_async_el(dst + cc * PA, srcJ + (size_t)(2 * cc) * cntJ);
+        cp_async_el(dst + cc * PA + 1, srcJ + (size_t)(2 * cc + 1) * cntJ);
+      }
+      cp_async_el(dst + DC * PA, srcJ + (size_t)(2 * (DC + 3)) * cntJ);
+      cp_async_el(dst + DC * PA + 1, srcJ + (size_t)(2 * (DC + 3) + 1) * cntJ);
     }
     cp_async_commit();
-    // a short last batch: the k rows up to the next multiple of 4 read as zero
-    const int k0 = 3 * nb, k1 = (k0 + 3) & ~3;
-    for (int e = tid; e < w * (k1 - k0); e += 128) { const int col = e / (k1 - k0); T[col * KP + k0 + (e - col * (k1 - k0))] = 0.0; }
+    if (nb < MP) {     // a short last mini-batch: the rows of the missing points read as zero
+      for (int e = lane; e < w * (KS - 3 * nb); e += 32) { const int col = e / (KS - 3 * nb); S[col * KS + 3 * nb + (e - col * (KS - 3 * nb))] = 0.0; }
+      for (int e = lane; e < m * (DC + 1) * (kSmKA - 2 * nb); e += 32) {
+        const int cc = e / (kSmKA - 2 * nb);
+        A[cc / (DC + 1) * CP * PA + cc % (DC + 1) * PA + 2 * nb + (e - cc * (kSmKA - 2 * nb))] = (JT)0;
+      }
+    }
   };
-  load_idx(r0);
-  issue(0, min(PB, r1 - r0));
-  load_idx(r0 + PB);
+  if (warp < nmb) {
+    load_idx(warp);
+    issue(0, min(MP, npts - MP * warp));
+    if (warp + 4 < nmb) load_idx(warp + 4);
+  }
   int buf = 0;
-  for (int b0 = r0; b0 < r1; b0 += PB, buf ^= 1) {
-    const int nbp = min(PB, r1 - b0);
-    if (b0 + PB < r1) {
-      issue(buf ^ 1, min(PB, r1 - b0 - PB));
-      load_idx(b0 + 2 * PB);
+  for (int mb = warp; mb < nmb; mb += 4, buf ^= 1) {
+    if (mb + 4 < nmb) {
+      issue(buf ^ 1, min(MP, npts - MP * (mb + 4)));
+      if (mb + 8 < nmb) load_idx(mb + 8);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
-    const double* T = sT + (size_t)buf * WP * KP;
-    const int ksteps = (3 * nbp + 3) >> 2;
-    for (int k4 = 0; k4 < ksteps; k4++) {
+    __syncwarp();
+    const double* S = sS + buf * WP * KS;
 #pragma unroll
-      for (int u = 0; u < TPW; u++) {
-        if (ti[u] < 0) continue;      // (warp-uniform)
-        const double a = -T[(8 * ti[u] + g) * KP + 4 * k4 + q];
-        const double b = T[(8 * tj[u] + g) * KP + 4 * k4 + q];
-        dmma_m8n8k4(acc[u][0], acc[u][1], a, b);
+    for (int k4 = 0; k4 < KS / 4; k4++) {
+      double f[NTT];
+#pragma unroll
+      for (int a = 0; a < NTT; a++) f[a] = a < NT ? S[(8 * a + g) * KS + 4 * k4 + q] : 0.0;
+#pragma unroll
+      for (int a = 0; a < NTT; a++)
+#pragma unroll
+        for (int b = a; b < NTT; b++)
+          if (b < NT) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], -f[a], f[b]);     // (warp-uniform)
+    }
+    const JT* A = sA + buf * m * CP * PA;
+#pragma unroll
+    for (int ci = 0; ci < kPtMaxObs; ci++) {
+      if (ci >= m) break;
+#pragma unroll
+      for (int k4 = 0; k4 < kSmKA / 4; k4++) {
+        double fa[CT];
+#pragma unroll
+        for (int x = 0; x < CT; x++) fa[x] = (double)A[(ci * CP + 8 * x + g) * PA + 4 * k4 + q];
+#pragma unroll
+        for (int x = 0; x < CT; x++)
+#pragma unroll
+          for (int y = x; y < CT; y++) dmma_m8n8k4(accA[ci][x * CT - x * (x - 1) / 2 + (y - x)][0], accA[ci][x * CT - x * (x - 1) / 2 + (y - x)][1], fa[x], fa[y]);
       }
     }
-    const JT* Ab = sA + (size_t)buf * PB * m * AW;
+    __syncwarp();
+  }
+  // ---- the four warps' sums, added in a fixed order in shared memory (the staging buffers are free now) ----
+  __syncthreads();
+  double* R = sm_dyn;                                          // [WP][WP], upper triangle used (WP^2 <= 96 WP doubles of S' staging)
+  for (int round = 0; round < 4; round++) {
+    if (warp == round) {
 #pragma unroll
-    for (int v = 0; v < AV; v++) {
-      if (aci[v] < 0) continue;
-      const JT* A = Ab + aci[v] * AW;
-      double sum = 0.0;
-      for (int pt = 0; pt < nbp; pt++, A += m * AW)
-        sum += (double)A[2 * ax[v]] * (double)A[2 * ay[v]] + (double)A[2 * ax[v] + 1] * (double)A[2 * ay[v] + 1];
-      aacc[v] += sum;
+      for (int a = 0; a < NTT; a++)
+#pragma unroll
+        for (int b = a; b < NTT; b++)
+          if (b < NT) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              double* dst = R + (8 * a + g) * WP + 8 * b + 2 * q + h;
+              *dst = round == 0 ? acc[a][b][h] : *dst + acc[a][b][h];
+            }
+          }
+      __syncwarp();
+#pragma unroll
+      for (int ci = 0; ci < kPtMaxObs; ci++) {
+        if (ci >= m) break;
+#pragma unroll
+        for (int x = 0; x < CT; x++)
+#pragma unroll
+          for (int y = x; y < CT; y++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int lx = 8 * x + g, ly = 8 * y + 2 * q + h;          // entry of [A_c b]^T [A_c b]; column DC = b
+              if (lx <= ly && ly <= DC) {
+                const int i = lx < DC ? ci * DC + lx : s, j = ly < DC ? ci * DC + ly : s;
+                R[i * WP + j] += accA[ci][x * CT - x * (x - 1) / 2 + (y - x)][h];
+              }
+            }
+        __syncwarp();          // (the b^T b of every camera lands on the same entry)
+      }
     }
     __syncthreads();
   }
@@ -1277,26 +1328,12 @@ leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ l
   double* P = t.arena + t.off[p];
   const int pn = t.nf[p] + t.ns[p] + 1;
   const int* map = t.ea_map + t.ea_ptr[c0];
-#pragma unroll
-  for (int u = 0; u < TPW; u++) {
-    if (ti[u] < 0) continue;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int i = 8 * ti[u] + g, j = 8 * tj[u] + 2 * q + h;
-      if (i <= j && j < w) {
-        const int a = map[i], bq = map[j];
-        const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
-        atomicAdd(P + lo + (size_t)hi * pn, acc[u][h]);
-      }
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < AV; v++) {
-    if (aci[v] < 0) continue;
-    const int i = ax[v] < DC ? aci[v] * DC + ax[v] : s, j = ay[v] < DC ? aci[v] * DC + ay[v] : s;
+  for (int e = tid; e < w * w; e += 128) {
+    const int i = e / w, j = e - i * w;
+    if (i > j) continue;
     const int a = map[i], bq = map[j];
     const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
-    atomicAdd(P + lo + (size_t)hi * pn, aacc[v]);
+    atomicAdd(P + lo + (size_t)hi * pn, R[i * WP + j]);
   }
 }
 

@@ -94,6 +94,17 @@ def main():
             except Exception:
                 pass
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "r02_ncu_dram_bytes.json"), "w"), indent=1)
+    # per workload and bench phase (what bench.py's roofline objects report as `traffic`): dram bytes of ONE launch of the phase's kernel
+    phase_of = {"front_df_kernel": "eliminate_large", "leaf_point_factor_kernel": "leaf_fused", "leaf_point_schur_mma_kernel": "leaf_schur",
+                "leaf_point_schur_kernel": "leaf_schur", "linearize_kernel<3": "linearize", "linearize_kernel<4": "linearize",
+                "linerr_kernel<3": "linear_error", "linerr_kernel<4": "linear_error", "error_kernel<3": "error", "error_kernel<4": "error"}
+    by_phase = {}
+    for name, rec in traffic.items():
+        wl = re.sub(r"^r02[a-z]?_.*?_(bal_\w+?|sphere\w+?)\.ncu-rep$", r"\1", rec["report"])
+        for prefix, ph in phase_of.items():
+            if name.startswith(prefix):
+                by_phase.setdefault(wl, {})[ph] = rec["dram_bytes"]
+    json.dump(by_phase, open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json"), "w"), indent=1)
 
 
 main()

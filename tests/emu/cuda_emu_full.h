@@ -160,6 +160,7 @@ template <class T> static inline T __ldcg(const T* p) { return *(const volatile 
 static inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 static inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 static inline unsigned atomicInc(unsigned* p, unsigned lim) { const unsigned o = *p; *p = o >= lim ? 0 : o + 1; return o; }
 
