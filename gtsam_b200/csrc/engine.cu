@@ -274,11 +274,11 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
       if (p->factor_staged)                                                                                                           \
       DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT, true>, dim3(nb), dim3(128), (size_t)16 * ncap * sizeof(double), st, t, gt, (const int*)p->d_fused_list, i0, i1, \
                (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
-               p->d_scalars, ncap));                                                                                                  \
+               p->d_scalars, ncap, (const int2*)p->d_pt_tab, (const int64_t*)p->d_pt_off));                                           \
       else                                                                                                                            \
       DISPATCH_JT(p, launch_k(leaf_point_factor_kernel<DC_, JT, false>, dim3(nb), dim3(128), 0, st, t, gt, (const int*)p->d_fused_list, i0, i1, \
                (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac, (const double*)p->d_lambda, hd, min_diag, max_diag,        \
-               p->d_scalars, ncap));
+               p->d_scalars, ncap, (const int2*)p->d_pt_tab, (const int64_t*)p->d_pt_off));
       if (kd == 1) { B200_LAUNCH_POINT(6) } else { B200_LAUNCH_POINT(9) }
 #undef B200_LAUNCH_POINT
       ctx->launches++;
@@ -303,7 +303,7 @@ static int enqueue_solve(b200_problem* p, bool damped, int diagonal, double min_
 #define B200_LAUNCH_SCHUR_MMA(DC_, T_)                                                                                                \
         if (!done && dc == DC_ && nt8 <= T_) {                                                                                        \
           DISPATCH_JT(p, launch_k(leaf_point_schur_mma_kernel<DC_, T_, JT>, dim3(nr), dim3(128), sm, st, t, gt, (const int*)p->d_fused_list, runs, \
-                   (const int*)p->d_fused_fac_ptr, (const int2*)p->d_fused_fac));                                                    \
+                   (const int2*)p->d_pt_tab, (const int64_t*)p->d_pt_off));                                                          \
           done = true;                                                                                                                \
         }
         B200_LAUNCH_SCHUR_MMA(6, 4) B200_LAUNCH_SCHUR_MMA(6, 5) B200_LAUNCH_SCHUR_MMA(6, 7)
@@ -1085,7 +1085,7 @@ int b200_problem_destroy(b200_problem* p) {
   cudaFree(p->d_view_idx[0]); cudaFree(p->d_view_idx[1]); cudaFree(p->d_view_buf); cudaFree(p->d_gather_buf);
   cudaFree(p->d_ts_cliques); cudaFree(p->d_ts_xoff); cudaFree(p->d_ts_owned); cudaFree(p->d_topx);
   cudaFree(p->d_fused_run_ptr);
-  cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
+  cudaFree(p->d_fused_list); cudaFree(p->d_fused_fac_ptr); cudaFree(p->d_fused_fac); cudaFree(p->d_pt_tab); cudaFree(p->d_pt_off); cudaFree(p->d_partials); cudaFree(p->d_counters); cudaFree(p->d_scalars);
   cudaFreeHost(p->h_scalars); cudaFreeHost(p->h_pinned); cudaFreeHost(p->h_lambda); cudaFree(p->d_lambda);
   for (int i = 0; i < 2; i++) if (p->try_graph[i]) cudaGraphExecDestroy(p->try_graph[i]);
   cudaFree(p->d_saved_values);
@@ -1382,6 +1382,25 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     UP(upload(&p->d_fused_run_ptr, run_ptr, st));
     UP(upload(&p->d_fused_fac_ptr, fptr, st));
     UP(upload(&p->d_fused_fac, ffac, st));
+    // BAL point leaves: one flat record per (point position, factor slot 0..7) = (factor index in its group, group << 8 | camera
+    // slot) and the offset of the point's conditional, so that the leaf kernels reach their operands through ONE level of index
+    // loads (list -> fac_ptr -> fac -> scat was a chain of three dependent loads in front of every batch of points)
+    if (p->leaf_pos_end[2] > p->leaf_pos_begin[1] || p->leaf_pos_end[1] > p->leaf_pos_begin[1]) {
+      std::vector<int2> tab((size_t)p->n_fused * kPtMaxObs, make_int2(-1, 0));
+      std::vector<int64_t> poff((size_t)p->n_fused, 0);
+      for (int i = 0; i < p->n_fused; i++) {
+        const int c = fused_list[i], kd = leaf_kind[c];
+        poff[i] = p->h_off[c];
+        if (kd == 0) continue;
+        const int dc = kd == 1 ? 6 : 9;
+        for (int q = fptr[i]; q < fptr[i + 1]; q++) {
+          const int2 gf = ffac[q];
+          tab[(size_t)i * kPtMaxObs + (q - fptr[i])] = make_int2(gf.y, (gf.x << 8) | ((hscat[gf.x][gf.y].y - 3) / dc));
+        }
+      }
+      UP(upload(&p->d_pt_tab, tab, st));
+      UP(upload(&p->d_pt_off, poff, st));
+    }
   }
   // ---- level plans: small (one warp per clique) / large (blocked) ----
   // phase 0: the subtrees this rank owns, leaves to subtree roots; phase 1: the replicated top.
@@ -1507,14 +1526,16 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   }
   p->ts_begin.push_back((int)p->ts_fronts.size());
   {
-    // Ticket order across levels (B200_DF_ORDER=1; 0 = level by level): by the ESTIMATED time a tile can finish, in pivot
+    // Ticket order across levels (B200_DF_ORDER=1, the default; 0 = level by level): by the ESTIMATED time a tile can finish, in pivot
     // steps — its front's start (= the latest finish of a child front) + the pivot steps it has to see; trailing-column tiles
     // optionally B200_DF_LAG steps later (they then find their pieces ready instead of idling on a slot).  A front whose
     // children are done early no longer waits for the tickets of the rest of its level.  Dependency-safe: a producer's key
     // is never larger than its consumer's (same front: fewer steps, pivot columns before trailing ones; children: finish
     // <= the parent's start), ties broken as before — and df_order_is_safe() below checks the result, whatever the order.
-    const int df_order = getenv("B200_DF_ORDER") ? atoi(getenv("B200_DF_ORDER")) : 0;
-    const int df_lag = getenv("B200_DF_LAG") ? std::max(0, atoi(getenv("B200_DF_LAG"))) : 0;
+    // (measured on the B200, profiles/r02_ab_summary.md: order 1 / lag 2 takes 3 % off the dense fronts of the 10M-factor graph and
+    // leaves the smaller trees where they were: the default)
+    const int df_order = getenv("B200_DF_ORDER") ? atoi(getenv("B200_DF_ORDER")) : 1;
+    const int df_lag = getenv("B200_DF_LAG") ? std::max(0, atoi(getenv("B200_DF_LAG"))) : 2;
     auto shape = [&](int c, int& K, int& NB) {
       const int f = S.nf[c], nn = f + S.ns[c] + 1;
       K = (f + kDfB - 1) / kDfB; NB = K + (nn - f + kDfB - 1) / kDfB;

@@ -154,6 +154,8 @@ struct b200_problem {
   int leaf_pos_begin[3] = {0, 0, 0}, leaf_pos_end[3] = {0, 0, 0};  // the same ranges as positions in d_fused_list
   int *d_fused_list = nullptr, *d_fused_fac_ptr = nullptr, *d_fused_run_ptr = nullptr;
   int2* d_fused_fac = nullptr;
+  int2* d_pt_tab = nullptr;         // BAL point leaves: per (list position, factor slot) (factor index, group << 8 | camera slot); -1: no factor
+  int64_t* d_pt_off = nullptr;      // ... and the arena offset of the point's conditional
   int64_t top_doubles = 0;          // [0, top_doubles) = fronts of the replicated top (all-reduced when sharded)
   int n_sub_levels = 0;             // levels[0..n_sub_levels) = owned subtrees, the rest = the top
   int64_t arena_doubles = 0, zero_doubles = 0;  // [0, zero_doubles) = non-leaf fronts (memset per solve)

@@ -858,25 +858,32 @@ template <int DC, typename JT = double, bool STAGED = false>
 __global__ void __launch_bounds__(128)
 leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, int i_begin, int i_end,
                          const int* __restrict__ fac_ptr, const int2* __restrict__ fac, const double* __restrict__ lambda_ptr,
-                         const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int ncap) {
+                         const double* __restrict__ hdiag, double min_diag, double max_diag, Scalars* sc, int ncap,
+                         const int2* __restrict__ pt_tab, const int64_t* __restrict__ pt_off) {
   pdl_sync();
   const double lambda = *lambda_ptr;
   const int sub = threadIdx.x & 7;
   const int idx = i_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
   const bool live = idx < i_end;
-  int c = 0, m = 0, f0 = 0;
-  if (live) { c = list[idx]; f0 = fac_ptr[idx]; m = fac_ptr[idx + 1] - f0; }
+  // one level of index loads: this lane's factor from the flat table, the conditional's offset, the clique id (failure
+  // code / diagonal damping only)
+  int c = 0;
+  int2 rec = make_int2(-1, 0);
+  int64_t moff = 0;
+  if (live) { rec = pt_tab[(size_t)idx * kPtMaxObs + sub]; moff = pt_off[idx]; c = list[idx]; }
+  int m = rec.x >= 0 ? 1 : 0;                                  // factors of this lane's point: summed over its 8 lanes
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
   double Ac[2][DC], Ap[2][3], b[2];
   int tk = 0;
   double v[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) v[i] = 0.0;
-  if (sub < m) {
-    const int2 gf = fac[f0 + sub];
-    const GroupView& g = gt.g[gf.x];
+  if (rec.x >= 0) {
+    const GroupView& g = gt.g[rec.y >> 8];
     const size_t cnt = (size_t)g.count;
-    const JT* J = reinterpret_cast<const JT*>(g.J) + gf.y;
-    tk = g.scat[gf.y].y - 3;
+    const JT* J = reinterpret_cast<const JT*>(g.J) + rec.x;
+    tk = DC * (rec.y & 0xff);
 #pragma unroll
     for (int cc = 0; cc < DC; cc++) { Ac[0][cc] = J[(size_t)(2 * cc) * cnt]; Ac[1][cc] = J[(size_t)(2 * cc + 1) * cnt]; }
 #pragma unroll
@@ -924,8 +931,8 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
   if (!(dexp(r11) - dexp(r22) < 12)) ok = false;
   if (!STAGED && !live) return;
   if (live && !ok && sub == 0) atomicMax(&sc->fail_code, INT_MAX - c);
-  const int n = live ? 3 + t.ns[c] + 1 : 0;
-  double* M = t.arena + t.off[c];   // compact conditional [R S' d'], column-major 3 x n
+  const int n = live ? 3 + DC * m + 1 : 0;          // (a point clique of these kinds: one factor per separator camera)
+  double* M = t.arena + moff;       // compact conditional [R S' d'], column-major 3 x n
   if (STAGED) {
     B200_DYN_SMEM(double, sm_dyn);
     M = sm_dyn + (size_t)(threadIdx.x >> 3) * ncap;     // this point's conditional, staged
@@ -939,7 +946,7 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
     M[6] = r02; M[7] = r12; M[8] = r22;
     M[3 * (n - 1)] = d0; M[3 * (n - 1) + 1] = d1; M[3 * (n - 1) + 2] = d2;
   }
-  if (sub < m) {
+  if (rec.x >= 0) {
     double* Mc = M + 3 * (3 + tk);
 #pragma unroll
     for (int cc = 0; cc < DC; cc++) {
@@ -958,10 +965,11 @@ leaf_point_factor_kernel(TreeView t, GroupTable gt, const int* __restrict__ list
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int pt = 0; pt < 4; pt++) {
-      const int np = __shfl_sync(0xffffffffu, n, 8 * pt), cp = __shfl_sync(0xffffffffu, c, 8 * pt);
+      const int np = __shfl_sync(0xffffffffu, n, 8 * pt);
+      const int64_t op = __shfl_sync(0xffffffffu, moff, 8 * pt);
       if (np == 0) continue;       // (warp-uniform: a point past the end of the list)
       const double* src = sm_dyn + (size_t)((threadIdx.x >> 5) * 4 + pt) * ncap;
-      double* dst = t.arena + t.off[cp];
+      double* dst = t.arena + op;
       for (int e = lane; e < 3 * np; e += 32) dst[e] = src[e];
     }
   }
@@ -1160,7 +1168,7 @@ constexpr int kSmPA = 12;
 template <int DC, int NTT, typename JT = double>   // NTT: 8-column strips of the widest separator (+ rhs column) of the kind
 __global__ void __launch_bounds__(128, (NTT <= 4 && DC == 6) ? 4 : ((NTT <= 5 && DC == 6) ? 3 : (NTT <= 7 ? 2 : 1)))
 leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ list, const int* __restrict__ run_ptr,
-                            const int* __restrict__ fac_ptr, const int2* __restrict__ fac) {
+                            const int2* __restrict__ pt_tab, const int64_t* __restrict__ pt_off) {
   pdl_sync();
   constexpr int MP = kSmMP, KS = kSmKS, PA = kSmPA;
   constexpr int CP = DC < 8 ? 8 : 16, CT = CP / 8;           // [A_c b] has DC + 1 columns: one 8x8 tile, or 2 x 2 at 9 dofs
@@ -1173,7 +1181,7 @@ leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ l
   const int p = t.parent[c0];
   if (p < 0) return;
   const int s = t.ns[c0], w = s + 1;
-  const int m = fac_ptr[r0 + 1] - fac_ptr[r0];
+  const int m = s / DC;                                       // one factor per separator camera
   const int NT = (w + 7) >> 3, WP = 8 * NT;
   const int s_doubles = 2 * WP * KS;                          // per warp: S'^T, two buffers
   const int a_elems = 2 * m * CP * PA;                        // per warp: [A_c b]^T of m cameras, two buffers, in JT
@@ -1202,16 +1210,19 @@ leaf_point_schur_mma_kernel(TreeView t, GroupTable gt, const int* __restrict__ l
   int slotJ = -1;
   auto load_idx = [&](int mb) {
     const int b0 = r0 + MP * mb, nb = min(MP, r1 - b0);
+    // one level of index loads (the flat table of the point leaves: engine.cu)
 #pragma unroll
-    for (int z = 0; z < MP; z++) srcS[z] = z < nb ? t.arena + t.off[list[b0 + z]] + 9 : nullptr;
+    for (int z = 0; z < MP; z++) srcS[z] = z < nb ? t.arena + pt_off[b0 + z] + 9 : nullptr;
     const int pt = lane >> 3, fi = lane & 7;
     slotJ = -1;
-    if (pt < nb && fi < m) {
-      const int2 gf = fac[fac_ptr[b0 + pt] + fi];
-      const GroupView& gv = gt.g[gf.x];
-      cntJ = (size_t)gv.count;
-      srcJ = reinterpret_cast<const JT*>(gv.J) + gf.y;
-      slotJ = (gv.scat[gf.y].y - 3) / DC;
+    if (pt < nb) {
+      const int2 rec = pt_tab[(size_t)(b0 + pt) * kPtMaxObs + fi];
+      if (rec.x >= 0) {
+        const GroupView& gv = gt.g[rec.y >> 8];
+        cntJ = (size_t)gv.count;
+        srcJ = reinterpret_cast<const JT*>(gv.J) + rec.x;
+        slotJ = rec.y & 0xff;
+      }
     }
   };
   auto issue = [&](int buf, int nb) {
