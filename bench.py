@@ -105,6 +105,11 @@ class ClockSampler:
                                           "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi needs a few hundred ms before its first row; the timed region of a 20-step run is shorter than that,
+            # so the sampler is started before the one-time problem setup and the bench waits here for the first row
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -274,6 +279,9 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
 
     jac32 = jac32_for(args, workload)
     jb = 4 if jac32 else 8
+    sampler = ClockSampler(local)
+    if rank == 0 and primary:
+        sampler.start()
     t0 = time.perf_counter()
     prob, weak = make_problem(args, workload, world)
     gen_s = time.perf_counter() - t0
@@ -373,9 +381,6 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         return ms, wall, nlaunch
 
     steps = args.steps
-    sampler = ClockSampler(local)
-    if rank == 0 and primary:
-        sampler.start()
     ms, wall, launches = timed(step_resident, steps, max(3, args.warmup), prepare=prepare_resident)
     clocks = sampler.stop(tuple(timed.region)) if (rank == 0 and primary) else None
     ms_e2e, wall_e2e, _ = timed(step_e2e, steps, 1)

@@ -1278,6 +1278,9 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     p->h_off[S.ncliques] = o;
   }
   // ---- factor tables ----
+  const bool reorder_leaf_factors = getenv("B200_NO_FACTOR_REORDER") == nullptr;
+  std::vector<int> leaf_list_pos(S.ncliques, INT_MAX);      // position of a point leaf (kinds 1 / 2) in fused_list
+  for (size_t i = 0; i < fused_list.size(); i++) if (leaf_kind[fused_list[i]] > 0) leaf_list_pos[fused_list[i]] = (int)i;
   std::vector<std::vector<int2>> hkeys(ngroups);
   std::vector<std::vector<int4>> hscat(ngroups);
   for (int64_t gi = 0; ld && gi < ngroups; gi++) {
@@ -1314,6 +1317,16 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     // keep only the factors this rank owns (all of them when world == 1)
     std::vector<int64_t>& keep = g.local_index;
     for (int64_t i = 0; i < s.count; i++) if (factor_owner[g.pos[i]] == rank) keep.push_back(i);
+    // Device order of a projection group = the order in which the leaf kernels visit its factors: by the position of the owning
+    // point leaf in fused_list (points of one run next to each other), graph order inside a point; factors of other cliques
+    // behind them.  Every row of the element-major SoA then holds a warp's 4 points x m factors contiguously.  In graph order
+    // (ncu, 10M factors, round 2) each point's 5 floats of a row sat alone in a 128-byte line: leaf_point_factor_kernel read
+    // 5.5 GB for 0.8 GB of Jacobians, leaf_point_schur_mma_kernel 5.5 GB for 2.8.  It also puts factors that share cameras
+    // (the points of a run) side by side for the gathers of linearize_kernel / error_kernel.  local_index maps back to the
+    // caller's order wherever that is visible (b200_get_jacobians, b200_set_group_noise).
+    if (reorder_leaf_factors && (s.type == B200_FACTOR_PROJECTION_CAL3S2 || s.type == B200_FACTOR_SFM_BUNDLER))
+      std::stable_sort(keep.begin(), keep.end(), [&](int64_t a, int64_t b) {
+        return leaf_list_pos[S.fac_clique[g.pos[a]]] < leaf_list_pos[S.fac_clique[g.pos[b]]]; });
     const int64_t nl = (int64_t)keep.size();
     hkeys[gi].resize(nl);
     hscat[gi].resize(nl);
@@ -1911,19 +1924,26 @@ int b200_get_jacobians(b200_problem* p, int64_t gi, double* out) {
   B200_CUDA(cudaSetDevice(p->ctx->device));
   auto& g = p->groups[gi];
   const size_t per = (size_t)g.d * g.ncols;
+  // the device order of a group is internal (create_problem): the caller's order when the whole group lives on this rank,
+  // the rank's own factors in device order when sharded
+  const bool whole = !p->linear && (int64_t)g.local_index.size() == g.count && g.count == (int64_t)g.pos.size();
   if (p->jac_f32) {   // stored as floats (b200_set_jacobian_precision): widened for the caller
     std::vector<float> soa(per * g.count);
     B200_CUDA(cudaMemcpyAsync(soa.data(), g.d_J, soa.size() * sizeof(float), cudaMemcpyDeviceToHost, p->ctx->stream));
     B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
-    for (int64_t f = 0; f < g.count; f++)
-      for (size_t e = 0; e < per; e++) out[f * per + e] = (double)soa[e * g.count + f];
+    for (int64_t f = 0; f < g.count; f++) {
+      const int64_t o = whole ? g.local_index[f] : f;
+      for (size_t e = 0; e < per; e++) out[o * per + e] = (double)soa[e * g.count + f];
+    }
     return B200_OK;
   }
   std::vector<double> soa(per * g.count);
   B200_CUDA(cudaMemcpyAsync(soa.data(), g.d_J, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(p->ctx->stream));
-  for (int64_t f = 0; f < g.count; f++)
-    for (size_t e = 0; e < per; e++) out[f * per + e] = soa[e * g.count + f];
+  for (int64_t f = 0; f < g.count; f++) {
+    const int64_t o = whole ? g.local_index[f] : f;
+    for (size_t e = 0; e < per; e++) out[o * per + e] = soa[e * g.count + f];
+  }
   return B200_OK;
 }
 

@@ -55,7 +55,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def captures(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep, or its raw page exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x.raw.csv`: the reports of
+    several launches exceed what gpurun copies back)"""
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
         return []
@@ -68,14 +70,14 @@ def captures(rep):
 
 
 def main():
-    print("# Round 2, final build: ncu evidence (one B200, `profiles/collect_r02c.sh`)\n")
+    print("# Round 2, final build: ncu evidence (one B200, `profiles/collect_r02f.sh`, commit 17da8ee)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES with the bench's phase timers, not absolutes.\n")
     for path in sorted(glob.glob(os.path.join(D, "r02_launches_*.csv"))):
         w = os.path.basename(path)[len("r02_launches_"):-4]
         table, _ = launches(path)
         print(f"## Launch list of one LM iteration, {w}\n\n{table}\n")
     traffic = {}
-    for rep in sorted(glob.glob(os.path.join(D, "r02_*.ncu-rep"))):
+    for rep in sorted(glob.glob(os.path.join(D, "r02_*.ncu-rep")) + glob.glob(os.path.join(D, "r02_*.raw.csv"))):
         print(f"## Full captures: `{os.path.basename(rep)}` (`ncu --set full --import-source on --clock-control none`)\n")
         seen = set()
         for name, m in captures(rep):
@@ -100,7 +102,7 @@ def main():
                 "linerr_kernel<3": "linear_error", "linerr_kernel<4": "linear_error", "error_kernel<3": "error", "error_kernel<4": "error"}
     by_phase = {}
     for name, rec in traffic.items():
-        wl = re.sub(r"^r02[a-z]?_.*?_(bal_\w+?|sphere\w+?)\.ncu-rep$", r"\1", rec["report"])
+        wl = re.sub(r"^r02[a-z]?_.*?_(bal_\w+?|sphere\w+?)\.(?:ncu-rep|raw\.csv)$", r"\1", rec["report"])
         for prefix, ph in phase_of.items():
             if name.startswith(prefix):
                 by_phase.setdefault(wl, {})[ph] = rec["dram_bytes"]
