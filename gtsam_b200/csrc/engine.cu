@@ -1324,9 +1324,17 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     // 5.5 GB for 0.8 GB of Jacobians, leaf_point_schur_mma_kernel 5.5 GB for 2.8.  It also puts factors that share cameras
     // (the points of a run) side by side for the gathers of linearize_kernel / error_kernel.  local_index maps back to the
     // caller's order wherever that is visible (b200_get_jacobians, b200_set_group_noise).
-    if (reorder_leaf_factors && (s.type == B200_FACTOR_PROJECTION_CAL3S2 || s.type == B200_FACTOR_SFM_BUNDLER))
-      std::stable_sort(keep.begin(), keep.end(), [&](int64_t a, int64_t b) {
-        return leaf_list_pos[S.fac_clique[g.pos[a]]] < leaf_list_pos[S.fac_clique[g.pos[b]]]; });
+    if (reorder_leaf_factors && (s.type == B200_FACTOR_PROJECTION_CAL3S2 || s.type == B200_FACTOR_SFM_BUNDLER) && !fused_list.empty()) {
+      // stable counting sort by list position (one bucket per leaf + one for "not a point leaf"): linear in the group
+      const size_t nb = fused_list.size() + 1;
+      std::vector<int64_t> start(nb + 1, 0);
+      auto bucket = [&](int64_t i) { const int q = leaf_list_pos[S.fac_clique[g.pos[i]]]; return q == INT_MAX ? nb - 1 : (size_t)q; };
+      for (int64_t i : keep) start[bucket(i) + 1]++;
+      for (size_t b = 0; b < nb; b++) start[b + 1] += start[b];
+      std::vector<int64_t> sorted(keep.size());
+      for (int64_t i : keep) sorted[start[bucket(i)]++] = i;
+      keep.swap(sorted);
+    }
     const int64_t nl = (int64_t)keep.size();
     hkeys[gi].resize(nl);
     hscat[gi].resize(nl);
