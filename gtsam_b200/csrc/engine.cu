@@ -2,6 +2,7 @@
 // scheduling (level-by-level walk of the junction tree) and the LM / GN host
 // control logic.  No CPU fallback anywhere: every numeric step is a kernel.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -1106,11 +1107,21 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   p->ctx = ctx;
   p->linear = ld != nullptr;
 #define FAIL(code, msg) do { set_error(msg); b200_problem_destroy(p); return code; } while (0)
+  // B200_SETUP_TIMING=1: where the one-time setup goes (host wall clock per stage, stderr)
+  const bool setup_timing = getenv("B200_SETUP_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!setup_timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b200 setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   Packed pk;
   {
     const int rc = d ? pack_and_symbolic(d, &pk) : pack_linear(ld, &pk);
     if (rc) { b200_problem_destroy(p); return rc; }
   }
+  lap("validate + symbolic phase");
   const int64_t n = d ? d->nvars : ld->nvars;
   const int64_t ngroups = d ? d->ngroups : ld->ngroups + ld->nhgroups;   // linear: Jacobian groups, then Hessian groups
   const int64_t total = pk.total;
@@ -1144,6 +1155,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
   B200_CUDA(cudaMemsetAsync(p->d_delta, 0, std::max<int64_t>(1, p->ndelta) * sizeof(double), st));
   B200_CUDA(cudaMalloc((void**)&p->d_hdiag, std::max<int64_t>(1, p->ndelta) * sizeof(double)));
   UP(upload(&p->d_var_dof, var_dof, st));
+  lap("values + variable tables");
   // ---- storage plan: fused leaf cliques keep only their f x n conditional; sharding -----
   std::vector<char> fused, is_top;
   std::vector<int> clique_owner, factor_owner, top_owner;
@@ -1230,6 +1242,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     p->leaf_lb_cap = lb; p->leaf_acc_cap = tri;
     for (int c : fused_list) p->leaf_max_w[kind[c]] = std::max(p->leaf_max_w[kind[c]], S.ns[c] + 1);
   }
+  lap("shard plan + leaf runs");
   p->n_fused = (int)fused_list.size();
   p->big_min_n = getenv("B200_BIG_MIN_N") ? atoi(getenv("B200_BIG_MIN_N")) : 1024;
   p->use_dmma = getenv("B200_NO_DMMA") == nullptr;
@@ -1277,6 +1290,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     p->arena_doubles = o;
     p->h_off[S.ncliques] = o;
   }
+  lap("front offsets");
   // ---- factor tables ----
   const bool reorder_leaf_factors = getenv("B200_NO_FACTOR_REORDER") == nullptr;
   std::vector<int> leaf_list_pos(S.ncliques, INT_MAX);      // position of a point leaf (kinds 1 / 2) in fused_list
@@ -1361,6 +1375,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.body_P_sensor) UP(upload(&g.d_body, s.body_P_sensor, 12, st));
     B200_CUDA(cudaMalloc((void**)&g.d_J, std::max<size_t>(1, (size_t)nl * g.d * g.ncols) * sizeof(double)));
   }
+  lap("factor tables");
   // ---- junction tree tables ----
   std::vector<int> parent32(S.ncliques);
   for (int64_t c = 0; c < S.ncliques; c++) parent32[c] = (int)S.parent[c];
@@ -1382,6 +1397,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
                                        ? -1 : p->h_off[c] + (S.var_slot[v] + k) * (nn + 1);
   }
   UP(upload(&p->d_diag_index, diag_index, st));
+  lap("tree tables");
   // fused leaf cliques: CSR of their factors as (group, index), graph order
   if (p->n_fused) {
     std::vector<int> lpos(S.ncliques, -1), fptr(p->n_fused + 1, 0);
@@ -1423,6 +1439,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
       UP(upload(&p->d_pt_off, poff, st));
     }
   }
+  lap("leaf factor lists + point table");
   // ---- level plans: small (one warp per clique) / large (blocked) ----
   // phase 0: the subtrees this rank owns, leaves to subtree roots; phase 1: the replicated top.
   // p->levels = [phase-0 levels ..., phase-1 levels ...]; elimination walks it forwards (with the
@@ -1672,6 +1689,7 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     for (auto& L : p->levels) maxl = std::max(maxl, L.large_count);
     B200_CUDA(cudaMalloc((void**)&p->d_rdiag, (size_t)maxl * kNB * kNB * sizeof(double)));
   }
+  lap("level plans + dataflow tickets");
   // ---- values views (sharded problems move only what a rank needs / owns between host and device) ----
   if (d) {
     std::vector<char> need(n, ctx->world == 1), own(n, ctx->world == 1);

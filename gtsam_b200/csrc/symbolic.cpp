@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 #include <thread>
@@ -22,6 +24,14 @@ AmalgOptions amalg_options_from_env() {
 bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int64_t m,
                     const int64_t* fptr, const int64_t* fkeys, Symbolic* S, const char** err,
                     const AmalgOptions& amalg) {
+  const bool timing = getenv("B200_SETUP_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b200 symbolic] %-26s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   S->nvars = n;
   S->var_dim.assign(var_dim, var_dim + n);
   S->var_dof.assign(n + 1, 0);
@@ -49,6 +59,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     for (int64_t i = 0; i < m; i++)
       for (int64_t q = fptr[i]; q < fptr[i + 1]; q++) vi[cur[fkeys[q]]++] = i;
   }
+  lap("variable index");
   // ---- elimination tree with path compression ----------------------------------
   std::vector<int64_t> eparent(n, -1), anc(n, -1), prevCol(m, -1), node_of_factor(m, -1);
   std::vector<int64_t> first_child(n, -1), last_child(n, -1), next_sib(n, -1);
@@ -75,6 +86,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
       prevCol[i] = j;
     }
   }
+  lap("elimination tree");
   // node -> own factors (CSR, ascending factor position)
   std::vector<int64_t> nf_ptr(n + 1, 0);
   for (int64_t i = 0; i < m; i++) nf_ptr[node_of_factor[i] + 1]++;
@@ -84,6 +96,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     std::vector<int64_t> cur(nf_ptr.begin(), nf_ptr.end() - 1);
     for (int64_t i = 0; i < m; i++) nfac[cur[node_of_factor[i]]++] = i;
   }
+  lap("node factor lists");
   // ---- symbolic elimination: separator (as positions) of every etree node -------
   std::vector<int64_t> sep_off(n + 1, 0), sep_pool;
   sep_pool.reserve((size_t)(fptr[m] + n));
@@ -125,6 +138,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     }
     if (merged_any) std::reverse(fr.begin(), fr.end());
   }
+  lap("symbolic elimination");
   // ---- the reference's cliques, kept for reporting (Symbolic::ref) ---------------------
   {
     RefCliques& R = S->ref;
@@ -205,6 +219,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
       for (int64_t c = 0; c < rc; c++) R.super[c] = newid[R.super[c]];
     }
   }
+  lap("reference cliques + amalgamation");
   // ---- clique tables (supernodes) ------------------------------------------------------
   std::vector<int64_t> cid(n, -1);
   int64_t nc = 0;
@@ -268,6 +283,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
     std::vector<int64_t> cur(S->lvl_ptr.begin(), S->lvl_ptr.end() - 1);
     for (int64_t c = 0; c < nc; c++) S->lvl_cliques[cur[S->level[c]]++] = (int)c;
   }
+  lap("supernode tables");
   // ---- scatter maps ------------------------------------------------------------------
   // factors by owning clique
   S->fac_clique.assign(m, -1); S->fac_slot0.assign(m, -1); S->fac_slot1.assign(m, -1);
@@ -302,6 +318,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   // Every clique writes only its own ranges (its didx rows, the slots of the factors it owns, the ea_map of its
   // children), so the cliques are processed in parallel: chunks handed out through an atomic counter, one slot[]
   // scratch per thread.  (4.5 of the 7.3 s of this phase at 10M factors were spent here on one thread.)
+  lap("scatter prelude");
   std::atomic<int64_t> next_chunk(0);
   std::atomic<int> failure(0);   // 1: factor variable missing, 2: child separator variable missing
   const int64_t chunk = 2048;
@@ -363,6 +380,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
       for (auto& t : pool) t.join();
     }
   }
+  lap("scatter maps (threads)");
   if (failure.load() == 1) { *err = "internal: factor variable not in owning clique"; return false; }
   if (failure.load() == 2) { *err = "internal: child separator variable not in parent clique"; return false; }
   return true;

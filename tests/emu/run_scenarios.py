@@ -402,6 +402,26 @@ def coverage(_):
         del dl
         dev.close()
     assert shrunk >= 1
+    # the device order of the projection groups (leaf-visit order, create_problem) is internal: Jacobians come back in the caller's
+    # order and every result is the same as with graph-order storage (B200_NO_FACTOR_REORDER=1)
+    for name in ("bal_tiny_s2", "bal_tiny_bundler", "bal_small_metis"):
+        prob = util.load_case(name)
+        res = []
+        for off in (False, True):
+            if off:
+                os.environ["B200_NO_FACTOR_REORDER"] = "1"
+            try:
+                dev = capi.DeviceProblem(ctx, prob)
+            finally:
+                os.environ.pop("B200_NO_FACTOR_REORDER", None)
+            dev.linearize()
+            st, e0, e1, _ = dev.solve(1e-2, True)
+            res.append(([dev.get_jacobians(gi) for gi in range(len(prob.groups))], dev.get_delta(), e0, e1, dev.hessian_diagonal()))
+            dev.close()
+        for Ja, Jb in zip(res[0][0], res[1][0]):
+            assert np.array_equal(Ja, Jb), name
+        assert util.rel2(res[0][1], res[1][1]) <= 1e-9 and abs(res[0][2] - res[1][2]) <= 1e-12 * res[1][2] and abs(res[0][3] - res[1][3]) <= 1e-9 * res[1][2]
+        assert util.relmax(res[0][4], res[1][4]) <= 1e-12
     # ticket order of the dataflow tiles across levels (B200_DF_ORDER=1, with and without lagged trailing columns): the emulator runs
     # the CTAs in ticket order, one after the other, so a dependency that pointed forwards would time out instead of passing
     for lag in ("0", "2", "5"):
