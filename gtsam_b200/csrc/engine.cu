@@ -9,12 +9,25 @@
 #include <dlfcn.h>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 #include "kernels.cuh"
 
 namespace b200 {
 
 static thread_local std::string g_err;
+
+// Host loops of the one-time setup that write disjoint ranges run on a few threads (B200_SETUP_THREADS; 1 = serial).
+template <class F>
+static void parallel_chunks(int64_t n, F f) {
+  int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  if (const char* e = getenv("B200_SETUP_THREADS")) nt = std::min(16, std::max(1, atoi(e)));
+  nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, n / 65536));
+  if (nt <= 1) { f((int64_t)0, n, 0); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; t++) pool.emplace_back([=, &f]() { f(n * t / nt, n * (t + 1) / nt, t); });
+  for (auto& th : pool) th.join();
+}
 void set_error(const std::string& s) { g_err = s; }
 
 static const int VAR_STORAGE[B200_NUM_VAR_TYPES] = {12, 3, 17, 3};
@@ -1355,16 +1368,24 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     std::vector<double> hmeas((size_t)nl * g.meas), hnoise;
     std::vector<int> hcal;
     if (s.noise_per_factor) hnoise.resize((size_t)nl * g.noise_size);
-    for (int64_t li = 0; li < nl; li++) {
-      const int64_t i = keep[li], pos = g.pos[i];
-      hkeys[gi][li] = make_int2((int)fkeys[fptr[pos]], g.arity == 2 ? (int)fkeys[fptr[pos] + 1] : -1);
-      const int isleaf = fused[S.fac_clique[pos]];
-      hscat[gi][li] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
-      if (!isleaf) g.n_nonleaf++;
-      memcpy(hmeas.data() + (size_t)li * g.meas, s.meas + (size_t)i * g.meas, (size_t)g.meas * sizeof(double));
-      if (s.noise_per_factor) memcpy(hnoise.data() + (size_t)li * g.noise_size, s.noise + (size_t)i * g.noise_size, (size_t)g.noise_size * sizeof(double));
-      if (s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.cal_index) hcal.push_back(s.cal_index[i]);
-    }
+    const bool with_cal = s.type == B200_FACTOR_PROJECTION_CAL3S2 && s.cal_index;
+    if (with_cal) hcal.resize((size_t)nl);
+    int64_t nonleaf_part[16] = {0};
+    parallel_chunks(nl, [&](int64_t l0, int64_t l1, int tid) {
+      int64_t nonleaf = 0;
+      for (int64_t li = l0; li < l1; li++) {
+        const int64_t i = keep[li], pos = g.pos[i];
+        hkeys[gi][li] = make_int2((int)fkeys[fptr[pos]], g.arity == 2 ? (int)fkeys[fptr[pos] + 1] : -1);
+        const int isleaf = fused[S.fac_clique[pos]];
+        hscat[gi][li] = make_int4(S.fac_clique[pos], S.fac_slot0[pos], S.fac_slot1[pos], isleaf);
+        if (!isleaf) nonleaf++;
+        memcpy(hmeas.data() + (size_t)li * g.meas, s.meas + (size_t)i * g.meas, (size_t)g.meas * sizeof(double));
+        if (s.noise_per_factor) memcpy(hnoise.data() + (size_t)li * g.noise_size, s.noise + (size_t)i * g.noise_size, (size_t)g.noise_size * sizeof(double));
+        if (with_cal) hcal[(size_t)li] = s.cal_index[i];
+      }
+      nonleaf_part[tid] = nonleaf;
+    });
+    for (int t = 0; t < 16; t++) g.n_nonleaf += nonleaf_part[t];
     g.count = nl;
     UP(upload(&g.d_keys, hkeys[gi], st));
     UP(upload(&g.d_scat, hscat[gi], st));
@@ -1411,10 +1432,17 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
         const int64_t pos = p->groups[gi].pos[p->groups[gi].local_index[li]];
         if (lpos[S.fac_clique[pos]] >= 0) ffac[cur[lpos[S.fac_clique[pos]]]++] = make_int2((int)gi, (int)li);
       }
-    // keep graph order inside each clique (groups may interleave in the graph)
-    for (int i = 0; i < p->n_fused; i++)
-      std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) {
-        return p->groups[a.x].pos[p->groups[a.x].local_index[a.y]] < p->groups[b.x].pos[p->groups[b.x].local_index[b.y]]; });
+    // keep graph order inside each clique (groups may interleave in the graph; a clique whose factors come from one group
+    // already has it)
+    parallel_chunks(p->n_fused, [&](int64_t i0, int64_t i1, int) {
+      auto gpos = [&](const int2& a) { return p->groups[a.x].pos[p->groups[a.x].local_index[a.y]]; };
+      for (int64_t i = i0; i < i1; i++) {
+        bool ordered = true;
+        for (int q = fptr[i] + 1; q < fptr[i + 1] && ordered; q++) ordered = gpos(ffac[q - 1]) < gpos(ffac[q]);
+        if (!ordered)
+          std::sort(ffac.begin() + fptr[i], ffac.begin() + fptr[i + 1], [&](const int2& a, const int2& b) { return gpos(a) < gpos(b); });
+      }
+    });
     UP(upload(&p->d_fused_list, fused_list, st));
     UP(upload(&p->d_fused_run_ptr, run_ptr, st));
     UP(upload(&p->d_fused_fac_ptr, fptr, st));
@@ -1425,16 +1453,18 @@ static int create_problem(b200_ctx* ctx, const b200_problem_desc* d, const b200_
     if (p->leaf_pos_end[2] > p->leaf_pos_begin[1] || p->leaf_pos_end[1] > p->leaf_pos_begin[1]) {
       std::vector<int2> tab((size_t)p->n_fused * kPtMaxObs, make_int2(-1, 0));
       std::vector<int64_t> poff((size_t)p->n_fused, 0);
-      for (int i = 0; i < p->n_fused; i++) {
-        const int c = fused_list[i], kd = leaf_kind[c];
-        poff[i] = p->h_off[c];
-        if (kd == 0) continue;
-        const int dc = kd == 1 ? 6 : 9;
-        for (int q = fptr[i]; q < fptr[i + 1]; q++) {
-          const int2 gf = ffac[q];
-          tab[(size_t)i * kPtMaxObs + (q - fptr[i])] = make_int2(gf.y, (gf.x << 8) | ((hscat[gf.x][gf.y].y - 3) / dc));
+      parallel_chunks(p->n_fused, [&](int64_t i0, int64_t i1, int) {
+        for (int64_t i = i0; i < i1; i++) {
+          const int c = fused_list[i], kd = leaf_kind[c];
+          poff[i] = p->h_off[c];
+          if (kd == 0) continue;
+          const int dc = kd == 1 ? 6 : 9;
+          for (int q = fptr[i]; q < fptr[i + 1]; q++) {
+            const int2 gf = ffac[q];
+            tab[(size_t)i * kPtMaxObs + (q - fptr[i])] = make_int2(gf.y, (gf.x << 8) | ((hscat[gf.x][gf.y].y - 3) / dc));
+          }
         }
-      }
+      });
       UP(upload(&p->d_pt_tab, tab, st));
       UP(upload(&p->d_pt_off, poff, st));
     }

@@ -372,6 +372,7 @@ bool build_symbolic(int64_t n, const int* var_dim, const int64_t* ordering, int6
   {
     int nthreads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<int64_t>(16, (nc + chunk - 1) / chunk));
     if (const char* e = getenv("B200_SYMBOLIC_THREADS")) nthreads = std::max(1, atoi(e));
+    if (timing) fprintf(stderr, "[b200 symbolic] scatter maps on %d threads (hardware_concurrency %u, %lld cliques)\n", nthreads, std::thread::hardware_concurrency(), (long long)nc);
     if (nthreads <= 1) {
       worker();
     } else {
