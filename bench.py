@@ -468,6 +468,7 @@ def measure(args, workload, ctx, dist, rank, local, world, primary):
         "roofline_linearize": roof("linearize"),
         "roofline_dense_fronts": roof("eliminate_large"),
         "roofline_back_substitute": roof("back_substitute"),
+        "roofline_leaf_factor": roof("leaf_fused"), "roofline_leaf_schur": roof("leaf_schur"),
         "phases_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
         "lm": {"error_after": st.error, "lambda_after": st.lambda_, "tries_per_step": tries},
         "tree": {"cliques": info.ncliques, "levels": info.nlevels, "max_frontal": info.max_frontal_dim,
@@ -599,7 +600,7 @@ def main():
     measure.fp64_peaks = ctx.measure_fp64_peak()
     tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
     if os.path.exists(tpath):
-        measure.traffic = json.load(open(tpath))
+        measure.traffic = {k: v for k, v in json.load(open(tpath)).items() if isinstance(v, dict)}
 
     workload = PRIMARY if args.workload == "auto" else args.workload
     rec = measure(args, workload, ctx, dist, rank, local, world, primary=True)

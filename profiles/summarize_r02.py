@@ -72,6 +72,10 @@ def captures(rep):
 def main():
     print("# Round 2, final build: ncu evidence (one B200, `profiles/collect_r02f.sh`, commit 17da8ee)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES with the bench's phase timers, not absolutes.\n")
+    print("These captures are of commit 17da8ee — the second-pass kernels, BEFORE the projection groups were stored in leaf-visit order "
+          "(commit 66544f1).  The 5.5 GB of DRAM reads of each leaf kernel at 10M factors below are what motivated that change; the bench "
+          "records after it are profiles/r02_bench_1gpu_final.json (default) and r02_bench_1gpu_graph_order.json (B200_NO_FACTOR_REORDER=1); "
+          "the GPU budget of the round did not allow a second ncu pass.\n")
     for path in sorted(glob.glob(os.path.join(D, "r02_launches_*.csv"))):
         w = os.path.basename(path)[len("r02_launches_"):-4]
         table, _ = launches(path)
@@ -106,7 +110,8 @@ def main():
         for prefix, ph in phase_of.items():
             if name.startswith(prefix):
                 by_phase.setdefault(wl, {})[ph] = rec["dram_bytes"]
-    json.dump(by_phase, open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json"), "w"), indent=1)
+    if "--traffic" in sys.argv:   # (profiles/r02_kernel_traffic.json is curated by hand: only captures that are still valid for the build)
+        json.dump(by_phase, open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json"), "w"), indent=1)
 
 
 main()
